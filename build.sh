@@ -1,0 +1,22 @@
+#!/bin/bash
+# Build libemap_b200.so for sm_100a (in-tree; the .so travels to the GPU box with the snapshot).
+set -e
+cd "$(dirname "$0")"
+SRC=emap_b200/csrc
+OUT=emap_b200/lib
+mkdir -p $OUT build
+NVCC=${NVCC:-/usr/local/cuda/bin/nvcc}
+FLAGS="-gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -std=c++17 -Xcompiler -fPIC -Xptxas -v"
+objs=""
+for f in cabi pack mlp_tc rays; do
+  [ -f $SRC/$f.cu ] || continue
+  if [ ! -f build/$f.o ] || [ $SRC/$f.cu -nt build/$f.o ] || [ $SRC/common.cuh -nt build/$f.o ] || [ $SRC/host.h -nt build/$f.o ] || [ include/emap_b200.h -nt build/$f.o ]; then
+    extra=""
+    [ $f = rays ] && extra="-fmad=false"
+    echo "nvcc $f.cu"
+    $NVCC $FLAGS $extra -c $SRC/$f.cu -o build/$f.o 2> build/$f.log || { cat build/$f.log; exit 1; }
+  fi
+  objs="$objs build/$f.o"
+done
+$NVCC -gencode arch=compute_100a,code=sm_100a -shared -o $OUT/libemap_b200.so $objs
+echo "built $OUT/libemap_b200.so"

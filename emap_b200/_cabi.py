@@ -1,0 +1,101 @@
+"""ctypes binding of the C-ABI shared library (include/emap_b200.h).
+
+The library is built in-tree by ``build.sh`` / ``__graft_entry__.build()`` into
+``emap_b200/lib/libemap_b200.so``.  There is NO fallback: if it is missing, or a call fails,
+this module raises -- the product path never routes through PyTorch eager or the CPU oracle.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+from typing import Optional
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "lib", "libemap_b200.so")
+
+PREC_FP32X3 = 3
+PREC_HALF = 1
+PRECISIONS = {"fp32": PREC_FP32X3, "fp32x3": PREC_FP32X3, "fp16": PREC_HALF, "bf16": PREC_HALF,
+              "half": PREC_HALF}
+
+
+class NetDesc(ctypes.Structure):
+    _fields_ = [("multires", ctypes.c_int32), ("udf_type", ctypes.c_int32),
+                ("scale", ctypes.c_float), ("elem_type", ctypes.c_int32)]
+
+
+UDF_TYPES = {"abs": 0, "square": 1, "sdf": 2}
+
+_lib: Optional[ctypes.CDLL] = None
+
+_vp, _i32, _i64, _f32 = ctypes.c_void_p, ctypes.c_int32, ctypes.c_int64, ctypes.c_float
+_nd = ctypes.POINTER(NetDesc)
+
+# name -> (restype, argtypes); every symbol declared in include/emap_b200.h
+SIGNATURES = {
+    "emap_last_error": (ctypes.c_char_p, []),
+    "emap_abi_version": (ctypes.c_int, []),
+    "emap_flat_param_count": (ctypes.c_size_t, [_nd]),
+    "emap_packed_size": (ctypes.c_size_t, [_nd]),
+    "emap_set_option": (ctypes.c_int, [ctypes.c_char_p, ctypes.c_int]),
+    "emap_wn_fold": (ctypes.c_int, [_nd, _vp, _vp, _vp]),
+    "emap_udf_forward": (ctypes.c_int, [_nd, _vp, _i32, _vp, _vp, _vp, _vp, _i32, _i64, _vp, _vp, _vp]),
+    "emap_udf_forward_grad": (ctypes.c_int, [_nd, _vp, _i32, _vp, _vp, _vp, _vp, _i32, _i64, _vp, _vp, _vp]),
+    "emap_debug_mlp": (ctypes.c_int, [_nd, _vp, _i32, _i32, _vp, _i64, _vp, _vp, _vp, _vp]),
+    "emap_coarse_z": (ctypes.c_int, [_vp, _vp, _i32, _vp, _vp, _i32, _i32, _vp, _vp]),
+    "emap_upsample_step": (ctypes.c_int, [_vp, _vp, _vp, _vp, _i32, _vp, _vp, _i32, _vp, _vp, _vp, _i32,
+                                          _vp, _vp, _vp, _vp, _i32, _f32, _f32, _f32, _i32, _i32, _vp]),
+    "emap_render_prep": (ctypes.c_int, [_vp, _vp, _i32, _i32, _vp, _vp, _vp]),
+    "emap_render_core_fwd": (ctypes.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _i32, _f32, _f32,
+                                            _f32, _f32, _i32, _i32, _i32, _vp, _vp, _vp, _vp, _vp, _vp,
+                                            _vp, _vp, _vp, _vp, _vp]),
+}
+
+
+def lib() -> ctypes.CDLL:
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError(
+                f"emap_b200: CUDA library not built ({LIB_PATH} missing). Run ./build.sh "
+                "(or python -c 'import __graft_entry__ as g; g.build()'). There is no CPU fallback.")
+        L = ctypes.CDLL(LIB_PATH)
+        for name, (res, args) in SIGNATURES.items():
+            fn = getattr(L, name)
+            fn.restype = res
+            fn.argtypes = args
+        if L.emap_abi_version() != 1:
+            raise RuntimeError("emap_b200: ABI version mismatch between _cabi.py and the library")
+        _lib = L
+    return _lib
+
+
+def check(rc: int) -> None:
+    if rc != 0:
+        raise RuntimeError("emap_b200: " + lib().emap_last_error().decode())
+
+
+def ptr(t: Optional[torch.Tensor]) -> Optional[int]:
+    if t is None:
+        return None
+    if not t.is_cuda:
+        raise RuntimeError("emap_b200: tensor must live on a CUDA device (no CPU path)")
+    if not t.is_contiguous():
+        raise RuntimeError("emap_b200: tensor must be contiguous")
+    return t.data_ptr()
+
+
+def f32(t: torch.Tensor) -> torch.Tensor:
+    if t.dtype != torch.float32:
+        raise RuntimeError(f"emap_b200: expected float32, got {t.dtype}")
+    return t.contiguous()
+
+
+def stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def set_option(name: str, value: int) -> None:
+    check(lib().emap_set_option(name.encode(), int(value)))

@@ -1,0 +1,618 @@
+// K1 / K1g: fused positional-encoding + 9-layer softplus MLP on the 5th-gen tensor cores.
+//
+// Replaces (reference paths relative to /root/reference):
+//   src/models/embedder.py:26-35      Embedder.embed           -> input stage (sincosf, fp32)
+//   src/models/udf_model.py:90-110    UDFNetwork.forward       -> MODE_FWD
+//   src/models/udf_model.py:121-135   UDFNetwork.gradient      -> MODE_GRAD (forward-mode tangents)
+//
+// Dataflow (one persistent CTA per SM, 10 warps, warp-specialised):
+//   warp 8   : producer -- streams the pre-swizzled weight images (pack.cu) from L2 into a ring of
+//              16 KiB stages with 1-D bulk copies (TMA engine, SASS UBLKCP), mbarrier tx-count.
+//   warp 9   : MMA issuer -- one thread issues tcgen05.mma (M=128, N<=128, K=16, kind::f16) with
+//              A = activation tile in shared memory (K-major, 128B swizzle), B = weight stage,
+//              D = fp32 accumulator in TMEM (two 256-column buffers, ping-pong across layers).
+//   warps 0-7: epilogue -- tcgen05.ld the accumulator, softplus (beta=100) in fp32, convert to
+//              fp16 (hi [+ lo]) and write the NEXT layer's A tile in place, 64-column chunk by chunk;
+//              the MMA of layer l+1 starts on chunk c as soon as it is written, so it overlaps the
+//              epilogue of layer l.  Activations never leave the SM.
+//
+// Precision modes (template NTERMS):
+//   3 : "fp32-faithful": every operand is split x = hi + lo (two fp16), and the product is formed as
+//       hi*hi + lo*hi + hi*lo with fp32 accumulation (3 MMAs) -> ~2^-22 relative, i.e. fp32-class.
+//   1 : one fp16 (or bf16) MMA.
+//
+// MODE_GRAD: a tile is 32 points x {value, d/dx, d/dy, d/dz} rows (row = 4*p + type inside each
+// 32-lane TMEM quarter).  Tangent rows carry J_gamma e_c through the same GEMMs; their epilogue is
+// multiplication by softplus'(a) = sigmoid(100 a) of the value row (exchanged through a warp-private
+// shared-memory scratch so that the transcendental work is spread over all 32 lanes).
+#include "common.cuh"
+#include "host.h"
+
+namespace emap {
+
+constexpr int kEpiWarps = 8;
+constexpr int kThreads = (kEpiWarps + 2) * 32;
+constexpr int kChunkBytes = 16384;           // one [128 x 64] 16-bit SW128 chunk
+constexpr int kScratchFloatsPerWarp = 8 * 36;
+
+struct MlpArgs {
+  const uint8_t* packed;
+  const float* pts;
+  const float* rays_o;
+  const float* rays_d;
+  const float* z;
+  int n_per_ray;
+  long long P;
+  float* udf_out;
+  float* grad_out;
+  float* pe_out;
+  float* dbg_acc;       // optional [9][128][256] dump of tile 0 accumulators (descaled), else NULL
+  int num_tiles;
+  int iters;
+};
+
+template <int NTERMS, int MODE>
+struct SmemPlan {
+  static constexpr int kStages = (NTERMS == 3) ? 3 : 6;
+  static constexpr int a_hi = 0;
+  static constexpr int pe_hi = a_hi + 4 * kChunkBytes;
+  static constexpr int a_lo = pe_hi + kChunkBytes;
+  static constexpr int pe_lo = a_lo + ((NTERMS == 3) ? 4 * kChunkBytes : 0);
+  static constexpr int ring = pe_lo + ((NTERMS == 3) ? kChunkBytes : 0);
+  static constexpr int scratch = ring + kStages * kStageBytes;
+  static constexpr int items = scratch + ((MODE == 1) ? kEpiWarps * kScratchFloatsPerWarp * 4 : 0);
+  static constexpr int bars = items + kMaxItems * (int)sizeof(RingItem);
+  static constexpr int total = bars + 256 + 1024;   // +1 KiB slack to 1024-align the base
+};
+
+template <typename T> struct Elem;
+template <> struct Elem<__half> {
+  static constexpr int fmt = 0;
+  static __device__ __forceinline__ uint32_t pack2(float a, float b) {
+    __half2 h = __floats2half2_rn(a, b);
+    return *reinterpret_cast<uint32_t*>(&h);
+  }
+  static __device__ __forceinline__ float2 unpack2(uint32_t u) {
+    return __half22float2(*reinterpret_cast<__half2*>(&u));
+  }
+};
+template <> struct Elem<__nv_bfloat16> {
+  static constexpr int fmt = 1;
+  static __device__ __forceinline__ uint32_t pack2(float a, float b) {
+    __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+    return *reinterpret_cast<uint32_t*>(&h);
+  }
+  static __device__ __forceinline__ float2 unpack2(uint32_t u) {
+    return __bfloat1622float2(*reinterpret_cast<__nv_bfloat162*>(&u));
+  }
+};
+
+// Write 8 consecutive columns (one 16-byte swizzle group) of one row of a chunk: hi (and lo) parts.
+template <int NTERMS, typename T>
+__device__ __forceinline__ void store_group(uint8_t* chunk_hi, uint8_t* chunk_lo, int row, int gidx,
+                                            const float (&v)[8]) {
+  const uint32_t off = (uint32_t)row * 128u + (uint32_t)(((gidx ^ (row & 7)) & 7) << 4);
+  uint4 hi;
+  hi.x = Elem<T>::pack2(v[0], v[1]);
+  hi.y = Elem<T>::pack2(v[2], v[3]);
+  hi.z = Elem<T>::pack2(v[4], v[5]);
+  hi.w = Elem<T>::pack2(v[6], v[7]);
+  *reinterpret_cast<uint4*>(chunk_hi + off) = hi;
+  if (NTERMS == 3) {
+    float2 b0 = Elem<T>::unpack2(hi.x), b1 = Elem<T>::unpack2(hi.y), b2 = Elem<T>::unpack2(hi.z),
+           b3 = Elem<T>::unpack2(hi.w);
+    uint4 lo;
+    lo.x = Elem<T>::pack2(v[0] - b0.x, v[1] - b0.y);
+    lo.y = Elem<T>::pack2(v[2] - b1.x, v[3] - b1.y);
+    lo.z = Elem<T>::pack2(v[4] - b2.x, v[5] - b2.y);
+    lo.w = Elem<T>::pack2(v[6] - b3.x, v[7] - b3.y);
+    *reinterpret_cast<uint4*>(chunk_lo + off) = lo;
+  }
+}
+
+// softplus(a; beta=100) and, optionally, its derivative sigmoid(100 a), from t = 100*a.
+// torch: log1p(exp(100 a))/100, identity above threshold 20 (udf_model.py:78) -- identical in fp32:
+// for t > 20 the log1p term is < 2.1e-11 and vanishes against a >= 0.2.
+template <bool WITH_SIG>
+__device__ __forceinline__ float softplus100(float t, float& sig) {
+  const float e = ex2_approx(-fabsf(t) * 1.4426950408889634f);  // exp(-|t|) in (0,1]
+  const float onepe = 1.f + e;
+  const float l2 = lg2_approx(onepe);
+  if (WITH_SIG) {
+    const float r = rcp_approx(onepe);
+    sig = (t >= 0.f) ? r : e * r;
+  }
+  return fmaf(l2, 0.0069314718055994531f, fmaxf(t, 0.f) * 0.01f);
+}
+
+__device__ __forceinline__ void load_point(const MlpArgs& a, long long idx, float scale, float (&x)[3]) {
+  if (idx >= a.P) idx = a.P - 1;
+  if (a.pts) {
+    x[0] = a.pts[idx * 3 + 0]; x[1] = a.pts[idx * 3 + 1]; x[2] = a.pts[idx * 3 + 2];
+  } else {
+    const long long ray = idx / a.n_per_ray;
+    const float zz = a.z[idx];
+    // reference forms pts = o + d*z as two rounded ops (udf_renderer_blending.py:448,812)
+#pragma unroll
+    for (int c = 0; c < 3; ++c) x[c] = __fadd_rn(a.rays_o[ray * 3 + c], __fmul_rn(a.rays_d[ray * 3 + c], zz));
+  }
+  if (scale != 1.f) {
+#pragma unroll
+    for (int c = 0; c < 3; ++c) x[c] = __fmul_rn(x[c], scale);
+  }
+}
+
+// Input stage for one row: the 32 PE columns owned by thread-half HF (kernel column order, see
+// common.cuh), written as four 16-byte groups of the PE chunk.
+//   MODE 0: row = point:            [x, sin(2^j x_c), cos(2^j x_c)]          (embedder.py:26-35)
+//   MODE 1: row = (point, type):    type 0 as above; type c+1 = d/dx_c of it (the tangent seed).
+template <int NTERMS, int MODE, typename T, int HF>
+__device__ __forceinline__ void pe_stage(const MlpArgs& args, const float (&x)[3], int multires,
+                                         int lane, int row, long long pt, long long tile,
+                                         uint8_t* PE_hi, uint8_t* PE_lo) {
+  constexpr int npairs = (HF == 0) ? 14 : 16;
+  constexpr int qbase = (HF == 0) ? 0 : 14;
+  constexpr int vofs = (HF == 0) ? 4 : 0;
+  const int ty = lane & 3;
+  float vals[32];
+  if (MODE == 0) {
+    if (HF == 0) { vals[0] = x[0]; vals[1] = x[1]; vals[2] = x[2]; vals[3] = 0.f; }
+#pragma unroll
+    for (int i = 0; i < npairs; ++i) {
+      const int qq = qbase + i, j = qq / 3, ax = qq % 3;
+      float s = 0.f, c = 0.f;
+      if (j < multires) sincosf(x[ax] * (float)(1 << j), &s, &c);
+      vals[vofs + 2 * i] = s; vals[vofs + 2 * i + 1] = c;
+    }
+    if (args.pe_out && pt < args.P && tile < args.num_tiles) {
+      const int pe = 3 + 6 * multires;
+#pragma unroll
+      for (int k = 0; k < 32; ++k) {
+        const int ref = pe_col_to_ref(HF * 32 + k, multires);
+        if (ref >= 0) args.pe_out[pt * pe + ref] = vals[k];
+      }
+    }
+  } else {
+    // the 4 lanes of a point split the sincos work, then exchange by shuffle
+    float ls[4], lc[4];
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+      // lane type ty evaluates pair i = 4r + ty: same instruction stream, per-lane argument
+      const int i = 4 * r + ty;
+      const int qq = qbase + i, j = qq / 3, ax = qq - 3 * j;
+      const float xa = (ax == 0) ? x[0] : (ax == 1 ? x[1] : x[2]);
+      ls[r] = 0.f; lc[r] = 0.f;
+      if (i < npairs && j < multires) sincosf(xa * (float)(1 << j), &ls[r], &lc[r]);
+    }
+    if (HF == 0) {
+      vals[0] = (ty == 0) ? x[0] : (ty == 1 ? 1.f : 0.f);
+      vals[1] = (ty == 0) ? x[1] : (ty == 2 ? 1.f : 0.f);
+      vals[2] = (ty == 0) ? x[2] : (ty == 3 ? 1.f : 0.f);
+      vals[3] = 0.f;
+    }
+#pragma unroll
+    for (int i = 0; i < npairs; ++i) {
+      const int src = (lane & ~3) | (i & 3);
+      const float S = __shfl_sync(0xffffffffu, ls[i >> 2], src);
+      const float C = __shfl_sync(0xffffffffu, lc[i >> 2], src);
+      const int qq = qbase + i, j = qq / 3, ax = qq % 3;
+      const float f = (float)(1 << j);
+      float vs, vc;
+      if (ty == 0) { vs = S; vc = C; }
+      else if (ax == ty - 1 && j < multires) { vs = f * C; vc = -f * S; }
+      else { vs = 0.f; vc = 0.f; }
+      vals[vofs + 2 * i] = vs; vals[vofs + 2 * i + 1] = vc;
+    }
+  }
+#pragma unroll
+  for (int g = 0; g < 4; ++g) {
+    float v8[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) v8[j] = vals[g * 8 + j];
+    store_group<NTERMS, T>(PE_hi, PE_lo, row, HF * 4 + g, v8);
+  }
+}
+
+template <int NTERMS, int MODE, typename T, int CL>
+__global__ void __launch_bounds__(kThreads, 1) mlp_kernel(const MlpArgs args) {
+  using Plan = SmemPlan<NTERMS, MODE>;
+  constexpr int kStages = Plan::kStages;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+
+  const PackedHeader* hdr = reinterpret_cast<const PackedHeader*>(args.packed);
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int tix = (NTERMS == 3) ? 1 : 0;
+  const int n_items = (int)hdr->n_items[tix];
+  const int multires = (int)hdr->multires;
+  const float net_scale = hdr->scale;
+  const int udf_type = (int)hdr->udf_type;
+  const float* bias100 = reinterpret_cast<const float*>(args.packed + hdr->bias100_off);
+
+  RingItem* s_items = reinterpret_cast<RingItem*>(smem + Plan::items);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Plan::bars);
+  uint64_t* full = bars;                  // [kStages]
+  uint64_t* empty = bars + 6;             // [kStages]
+  uint64_t* a_ready = bars + 12;          // [5]
+  uint64_t* acc_full = bars + 17;         // [2]
+  uint64_t* acc_empty = bars + 19;        // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 22);
+
+  {
+    const uint4* src = reinterpret_cast<const uint4*>(args.packed + hdr->items_off[tix]);
+    uint4* dst = reinterpret_cast<uint4*>(s_items);
+    for (int i = threadIdx.x; i < n_items; i += kThreads) dst[i] = src[i];
+  }
+  if (warp == 8 && lane == 0) {
+    for (int s = 0; s < kStages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], CL); }
+    for (int c = 0; c < 4; ++c) mbar_init(&a_ready[c], 4);
+    mbar_init(&a_ready[4], 8);
+    for (int b = 0; b < 2; ++b) { mbar_init(&acc_full[b], 1); mbar_init(&acc_empty[b], kEpiWarps); }
+    fence_barrier_init();
+  }
+  if (warp == 9) { tmem_alloc(tmem_slot, 512); tmem_relinquish(); }
+  tc_fence_before();
+  if (CL > 1) cluster_sync_all(); else __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 8) {
+    // ===================================== producer =====================================
+    if (lane == 0) {
+      const uint32_t rank = (CL > 1) ? cluster_ctarank() : 0;
+      uint32_t g = 0;
+      for (int iter = 0; iter < args.iters; ++iter) {
+        for (int i = 0; i < n_items; ++i, ++g) {
+          const uint32_t s = g % kStages, use = g / kStages;
+          if (use > 0) mbar_wait(&empty[s], (use - 1) & 1, 100 + s, (int)g);
+          const RingItem it = s_items[i];
+          const uint32_t bytes = (uint32_t)it.bytes16 * 16u;
+          mbar_arrive_expect_tx(&full[s], bytes);
+          uint8_t* dst = smem + Plan::ring + s * kStageBytes;
+          const uint8_t* src = args.packed + it.gmem_off;
+          if (CL == 1) {
+            bulk_g2s(dst, src, bytes, &full[s]);
+          } else {
+            const uint32_t slice = bytes / CL;
+            bulk_g2s_multicast(dst + rank * slice, src + rank * slice, slice, &full[s],
+                               (uint16_t)((1u << CL) - 1));
+          }
+        }
+      }
+    }
+  } else if (warp == 9) {
+    // ===================================== MMA issuer ===================================
+    if (lane == 0) {
+      uint32_t g = 0;
+      // Phase bookkeeping is closed-form in (iter, layer) -- no mutable per-thread arrays:
+      //   acc buffer 0 hosts layers 0,2,4,6,8 (5 uses per tile), buffer 1 layers 1,3,5,7 (4 uses);
+      //   a_ready[0..3] complete once per layer 1..8 input (8 per tile), a_ready[4] once per tile.
+      const uint32_t a_hi_addr = smem_u32(smem + Plan::a_hi), pe_hi_addr = smem_u32(smem + Plan::pe_hi);
+      const uint32_t a_lo_addr = smem_u32(smem + Plan::a_lo), pe_lo_addr = smem_u32(smem + Plan::pe_lo);
+      const uint32_t ring_addr = smem_u32(smem + Plan::ring);
+      for (int iter = 0; iter < args.iters; ++iter) {
+        for (int i = 0; i < n_items; ++i, ++g) {
+          const uint32_t s = g % kStages, use = g / kStages;
+          const RingItem it = s_items[i];
+          const int buf = it.layer & 1;
+          if (it.flags & kItemFirstOfLayer) {
+            const uint32_t started = (uint32_t)iter * (buf ? 4u : 5u) + (uint32_t)(it.layer >> 1);
+            if (started > 0) mbar_wait(&acc_empty[buf], (started - 1) & 1, 200 + buf, (int)g);
+          }
+          const int c = it.a_chunk;
+          if (it.flags & kItemWaitA) {
+            const uint32_t uses = (c == 4) ? (uint32_t)iter : (uint32_t)iter * 8u + (uint32_t)(it.layer - 1);
+            mbar_wait(&a_ready[c], uses & 1, 300 + c, (int)g);
+          }
+          mbar_wait(&full[s], use & 1, 400 + s, (int)g);
+          tc_fence_after();
+          const uint32_t n = (uint32_t)it.n_rows8 * 8u;
+          const uint32_t idesc = make_idesc_f16(128, (int)n, Elem<T>::fmt);
+          const uint32_t d = tmem_base + (uint32_t)buf * 256u + (uint32_t)it.n_off8 * 8u;
+          const uint64_t bdesc = make_sw128_kmajor_desc(ring_addr + s * kStageBytes);
+          const uint64_t ahi = make_sw128_kmajor_desc(c == 4 ? pe_hi_addr : a_hi_addr + c * kChunkBytes);
+          const uint32_t first = (it.flags & kItemFirstOfAcc) ? 1u : 0u;
+          if (it.part == 0) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+              umma_f16(d, ahi + 2 * k, bdesc + 2 * k, idesc, (first && k == 0) ? 0u : 1u);
+            if (NTERMS == 3) {
+              const uint64_t alo = make_sw128_kmajor_desc(c == 4 ? pe_lo_addr : a_lo_addr + c * kChunkBytes);
+#pragma unroll
+              for (int k = 0; k < 4; ++k) umma_f16(d, alo + 2 * k, bdesc + 2 * k, idesc, 1u);
+            }
+          } else {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) umma_f16(d, ahi + 2 * k, bdesc + 2 * k, idesc, 1u);
+          }
+          if (CL == 1) umma_commit(&empty[s]);
+          else umma_commit_multicast(&empty[s], (uint16_t)((1u << CL) - 1));
+          if (it.flags & kItemLastOfLayer) umma_commit(&acc_full[buf]);
+        }
+      }
+    }
+  } else {
+    // ===================================== epilogue warps ================================
+    const int q = warp & 3, hf = warp >> 2;
+    const int row = q * 32 + lane;                 // TMEM lane == A-tile row
+    const uint32_t lane_taddr = tmem_base + ((uint32_t)(q * 32) << 16);
+    uint8_t* A_hi = smem + Plan::a_hi;
+    uint8_t* A_lo = smem + Plan::a_lo;
+    uint8_t* PE_hi = smem + Plan::pe_hi;
+    uint8_t* PE_lo = smem + Plan::pe_lo;
+    float* sc = reinterpret_cast<float*>(smem + Plan::scratch) + warp * kScratchFloatsPerWarp;
+    const float k1 = kSoftplusBeta * kInvWeightScale;
+    const int p8 = lane >> 2, ty = lane & 3;       // MODE_GRAD: point-in-warp, row type
+    const float b8 = bias100[8 * kHidden];
+
+    for (int iter = 0; iter < args.iters; ++iter) {
+      const long long tile = (long long)blockIdx.x + (long long)iter * gridDim.x;
+      // ------------------------------------------------ input stage: positional encoding
+      long long pt;
+      if (MODE == 0) pt = tile * 128 + row;
+      else pt = tile * 32 + q * 8 + p8;
+      float x[3];
+      load_point(args, pt, net_scale, x);
+      if (hf == 0)
+        pe_stage<NTERMS, MODE, T, 0>(args, x, multires, lane, row, pt, tile, PE_hi, PE_lo);
+      else
+        pe_stage<NTERMS, MODE, T, 1>(args, x, multires, lane, row, pt, tile, PE_hi, PE_lo);
+      fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&a_ready[4]);
+
+      // ------------------------------------------------ hidden layers 0..7
+      for (int l = 0; l < 8; ++l) {
+        const int buf = l & 1;
+        mbar_wait(&acc_full[buf], ((uint32_t)iter * (buf ? 4u : 5u) + (uint32_t)(l >> 1)) & 1, 500 + buf, l);
+        tc_fence_after();
+        const float* bl = bias100 + l * kHidden;
+#pragma unroll 1
+        for (int cc = 0; cc < 2; ++cc) {
+          const int chunk = 2 * cc + hf;
+          uint8_t* dst_hi = A_hi + chunk * kChunkBytes;
+          uint8_t* dst_lo = A_lo + chunk * kChunkBytes;
+#pragma unroll 1
+          for (int half = 0; half < 2; ++half) {
+            const int col0 = chunk * 64 + half * 32;
+            uint32_t r[32];
+            tmem_ld_32x32b_x32(lane_taddr + (uint32_t)(buf * 256 + col0), r);
+            tmem_wait_ld();
+            if (args.dbg_acc && tile == 0) {
+#pragma unroll
+              for (int k = 0; k < 32; ++k)
+                args.dbg_acc[((size_t)l * 128 + row) * 256 + col0 + k] = __uint_as_float(r[k]) * kInvWeightScale;
+            }
+            if (MODE == 0) {
+#pragma unroll
+              for (int g = 0; g < 4; ++g) {
+                const float4 bA = __ldg(reinterpret_cast<const float4*>(bl + col0 + g * 8));
+                const float4 bB = __ldg(reinterpret_cast<const float4*>(bl + col0 + g * 8 + 4));
+                const float bb[8] = {bA.x, bA.y, bA.z, bA.w, bB.x, bB.y, bB.z, bB.w};
+                float h[8];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                  float dummy;
+                  h[j] = softplus100<false>(fmaf(__uint_as_float(r[g * 8 + j]), k1, bb[j]), dummy);
+                }
+                store_group<NTERMS, T>(dst_hi, dst_lo, row, half * 4 + g, h);
+              }
+            } else {
+              // phase A: value lanes publish their raw accumulators
+              if (ty == 0) {
+#pragma unroll
+                for (int i = 0; i < 8; ++i)
+                  *reinterpret_cast<float4*>(sc + p8 * 36 + 4 * i) =
+                      make_float4(__uint_as_float(r[4 * i]), __uint_as_float(r[4 * i + 1]),
+                                  __uint_as_float(r[4 * i + 2]), __uint_as_float(r[4 * i + 3]));
+              }
+              __syncwarp();
+              // phase B: every lane does 8 columns of its point's value row
+              {
+                const float4 vA = *reinterpret_cast<const float4*>(sc + p8 * 36 + 8 * ty);
+                const float4 vB = *reinterpret_cast<const float4*>(sc + p8 * 36 + 8 * ty + 4);
+                const float va[8] = {vA.x, vA.y, vA.z, vA.w, vB.x, vB.y, vB.z, vB.w};
+                const float4 bA = __ldg(reinterpret_cast<const float4*>(bl + col0 + 8 * ty));
+                const float4 bB = __ldg(reinterpret_cast<const float4*>(bl + col0 + 8 * ty + 4));
+                const float bb[8] = {bA.x, bA.y, bA.z, bA.w, bB.x, bB.y, bB.z, bB.w};
+                float h[8], sg[8];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                  float s;
+                  h[j] = softplus100<true>(fmaf(va[j], k1, bb[j]), s);
+                  sg[j] = s * kInvWeightScale;   // tangent accumulators carry the weight pre-scale
+                }
+                store_group<NTERMS, T>(dst_hi, dst_lo, q * 32 + 4 * p8, half * 4 + ty, h);
+                *reinterpret_cast<float4*>(sc + p8 * 36 + 8 * ty) = make_float4(sg[0], sg[1], sg[2], sg[3]);
+                *reinterpret_cast<float4*>(sc + p8 * 36 + 8 * ty + 4) = make_float4(sg[4], sg[5], sg[6], sg[7]);
+              }
+              __syncwarp();
+              // phase C: tangent rows: d h = sigmoid(100 a) * d a
+              if (ty != 0) {
+#pragma unroll
+                for (int g = 0; g < 4; ++g) {
+                  const float4 sA = *reinterpret_cast<const float4*>(sc + p8 * 36 + 8 * g);
+                  const float4 sB = *reinterpret_cast<const float4*>(sc + p8 * 36 + 8 * g + 4);
+                  const float ss[8] = {sA.x, sA.y, sA.z, sA.w, sB.x, sB.y, sB.z, sB.w};
+                  float tv[8];
+#pragma unroll
+                  for (int j = 0; j < 8; ++j) tv[j] = ss[j] * __uint_as_float(r[g * 8 + j]);
+                  store_group<NTERMS, T>(dst_hi, dst_lo, row, half * 4 + g, tv);
+                }
+              }
+              __syncwarp();
+            }
+          }
+          fence_proxy_async_smem();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&a_ready[chunk]);
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&acc_empty[buf]);
+      }
+
+      // ------------------------------------------------ output layer (layer 8, accumulator buf 0, col 0)
+      mbar_wait(&acc_full[0], ((uint32_t)iter * 5u + 4u) & 1, 510);
+      tc_fence_after();
+      if (hf == 0) {
+        const float accv = __uint_as_float(tmem_ld_32x32b_x1(lane_taddr)) * kInvWeightScale;
+        tmem_wait_ld();
+        if (args.dbg_acc && tile == 0) args.dbg_acc[((size_t)8 * 128 + row) * 256] = accv;
+        const bool ok = (tile < args.num_tiles) && (pt < args.P);
+        if (MODE == 0) {
+          const float a = accv + b8;
+          float u = (udf_type == 0) ? fabsf(a) : (udf_type == 1 ? a * a : a);
+          if (ok) args.udf_out[pt] = u / net_scale;
+        } else {
+          const float a_own = accv + b8;
+          const float a = __shfl_sync(0xffffffffu, a_own, lane & ~3);
+          if (ty == 0) {
+            float u = (udf_type == 0) ? fabsf(a) : (udf_type == 1 ? a * a : a);
+            if (ok) args.udf_out[pt] = u / net_scale;
+          } else {
+            float gmul = 1.f;
+            if (udf_type == 0) gmul = (a > 0.f) ? 1.f : (a < 0.f ? -1.f : 0.f);
+            else if (udf_type == 1) gmul = 2.f * a;
+            if (ok) args.grad_out[pt * 3 + (ty - 1)] = gmul * accv;
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&acc_empty[0]);
+    }
+  }
+
+  // ---- teardown
+  tc_fence_before();
+  if (CL > 1) cluster_sync_all(); else __syncthreads();
+  if (warp == 9) tmem_dealloc(tmem_base, 512);
+}
+
+// ---------------------------------------------------------------------------------------------
+template <int NTERMS, int MODE, typename T, int CL>
+static int launch(const MlpArgs& a_in, cudaStream_t stream) {
+  using Plan = SmemPlan<NTERMS, MODE>;
+  MlpArgs a = a_in;
+  const int pts_per_tile = (MODE == 0) ? 128 : 32;
+  const long long tiles = (a.P + pts_per_tile - 1) / pts_per_tile;
+  if (tiles > 0x7fffffffLL) return set_error("too many points");
+  a.num_tiles = (int)tiles;
+  int grid = sm_count();
+  grid = grid / CL * CL;
+  if (tiles < grid) grid = (int)((tiles + CL - 1) / CL * CL);
+  a.iters = (int)((tiles + grid - 1) / grid);
+  auto kern = mlp_kernel<NTERMS, MODE, T, CL>;
+  static bool attr_done = false;   // per template instantiation
+  if (!attr_done) {
+    EMAP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Plan::total));
+    attr_done = true;
+  }
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = dim3(grid);
+  cfg.blockDim = dim3(kThreads);
+  cfg.dynamicSmemBytes = Plan::total;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = CL;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  EMAP_CUDA(cudaLaunchKernelEx(&cfg, kern, a));
+  return 0;
+}
+
+static int g_cluster = 1;   // weight-stream multicast width (1, 2 or 4); see emap_set_option
+
+template <int MODE>
+static int dispatch(const emap_net_desc* net, int precision, const MlpArgs& a, cudaStream_t st) {
+  const int cl = g_cluster;
+#define EMAP_LAUNCH(NT, TT)                                              \
+  do {                                                                   \
+    if (cl == 4) return launch<NT, MODE, TT, 4>(a, st);                  \
+    if (cl == 2) return launch<NT, MODE, TT, 2>(a, st);                  \
+    return launch<NT, MODE, TT, 1>(a, st);                               \
+  } while (0)
+  if (precision == EMAP_PREC_FP32X3) {
+    if (net->elem_type == 0) EMAP_LAUNCH(3, __half); else EMAP_LAUNCH(3, __nv_bfloat16);
+  } else if (precision == EMAP_PREC_HALF) {
+    if (net->elem_type == 0) EMAP_LAUNCH(1, __half); else EMAP_LAUNCH(1, __nv_bfloat16);
+  }
+#undef EMAP_LAUNCH
+  return set_error("precision must be EMAP_PREC_FP32X3 (3) or EMAP_PREC_HALF (1)");
+}
+
+static int check_points(const float* pts, const float* rays_o, const float* rays_d, const float* z,
+                        int n_per_ray, long long P) {
+  if (P <= 0) return set_error("P must be > 0");
+  if (!pts) {
+    if (!rays_o || !rays_d || !z) return set_error("give either pts or (rays_o, rays_d, z)");
+    if (n_per_ray <= 0 || P % n_per_ray) return set_error("P must be a multiple of n_per_ray");
+  }
+  return 0;
+}
+
+int set_cluster_width(int v) {
+  if (v != 1 && v != 2 && v != 4) return set_error("cluster width must be 1, 2 or 4");
+  g_cluster = v;
+  return 0;
+}
+
+}  // namespace emap
+
+using namespace emap;
+
+extern "C" int emap_udf_forward(const emap_net_desc* net, const void* packed, int precision,
+                                const float* pts, const float* rays_o, const float* rays_d,
+                                const float* z, int32_t n_per_ray, int64_t P, float* udf_out,
+                                float* pe_out, void* stream) {
+  if (check_net(net)) return 1;
+  if (!packed || !udf_out) return set_error("emap_udf_forward: NULL pointer");
+  if (check_points(pts, rays_o, rays_d, z, n_per_ray, P)) return 1;
+  MlpArgs a;
+  memset(&a, 0, sizeof(a));
+  a.packed = (const uint8_t*)packed; a.pts = pts; a.rays_o = rays_o; a.rays_d = rays_d; a.z = z;
+  a.n_per_ray = n_per_ray; a.P = P; a.udf_out = udf_out; a.pe_out = pe_out;
+  return dispatch<0>(net, precision, a, (cudaStream_t)stream);
+}
+
+extern "C" int emap_udf_forward_grad(const emap_net_desc* net, const void* packed, int precision,
+                                     const float* pts, const float* rays_o, const float* rays_d,
+                                     const float* z, int32_t n_per_ray, int64_t P, float* udf_out,
+                                     float* grad_out, void* stream) {
+  if (check_net(net)) return 1;
+  if (!packed || !udf_out || !grad_out) return set_error("emap_udf_forward_grad: NULL pointer");
+  if (check_points(pts, rays_o, rays_d, z, n_per_ray, P)) return 1;
+  MlpArgs a;
+  memset(&a, 0, sizeof(a));
+  a.packed = (const uint8_t*)packed; a.pts = pts; a.rays_o = rays_o; a.rays_d = rays_d; a.z = z;
+  a.n_per_ray = n_per_ray; a.P = P; a.udf_out = udf_out; a.grad_out = grad_out;
+  return dispatch<1>(net, precision, a, (cudaStream_t)stream);
+}
+
+// Debug / test hook: run the forward (mode 0) or forward+grad (mode 1) kernel and additionally dump
+// the de-scaled accumulators of tile 0, layer by layer: dbg_acc[9][128][256] floats.
+extern "C" int emap_debug_mlp(const emap_net_desc* net, const void* packed, int precision, int mode,
+                              const float* pts, int64_t P, float* udf_out, float* grad_out,
+                              float* dbg_acc, void* stream) {
+  if (check_net(net)) return 1;
+  if (!packed || !udf_out || !pts) return set_error("emap_debug_mlp: NULL pointer");
+  MlpArgs a;
+  memset(&a, 0, sizeof(a));
+  a.packed = (const uint8_t*)packed; a.pts = pts; a.P = P; a.udf_out = udf_out; a.grad_out = grad_out;
+  a.dbg_acc = dbg_acc;
+  if (mode == 0) return dispatch<0>(net, precision, a, (cudaStream_t)stream);
+  if (!grad_out) return set_error("emap_debug_mlp: grad_out required for mode 1");
+  return dispatch<1>(net, precision, a, (cudaStream_t)stream);
+}
+
+extern "C" int emap_set_option(const char* name, int value) {
+  if (!name) return set_error("option name is NULL");
+  if (!strcmp(name, "cluster")) return set_cluster_width(value);
+  return set_error("unknown option '%s'", name);
+}

@@ -1,0 +1,243 @@
+// K0: weight-norm fold + packing of the MLP weights into tensor-core operand images.
+//
+// Replaces the reference's per-forward `torch._weight_norm` (src/models/udf_model.py:74; run 63x per
+// render()) by one fold per optimizer step.  Outputs, all in one device buffer ("packed"):
+//   * W_eff (fp32, row-major [out,in]) per layer:  W = g * v / ||v||_row
+//   * bias100 = 100*b  (the epilogue evaluates softplus on t = 100*a)
+//   * for every (layer, K-chunk of 64, N-half) a [rows x 64] K-major, 128B-swizzled 16-bit image
+//     of W * 16 (hi part) and of the residual (lo part) -- exactly the byte layout tcgen05.mma
+//     expects in shared memory, so the MLP kernel streams them with 1-D bulk copies.
+//   * the two "ring item" tables (1-term and 3-term MMA schedules) describing the stream order.
+#include <math.h>
+#include <string.h>
+#include <vector>
+
+#include "common.cuh"
+#include "host.h"
+
+namespace emap {
+
+void net_dims(int multires, int* in_dim, int* out_dim) {
+  const int pe = 3 + 6 * multires;
+  for (int l = 0; l < kNumLinear; ++l) { in_dim[l] = kHidden; out_dim[l] = kHidden; }
+  in_dim[0] = pe;
+  out_dim[kSkipLayer - 1] = kHidden - pe;
+  out_dim[kNumLinear - 1] = 1;
+}
+
+size_t flat_param_count(int multires) {
+  int in_dim[kNumLinear], out_dim[kNumLinear];
+  net_dims(multires, in_dim, out_dim);
+  size_t n = 0;
+  for (int l = 0; l < kNumLinear; ++l) n += (size_t)out_dim[l] * (2 + in_dim[l]);
+  return n;
+}
+
+static inline uint32_t align_up(uint32_t x, uint32_t a) { return (x + a - 1) / a * a; }
+
+// Build header + item tables (host).  Deterministic function of (multires, elem_type).
+void build_layout(const emap_net_desc& net, PackedHeader& h, std::vector<RingItem>& t1,
+                  std::vector<RingItem>& t3) {
+  memset(&h, 0, sizeof(h));
+  h.magic = 0x50414D45u;  // "EMAP"
+  h.multires = (uint32_t)net.multires;
+  h.elem_type = (uint32_t)net.elem_type;
+  h.scale = net.scale;
+  h.udf_type = (uint32_t)net.udf_type;
+  int in_dim[kNumLinear], out_dim[kNumLinear];
+  net_dims(net.multires, in_dim, out_dim);
+  for (int l = 0; l < kNumLinear; ++l) { h.in_dim[l] = in_dim[l]; h.out_dim[l] = out_dim[l]; }
+
+  uint32_t off = align_up(sizeof(PackedHeader), 256);
+  h.items_off[0] = off;  off += kMaxItems * sizeof(RingItem);
+  h.items_off[1] = off;  off += kMaxItems * sizeof(RingItem);
+  h.bias100_off = off;   off += kNumLinear * kHidden * sizeof(float);
+  h.weff_off = off;
+  for (int l = 0; l < kNumLinear; ++l) {
+    h.weff_layer_off[l] = off;
+    off += (uint32_t)out_dim[l] * in_dim[l] * sizeof(float);
+  }
+  off = align_up(off, 1024);
+  h.images_off = off;
+
+  t1.clear(); t3.clear();
+  uint32_t img = 0;
+  for (int l = 0; l < kNumLinear; ++l) {
+    int N = kHidden;
+    // layer 3 keeps N=256: its zero-padded weight rows make the unused accumulator columns exact
+    // zeros (stale TMEM there could hold NaN patterns that would poison layer 4 through 0*NaN)
+    if (l == kNumLinear - 1) N = 16;
+    int kcs[5]; int nkc = 0;
+    if (l == 0) { kcs[nkc++] = 4; }
+    else { for (int c = 0; c < 4; ++c) kcs[nkc++] = c; if (l == kSkipLayer) kcs[nkc++] = 4; }
+    struct Half { int off, rows; } halves[2]; int nh = 0;
+    if (N <= 128) { halves[nh++] = {0, N}; }
+    else { halves[nh++] = {0, 128}; halves[nh++] = {128, N - 128}; }
+    for (int ic = 0; ic < nkc; ++ic) {
+      for (int ih = 0; ih < nh; ++ih) {
+        for (int part = 0; part < 2; ++part) {
+          RingItem it; memset(&it, 0, sizeof(it));
+          it.gmem_off = h.images_off + img;
+          const uint32_t bytes = (uint32_t)halves[ih].rows * 128u;
+          it.bytes16 = (uint16_t)(bytes / 16);
+          it.layer = (uint8_t)l;
+          it.a_chunk = (uint8_t)kcs[ic];
+          it.n_off8 = (uint8_t)(halves[ih].off / 8);
+          it.n_rows8 = (uint8_t)(halves[ih].rows / 8);
+          it.part = (uint8_t)part;
+          uint8_t fl = 0;
+          if (ic == 0 && part == 0) fl |= kItemFirstOfAcc;
+          // layer 4 re-reads the PE chunk written for layer 0: nothing to wait for
+          if (ih == 0 && part == 0 && !(l == kSkipLayer && kcs[ic] == 4)) fl |= kItemWaitA;
+          if (ic == 0 && ih == 0 && part == 0) fl |= kItemFirstOfLayer;
+          it.flags = fl;
+          img += bytes;
+          t3.push_back(it);
+          if (part == 0) t1.push_back(it);
+        }
+      }
+    }
+    t1.back().flags |= kItemLastOfLayer;
+    t3.back().flags |= kItemLastOfLayer;
+  }
+  h.images_bytes = img;
+  h.n_items[0] = (uint32_t)t1.size();
+  h.n_items[1] = (uint32_t)t3.size();
+  h.total_bytes = align_up(h.images_off + img, 1024);
+}
+
+// ---- kernels -----------------------------------------------------------------------------------
+// One warp per output row of one layer: W_eff[row,:] = g[row] * v[row,:] / ||v[row,:]||.
+__global__ void wn_fold_kernel(const float* __restrict__ flat, uint8_t* __restrict__ packed,
+                               int multires) {
+  const PackedHeader* h = reinterpret_cast<const PackedHeader*>(packed);
+  int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  int lane = threadIdx.x & 31;
+  // locate (layer,row)
+  int l = 0, row = warp;
+  size_t poff = 0;
+  for (; l < kNumLinear; ++l) {
+    int od = (int)h->out_dim[l], id = (int)h->in_dim[l];
+    if (row < od) break;
+    row -= od;
+    poff += (size_t)od * (2 + id);
+  }
+  if (l >= kNumLinear) return;
+  const int od = (int)h->out_dim[l], id = (int)h->in_dim[l];
+  const float* bias = flat + poff;
+  const float* g = bias + od;
+  const float* v = g + od + (size_t)row * id;
+  double ss = 0.0;
+  for (int k = lane; k < id; k += 32) { double t = (double)v[k]; ss += t * t; }
+  for (int o = 16; o; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
+  // torch._weight_norm: w = v * (g / norm) in fp32
+  const float norm = (float)sqrt(ss);
+  const float ratio = g[row] / norm;
+  float* W = reinterpret_cast<float*>(packed + h->weff_layer_off[l]) + (size_t)row * id;
+  for (int k = lane; k < id; k += 32) W[k] = v[k] * ratio;
+  if (lane == 0) {
+    float* b100 = reinterpret_cast<float*>(packed + h->bias100_off) + l * kHidden;
+    b100[row] = (l == kNumLinear - 1) ? bias[row] : kSoftplusBeta * bias[row];
+  }
+  // zero the padded tail of the bias row (layer 3: rows >= out_dim; layer 8: rows >= 1)
+  if (row == 0) {
+    float* b100 = reinterpret_cast<float*>(packed + h->bias100_off) + l * kHidden;
+    for (int k = od + lane; k < kHidden; k += 32) b100[k] = 0.f;
+  }
+}
+
+template <typename T> __device__ __forceinline__ T to_elem(float x);
+template <> __device__ __forceinline__ __half to_elem<__half>(float x) { return __float2half_rn(x); }
+template <> __device__ __forceinline__ __nv_bfloat16 to_elem<__nv_bfloat16>(float x) { return __float2bfloat16_rn(x); }
+template <typename T> __device__ __forceinline__ float from_elem(T x);
+template <> __device__ __forceinline__ float from_elem<__half>(__half x) { return __half2float(x); }
+template <> __device__ __forceinline__ float from_elem<__nv_bfloat16>(__nv_bfloat16 x) { return __bfloat162float(x); }
+
+// One block per item of the 3-term table (which enumerates every image, hi and lo).
+template <typename T>
+__global__ void pack_images_kernel(uint8_t* __restrict__ packed) {
+  const PackedHeader* h = reinterpret_cast<const PackedHeader*>(packed);
+  const RingItem it = reinterpret_cast<const RingItem*>(packed + h->items_off[1])[blockIdx.x];
+  const int l = it.layer, kc = it.a_chunk, n_off = it.n_off8 * 8, rows = it.n_rows8 * 8;
+  const int od = (int)h->out_dim[l], id = (int)h->in_dim[l];
+  const int L = (int)h->multires, pe = 3 + 6 * L;
+  const float* W = reinterpret_cast<const float*>(packed + h->weff_layer_off[l]);
+  T* img = reinterpret_cast<T*>(packed + it.gmem_off);
+  const float inv_sqrt2 = 0.70710678118654752440f;
+  for (int e = threadIdx.x; e < rows * 64; e += blockDim.x) {
+    const int n = e >> 6, kk = e & 63;
+    const int o = n_off + n;
+    float val = 0.f;
+    if (o < od) {
+      int src = -1;
+      float mul = 1.f;
+      if (l == 0) {
+        src = pe_col_to_ref(kk, L);
+      } else if (l == kSkipLayer) {
+        mul = inv_sqrt2;
+        if (kc < 4) { int idx = kc * 64 + kk; src = (idx < kHidden - pe) ? idx : -1; }
+        else { int r = pe_col_to_ref(kk, L); src = (r >= 0) ? (kHidden - pe) + r : -1; }
+      } else {
+        src = kc * 64 + kk;
+      }
+      if (src >= 0 && src < id) val = W[(size_t)o * id + src] * mul * kWeightScale;
+    }
+    const T hi = to_elem<T>(val);
+    const T out = (it.part == 0) ? hi : to_elem<T>(val - from_elem<T>(hi));
+    img[sw128_offset(n, kk) >> 1] = out;
+  }
+}
+
+// ---- host entry points -------------------------------------------------------------------------
+int check_net(const emap_net_desc* net) {
+  if (!net) return set_error("net desc is NULL");
+  if (net->multires < 0 || net->multires > kMaxFreq) return set_error("multires must be in [0,10]");
+  if (net->udf_type < 0 || net->udf_type > 2) return set_error("udf_type must be 0(abs),1(square),2(sdf)");
+  if (net->elem_type < 0 || net->elem_type > 1) return set_error("elem_type must be 0(fp16) or 1(bf16)");
+  if (!(net->scale > 0.f)) return set_error("scale must be > 0");
+  return 0;
+}
+
+}  // namespace emap
+
+using namespace emap;
+
+extern "C" size_t emap_flat_param_count(const emap_net_desc* net) {
+  if (check_net(net)) return 0;
+  return flat_param_count(net->multires);
+}
+
+extern "C" size_t emap_packed_size(const emap_net_desc* net) {
+  if (check_net(net)) return 0;
+  PackedHeader h; std::vector<RingItem> t1, t3;
+  build_layout(*net, h, t1, t3);
+  return h.total_bytes;
+}
+
+extern "C" int emap_wn_fold(const emap_net_desc* net, const float* flat_params, void* packed,
+                            void* stream_) {
+  if (check_net(net)) return 1;
+  if (!flat_params || !packed) return set_error("emap_wn_fold: NULL pointer");
+  cudaStream_t stream = (cudaStream_t)stream_;
+  PackedHeader h; std::vector<RingItem> t1, t3;
+  build_layout(*net, h, t1, t3);
+  if (t3.size() > (size_t)kMaxItems) return set_error("internal: item table overflow");
+  // header + tables: small pageable H2D copies (stream-ordered; contents are a pure function of net)
+  uint8_t* p = reinterpret_cast<uint8_t*>(packed);
+  EMAP_CUDA(cudaMemcpyAsync(p, &h, sizeof(h), cudaMemcpyHostToDevice, stream));
+  EMAP_CUDA(cudaMemcpyAsync(p + h.items_off[0], t1.data(), t1.size() * sizeof(RingItem),
+                            cudaMemcpyHostToDevice, stream));
+  EMAP_CUDA(cudaMemcpyAsync(p + h.items_off[1], t3.data(), t3.size() * sizeof(RingItem),
+                            cudaMemcpyHostToDevice, stream));
+  int rows = 0;
+  for (int l = 0; l < kNumLinear; ++l) rows += (int)h.out_dim[l];
+  const int threads = 256, wpb = threads / 32;
+  wn_fold_kernel<<<(rows + wpb - 1) / wpb, threads, 0, stream>>>(flat_params, p, net->multires);
+  EMAP_CUDA(cudaGetLastError());
+  if (net->elem_type == 0)
+    pack_images_kernel<__half><<<(unsigned)t3.size(), 256, 0, stream>>>(p);
+  else
+    pack_images_kernel<__nv_bfloat16><<<(unsigned)t3.size(), 256, 0, stream>>>(p);
+  EMAP_CUDA(cudaGetLastError());
+  return 0;
+}

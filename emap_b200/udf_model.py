@@ -1,0 +1,210 @@
+"""Drop-in replacements for the reference's field modules (``src/models/udf_model.py``).
+
+Same class names, constructor kwargs, method names, return shapes and ``state_dict`` keys as the
+reference, so ``runner_base.py:96-117`` / ``runner_udf.py:252-285,520-526`` work
+unchanged -- but ``forward`` / ``udf`` / ``gradient`` execute the sm_100a kernels behind the C ABI
+(``include/emap_b200.h``): K0 weight-norm fold, K1 fused PE+MLP forward, K1g forward+gradient,
+K1b backward.  There is no eager/CPU fallback: calling these on CPU tensors raises.
+"""
+from __future__ import annotations
+
+import math
+from typing import Optional, Tuple
+
+import torch
+import torch.nn as nn
+
+from . import _cabi as C
+from . import ops
+from .embedder import get_embedder
+
+
+class UDFNetwork(nn.Module):
+    """9-Linear weight-normed softplus MLP on a 63-d positional encoding.
+
+    reference: src/models/udf_model.py:7-135.  ``precision`` is new: "fp32" (default; split-fp16
+    3-MMA tensor-core arithmetic, fp32-class accuracy), "fp16" or "bf16" (single MMA).
+    """
+
+    def __init__(self, d_in, d_out, d_hidden, n_layers, skip_in=(4,), multires=0, scale=1, bias=0.5,
+                 geometric_init=True, weight_norm=True, udf_type="abs", precision="fp32"):
+        super().__init__()
+        skip_in = tuple(skip_in)
+        if (d_in, d_out, d_hidden, n_layers, skip_in) != (3, 1, 256, 8, (4,)) or not weight_norm:
+            raise NotImplementedError(
+                "emap_b200 kernels are built for the reference topology d_in=3, d_out=1, d_hidden=256, "
+                "n_layers=8, skip_in=[4], weight_norm=True (confs/*.conf udf_network); got "
+                f"{(d_in, d_out, d_hidden, n_layers, skip_in, weight_norm)}")
+        if not (0 <= multires <= 10):
+            raise NotImplementedError("multires must be in [0, 10]")
+        if udf_type not in C.UDF_TYPES:
+            raise ValueError(f"unknown udf_type {udf_type!r}")
+        if precision not in C.PRECISIONS:
+            raise ValueError(f"precision must be one of {sorted(C.PRECISIONS)}")
+
+        self.embed_fn_fine = None
+        dims = [d_in] + [d_hidden] * n_layers + [d_out]
+        if multires > 0:
+            self.embed_fn_fine, dims[0] = get_embedder(multires, input_dims=d_in)
+        self.num_layers = len(dims)
+        self.skip_in = skip_in
+        self.scale = scale
+        self.multires = multires
+        self.geometric_init = geometric_init
+        self.udf_type = udf_type
+        self.precision = precision
+
+        # Parameters are created through the same torch calls, in the same order, as the reference
+        # constructor, so a given torch seed yields bit-identical initial weights and the same
+        # state_dict keys (lin{l}.bias, lin{l}.parametrizations.weight.original0/1).
+        last = self.num_layers - 2
+        for l in range(self.num_layers - 1):
+            fan_out = dims[l + 1] - dims[0] if (l + 1) in skip_in else dims[l + 1]
+            lin = nn.Linear(dims[l], fan_out)
+            if geometric_init:
+                self._sphere_init(lin, l, last, dims, fan_out, multires, bias)
+            lin = nn.utils.parametrizations.weight_norm(lin)
+            setattr(self, f"lin{l}", lin)
+
+        self.activation = nn.Softplus(beta=100)   # kept for API parity; the kernels fuse it
+        self._net: Optional[ops.PackedNet] = None
+        self._folded_version = None
+
+    @staticmethod
+    def _sphere_init(lin, l, last, dims, fan_out, multires, bias):
+        """Geometric (sphere) initialisation, udf_model.py:47-72."""
+        w, b = lin.weight, lin.bias
+        std = math.sqrt(2) / math.sqrt(fan_out)
+        with torch.no_grad():
+            if l == last:
+                nn.init.normal_(w, mean=math.sqrt(math.pi) / math.sqrt(dims[l]), std=0.0001)
+                nn.init.constant_(b, -bias)
+            elif multires > 0 and l == 0:
+                nn.init.constant_(b, 0.0)
+                nn.init.constant_(w[:, 3:], 0.0)
+                nn.init.normal_(w[:, :3], 0.0, std)
+            elif multires > 0 and l in (4,):
+                nn.init.constant_(b, 0.0)
+                nn.init.normal_(w, 0.0, std)
+                nn.init.constant_(w[:, -(dims[0] - 3):], 0.0)
+            else:
+                nn.init.constant_(b, 0.0)
+                nn.init.normal_(w, 0.0, std)
+
+    # ------------------------------------------------------------------ device-side state
+    def flat_param_list(self):
+        """Parameters in ``parameters()`` order: per layer bias, g (original0), v (original1)."""
+        return list(self.parameters())
+
+    def _params_version(self):
+        ps = self.flat_param_list()
+        return (tuple(p._version for p in ps), tuple(p.data_ptr() for p in ps), self.precision)
+
+    def packed(self) -> ops.PackedNet:
+        """Fold weight-norm and (re)pack the tensor-core operands iff a parameter changed."""
+        ps = self.flat_param_list()
+        dev = ps[0].device
+        if dev.type != "cuda":
+            raise RuntimeError("emap_b200.UDFNetwork runs on CUDA only (no CPU path); call .to('cuda')")
+        elem = "bf16" if self.precision == "bf16" else "fp16"
+        if self._net is None or self._net.packed.device != dev or self._net_elem != elem:
+            self._net = ops.PackedNet(self.multires, self.udf_type, float(self.scale), elem, dev)
+            self._net_elem = elem
+            self._folded_version = None
+        ver = self._params_version()
+        if ver != self._folded_version:
+            with torch.no_grad():
+                flat = torch.cat([p.detach().reshape(-1) for p in ps])
+            self._net.fold(flat)
+            self._folded_version = ver
+        return self._net
+
+    @property
+    def prec_code(self) -> int:
+        return C.PRECISIONS[self.precision]
+
+    # ------------------------------------------------------------------ reference API
+    def udf_out(self, x):
+        if self.udf_type == "abs":
+            return torch.abs(x)
+        if self.udf_type == "square":
+            return x ** 2
+        return x
+
+    def forward(self, inputs):
+        """-> (out[P,1], PE[P,3+6L])   (udf_model.py:90-110)"""
+        from .autograd import udf_forward_fn
+        x = inputs.reshape(-1, 3)
+        udf, pe = udf_forward_fn(self, x, want_pe=True)
+        return udf.unsqueeze(-1), pe
+
+    def udf(self, x):
+        """-> (udf[P,1], feature[P,0], PE)   (udf_model.py:112-116)"""
+        out, pe = self.forward(x)
+        return out[:, :1], out[:, 1:], pe
+
+    def udf_hidden_appearance(self, x):
+        return self.forward(x)
+
+    def gradient(self, x):
+        """d udf / d x, [P,1,3], differentiable w.r.t. the parameters (udf_model.py:121-135)."""
+        from .autograd import udf_forward_grad_fn
+        x.requires_grad_(True)
+        _, g = udf_forward_grad_fn(self, x.reshape(-1, 3))
+        return g.unsqueeze(1)
+
+    def udf_and_gradient(self, x=None, rays_o=None, rays_d=None, z=None):
+        """Fused value + input-gradient (one kernel).  New entry point used by the renderer."""
+        from .autograd import udf_forward_grad_fn
+        return udf_forward_grad_fn(self, x, rays_o, rays_d, z)
+
+
+class SingleVarianceNetwork(nn.Module):
+    """inv_s = exp(10 * variance)   (udf_model.py:212-232)."""
+
+    def __init__(self, init_val, requires_grad=True):
+        super().__init__()
+        self.variance = nn.Parameter(torch.Tensor([init_val]), requires_grad=requires_grad)
+        self.second_variance = nn.Parameter(torch.Tensor([init_val]), requires_grad=requires_grad)
+
+    def set_trainable(self):
+        self.variance.requires_grad = True
+        self.second_variance.requires_grad = True
+
+    def forward(self, x):
+        return torch.ones([len(x), 1], device=x.device) * torch.exp(self.variance * 10.0)
+
+    def get_secondvariance(self, x):
+        return torch.ones([len(x), 1], device=x.device) * torch.exp(self.second_variance * 10.0)
+
+
+class BetaNetwork(nn.Module):
+    """beta / gamma / zeta scalars   (udf_model.py:235-286)."""
+
+    def __init__(self, init_var_beta=0.1, init_var_gamma=0.1, init_var_zeta=0.05, beta_min=0.00005,
+                 requires_grad_beta=True, requires_grad_gamma=True, requires_grad_zeta=True):
+        super().__init__()
+        self.beta = nn.Parameter(torch.Tensor([init_var_beta]), requires_grad=requires_grad_beta)
+        self.gamma = nn.Parameter(torch.Tensor([init_var_gamma]), requires_grad=requires_grad_gamma)
+        self.zeta = nn.Parameter(torch.Tensor([init_var_zeta]), requires_grad=requires_grad_zeta)
+        self.beta_min = beta_min
+
+    def get_beta(self):
+        return torch.exp(self.beta * 10).clip(0, 1.0 / self.beta_min)
+
+    def get_gamma(self):
+        return torch.exp(self.gamma * 10)
+
+    def get_zeta(self):
+        return self.zeta.abs()
+
+    def set_beta_trainable(self):
+        self.beta.requires_grad = True
+
+    @torch.no_grad()
+    def set_gamma(self, x):
+        self.gamma = nn.Parameter(torch.Tensor([x]), requires_grad=self.gamma.requires_grad).to(
+            self.gamma.device)
+
+    def forward(self):
+        return self.get_beta(), self.get_gamma(), self.get_zeta()

@@ -1,0 +1,125 @@
+/* emap_b200 -- C ABI of the B200-native EMAP volume-rendering hot path.
+ *
+ * Plain C, raw device pointers + explicit sizes, a cudaStream_t (as void*) last, int status
+ * return (0 = ok, non-zero = error; text via emap_last_error()).  No torch types cross this
+ * boundary.  All pointers are DEVICE pointers unless the name ends in _host.
+ *
+ * The reference (cvg/EMAP) has no FFI layer: its "interface" for this path is the Python methods
+ * of src/models/udf_model.py and src/models/udf_renderer_blending.py.  Each entry point below
+ * names the reference method(s) it replaces (file:line relative to the reference root); the Python
+ * classes in emap_b200/ (same names / kwargs / return dicts as the reference) are thin shims over
+ * these calls.  INTEGRATION.md shows the ctypes binding a maintainer of the reference would add.
+ */
+#ifndef EMAP_B200_H
+#define EMAP_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define EMAP_ABI_VERSION 1
+
+/* Network description == the `model.udf_network` conf block (confs/ABC.conf:65-77) restricted
+ * to the topology the kernels are built for: d_in=3, d_hidden=256, n_layers=8, skip_in=[4],
+ * d_out=1, weight_norm=True.  Anything else is rejected with an error (never silently emulated). */
+typedef struct emap_net_desc {
+  int32_t multires;   /* number of PE frequencies L, 0..10  (udf_model.py:30-33)            */
+  int32_t udf_type;   /* 0 = "abs", 1 = "square", 2 = "sdf" (udf_model.py:82-88)           */
+  float   scale;      /* UDFNetwork.scale                   (udf_model.py:36,91,108)       */
+  int32_t elem_type;  /* tensor-core operand type: 0 = fp16, 1 = bf16                       */
+} emap_net_desc;
+
+/* MLP arithmetic mode */
+#define EMAP_PREC_FP32X3 3 /* fp32-faithful: 3 split-fp16 tcgen05 MMAs (hi*hi + lo*hi + hi*lo), fp32 accum */
+#define EMAP_PREC_HALF   1 /* one fp16 (or bf16) tcgen05 MMA, fp32 accumulate                              */
+
+/* Flat parameter buffer layout (fp32), identical to list(UDFNetwork.parameters()) order:
+ *   for l in 0..8: bias[out_l], g[out_l] ("original0"), v[out_l*in_l] ("original1")
+ *   in  = [pe,256,256,256,256,256,256,256,256], out = [256,256,256,256-pe,256,256,256,256,1],
+ *   pe = 3+6*multires.   (udf_model.py:39-76; checkpoint keys SURVEY §5)                          */
+size_t emap_flat_param_count(const emap_net_desc* net);
+
+const char* emap_last_error(void);
+int emap_abi_version(void);
+
+/* ---- K0: weight-norm fold + tensor-core operand packing ------------------------------------
+ * replaces: torch weight_norm recomputation on every forward (udf_model.py:74; 63 calls/render).
+ * `packed` must hold emap_packed_size(net) bytes; it is rewritten whenever parameters change.   */
+size_t emap_packed_size(const emap_net_desc* net);
+int emap_wn_fold(const emap_net_desc* net, const float* flat_params, void* packed, void* stream);
+
+/* ---- K1: fused PE + 9-layer MLP forward -------------------------------------------------------
+ * replaces: Embedder.embed (embedder.py:34) + UDFNetwork.forward/.udf (udf_model.py:90-116).
+ * Points are given either explicitly (pts[P,3]) or implicitly as rays: P = n_rays*n_per_ray,
+ * point i = rays_o[i/n] + rays_d[i/n] * z[i]  (udf_renderer_blending.py:812, :360, :448).
+ * udf_out[P]; pe_out (optional) [P, 3+6L] in the reference column order.                         */
+int emap_udf_forward(const emap_net_desc* net, const void* packed, int precision,
+                     const float* pts, const float* rays_o, const float* rays_d, const float* z,
+                     int32_t n_per_ray, int64_t P, float* udf_out, float* pe_out, void* stream);
+
+/* ---- K1g: forward + d udf / d x in one pass (forward-mode tangents on the tensor cores) -------
+ * replaces: UDFNetwork.forward + UDFNetwork.gradient (udf_model.py:121-135), i.e. the second
+ * forward and the autograd.grad call at udf_renderer_blending.py:457-461.  grad_out[P,3].        */
+int emap_udf_forward_grad(const emap_net_desc* net, const void* packed, int precision,
+                          const float* pts, const float* rays_o, const float* rays_d,
+                          const float* z, int32_t n_per_ray, int64_t P, float* udf_out,
+                          float* grad_out, void* stream);
+
+/* ---- per-ray kernels (one warp per ray; <= 512 samples per ray, <= 64 new samples per step) ----
+ * z = near + (far-near)*lin + t_rand*2/n                   (udf_renderer_blending.py:705-720)
+ * near/far: device scalars [1] (near_is_per_ray=0) or [B] (=1); lin = torch.linspace(0,1,n) on
+ * the device; t_rand [B] = rand-0.5 (NULL when perturb == 0).                                    */
+int emap_coarse_z(const float* near, const float* far, int32_t near_is_per_ray, const float* lin,
+                  const float* t_rand, int32_t B, int32_t n, float* z_out, void* stream);
+
+/* One hierarchical up-sampling step, fused:
+ *   (1) if ka > 0: merge the pending samples (z_add, udf_add)[B,ka] into (z_in, udf_in)[B,n]
+ *       -> (z_out, udf_out)[B,n+ka]                      replaces cat_z_vals  (:355-377)
+ *   (2) if k > 0: density -> transmittance -> weights -> inverse CDF at the fixed quantiles u[k]
+ *       -> z_new[B,k] (ascending), inds_out[B,k] (searchsorted result, int64, optional),
+ *       weights_out[B,n+ka-1] (optional)   replaces up_sample_unbias (:228-353) [mode 0],
+ *       up_sample_no_occ_aware (:920-975) [mode 1] and sample_pdf(det=True) (:69-109);
+ *       mode 2 = sample_pdf alone: udf_in then holds the weights [B,n-1] as given.
+ * alpha_type: 0 "numerical", 1 "theorical" (:399-414).  sample_dist: device scalar.              */
+int emap_upsample_step(const float* rays_o, const float* rays_d, const float* z_in,
+                       const float* udf_in, int32_t n, const float* z_add, const float* udf_add,
+                       int32_t ka, float* z_out, float* udf_out, const float* u, int32_t k,
+                       float* z_new, int64_t* inds_out, float* weights_out, const float* sample_dist,
+                       int32_t B, float inv_s, float beta, float gamma, int32_t mode,
+                       int32_t alpha_type, void* stream);
+
+/* render_core before the MLP: dists, mid_z_vals          (udf_renderer_blending.py:435-446)     */
+int emap_render_prep(const float* z, const float* sample_dist, int32_t B, int32_t n, float* dists,
+                     float* mid_z, void* stream);
+
+/* render_core after the MLP (:463-650): occlusion-aware alpha, transmittance scan, compositing,
+ * eikonal / sparsity reductions.  scalars = device [inv_s, beta, gamma] (already exp'ed + clipped,
+ * :466-472).  cos_anneal_ratio < 0 means None.  Outputs: per sample weights, alpha (optional),
+ * grad_flip[B,n,3], inside_sphere, grad_mag; per ray edge, depth (un-scaled), normals[B,3];
+ * partials[B,5] (fp64 scratch); reduced[5] = {gradient_error, gradient_error_near_surface,
+ * sparse_error, sum(relax_inside_sphere), sum(near_surface)}.                                    */
+int emap_render_core_fwd(const float* rays_o, const float* rays_d, const float* mid_z,
+                         const float* dists, const float* udf, const float* grad,
+                         const float* scalars, int32_t B, int32_t n, float cos_anneal_ratio,
+                         float flip_saturation, float near_surface, float sparse_scale,
+                         int32_t use_unbias, int32_t use_norm_grad, int32_t alpha_type,
+                         float* weights, float* alpha, float* grad_flip, float* inside_sphere,
+                         float* grad_mag, float* edge, float* depth, float* normals,
+                         double* partials, float* reduced, void* stream);
+
+/* ---- misc ------------------------------------------------------------------------------------ */
+/* options: "cluster" = 1|2|4 : width of the weight-stream multicast cluster of the MLP kernels.  */
+int emap_set_option(const char* name, int value);
+/* test hook: MLP forward (mode 0) / forward+grad (mode 1) that also dumps the de-scaled
+ * accumulators of tile 0, dbg_acc[9][128][256].                                                  */
+int emap_debug_mlp(const emap_net_desc* net, const void* packed, int precision, int mode,
+                   const float* pts, int64_t P, float* udf_out, float* grad_out, float* dbg_acc,
+                   void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* EMAP_B200_H */
