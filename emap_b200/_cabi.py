@@ -51,6 +51,9 @@ SIGNATURES = {
     "emap_render_core_fwd": (ctypes.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _i32, _f32, _f32,
                                             _f32, _f32, _i32, _i32, _i32, _vp, _vp, _vp, _vp, _vp, _vp,
                                             _vp, _vp, _vp, _vp, _vp]),
+    "emap_render_core_bwd": (ctypes.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _i32, _f32, _f32,
+                                            _f32, _f32, _i32, _i32, _i32, _vp, _vp, _vp, _vp, _vp, _vp,
+                                            _vp, _vp, _vp, _vp, _vp, _vp]),
 }
 
 

@@ -431,6 +431,292 @@ __global__ void render_reduce_kernel(const double* __restrict__ partials, int B,
   }
 }
 
+
+// --------------------------------------------------------------------------------------------
+// K3 backward: cotangents of (weights, edge, depth, normals, gradient_error[_near_surface],
+// sparse_error) -> cotangents of (udf, grad, inv_s, beta, gamma).  One warp per ray; the forward
+// quantities are recomputed (cheaper than storing them); the two transmittance products are
+// differentiated with exclusive suffix sums:  d/dm_t prod_{t<i} m_t = (prod)/m_t.
+constexpr int kBwdWarps = 2;
+
+// out[t] = float( sum_{i>t} arr[i] )  in fp64
+__device__ __forceinline__ void excl_suffix_sum(const float* arr, float* out, int m, int lane) {
+  double carry = 0.0;
+  const int rows = (m + 31) / 32;
+  for (int rr = rows - 1; rr >= 0; --rr) {
+    const int i = rr * 32 + lane;
+    const double v = (i < m) ? (double)arr[i] : 0.0;
+    double inc = v;                       // inclusive suffix within the row: lane j gets sum_{l>=j}
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      int lo = __double2loint(inc), hi = __double2hiint(inc);
+      lo = __shfl_down_sync(0xffffffffu, lo, d);
+      hi = __shfl_down_sync(0xffffffffu, hi, d);
+      if (lane + d < 32) inc += __hiloint2double(hi, lo);
+    }
+    const double tot = shfl_d(inc, 0);
+    __syncwarp();
+    if (i < m) out[i] = (float)(carry + (inc - v));
+    carry += tot;
+  }
+  __syncwarp();
+}
+
+struct AlphaGrad { float d_sdf, d_itercos, d_invs; };
+
+// backward of sdf2alpha w.r.t. (sdf, iter_cos, inv_s) for upstream cotangent `da`
+__device__ __forceinline__ AlphaGrad sdf2alpha_bwd(float sdf, float iter_cos, float dists, float inv_s,
+                                                  int type, float da) {
+  AlphaGrad g = {0.f, 0.f, 0.f};
+  if (da == 0.f) return g;
+  if (type == 0) {
+    const float hstep = iter_cos * dists * 0.5f;
+    const float prv = sdf - hstep, nxt = sdf + hstep;
+    const float pc = sigmoidf_(prv * inv_s), nc = sigmoidf_(nxt * inv_s);
+    const float den = pc + 1e-5f;
+    const float a_raw = ((pc - nc) + 1e-5f) / den;
+    if (a_raw < 0.f || a_raw > 1.f) return g;
+    const float d_pc = da * nc / (den * den);
+    const float d_nc = -da / den;
+    const float sp = pc * (1.f - pc), sn = nc * (1.f - nc);
+    const float d_prv = d_pc * inv_s * sp, d_nxt = d_nc * inv_s * sn;
+    g.d_invs = d_pc * prv * sp + d_nc * nxt * sn;
+    g.d_sdf = d_prv + d_nxt;
+    g.d_itercos = (d_nxt - d_prv) * dists * 0.5f;
+  } else {
+    const float sg = sigmoidf_(sdf * inv_s);
+    const float aic = fabsf(iter_cos);
+    const float raw = aic * inv_s * (1.0f - sg);
+    if (raw <= 0.f) return g;
+    const float d_raw = da * dists * expf(-raw * dists);
+    g.d_invs = d_raw * (aic * (1.0f - sg) - aic * inv_s * sg * (1.f - sg) * sdf);
+    g.d_sdf = -d_raw * aic * inv_s * inv_s * sg * (1.f - sg);
+    const float sgn = (iter_cos > 0.f) ? 1.f : ((iter_cos < 0.f) ? -1.f : 0.f);
+    g.d_itercos = d_raw * inv_s * (1.0f - sg) * sgn;
+  }
+  return g;
+}
+
+struct CoreBwdArgs {
+  const float* rays_o; const float* rays_d; const float* mid_z; const float* dists;
+  const float* udf; const float* grad; const float* scalars; const float* reduced;
+  int B, n;
+  float cos_anneal_ratio, flip_saturation, near_surface, sparse_scale;
+  int use_unbias, use_norm_grad, alpha_type;
+  const float* d_w; const float* d_edge; const float* d_depth; const float* d_normals;   // may be NULL
+  const float* d_gerr; const float* d_gerr_ns; const float* d_sparse;                    // device scalars or NULL
+  float* d_udf; float* d_grad; double* partials;   // partials [B,3]: d_inv_s, d_beta, d_gamma
+};
+
+__global__ void __launch_bounds__(kBwdWarps * 32) render_core_bwd_kernel(const CoreBwdArgs a) {
+  __shared__ float s_tc[kBwdWarps][kMaxSamples];
+  __shared__ float s_vt[kBwdWarps][kMaxSamples];
+  __shared__ float s_V[kBwdWarps][kMaxSamples];
+  __shared__ float s_al[kBwdWarps][kMaxSamples];
+  __shared__ float s_T[kBwdWarps][kMaxSamples];
+  __shared__ float s_x[kBwdWarps][kMaxSamples];
+  __shared__ float s_y[kBwdWarps][kMaxSamples];
+  const int wib = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int ray = blockIdx.x * kBwdWarps + wib;
+  if (ray >= a.B) return;
+  float* tcs = s_tc[wib]; float* vt = s_vt[wib]; float* V = s_V[wib]; float* al = s_al[wib];
+  float* T = s_T[wib]; float* sx = s_x[wib]; float* sy = s_y[wib];
+  const int n = a.n;
+  const size_t base = (size_t)ray * n;
+  const float ox = a.rays_o[ray * 3 + 0], oy = a.rays_o[ray * 3 + 1], oz = a.rays_o[ray * 3 + 2];
+  const float dx = a.rays_d[ray * 3 + 0], dy = a.rays_d[ray * 3 + 1], dz = a.rays_d[ray * 3 + 2];
+  const float inv_s = a.scalars[0], beta = a.scalars[1], gamma = a.scalars[2];
+  const float ratio = a.cos_anneal_ratio;
+  const float de = a.d_edge ? a.d_edge[ray] : 0.f;
+  const float dd = a.d_depth ? a.d_depth[ray] : 0.f;
+  const float dn0 = a.d_normals ? a.d_normals[ray * 3 + 0] : 0.f;
+  const float dn1 = a.d_normals ? a.d_normals[ray * 3 + 1] : 0.f;
+  const float dn2 = a.d_normals ? a.d_normals[ray * 3 + 2] : 0.f;
+  const float dge = a.d_gerr ? a.d_gerr[0] / (a.reduced[3] + 1e-5f) : 0.f;
+  const float dgn = a.d_gerr_ns ? a.d_gerr_ns[0] / (a.reduced[4] + 1e-5f) : 0.f;
+  const float dsp = a.d_sparse ? a.d_sparse[0] / (float)a.B : 0.f;
+
+  // ---- recompute forward
+  for (int i = lane; i < n; i += 32) {
+    const float gx = a.grad[(base + i) * 3 + 0], gy = a.grad[(base + i) * 3 + 1], gz = a.grad[(base + i) * 3 + 2];
+    float tc = dx * gx + dy * gy + dz * gz;
+    if (a.use_norm_grad) { const float inv = sqrtf(gx * gx + gy * gy + gz * gz) + 1e-5f; tc = dx * (gx / inv) + dy * (gy / inv) + dz * (gz / inv); }
+    tcs[i] = tc;
+  }
+  __syncwarp();
+  if (a.use_unbias) {
+    for (int i = lane; i < n; i += 32) {
+      const float udf = a.udf[base + i], dist = a.dists[base + i];
+      const float ao = 1.0f - expf(-fmaxf(udf2logistic(udf, beta), 0.f) * gamma * dist);
+      const float vm = (i + 1 < n) ? ((tcs[i + 1] < 0.01f) ? 1.f : 0.f) : 1.f;
+      vt[i] = fminf(fmaxf((1.0f - ao) + a.flip_saturation * vm, 0.f), 1.f) + 1e-7f;
+    }
+    __syncwarp();
+    excl_cumprod(vt, V, n, lane);
+    for (int i = lane; i < n; i += 32) {
+      const float vp = fminf(fmaxf(V[i], 0.f), 1.f);
+      const float udf = a.udf[base + i], dist = a.dists[base + i];
+      const float nac = -1.f * fabsf(tcs[i]);
+      const float ap = sdf2alpha(udf, nac, dist, inv_s, ratio, a.alpha_type);
+      const float am = sdf2alpha(-udf, nac, dist, inv_s, ratio, a.alpha_type);
+      al[i] = ap * vp + am * (1.0f - vp);
+    }
+  } else {
+    for (int i = lane; i < n; i += 32) {
+      const float udf = a.udf[base + i], dist = a.dists[base + i];
+      al[i] = 1.0f - expf(-fmaxf(udf2logistic(udf, beta), 0.f) * gamma * dist);
+    }
+  }
+  __syncwarp();
+  for (int i = lane; i < n; i += 32) sx[i] = (1.0f - al[i]) + 1e-7f;     // m_i
+  __syncwarp();
+  excl_cumprod(sx, T, n, lane);
+
+  // ---- d alpha:  Wbar_i T_i  -  (sum_{j>i} Wbar_j alpha_j T_j) / m_i
+  for (int i = lane; i < n; i += 32) {
+    const float gx = a.grad[(base + i) * 3 + 0], gy = a.grad[(base + i) * 3 + 1], gz = a.grad[(base + i) * 3 + 2];
+    float flip = 1.f;
+    if (a.use_unbias) {
+      const float inv = sqrtf(gx * gx + gy * gy + gz * gz) + 1e-5f;
+      const float cosn = dx * (gx / inv) + dy * (gy / inv) + dz * (gz / inv);
+      flip = (cosn > 0.f) ? -1.f : 1.f;
+    }
+    const float wbar = (a.d_w ? a.d_w[base + i] : 0.f) + de + a.mid_z[base + i] * dd +
+                       flip * (gx * dn0 + gy * dn1 + gz * dn2);
+    sy[i] = wbar;                              // keep Wbar
+    V[i] = V[i];                               // (V stays)
+    vt[i] = vt[i];
+    // product term for the suffix sum
+    al[i] = al[i];
+  }
+  __syncwarp();
+  // suffix over Wbar_j * alpha_j * T_j  -> reuse sx as input (m_i is recomputed from alpha below)
+  for (int i = lane; i < n; i += 32) sx[i] = sy[i] * al[i] * T[i];
+  __syncwarp();
+  excl_suffix_sum(sx, sx, n, lane);            // sx[i] = R_i
+  double p_s = 0.0, p_b = 0.0, p_g = 0.0;
+  // d_alpha into sy
+  for (int i = lane; i < n; i += 32) {
+    const float m_i = (1.0f - al[i]) + 1e-7f;
+    sy[i] = sy[i] * T[i] - sx[i] / m_i;
+  }
+  __syncwarp();
+
+  if (a.use_unbias) {
+    // d vp_i = d_alpha_i (ap - am);  through clip and the vis product
+    for (int i = lane; i < n; i += 32) {
+      const float udf = a.udf[base + i], dist = a.dists[base + i];
+      const float nac = -1.f * fabsf(tcs[i]);
+      const float ap = sdf2alpha(udf, nac, dist, inv_s, ratio, a.alpha_type);
+      const float am = sdf2alpha(-udf, nac, dist, inv_s, ratio, a.alpha_type);
+      const float Vi = V[i];
+      const float dV = (Vi >= 0.f && Vi <= 1.f) ? sy[i] * (ap - am) : 0.f;
+      sx[i] = dV * Vi;
+    }
+    __syncwarp();
+    excl_suffix_sum(sx, sx, n, lane);          // sx[t] = sum_{i>t} dV_i V_i
+  }
+  __syncwarp();
+
+  for (int i = lane; i < n; i += 32) {
+    const float udf = a.udf[base + i], dist = a.dists[base + i], mz = a.mid_z[base + i];
+    const float gx = a.grad[(base + i) * 3 + 0], gy = a.grad[(base + i) * 3 + 1], gz = a.grad[(base + i) * 3 + 2];
+    const float mag = sqrtf(gx * gx + gy * gy + gz * gz);
+    float du = 0.f, dgx = 0.f, dgy = 0.f, dgz = 0.f;
+    const float dal = sy[i];
+    // logistic density pieces
+    const float ex = expf(-beta * udf);
+    const float opl = 1.0f + ex;
+    const float raw = beta * ex / (opl * opl);
+    const float E = expf(-raw * gamma * dist);
+    const float fprime = (1.0f - ex) / (opl * opl * opl);          // d/dy [y/(1+y)^2]
+    const float draw_du = -beta * beta * ex * fprime;
+    const float draw_db = ex / (opl * opl) - beta * udf * ex * fprime;
+    float d_ao = 0.f;
+    float d_tc = 0.f;
+    if (a.use_unbias) {
+      const float q = (1.0f - (1.0f - E)) + a.flip_saturation * ((i + 1 < n) ? ((tcs[i + 1] < 0.01f) ? 1.f : 0.f) : 1.f);
+      const float d_vt = sx[i] / vt[i];
+      const float d_q = (q >= 0.f && q <= 1.f) ? d_vt : 0.f;
+      d_ao = -d_q;
+      const float vp = fminf(fmaxf(V[i], 0.f), 1.f);
+      const float tc = tcs[i];
+      const float nac = -1.f * fabsf(tc);
+      float iter_cos = nac, dic_dnac = 1.f;
+      if (ratio >= 0.f) {
+        const float r1 = -nac * 0.5f + 0.5f, r2 = -nac;
+        iter_cos = -(fmaxf(r1, 0.f) * (1.0f - ratio) + fmaxf(r2, 0.f) * ratio);
+        dic_dnac = ((r1 > 0.f) ? 0.5f * (1.0f - ratio) : 0.f) + ((r2 > 0.f) ? ratio : 0.f);
+      }
+      const AlphaGrad gp = sdf2alpha_bwd(udf, iter_cos, dist, inv_s, a.alpha_type, dal * vp);
+      const AlphaGrad gm = sdf2alpha_bwd(-udf, iter_cos, dist, inv_s, a.alpha_type, dal * (1.0f - vp));
+      du += gp.d_sdf - gm.d_sdf;
+      p_s += (double)(gp.d_invs + gm.d_invs);
+      const float d_nac = (gp.d_itercos + gm.d_itercos) * dic_dnac;
+      const float sgn = (tc > 0.f) ? 1.f : ((tc < 0.f) ? -1.f : 0.f);
+      d_tc = -d_nac * sgn;
+    } else {
+      d_ao = dal;
+    }
+    // ao = 1 - exp(-raw*gamma*dist)
+    const float d_raw = d_ao * gamma * dist * E;
+    p_g += (double)(d_ao * raw * dist * E);
+    du += d_raw * draw_du;
+    p_b += (double)(d_raw * draw_db);
+    // true_cos -> grad
+    if (d_tc != 0.f) {
+      if (a.use_norm_grad) {
+        const float inv = mag + 1e-5f;
+        const float dot = dx * gx + dy * gy + dz * gz;
+        const float k = (mag > 0.f) ? dot / (mag * inv * inv) : 0.f;
+        dgx += d_tc * (dx / inv - k * gx); dgy += d_tc * (dy / inv - k * gy); dgz += d_tc * (dz / inv - k * gz);
+      } else {
+        dgx += d_tc * dx; dgy += d_tc * dy; dgz += d_tc * dz;
+      }
+    }
+    // normals = sum flip*g*w
+    {
+      float flip = 1.f;
+      if (a.use_unbias) {
+        const float inv = mag + 1e-5f;
+        const float cosn = dx * (gx / inv) + dy * (gy / inv) + dz * (gz / inv);
+        flip = (cosn > 0.f) ? -1.f : 1.f;
+      }
+      const float w = al[i] * T[i];
+      dgx += flip * w * dn0; dgy += flip * w * dn1; dgz += flip * w * dn2;
+    }
+    // eikonal terms
+    {
+      const float px = ox + dx * mz, py = oy + dy * mz, pz = oz + dz * mz;
+      const float pn = sqrtf(px * px + py * py + pz * pz);
+      const float relax = (pn < 2.4f) ? 1.f : 0.f;
+      const float near = (udf < a.near_surface) ? 1.f : 0.f;
+      const float coef = (dge * relax + dgn * near) * 2.0f * (mag - 1.0f);
+      if (mag > 0.f) { dgx += coef * gx / mag; dgy += coef * gy / mag; dgz += coef * gz / mag; }
+    }
+    if (dsp != 0.f) du += dsp * (-a.sparse_scale) * expf(-a.sparse_scale * udf);
+    a.d_udf[base + i] = du;
+    a.d_grad[(base + i) * 3 + 0] = dgx; a.d_grad[(base + i) * 3 + 1] = dgy; a.d_grad[(base + i) * 3 + 2] = dgz;
+  }
+  p_s = warp_sum_d(p_s); p_b = warp_sum_d(p_b); p_g = warp_sum_d(p_g);
+  if (lane == 0) { a.partials[(size_t)ray * 3 + 0] = p_s; a.partials[(size_t)ray * 3 + 1] = p_b; a.partials[(size_t)ray * 3 + 2] = p_g; }
+}
+
+__global__ void scalar_reduce_kernel(const double* __restrict__ partials, int B, int ncol, float* __restrict__ out) {
+  __shared__ double sh[8][32];
+  double acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  for (int r = threadIdx.x; r < B; r += blockDim.x)
+    for (int c = 0; c < ncol; ++c) acc[c] += partials[(size_t)r * ncol + c];
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  for (int c = 0; c < ncol; ++c) { acc[c] = warp_sum_d(acc[c]); if (lane == 0) sh[c][w] = acc[c]; }
+  __syncthreads();
+  if (threadIdx.x < ncol) {
+    double t = 0;
+    for (int i = 0; i < (int)(blockDim.x >> 5); ++i) t += sh[threadIdx.x][i];
+    out[threadIdx.x] = (float)t;
+  }
+}
+
 }  // namespace emap
 
 using namespace emap;
@@ -506,6 +792,35 @@ extern "C" int emap_render_core_fwd(const float* rays_o, const float* rays_d, co
   render_core_fwd_kernel<<<(B + kRayWarps - 1) / kRayWarps, kRayWarps * 32, 0, st>>>(a);
   EMAP_CUDA(cudaGetLastError());
   render_reduce_kernel<<<1, 1024, 0, st>>>(partials, B, reduced);
+  EMAP_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int emap_render_core_bwd(const float* rays_o, const float* rays_d, const float* mid_z,
+                                    const float* dists, const float* udf, const float* grad,
+                                    const float* scalars, const float* reduced, int32_t B, int32_t n,
+                                    float cos_anneal_ratio, float flip_saturation, float near_surface,
+                                    float sparse_scale, int32_t use_unbias, int32_t use_norm_grad,
+                                    int32_t alpha_type, const float* d_weights, const float* d_edge,
+                                    const float* d_depth, const float* d_normals, const float* d_gerr,
+                                    const float* d_gerr_ns, const float* d_sparse, float* d_udf,
+                                    float* d_grad, double* partials, float* d_scalars, void* stream) {
+  if (!rays_o || !rays_d || !mid_z || !dists || !udf || !grad || !scalars || !reduced || !d_udf ||
+      !d_grad || !partials || !d_scalars)
+    return set_error("emap_render_core_bwd: NULL pointer");
+  if (B <= 0 || n <= 0 || n > kMaxSamples) return set_error("emap_render_core_bwd: bad sizes");
+  CoreBwdArgs a;
+  a.rays_o = rays_o; a.rays_d = rays_d; a.mid_z = mid_z; a.dists = dists; a.udf = udf; a.grad = grad;
+  a.scalars = scalars; a.reduced = reduced; a.B = B; a.n = n; a.cos_anneal_ratio = cos_anneal_ratio;
+  a.flip_saturation = flip_saturation; a.near_surface = near_surface; a.sparse_scale = sparse_scale;
+  a.use_unbias = use_unbias; a.use_norm_grad = use_norm_grad; a.alpha_type = alpha_type;
+  a.d_w = d_weights; a.d_edge = d_edge; a.d_depth = d_depth; a.d_normals = d_normals;
+  a.d_gerr = d_gerr; a.d_gerr_ns = d_gerr_ns; a.d_sparse = d_sparse;
+  a.d_udf = d_udf; a.d_grad = d_grad; a.partials = partials;
+  cudaStream_t st = (cudaStream_t)stream;
+  render_core_bwd_kernel<<<(B + kBwdWarps - 1) / kBwdWarps, kBwdWarps * 32, 0, st>>>(a);
+  EMAP_CUDA(cudaGetLastError());
+  scalar_reduce_kernel<<<1, 1024, 0, st>>>(partials, B, 3, d_scalars);
   EMAP_CUDA(cudaGetLastError());
   return 0;
 }

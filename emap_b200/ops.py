@@ -193,3 +193,24 @@ def render_core_fwd(rays_o, rays_d, mid_z, dists, udf, grad, scalars, B, n, cfg,
         C.ptr(grad_mag), C.ptr(edge), C.ptr(depth), C.ptr(normals), C.ptr(partials), C.ptr(reduced),
         C.stream()))
     return weights, alpha, grad_flip, inside, grad_mag, edge, depth, normals, reduced
+
+
+def _opt(t):
+    return None if t is None else C.f32(t)
+
+
+def render_core_bwd(rays_o, rays_d, mid_z, dists, udf, grad, scalars, reduced, B, n, cfg, d_w, d_edge,
+                    d_depth, d_normals, d_gerr, d_gerr_ns, d_sparse):
+    dev = mid_z.device
+    d_udf = torch.empty(B * n, dtype=torch.float32, device=dev)
+    d_grad = torch.empty(B * n, 3, dtype=torch.float32, device=dev)
+    partials = torch.empty(B, 3, dtype=torch.float64, device=dev)
+    d_scalars = torch.empty(3, dtype=torch.float32, device=dev)
+    C.check(C.lib().emap_render_core_bwd(
+        C.ptr(rays_o), C.ptr(rays_d), C.ptr(mid_z), C.ptr(dists), C.ptr(C.f32(udf)), C.ptr(C.f32(grad)),
+        C.ptr(C.f32(scalars)), C.ptr(reduced), B, n, cfg["cos_anneal_ratio"], cfg["flip_saturation"],
+        cfg["near_surface"], cfg["sparse_scale"], cfg["use_unbias"], cfg["use_norm_grad"],
+        cfg["alpha_type"], C.ptr(_opt(d_w)), C.ptr(_opt(d_edge)), C.ptr(_opt(d_depth)),
+        C.ptr(_opt(d_normals)), C.ptr(_opt(d_gerr)), C.ptr(_opt(d_gerr_ns)), C.ptr(_opt(d_sparse)),
+        C.ptr(d_udf), C.ptr(d_grad), C.ptr(partials), C.ptr(d_scalars), C.stream()))
+    return d_udf, d_grad, d_scalars

@@ -110,6 +110,21 @@ int emap_render_core_fwd(const float* rays_o, const float* rays_d, const float* 
                          float* grad_mag, float* edge, float* depth, float* normals,
                          double* partials, float* reduced, void* stream);
 
+/* backward of emap_render_core_fwd: cotangents (any may be NULL = zero) of weights[B,n], edge[B],
+ * depth[B], normals[B,3] and of the three scalar reductions (device scalars) -> d_udf[B*n],
+ * d_grad[B*n,3], d_scalars[3] = d/d(inv_s, beta, gamma).  `reduced` is the forward's output (its
+ * mask sums are the denominators of the eikonal terms).  partials: fp64 scratch [B,3].
+ * replaces: autograd through udf_renderer_blending.py:463-650.                                    */
+int emap_render_core_bwd(const float* rays_o, const float* rays_d, const float* mid_z,
+                         const float* dists, const float* udf, const float* grad,
+                         const float* scalars, const float* reduced, int32_t B, int32_t n,
+                         float cos_anneal_ratio, float flip_saturation, float near_surface,
+                         float sparse_scale, int32_t use_unbias, int32_t use_norm_grad,
+                         int32_t alpha_type, const float* d_weights, const float* d_edge,
+                         const float* d_depth, const float* d_normals, const float* d_gerr,
+                         const float* d_gerr_ns, const float* d_sparse, float* d_udf, float* d_grad,
+                         double* partials, float* d_scalars, void* stream);
+
 /* ---- misc ------------------------------------------------------------------------------------ */
 /* options: "cluster" = 1|2|4 : width of the weight-stream multicast cluster of the MLP kernels.  */
 int emap_set_option(const char* name, int value);

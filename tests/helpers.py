@@ -17,7 +17,7 @@ def oracle_scalars() -> O.ScalarParams:
 
 
 def maxdiff(a: torch.Tensor, b: torch.Tensor) -> float:
-    return float((a.double() - b.double()).abs().max())
+    return float((a.detach().double() - b.detach().double()).abs().max())
 
 
 def relerr(a: torch.Tensor, b: torch.Tensor) -> float:
