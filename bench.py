@@ -1,0 +1,387 @@
+#!/usr/bin/env python
+"""bench.py -- ray-samples/s through the full UDF render path (BASELINE.json metric).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--mode infer|train]
+                  [--precision fp32|fp16|bf16]
+
+A "step" is one pass of the hot path over one batch of synthetic rays per GPU:
+  infer : UDFRendererBlending.render()  (coarse z -> 4 up-sampling rounds -> render_core)
+  train : render() + loss + backward (all 462,985 parameter gradients) + one flat NCCL allreduce
+          + Adam step     (default as soon as the backward kernels are present)
+Workload (config.workload): BASELINE.json configs[3] / north_star target -- 4096 rays x 256 samples
+(n_samples=128 + n_importance=128 in 4 up-sampling steps) per GPU, rays sharded across ranks with no
+data-path collective in the forward (weak scaling), synthetic random cameras.
+
+One JSON line on rank 0.  `value` = whole-job ray-samples/s with inputs resident in HBM (CUDA events,
+max over ranks, L2 flushed between steps); `e2e` = same through the public API with pinned HOST
+inputs, H2D and D2H inside the timed region; `roofline` = the dominant kernel (fused MLP
+forward+gradient) timed alone, algorithmic FLOPs / measured duration vs the measured bf16 GEMM peak;
+`cpu_baseline` = the CPU oracle (port of the reference, torch CPU fp32, all host threads) on a
+bounded sample of the same workload.  `--impl reference` prints the CPU arm as the headline.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+F_FWD = 918016.0                      # FLOP of one MLP forward per point
+N0, NI, STEPS = 128, 128, 4           # 256 samples per ray
+RAYS_PER_GPU = 4096
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return d, "measured"
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0}, "fallback"
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+
+    def __init__(self, index=0):
+        super().__init__(daemon=True)
+        self.index = index
+        self.rows = []
+        self.proc = None
+
+    def run(self):
+        q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+             "clocks_event_reasons.sw_power_cap")
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits",
+                                          "-i", str(self.index), "-lms", "100"], stdout=subprocess.PIPE,
+                                         text=True)
+            for line in self.proc.stdout:
+                self.rows.append([x.strip() for x in line.split(",")])
+        except Exception:
+            pass
+
+    def stop(self):
+        if self.proc:
+            self.proc.terminate()
+        rows = [r for r in self.rows if len(r) >= 7]
+        if not rows:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unavailable"]}
+        sm = sorted(float(r[0]) for r in rows if r[0].replace(".", "").isdigit())
+        reasons = []
+        for i, name in ((3, "hw_slowdown"), (4, "hw_thermal_slowdown"), (5, "sw_thermal_slowdown"),
+                        (6, "sw_power_cap")):
+            if any(r[i].lower().startswith("active") for r in rows):
+                reasons.append(name)
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": float(rows[0][1]),
+                "reasons": reasons, "samples": len(rows)}
+
+
+def synthetic_problem(B, seed_offset=0):
+    from oracle import emap_oracle as O   # input generator only (shared with the tests)
+    o, d = O.synthetic_rays(B, seed=1234 + seed_offset)
+    near, far = torch.full((B, 1), 0.05), torch.full((B, 1), 6.0)
+    return o, d, near, far, torch.ones(B, 1)
+
+
+def build_ours(dev, precision):
+    from emap_b200.udf_model import BetaNetwork, SingleVarianceNetwork, UDFNetwork
+    from emap_b200.udf_renderer_blending import UDFRendererBlending
+    from oracle import emap_oracle as O
+    torch.manual_seed(0)
+    net = UDFNetwork(d_in=3, d_out=1, d_hidden=256, n_layers=8, skip_in=[4], multires=10, bias=0.5,
+                     scale=1.0, geometric_init=True, weight_norm=True, udf_type="abs", precision=precision)
+    # second weight set of SURVEY §8d (geometric init + 1/f noise): exercises every PE column
+    p2 = O.perturbed_params(O.UDFParams.from_state_dict(net.state_dict()))
+    sd = net.state_dict()
+    for l in range(9):
+        sd[f"lin{l}.parametrizations.weight.original1"] = p2.v[l]
+        sd[f"lin{l}.parametrizations.weight.original0"] = p2.g[l]
+        sd[f"lin{l}.bias"] = p2.b[l]
+    net.load_state_dict(sd)
+    net = net.to(dev)
+    var = SingleVarianceNetwork(0.3).to(dev)
+    beta = BetaNetwork(0.5, 0.3, 0.3, 5e-5, True, True, False).to(dev)
+    r = UDFRendererBlending(None, net, var, beta, n_samples=N0, n_importance=NI, n_outside=0,
+                            up_sample_steps=STEPS, perturb=1.0, device=dev)
+    return net, var, beta, r
+
+
+def oracle_step_fn(mode, B):
+    """CPU oracle (port of the reference) on B rays of the same workload; returns a callable."""
+    from oracle import emap_oracle as O
+    p = O.perturbed_params(O.geometric_init(generator=torch.Generator().manual_seed(0)))
+    s = O.ScalarParams(torch.tensor([0.3]), torch.tensor([0.5]), torch.tensor([0.3]))
+    cfg = O.RenderConfig(n_samples=N0, n_importance=NI, up_sample_steps=STEPS)
+    o, d, near, far, ds = synthetic_problem(B)
+    t_rand = O.synthetic_t_rand(B)
+    true_edge = torch.rand(B, 1, generator=torch.Generator().manual_seed(21))
+    if mode == "train":
+        p.requires_grad_(True)
+        for t in (s.variance, s.beta, s.gamma):
+            t.requires_grad_(True)
+
+    def step():
+        out = O.render(p, s, cfg, o, d, near, far, ds, cos_anneal_ratio=1.0, flip_saturation=0.9,
+                       t_rand=t_rand)
+        if mode == "train":
+            loss = (torch.nn.functional.mse_loss(out["edge"], true_edge)
+                    + 0.01 * out["gradient_error_near_surface"] + 0.1 * out["gradient_error"])
+            torch.autograd.grad(loss, p.tensors() + [s.variance, s.beta, s.gamma])
+        else:
+            with torch.no_grad():
+                pass
+        return out["edge"]
+
+    if mode != "train":
+        inner = step
+
+        def step():  # noqa: F811
+            with torch.no_grad():
+                return inner()
+    return step
+
+
+def cpu_baseline(mode, sample_rays=1024, reps=2):
+    step = oracle_step_fn(mode, sample_rays)
+    step()                                     # warm-up
+    t0 = time.perf_counter()
+    for _ in range(reps):
+        step()
+    dt = (time.perf_counter() - t0) / reps
+    n = N0 + NI
+    return {"value": sample_rays * n / dt, "unit": "ray-samples/s", "cores": torch.get_num_threads(),
+            "kind": "port", "sample": f"{sample_rays} rays x {n} samples of the same workload, "
+            f"{mode}, torch CPU fp32 oracle (port of the reference), {reps} rep(s), {dt:.2f} s each"}
+
+
+def run_reference(args, rank, world):
+    """--impl reference: the reference's CPU implementation of the path (oracle port), rank 0 only."""
+    if rank != 0:
+        return
+    step = oracle_step_fn(args.mode, args.ref_rays)
+    for _ in range(max(1, min(args.warmup, 1))):
+        step()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        step()
+    dt = (time.perf_counter() - t0) / args.steps
+    n = N0 + NI
+    val = args.ref_rays * n / dt
+    line = {
+        "impl": "reference", "metric": "ray-samples/s through UDF render path", "value": val,
+        "unit": "ray-samples/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"replica-style synthetic cameras, {RAYS_PER_GPU} rays x {n} samples "
+                               f"({N0}+{NI}/{STEPS} hierarchical) per GPU, {args.mode}",
+                   "step_sample": f"{args.ref_rays} rays x {n} samples per step (bounded CPU sample)"},
+        "cpu_baseline": {"value": val, "unit": "ray-samples/s", "cores": torch.get_num_threads(),
+                         "kind": "port", "sample": f"{args.ref_rays} rays x {n} samples per step"},
+        "e2e": {"value": val, "unit": "ray-samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--mode", default=None, choices=["infer", "train"])
+    ap.add_argument("--precision", default="fp32", choices=["fp32", "fp16", "bf16"])
+    ap.add_argument("--rays", type=int, default=RAYS_PER_GPU)
+    ap.add_argument("--ref-rays", type=int, default=512)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+
+    rank = int(os.environ.get("RANK", 0))
+    local = int(os.environ.get("LOCAL_RANK", 0))
+    world = int(os.environ.get("WORLD_SIZE", 1))
+
+    from emap_b200 import ops
+    have_bwd = hasattr(ops, "udf_backward")
+    if args.mode is None:
+        args.mode = "train" if have_bwd else "infer"
+
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+
+    if args.mode == "train" and not have_bwd:
+        raise SystemExit("train mode needs the backward kernels (ops.udf_backward)")
+    assert torch.cuda.is_available(), "bench.py --impl ours needs a GPU (no CPU fallback)"
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=dev)
+
+    from emap_b200 import _cabi as C
+    net, var, beta, r = build_ours(dev, args.precision)
+    B, n = args.rays, N0 + NI
+    o, d, near, far, ds = synthetic_problem(B, seed_offset=rank)
+    o_d, d_d, ds_d = o.to(dev), d.to(dev), ds.to(dev)
+    true_edge = torch.rand(B, 1, generator=torch.Generator().manual_seed(21 + rank)).to(dev)
+    near_f, far_f = 0.05, 6.0
+    opt = None
+    if args.mode == "train":
+        from emap_b200.parallel import FlatGradAllReduce
+        params = list(net.parameters()) + list(var.parameters()) + list(beta.parameters())
+        opt = torch.optim.Adam([{"params": list(net.parameters()), "lr": 1e-4},
+                                {"params": list(var.parameters()) + list(beta.parameters())}], lr=5e-4)
+        reducer = FlatGradAllReduce(params)
+
+    def step_device():
+        if args.mode == "infer":
+            with torch.no_grad():
+                out = r.render(o_d, d_d, near_f, far_f, ds_d, cos_anneal_ratio=1.0, flip_saturation=0.9)
+            return out["edge"]
+        out = r.render(o_d, d_d, near_f, far_f, ds_d, cos_anneal_ratio=1.0, flip_saturation=0.9)
+        loss = (torch.nn.functional.mse_loss(out["edge"], true_edge)
+                + 0.01 * out["gradient_error_near_surface"] + 0.1 * out["gradient_error"])
+        opt.zero_grad(set_to_none=True)
+        loss.backward()
+        reducer.allreduce_()
+        opt.step()
+        return loss
+
+    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)   # > 126 MB L2
+
+    def barrier():
+        if world > 1:
+            torch.distributed.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        step_device()
+    barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    C.launch_count = 0
+    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+           for _ in range(args.steps)]
+    barrier()
+    for s0, s1 in evs:
+        flush.fill_(1)                      # L2 flush between timed iterations (not timed)
+        s0.record()
+        step_device()
+        s1.record()
+    barrier()
+    launches = C.launch_count // args.steps
+    clocks = sampler.stop() if rank == 0 else None
+    ms = sum(a.elapsed_time(b) for a, b in evs) / args.steps
+    t = torch.tensor([ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
+    ms = float(t)
+    value = world * B * n / (ms * 1e-3)
+
+    # ---- e2e through the public API with pinned host inputs (H2D + D2H inside the timed region)
+    o_h, d_h, ds_h = o.pin_memory(), d.pin_memory(), ds.pin_memory()
+    te_h = true_edge.cpu().pin_memory()
+    res_h = torch.empty(B, 1).pin_memory()
+
+    def step_e2e():
+        oo, dd = o_h.to(dev, non_blocking=True), d_h.to(dev, non_blocking=True)
+        sc = ds_h.to(dev, non_blocking=True)
+        if args.mode == "infer":
+            with torch.no_grad():
+                out = r.render(oo, dd, near_f, far_f, sc, cos_anneal_ratio=1.0, flip_saturation=0.9)
+            res_h.copy_(out["edge"], non_blocking=True)
+        else:
+            te = te_h.to(dev, non_blocking=True)
+            out = r.render(oo, dd, near_f, far_f, sc, cos_anneal_ratio=1.0, flip_saturation=0.9)
+            loss = (torch.nn.functional.mse_loss(out["edge"], te)
+                    + 0.01 * out["gradient_error_near_surface"] + 0.1 * out["gradient_error"])
+            opt.zero_grad(set_to_none=True)
+            loss.backward()
+            reducer.allreduce_()
+            opt.step()
+            res_h[:1].copy_(loss.detach().reshape(1, 1), non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+
+    for _ in range(2):
+        step_e2e()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        step_e2e()
+    barrier()
+    e2e_ms = (time.perf_counter() - t0) / args.steps * 1e3
+    t = torch.tensor([e2e_ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
+    e2e_ms = float(t)
+    h2d = (o_h.numel() + d_h.numel() + ds_h.numel()) * 4 + (te_h.numel() * 4 if args.mode == "train" else 0)
+    d2h = B * 4 if args.mode == "infer" else 4
+
+    if rank == 0:
+        # ---- roofline of the dominant kernel: fused MLP forward+gradient on the B*n core points
+        pk, pk_src = peaks()
+        with torch.no_grad():
+            out = r.render(o_d, d_d, near_f, far_f, ds_d, cos_anneal_ratio=1.0, flip_saturation=0.9)
+        mid = out["mid_z_vals"].contiguous()
+        pn = net.packed()
+        reps = 5
+        kev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(reps)]
+        for _ in range(2):
+            ops.udf_forward_grad(pn, net.prec_code, rays_o=o_d, rays_d=d_d, z=mid)
+        for a0, a1 in kev:
+            flush.fill_(1)
+            a0.record()
+            ops.udf_forward_grad(pn, net.prec_code, rays_o=o_d, rays_d=d_d, z=mid)
+            a1.record()
+        torch.cuda.synchronize()
+        k_ms = sum(a.elapsed_time(b) for a, b in kev) / reps
+        P = B * n
+        alg_flop = 2.0 * F_FWD * P                       # forward + reverse-mode d/dx
+        nterms = 3 if args.precision == "fp32" else 1
+        exe_flop = 4.0 * F_FWD * P * nterms              # forward-mode: 4 rows per point, x MMA terms
+        achieved = alg_flop / (k_ms * 1e-3) / 1e12
+        roof = {"bound": "tensor", "kernel": "mlp_kernel<MODE_GRAD> (emap_udf_forward_grad)",
+                "achieved": achieved, "peak": pk["bf16_tflops"], "unit": "TFLOP/s",
+                "frac": achieved / pk["bf16_tflops"], "traffic": None, "peak_source": pk_src + " burst bf16",
+                "ms_per_launch": k_ms, "points_per_launch": P,
+                "algorithmic_flop_per_point": 2.0 * F_FWD,
+                "executed_tflops": exe_flop / (k_ms * 1e-3) / 1e12,
+                "note": "algorithmic = 2F/point (fwd + reverse-mode grad); the kernel executes forward-mode "
+                        "(4 rows/point) and, in fp32 mode, 3 split-fp16 MMAs per product"}
+        cpu = None if args.no_cpu_baseline else cpu_baseline(args.mode)
+        line = {
+            "metric": "ray-samples/s through UDF render path", "value": value, "unit": "ray-samples/s",
+            "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": {"fp32": "f32 (3x split-fp16 tcgen05 MMA, fp32 accumulate)", "fp16": "f16",
+                      "bf16": "bf16"}[args.precision],
+            "data": "synthetic",
+            "config": {"workload": f"replica-style synthetic cameras, {B} rays x {n} samples "
+                                   f"({N0}+{NI}/{STEPS} hierarchical) per GPU, {args.mode}",
+                       "mode": args.mode, "rays_per_gpu": B, "samples_per_ray": n,
+                       "parallelism": f"rays sharded x{world}" + (", flat grad allreduce" if args.mode == "train" else ""),
+                       "l2": "flushed (256 MiB write) between timed steps"},
+            "clocks": clocks,
+            "e2e": {"value": world * B * n / (e2e_ms * 1e-3), "unit": "ray-samples/s",
+                    "ms_per_step": e2e_ms, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
+            "gpu_launches": launches,
+            "roofline": roof,
+            "cpu_baseline": cpu,
+        }
+        print(json.dumps(line))
+    if world > 1:
+        torch.distributed.barrier()
+        torch.distributed.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

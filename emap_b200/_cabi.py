@@ -28,7 +28,7 @@ class NetDesc(ctypes.Structure):
 
 UDF_TYPES = {"abs": 0, "square": 1, "sdf": 2}
 
-_lib: Optional[ctypes.CDLL] = None
+_lib = None
 
 _vp, _i32, _i64, _f32 = ctypes.c_void_p, ctypes.c_int32, ctypes.c_int64, ctypes.c_float
 _nd = ctypes.POINTER(NetDesc)
@@ -57,7 +57,39 @@ SIGNATURES = {
 }
 
 
-def lib() -> ctypes.CDLL:
+# kernel launches issued by each entry point (for bench.py's `gpu_launches` claim)
+LAUNCHES_PER_CALL = {
+    "emap_wn_fold": 2, "emap_udf_forward": 1, "emap_udf_forward_grad": 1, "emap_debug_mlp": 1,
+    "emap_coarse_z": 1, "emap_upsample_step": 1, "emap_render_prep": 1, "emap_render_core_fwd": 2,
+    "emap_render_core_bwd": 2, "emap_udf_backward": 0,
+}
+launch_count = 0
+
+
+class _Counting:
+    """Proxy over the CDLL that counts kernel launches per C-ABI call."""
+
+    def __init__(self, cdll):
+        self._cdll = cdll
+        self._cache = {}
+
+    def __getattr__(self, name):
+        fn = self._cache.get(name)
+        if fn is None:
+            raw = getattr(self._cdll, name)
+            k = LAUNCHES_PER_CALL.get(name, 0)
+            if k:
+                def fn(*args, _raw=raw, _k=k):
+                    global launch_count
+                    launch_count += _k
+                    return _raw(*args)
+            else:
+                fn = raw
+            self._cache[name] = fn
+        return fn
+
+
+def lib():
     global _lib
     if _lib is None:
         if not os.path.exists(LIB_PATH):
@@ -71,7 +103,7 @@ def lib() -> ctypes.CDLL:
             fn.argtypes = args
         if L.emap_abi_version() != 1:
             raise RuntimeError("emap_b200: ABI version mismatch between _cabi.py and the library")
-        _lib = L
+        _lib = _Counting(L)
     return _lib
 
 
