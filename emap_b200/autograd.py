@@ -40,8 +40,9 @@ class _UDFForward(torch.autograd.Function):
     def backward(ctx, d_udf, *unused):
         module = ctx.module
         x, ro, rd, z = ctx.pts
-        flat_grad = ops.udf_backward(module.packed(), module.prec_code, d_udf.contiguous(), None,
-                                     pts=x, rays_o=ro, rays_d=rd, z=z)
+        net = module.packed()
+        flat_grad = ops.udf_backward(net, module.prec_code, d_udf.contiguous(), None,
+                                     pts=x, rays_o=ro, rays_d=rd, z=z, flat_params=net.flat)
         grads = _split_flat(flat_grad, module.flat_param_list())
         return (None, None, None, None, None, None, *grads)
 
@@ -59,10 +60,11 @@ class _UDFForwardGrad(torch.autograd.Function):
     def backward(ctx, d_udf, d_grad):
         module = ctx.module
         x, ro, rd, z = ctx.pts
-        flat_grad = ops.udf_backward(module.packed(), module.prec_code,
+        net = module.packed()
+        flat_grad = ops.udf_backward(net, module.prec_code,
                                      None if d_udf is None else d_udf.contiguous(),
                                      None if d_grad is None else d_grad.contiguous(),
-                                     pts=x, rays_o=ro, rays_d=rd, z=z)
+                                     pts=x, rays_o=ro, rays_d=rd, z=z, flat_params=net.flat)
         grads = _split_flat(flat_grad, module.flat_param_list())
         return (None, None, None, None, None, *grads)
 

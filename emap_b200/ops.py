@@ -214,3 +214,100 @@ def render_core_bwd(rays_o, rays_d, mid_z, dists, udf, grad, scalars, reduced, B
         C.ptr(_opt(d_normals)), C.ptr(_opt(d_gerr)), C.ptr(_opt(d_gerr_ns)), C.ptr(_opt(d_sparse)),
         C.ptr(d_udf), C.ptr(d_grad), C.ptr(partials), C.ptr(d_scalars), C.stream()))
     return d_udf, d_grad, d_scalars
+
+
+# ----------------------------------------------------------------------------- K1b backward
+def _weff_views(net: PackedNet):
+    """fp32 views of W_eff (layer 0..8) inside the packed buffer + cached fp16 GEMM operands."""
+    if getattr(net, "_offsets", None) is None:
+        arr = (ctypes.c_uint32 * 10)()
+        C.check(C.lib().emap_packed_offsets(ctypes.byref(net.desc), arr))
+        net._offsets = list(arr)
+    in_dim, out_dim = net_dims(net.multires)
+    W = []
+    for l in range(9):
+        off = net._offsets[1 + l]
+        n = in_dim[l] * out_dim[l]
+        W.append(net.packed[off:off + 4 * n].view(torch.float32).view(out_dim[l], in_dim[l]))
+    return W, in_dim, out_dim
+
+
+def _half_weights(net: PackedNet, fold_id):
+    """fp16 copies of W_eff for the library GEMMs of the backward (re-made after each fold):
+    layer 0 padded to K=64, layer 3 padded to 256 rows, layer 4 carries the skip 1/sqrt(2)."""
+    if getattr(net, "_wh_id", None) == fold_id and getattr(net, "_wh", None) is not None:
+        return net._wh
+    W, in_dim, out_dim = _weff_views(net)
+    dev = net.packed.device
+    wh = []
+    for l in range(8):
+        w = W[l]
+        if l == 4:
+            w = w * (1.0 / (2.0 ** 0.5))
+        k = 64 if l == 0 else 256
+        t = torch.zeros(256, k, dtype=torch.float16, device=dev)
+        t[:out_dim[l], :in_dim[l]] = w.to(torch.float16)
+        wh.append(t)
+    net._wh, net._wh_id = wh, fold_id
+    return wh
+
+
+def udf_backward(net: PackedNet, precision: int, d_udf: Optional[torch.Tensor],
+                 d_grad: Optional[torch.Tensor], pts=None, rays_o=None, rays_d=None, z=None,
+                 flat_params: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """Pull the cotangents (d_udf[P], d_grad[P,3]) back to the flat parameter gradient."""
+    L = C.lib()
+    pts, ro, rd, zz, n, P = _points_args(pts, rays_o, rays_d, z)
+    dev = net.packed.device
+    if flat_params is None:
+        raise RuntimeError("udf_backward needs the flat parameter buffer")
+    flat_params = C.f32(flat_params)
+    W, in_dim, out_dim = _weff_views(net)
+    wh = _half_weights(net, getattr(net, "fold_id", 0))
+    pe = 3 + 6 * net.multires
+    h16 = lambda *s: torch.empty(*s, dtype=torch.float16, device=dev)  # noqa: E731
+    st = C.stream()
+    desc = ctypes.byref(net.desc)
+    # bias views inside the flat parameter buffer
+    boff, off = [], 0
+    for l in range(9):
+        boff.append(off)
+        off += out_dim[l] * (2 + in_dim[l])
+
+    U = [h16(2 * P, 64)]
+    C.check(L.emap_bwd_pe_dual(desc, C.ptr(pts), C.ptr(ro), C.ptr(rd), C.ptr(zz), n, P,
+                               C.ptr(None if d_grad is None else C.f32(d_grad)), C.ptr(U[0]), st))
+    sig, adot = [], []
+    for l in range(8):
+        acc = torch.mm(U[l], wh[l].t(), out_dtype=torch.float32)            # library GEMM [2P,256]
+        un, sg, ad = h16(2 * P, 256), h16(P, 256), h16(P, 256)
+        bias = flat_params[boff[l]:boff[l] + out_dim[l]]
+        C.check(L.emap_bwd_act_fwd(C.ptr(acc), 256, C.ptr(bias), P, out_dim[l],
+                                   C.ptr(U[0]) if l == 3 else None, pe, C.ptr(un), C.ptr(sg), C.ptr(ad), st))
+        U.append(un); sig.append(sg); adot.append(ad)
+        del acc
+    eta = torch.empty(2 * P, 256, dtype=torch.float32, device=dev)
+    coef = torch.empty(2 * P, dtype=torch.float32, device=dev)
+    w8 = W[8].reshape(-1)
+    b8 = flat_params[boff[8]:boff[8] + 1]
+    C.check(L.emap_bwd_top(desc, C.ptr(U[8]), C.ptr(w8), C.ptr(b8),
+                           C.ptr(None if d_udf is None else C.f32(d_udf)), P, C.ptr(eta), C.ptr(coef), st))
+    dW = [None] * 9
+    db = [None] * 9
+    dW[8] = torch.mm(coef.to(torch.float16).view(1, 2 * P), U[8], out_dtype=torch.float32)   # [1,256]
+    db[8] = coef[:P].sum().reshape(1)
+    A = h16(2 * P, 256)
+    for l in range(7, -1, -1):
+        C.check(L.emap_bwd_act_bwd(C.ptr(eta), 256, 1.0, P, out_dim[l], C.ptr(sig[l]), C.ptr(adot[l]),
+                                   C.ptr(A), st))
+        dW[l] = torch.mm(A.t(), U[l], out_dtype=torch.float32)                 # [256, 64|256]
+        db[l] = A[:P].sum(dim=0, dtype=torch.float32)
+        if l > 0:
+            eta = torch.mm(A, wh[l], out_dtype=torch.float32)                  # [2P,256]
+    flat_grad = torch.empty_like(flat_params)
+    dW_p = (ctypes.c_void_p * 9)(*[t.data_ptr() for t in dW])
+    db_p = (ctypes.c_void_p * 9)(*[t.data_ptr() for t in db])
+    ldw = (ctypes.c_int32 * 9)(*[t.shape[1] for t in dW])
+    mul = (ctypes.c_float * 9)(*[(2.0 ** -0.5) if l == 4 else 1.0 for l in range(9)])
+    C.check(L.emap_bwd_weight_norm(desc, C.ptr(flat_params), dW_p, ldw, mul, db_p, C.ptr(flat_grad), st))
+    return flat_grad

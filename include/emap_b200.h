@@ -68,6 +68,32 @@ int emap_udf_forward_grad(const emap_net_desc* net, const void* packed, int prec
                           const float* z, int32_t n_per_ray, int64_t P, float* udf_out,
                           float* grad_out, void* stream);
 
+/* ---- K1b: backward of (udf, d udf/dx) w.r.t. the 462,980 MLP parameters -------------------------
+ * replaces: autograd through UDFNetwork.forward + .gradient(create_graph=True)
+ * (udf_model.py:90-135; loss.backward() at runner_udf.py:167).  Round-1 structure: the element-wise
+ * stages are the kernels below; the per-layer GEMMs between them are plain library GEMMs issued by
+ * the host shim (emap_b200/ops.py: udf_backward).  All *_half pointers are fp16 device buffers;
+ * "dual" tensors hold value rows [0,P) and tangent rows [P,2P).                                    */
+int emap_bwd_pe_dual(const emap_net_desc* net, const float* pts, const float* rays_o,
+                     const float* rays_d, const float* z, int32_t n_per_ray, int64_t P,
+                     const float* d_grad /*[P,3] or NULL*/, void* U0_half /*[2P,64]*/, void* stream);
+int emap_bwd_act_fwd(const float* acc /*[2P,ld]*/, int32_t ld, const float* bias, int64_t P,
+                     int32_t n_out, const void* U0_half /*skip layer only, else NULL*/, int32_t pe,
+                     void* Unext_half /*[2P,256]*/, void* sig_half /*[P,256]*/, void* adot_half /*[P,256]*/,
+                     void* stream);
+int emap_bwd_top(const emap_net_desc* net, const void* U8_half, const float* w8, const float* b8,
+                 const float* d_udf /*[P] or NULL*/, int64_t P, float* Eta8 /*[2P,256]*/,
+                 float* coef /*[2P]*/, void* stream);
+int emap_bwd_act_bwd(const float* eta /*[2P,ld]*/, int32_t ld, float mul, int64_t P, int32_t n,
+                     const void* sig_half, const void* adot_half, void* A_half /*[2P,256]*/, void* stream);
+/* weight-norm backward + scatter into the flat gradient (same layout as the flat parameters).
+ * dW[l]: fp32 [out_l, ldw[l]] (d/dW_eff, times mul[l]); db[l]: fp32 [out_l].                       */
+int emap_bwd_weight_norm(const emap_net_desc* net, const float* flat_params, const float* const* dW,
+                         const int32_t* ldw, const float* mul, const float* const* db,
+                         float* flat_grad, void* stream);
+/* byte offsets inside the packed buffer: out[0] = 100*bias table, out[1..9] = W_eff of layer 0..8. */
+int emap_packed_offsets(const emap_net_desc* net, uint32_t* out10);
+
 /* ---- per-ray kernels (one warp per ray; <= 512 samples per ray, <= 64 new samples per step) ----
  * z = near + (far-near)*lin + t_rand*2/n                   (udf_renderer_blending.py:705-720)
  * near/far: device scalars [1] (near_is_per_ray=0) or [B] (=1); lin = torch.linspace(0,1,n) on
