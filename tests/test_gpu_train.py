@@ -90,26 +90,40 @@ def test_render_loss_param_grads_vs_reference(golden, tag, pert, rkw):
         assert maxdiff(p.grad.cpu(), ref) <= rel * (float(ref.abs().max()) + 1e-9) + 1e-9, name
 
 
-def test_training_steps_reduce_loss():
-    """a few Adam steps on a synthetic target through the drop-in classes: finite, decreasing loss"""
+def test_optimizer_step_descends():
+    """drop-in training step through the public classes: after one small Adam step (= lr * sign(grad))
+    the loss on the SAME batch and jitter must go down by about lr * sum|grad| (first-order check of the
+    whole gradient, all 462,985 entries at once), and stay finite over a few more steps."""
     from oracle import emap_oracle as O
     net, var, beta, r = build(10, True, n_samples=64, n_importance=50, up_sample_steps=5)
-    opt = torch.optim.Adam([{"params": list(net.parameters()), "lr": 5e-4},
-                            {"params": list(var.parameters()) + list(beta.parameters())}], lr=5e-4)
+    params = list(net.parameters()) + list(var.parameters()) + list(beta.parameters())
+    lr = 1e-5
+    opt = torch.optim.Adam(params, lr=lr)
     B = 256
     o, d = O.synthetic_rays(B)
     o, d = o.to(dev), d.to(dev)
     target = torch.rand(B, 1, generator=torch.Generator().manual_seed(3)).to(dev) * 0.2
     ds = torch.ones(B, 1, device=dev)
-    losses = []
-    torch.manual_seed(11)
-    for it in range(12):
+
+    def loss_fn():
+        torch.manual_seed(11)                      # same jitter every evaluation
         out = r.render(o, d, 0.05, 6.0, ds, cos_anneal_ratio=1.0, flip_saturation=0.9)
-        loss = (torch.nn.functional.mse_loss(out["edge"], target) + 0.01 * out["gradient_error_near_surface"]
+        return (torch.nn.functional.mse_loss(out["edge"], target) + 0.01 * out["gradient_error_near_surface"]
                 + 0.1 * out["gradient_error"])
+
+    l0 = loss_fn()
+    opt.zero_grad()
+    l0.backward()
+    predicted = lr * sum(float(p.grad.abs().sum()) for p in params if p.grad is not None)
+    opt.step()
+    with torch.no_grad():
+        l1 = loss_fn()
+    drop = float(l0) - float(l1)
+    assert drop > 0.0, (float(l0), float(l1))
+    assert 0.3 * predicted <= drop <= 1.5 * predicted, (drop, predicted)
+    for _ in range(3):
+        l = loss_fn()
         opt.zero_grad()
-        loss.backward()
+        l.backward()
         opt.step()
-        losses.append(float(loss))
-    assert all(l == l and abs(l) < 1e6 for l in losses)
-    assert min(losses[-4:]) < losses[0]
+        assert torch.isfinite(l)
