@@ -44,6 +44,7 @@ SIGNATURES = {
     "emap_udf_forward": (ctypes.c_int, [_nd, _vp, _i32, _vp, _vp, _vp, _vp, _i32, _i64, _vp, _vp, _vp]),
     "emap_udf_forward_grad": (ctypes.c_int, [_nd, _vp, _i32, _vp, _vp, _vp, _vp, _i32, _i64, _vp, _vp, _vp]),
     "emap_debug_mlp": (ctypes.c_int, [_nd, _vp, _i32, _i32, _vp, _i64, _vp, _vp, _vp, _vp]),
+    "emap_debug_set_clk_buffer": (ctypes.c_int, [_vp]),
     "emap_coarse_z": (ctypes.c_int, [_vp, _vp, _i32, _vp, _vp, _i32, _i32, _vp, _vp]),
     "emap_upsample_step": (ctypes.c_int, [_vp, _vp, _vp, _vp, _i32, _vp, _vp, _i32, _vp, _vp, _vp, _i32,
                                           _vp, _vp, _vp, _vp, _i32, _f32, _f32, _f32, _i32, _i32, _vp]),
@@ -111,6 +112,8 @@ def lib():
         if L.emap_abi_version() != 1:
             raise RuntimeError("emap_b200: ABI version mismatch between _cabi.py and the library")
         _lib = _Counting(L)
+        if os.environ.get("EMAP_CLUSTER"):
+            check(L.emap_set_option(b"cluster", int(os.environ["EMAP_CLUSTER"])))
     return _lib
 
 

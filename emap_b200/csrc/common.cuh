@@ -66,7 +66,8 @@ constexpr uint8_t kItemFirstOfAcc   = 1;   // first MMA into this accumulator ha
 constexpr uint8_t kItemLastOfLayer  = 2;   // commit acc_full after this item
 constexpr uint8_t kItemWaitA        = 4;   // first use of a_chunk in this layer: wait a_ready[a_chunk]
 constexpr uint8_t kItemFirstOfLayer = 8;   // wait acc_empty[layer&1] before issuing
-constexpr int kMaxItems = 192;
+constexpr uint8_t kItemChunk0Done   = 16;  // layer 4: last item reading activation chunk 0 -> commit c0_free
+constexpr int kMaxItems = 128;
 constexpr int kStageBytes = 16384;
 
 // Header of the packed-weights buffer (device memory, written by emap_wn_fold).
@@ -237,6 +238,16 @@ __device__ __forceinline__ void tmem_ld_32x32b_x32(uint32_t taddr, uint32_t (&r)
         "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]),
         "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]),
         "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld_32x32b_x16(uint32_t taddr, uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]),
+        "=r"(r[15])
       : "r"(taddr)
       : "memory");
 }

@@ -30,10 +30,12 @@
 
 namespace emap {
 
-constexpr int kEpiWarps = 8;
+constexpr int kEpiWarps = 16;                 // 4 per TMEM lane quarter
+constexpr int kProducerWarp = kEpiWarps;
+constexpr int kMmaWarp = kEpiWarps + 1;
 constexpr int kThreads = (kEpiWarps + 2) * 32;
 constexpr int kChunkBytes = 16384;           // one [128 x 64] 16-bit SW128 chunk
-constexpr int kScratchFloatsPerWarp = 8 * 36;
+constexpr int kScratchFloatsPerWarp = 8 * 20;   // MODE_GRAD: 8 points x 16 columns (+4 pad: conflict-free)
 
 struct MlpArgs {
   const uint8_t* packed;
@@ -49,21 +51,26 @@ struct MlpArgs {
   float* dbg_acc;       // optional [9][128][256] dump of tile 0 accumulators (descaled), else NULL
   int num_tiles;
   int iters;
+  long long* dbg_clk;   // optional [2][9][8] clock64 stamps of block 0, tile iteration 1 (epilogue warp 0 / MMA role 0)
+  int dbg_flags;        // timing experiments only: 1 = no MMA issue, 2 = no weight copies, 4 = no epilogue math
 };
 
 template <int NTERMS, int MODE>
 struct SmemPlan {
-  static constexpr int kStages = (NTERMS == 3) ? 3 : 6;
+  // fp32x3: A_hi + A_lo = 128 KiB, ring 4-5 x 16 KiB; single-MMA modes: A = 64 KiB, ring 8 x 16 KiB.
+  // (The PE chunk is not kept resident: it is written into activation chunk 0 for layer 0 and
+  //  re-generated there for the skip term of layer 4 -- that frees 32 KiB for the weight ring.)
+  static constexpr int kStages = (NTERMS == 3) ? 4 : 8;      // power of two: stage = item & (kStages-1)
   static constexpr int a_hi = 0;
-  static constexpr int pe_hi = a_hi + 4 * kChunkBytes;
-  static constexpr int a_lo = pe_hi + kChunkBytes;
-  static constexpr int pe_lo = a_lo + ((NTERMS == 3) ? 4 * kChunkBytes : 0);
-  static constexpr int ring = pe_lo + ((NTERMS == 3) ? kChunkBytes : 0);
+  static constexpr int a_lo = a_hi + 4 * kChunkBytes;
+  static constexpr int ring = a_lo + ((NTERMS == 3) ? 4 * kChunkBytes : 0);
   static constexpr int scratch = ring + kStages * kStageBytes;
   static constexpr int items = scratch + ((MODE == 1) ? kEpiWarps * kScratchFloatsPerWarp * 4 : 0);
   static constexpr int bars = items + kMaxItems * (int)sizeof(RingItem);
   static constexpr int total = bars + 256 + 1024;   // +1 KiB slack to 1024-align the base
 };
+static_assert(SmemPlan<3, 1>::total <= 232448 && SmemPlan<3, 0>::total <= 232448 &&
+              SmemPlan<1, 1>::total <= 232448, "shared memory plan exceeds 227 KiB");
 
 template <typename T> struct Elem;
 template <> struct Elem<__half> {
@@ -110,6 +117,24 @@ __device__ __forceinline__ void store_group(uint8_t* chunk_hi, uint8_t* chunk_lo
   }
 }
 
+// Write 4 consecutive columns (half of a 16-byte swizzle group): `half4` selects the low/high 8 bytes.
+template <int NTERMS, typename T>
+__device__ __forceinline__ void store_half_group(uint8_t* chunk_hi, uint8_t* chunk_lo, int row, int gidx,
+                                                 int half4, const float (&v)[4]) {
+  const uint32_t off = (uint32_t)row * 128u + (uint32_t)(((gidx ^ (row & 7)) & 7) << 4) + (uint32_t)half4 * 8u;
+  uint2 hi;
+  hi.x = Elem<T>::pack2(v[0], v[1]);
+  hi.y = Elem<T>::pack2(v[2], v[3]);
+  *reinterpret_cast<uint2*>(chunk_hi + off) = hi;
+  if (NTERMS == 3) {
+    float2 b0 = Elem<T>::unpack2(hi.x), b1 = Elem<T>::unpack2(hi.y);
+    uint2 lo;
+    lo.x = Elem<T>::pack2(v[0] - b0.x, v[1] - b0.y);
+    lo.y = Elem<T>::pack2(v[2] - b1.x, v[3] - b1.y);
+    *reinterpret_cast<uint2*>(chunk_lo + off) = lo;
+  }
+}
+
 // softplus(a; beta=100) and, optionally, its derivative sigmoid(100 a), from t = 100*a.
 // torch: log1p(exp(100 a))/100, identity above threshold 20 (udf_model.py:78) -- identical in fp32:
 // for t > 20 the log1p term is < 2.1e-11 and vanishes against a >= 0.2.
@@ -149,7 +174,7 @@ __device__ __forceinline__ void load_point(const MlpArgs& a, long long idx, floa
 template <int NTERMS, int MODE, typename T, int HF>
 __device__ __forceinline__ void pe_stage(const MlpArgs& args, const float (&x)[3], int multires,
                                          int lane, int row, long long pt, long long tile,
-                                         uint8_t* PE_hi, uint8_t* PE_lo) {
+                                         bool emit_pe_out, uint8_t* PE_hi, uint8_t* PE_lo) {
   constexpr int npairs = (HF == 0) ? 14 : 16;
   constexpr int qbase = (HF == 0) ? 0 : 14;
   constexpr int vofs = (HF == 0) ? 4 : 0;
@@ -164,7 +189,7 @@ __device__ __forceinline__ void pe_stage(const MlpArgs& args, const float (&x)[3
       if (j < multires) sincosf(x[ax] * (float)(1 << j), &s, &c);
       vals[vofs + 2 * i] = s; vals[vofs + 2 * i + 1] = c;
     }
-    if (args.pe_out && pt < args.P && tile < args.num_tiles) {
+    if (emit_pe_out && args.pe_out && pt < args.P && tile < args.num_tiles) {
       const int pe = 3 + 6 * multires;
 #pragma unroll
       for (int k = 0; k < 32; ++k) {
@@ -232,45 +257,53 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_kernel(const MlpArgs args) {
 
   RingItem* s_items = reinterpret_cast<RingItem*>(smem + Plan::items);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Plan::bars);
-  uint64_t* full = bars;                  // [kStages]
-  uint64_t* empty = bars + 6;             // [kStages]
-  uint64_t* a_ready = bars + 12;          // [5]
-  uint64_t* acc_full = bars + 17;         // [2]
-  uint64_t* acc_empty = bars + 19;        // [2]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 22);
+  uint64_t* full = bars;                  // [8]
+  uint64_t* empty = bars + 8;             // [8]
+  uint64_t* a_ready = bars + 16;          // [5]  (index 4 = PE written into chunk 0)
+  uint64_t* acc_full = bars + 21;         // [2]
+  uint64_t* acc_empty = bars + 23;        // [2]
+  uint64_t* c0_free = bars + 25;          // layer 4 has consumed chunk 0 -> PE may be regenerated there
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 27);
 
   {
     const uint4* src = reinterpret_cast<const uint4*>(args.packed + hdr->items_off[tix]);
     uint4* dst = reinterpret_cast<uint4*>(s_items);
     for (int i = threadIdx.x; i < n_items; i += kThreads) dst[i] = src[i];
   }
-  if (warp == 8 && lane == 0) {
+  if (warp == kProducerWarp && lane == 0) {
     for (int s = 0; s < kStages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], CL); }
-    for (int c = 0; c < 4; ++c) mbar_init(&a_ready[c], 4);
+    for (int c = 0; c < 4; ++c) mbar_init(&a_ready[c], kEpiWarps);
     mbar_init(&a_ready[4], 8);
     for (int b = 0; b < 2; ++b) { mbar_init(&acc_full[b], 1); mbar_init(&acc_empty[b], kEpiWarps); }
+    mbar_init(c0_free, 1);
     fence_barrier_init();
   }
-  if (warp == 9) { tmem_alloc(tmem_slot, 512); tmem_relinquish(); }
+  if (warp == kMmaWarp) { tmem_alloc(tmem_slot, 512); tmem_relinquish(); }
   tc_fence_before();
   if (CL > 1) cluster_sync_all(); else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  if (warp == 8) {
+  if (warp == kProducerWarp) {
     // ===================================== producer =====================================
     if (lane == 0) {
       const uint32_t rank = (CL > 1) ? cluster_ctarank() : 0;
       uint32_t g = 0;
+      uint8_t* ring = smem + Plan::ring;
       for (int iter = 0; iter < args.iters; ++iter) {
+#pragma unroll 1
         for (int i = 0; i < n_items; ++i, ++g) {
-          const uint32_t s = g % kStages, use = g / kStages;
+          const uint32_t s = g & (kStages - 1), use = g / kStages;
+          const uint4 raw = reinterpret_cast<const uint4*>(s_items)[i];
+          const uint32_t bytes = (raw.y & 0xffffu) * 16u;
+          const bool stp = args.dbg_clk && blockIdx.x == 0 && iter == 1 && i >= 24 && i < 28;
+          if (stp) args.dbg_clk[152 + (i - 24) * 3 + 0] = clock64();
           if (use > 0) mbar_wait(&empty[s], (use - 1) & 1, 100 + s, (int)g);
-          const RingItem it = s_items[i];
-          const uint32_t bytes = (uint32_t)it.bytes16 * 16u;
+          if (stp) args.dbg_clk[152 + (i - 24) * 3 + 1] = clock64();
+          if (args.dbg_flags & 2) { mbar_arrive(&full[s]); continue; }
           mbar_arrive_expect_tx(&full[s], bytes);
-          uint8_t* dst = smem + Plan::ring + s * kStageBytes;
-          const uint8_t* src = args.packed + it.gmem_off;
+          uint8_t* dst = ring + s * kStageBytes;
+          const uint8_t* src = args.packed + raw.x;
           if (CL == 1) {
             bulk_g2s(dst, src, bytes, &full[s]);
           } else {
@@ -278,69 +311,107 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_kernel(const MlpArgs args) {
             bulk_g2s_multicast(dst + rank * slice, src + rank * slice, slice, &full[s],
                                (uint16_t)((1u << CL) - 1));
           }
+          if (stp) args.dbg_clk[152 + (i - 24) * 3 + 2] = clock64();
         }
       }
     }
-  } else if (warp == 9) {
+  } else if (warp == kMmaWarp) {
     // ===================================== MMA issuer ===================================
-    if (lane == 0) {
-      uint32_t g = 0;
-      // Phase bookkeeping is closed-form in (iter, layer) -- no mutable per-thread arrays:
-      //   acc buffer 0 hosts layers 0,2,4,6,8 (5 uses per tile), buffer 1 layers 1,3,5,7 (4 uses);
-      //   a_ready[0..3] complete once per layer 1..8 input (8 per tile), a_ready[4] once per tile.
-      const uint32_t a_hi_addr = smem_u32(smem + Plan::a_hi), pe_hi_addr = smem_u32(smem + Plan::pe_hi);
-      const uint32_t a_lo_addr = smem_u32(smem + Plan::a_lo), pe_lo_addr = smem_u32(smem + Plan::pe_lo);
-      const uint32_t ring_addr = smem_u32(smem + Plan::ring);
-      for (int iter = 0; iter < args.iters; ++iter) {
-        for (int i = 0; i < n_items; ++i, ++g) {
-          const uint32_t s = g % kStages, use = g / kStages;
-          const RingItem it = s_items[i];
-          const int buf = it.layer & 1;
-          if (it.flags & kItemFirstOfLayer) {
-            const uint32_t started = (uint32_t)iter * (buf ? 4u : 5u) + (uint32_t)(it.layer >> 1);
-            if (started > 0) mbar_wait(&acc_empty[buf], (started - 1) & 1, 200 + buf, (int)g);
-          }
-          const int c = it.a_chunk;
-          if (it.flags & kItemWaitA) {
-            const uint32_t uses = (c == 4) ? (uint32_t)iter : (uint32_t)iter * 8u + (uint32_t)(it.layer - 1);
+    // One warp, uniform control flow, the instructions themselves issued by one elected lane (so
+    // descriptors live in uniform registers).  The weight stream is a fixed schedule (pack.cu: layer ->
+    // K chunk -> hi/lo part -> N half); the two N halves of a part sit in adjacent ring stages and are
+    // consumed by N=256 MMAs.  (Measured before this structure: a table-driven issuer under `lane==0`
+    // paid ~95 clk per tcgen05.mma and ~600 clk of loop overhead per 16 KiB item.)
+    const uint32_t a_hi_addr = smem_u32(smem + Plan::a_hi);
+    const uint32_t a_lo_addr = smem_u32(smem + Plan::a_lo);
+    const uint32_t ring_addr = smem_u32(smem + Plan::ring);
+    const uint32_t idesc256 = make_idesc_f16(128, 256, Elem<T>::fmt);
+    const uint32_t idesc16 = make_idesc_f16(128, 16, Elem<T>::fmt);
+    const bool no_mma = (args.dbg_flags & 1) != 0;
+    constexpr int kParts = (NTERMS == 3) ? 2 : 1;
+    uint32_t g = 0;
+    for (int iter = 0; iter < args.iters; ++iter) {
+#pragma unroll
+      for (int l = 0; l < kNumLinear; ++l) {
+        const int buf = l & 1;
+        const bool stamp = args.dbg_clk && blockIdx.x == 0 && iter == 1 && lane == 0;
+        if (stamp) args.dbg_clk[72 + l * 8 + 0] = clock64();
+        {
+          const uint32_t started = (uint32_t)iter * (buf ? 4u : 5u) + (uint32_t)(l >> 1);
+          if (started > 0) mbar_wait(&acc_empty[buf], (started - 1) & 1, 200 + buf, (int)g);
+        }
+        if (stamp) args.dbg_clk[72 + l * 8 + 1] = clock64();
+        const int nkc = (l == 0) ? 1 : ((l == kSkipLayer) ? 5 : 4);
+        const bool last = (l == kNumLinear - 1);
+        const uint32_t idesc = last ? idesc16 : idesc256;
+        const uint32_t d = tmem_base + (uint32_t)buf * 256u;
+#pragma unroll
+        for (int ic = 0; ic < nkc; ++ic) {
+          const int c = (l == 0) ? 4 : ((ic < 4) ? ic : 4);
+          {
+            const uint32_t uses = (c == 4) ? (uint32_t)iter * 2u + (l == kSkipLayer ? 1u : 0u)
+                                           : (uint32_t)iter * 8u + (uint32_t)(l - 1);
             mbar_wait(&a_ready[c], uses & 1, 300 + c, (int)g);
           }
-          mbar_wait(&full[s], use & 1, 400 + s, (int)g);
           tc_fence_after();
-          const uint32_t n = (uint32_t)it.n_rows8 * 8u;
-          const uint32_t idesc = make_idesc_f16(128, (int)n, Elem<T>::fmt);
-          const uint32_t d = tmem_base + (uint32_t)buf * 256u + (uint32_t)it.n_off8 * 8u;
-          const uint64_t bdesc = make_sw128_kmajor_desc(ring_addr + s * kStageBytes);
-          const uint64_t ahi = make_sw128_kmajor_desc(c == 4 ? pe_hi_addr : a_hi_addr + c * kChunkBytes);
-          const uint32_t first = (it.flags & kItemFirstOfAcc) ? 1u : 0u;
-          if (it.part == 0) {
+          if (stamp && ic < 4) args.dbg_clk[72 + l * 8 + 2 + ic] = clock64();
+          const uint32_t coff = (c == 4) ? 0u : (uint32_t)c * kChunkBytes;   // PE lives in chunk 0
+          const uint64_t ahi = make_sw128_kmajor_desc(a_hi_addr + coff);
+          const uint64_t alo = make_sw128_kmajor_desc(a_lo_addr + coff);
 #pragma unroll
-            for (int k = 0; k < 4; ++k)
-              umma_f16(d, ahi + 2 * k, bdesc + 2 * k, idesc, (first && k == 0) ? 0u : 1u);
-            if (NTERMS == 3) {
-              const uint64_t alo = make_sw128_kmajor_desc(c == 4 ? pe_lo_addr : a_lo_addr + c * kChunkBytes);
+          for (int part = 0; part < kParts; ++part) {
+            const uint32_t s = g & (kStages - 1), use = g / kStages;
+            const bool st2 = stamp && l == 2 && ic == 1;
+            if (st2) args.dbg_clk[144 + part * 4 + 0] = clock64();
+            mbar_wait(&full[s], use & 1, 400 + s, (int)g);
+            if (!last) mbar_wait(&full[s + 1], use & 1, 410 + s, (int)g);
+            tc_fence_after();
+            if (st2) args.dbg_clk[144 + part * 4 + 1] = clock64();
+            const uint64_t bdesc = make_sw128_kmajor_desc(ring_addr + s * kStageBytes);
+            if (elect_one()) {
+              if (!no_mma) {
+                if (part == 0) {
 #pragma unroll
-              for (int k = 0; k < 4; ++k) umma_f16(d, alo + 2 * k, bdesc + 2 * k, idesc, 1u);
+                  for (int k = 0; k < 4; ++k)
+                    umma_f16(d, ahi + 2 * k, bdesc + 2 * k, idesc, (ic == 0 && k == 0) ? 0u : 1u);
+                  if (NTERMS == 3) {
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) umma_f16(d, alo + 2 * k, bdesc + 2 * k, idesc, 1u);
+                  }
+                } else {
+#pragma unroll
+                  for (int k = 0; k < 4; ++k) umma_f16(d, ahi + 2 * k, bdesc + 2 * k, idesc, 1u);
+                }
+              }
+              if (CL == 1) {
+                umma_commit(&empty[s]);
+                if (!last) umma_commit(&empty[s + 1]);
+              } else {
+                umma_commit_multicast(&empty[s], (uint16_t)((1u << CL) - 1));
+                if (!last) umma_commit_multicast(&empty[s + 1], (uint16_t)((1u << CL) - 1));
+              }
             }
-          } else {
-#pragma unroll
-            for (int k = 0; k < 4; ++k) umma_f16(d, ahi + 2 * k, bdesc + 2 * k, idesc, 1u);
+            __syncwarp();
+            if (st2) args.dbg_clk[144 + part * 4 + 2] = clock64();
+            g += last ? 1u : 2u;
           }
-          if (CL == 1) umma_commit(&empty[s]);
-          else umma_commit_multicast(&empty[s], (uint16_t)((1u << CL) - 1));
-          if (it.flags & kItemLastOfLayer) umma_commit(&acc_full[buf]);
+          if (l == kSkipLayer && ic == 0) { if (elect_one()) umma_commit(c0_free); __syncwarp(); }
         }
+        if (elect_one()) umma_commit(&acc_full[buf]);
+        __syncwarp();
+        if (stamp) args.dbg_clk[72 + l * 8 + 6] = clock64();
       }
     }
   } else {
     // ===================================== epilogue warps ================================
-    const int q = warp & 3, hf = warp >> 2;
+    // warp = 4*sub + q: q = TMEM lane quarter; per layer each warp converts two 32-column pieces:
+    // phase 0 -> chunk (sub>>1), phase 1 -> chunk 2+(sub>>1); piece (sub&1) of the chunk.  Chunks 0,1 are
+    // therefore complete after half of the epilogue and the next layer's MMA starts on them.
+    const int q = warp & 3, sub = warp >> 2;
     const int row = q * 32 + lane;                 // TMEM lane == A-tile row
     const uint32_t lane_taddr = tmem_base + ((uint32_t)(q * 32) << 16);
     uint8_t* A_hi = smem + Plan::a_hi;
     uint8_t* A_lo = smem + Plan::a_lo;
-    uint8_t* PE_hi = smem + Plan::pe_hi;
-    uint8_t* PE_lo = smem + Plan::pe_lo;
     float* sc = reinterpret_cast<float*>(smem + Plan::scratch) + warp * kScratchFloatsPerWarp;
     const float k1 = kSoftplusBeta * kInvWeightScale;
     const int p8 = lane >> 2, ty = lane & 3;       // MODE_GRAD: point-in-warp, row type
@@ -348,115 +419,129 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_kernel(const MlpArgs args) {
 
     for (int iter = 0; iter < args.iters; ++iter) {
       const long long tile = (long long)blockIdx.x + (long long)iter * gridDim.x;
-      // ------------------------------------------------ input stage: positional encoding
+      // ------------------------------------------------ input stage: positional encoding -> chunk 0
       long long pt;
       if (MODE == 0) pt = tile * 128 + row;
       else pt = tile * 32 + q * 8 + p8;
       float x[3];
       load_point(args, pt, net_scale, x);
-      if (hf == 0)
-        pe_stage<NTERMS, MODE, T, 0>(args, x, multires, lane, row, pt, tile, PE_hi, PE_lo);
-      else
-        pe_stage<NTERMS, MODE, T, 1>(args, x, multires, lane, row, pt, tile, PE_hi, PE_lo);
-      fence_proxy_async_smem();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&a_ready[4]);
+      if (sub < 2) {
+        if (sub == 0) pe_stage<NTERMS, MODE, T, 0>(args, x, multires, lane, row, pt, tile, true, A_hi, A_lo);
+        else          pe_stage<NTERMS, MODE, T, 1>(args, x, multires, lane, row, pt, tile, true, A_hi, A_lo);
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&a_ready[4]);
+      }
 
       // ------------------------------------------------ hidden layers 0..7
       for (int l = 0; l < 8; ++l) {
         const int buf = l & 1;
+        const bool stamp = args.dbg_clk && blockIdx.x == 0 && iter == 1 && warp == 0 && lane == 0;
+        if (stamp) args.dbg_clk[l * 8 + 0] = clock64();
         mbar_wait(&acc_full[buf], ((uint32_t)iter * (buf ? 4u : 5u) + (uint32_t)(l >> 1)) & 1, 500 + buf, l);
         tc_fence_after();
+        if (stamp) args.dbg_clk[l * 8 + 1] = clock64();
         const float* bl = bias100 + l * kHidden;
 #pragma unroll 1
-        for (int cc = 0; cc < 2; ++cc) {
-          const int chunk = 2 * cc + hf;
+        for (int chunk = 0; chunk < 4; ++chunk) {
+          // all 16 warps convert the same 64-column chunk (16 columns each), so chunk c of the next
+          // layer's A tile is complete after (c+1)/4 of the epilogue and its MMAs start then
           uint8_t* dst_hi = A_hi + chunk * kChunkBytes;
           uint8_t* dst_lo = A_lo + chunk * kChunkBytes;
-#pragma unroll 1
-          for (int half = 0; half < 2; ++half) {
-            const int col0 = chunk * 64 + half * 32;
-            uint32_t r[32];
-            tmem_ld_32x32b_x32(lane_taddr + (uint32_t)(buf * 256 + col0), r);
-            tmem_wait_ld();
-            if (args.dbg_acc && tile == 0) {
+          const int col0 = chunk * 64 + sub * 16;
+          uint32_t r[16];
+          tmem_ld_32x32b_x16(lane_taddr + (uint32_t)(buf * 256 + col0), r);
+          tmem_wait_ld();
+          if (stamp && chunk < 2) args.dbg_clk[l * 8 + 2 + 3 * chunk] = clock64();
+          if (args.dbg_acc && tile == 0) {
 #pragma unroll
-              for (int k = 0; k < 32; ++k)
-                args.dbg_acc[((size_t)l * 128 + row) * 256 + col0 + k] = __uint_as_float(r[k]) * kInvWeightScale;
-            }
-            if (MODE == 0) {
-#pragma unroll
-              for (int g = 0; g < 4; ++g) {
-                const float4 bA = __ldg(reinterpret_cast<const float4*>(bl + col0 + g * 8));
-                const float4 bB = __ldg(reinterpret_cast<const float4*>(bl + col0 + g * 8 + 4));
-                const float bb[8] = {bA.x, bA.y, bA.z, bA.w, bB.x, bB.y, bB.z, bB.w};
-                float h[8];
-#pragma unroll
-                for (int j = 0; j < 8; ++j) {
-                  float dummy;
-                  h[j] = softplus100<false>(fmaf(__uint_as_float(r[g * 8 + j]), k1, bb[j]), dummy);
-                }
-                store_group<NTERMS, T>(dst_hi, dst_lo, row, half * 4 + g, h);
-              }
-            } else {
-              // phase A: value lanes publish their raw accumulators
-              if (ty == 0) {
-#pragma unroll
-                for (int i = 0; i < 8; ++i)
-                  *reinterpret_cast<float4*>(sc + p8 * 36 + 4 * i) =
-                      make_float4(__uint_as_float(r[4 * i]), __uint_as_float(r[4 * i + 1]),
-                                  __uint_as_float(r[4 * i + 2]), __uint_as_float(r[4 * i + 3]));
-              }
-              __syncwarp();
-              // phase B: every lane does 8 columns of its point's value row
-              {
-                const float4 vA = *reinterpret_cast<const float4*>(sc + p8 * 36 + 8 * ty);
-                const float4 vB = *reinterpret_cast<const float4*>(sc + p8 * 36 + 8 * ty + 4);
-                const float va[8] = {vA.x, vA.y, vA.z, vA.w, vB.x, vB.y, vB.z, vB.w};
-                const float4 bA = __ldg(reinterpret_cast<const float4*>(bl + col0 + 8 * ty));
-                const float4 bB = __ldg(reinterpret_cast<const float4*>(bl + col0 + 8 * ty + 4));
-                const float bb[8] = {bA.x, bA.y, bA.z, bA.w, bB.x, bB.y, bB.z, bB.w};
-                float h[8], sg[8];
-#pragma unroll
-                for (int j = 0; j < 8; ++j) {
-                  float s;
-                  h[j] = softplus100<true>(fmaf(va[j], k1, bb[j]), s);
-                  sg[j] = s * kInvWeightScale;   // tangent accumulators carry the weight pre-scale
-                }
-                store_group<NTERMS, T>(dst_hi, dst_lo, q * 32 + 4 * p8, half * 4 + ty, h);
-                *reinterpret_cast<float4*>(sc + p8 * 36 + 8 * ty) = make_float4(sg[0], sg[1], sg[2], sg[3]);
-                *reinterpret_cast<float4*>(sc + p8 * 36 + 8 * ty + 4) = make_float4(sg[4], sg[5], sg[6], sg[7]);
-              }
-              __syncwarp();
-              // phase C: tangent rows: d h = sigmoid(100 a) * d a
-              if (ty != 0) {
-#pragma unroll
-                for (int g = 0; g < 4; ++g) {
-                  const float4 sA = *reinterpret_cast<const float4*>(sc + p8 * 36 + 8 * g);
-                  const float4 sB = *reinterpret_cast<const float4*>(sc + p8 * 36 + 8 * g + 4);
-                  const float ss[8] = {sA.x, sA.y, sA.z, sA.w, sB.x, sB.y, sB.z, sB.w};
-                  float tv[8];
-#pragma unroll
-                  for (int j = 0; j < 8; ++j) tv[j] = ss[j] * __uint_as_float(r[g * 8 + j]);
-                  store_group<NTERMS, T>(dst_hi, dst_lo, row, half * 4 + g, tv);
-                }
-              }
-              __syncwarp();
-            }
+            for (int k = 0; k < 16; ++k)
+              args.dbg_acc[((size_t)l * 128 + row) * 256 + col0 + k] = __uint_as_float(r[k]) * kInvWeightScale;
           }
+          if (args.dbg_flags & 4) {
+            // timing experiment: no epilogue math / stores
+          } else if (MODE == 0) {
+#pragma unroll
+            for (int g = 0; g < 2; ++g) {
+              const float4 bA = __ldg(reinterpret_cast<const float4*>(bl + col0 + g * 8));
+              const float4 bB = __ldg(reinterpret_cast<const float4*>(bl + col0 + g * 8 + 4));
+              const float bb[8] = {bA.x, bA.y, bA.z, bA.w, bB.x, bB.y, bB.z, bB.w};
+              float h[8];
+#pragma unroll
+              for (int j = 0; j < 8; ++j) {
+                float dummy;
+                h[j] = softplus100<false>(fmaf(__uint_as_float(r[g * 8 + j]), k1, bb[j]), dummy);
+              }
+              store_group<NTERMS, T>(dst_hi, dst_lo, row, sub * 2 + g, h);
+            }
+          } else {
+            // phase A: value lanes publish their raw accumulators (16 columns)
+            if (ty == 0) {
+#pragma unroll
+              for (int i = 0; i < 4; ++i)
+                *reinterpret_cast<float4*>(sc + p8 * 20 + 4 * i) =
+                    make_float4(__uint_as_float(r[4 * i]), __uint_as_float(r[4 * i + 1]),
+                                __uint_as_float(r[4 * i + 2]), __uint_as_float(r[4 * i + 3]));
+            }
+            __syncwarp();
+            // phase B: every lane does 4 columns of its point's value row
+            {
+              const float4 vA = *reinterpret_cast<const float4*>(sc + p8 * 20 + 4 * ty);
+              const float va[4] = {vA.x, vA.y, vA.z, vA.w};
+              const float4 bA = __ldg(reinterpret_cast<const float4*>(bl + col0 + 4 * ty));
+              const float bb[4] = {bA.x, bA.y, bA.z, bA.w};
+              float h[4], sg[4];
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                float sgm;
+                h[j] = softplus100<true>(fmaf(va[j], k1, bb[j]), sgm);
+                sg[j] = sgm * kInvWeightScale;   // tangent accumulators carry the weight pre-scale
+              }
+              store_half_group<NTERMS, T>(dst_hi, dst_lo, q * 32 + 4 * p8, sub * 2 + (ty >> 1), ty & 1, h);
+              *reinterpret_cast<float4*>(sc + p8 * 20 + 4 * ty) = make_float4(sg[0], sg[1], sg[2], sg[3]);
+            }
+            __syncwarp();
+            // phase C: tangent rows: d h = sigmoid(100 a) * d a
+            if (ty != 0) {
+#pragma unroll
+              for (int g = 0; g < 2; ++g) {
+                const float4 sA = *reinterpret_cast<const float4*>(sc + p8 * 20 + 8 * g);
+                const float4 sB = *reinterpret_cast<const float4*>(sc + p8 * 20 + 8 * g + 4);
+                const float ss[8] = {sA.x, sA.y, sA.z, sA.w, sB.x, sB.y, sB.z, sB.w};
+                float tv[8];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) tv[j] = ss[j] * __uint_as_float(r[g * 8 + j]);
+                store_group<NTERMS, T>(dst_hi, dst_lo, row, sub * 2 + g, tv);
+              }
+            }
+            __syncwarp();
+          }
+          if (stamp && chunk < 2) args.dbg_clk[l * 8 + 3 + 3 * chunk] = clock64();
           fence_proxy_async_smem();
           __syncwarp();
           if (lane == 0) mbar_arrive(&a_ready[chunk]);
+          if (stamp && chunk < 2) args.dbg_clk[l * 8 + 4 + 3 * chunk] = clock64();
         }
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(&acc_empty[buf]);
+
+        if (l == kSkipLayer - 1 && sub < 2) {
+          // skip connection: layer 4 = [h4 ; PE]/sqrt2.  Once its MMAs on chunk 0 are done, regenerate
+          // the PE there (same code, same inputs as at tile start) as the 5th K chunk of layer 4.
+          mbar_wait(c0_free, (uint32_t)iter & 1, 520);
+          if (sub == 0) pe_stage<NTERMS, MODE, T, 0>(args, x, multires, lane, row, pt, tile, false, A_hi, A_lo);
+          else          pe_stage<NTERMS, MODE, T, 1>(args, x, multires, lane, row, pt, tile, false, A_hi, A_lo);
+          fence_proxy_async_smem();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&a_ready[4]);
+        }
       }
 
       // ------------------------------------------------ output layer (layer 8, accumulator buf 0, col 0)
       mbar_wait(&acc_full[0], ((uint32_t)iter * 5u + 4u) & 1, 510);
       tc_fence_after();
-      if (hf == 0) {
+      if (sub == 0) {
         const float accv = __uint_as_float(tmem_ld_32x32b_x1(lane_taddr)) * kInvWeightScale;
         tmem_wait_ld();
         if (args.dbg_acc && tile == 0) args.dbg_acc[((size_t)8 * 128 + row) * 256] = accv;
@@ -488,8 +573,11 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_kernel(const MlpArgs args) {
   // ---- teardown
   tc_fence_before();
   if (CL > 1) cluster_sync_all(); else __syncthreads();
-  if (warp == 9) tmem_dealloc(tmem_base, 512);
+  if (warp == kMmaWarp) tmem_dealloc(tmem_base, 512);
 }
+
+static long long* g_dbg_clk = nullptr;   // emap_debug_set_clk_buffer
+static int g_dbg_flags = 0;   // timing experiments (emap_set_option("dbg", flags)); 0 in production
 
 // ---------------------------------------------------------------------------------------------
 template <int NTERMS, int MODE, typename T, int CL>
@@ -500,6 +588,7 @@ static int launch(const MlpArgs& a_in, cudaStream_t stream) {
   const long long tiles = (a.P + pts_per_tile - 1) / pts_per_tile;
   if (tiles > 0x7fffffffLL) return set_error("too many points");
   a.num_tiles = (int)tiles;
+  a.dbg_flags = g_dbg_flags;
   int grid = sm_count();
   grid = grid / CL * CL;
   if (tiles < grid) grid = (int)((tiles + CL - 1) / CL * CL);
@@ -606,6 +695,7 @@ extern "C" int emap_debug_mlp(const emap_net_desc* net, const void* packed, int 
   memset(&a, 0, sizeof(a));
   a.packed = (const uint8_t*)packed; a.pts = pts; a.P = P; a.udf_out = udf_out; a.grad_out = grad_out;
   a.dbg_acc = dbg_acc;
+  a.dbg_clk = g_dbg_clk;
   if (mode == 0) return dispatch<0>(net, precision, a, (cudaStream_t)stream);
   if (!grad_out) return set_error("emap_debug_mlp: grad_out required for mode 1");
   return dispatch<1>(net, precision, a, (cudaStream_t)stream);
@@ -614,5 +704,11 @@ extern "C" int emap_debug_mlp(const emap_net_desc* net, const void* packed, int 
 extern "C" int emap_set_option(const char* name, int value) {
   if (!name) return set_error("option name is NULL");
   if (!strcmp(name, "cluster")) return set_cluster_width(value);
+  if (!strcmp(name, "dbg")) { emap::g_dbg_flags = value; return 0; }
   return set_error("unknown option '%s'", name);
+}
+
+extern "C" int emap_debug_set_clk_buffer(void* dev_buf_144_int64) {
+  emap::g_dbg_clk = (long long*)dev_buf_144_int64;
+  return 0;
 }

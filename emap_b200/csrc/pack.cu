@@ -68,14 +68,18 @@ void build_layout(const emap_net_desc& net, PackedHeader& h, std::vector<RingIte
     // zeros (stale TMEM there could hold NaN patterns that would poison layer 4 through 0*NaN)
     if (l == kNumLinear - 1) N = 16;
     int kcs[5]; int nkc = 0;
+    // a_chunk 4 = "PE": it is generated into activation chunk 0 (tile start, and again for the skip
+    // term of layer 4 after that layer's chunk-0 items have completed -- hence PE comes last there)
     if (l == 0) { kcs[nkc++] = 4; }
     else { for (int c = 0; c < 4; ++c) kcs[nkc++] = c; if (l == kSkipLayer) kcs[nkc++] = 4; }
     struct Half { int off, rows; } halves[2]; int nh = 0;
     if (N <= 128) { halves[nh++] = {0, N}; }
     else { halves[nh++] = {0, 128}; halves[nh++] = {128, N - 128}; }
     for (int ic = 0; ic < nkc; ++ic) {
-      for (int ih = 0; ih < nh; ++ih) {
-        for (int part = 0; part < 2; ++part) {
+      // stream order inside a K chunk: part (hi, lo) outer, N half inner -- the two halves of one part
+      // land in adjacent ring stages and are consumed by a single N=256 MMA group
+      for (int part = 0; part < 2; ++part) {
+        for (int ih = 0; ih < nh; ++ih) {
           RingItem it; memset(&it, 0, sizeof(it));
           it.gmem_off = h.images_off + img;
           const uint32_t bytes = (uint32_t)halves[ih].rows * 128u;
@@ -87,13 +91,17 @@ void build_layout(const emap_net_desc& net, PackedHeader& h, std::vector<RingIte
           it.part = (uint8_t)part;
           uint8_t fl = 0;
           if (ic == 0 && part == 0) fl |= kItemFirstOfAcc;
-          // layer 4 re-reads the PE chunk written for layer 0: nothing to wait for
-          if (ih == 0 && part == 0 && !(l == kSkipLayer && kcs[ic] == 4)) fl |= kItemWaitA;
+          if (ih == 0 && part == 0) fl |= kItemWaitA;
           if (ic == 0 && ih == 0 && part == 0) fl |= kItemFirstOfLayer;
           it.flags = fl;
           img += bytes;
           t3.push_back(it);
           if (part == 0) t1.push_back(it);
+          // last item of layer 4 that reads activation chunk 0
+          if (l == kSkipLayer && kcs[ic] == 0 && ih == nh - 1) {
+            if (part == 1) t3.back().flags |= kItemChunk0Done;
+            if (part == 0) t1.back().flags |= kItemChunk0Done;
+          }
         }
       }
     }

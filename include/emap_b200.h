@@ -156,6 +156,8 @@ int emap_render_core_bwd(const float* rays_o, const float* rays_d, const float* 
 int emap_set_option(const char* name, int value);
 /* test hook: MLP forward (mode 0) / forward+grad (mode 1) that also dumps the de-scaled
  * accumulators of tile 0, dbg_acc[9][128][256].                                                  */
+/* test hook: device buffer of 144 int64 receiving clock64 stamps from emap_debug_mlp runs.        */
+int emap_debug_set_clk_buffer(void* dev_buf_144_int64);
 int emap_debug_mlp(const emap_net_desc* net, const void* packed, int precision, int mode,
                    const float* pts, int64_t P, float* udf_out, float* grad_out, float* dbg_acc,
                    void* stream);
