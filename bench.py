@@ -148,7 +148,19 @@ def oracle_step_fn(mode, B):
     return step
 
 
+def use_all_host_threads():
+    """torchrun exports OMP_NUM_THREADS=1; the CPU arm is meant to use every host core."""
+    n = os.cpu_count() or 1
+    try:
+        n = len(os.sched_getaffinity(0))
+    except Exception:
+        pass
+    torch.set_num_threads(max(1, n))
+    return torch.get_num_threads()
+
+
 def cpu_baseline(mode, sample_rays=1024, reps=2):
+    use_all_host_threads()
     step = oracle_step_fn(mode, sample_rays)
     step()                                     # warm-up
     t0 = time.perf_counter()
@@ -165,6 +177,7 @@ def run_reference(args, rank, world):
     """--impl reference: the reference's CPU implementation of the path (oracle port), rank 0 only."""
     if rank != 0:
         return
+    use_all_host_threads()
     step = oracle_step_fn(args.mode, args.ref_rays)
     for _ in range(max(1, min(args.warmup, 1))):
         step()

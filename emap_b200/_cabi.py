@@ -47,7 +47,7 @@ SIGNATURES = {
     "emap_debug_set_clk_buffer": (ctypes.c_int, [_vp]),
     "emap_coarse_z": (ctypes.c_int, [_vp, _vp, _i32, _vp, _vp, _i32, _i32, _vp, _vp]),
     "emap_upsample_step": (ctypes.c_int, [_vp, _vp, _vp, _vp, _i32, _vp, _vp, _i32, _vp, _vp, _vp, _i32,
-                                          _vp, _vp, _vp, _vp, _i32, _f32, _f32, _f32, _i32, _i32, _vp]),
+                                          _vp, _vp, _vp, _vp, _i32, _f32, _f32, _f32, _vp, _i32, _i32, _vp]),
     "emap_render_prep": (ctypes.c_int, [_vp, _vp, _i32, _i32, _vp, _vp, _vp]),
     "emap_render_core_fwd": (ctypes.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _i32, _f32, _f32,
                                             _f32, _f32, _i32, _i32, _i32, _vp, _vp, _vp, _vp, _vp, _vp,

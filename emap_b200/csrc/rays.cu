@@ -120,6 +120,7 @@ struct UpsampleArgs {
   const float* u;                                          // [k] quantiles linspace(.5/k, 1-.5/k, k)
   float* z_new; long long* inds; float* w_out;             // [B,k] sorted, [B,k] optional, [B,m-1] optional
   const float* sample_dist;                                // device scalar
+  const float* gamma_ptr;                                  // optional device scalar overriding `gamma`
   int B, k;
   float inv_s, beta, gamma;
   int mode;        // 0 unbias (occlusion aware), 1 no_occ_aware, 2 weights given (sample_pdf only)
@@ -177,7 +178,7 @@ __global__ void __launch_bounds__(kRayWarps * 32) upsample_step_kernel(const Ups
   const float ox = a.rays_o[ray * 3 + 0], oy = a.rays_o[ray * 3 + 1], oz = a.rays_o[ray * 3 + 2];
   const float dx = a.rays_d[ray * 3 + 0], dy = a.rays_d[ray * 3 + 1], dz = a.rays_d[ray * 3 + 2];
   const float sample_dist = *a.sample_dist;
-  const float inv_s = a.inv_s, beta = a.beta, gamma = a.gamma;
+  const float inv_s = a.inv_s, beta = a.beta, gamma = a.gamma_ptr ? *a.gamma_ptr : a.gamma;
 
   // ---- weights[0..m-1)
   if (a.mode == 0) {
@@ -738,8 +739,8 @@ extern "C" int emap_upsample_step(const float* rays_o, const float* rays_d, cons
                                   const float* udf_add, int32_t ka, float* z_out, float* udf_out,
                                   const float* u, int32_t k, float* z_new, int64_t* inds_out,
                                   float* weights_out, const float* sample_dist, int32_t B, float inv_s,
-                                  float beta, float gamma, int32_t mode, int32_t alpha_type,
-                                  void* stream) {
+                                  float beta, float gamma, const float* gamma_dev, int32_t mode,
+                                  int32_t alpha_type, void* stream) {
   if (!z_in || B <= 0 || n <= 0) return set_error("emap_upsample_step: bad arguments");
   if (n + ka > kMaxSamples) return set_error("emap_upsample_step: more than %d samples per ray", kMaxSamples);
   if (k > kMaxNew || ka > kMaxNew) return set_error("emap_upsample_step: more than %d new samples per step", kMaxNew);
@@ -753,7 +754,7 @@ extern "C" int emap_upsample_step(const float* rays_o, const float* rays_d, cons
   a.rays_o = rays_o; a.rays_d = rays_d; a.z_in = z_in; a.udf_in = udf_in; a.n = n;
   a.z_add = z_add; a.udf_add = udf_add; a.ka = ka; a.z_out = z_out; a.udf_out = udf_out;
   a.u = u; a.z_new = z_new; a.inds = (long long*)inds_out; a.w_out = weights_out;
-  a.sample_dist = sample_dist; a.B = B; a.k = k; a.inv_s = inv_s; a.beta = beta; a.gamma = gamma;
+  a.sample_dist = sample_dist; a.gamma_ptr = gamma_dev; a.B = B; a.k = k; a.inv_s = inv_s; a.beta = beta; a.gamma = gamma;
   a.mode = mode; a.alpha_type = alpha_type;
   upsample_step_kernel<<<(B + kRayWarps - 1) / kRayWarps, kRayWarps * 32, 0, (cudaStream_t)stream>>>(a);
   EMAP_CUDA(cudaGetLastError());

@@ -127,7 +127,7 @@ def coarse_z(near: torch.Tensor, far: torch.Tensor, per_ray: bool, lin: torch.Te
 
 
 def upsample_step(rays_o, rays_d, z_in, udf_in, z_add, udf_add, u, k, sample_dist, inv_s, beta, gamma,
-                  mode=0, alpha_type=0, want_inds=False, want_weights=False):
+                  mode=0, alpha_type=0, want_inds=False, want_weights=False, gamma_dev=None):
     """Fused [merge pending samples] + [one up-sampling step].  Returns
     (z_cur[B,n+ka], udf_cur or None, z_new[B,k] or None, inds or None, weights or None)."""
     z_in = C.f32(z_in)
@@ -146,8 +146,8 @@ def upsample_step(rays_o, rays_d, z_in, udf_in, z_add, udf_add, u, k, sample_dis
         C.ptr(rays_o), C.ptr(rays_d), C.ptr(z_in), C.ptr(None if udf_in is None else C.f32(udf_in)), n,
         C.ptr(None if z_add is None else C.f32(z_add)), C.ptr(None if udf_add is None else C.f32(udf_add)),
         ka, C.ptr(z_out), C.ptr(udf_out), C.ptr(u), k, C.ptr(z_new), C.ptr(inds), C.ptr(w),
-        C.ptr(sample_dist), B, float(inv_s), float(beta), float(gamma), int(mode), int(alpha_type),
-        C.stream()))
+        C.ptr(sample_dist), B, float(inv_s), float(beta), float(gamma),
+        C.ptr(None if gamma_dev is None else C.f32(gamma_dev)), int(mode), int(alpha_type), C.stream()))
     z_cur = z_out if ka > 0 else z_in
     udf_cur = udf_out if ka > 0 else udf_in
     return z_cur, udf_cur, z_new, inds, w

@@ -95,3 +95,25 @@ def global_denominators(local_sums: torch.Tensor, group=None) -> torch.Tensor:
     if w > 1:
         dist.all_reduce(out, op=dist.ReduceOp.SUM, group=group)
     return out
+
+
+def globalize_eikonal(reduced: torch.Tensor, group=None) -> torch.Tensor:
+    """Turn the per-shard eikonal means into terms whose rank-average is the GLOBAL-batch mean.
+
+    ``reduced`` = [gerr, gerr_near, sparse, sum_relax, sum_near] of this rank's shard
+    (emap_render_core_fwd).  gerr = N_local/(D_local+1e-5).  The reference's semantics on the full
+    batch is N_global/(D_global+1e-5) (udf_renderer_blending.py:618-625).  With gradient averaging over
+    W ranks, each rank must contribute  W*N_local/(D_global+1e-5):  their mean is exactly the global
+    value and so is the averaged gradient.  Returns a new 5-vector whose entries 3,4 are the effective
+    denominators (D_global+1e-5)/W - 1e-5 to be used by the backward kernel.  One 2-float all-reduce."""
+    _, w = world()
+    if w == 1:
+        return reduced
+    local_d = reduced[3:5]
+    numer = reduced[0:2] * (local_d + 1e-5)
+    glob_d = global_denominators(local_d, group)
+    eff_d = (glob_d + 1e-5) / w - 1e-5
+    out = reduced.clone()
+    out[0:2] = numer / (eff_d + 1e-5)
+    out[3:5] = eff_d
+    return out

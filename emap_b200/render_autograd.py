@@ -17,6 +17,9 @@ class _RenderCore(torch.autograd.Function):
     def forward(ctx, udf, grad, scalars, rays_o, rays_d, mid_z, dists, B, n, cfg):
         (weights, alpha, grad_flip, inside, grad_mag, edge, depth, normals, reduced) = ops.render_core_fwd(
             rays_o, rays_d, mid_z, dists, udf, grad, scalars, B, n, cfg)
+        if cfg.get("global_stats"):
+            from .parallel import globalize_eikonal
+            reduced = globalize_eikonal(reduced)       # exact full-batch eikonal means across ray shards
         ctx.save_for_backward(udf, grad, scalars, rays_o, rays_d, mid_z, dists, reduced)
         ctx.cfg, ctx.B, ctx.n = cfg, B, n
         gerr, gerr_ns, sparse = reduced[0], reduced[1], reduced[2]

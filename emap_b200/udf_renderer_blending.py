@@ -59,10 +59,12 @@ class UDFRendererBlending:
             raise NotImplementedError("n_outside > 0 / NeRF background is dead code in the reference")
         if sdf2alpha_type not in ("numerical", "theorical"):
             raise ValueError(f"unknown sdf2alpha_type {sdf2alpha_type!r}")
-        if upsampling_type not in ("classical",):
-            raise NotImplementedError("upsampling_type='mix' (importance_sample_mix) is not built yet")
+        if upsampling_type not in ("classical", "mix"):
+            raise ValueError(f"unknown upsampling_type {upsampling_type!r}")
         self._alpha_type = 0 if sdf2alpha_type == "numerical" else 1
         self._const_cache: Dict = {}
+        # multi-GPU: make the two eikonal means those of the whole (sharded) batch (parallel.py)
+        self.global_batch_stats = False
 
     # ------------------------------------------------------------------ cached device constants
     def _const(self, key, make):
@@ -111,6 +113,38 @@ class UDFRendererBlending:
                                               sample_dist, 0.0, 0.0, 0.0, mode, self._alpha_type)
         return cur_z
 
+    @torch.no_grad()
+    def importance_sample_mix(self, rays_o, rays_d, z_vals, sample_dist):
+        """upsampling_type="mix" (udf_renderer_blending.py:843-918): S occlusion-unaware steps using
+        the learnable BetaNetwork gamma, then one occlusion-aware step; k = n_importance // (S+1)."""
+        net = self.udf_network
+        S = self.up_sample_steps
+        k = self.n_importance // (S + 1)
+        if not torch.is_tensor(sample_dist):
+            sample_dist = torch.tensor([sample_dist], dtype=torch.float32, device=self.device)
+        u = self._quantiles(k)
+        gamma_dev = self.beta_network.get_gamma().clip(1e-6, 1e6).detach().reshape(1).contiguous()
+        cur_z = z_vals
+        cur_udf, _ = udf_forward_fn(net, rays_o=rays_o, rays_d=rays_d, z=cur_z)
+        cur_udf = cur_udf.view_as(cur_z)
+        pend_z = pend_udf = None
+        schedule = [(1, 64.0 * 2 ** i, 64.0 * 2 ** (i + 1), 0.0, gamma_dev) for i in range(S)]
+        i = S - 1
+        schedule.append((0, 64.0 * 2 ** i, 64.0 * 2 ** (i + 1), 20.0 if i < 4 else 10.0, None))
+        for j, (mode, inv_s, beta, gamma, gdev) in enumerate(schedule):
+            cur_z, cur_udf, z_new, _, _ = ops.upsample_step(
+                rays_o, rays_d, cur_z, cur_udf, pend_z, pend_udf, u, k, sample_dist, inv_s, beta, gamma,
+                mode, self._alpha_type, gamma_dev=gdev)
+            pend_z = z_new
+            if j + 1 < len(schedule):
+                pend_udf, _ = udf_forward_fn(net, rays_o=rays_o, rays_d=rays_d, z=z_new)
+                pend_udf = pend_udf.view_as(z_new)
+            else:
+                pend_udf = None
+        cur_z, _, _, _, _ = ops.upsample_step(rays_o, rays_d, cur_z, None, pend_z, None, None, 0,
+                                              sample_dist, 0.0, 0.0, 0.0, 0, self._alpha_type)
+        return cur_z
+
     # ------------------------------------------------------------------ a13 render core
     def render_core(self, rays_o, rays_d, z_vals, sample_dist, udf_network, deviation_network,
                     beta_network=None, cos_anneal_ratio=None, background_rgb=None,
@@ -132,7 +166,8 @@ class UDFRendererBlending:
         cfg = dict(cos_anneal_ratio=-1.0 if cos_anneal_ratio is None else float(cos_anneal_ratio),
                    flip_saturation=float(flip_saturation), near_surface=float(self.near_surface),
                    sparse_scale=float(self.sparse_scale_factor), use_unbias=int(self.use_unbias_render),
-                   use_norm_grad=int(self.use_norm_grad_for_cosine), alpha_type=self._alpha_type)
+                   use_norm_grad=int(self.use_norm_grad_for_cosine), alpha_type=self._alpha_type,
+                   global_stats=bool(self.global_batch_stats))
         (weights, edge, depth, normals, gerr, gerr_ns, sparse, alpha, grad_flip, inside,
          grad_mag) = render_core_fn(udf, grad, scalars, rays_o, rays_d, mid_z, dists, B, n, cfg)
         if background_rgb is not None:
@@ -186,7 +221,10 @@ class UDFRendererBlending:
 
         n_samples = n0
         if self.n_importance > 0:
-            z_vals = self.importance_sample(rays_o, rays_d, z_vals, sd_t)
+            if self.upsampling_type == "classical":
+                z_vals = self.importance_sample(rays_o, rays_d, z_vals, sd_t)
+            else:
+                z_vals = self.importance_sample_mix(rays_o, rays_d, z_vals, sd_t)
             n_samples = n0 + self.n_importance
 
         r = self.render_core(rays_o, rays_d, z_vals, sd_t, self.udf_network, self.deviation_network,

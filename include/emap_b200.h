@@ -109,13 +109,15 @@ int emap_coarse_z(const float* near, const float* far, int32_t near_is_per_ray, 
  *       weights_out[B,n+ka-1] (optional)   replaces up_sample_unbias (:228-353) [mode 0],
  *       up_sample_no_occ_aware (:920-975) [mode 1] and sample_pdf(det=True) (:69-109);
  *       mode 2 = sample_pdf alone: udf_in then holds the weights [B,n-1] as given.
- * alpha_type: 0 "numerical", 1 "theorical" (:399-414).  sample_dist: device scalar.              */
+ * alpha_type: 0 "numerical", 1 "theorical" (:399-414).  sample_dist: device scalar.  gamma_dev
+ * (optional device scalar) overrides `gamma` -- importance_sample_mix passes the learnable
+ * BetaNetwork gamma (:873,:885) without a host sync.                                             */
 int emap_upsample_step(const float* rays_o, const float* rays_d, const float* z_in,
                        const float* udf_in, int32_t n, const float* z_add, const float* udf_add,
                        int32_t ka, float* z_out, float* udf_out, const float* u, int32_t k,
                        float* z_new, int64_t* inds_out, float* weights_out, const float* sample_dist,
-                       int32_t B, float inv_s, float beta, float gamma, int32_t mode,
-                       int32_t alpha_type, void* stream);
+                       int32_t B, float inv_s, float beta, float gamma, const float* gamma_dev,
+                       int32_t mode, int32_t alpha_type, void* stream);
 
 /* render_core before the MLP: dists, mid_z_vals          (udf_renderer_blending.py:435-446)     */
 int emap_render_prep(const float* z, const float* sample_dist, int32_t B, int32_t n, float* dists,

@@ -374,6 +374,28 @@ def importance_sample(p: UDFParams, rays_o, rays_d, z, sample_dist, n_importance
     return z
 
 
+@torch.no_grad()
+def importance_sample_mix(p: UDFParams, s: "ScalarParams", rays_o, rays_d, z, sample_dist,
+                          n_importance, up_sample_steps, sdf2alpha_type: str = "numerical"):
+    """upsampling_type="mix" (udf_renderer_blending.py:843-918): S occlusion-UNaware steps (density
+    peaks everywhere udf ~ 0) followed by one occlusion-aware step; k = n_importance // (S+1)."""
+    B, n0 = z.shape
+    S = up_sample_steps
+    k = n_importance // (S + 1)
+    pts = rays_o[:, None, :] + rays_d[:, None, :] * z[..., :, None]
+    udf = udf_forward(p, pts.reshape(-1, 3))[0][:, 0].reshape(B, n0)
+    gamma = s.gamma_val()
+    for i in range(S):
+        z_new = up_sample_no_occ_aware(rays_o, rays_d, z, udf, sample_dist, k, 64 * 2 ** i,
+                                       64 * 2 ** (i + 1), gamma)
+        z, udf = cat_z_vals(p, rays_o, rays_d, z, z_new, udf, last=False)
+    for i in range(S - 1, S):
+        z_new = up_sample_unbias(rays_o, rays_d, z, udf, sample_dist, k, 64 * 2 ** i, 64 * 2 ** (i + 1),
+                                 20 if i < 4 else 10, sdf2alpha_type=sdf2alpha_type)
+        z, udf = cat_z_vals(p, rays_o, rays_d, z, z_new, udf, last=(i + 1 == S))
+    return z
+
+
 # --------------------------------------------------------------------------- #
 # a13  render_core                 udf_renderer_blending.py:418-677
 # --------------------------------------------------------------------------- #
@@ -494,11 +516,13 @@ def render(p: UDFParams, s: ScalarParams, cfg: RenderConfig, rays_o, rays_d, nea
     if z_override is not None:
         z = z_override
     elif cfg.n_importance > 0:
-        if cfg.upsampling_type != "classical":
-            raise NotImplementedError("oracle covers upsampling_type='classical' only")
-        z = importance_sample(p, rays_o, rays_d, z, sample_dist, cfg.n_importance,
-                              cfg.up_sample_steps, cfg.use_unbias_render, trace=trace,
-                              sdf2alpha_type=cfg.sdf2alpha_type)
+        if cfg.upsampling_type == "mix":
+            z = importance_sample_mix(p, s, rays_o, rays_d, z, sample_dist, cfg.n_importance,
+                                      cfg.up_sample_steps, cfg.sdf2alpha_type)
+        else:
+            z = importance_sample(p, rays_o, rays_d, z, sample_dist, cfg.n_importance,
+                                  cfg.up_sample_steps, cfg.use_unbias_render, trace=trace,
+                                  sdf2alpha_type=cfg.sdf2alpha_type)
     r = render_core(p, s, rays_o, rays_d, z, sample_dist, cos_anneal_ratio, flip_saturation,
                     cfg.near_surface, cfg.sparse_scale_factor, cfg.use_unbias_render,
                     cfg.use_norm_grad_for_cosine, cfg.sdf2alpha_type)

@@ -44,7 +44,12 @@ def npify(d):
     return {k: (v.detach().cpu().numpy() if torch.is_tensor(v) else np.asarray(v)) for k, v in d.items()}
 
 
+ONLY = os.environ.get("EMAP_GOLDEN_ONLY")   # comma-separated fixture names; default: all
+
+
 def save(name, **arrs):
+    if ONLY and name not in ONLY.split(","):
+        return
     path = os.path.join(HERE, name + ".npz")
     np.savez_compressed(path, **npify(arrs))
     print(f"{name}.npz  {os.path.getsize(path) / 1024:.0f} KiB  keys={len(arrs)}")
@@ -218,6 +223,9 @@ def main():
     run_render("var_biased", True, 64, 50, 5, 8, 0.9, 1.0, grads=False, use_unbias_render=False)
     run_render("var_theorical", True, 64, 50, 5, 8, 0.9, 0.7, grads=False, sdf2alpha_type="theorical")
     run_render("var_normgrad", True, 64, 50, 5, 8, 0.9, 1.0, grads=False, use_norm_grad_for_cosine=True)
+    # upsampling_type="mix": n_importance // (steps+1) = 10 per step, 6 steps -> 64+60 samples, while the
+    # reference's render() still reports n_samples + n_importance = 114 in weight_sum (quirk kept)
+    run_render("var_mix", True, 64, 60, 5, 8, 0.9, 1.0, grads=False, upsampling_type="mix")
 
     # ------------------------------------------------------------------ a14 RenderingNetwork
     torch.manual_seed(3)

@@ -51,6 +51,20 @@ def _worker(rank, world, port, ret):
 
         den = parallel.global_denominators(torch.tensor([float(rank + 1), 10.0 * (rank + 1)]))
         assert torch.allclose(den, torch.tensor([3.0, 30.0]))
+
+        # exact full-batch eikonal means from per-shard ratios: mean over ranks == global ratio
+        numer = torch.tensor([2.0 + rank, 5.0 + 3 * rank])
+        dloc = torch.tensor([10.0 + 4 * rank, 3.0 + rank])
+        red = torch.cat([numer / (dloc + 1e-5), torch.tensor([0.5]), dloc])
+        g = parallel.globalize_eikonal(red)
+        acc = g[0:2].clone()
+        dist.all_reduce(acc)
+        acc /= world
+        n_all = torch.tensor([2.0 + 3.0, 5.0 + 8.0])
+        d_all = torch.tensor([10.0 + 14.0, 3.0 + 4.0])
+        assert torch.allclose(acc, n_all / (d_all + 1e-5), rtol=1e-6)
+        # the backward divides the cotangent by (entry + 1e-5): must equal W / (D_global + 1e-5)
+        assert torch.allclose(1.0 / (g[3:5] + 1e-5), world / (d_all + 1e-5), rtol=1e-6)
         ret[rank] = "ok"
     finally:
         dist.destroy_process_group()

@@ -51,6 +51,7 @@ CASES = [
     ("var_biased", True, 10, dict(n_samples=64, n_importance=50, up_sample_steps=5, use_unbias_render=False)),
     ("var_theorical", True, 10, dict(n_samples=64, n_importance=50, up_sample_steps=5, sdf2alpha_type="theorical")),
     ("var_normgrad", True, 10, dict(n_samples=64, n_importance=50, up_sample_steps=5, use_norm_grad_for_cosine=True)),
+    ("var_mix", True, 10, dict(n_samples=64, n_importance=60, up_sample_steps=5, upsampling_type="mix")),
 ]
 
 

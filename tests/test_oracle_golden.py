@@ -104,6 +104,7 @@ RENDER_CASES = [
                                      sdf2alpha_type="theorical")),
     ("var_normgrad", True, 10, dict(n_samples=64, n_importance=50, up_sample_steps=5,
                                     use_norm_grad_for_cosine=True)),
+    ("var_mix", True, 10, dict(n_samples=64, n_importance=60, up_sample_steps=5, upsampling_type="mix")),
 ]
 
 OUT_KEYS = ["udf", "edge", "weight_sum", "weight_sum_fg_bg", "depth", "beta", "gamma", "normals",
