@@ -52,6 +52,8 @@ SIGNATURES = {
     "emap_render_core_fwd": (ctypes.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _i32, _f32, _f32,
                                             _f32, _f32, _i32, _i32, _i32, _vp, _vp, _vp, _vp, _vp, _vp,
                                             _vp, _vp, _vp, _vp, _vp]),
+    "emap_bwd_dual_forward": (ctypes.c_int, [_nd, _vp, _i32, _vp, _vp, _vp, _vp, _i32, _i64, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "emap_bwd_reverse_sweep": (ctypes.c_int, [_nd, _vp, _vp, _vp, _vp, _vp, _i64, _vp]),
     "emap_bwd_pe_dual": (ctypes.c_int, [_nd, _vp, _vp, _vp, _vp, _i32, _i64, _vp, _vp, _vp]),
     "emap_bwd_act_fwd": (ctypes.c_int, [_vp, _i32, _vp, _i64, _i32, _vp, _i32, _vp, _vp, _vp, _vp]),
     "emap_bwd_top": (ctypes.c_int, [_nd, _vp, _vp, _vp, _vp, _i64, _vp, _vp, _vp]),
@@ -66,10 +68,11 @@ SIGNATURES = {
 
 # kernel launches issued by each entry point (for bench.py's `gpu_launches` claim)
 LAUNCHES_PER_CALL = {
-    "emap_wn_fold": 2, "emap_udf_forward": 1, "emap_udf_forward_grad": 1, "emap_debug_mlp": 1,
+    "emap_wn_fold": 3, "emap_udf_forward": 1, "emap_udf_forward_grad": 1, "emap_debug_mlp": 1,
     "emap_coarse_z": 1, "emap_upsample_step": 1, "emap_render_prep": 1, "emap_render_core_fwd": 2,
     "emap_render_core_bwd": 2, "emap_bwd_pe_dual": 1, "emap_bwd_act_fwd": 1, "emap_bwd_top": 1,
-    "emap_bwd_act_bwd": 1, "emap_bwd_weight_norm": 1,
+    "emap_bwd_act_bwd": 1, "emap_bwd_weight_norm": 1, "emap_bwd_dual_forward": 1,
+    "emap_bwd_reverse_sweep": 1,
 }
 launch_count = 0
 

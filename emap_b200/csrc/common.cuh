@@ -281,6 +281,18 @@ __host__ __device__ inline uint32_t sw128_offset(int row, int col) {
   return static_cast<uint32_t>(row) * 128u + ((((col >> 3) ^ (row & 7)) & 7) << 4) + ((col & 7) << 1);
 }
 
+// ---- 256-bit global accesses (sm_100: LDG.E.256 / STG.E.256): one full 32-byte sector per lane
+__device__ __forceinline__ void stg256(void* p, const uint32_t (&v)[8]) {
+  asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p), "r"(v[0]), "r"(v[1]), "r"(v[2]),
+               "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7])
+               : "memory");
+}
+__device__ __forceinline__ void ldg256(const void* p, uint32_t (&v)[8]) {
+  asm volatile("ld.global.nc.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])
+               : "l"(p));
+}
+
 // ---- small math helpers ----------------------------------------------------------------------
 __device__ __forceinline__ float ex2_approx(float x) {
   float y;

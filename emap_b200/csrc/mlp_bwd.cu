@@ -134,10 +134,12 @@ __global__ void dual_top_kernel(const __half* __restrict__ U8, const float* __re
   const float ub = ubar ? ubar[p] : 0.f;
   const float alpha = ub * f1 / scale + f2 * adot;
   const float alphadot = f1;
-  for (int c = lane; c < 256; c += 32) {
-    const float w = w8[c];
-    Eta8[p * 256 + c] = alpha * w;
-    Eta8[(P + p) * 256 + c] = alphadot * w;
+  if (Eta8) {
+    for (int c = lane; c < 256; c += 32) {
+      const float w = w8[c];
+      Eta8[p * 256 + c] = alpha * w;
+      Eta8[(P + p) * 256 + c] = alphadot * w;
+    }
   }
   if (lane == 0) { coef[p] = alpha; coef[P + p] = alphadot; }
 }
@@ -247,7 +249,7 @@ extern "C" int emap_bwd_act_fwd(const float* acc, int32_t ld, const float* bias,
 extern "C" int emap_bwd_top(const emap_net_desc* net, const void* U8_half, const float* w8, const float* b8,
                             const float* d_udf, int64_t P, float* Eta8, float* coef, void* stream) {
   if (check_net(net)) return 1;
-  if (!U8_half || !w8 || !b8 || !Eta8 || !coef || P <= 0) return set_error("emap_bwd_top: bad arguments");
+  if (!U8_half || !w8 || !b8 || !coef || P <= 0) return set_error("emap_bwd_top: bad arguments");
   dual_top_kernel<<<nblk(P * 32, 256), 256, 0, (cudaStream_t)stream>>>((const __half*)U8_half, w8, b8, d_udf, P,
                                                                        net->udf_type, net->scale, Eta8, coef);
   EMAP_CUDA(cudaGetLastError());

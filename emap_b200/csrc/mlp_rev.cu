@@ -1,0 +1,274 @@
+// K1b stage 2: fused reverse sweep of the dual network on the tensor cores.
+//
+// Given the stashes of the dual forward (emap_bwd_dual_forward: sigma_l = softplus'(a_l), adot_l) and the
+// output-layer pull-back (emap_bwd_top: alpha_8, alphadot_8 per point), one persistent kernel walks the
+// layers 7 -> 0 per tile of 64 points x {alpha, alphadot} rows:
+//     alpha_l    = eta_{l+1} sigma_l + etadot_{l+1} adot_l softplus''(a_l)      (value row)
+//     alphadot_l = etadot_{l+1} sigma_l                                        (tangent row)
+//     [eta_l ; etadot_l] = [alpha_l ; alphadot_l] W_l                           (tcgen05.mma, W_l^T images)
+// and stashes A_l = [alpha_l ; alphadot_l] (fp16, row-major) for the weight-gradient GEMMs
+// dW_l = A_l^T U_l.  Same skeleton as mlp_tc.cu (bulk-copy weight ring, one MMA-issuing warp, 16
+// epilogue warps converting 64-column chunks in order so the next layer's MMA overlaps); single-MMA
+// fp16 arithmetic with fp32 accumulation.  Replaces the autograd reverse pass through
+// src/models/udf_model.py:90-135 (loss.backward(), runner_udf.py:167).
+#include "common.cuh"
+#include "host.h"
+
+namespace emap {
+
+namespace rev {
+
+constexpr int kEpiWarps = 16;
+constexpr int kProducerWarp = kEpiWarps;
+constexpr int kMmaWarp = kEpiWarps + 1;
+constexpr int kThreads = (kEpiWarps + 2) * 32;
+constexpr int kChunkBytes = 16384;
+constexpr int kStages = 8;
+constexpr int kRevLayers = 7;          // MMA layers l = 7..1
+constexpr int kRevItems = kRevLayers * 4 * 2;
+
+struct Smem {
+  static constexpr int a = 0;                                   // [4 chunks][128 x 64] fp16 SW128
+  static constexpr int ring = a + 4 * kChunkBytes;
+  static constexpr int items = ring + kStages * kStageBytes;
+  static constexpr int bars = items + 64 * (int)sizeof(RingItem);
+  static constexpr int total = bars + 256 + 1024;
+};
+
+struct Args {
+  const uint8_t* packed;
+  const float* coef;        // [2P] alpha_8 (rows [0,P)), alphadot_8 (rows [P,2P))
+  const __half* st_sig;     // [8][P,256]
+  const __half* st_adot;    // [8][P,256]
+  __half* st_a;             // [8][2P,256]  out: A_l, l = 0..7
+  long long P;
+  int num_tiles, iters;
+};
+
+__device__ __forceinline__ uint32_t pack2h(float a, float b) {
+  __half2 h = __floats2half2_rn(a, b);
+  return *reinterpret_cast<uint32_t*>(&h);
+}
+
+// one 16-byte swizzle group (8 columns) of a row of an A-tile chunk + the same 16 bytes to the stash
+__device__ __forceinline__ void put_group(uint8_t* chunk, int row, int gidx, const float (&v)[8],
+                                          bool to_tile, __half* stash_or_null) {
+  uint4 q;
+  q.x = pack2h(v[0], v[1]); q.y = pack2h(v[2], v[3]); q.z = pack2h(v[4], v[5]); q.w = pack2h(v[6], v[7]);
+  if (to_tile)
+    *reinterpret_cast<uint4*>(chunk + (uint32_t)row * 128u + (uint32_t)(((gidx ^ (row & 7)) & 7) << 4)) = q;
+  if (stash_or_null) *reinterpret_cast<uint4*>(stash_or_null) = q;
+}
+
+__global__ void __launch_bounds__(kThreads, 1) mlp_rev_kernel(const Args args) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  const PackedHeader* hdr = reinterpret_cast<const PackedHeader*>(args.packed);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int out3 = (int)hdr->out_dim[kSkipLayer - 1];          // 256 - pe: valid columns of alpha_3
+
+  RingItem* s_items = reinterpret_cast<RingItem*>(smem + Smem::items);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Smem::bars);
+  uint64_t* full = bars;            // [8]
+  uint64_t* empty = bars + 8;       // [8]
+  uint64_t* a_ready = bars + 16;    // [4]
+  uint64_t* acc_full = bars + 20;   // [2]
+  uint64_t* acc_empty = bars + 22;  // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 25);
+
+  {
+    const uint4* src = reinterpret_cast<const uint4*>(args.packed + hdr->reserved[0]);
+    uint4* dst = reinterpret_cast<uint4*>(s_items);
+    for (int i = threadIdx.x; i < kRevItems; i += kThreads) dst[i] = src[i];
+  }
+  if (warp == kProducerWarp && lane == 0) {
+    for (int s = 0; s < kStages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+    for (int c = 0; c < 4; ++c) mbar_init(&a_ready[c], kEpiWarps);
+    for (int b = 0; b < 2; ++b) { mbar_init(&acc_full[b], 1); mbar_init(&acc_empty[b], kEpiWarps); }
+    fence_barrier_init();
+  }
+  if (warp == kMmaWarp) { tmem_alloc(tmem_slot, 512); tmem_relinquish(); }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == kProducerWarp) {
+    if (lane == 0) {
+      uint32_t g = 0;
+      uint8_t* ring = smem + Smem::ring;
+      for (int iter = 0; iter < args.iters; ++iter) {
+#pragma unroll 1
+        for (int i = 0; i < kRevItems; ++i, ++g) {
+          const uint32_t s = g & (kStages - 1), use = g / kStages;
+          const uint4 raw = reinterpret_cast<const uint4*>(s_items)[i];
+          if (use > 0) mbar_wait(&empty[s], (use - 1) & 1, 100 + s, (int)g);
+          mbar_arrive_expect_tx(&full[s], kStageBytes);
+          bulk_g2s(ring + s * kStageBytes, args.packed + raw.x, kStageBytes, &full[s]);
+        }
+      }
+    }
+  } else if (warp == kMmaWarp) {
+    const uint32_t a_addr = smem_u32(smem + Smem::a);
+    const uint32_t ring_addr = smem_u32(smem + Smem::ring);
+    const uint32_t idesc = make_idesc_f16(128, 256, 0);
+    uint32_t g = 0;
+    for (int iter = 0; iter < args.iters; ++iter) {
+#pragma unroll
+      for (int j = 0; j < kRevLayers; ++j) {
+        const int buf = j & 1;
+        {
+          const uint32_t started = (uint32_t)iter * (buf ? 3u : 4u) + (uint32_t)(j >> 1);
+          if (started > 0) mbar_wait(&acc_empty[buf], (started - 1) & 1, 200 + buf, (int)g);
+        }
+        const uint32_t d = tmem_base + (uint32_t)buf * 256u;
+#pragma unroll
+        for (int kc = 0; kc < 4; ++kc) {
+          mbar_wait(&a_ready[kc], ((uint32_t)iter * 7u + (uint32_t)j) & 1, 300 + kc, (int)g);
+          const uint32_t s = g & (kStages - 1), use = g / kStages;
+          mbar_wait(&full[s], use & 1, 400 + s, (int)g);
+          mbar_wait(&full[s + 1], use & 1, 410 + s, (int)g);
+          tc_fence_after();
+          const uint64_t adesc = make_sw128_kmajor_desc(a_addr + kc * kChunkBytes);
+          const uint64_t bdesc = make_sw128_kmajor_desc(ring_addr + s * kStageBytes);
+          if (elect_one()) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+              umma_f16(d, adesc + 2 * k, bdesc + 2 * k, idesc, (kc == 0 && k == 0) ? 0u : 1u);
+            umma_commit(&empty[s]);
+            umma_commit(&empty[s + 1]);
+          }
+          __syncwarp();
+          g += 2;
+        }
+        if (elect_one()) umma_commit(&acc_full[buf]);
+        __syncwarp();
+      }
+    }
+  } else {
+    // ===================================== epilogue warps ================================
+    const int q = warp & 3, sub = warp >> 2;
+    const int row = q * 32 + lane;
+    const int t2 = lane & 1;                                  // 0: alpha (value) row, 1: alphadot row
+    const uint32_t lane_taddr = tmem_base + ((uint32_t)(q * 32) << 16);
+    uint8_t* A = smem + Smem::a;
+    const float* w8 = reinterpret_cast<const float*>(args.packed + hdr->weff_layer_off[8]);
+    const size_t P = (size_t)args.P;
+
+    for (int iter = 0; iter < args.iters; ++iter) {
+      const long long tile = (long long)blockIdx.x + (long long)iter * gridDim.x;
+      const long long pt = tile * 64 + q * 16 + (lane >> 1);
+      const bool ok = (tile < args.num_tiles) && (pt < args.P);
+      const size_t pc = ok ? (size_t)pt : 0;
+      const size_t rowg = (t2 ? P : 0) + pc;
+      // cotangents of a8 / adot8 for this point
+      const float c_v = ok ? args.coef[pc] : 0.f;
+      const float c_t = ok ? args.coef[P + pc] : 0.f;
+
+      // stage j = -1 builds A_7 from the output-layer pull-back; stages j = 0..6 from the accumulators
+#pragma unroll 1
+      for (int j = -1; j < kRevLayers; ++j) {
+        const int lt = 6 - j;                   // layer whose A_l = [alpha ; alphadot] this stage produces
+        const int buf = j & 1;
+        if (j >= 0) {
+          mbar_wait(&acc_full[buf], ((uint32_t)iter * (buf ? 3u : 4u) + (uint32_t)(j >> 1)) & 1, 500 + buf, j);
+          tc_fence_after();
+        }
+        const __half* sig_l = args.st_sig + (size_t)lt * P * 256 + pc * 256;
+        const __half* ad_l = args.st_adot + (size_t)lt * P * 256 + pc * 256;
+        __half* a_out = args.st_a + (size_t)lt * 2 * P * 256 + rowg * 256;
+        const int ncols = (lt == kSkipLayer - 1) ? out3 : 256;
+#pragma unroll 1
+        for (int chunk = 0; chunk < 4; ++chunk) {
+          const int col0 = chunk * 64 + sub * 16;
+          float own[16];
+          if (j >= 0) {
+            uint32_t r[16];
+            tmem_ld_32x32b_x16(lane_taddr + (uint32_t)(buf * 256 + col0), r);
+            tmem_wait_ld();
+#pragma unroll
+            for (int k = 0; k < 16; ++k) own[k] = __uint_as_float(r[k]) * kInvWeightScale;
+          } else {
+            const float cf = t2 ? c_t : c_v;
+#pragma unroll
+            for (int k = 0; k < 16; k += 4) {
+              const float4 w = __ldg(reinterpret_cast<const float4*>(w8 + col0 + k));
+              own[k] = cf * w.x; own[k + 1] = cf * w.y; own[k + 2] = cf * w.z; own[k + 3] = cf * w.w;
+            }
+          }
+          uint32_t sw[8], aw[8], outp[8];
+          ldg256(sig_l + col0, sw);
+          ldg256(ad_l + col0, aw);
+#pragma unroll
+          for (int g = 0; g < 2; ++g) {
+            float v[8];
+#pragma unroll
+            for (int h2 = 0; h2 < 4; ++h2) {
+              const float2 sg = __half22float2(*reinterpret_cast<const __half2*>(&sw[g * 4 + h2]));
+              const float2 ad = __half22float2(*reinterpret_cast<const __half2*>(&aw[g * 4 + h2]));
+              const float sgv[2] = {sg.x, sg.y}, adv[2] = {ad.x, ad.y};
+#pragma unroll
+              for (int e = 0; e < 2; ++e) {
+                const int k = g * 8 + h2 * 2 + e;
+                const float mine = own[k];
+                const float other = __shfl_xor_sync(0xffffffffu, mine, 1);   // partner row's adjoint
+                const float s = sgv[e];
+                // value row: eta*sigma + etadot*adot*sp'' ;  tangent row: etadot*sigma
+                const float etad = t2 ? mine : other;
+                float res = mine * s;
+                if (!t2) res += etad * adv[e] * (kSoftplusBeta * s * (1.0f - s));
+                v[h2 * 2 + e] = (col0 + k < ncols && ok) ? res : 0.f;
+              }
+              outp[g * 4 + h2] = pack2h(v[h2 * 2], v[h2 * 2 + 1]);
+            }
+            put_group(A + chunk * kChunkBytes, row, sub * 2 + g, v, /*to_tile=*/lt >= 1, nullptr);
+          }
+          if (ok) stg256(a_out + col0, outp);
+          if (lt >= 1) {
+            fence_proxy_async_smem();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&a_ready[chunk]);
+          }
+        }
+        if (j >= 0) {
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&acc_empty[buf]);
+        }
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == kMmaWarp) tmem_dealloc(tmem_base, 512);
+}
+
+}  // namespace rev
+}  // namespace emap
+
+using namespace emap;
+
+extern "C" int emap_bwd_reverse_sweep(const emap_net_desc* net, const void* packed, const float* coef,
+                                      const void* st_sig, const void* st_adot, void* st_a, int64_t P,
+                                      void* stream) {
+  if (check_net(net)) return 1;
+  if (net->elem_type != 0) return set_error("emap_bwd_reverse_sweep: fp16 operand images required");
+  if (!packed || !coef || !st_sig || !st_adot || !st_a || P <= 0) return set_error("emap_bwd_reverse_sweep: bad arguments");
+  rev::Args a;
+  a.packed = (const uint8_t*)packed; a.coef = coef; a.st_sig = (const __half*)st_sig;
+  a.st_adot = (const __half*)st_adot; a.st_a = (__half*)st_a; a.P = P;
+  const long long tiles = (P + 63) / 64;
+  a.num_tiles = (int)tiles;
+  int grid = sm_count();
+  if (tiles < grid) grid = (int)tiles;
+  a.iters = (int)((tiles + grid - 1) / grid);
+  static bool attr_done = false;
+  if (!attr_done) {
+    EMAP_CUDA(cudaFuncSetAttribute(rev::mlp_rev_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, rev::Smem::total));
+    attr_done = true;
+  }
+  rev::mlp_rev_kernel<<<grid, rev::kThreads, rev::Smem::total, (cudaStream_t)stream>>>(a);
+  EMAP_CUDA(cudaGetLastError());
+  return 0;
+}

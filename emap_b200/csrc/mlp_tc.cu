@@ -48,6 +48,12 @@ struct MlpArgs {
   float* udf_out;
   float* grad_out;
   float* pe_out;
+  // MODE_DUAL (backward recompute): cotangent direction + fp16 stashes for the reverse sweep / dW GEMMs
+  const float* gbar;    // [P,3] dL/d(grad udf) or NULL (zero tangent)
+  __half* st_u0;        // [2P,64]  dual PE in kernel column order (rows [0,P) value, [P,2P) tangent)
+  __half* st_u;         // [8][2P,256] inputs of layers 1..8 (h ; hdot)
+  __half* st_sig;       // [8][P,256]  sigmoid(100 a_l)
+  __half* st_adot;      // [8][P,256]  tangent pre-activations
   float* dbg_acc;       // optional [9][128][256] dump of tile 0 accumulators (descaled), else NULL
   int num_tiles;
   int iters;
@@ -70,7 +76,17 @@ struct SmemPlan {
   static constexpr int total = bars + 256 + 1024;   // +1 KiB slack to 1024-align the base
 };
 static_assert(SmemPlan<3, 1>::total <= 232448 && SmemPlan<3, 0>::total <= 232448 &&
-              SmemPlan<1, 1>::total <= 232448, "shared memory plan exceeds 227 KiB");
+              SmemPlan<1, 1>::total <= 232448 && SmemPlan<3, 2>::total <= 232448, "shared memory plan exceeds 227 KiB");
+
+// per-mode schedule constants (MODE 0 forward, 1 forward+grad (4 rows/point), 2 dual forward with
+// stashes for the backward (2 rows/point, layers 0..7 only -- the output layer is pulled back by a
+// separate small kernel))
+template <int MODE> struct ModeInfo {
+  static constexpr int kLayers = (MODE == 2) ? 8 : 9;          // MMA layers per tile
+  static constexpr int kUses0 = (MODE == 2) ? 4 : 5;           // accumulator-0 uses per tile
+  static constexpr int kAPerTile = (MODE == 2) ? 7 : 8;        // a_ready[0..3] completions per tile
+  static constexpr int kPtsPerTile = (MODE == 0) ? 128 : ((MODE == 1) ? 32 : 64);
+};
 
 template <typename T> struct Elem;
 template <> struct Elem<__half> {
@@ -174,7 +190,8 @@ __device__ __forceinline__ void load_point(const MlpArgs& a, long long idx, floa
 template <int NTERMS, int MODE, typename T, int HF>
 __device__ __forceinline__ void pe_stage(const MlpArgs& args, const float (&x)[3], int multires,
                                          int lane, int row, long long pt, long long tile,
-                                         bool emit_pe_out, uint8_t* PE_hi, uint8_t* PE_lo) {
+                                         bool emit_pe_out, uint8_t* PE_hi, uint8_t* PE_lo,
+                                         const float (&gb)[3]) {
   constexpr int npairs = (HF == 0) ? 14 : 16;
   constexpr int qbase = (HF == 0) ? 0 : 14;
   constexpr int vofs = (HF == 0) ? 4 : 0;
@@ -195,6 +212,48 @@ __device__ __forceinline__ void pe_stage(const MlpArgs& args, const float (&x)[3
       for (int k = 0; k < 32; ++k) {
         const int ref = pe_col_to_ref(HF * 32 + k, multires);
         if (ref >= 0) args.pe_out[pt * pe + ref] = vals[k];
+      }
+    }
+  } else if (MODE == 2) {
+    // dual rows: lane pair (value, tangent along gb); the two lanes split the sincos work
+    const int t2 = lane & 1;
+    float ls[8], lc[8];
+#pragma unroll
+    for (int r = 0; r < 8; ++r) {
+      const int i = 2 * r + t2;
+      const int qq = qbase + i, j = qq / 3, ax = qq - 3 * j;
+      const float xa = (ax == 0) ? x[0] : (ax == 1 ? x[1] : x[2]);
+      ls[r] = 0.f; lc[r] = 0.f;
+      if (i < npairs && j < multires) sincosf(xa * (float)(1 << j), &ls[r], &lc[r]);
+    }
+    if (HF == 0) {
+      vals[0] = t2 ? gb[0] : x[0];
+      vals[1] = t2 ? gb[1] : x[1];
+      vals[2] = t2 ? gb[2] : x[2];
+      vals[3] = 0.f;
+    }
+#pragma unroll
+    for (int i = 0; i < npairs; ++i) {
+      const int src = (lane & ~1) | (i & 1);
+      const float S = __shfl_sync(0xffffffffu, ls[i >> 1], src);
+      const float C = __shfl_sync(0xffffffffu, lc[i >> 1], src);
+      const int qq = qbase + i, j = qq / 3, ax = qq % 3;
+      const float f = (float)(1 << j);
+      const float ga = (ax == 0) ? gb[0] : (ax == 1 ? gb[1] : gb[2]);
+      float vs = S, vc = C;
+      if (t2) { vs = (j < multires) ? f * C * ga : 0.f; vc = (j < multires) ? -f * S * ga : 0.f; }
+      vals[vofs + 2 * i] = vs; vals[vofs + 2 * i + 1] = vc;
+    }
+    if (emit_pe_out && args.st_u0 && pt < args.P && tile < args.num_tiles) {
+      __half* dst = args.st_u0 + ((t2 ? args.P : 0) + pt) * 64 + HF * 32;
+#pragma unroll
+      for (int g = 0; g < 4; ++g) {
+        uint4 v;
+        v.x = Elem<__half>::pack2(vals[g * 8 + 0], vals[g * 8 + 1]);
+        v.y = Elem<__half>::pack2(vals[g * 8 + 2], vals[g * 8 + 3]);
+        v.z = Elem<__half>::pack2(vals[g * 8 + 4], vals[g * 8 + 5]);
+        v.w = Elem<__half>::pack2(vals[g * 8 + 6], vals[g * 8 + 7]);
+        *reinterpret_cast<uint4*>(dst + g * 8) = v;
       }
     }
   } else {
@@ -241,6 +300,7 @@ __device__ __forceinline__ void pe_stage(const MlpArgs& args, const float (&x)[3
 template <int NTERMS, int MODE, typename T, int CL>
 __global__ void __launch_bounds__(kThreads, 1) mlp_kernel(const MlpArgs args) {
   using Plan = SmemPlan<NTERMS, MODE>;
+  using MI = ModeInfo<MODE>;
   constexpr int kStages = Plan::kStages;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
@@ -249,7 +309,8 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_kernel(const MlpArgs args) {
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const int tix = (NTERMS == 3) ? 1 : 0;
-  const int n_items = (int)hdr->n_items[tix];
+  // MODE_DUAL runs layers 0..7 only: drop the output layer's items (4 K chunks x parts) from the stream
+  const int n_items = (int)hdr->n_items[tix] - ((MODE == 2) ? ((NTERMS == 3) ? 8 : 4) : 0);
   const int multires = (int)hdr->multires;
   const float net_scale = hdr->scale;
   const int udf_type = (int)hdr->udf_type;
@@ -332,12 +393,12 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_kernel(const MlpArgs args) {
     uint32_t g = 0;
     for (int iter = 0; iter < args.iters; ++iter) {
 #pragma unroll
-      for (int l = 0; l < kNumLinear; ++l) {
+      for (int l = 0; l < MI::kLayers; ++l) {
         const int buf = l & 1;
         const bool stamp = args.dbg_clk && blockIdx.x == 0 && iter == 1 && lane == 0;
         if (stamp) args.dbg_clk[72 + l * 8 + 0] = clock64();
         {
-          const uint32_t started = (uint32_t)iter * (buf ? 4u : 5u) + (uint32_t)(l >> 1);
+          const uint32_t started = (uint32_t)iter * (buf ? 4u : (uint32_t)MI::kUses0) + (uint32_t)(l >> 1);
           if (started > 0) mbar_wait(&acc_empty[buf], (started - 1) & 1, 200 + buf, (int)g);
         }
         if (stamp) args.dbg_clk[72 + l * 8 + 1] = clock64();
@@ -350,7 +411,7 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_kernel(const MlpArgs args) {
           const int c = (l == 0) ? 4 : ((ic < 4) ? ic : 4);
           {
             const uint32_t uses = (c == 4) ? (uint32_t)iter * 2u + (l == kSkipLayer ? 1u : 0u)
-                                           : (uint32_t)iter * 8u + (uint32_t)(l - 1);
+                                           : (uint32_t)iter * (uint32_t)MI::kAPerTile + (uint32_t)(l - 1);
             mbar_wait(&a_ready[c], uses & 1, 300 + c, (int)g);
           }
           tc_fence_after();
@@ -422,12 +483,18 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_kernel(const MlpArgs args) {
       // ------------------------------------------------ input stage: positional encoding -> chunk 0
       long long pt;
       if (MODE == 0) pt = tile * 128 + row;
-      else pt = tile * 32 + q * 8 + p8;
+      else if (MODE == 1) pt = tile * 32 + q * 8 + p8;
+      else pt = tile * 64 + q * 16 + (lane >> 1);
       float x[3];
       load_point(args, pt, net_scale, x);
+      float gb[3] = {0.f, 0.f, 0.f};
+      if (MODE == 2 && args.gbar) {
+        const long long pc = (pt < args.P) ? pt : args.P - 1;
+        gb[0] = args.gbar[pc * 3]; gb[1] = args.gbar[pc * 3 + 1]; gb[2] = args.gbar[pc * 3 + 2];
+      }
       if (sub < 2) {
-        if (sub == 0) pe_stage<NTERMS, MODE, T, 0>(args, x, multires, lane, row, pt, tile, true, A_hi, A_lo);
-        else          pe_stage<NTERMS, MODE, T, 1>(args, x, multires, lane, row, pt, tile, true, A_hi, A_lo);
+        if (sub == 0) pe_stage<NTERMS, MODE, T, 0>(args, x, multires, lane, row, pt, tile, true, A_hi, A_lo, gb);
+        else          pe_stage<NTERMS, MODE, T, 1>(args, x, multires, lane, row, pt, tile, true, A_hi, A_lo, gb);
         fence_proxy_async_smem();
         __syncwarp();
         if (lane == 0) mbar_arrive(&a_ready[4]);
@@ -438,7 +505,7 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_kernel(const MlpArgs args) {
         const int buf = l & 1;
         const bool stamp = args.dbg_clk && blockIdx.x == 0 && iter == 1 && warp == 0 && lane == 0;
         if (stamp) args.dbg_clk[l * 8 + 0] = clock64();
-        mbar_wait(&acc_full[buf], ((uint32_t)iter * (buf ? 4u : 5u) + (uint32_t)(l >> 1)) & 1, 500 + buf, l);
+        mbar_wait(&acc_full[buf], ((uint32_t)iter * (buf ? 4u : (uint32_t)MI::kUses0) + (uint32_t)(l >> 1)) & 1, 500 + buf, l);
         tc_fence_after();
         if (stamp) args.dbg_clk[l * 8 + 1] = clock64();
         const float* bl = bias100 + l * kHidden;
@@ -460,6 +527,44 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_kernel(const MlpArgs args) {
           }
           if (args.dbg_flags & 4) {
             // timing experiment: no epilogue math / stores
+          } else if (MODE == 2) {
+            // dual rows (lane pair = value, tangent).  The tangent lane fetches its partner's value
+            // accumulator, both lanes run the same softplus/sigmoid stream; value lane keeps h, tangent
+            // lane keeps sigma * adot.  Everything is also stashed (fp16, row-major) for the reverse sweep.
+            const int t2 = lane & 1;
+            const bool okp = (tile < args.num_tiles) && (pt < args.P);
+            const long long rowg = (t2 ? args.P : 0) + pt;
+            uint32_t pu[8], ps[8];                       // 16 columns = 32 B per stash row
+#pragma unroll
+            for (int g = 0; g < 2; ++g) {
+              const float4 bA = __ldg(reinterpret_cast<const float4*>(bl + col0 + g * 8));
+              const float4 bB = __ldg(reinterpret_cast<const float4*>(bl + col0 + g * 8 + 4));
+              const float bb[8] = {bA.x, bA.y, bA.z, bA.w, bB.x, bB.y, bB.z, bB.w};
+              float outv[8], st2[8];
+#pragma unroll
+              for (int j = 0; j < 8; ++j) {
+                const uint32_t own = r[g * 8 + j];
+                const uint32_t oth = __shfl_xor_sync(0xffffffffu, own, 1);
+                const float aval = __uint_as_float(t2 ? oth : own);
+                float sgm;
+                const float h = softplus100<true>(fmaf(aval, k1, bb[j]), sgm);
+                const float adot = __uint_as_float(own) * kInvWeightScale;
+                outv[j] = t2 ? sgm * adot : h;
+                st2[j] = t2 ? adot : sgm;
+              }
+              if (l < 7) store_group<NTERMS, T>(dst_hi, dst_lo, row, sub * 2 + g, outv);
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                pu[g * 4 + j] = Elem<__half>::pack2(outv[2 * j], outv[2 * j + 1]);
+                ps[g * 4 + j] = Elem<__half>::pack2(st2[2 * j], st2[2 * j + 1]);
+              }
+            }
+            if (okp) {
+              const size_t plane_u = (size_t)l * 2 * (size_t)args.P * 256;
+              const size_t plane_s = (size_t)l * (size_t)args.P * 256;
+              stg256(args.st_u + plane_u + (size_t)rowg * 256 + col0, pu);
+              stg256((t2 ? args.st_adot : args.st_sig) + plane_s + (size_t)pt * 256 + col0, ps);
+            }
           } else if (MODE == 0) {
 #pragma unroll
             for (int g = 0; g < 2; ++g) {
@@ -519,7 +624,7 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_kernel(const MlpArgs args) {
           if (stamp && chunk < 2) args.dbg_clk[l * 8 + 3 + 3 * chunk] = clock64();
           fence_proxy_async_smem();
           __syncwarp();
-          if (lane == 0) mbar_arrive(&a_ready[chunk]);
+          if (lane == 0 && !(MODE == 2 && l == 7)) mbar_arrive(&a_ready[chunk]);
           if (stamp && chunk < 2) args.dbg_clk[l * 8 + 4 + 3 * chunk] = clock64();
         }
         tc_fence_before();
@@ -530,8 +635,8 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_kernel(const MlpArgs args) {
           // skip connection: layer 4 = [h4 ; PE]/sqrt2.  Once its MMAs on chunk 0 are done, regenerate
           // the PE there (same code, same inputs as at tile start) as the 5th K chunk of layer 4.
           mbar_wait(c0_free, (uint32_t)iter & 1, 520);
-          if (sub == 0) pe_stage<NTERMS, MODE, T, 0>(args, x, multires, lane, row, pt, tile, false, A_hi, A_lo);
-          else          pe_stage<NTERMS, MODE, T, 1>(args, x, multires, lane, row, pt, tile, false, A_hi, A_lo);
+          if (sub == 0) pe_stage<NTERMS, MODE, T, 0>(args, x, multires, lane, row, pt, tile, false, A_hi, A_lo, gb);
+          else          pe_stage<NTERMS, MODE, T, 1>(args, x, multires, lane, row, pt, tile, false, A_hi, A_lo, gb);
           fence_proxy_async_smem();
           __syncwarp();
           if (lane == 0) mbar_arrive(&a_ready[4]);
@@ -539,6 +644,7 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_kernel(const MlpArgs args) {
       }
 
       // ------------------------------------------------ output layer (layer 8, accumulator buf 0, col 0)
+      if (MODE == 2) continue;        // dual forward stops at layer 7 (the output layer is pulled back separately)
       mbar_wait(&acc_full[0], ((uint32_t)iter * 5u + 4u) & 1, 510);
       tc_fence_after();
       if (sub == 0) {
@@ -584,7 +690,7 @@ template <int NTERMS, int MODE, typename T, int CL>
 static int launch(const MlpArgs& a_in, cudaStream_t stream) {
   using Plan = SmemPlan<NTERMS, MODE>;
   MlpArgs a = a_in;
-  const int pts_per_tile = (MODE == 0) ? 128 : 32;
+  const int pts_per_tile = ModeInfo<MODE>::kPtsPerTile;
   const long long tiles = (a.P + pts_per_tile - 1) / pts_per_tile;
   if (tiles > 0x7fffffffLL) return set_error("too many points");
   a.num_tiles = (int)tiles;
@@ -682,6 +788,22 @@ extern "C" int emap_udf_forward_grad(const emap_net_desc* net, const void* packe
   a.packed = (const uint8_t*)packed; a.pts = pts; a.rays_o = rays_o; a.rays_d = rays_d; a.z = z;
   a.n_per_ray = n_per_ray; a.P = P; a.udf_out = udf_out; a.grad_out = grad_out;
   return dispatch<1>(net, precision, a, (cudaStream_t)stream);
+}
+
+// K1b stage 1: dual forward (value + one tangent along d_grad) of layers 0..7 with fp16 stashes.
+extern "C" int emap_bwd_dual_forward(const emap_net_desc* net, const void* packed, int precision,
+                                     const float* pts, const float* rays_o, const float* rays_d,
+                                     const float* z, int32_t n_per_ray, int64_t P, const float* d_grad,
+                                     void* st_u0, void* st_u, void* st_sig, void* st_adot, void* stream) {
+  if (check_net(net)) return 1;
+  if (!packed || !st_u0 || !st_u || !st_sig || !st_adot) return set_error("emap_bwd_dual_forward: NULL pointer");
+  if (check_points(pts, rays_o, rays_d, z, n_per_ray, P)) return 1;
+  MlpArgs a;
+  memset(&a, 0, sizeof(a));
+  a.packed = (const uint8_t*)packed; a.pts = pts; a.rays_o = rays_o; a.rays_d = rays_d; a.z = z;
+  a.n_per_ray = n_per_ray; a.P = P; a.gbar = d_grad;
+  a.st_u0 = (__half*)st_u0; a.st_u = (__half*)st_u; a.st_sig = (__half*)st_sig; a.st_adot = (__half*)st_adot;
+  return dispatch<2>(net, precision, a, (cudaStream_t)stream);
 }
 
 // Debug / test hook: run the forward (mode 0) or forward+grad (mode 1) kernel and additionally dump

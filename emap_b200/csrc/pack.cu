@@ -111,7 +111,27 @@ void build_layout(const emap_net_desc& net, PackedHeader& h, std::vector<RingIte
   h.images_bytes = img;
   h.n_items[0] = (uint32_t)t1.size();
   h.n_items[1] = (uint32_t)t3.size();
-  h.total_bytes = align_up(h.images_off + img, 1024);
+  // reverse-sweep stream (K1b): W_l^T images for l = 7..1, K chunk = 64 OUTPUT neurons, N half = 128
+  // INPUT neurons, hi part only (the backward runs single-MMA fp16).  Table right after the images.
+  uint32_t roff = align_up(h.images_off + img, 1024);
+  h.reserved[0] = roff;                                   // rev item table offset
+  h.reserved[1] = 7 * 4 * 2;                              // number of rev items
+  h.reserved[2] = align_up(roff + h.reserved[1] * (uint32_t)sizeof(RingItem), 1024);   // rev images offset
+  h.total_bytes = align_up(h.reserved[2] + h.reserved[1] * (uint32_t)kStageBytes, 1024);
+}
+
+void build_rev_items(const PackedHeader& h, std::vector<RingItem>& tr) {
+  tr.clear();
+  uint32_t off = h.reserved[2];
+  for (int l = 7; l >= 1; --l)
+    for (int kc = 0; kc < 4; ++kc)
+      for (int nh = 0; nh < 2; ++nh) {
+        RingItem it; memset(&it, 0, sizeof(it));
+        it.gmem_off = off; it.bytes16 = (uint16_t)(kStageBytes / 16);
+        it.layer = (uint8_t)l; it.a_chunk = (uint8_t)kc; it.n_off8 = (uint8_t)(nh * 16); it.n_rows8 = 16;
+        tr.push_back(it);
+        off += kStageBytes;
+      }
 }
 
 // ---- kernels -----------------------------------------------------------------------------------
@@ -196,6 +216,28 @@ __global__ void pack_images_kernel(uint8_t* __restrict__ packed) {
   }
 }
 
+// One block per reverse item: image[n][kk] = 16 * W_l[out = kc*64+kk][in = nh*128+n]  (x 1/sqrt2 for
+// the skip layer, whose PE inputs -- in >= 256-pe -- get no adjoint and are zeroed).
+template <typename T>
+__global__ void pack_rev_images_kernel(uint8_t* __restrict__ packed) {
+  const PackedHeader* h = reinterpret_cast<const PackedHeader*>(packed);
+  const RingItem it = reinterpret_cast<const RingItem*>(packed + h->reserved[0])[blockIdx.x];
+  const int l = it.layer, kc = it.a_chunk, n_off = it.n_off8 * 8;
+  const int od = (int)h->out_dim[l], id = (int)h->in_dim[l];
+  const int pe = 3 + 6 * (int)h->multires;
+  const float* W = reinterpret_cast<const float*>(packed + h->weff_layer_off[l]);
+  T* img = reinterpret_cast<T*>(packed + it.gmem_off);
+  const float mul = (l == kSkipLayer) ? 0.70710678118654752440f : 1.f;
+  const int in_valid = (l == kSkipLayer) ? (kHidden - pe) : id;
+  for (int e = threadIdx.x; e < 128 * 64; e += blockDim.x) {
+    const int n = e >> 6, kk = e & 63;
+    const int in_idx = n_off + n, out_idx = kc * 64 + kk;
+    float val = 0.f;
+    if (out_idx < od && in_idx < in_valid) val = W[(size_t)out_idx * id + in_idx] * mul * kWeightScale;
+    img[sw128_offset(n, kk) >> 1] = to_elem<T>(val);
+  }
+}
+
 // ---- host entry points -------------------------------------------------------------------------
 int check_net(const emap_net_desc* net) {
   if (!net) return set_error("net desc is NULL");
@@ -237,6 +279,10 @@ extern "C" int emap_wn_fold(const emap_net_desc* net, const float* flat_params, 
                             cudaMemcpyHostToDevice, stream));
   EMAP_CUDA(cudaMemcpyAsync(p + h.items_off[1], t3.data(), t3.size() * sizeof(RingItem),
                             cudaMemcpyHostToDevice, stream));
+  std::vector<RingItem> tr;
+  build_rev_items(h, tr);
+  EMAP_CUDA(cudaMemcpyAsync(p + h.reserved[0], tr.data(), tr.size() * sizeof(RingItem),
+                            cudaMemcpyHostToDevice, stream));
   int rows = 0;
   for (int l = 0; l < kNumLinear; ++l) rows += (int)h.out_dim[l];
   const int threads = 256, wpb = threads / 32;
@@ -246,6 +292,11 @@ extern "C" int emap_wn_fold(const emap_net_desc* net, const float* flat_params, 
     pack_images_kernel<__half><<<(unsigned)t3.size(), 256, 0, stream>>>(p);
   else
     pack_images_kernel<__nv_bfloat16><<<(unsigned)t3.size(), 256, 0, stream>>>(p);
+  EMAP_CUDA(cudaGetLastError());
+  if (net->elem_type == 0)
+    pack_rev_images_kernel<__half><<<(unsigned)tr.size(), 256, 0, stream>>>(p);
+  else
+    pack_rev_images_kernel<__nv_bfloat16><<<(unsigned)tr.size(), 256, 0, stream>>>(p);
   EMAP_CUDA(cudaGetLastError());
   return 0;
 }

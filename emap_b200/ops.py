@@ -252,10 +252,106 @@ def _half_weights(net: PackedNet, fold_id):
     return wh
 
 
+_PE_PERM = {}
+
+
+def _pe_perm(multires: int, device):
+    """kernel PE column -> reference PE index (common.cuh: pe_col_to_ref); -1 = padding."""
+    key = (multires, str(device))
+    if key not in _PE_PERM:
+        ref = []
+        for col in range(64):
+            if col < 3:
+                r = col
+            elif col == 3:
+                r = -1
+            else:
+                if col < 32:
+                    qq, is_cos = (col - 4) >> 1, (col - 4) & 1
+                else:
+                    qq, is_cos = 14 + ((col - 32) >> 1), (col - 32) & 1
+                j, c = qq // 3, qq % 3
+                r = -1 if j >= multires else 3 + 6 * j + 3 * is_cos + c
+            ref.append(r)
+        cols = [c for c, r in enumerate(ref) if r >= 0]
+        refs = [r for r in ref if r >= 0]
+        _PE_PERM[key] = (torch.tensor(cols, device=device), torch.tensor(refs, device=device))
+    return _PE_PERM[key]
+
+
 def udf_backward(net: PackedNet, precision: int, d_udf: Optional[torch.Tensor],
                  d_grad: Optional[torch.Tensor], pts=None, rays_o=None, rays_d=None, z=None,
                  flat_params: Optional[torch.Tensor] = None) -> torch.Tensor:
-    """Pull the cotangents (d_udf[P], d_grad[P,3]) back to the flat parameter gradient."""
+    """Pull the cotangents (d_udf[P], d_grad[P,3]) back to the flat parameter gradient.
+
+    Fused path (default; fp16 operand images): dual forward with stashes and the reverse sweep are two
+    tcgen05 kernels on the K1 skeleton; the 9 weight-gradient contractions dW_l = A_l^T U_l are plain
+    library GEMMs.  EMAP_BWD=layerwise selects the round-1 layer-by-layer structure (kept as a
+    cross-check: element-wise kernels + a library GEMM per layer and direction)."""
+    import os
+    if net.desc.elem_type != 0 or os.environ.get("EMAP_BWD") == "layerwise":
+        return udf_backward_layerwise(net, precision, d_udf, d_grad, pts, rays_o, rays_d, z, flat_params)
+    L = C.lib()
+    pts, ro, rd, zz, n, P = _points_args(pts, rays_o, rays_d, z)
+    dev = net.packed.device
+    if flat_params is None:
+        raise RuntimeError("udf_backward needs the flat parameter buffer")
+    flat_params = C.f32(flat_params)
+    W, in_dim, out_dim = _weff_views(net)
+    pe = 3 + 6 * net.multires
+    st = C.stream()
+    desc = ctypes.byref(net.desc)
+    h16 = lambda *s: torch.empty(*s, dtype=torch.float16, device=dev)  # noqa: E731
+    boff, off = [], 0
+    for l in range(9):
+        boff.append(off)
+        off += out_dim[l] * (2 + in_dim[l])
+
+    st_u0, st_u = h16(2 * P, 64), h16(8, 2 * P, 256)
+    st_sig, st_adot, st_a = h16(8, P, 256), h16(8, P, 256), h16(8, 2 * P, 256)
+    C.check(L.emap_bwd_dual_forward(desc, C.ptr(net.packed), C.PREC_HALF, C.ptr(pts), C.ptr(ro), C.ptr(rd),
+                                    C.ptr(zz), n, P, C.ptr(None if d_grad is None else C.f32(d_grad)),
+                                    C.ptr(st_u0), C.ptr(st_u), C.ptr(st_sig), C.ptr(st_adot), st))
+    coef = torch.empty(2 * P, dtype=torch.float32, device=dev)
+    U8 = st_u[7]
+    C.check(L.emap_bwd_top(desc, C.ptr(U8), C.ptr(W[8].reshape(-1)), C.ptr(flat_params[boff[8]:boff[8] + 1]),
+                           C.ptr(None if d_udf is None else C.f32(d_udf)), P, None, C.ptr(coef), st))
+    C.check(L.emap_bwd_reverse_sweep(desc, C.ptr(net.packed), C.ptr(coef), C.ptr(st_sig), C.ptr(st_adot),
+                                     C.ptr(st_a), P, st))
+    cols, refs = _pe_perm(net.multires, dev)
+    dW, db = [None] * 9, [None] * 9
+    dW[8] = torch.mm(coef.to(torch.float16).view(1, 2 * P), U8, out_dtype=torch.float32)
+    db[8] = coef[:P].sum().reshape(1)
+    for l in range(8):
+        A = st_a[l]
+        db[l] = A[:P].sum(dim=0, dtype=torch.float32)
+        if l == 0:
+            dk = torch.mm(A.t(), st_u0, out_dtype=torch.float32)              # [256,64] kernel PE order
+            d0 = torch.zeros(256, pe, dtype=torch.float32, device=dev)
+            d0[:, refs] = dk[:, cols]
+            dW[0] = d0
+        elif l == 4:
+            dh = torch.mm(A.t(), st_u[3], out_dtype=torch.float32)            # [256,256]; cols < 256-pe real
+            dk = torch.mm(A.t(), st_u0, out_dtype=torch.float32)
+            d4 = torch.empty(256, 256, dtype=torch.float32, device=dev)
+            d4[:, :256 - pe] = dh[:, :256 - pe]
+            d4[:, (256 - pe) + refs] = dk[:, cols]
+            dW[4] = d4
+        else:
+            dW[l] = torch.mm(A.t(), st_u[l - 1], out_dtype=torch.float32)
+    flat_grad = torch.empty_like(flat_params)
+    dW_p = (ctypes.c_void_p * 9)(*[t.data_ptr() for t in dW])
+    db_p = (ctypes.c_void_p * 9)(*[t.data_ptr() for t in db])
+    ldw = (ctypes.c_int32 * 9)(*[t.shape[1] for t in dW])
+    mul = (ctypes.c_float * 9)(*[(2.0 ** -0.5) if l == 4 else 1.0 for l in range(9)])
+    C.check(L.emap_bwd_weight_norm(desc, C.ptr(flat_params), dW_p, ldw, mul, db_p, C.ptr(flat_grad), st))
+    return flat_grad
+
+
+def udf_backward_layerwise(net: PackedNet, precision: int, d_udf: Optional[torch.Tensor],
+                           d_grad: Optional[torch.Tensor], pts=None, rays_o=None, rays_d=None, z=None,
+                           flat_params: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """Round-1 structure of the backward (see udf_backward)."""
     L = C.lib()
     pts, ro, rd, zz, n, P = _points_args(pts, rays_o, rays_d, z)
     dev = net.packed.device
