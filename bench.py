@@ -155,11 +155,13 @@ def use_all_host_threads():
         n = len(os.sched_getaffinity(0))
     except Exception:
         pass
-    torch.set_num_threads(max(1, n))
+    # one thread per PHYSICAL core: on the B200 host (128 logical CPUs) 128 threads ran this workload
+    # 9x slower than 64 (measured: 2.1 k vs 19.7 k ray-samples/s) -- SMT oversubscription
+    torch.set_num_threads(max(1, n // 2))
     return torch.get_num_threads()
 
 
-def cpu_baseline(mode, sample_rays=1024, reps=2):
+def cpu_baseline(mode, sample_rays=1024, reps=1):
     use_all_host_threads()
     step = oracle_step_fn(mode, sample_rays)
     step()                                     # warm-up
@@ -212,7 +214,7 @@ def main():
     ap.add_argument("--mode", default=None, choices=["infer", "train"])
     ap.add_argument("--precision", default="fp32", choices=["fp32", "fp16", "bf16"])
     ap.add_argument("--rays", type=int, default=RAYS_PER_GPU)
-    ap.add_argument("--ref-rays", type=int, default=512)
+    ap.add_argument("--ref-rays", type=int, default=128)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup

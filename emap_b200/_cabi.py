@@ -52,8 +52,8 @@ SIGNATURES = {
     "emap_render_core_fwd": (ctypes.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _i32, _f32, _f32,
                                             _f32, _f32, _i32, _i32, _i32, _vp, _vp, _vp, _vp, _vp, _vp,
                                             _vp, _vp, _vp, _vp, _vp]),
-    "emap_bwd_dual_forward": (ctypes.c_int, [_nd, _vp, _i32, _vp, _vp, _vp, _vp, _i32, _i64, _vp, _vp, _vp, _vp, _vp, _vp]),
-    "emap_bwd_reverse_sweep": (ctypes.c_int, [_nd, _vp, _vp, _vp, _vp, _vp, _i64, _vp]),
+    "emap_bwd_dual_forward": (ctypes.c_int, [_nd, _vp, _i32, _vp, _vp, _vp, _vp, _i32, _i64, _vp, _vp, _vp, _vp]),
+    "emap_bwd_reverse_sweep": (ctypes.c_int, [_nd, _vp, _vp, _vp, _vp, _i64, _vp]),
     "emap_bwd_pe_dual": (ctypes.c_int, [_nd, _vp, _vp, _vp, _vp, _i32, _i64, _vp, _vp, _vp]),
     "emap_bwd_act_fwd": (ctypes.c_int, [_vp, _i32, _vp, _i64, _i32, _vp, _i32, _vp, _vp, _vp, _vp]),
     "emap_bwd_top": (ctypes.c_int, [_nd, _vp, _vp, _vp, _vp, _i64, _vp, _vp, _vp]),

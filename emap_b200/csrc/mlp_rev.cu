@@ -1,6 +1,7 @@
 // K1b stage 2: fused reverse sweep of the dual network on the tensor cores.
 //
-// Given the stashes of the dual forward (emap_bwd_dual_forward: sigma_l = softplus'(a_l), adot_l) and the
+// Given the stash of the dual forward (emap_bwd_dual_forward: U_{l+1} = (h_{l+1} ; hdot_{l+1}), from which
+// sigma_l = 1 - exp(-100 h_{l+1}) and adot_l softplus''(a_l) = 100 hdot_{l+1} (1 - sigma_l) follow) and the
 // output-layer pull-back (emap_bwd_top: alpha_8, alphadot_8 per point), one persistent kernel walks the
 // layers 7 -> 0 per tile of 64 points x {alpha, alphadot} rows:
 //     alpha_l    = eta_{l+1} sigma_l + etadot_{l+1} adot_l softplus''(a_l)      (value row)
@@ -38,8 +39,7 @@ struct Smem {
 struct Args {
   const uint8_t* packed;
   const float* coef;        // [2P] alpha_8 (rows [0,P)), alphadot_8 (rows [P,2P))
-  const __half* st_sig;     // [8][P,256]
-  const __half* st_adot;    // [8][P,256]
+  const __half* st_u;       // [8][2P,256] dual activations (h ; hdot) = inputs of layers 1..8
   __half* st_a;             // [8][2P,256]  out: A_l, l = 0..7
   long long P;
   int num_tiles, iters;
@@ -174,8 +174,8 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_rev_kernel(const Args args) {
           mbar_wait(&acc_full[buf], ((uint32_t)iter * (buf ? 3u : 4u) + (uint32_t)(j >> 1)) & 1, 500 + buf, j);
           tc_fence_after();
         }
-        const __half* sig_l = args.st_sig + (size_t)lt * P * 256 + pc * 256;
-        const __half* ad_l = args.st_adot + (size_t)lt * P * 256 + pc * 256;
+        // own row of U_{lt+1}: h (value lane) or hdot (tangent lane); the partner's comes by shuffle
+        const __half* u_l = args.st_u + (size_t)lt * 2 * P * 256 + rowg * 256;
         __half* a_out = args.st_a + (size_t)lt * 2 * P * 256 + rowg * 256;
         const int ncols = (lt == kSkipLayer - 1) ? out3 : 256;
 #pragma unroll 1
@@ -196,27 +196,31 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_rev_kernel(const Args args) {
               own[k] = cf * w.x; own[k + 1] = cf * w.y; own[k + 2] = cf * w.z; own[k + 3] = cf * w.w;
             }
           }
-          uint32_t sw[8], aw[8], outp[8];
-          ldg256(sig_l + col0, sw);
-          ldg256(ad_l + col0, aw);
+          uint32_t uw[8], outp[8];
+          ldg256(u_l + col0, uw);
 #pragma unroll
           for (int g = 0; g < 2; ++g) {
             float v[8];
 #pragma unroll
             for (int h2 = 0; h2 < 4; ++h2) {
-              const float2 sg = __half22float2(*reinterpret_cast<const __half2*>(&sw[g * 4 + h2]));
-              const float2 ad = __half22float2(*reinterpret_cast<const __half2*>(&aw[g * 4 + h2]));
-              const float sgv[2] = {sg.x, sg.y}, adv[2] = {ad.x, ad.y};
+              const uint32_t uo = __shfl_xor_sync(0xffffffffu, uw[g * 4 + h2], 1);
+              const float2 mine2 = __half22float2(*reinterpret_cast<const __half2*>(&uw[g * 4 + h2]));
+              const float2 oth2 = __half22float2(*reinterpret_cast<const __half2*>(&uo));
+              // h = softplus(a) of the value row, hdot = sigma * adot of the tangent row
+              const float hv[2] = {t2 ? oth2.x : mine2.x, t2 ? oth2.y : mine2.y};
+              const float hd[2] = {t2 ? mine2.x : oth2.x, t2 ? mine2.y : oth2.y};
 #pragma unroll
               for (int e = 0; e < 2; ++e) {
                 const int k = g * 8 + h2 * 2 + e;
                 const float mine = own[k];
                 const float other = __shfl_xor_sync(0xffffffffu, mine, 1);   // partner row's adjoint
-                const float s = sgv[e];
+                // sigma = softplus'(a) = 1 - exp(-100 h);  adot * softplus''(a) = 100 * hdot * (1 - sigma)
+                const float one_m_s = __expf(-kSoftplusBeta * hv[e]);
+                const float s = 1.0f - one_m_s;
                 // value row: eta*sigma + etadot*adot*sp'' ;  tangent row: etadot*sigma
                 const float etad = t2 ? mine : other;
                 float res = mine * s;
-                if (!t2) res += etad * adv[e] * (kSoftplusBeta * s * (1.0f - s));
+                if (!t2) res += etad * (kSoftplusBeta * hd[e] * one_m_s);
                 v[h2 * 2 + e] = (col0 + k < ncols && ok) ? res : 0.f;
               }
               outp[g * 4 + h2] = pack2h(v[h2 * 2], v[h2 * 2 + 1]);
@@ -250,14 +254,13 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_rev_kernel(const Args args) {
 using namespace emap;
 
 extern "C" int emap_bwd_reverse_sweep(const emap_net_desc* net, const void* packed, const float* coef,
-                                      const void* st_sig, const void* st_adot, void* st_a, int64_t P,
-                                      void* stream) {
+                                      const void* st_u, void* st_a, int64_t P, void* stream) {
   if (check_net(net)) return 1;
   if (net->elem_type != 0) return set_error("emap_bwd_reverse_sweep: fp16 operand images required");
-  if (!packed || !coef || !st_sig || !st_adot || !st_a || P <= 0) return set_error("emap_bwd_reverse_sweep: bad arguments");
+  if (!packed || !coef || !st_u || !st_a || P <= 0) return set_error("emap_bwd_reverse_sweep: bad arguments");
   rev::Args a;
-  a.packed = (const uint8_t*)packed; a.coef = coef; a.st_sig = (const __half*)st_sig;
-  a.st_adot = (const __half*)st_adot; a.st_a = (__half*)st_a; a.P = P;
+  a.packed = (const uint8_t*)packed; a.coef = coef; a.st_u = (const __half*)st_u;
+  a.st_a = (__half*)st_a; a.P = P;
   const long long tiles = (P + 63) / 64;
   a.num_tiles = (int)tiles;
   int grid = sm_count();

@@ -51,9 +51,9 @@ struct MlpArgs {
   // MODE_DUAL (backward recompute): cotangent direction + fp16 stashes for the reverse sweep / dW GEMMs
   const float* gbar;    // [P,3] dL/d(grad udf) or NULL (zero tangent)
   __half* st_u0;        // [2P,64]  dual PE in kernel column order (rows [0,P) value, [P,2P) tangent)
-  __half* st_u;         // [8][2P,256] inputs of layers 1..8 (h ; hdot)
-  __half* st_sig;       // [8][P,256]  sigmoid(100 a_l)
-  __half* st_adot;      // [8][P,256]  tangent pre-activations
+  __half* st_u;         // [8][2P,256] inputs of layers 1..8 (h ; hdot).  This is the ONLY per-layer stash:
+                        // sigma_l = 1 - exp(-100 h_{l+1}) and adot_l * softplus''(a_l) = 100 hdot_{l+1} (1 - sigma_l)
+                        // are recovered from it by the reverse sweep.
   float* dbg_acc;       // optional [9][128][256] dump of tile 0 accumulators (descaled), else NULL
   int num_tiles;
   int iters;
@@ -534,13 +534,13 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_kernel(const MlpArgs args) {
             const int t2 = lane & 1;
             const bool okp = (tile < args.num_tiles) && (pt < args.P);
             const long long rowg = (t2 ? args.P : 0) + pt;
-            uint32_t pu[8], ps[8];                       // 16 columns = 32 B per stash row
+            uint32_t pu[8];                              // 16 columns = 32 B per stash row
 #pragma unroll
             for (int g = 0; g < 2; ++g) {
               const float4 bA = __ldg(reinterpret_cast<const float4*>(bl + col0 + g * 8));
               const float4 bB = __ldg(reinterpret_cast<const float4*>(bl + col0 + g * 8 + 4));
               const float bb[8] = {bA.x, bA.y, bA.z, bA.w, bB.x, bB.y, bB.z, bB.w};
-              float outv[8], st2[8];
+              float outv[8];
 #pragma unroll
               for (int j = 0; j < 8; ++j) {
                 const uint32_t own = r[g * 8 + j];
@@ -550,20 +550,14 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_kernel(const MlpArgs args) {
                 const float h = softplus100<true>(fmaf(aval, k1, bb[j]), sgm);
                 const float adot = __uint_as_float(own) * kInvWeightScale;
                 outv[j] = t2 ? sgm * adot : h;
-                st2[j] = t2 ? adot : sgm;
               }
               if (l < 7) store_group<NTERMS, T>(dst_hi, dst_lo, row, sub * 2 + g, outv);
 #pragma unroll
-              for (int j = 0; j < 4; ++j) {
-                pu[g * 4 + j] = Elem<__half>::pack2(outv[2 * j], outv[2 * j + 1]);
-                ps[g * 4 + j] = Elem<__half>::pack2(st2[2 * j], st2[2 * j + 1]);
-              }
+              for (int j = 0; j < 4; ++j) pu[g * 4 + j] = Elem<__half>::pack2(outv[2 * j], outv[2 * j + 1]);
             }
-            if (okp) {
+            if (okp && !(args.dbg_flags & 8)) {
               const size_t plane_u = (size_t)l * 2 * (size_t)args.P * 256;
-              const size_t plane_s = (size_t)l * (size_t)args.P * 256;
               stg256(args.st_u + plane_u + (size_t)rowg * 256 + col0, pu);
-              stg256((t2 ? args.st_adot : args.st_sig) + plane_s + (size_t)pt * 256 + col0, ps);
             }
           } else if (MODE == 0) {
 #pragma unroll
@@ -794,15 +788,15 @@ extern "C" int emap_udf_forward_grad(const emap_net_desc* net, const void* packe
 extern "C" int emap_bwd_dual_forward(const emap_net_desc* net, const void* packed, int precision,
                                      const float* pts, const float* rays_o, const float* rays_d,
                                      const float* z, int32_t n_per_ray, int64_t P, const float* d_grad,
-                                     void* st_u0, void* st_u, void* st_sig, void* st_adot, void* stream) {
+                                     void* st_u0, void* st_u, void* stream) {
   if (check_net(net)) return 1;
-  if (!packed || !st_u0 || !st_u || !st_sig || !st_adot) return set_error("emap_bwd_dual_forward: NULL pointer");
+  if (!packed || !st_u0 || !st_u) return set_error("emap_bwd_dual_forward: NULL pointer");
   if (check_points(pts, rays_o, rays_d, z, n_per_ray, P)) return 1;
   MlpArgs a;
   memset(&a, 0, sizeof(a));
   a.packed = (const uint8_t*)packed; a.pts = pts; a.rays_o = rays_o; a.rays_d = rays_d; a.z = z;
   a.n_per_ray = n_per_ray; a.P = P; a.gbar = d_grad;
-  a.st_u0 = (__half*)st_u0; a.st_u = (__half*)st_u; a.st_sig = (__half*)st_sig; a.st_adot = (__half*)st_adot;
+  a.st_u0 = (__half*)st_u0; a.st_u = (__half*)st_u;
   return dispatch<2>(net, precision, a, (cudaStream_t)stream);
 }
 

@@ -307,17 +307,15 @@ def udf_backward(net: PackedNet, precision: int, d_udf: Optional[torch.Tensor],
         boff.append(off)
         off += out_dim[l] * (2 + in_dim[l])
 
-    st_u0, st_u = h16(2 * P, 64), h16(8, 2 * P, 256)
-    st_sig, st_adot, st_a = h16(8, P, 256), h16(8, P, 256), h16(8, 2 * P, 256)
+    st_u0, st_u, st_a = h16(2 * P, 64), h16(8, 2 * P, 256), h16(8, 2 * P, 256)
     C.check(L.emap_bwd_dual_forward(desc, C.ptr(net.packed), C.PREC_HALF, C.ptr(pts), C.ptr(ro), C.ptr(rd),
                                     C.ptr(zz), n, P, C.ptr(None if d_grad is None else C.f32(d_grad)),
-                                    C.ptr(st_u0), C.ptr(st_u), C.ptr(st_sig), C.ptr(st_adot), st))
+                                    C.ptr(st_u0), C.ptr(st_u), st))
     coef = torch.empty(2 * P, dtype=torch.float32, device=dev)
     U8 = st_u[7]
     C.check(L.emap_bwd_top(desc, C.ptr(U8), C.ptr(W[8].reshape(-1)), C.ptr(flat_params[boff[8]:boff[8] + 1]),
                            C.ptr(None if d_udf is None else C.f32(d_udf)), P, None, C.ptr(coef), st))
-    C.check(L.emap_bwd_reverse_sweep(desc, C.ptr(net.packed), C.ptr(coef), C.ptr(st_sig), C.ptr(st_adot),
-                                     C.ptr(st_a), P, st))
+    C.check(L.emap_bwd_reverse_sweep(desc, C.ptr(net.packed), C.ptr(coef), C.ptr(st_u), C.ptr(st_a), P, st))
     cols, refs = _pe_perm(net.multires, dev)
     dW, db = [None] * 9, [None] * 9
     dW[8] = torch.mm(coef.to(torch.float16).view(1, 2 * P), U8, out_dtype=torch.float32)

@@ -88,17 +88,18 @@ int emap_bwd_act_bwd(const float* eta /*[2P,ld]*/, int32_t ld, float mul, int64_
                      const void* sig_half, const void* adot_half, void* A_half /*[2P,256]*/, void* stream);
 /* Fused tensor-core stages of K1b (hand-written tcgen05 kernels on the K1 skeleton):
  *  emap_bwd_dual_forward : layers 0..7 of the dual network (value + ONE tangent along d_grad) with
- *     fp16 stashes  st_u0[2P,64] (dual PE, kernel column order), st_u[8][2P,256] (inputs of layers 1..8),
- *     st_sig[8][P,256], st_adot[8][P,256].
- *  emap_bwd_reverse_sweep: layers 7..0 of the reverse sweep from coef[2P] (emap_bwd_top) and the stashes;
+ *     fp16 stashes  st_u0[2P,64] (dual PE, kernel column order), st_u[8][2P,256] (inputs of layers 1..8:
+ *     h_{l+1} in rows [0,P), hdot_{l+1} in rows [P,2P)).  No sigma / adot stash is needed:
+ *     softplus'(a_l) = 1 - exp(-100 h_{l+1}) and adot_l softplus''(a_l) = 100 hdot_{l+1} (1 - sigma_l).
+ *  emap_bwd_reverse_sweep: layers 7..0 of the reverse sweep from coef[2P] (emap_bwd_top) and st_u;
  *     writes st_a[8][2P,256] = [alpha_l ; alphadot_l].  The weight gradients are then the plain GEMMs
  *     dW_l = A_l^T U_l (library) and emap_bwd_weight_norm.                                            */
 int emap_bwd_dual_forward(const emap_net_desc* net, const void* packed, int precision,
                           const float* pts, const float* rays_o, const float* rays_d, const float* z,
                           int32_t n_per_ray, int64_t P, const float* d_grad, void* st_u0, void* st_u,
-                          void* st_sig, void* st_adot, void* stream);
+                          void* stream);
 int emap_bwd_reverse_sweep(const emap_net_desc* net, const void* packed, const float* coef,
-                           const void* st_sig, const void* st_adot, void* st_a, int64_t P, void* stream);
+                           const void* st_u, void* st_a, int64_t P, void* stream);
 /* weight-norm backward + scatter into the flat gradient (same layout as the flat parameters).
  * dW[l]: fp32 [out_l, ldw[l]] (d/dW_eff, times mul[l]); db[l]: fp32 [out_l].                       */
 int emap_bwd_weight_norm(const emap_net_desc* net, const float* flat_params, const float* const* dW,

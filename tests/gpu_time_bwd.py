@@ -23,10 +23,10 @@ del os.environ["EMAP_BWD"]
 L = C.lib(); desc = ctypes.byref(net.desc); st = C.stream()
 h16 = lambda *s: torch.empty(*s, dtype=torch.float16, device="cuda")
 st_u0, st_u = h16(2 * P, 64), h16(8, 2 * P, 256)
-st_sig, st_adot, st_a = h16(8, P, 256), h16(8, P, 256), h16(8, 2 * P, 256)
+st_a = h16(8, 2 * P, 256)
 coef = torch.randn(2 * P, device="cuda")
-print("dual forward kernel:", round(t(lambda: C.check(L.emap_bwd_dual_forward(desc, C.ptr(net.packed), 1, C.ptr(x), None, None, None, 0, P, C.ptr(dg), C.ptr(st_u0), C.ptr(st_u), C.ptr(st_sig), C.ptr(st_adot), st))), 2), "ms")
-print("reverse sweep kernel:", round(t(lambda: C.check(L.emap_bwd_reverse_sweep(desc, C.ptr(net.packed), C.ptr(coef), C.ptr(st_sig), C.ptr(st_adot), C.ptr(st_a), P, st))), 2), "ms")
+print("dual forward kernel:", round(t(lambda: C.check(L.emap_bwd_dual_forward(desc, C.ptr(net.packed), 1, C.ptr(x), None, None, None, 0, P, C.ptr(dg), C.ptr(st_u0), C.ptr(st_u), st))), 2), "ms")
+print("reverse sweep kernel:", round(t(lambda: C.check(L.emap_bwd_reverse_sweep(desc, C.ptr(net.packed), C.ptr(coef), C.ptr(st_u), C.ptr(st_a), P, st))), 2), "ms")
 A = st_a[3]; U = st_u[2]
 print("one dW GEMM [256x2M]@[2Mx256] (torch.mm fp16->fp32):", round(t(lambda: torch.mm(A.t(), U, out_dtype=torch.float32)), 2), "ms")
 print("one db sum:", round(t(lambda: A[:P].sum(dim=0, dtype=torch.float32)), 2), "ms")
