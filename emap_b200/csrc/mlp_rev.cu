@@ -170,15 +170,21 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_rev_kernel(const Args args) {
       for (int j = -1; j < kRevLayers; ++j) {
         const int lt = 6 - j;                   // layer whose A_l = [alpha ; alphadot] this stage produces
         const int buf = j & 1;
+        // the stash reads of this stage do not depend on the MMA: issue them before waiting for it
+        uint32_t uw_all[4][8];
+        {
+          const __half* u_pre = args.st_u + (size_t)lt * 2 * P * 256 + rowg * 256 + sub * 16;
+#pragma unroll
+          for (int c4 = 0; c4 < 4; ++c4) ldg256(u_pre + c4 * 64, uw_all[c4]);
+        }
         if (j >= 0) {
           mbar_wait(&acc_full[buf], ((uint32_t)iter * (buf ? 3u : 4u) + (uint32_t)(j >> 1)) & 1, 500 + buf, j);
           tc_fence_after();
         }
         // own row of U_{lt+1}: h (value lane) or hdot (tangent lane); the partner's comes by shuffle
-        const __half* u_l = args.st_u + (size_t)lt * 2 * P * 256 + rowg * 256;
         __half* a_out = args.st_a + (size_t)lt * 2 * P * 256 + rowg * 256;
         const int ncols = (lt == kSkipLayer - 1) ? out3 : 256;
-#pragma unroll 1
+#pragma unroll
         for (int chunk = 0; chunk < 4; ++chunk) {
           const int col0 = chunk * 64 + sub * 16;
           float own[16];
@@ -196,8 +202,8 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_rev_kernel(const Args args) {
               own[k] = cf * w.x; own[k + 1] = cf * w.y; own[k + 2] = cf * w.z; own[k + 3] = cf * w.w;
             }
           }
-          uint32_t uw[8], outp[8];
-          ldg256(u_l + col0, uw);
+          uint32_t outp[8];
+          const uint32_t (&uw)[8] = uw_all[chunk];
 #pragma unroll
           for (int g = 0; g < 2; ++g) {
             float v[8];

@@ -320,9 +320,10 @@ def udf_backward(net: PackedNet, precision: int, d_udf: Optional[torch.Tensor],
     dW, db = [None] * 9, [None] * 9
     dW[8] = torch.mm(coef.to(torch.float16).view(1, 2 * P), U8, out_dtype=torch.float32)
     db[8] = coef[:P].sum().reshape(1)
+    db_all = st_a[:, :P].sum(dim=1, dtype=torch.float32)                  # [8,256] in one pass
     for l in range(8):
         A = st_a[l]
-        db[l] = A[:P].sum(dim=0, dtype=torch.float32)
+        db[l] = db_all[l]
         if l == 0:
             dk = torch.mm(A.t(), st_u0, out_dtype=torch.float32)              # [256,64] kernel PE order
             d0 = torch.zeros(256, pe, dtype=torch.float32, device=dev)
