@@ -24,15 +24,15 @@ constexpr int kProducerWarp = kEpiWarps;
 constexpr int kMmaWarp = kEpiWarps + 1;
 constexpr int kThreads = (kEpiWarps + 2) * 32;
 constexpr int kChunkBytes = 16384;
-constexpr int kStages = 8;
+constexpr int kStages = 4;             // ring stages of 32 KiB: one [256 x 64] W^T operand (both N halves)
+constexpr int kRingStageBytes = 2 * kStageBytes;
 constexpr int kRevLayers = 7;          // MMA layers l = 7..1
-constexpr int kRevItems = kRevLayers * 4 * 2;
+constexpr int kRevParts = kRevLayers * 4;
 
 struct Smem {
   static constexpr int a = 0;                                   // [4 chunks][128 x 64] fp16 SW128
   static constexpr int ring = a + 4 * kChunkBytes;
-  static constexpr int items = ring + kStages * kStageBytes;
-  static constexpr int bars = items + 64 * (int)sizeof(RingItem);
+  static constexpr int bars = ring + kStages * kRingStageBytes;
   static constexpr int total = bars + 256 + 1024;
 };
 
@@ -67,7 +67,6 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_rev_kernel(const Args args) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int out3 = (int)hdr->out_dim[kSkipLayer - 1];          // 256 - pe: valid columns of alpha_3
 
-  RingItem* s_items = reinterpret_cast<RingItem*>(smem + Smem::items);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Smem::bars);
   uint64_t* full = bars;            // [8]
   uint64_t* empty = bars + 8;       // [8]
@@ -76,11 +75,6 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_rev_kernel(const Args args) {
   uint64_t* acc_empty = bars + 22;  // [2]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 25);
 
-  {
-    const uint4* src = reinterpret_cast<const uint4*>(args.packed + hdr->reserved[0]);
-    uint4* dst = reinterpret_cast<uint4*>(s_items);
-    for (int i = threadIdx.x; i < kRevItems; i += kThreads) dst[i] = src[i];
-  }
   if (warp == kProducerWarp && lane == 0) {
     for (int s = 0; s < kStages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
     for (int c = 0; c < 4; ++c) mbar_init(&a_ready[c], kEpiWarps);
@@ -94,52 +88,52 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_rev_kernel(const Args args) {
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp == kProducerWarp) {
-    if (lane == 0) {
-      uint32_t g = 0;
-      uint8_t* ring = smem + Smem::ring;
-      for (int iter = 0; iter < args.iters; ++iter) {
+    // W_l^T images, l = 7..1, K chunk by K chunk, are contiguous from hdr->reserved[2] (pack.cu:
+    // build_rev_items): one 32 KiB bulk copy per (layer, K chunk); uniform control flow, elected issue.
+    const uint8_t* img = args.packed + hdr->reserved[2];
+    uint8_t* ring = smem + Smem::ring;
+    uint32_t stage = 0, round = 0;
+    for (int iter = 0; iter < args.iters; ++iter) {
 #pragma unroll 1
-        for (int i = 0; i < kRevItems; ++i, ++g) {
-          const uint32_t s = g & (kStages - 1), use = g / kStages;
-          const uint4 raw = reinterpret_cast<const uint4*>(s_items)[i];
-          if (use > 0) mbar_wait(&empty[s], (use - 1) & 1, 100 + s, (int)g);
-          mbar_arrive_expect_tx(&full[s], kStageBytes);
-          bulk_g2s(ring + s * kStageBytes, args.packed + raw.x, kStageBytes, &full[s]);
+      for (int i = 0; i < kRevParts; ++i) {
+        if (round > 0) mbar_wait(&empty[stage], (round - 1) & 1, 100 + (int)stage, i);
+        if (elect_one()) {
+          mbar_arrive_expect_tx(&full[stage], kRingStageBytes);
+          bulk_g2s(ring + stage * kRingStageBytes, img + (size_t)i * kRingStageBytes, kRingStageBytes, &full[stage]);
         }
+        __syncwarp();
+        if (++stage == (uint32_t)kStages) { stage = 0; ++round; }
       }
     }
   } else if (warp == kMmaWarp) {
     const uint32_t a_addr = smem_u32(smem + Smem::a);
     const uint32_t ring_addr = smem_u32(smem + Smem::ring);
     const uint32_t idesc = make_idesc_f16(128, 256, 0);
-    uint32_t g = 0;
+    uint32_t stage = 0, round = 0;
     for (int iter = 0; iter < args.iters; ++iter) {
 #pragma unroll
       for (int j = 0; j < kRevLayers; ++j) {
         const int buf = j & 1;
         {
           const uint32_t started = (uint32_t)iter * (buf ? 3u : 4u) + (uint32_t)(j >> 1);
-          if (started > 0) mbar_wait(&acc_empty[buf], (started - 1) & 1, 200 + buf, (int)g);
+          if (started > 0) mbar_wait(&acc_empty[buf], (started - 1) & 1, 200 + buf, j);
         }
         const uint32_t d = tmem_base + (uint32_t)buf * 256u;
 #pragma unroll
         for (int kc = 0; kc < 4; ++kc) {
-          mbar_wait(&a_ready[kc], ((uint32_t)iter * 7u + (uint32_t)j) & 1, 300 + kc, (int)g);
-          const uint32_t s = g & (kStages - 1), use = g / kStages;
-          mbar_wait(&full[s], use & 1, 400 + s, (int)g);
-          mbar_wait(&full[s + 1], use & 1, 410 + s, (int)g);
+          mbar_wait(&a_ready[kc], ((uint32_t)iter * 7u + (uint32_t)j) & 1, 300 + kc, j);
+          mbar_wait(&full[stage], round & 1, 400 + (int)stage, j * 4 + kc);
           tc_fence_after();
           const uint64_t adesc = make_sw128_kmajor_desc(a_addr + kc * kChunkBytes);
-          const uint64_t bdesc = make_sw128_kmajor_desc(ring_addr + s * kStageBytes);
+          const uint64_t bdesc = make_sw128_kmajor_desc(ring_addr + stage * kRingStageBytes);
           if (elect_one()) {
 #pragma unroll
             for (int k = 0; k < 4; ++k)
               umma_f16(d, adesc + 2 * k, bdesc + 2 * k, idesc, (kc == 0 && k == 0) ? 0u : 1u);
-            umma_commit(&empty[s]);
-            umma_commit(&empty[s + 1]);
+            umma_commit(&empty[stage]);
           }
           __syncwarp();
-          g += 2;
+          if (++stage == (uint32_t)kStages) { stage = 0; ++round; }
         }
         if (elect_one()) umma_commit(&acc_full[buf]);
         __syncwarp();

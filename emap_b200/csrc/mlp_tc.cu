@@ -6,12 +6,14 @@
 //   src/models/udf_model.py:121-135   UDFNetwork.gradient      -> MODE_GRAD (forward-mode tangents)
 //
 // Dataflow (one persistent CTA per SM, 10 warps, warp-specialised):
-//   warp 8   : producer -- streams the pre-swizzled weight images (pack.cu) from L2 into a ring of
-//              16 KiB stages with 1-D bulk copies (TMA engine, SASS UBLKCP), mbarrier tx-count.
-//   warp 9   : MMA issuer -- one thread issues tcgen05.mma (M=128, N<=128, K=16, kind::f16) with
-//              A = activation tile in shared memory (K-major, 128B swizzle), B = weight stage,
+//   warp 16  : producer -- streams the pre-swizzled weight images (pack.cu) from L2 into a ring of
+//              32 KiB stages (one [256 x 64] N x K operand = both N halves of one part) with 1-D bulk
+//              copies (TMA engine, SASS UBLKCP), mbarrier tx-count.  The schedule is a fixed function
+//              of (layer, K chunk, part): no table, one elected lane, ~20 instructions per copy.
+//   warp 17  : MMA issuer -- one elected thread issues tcgen05.mma (M=128, N=256, K=16, kind::f16)
+//              with A = activation tile in shared memory (K-major, 128B swizzle), B = weight stage,
 //              D = fp32 accumulator in TMEM (two 256-column buffers, ping-pong across layers).
-//   warps 0-7: epilogue -- tcgen05.ld the accumulator, softplus (beta=100) in fp32, convert to
+//   warps 0-15: epilogue -- tcgen05.ld the accumulator, softplus (beta=100) in fp32, convert to
 //              fp16 (hi [+ lo]) and write the NEXT layer's A tile in place, 64-column chunk by chunk;
 //              the MMA of layer l+1 starts on chunk c as soon as it is written, so it overlaps the
 //              epilogue of layer l.  Activations never leave the SM.
@@ -61,18 +63,22 @@ struct MlpArgs {
   int dbg_flags;        // timing experiments only: 1 = no MMA issue, 2 = no weight copies, 4 = no epilogue math
 };
 
+constexpr int kRingStageBytes = 2 * kStageBytes;   // one part: [256 x 64] 16-bit SW128 image (N halves adjacent)
+
 template <int NTERMS, int MODE>
 struct SmemPlan {
-  // fp32x3: A_hi + A_lo = 128 KiB, ring 4-5 x 16 KiB; single-MMA modes: A = 64 KiB, ring 8 x 16 KiB.
+  // fp32x3: A_hi + A_lo = 128 KiB, ring 3 x 32 KiB; single-MMA modes: A = 64 KiB, ring 4 x 32 KiB.
   // (The PE chunk is not kept resident: it is written into activation chunk 0 for layer 0 and
-  //  re-generated there for the skip term of layer 4 -- that frees 32 KiB for the weight ring.)
-  static constexpr int kStages = (NTERMS == 3) ? 4 : 8;      // power of two: stage = item & (kStages-1)
+  //  re-generated there for the skip term of layer 4.  The weight schedule is computed, not tabled.
+  //  In fp32x3 MODE_GRAD the value->tangent exchange scratch aliases the destination chunk -- see the
+  //  epilogue -- so that the third ring stage fits.)
+  static constexpr int kStages = (NTERMS == 3) ? 3 : 4;
+  static constexpr bool kOwnScratch = (MODE == 1 && NTERMS == 1);
   static constexpr int a_hi = 0;
   static constexpr int a_lo = a_hi + 4 * kChunkBytes;
   static constexpr int ring = a_lo + ((NTERMS == 3) ? 4 * kChunkBytes : 0);
-  static constexpr int scratch = ring + kStages * kStageBytes;
-  static constexpr int items = scratch + ((MODE == 1) ? kEpiWarps * kScratchFloatsPerWarp * 4 : 0);
-  static constexpr int bars = items + kMaxItems * (int)sizeof(RingItem);
+  static constexpr int scratch = ring + kStages * kRingStageBytes;
+  static constexpr int bars = scratch + (kOwnScratch ? kEpiWarps * kScratchFloatsPerWarp * 4 : 0);
   static constexpr int total = bars + 256 + 1024;   // +1 KiB slack to 1024-align the base
 };
 static_assert(SmemPlan<3, 1>::total <= 232448 && SmemPlan<3, 0>::total <= 232448 &&
@@ -308,29 +314,20 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_kernel(const MlpArgs args) {
   const PackedHeader* hdr = reinterpret_cast<const PackedHeader*>(args.packed);
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const int tix = (NTERMS == 3) ? 1 : 0;
-  // MODE_DUAL runs layers 0..7 only: drop the output layer's items (4 K chunks x parts) from the stream
-  const int n_items = (int)hdr->n_items[tix] - ((MODE == 2) ? ((NTERMS == 3) ? 8 : 4) : 0);
   const int multires = (int)hdr->multires;
   const float net_scale = hdr->scale;
   const int udf_type = (int)hdr->udf_type;
   const float* bias100 = reinterpret_cast<const float*>(args.packed + hdr->bias100_off);
 
-  RingItem* s_items = reinterpret_cast<RingItem*>(smem + Plan::items);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Plan::bars);
-  uint64_t* full = bars;                  // [8]
-  uint64_t* empty = bars + 8;             // [8]
+  uint64_t* full = bars;                  // [kStages]
+  uint64_t* empty = bars + 8;             // [kStages]
   uint64_t* a_ready = bars + 16;          // [5]  (index 4 = PE written into chunk 0)
   uint64_t* acc_full = bars + 21;         // [2]
   uint64_t* acc_empty = bars + 23;        // [2]
   uint64_t* c0_free = bars + 25;          // layer 4 has consumed chunk 0 -> PE may be regenerated there
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 27);
 
-  {
-    const uint4* src = reinterpret_cast<const uint4*>(args.packed + hdr->items_off[tix]);
-    uint4* dst = reinterpret_cast<uint4*>(s_items);
-    for (int i = threadIdx.x; i < n_items; i += kThreads) dst[i] = src[i];
-  }
   if (warp == kProducerWarp && lane == 0) {
     for (int s = 0; s < kStages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], CL); }
     for (int c = 0; c < 4; ++c) mbar_init(&a_ready[c], kEpiWarps);
@@ -344,53 +341,63 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_kernel(const MlpArgs args) {
   if (CL > 1) cluster_sync_all(); else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  constexpr int kParts = (NTERMS == 3) ? 2 : 1;
 
   if (warp == kProducerWarp) {
     // ===================================== producer =====================================
-    if (lane == 0) {
-      const uint32_t rank = (CL > 1) ? cluster_ctarank() : 0;
-      uint32_t g = 0;
-      uint8_t* ring = smem + Plan::ring;
-      for (int iter = 0; iter < args.iters; ++iter) {
+    // The weight stream of a tile is a fixed function of the schedule (pack.cu: layer -> K chunk ->
+    // hi/lo part, both N halves of a part adjacent in memory): one 32 KiB bulk copy per part (2 KiB for
+    // the N=16 output layer).  Uniform control flow, the copy itself issued by one elected lane.
+    const uint32_t rank = (CL > 1) ? cluster_ctarank() : 0;
+    const uint8_t* img = args.packed + hdr->images_off;
+    uint8_t* ring = smem + Plan::ring;
+    const bool no_copy = (args.dbg_flags & 2) != 0;
+    uint32_t stage = 0, round = 0;
+    for (int iter = 0; iter < args.iters; ++iter) {
+      uint32_t off = 0;
 #pragma unroll 1
-        for (int i = 0; i < n_items; ++i, ++g) {
-          const uint32_t s = g & (kStages - 1), use = g / kStages;
-          const uint4 raw = reinterpret_cast<const uint4*>(s_items)[i];
-          const uint32_t bytes = (raw.y & 0xffffu) * 16u;
-          const bool stp = args.dbg_clk && blockIdx.x == 0 && iter == 1 && i >= 24 && i < 28;
-          if (stp) args.dbg_clk[152 + (i - 24) * 3 + 0] = clock64();
-          if (use > 0) mbar_wait(&empty[s], (use - 1) & 1, 100 + s, (int)g);
-          if (stp) args.dbg_clk[152 + (i - 24) * 3 + 1] = clock64();
-          if (args.dbg_flags & 2) { mbar_arrive(&full[s]); continue; }
-          mbar_arrive_expect_tx(&full[s], bytes);
-          uint8_t* dst = ring + s * kStageBytes;
-          const uint8_t* src = args.packed + raw.x;
-          if (CL == 1) {
-            bulk_g2s(dst, src, bytes, &full[s]);
-          } else {
-            const uint32_t slice = bytes / CL;
-            bulk_g2s_multicast(dst + rank * slice, src + rank * slice, slice, &full[s],
-                               (uint16_t)((1u << CL) - 1));
+      for (int l = 0; l < MI::kLayers; ++l) {
+        const int nkc = (l == 0) ? 1 : ((l == kSkipLayer) ? 5 : 4);
+        const uint32_t bytes = (l == kNumLinear - 1) ? 2048u : (uint32_t)kRingStageBytes;
+#pragma unroll 1
+        for (int ip = 0; ip < nkc * 2; ++ip, off += bytes) {
+          if (NTERMS == 1 && (ip & 1)) continue;          // single-MMA modes stream the hi images only
+          if (round > 0) mbar_wait(&empty[stage], (round - 1) & 1, 100 + (int)stage, l * 16 + ip);
+          if (elect_one()) {
+            if (no_copy) {
+              mbar_arrive(&full[stage]);
+            } else {
+              mbar_arrive_expect_tx(&full[stage], bytes);
+              uint8_t* dst = ring + stage * kRingStageBytes;
+              const uint8_t* src = img + off;
+              if (CL == 1) {
+                bulk_g2s(dst, src, bytes, &full[stage]);
+              } else {
+                const uint32_t slice = bytes / CL;
+                bulk_g2s_multicast(dst + rank * slice, src + rank * slice, slice, &full[stage],
+                                   (uint16_t)((1u << CL) - 1));
+              }
+            }
           }
-          if (stp) args.dbg_clk[152 + (i - 24) * 3 + 2] = clock64();
+          __syncwarp();
+          if (++stage == (uint32_t)kStages) { stage = 0; ++round; }
         }
       }
     }
   } else if (warp == kMmaWarp) {
     // ===================================== MMA issuer ===================================
     // One warp, uniform control flow, the instructions themselves issued by one elected lane (so
-    // descriptors live in uniform registers).  The weight stream is a fixed schedule (pack.cu: layer ->
-    // K chunk -> hi/lo part -> N half); the two N halves of a part sit in adjacent ring stages and are
-    // consumed by N=256 MMAs.  (Measured before this structure: a table-driven issuer under `lane==0`
-    // paid ~95 clk per tcgen05.mma and ~600 clk of loop overhead per 16 KiB item.)
+    // descriptors live in uniform registers).  Fixed schedule: layer -> K chunk -> hi/lo part; one ring
+    // stage = one part = the B operand of N=256 MMAs.  (Measured before this structure: a table-driven
+    // issuer under `lane==0` paid ~95 clk per tcgen05.mma and ~600 clk of loop overhead per item; 16 KiB
+    // stages consumed in pairs left only two parts in flight and made the producer the bottleneck.)
     const uint32_t a_hi_addr = smem_u32(smem + Plan::a_hi);
     const uint32_t a_lo_addr = smem_u32(smem + Plan::a_lo);
     const uint32_t ring_addr = smem_u32(smem + Plan::ring);
     const uint32_t idesc256 = make_idesc_f16(128, 256, Elem<T>::fmt);
     const uint32_t idesc16 = make_idesc_f16(128, 16, Elem<T>::fmt);
     const bool no_mma = (args.dbg_flags & 1) != 0;
-    constexpr int kParts = (NTERMS == 3) ? 2 : 1;
-    uint32_t g = 0;
+    uint32_t stage = 0, round = 0;
     for (int iter = 0; iter < args.iters; ++iter) {
 #pragma unroll
       for (int l = 0; l < MI::kLayers; ++l) {
@@ -399,7 +406,7 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_kernel(const MlpArgs args) {
         if (stamp) args.dbg_clk[72 + l * 8 + 0] = clock64();
         {
           const uint32_t started = (uint32_t)iter * (buf ? 4u : (uint32_t)MI::kUses0) + (uint32_t)(l >> 1);
-          if (started > 0) mbar_wait(&acc_empty[buf], (started - 1) & 1, 200 + buf, (int)g);
+          if (started > 0) mbar_wait(&acc_empty[buf], (started - 1) & 1, 200 + buf, l);
         }
         if (stamp) args.dbg_clk[72 + l * 8 + 1] = clock64();
         const int nkc = (l == 0) ? 1 : ((l == kSkipLayer) ? 5 : 4);
@@ -412,7 +419,7 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_kernel(const MlpArgs args) {
           {
             const uint32_t uses = (c == 4) ? (uint32_t)iter * 2u + (l == kSkipLayer ? 1u : 0u)
                                            : (uint32_t)iter * (uint32_t)MI::kAPerTile + (uint32_t)(l - 1);
-            mbar_wait(&a_ready[c], uses & 1, 300 + c, (int)g);
+            mbar_wait(&a_ready[c], uses & 1, 300 + c, l);
           }
           tc_fence_after();
           if (stamp && ic < 4) args.dbg_clk[72 + l * 8 + 2 + ic] = clock64();
@@ -421,14 +428,12 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_kernel(const MlpArgs args) {
           const uint64_t alo = make_sw128_kmajor_desc(a_lo_addr + coff);
 #pragma unroll
           for (int part = 0; part < kParts; ++part) {
-            const uint32_t s = g & (kStages - 1), use = g / kStages;
             const bool st2 = stamp && l == 2 && ic == 1;
             if (st2) args.dbg_clk[144 + part * 4 + 0] = clock64();
-            mbar_wait(&full[s], use & 1, 400 + s, (int)g);
-            if (!last) mbar_wait(&full[s + 1], use & 1, 410 + s, (int)g);
+            mbar_wait(&full[stage], round & 1, 400 + (int)stage, l * 16 + ic * 2 + part);
             tc_fence_after();
             if (st2) args.dbg_clk[144 + part * 4 + 1] = clock64();
-            const uint64_t bdesc = make_sw128_kmajor_desc(ring_addr + s * kStageBytes);
+            const uint64_t bdesc = make_sw128_kmajor_desc(ring_addr + stage * kRingStageBytes);
             if (elect_one()) {
               if (!no_mma) {
                 if (part == 0) {
@@ -444,17 +449,12 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_kernel(const MlpArgs args) {
                   for (int k = 0; k < 4; ++k) umma_f16(d, ahi + 2 * k, bdesc + 2 * k, idesc, 1u);
                 }
               }
-              if (CL == 1) {
-                umma_commit(&empty[s]);
-                if (!last) umma_commit(&empty[s + 1]);
-              } else {
-                umma_commit_multicast(&empty[s], (uint16_t)((1u << CL) - 1));
-                if (!last) umma_commit_multicast(&empty[s + 1], (uint16_t)((1u << CL) - 1));
-              }
+              if (CL == 1) umma_commit(&empty[stage]);
+              else umma_commit_multicast(&empty[stage], (uint16_t)((1u << CL) - 1));
             }
             __syncwarp();
             if (st2) args.dbg_clk[144 + part * 4 + 2] = clock64();
-            g += last ? 1u : 2u;
+            if (++stage == (uint32_t)kStages) { stage = 0; ++round; }
           }
           if (l == kSkipLayer && ic == 0) { if (elect_one()) umma_commit(c0_free); __syncwarp(); }
         }
@@ -473,7 +473,7 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_kernel(const MlpArgs args) {
     const uint32_t lane_taddr = tmem_base + ((uint32_t)(q * 32) << 16);
     uint8_t* A_hi = smem + Plan::a_hi;
     uint8_t* A_lo = smem + Plan::a_lo;
-    float* sc = reinterpret_cast<float*>(smem + Plan::scratch) + warp * kScratchFloatsPerWarp;
+    float* sc = reinterpret_cast<float*>(smem + Plan::scratch) + warp * kScratchFloatsPerWarp;   // kOwnScratch only
     const float k1 = kSoftplusBeta * kInvWeightScale;
     const int p8 = lane >> 2, ty = lane & 3;       // MODE_GRAD: point-in-warp, row type
     const float b8 = bias100[8 * kHidden];
@@ -528,32 +528,42 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_kernel(const MlpArgs args) {
           if (args.dbg_flags & 4) {
             // timing experiment: no epilogue math / stores
           } else if (MODE == 2) {
-            // dual rows (lane pair = value, tangent).  The tangent lane fetches its partner's value
-            // accumulator, both lanes run the same softplus/sigmoid stream; value lane keeps h, tangent
-            // lane keeps sigma * adot.  Everything is also stashed (fp16, row-major) for the reverse sweep.
+            // dual rows (lane pair = value, tangent).  The pair splits the transcendental work: the value
+            // lane runs softplus/sigmoid on columns 0-7 of the value accumulator, the tangent lane on
+            // columns 8-15 (fetched by shuffle); then the value lane receives h[8..15] and the tangent lane
+            // sigma[0..7].  Value lane keeps h, tangent lane keeps sigma * adot.  Everything is also
+            // stashed (fp16, row-major) for the reverse sweep.
             const int t2 = lane & 1;
             const bool okp = (tile < args.num_tiles) && (pt < args.P);
             const long long rowg = (t2 ? args.P : 0) + pt;
+            const float4 bA = __ldg(reinterpret_cast<const float4*>(bl + col0 + t2 * 8));
+            const float4 bB = __ldg(reinterpret_cast<const float4*>(bl + col0 + t2 * 8 + 4));
+            const float bb[8] = {bA.x, bA.y, bA.z, bA.w, bB.x, bB.y, bB.z, bB.w};
+            float hm[8], sm[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const uint32_t up = __shfl_xor_sync(0xffffffffu, r[8 + j], 1);   // value lane's acc[8+j]
+              const float aval = __uint_as_float(t2 ? up : r[j]);
+              hm[j] = softplus100<true>(fmaf(aval, k1, bb[j]), sm[j]);
+            }
+            float outv[16];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const float y = __shfl_xor_sync(0xffffffffu, t2 ? hm[j] : sm[j], 1);   // -> h[8+j] | sigma[j]
+              const float ad_lo = __uint_as_float(r[j]) * kInvWeightScale;
+              const float ad_hi = __uint_as_float(r[8 + j]) * kInvWeightScale;
+              outv[j] = t2 ? y * ad_lo : hm[j];
+              outv[8 + j] = t2 ? sm[j] * ad_hi : y;
+            }
             uint32_t pu[8];                              // 16 columns = 32 B per stash row
 #pragma unroll
             for (int g = 0; g < 2; ++g) {
-              const float4 bA = __ldg(reinterpret_cast<const float4*>(bl + col0 + g * 8));
-              const float4 bB = __ldg(reinterpret_cast<const float4*>(bl + col0 + g * 8 + 4));
-              const float bb[8] = {bA.x, bA.y, bA.z, bA.w, bB.x, bB.y, bB.z, bB.w};
-              float outv[8];
+              float v8[8];
 #pragma unroll
-              for (int j = 0; j < 8; ++j) {
-                const uint32_t own = r[g * 8 + j];
-                const uint32_t oth = __shfl_xor_sync(0xffffffffu, own, 1);
-                const float aval = __uint_as_float(t2 ? oth : own);
-                float sgm;
-                const float h = softplus100<true>(fmaf(aval, k1, bb[j]), sgm);
-                const float adot = __uint_as_float(own) * kInvWeightScale;
-                outv[j] = t2 ? sgm * adot : h;
-              }
-              if (l < 7) store_group<NTERMS, T>(dst_hi, dst_lo, row, sub * 2 + g, outv);
+              for (int j = 0; j < 8; ++j) v8[j] = outv[g * 8 + j];
+              if (l < 7) store_group<NTERMS, T>(dst_hi, dst_lo, row, sub * 2 + g, v8);
 #pragma unroll
-              for (int j = 0; j < 4; ++j) pu[g * 4 + j] = Elem<__half>::pack2(outv[2 * j], outv[2 * j + 1]);
+              for (int j = 0; j < 4; ++j) pu[g * 4 + j] = Elem<__half>::pack2(v8[2 * j], v8[2 * j + 1]);
             }
             if (okp && !(args.dbg_flags & 8)) {
               const size_t plane_u = (size_t)l * 2 * (size_t)args.P * 256;
@@ -574,18 +584,31 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_kernel(const MlpArgs args) {
               store_group<NTERMS, T>(dst_hi, dst_lo, row, sub * 2 + g, h);
             }
           } else {
+            // Exchange slots of point p8: four 16-byte slots (columns 4i..4i+3).  Single-MMA modes have a
+            // warp-private scratch; in fp32x3 mode (no shared memory to spare) the slots alias this warp's
+            // own 64 bytes of the first tangent row (hi/lo x two swizzle groups) of the DESTINATION chunk:
+            // the MMAs that read it are complete (acc_full), and phase C overwrites it last -- slots
+            // (2g, 2g+1) are exactly the hi/lo group g of that row, read by all lanes before lane ty=1
+            // stores there.
+            const int r1 = q * 32 + 4 * p8 + 1;
+            auto slot = [&](int i) -> float4* {
+              if (Plan::kOwnScratch) return reinterpret_cast<float4*>(sc + p8 * 20 + 4 * i);
+              uint8_t* base = (i & 1) ? dst_lo : dst_hi;
+              return reinterpret_cast<float4*>(base + (uint32_t)r1 * 128u +
+                                               (uint32_t)((((sub * 2 + (i >> 1)) ^ (r1 & 7)) & 7) << 4));
+            };
             // phase A: value lanes publish their raw accumulators (16 columns)
             if (ty == 0) {
 #pragma unroll
               for (int i = 0; i < 4; ++i)
-                *reinterpret_cast<float4*>(sc + p8 * 20 + 4 * i) =
-                    make_float4(__uint_as_float(r[4 * i]), __uint_as_float(r[4 * i + 1]),
-                                __uint_as_float(r[4 * i + 2]), __uint_as_float(r[4 * i + 3]));
+                *slot(i) = make_float4(__uint_as_float(r[4 * i]), __uint_as_float(r[4 * i + 1]),
+                                       __uint_as_float(r[4 * i + 2]), __uint_as_float(r[4 * i + 3]));
             }
             __syncwarp();
             // phase B: every lane does 4 columns of its point's value row
             {
-              const float4 vA = *reinterpret_cast<const float4*>(sc + p8 * 20 + 4 * ty);
+              float4* my = slot(ty);
+              const float4 vA = *my;
               const float va[4] = {vA.x, vA.y, vA.z, vA.w};
               const float4 bA = __ldg(reinterpret_cast<const float4*>(bl + col0 + 4 * ty));
               const float bb[4] = {bA.x, bA.y, bA.z, bA.w};
@@ -597,15 +620,16 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_kernel(const MlpArgs args) {
                 sg[j] = sgm * kInvWeightScale;   // tangent accumulators carry the weight pre-scale
               }
               store_half_group<NTERMS, T>(dst_hi, dst_lo, q * 32 + 4 * p8, sub * 2 + (ty >> 1), ty & 1, h);
-              *reinterpret_cast<float4*>(sc + p8 * 20 + 4 * ty) = make_float4(sg[0], sg[1], sg[2], sg[3]);
+              *my = make_float4(sg[0], sg[1], sg[2], sg[3]);
             }
             __syncwarp();
             // phase C: tangent rows: d h = sigmoid(100 a) * d a
-            if (ty != 0) {
 #pragma unroll
-              for (int g = 0; g < 2; ++g) {
-                const float4 sA = *reinterpret_cast<const float4*>(sc + p8 * 20 + 8 * g);
-                const float4 sB = *reinterpret_cast<const float4*>(sc + p8 * 20 + 8 * g + 4);
+            for (int g = 0; g < 2; ++g) {
+              const float4 sA = *slot(2 * g);
+              const float4 sB = *slot(2 * g + 1);
+              __syncwarp();                       // all lanes have read the slots before any row store
+              if (ty != 0) {
                 const float ss[8] = {sA.x, sA.y, sA.z, sA.w, sB.x, sB.y, sB.z, sB.w};
                 float tv[8];
 #pragma unroll
