@@ -35,6 +35,9 @@ import torch  # noqa: E402
 F_FWD = 918016.0                      # FLOP of one MLP forward per point
 N0, NI, STEPS = 128, 128, 4           # 256 samples per ray
 RAYS_PER_GPU = 4096
+# DRAM bytes of ONE launch of the dominant kernel (ncu --set full capture of this workload, see profiles/):
+# (precision, rays, samples) -> dram__bytes_read.sum + dram__bytes_write.sum.  None = not captured.
+NCU_DRAM_BYTES_PER_LAUNCH = {}
 
 
 def peaks():
@@ -284,6 +287,8 @@ def main():
     if rank == 0:
         sampler.start()
     C.launch_count = 0
+    C.timed_events.clear()
+    C.timed_call = "emap_udf_forward_grad"       # dominant kernel, timed live inside the timed region
     evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
            for _ in range(args.steps)]
     barrier()
@@ -293,6 +298,8 @@ def main():
         step_device()
         s1.record()
     barrier()
+    C.timed_call = None
+    k_live = [a.elapsed_time(b) for a, b in C.timed_events]
     launches = C.launch_count // args.steps
     clocks = sampler.stop() if rank == 0 else None
     ms = sum(a.elapsed_time(b) for a, b in evs) / args.steps
@@ -342,23 +349,10 @@ def main():
     d2h = B * 4 if args.mode == "infer" else 4
 
     if rank == 0:
-        # ---- roofline of the dominant kernel: fused MLP forward+gradient on the B*n core points
+        # ---- roofline of the dominant kernel (fused MLP forward+gradient on the B*n core points): its
+        # launches inside the timed region above were bracketed by CUDA events on the launching stream
         pk, pk_src = peaks()
-        with torch.no_grad():
-            out = r.render(o_d, d_d, near_f, far_f, ds_d, cos_anneal_ratio=1.0, flip_saturation=0.9)
-        mid = out["mid_z_vals"].contiguous()
-        pn = net.packed()
-        reps = 5
-        kev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(reps)]
-        for _ in range(2):
-            ops.udf_forward_grad(pn, net.prec_code, rays_o=o_d, rays_d=d_d, z=mid)
-        for a0, a1 in kev:
-            flush.fill_(1)
-            a0.record()
-            ops.udf_forward_grad(pn, net.prec_code, rays_o=o_d, rays_d=d_d, z=mid)
-            a1.record()
-        torch.cuda.synchronize()
-        k_ms = sum(a.elapsed_time(b) for a, b in kev) / reps
+        k_ms = sum(k_live) / max(len(k_live), 1)
         P = B * n
         alg_flop = 2.0 * F_FWD * P                       # forward + reverse-mode d/dx
         nterms = 3 if args.precision == "fp32" else 1
@@ -366,8 +360,13 @@ def main():
         achieved = alg_flop / (k_ms * 1e-3) / 1e12
         roof = {"bound": "tensor", "kernel": "mlp_kernel<MODE_GRAD> (emap_udf_forward_grad)",
                 "achieved": achieved, "peak": pk["bf16_tflops"], "unit": "TFLOP/s",
-                "frac": achieved / pk["bf16_tflops"], "traffic": None, "peak_source": pk_src + " burst bf16",
-                "ms_per_launch": k_ms, "points_per_launch": P,
+                "frac": achieved / pk["bf16_tflops"],
+                "traffic": NCU_DRAM_BYTES_PER_LAUNCH.get((args.precision, B, n)),
+                "traffic_source": "profiles/r01_mlp_ncu_raw.csv (ncu --set full, dram__bytes_read.sum + "
+                                  "dram__bytes_write.sum of one launch of this workload)",
+                "peak_source": pk_src + " burst bf16 (cuBLAS)",
+                "ms_per_launch": k_ms, "launches_timed": len(k_live), "points_per_launch": P,
+                "share_of_step": k_ms / ms,
                 "algorithmic_flop_per_point": 2.0 * F_FWD,
                 "executed_tflops": exe_flop / (k_ms * 1e-3) / 1e12,
                 "note": "algorithmic = 2F/point (fwd + reverse-mode grad); the kernel executes forward-mode "

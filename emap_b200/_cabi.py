@@ -75,10 +75,15 @@ LAUNCHES_PER_CALL = {
     "emap_bwd_reverse_sweep": 1,
 }
 launch_count = 0
+# bench.py: name of ONE C-ABI entry point whose launches are bracketed by CUDA events on the current
+# stream (the stream the kernel is launched on), collected in `timed_events` -- the roofline of the
+# dominant kernel is measured live inside the timed region, not in a separate loop.
+timed_call = None
+timed_events = []
 
 
 class _Counting:
-    """Proxy over the CDLL that counts kernel launches per C-ABI call."""
+    """Proxy over the CDLL that counts kernel launches per C-ABI call (and optionally times one)."""
 
     def __init__(self, cdll):
         self._cdll = cdll
@@ -90,9 +95,16 @@ class _Counting:
             raw = getattr(self._cdll, name)
             k = LAUNCHES_PER_CALL.get(name, 0)
             if k:
-                def fn(*args, _raw=raw, _k=k):
+                def fn(*args, _raw=raw, _k=k, _name=name):
                     global launch_count
                     launch_count += _k
+                    if timed_call == _name:
+                        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                        e0.record()
+                        rc = _raw(*args)
+                        e1.record()
+                        timed_events.append((e0, e1))
+                        return rc
                     return _raw(*args)
             else:
                 fn = raw

@@ -50,16 +50,6 @@ __device__ __forceinline__ uint32_t pack2h(float a, float b) {
   return *reinterpret_cast<uint32_t*>(&h);
 }
 
-// one 16-byte swizzle group (8 columns) of a row of an A-tile chunk + the same 16 bytes to the stash
-__device__ __forceinline__ void put_group(uint8_t* chunk, int row, int gidx, const float (&v)[8],
-                                          bool to_tile, __half* stash_or_null) {
-  uint4 q;
-  q.x = pack2h(v[0], v[1]); q.y = pack2h(v[2], v[3]); q.z = pack2h(v[4], v[5]); q.w = pack2h(v[6], v[7]);
-  if (to_tile)
-    *reinterpret_cast<uint4*>(chunk + (uint32_t)row * 128u + (uint32_t)(((gidx ^ (row & 7)) & 7) << 4)) = q;
-  if (stash_or_null) *reinterpret_cast<uint4*>(stash_or_null) = q;
-}
-
 __global__ void __launch_bounds__(kThreads, 1) mlp_rev_kernel(const Args args) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
@@ -196,36 +186,56 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_rev_kernel(const Args args) {
               own[k] = cf * w.x; own[k + 1] = cf * w.y; own[k + 2] = cf * w.z; own[k + 3] = cf * w.w;
             }
           }
+          // The lane pair (value row, tangent row) splits the 16 columns: the value lane evaluates columns
+          // 0-7 of BOTH rows, the tangent lane columns 8-15, so sigma = 1 - exp(-100 h) is formed once per
+          // (point, column).  12 shuffles bring the partner row's adjoints / activations for the lane's 8
+          // columns, 4 more return the packed results to the row that owns them.
           uint32_t outp[8];
           const uint32_t (&uw)[8] = uw_all[chunk];
+          float oacc[8];
+          uint32_t ou[4];
 #pragma unroll
-          for (int g = 0; g < 2; ++g) {
-            float v[8];
+          for (int k = 0; k < 8; ++k) oacc[k] = __shfl_xor_sync(0xffffffffu, t2 ? own[k] : own[8 + k], 1);
 #pragma unroll
-            for (int h2 = 0; h2 < 4; ++h2) {
-              const uint32_t uo = __shfl_xor_sync(0xffffffffu, uw[g * 4 + h2], 1);
-              const float2 mine2 = __half22float2(*reinterpret_cast<const __half2*>(&uw[g * 4 + h2]));
-              const float2 oth2 = __half22float2(*reinterpret_cast<const __half2*>(&uo));
-              // h = softplus(a) of the value row, hdot = sigma * adot of the tangent row
-              const float hv[2] = {t2 ? oth2.x : mine2.x, t2 ? oth2.y : mine2.y};
-              const float hd[2] = {t2 ? mine2.x : oth2.x, t2 ? mine2.y : oth2.y};
+          for (int w = 0; w < 4; ++w) ou[w] = __shfl_xor_sync(0xffffffffu, t2 ? uw[w] : uw[4 + w], 1);
+          uint32_t mine_p[4], send_p[4];
 #pragma unroll
-              for (int e = 0; e < 2; ++e) {
-                const int k = g * 8 + h2 * 2 + e;
-                const float mine = own[k];
-                const float other = __shfl_xor_sync(0xffffffffu, mine, 1);   // partner row's adjoint
-                // sigma = softplus'(a) = 1 - exp(-100 h);  adot * softplus''(a) = 100 * hdot * (1 - sigma)
-                const float one_m_s = __expf(-kSoftplusBeta * hv[e]);
-                const float s = 1.0f - one_m_s;
-                // value row: eta*sigma + etadot*adot*sp'' ;  tangent row: etadot*sigma
-                const float etad = t2 ? mine : other;
-                float res = mine * s;
-                if (!t2) res += etad * (kSoftplusBeta * hd[e] * one_m_s);
-                v[h2 * 2 + e] = (col0 + k < ncols && ok) ? res : 0.f;
-              }
-              outp[g * 4 + h2] = pack2h(v[h2 * 2], v[h2 * 2 + 1]);
+          for (int w = 0; w < 4; ++w) {
+            const uint32_t um = t2 ? uw[4 + w] : uw[w];            // own row, my columns
+            const float2 m2 = __half22float2(*reinterpret_cast<const __half2*>(&um));
+            const float2 o2 = __half22float2(*reinterpret_cast<const __half2*>(&ou[w]));
+            const float hv[2] = {t2 ? o2.x : m2.x, t2 ? o2.y : m2.y};   // h of the value row
+            const float hd[2] = {t2 ? m2.x : o2.x, t2 ? m2.y : o2.y};   // hdot of the tangent row
+            float al[2], ad[2];
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+              const int k = 2 * w + e;                             // column inside my half
+              const float mine = t2 ? own[8 + k] : own[k];
+              const float eta = t2 ? oacc[k] : mine;               // adjoint of the value row
+              const float etad = t2 ? mine : oacc[k];              // adjoint of the tangent row
+              // sigma = softplus'(a) = 1 - exp(-100 h);  adot * softplus''(a) = 100 * hdot * (1 - sigma)
+              const float one_m_s = __expf(-kSoftplusBeta * hv[e]);
+              const float sg = 1.0f - one_m_s;
+              const bool live = (col0 + t2 * 8 + k < ncols) && ok;
+              al[e] = live ? fmaf(etad, kSoftplusBeta * hd[e] * one_m_s, eta * sg) : 0.f;   // alpha
+              ad[e] = live ? etad * sg : 0.f;                                                // alphadot
             }
-            put_group(A + chunk * kChunkBytes, row, sub * 2 + g, v, /*to_tile=*/lt >= 1, nullptr);
+            const uint32_t pa = pack2h(al[0], al[1]), pd = pack2h(ad[0], ad[1]);
+            mine_p[w] = t2 ? pd : pa;                              // stays in my row
+            send_p[w] = t2 ? pa : pd;                              // belongs to the partner's row
+          }
+#pragma unroll
+          for (int w = 0; w < 4; ++w) {
+            const uint32_t got = __shfl_xor_sync(0xffffffffu, send_p[w], 1);
+            outp[w] = t2 ? got : mine_p[w];                        // columns 0-7 of my row
+            outp[4 + w] = t2 ? mine_p[w] : got;                    // columns 8-15
+          }
+          if (lt >= 1) {
+#pragma unroll
+            for (int g = 0; g < 2; ++g)
+              *reinterpret_cast<uint4*>(A + chunk * kChunkBytes + (uint32_t)row * 128u +
+                                        (uint32_t)((((sub * 2 + g) ^ (row & 7)) & 7) << 4)) =
+                  make_uint4(outp[g * 4], outp[g * 4 + 1], outp[g * 4 + 2], outp[g * 4 + 3]);
           }
           if (ok) stg256(a_out + col0, outp);
           if (lt >= 1) {
