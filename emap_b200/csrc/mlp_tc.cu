@@ -509,6 +509,10 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_kernel(const MlpArgs args) {
         tc_fence_after();
         if (stamp) args.dbg_clk[l * 8 + 1] = clock64();
         const float* bl = bias100 + l * kHidden;
+        // accumulator reads are software-pipelined: the tcgen05.ld of chunk c+1 is in flight while chunk c
+        // is converted (the TMEM read port serves the 16 warps at 64 B/clk: ~500 clk per chunk)
+        uint32_t rn[16];
+        tmem_ld_32x32b_x16(lane_taddr + (uint32_t)(buf * 256 + sub * 16), rn);
 #pragma unroll 1
         for (int chunk = 0; chunk < 4; ++chunk) {
           // all 16 warps convert the same 64-column chunk (16 columns each), so chunk c of the next
@@ -517,8 +521,10 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_kernel(const MlpArgs args) {
           uint8_t* dst_lo = A_lo + chunk * kChunkBytes;
           const int col0 = chunk * 64 + sub * 16;
           uint32_t r[16];
-          tmem_ld_32x32b_x16(lane_taddr + (uint32_t)(buf * 256 + col0), r);
           tmem_wait_ld();
+#pragma unroll
+          for (int k = 0; k < 16; ++k) r[k] = rn[k];
+          if (chunk < 3) tmem_ld_32x32b_x16(lane_taddr + (uint32_t)(buf * 256 + col0 + 64), rn);
           if (stamp && chunk < 2) args.dbg_clk[l * 8 + 2 + 3 * chunk] = clock64();
           if (args.dbg_acc && tile == 0) {
 #pragma unroll
@@ -586,11 +592,11 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_kernel(const MlpArgs args) {
           } else {
             // Exchange slots of point p8: four 16-byte slots (columns 4i..4i+3).  Single-MMA modes have a
             // warp-private scratch; in fp32x3 mode (no shared memory to spare) the slots alias this warp's
-            // own 64 bytes of the first tangent row (hi/lo x two swizzle groups) of the DESTINATION chunk:
-            // the MMAs that read it are complete (acc_full), and phase C overwrites it last -- slots
-            // (2g, 2g+1) are exactly the hi/lo group g of that row, read by all lanes before lane ty=1
-            // stores there.
-            const int r1 = q * 32 + 4 * p8 + 1;
+            // own 64 bytes of one tangent row (hi/lo x two swizzle groups) of the DESTINATION chunk: the
+            // MMAs that read it are complete (acc_full), and phase C overwrites it last -- slots
+            // (2g, 2g+1) are exactly the hi/lo group g of that row, read by all lanes before the lane that
+            // owns the row stores there.
+            const int r1 = q * 32 + 4 * p8 + 1 + ((p8 >> 1) % 3);   // (r1 & 7) spread over the 8 points: banks
             auto slot = [&](int i) -> float4* {
               if (Plan::kOwnScratch) return reinterpret_cast<float4*>(sc + p8 * 20 + 4 * i);
               uint8_t* base = (i & 1) ? dst_lo : dst_hi;
