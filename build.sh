@@ -8,11 +8,12 @@ mkdir -p $OUT build
 NVCC=${NVCC:-/usr/local/cuda/bin/nvcc}
 FLAGS="-gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -std=c++17 -Xcompiler -fPIC -Xptxas -v"
 objs=""
-for f in cabi pack mlp_tc mlp_rev rays mlp_bwd; do
+for f in cabi pack mlp_tc mlp_rev rays mlp_bwd extract; do
   [ -f $SRC/$f.cu ] || continue
   if [ ! -f build/$f.o ] || [ $SRC/$f.cu -nt build/$f.o ] || [ $SRC/common.cuh -nt build/$f.o ] || [ $SRC/host.h -nt build/$f.o ] || [ include/emap_b200.h -nt build/$f.o ]; then
     extra=""
     [ $f = rays ] && extra="-fmad=false"
+    [ $f = extract ] && extra="-fmad=false"
     echo "nvcc $f.cu"
     $NVCC $FLAGS $extra -c $SRC/$f.cu -o build/$f.o 2> build/$f.log || { cat build/$f.log; exit 1; }
   fi

@@ -168,19 +168,16 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_rev_kernel(const Args args) {
         // own row of U_{lt+1}: h (value lane) or hdot (tangent lane); the partner's comes by shuffle
         __half* a_out = args.st_a + (size_t)lt * 2 * P * 256 + rowg * 256;
         const int ncols = (lt == kSkipLayer - 1) ? out3 : 256;
-        // accumulator reads are software-pipelined: chunk c+1's tcgen05.ld is in flight while chunk c is
-        // converted
-        uint32_t rn[16];
-        if (j >= 0) tmem_ld_32x32b_x16(lane_taddr + (uint32_t)(buf * 256 + sub * 16), rn);
 #pragma unroll
         for (int chunk = 0; chunk < 4; ++chunk) {
           const int col0 = chunk * 64 + sub * 16;
           float own[16];
           if (j >= 0) {
+            uint32_t r[16];
+            tmem_ld_32x32b_x16(lane_taddr + (uint32_t)(buf * 256 + col0), r);
             tmem_wait_ld();
 #pragma unroll
-            for (int k = 0; k < 16; ++k) own[k] = __uint_as_float(rn[k]) * kInvWeightScale;
-            if (chunk < 3) tmem_ld_32x32b_x16(lane_taddr + (uint32_t)(buf * 256 + col0 + 64), rn);
+            for (int k = 0; k < 16; ++k) own[k] = __uint_as_float(r[k]) * kInvWeightScale;
           } else {
             const float cf = t2 ? c_t : c_v;
 #pragma unroll

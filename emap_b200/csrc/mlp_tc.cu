@@ -509,22 +509,17 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_kernel(const MlpArgs args) {
         tc_fence_after();
         if (stamp) args.dbg_clk[l * 8 + 1] = clock64();
         const float* bl = bias100 + l * kHidden;
-        // accumulator reads are software-pipelined: the tcgen05.ld of chunk c+1 is in flight while chunk c
-        // is converted (the TMEM read port serves the 16 warps at 64 B/clk: ~500 clk per chunk)
-        uint32_t rn[16];
-        tmem_ld_32x32b_x16(lane_taddr + (uint32_t)(buf * 256 + sub * 16), rn);
 #pragma unroll 1
         for (int chunk = 0; chunk < 4; ++chunk) {
           // all 16 warps convert the same 64-column chunk (16 columns each), so chunk c of the next
           // layer's A tile is complete after (c+1)/4 of the epilogue and its MMAs start then
+          // (software-pipelining the tcgen05.ld one chunk ahead was measured: slower -- register pressure)
           uint8_t* dst_hi = A_hi + chunk * kChunkBytes;
           uint8_t* dst_lo = A_lo + chunk * kChunkBytes;
           const int col0 = chunk * 64 + sub * 16;
           uint32_t r[16];
+          tmem_ld_32x32b_x16(lane_taddr + (uint32_t)(buf * 256 + col0), r);
           tmem_wait_ld();
-#pragma unroll
-          for (int k = 0; k < 16; ++k) r[k] = rn[k];
-          if (chunk < 3) tmem_ld_32x32b_x16(lane_taddr + (uint32_t)(buf * 256 + col0 + 64), rn);
           if (stamp && chunk < 2) args.dbg_clk[l * 8 + 2 + 3 * chunk] = clock64();
           if (args.dbg_acc && tile == 0) {
 #pragma unroll

@@ -406,3 +406,36 @@ def udf_backward_layerwise(net: PackedNet, precision: int, d_udf: Optional[torch
     mul = (ctypes.c_float * 9)(*[(2.0 ** -0.5) if l == 4 else 1.0 for l in range(9)])
     C.check(L.emap_bwd_weight_norm(desc, C.ptr(flat_params), dW_p, ldw, mul, db_p, C.ptr(flat_grad), st))
     return flat_grad
+
+
+# ----------------------------------------------------------------------------- SURVEY §8f rows 1-2
+def null_direction(grad_ld: torch.Tensor) -> torch.Tensor:
+    """[M,S,3] stacked gradients -> [M,3] unit right-singular vector of the smallest singular value
+    (extract_pointcloud.py:86-89: svd + vh[:, -1, :] + F.normalize), one thread per voxel."""
+    grad_ld = C.f32(grad_ld)
+    if grad_ld.dim() != 3 or grad_ld.shape[2] != 3:
+        raise RuntimeError("grad_ld must be [M,S,3]")
+    M, S, _ = grad_ld.shape
+    out = torch.empty(M, 3, dtype=torch.float32, device=grad_ld.device)
+    C.check(C.lib().emap_null_direction(C.ptr(grad_ld), M, S, C.ptr(out), C.stream()))
+    return out
+
+
+def rays_from_pixels(pixels_x, pixels_y, edge_img, intr_inv, pose):
+    """pixels [B] int64 (device) of one image -> dict of the per-ray tensors of
+    gen_random_rays_patches_at (dataset.py:268-305).  intr_inv / pose: [4,4] tensors (any device)."""
+    if pixels_x.dtype != torch.int64 or pixels_y.dtype != torch.int64:
+        raise RuntimeError("pixels must be int64")
+    dev = pixels_x.device
+    edge_img = C.f32(edge_img)
+    H, W = int(edge_img.shape[0]), int(edge_img.shape[1])
+    B = pixels_x.numel()
+    f = lambda *s: torch.empty(*s, dtype=torch.float32, device=dev)  # noqa: E731
+    rays_o, rays_v, edge, ndc, p_cam, ds = f(B, 3), f(B, 3), f(B, 1), f(B, 2), f(B, 3), f(B, 1)
+    kinv = (ctypes.c_float * 9)(*[float(v) for v in intr_inv[:3, :3].reshape(-1).tolist()])
+    pm = (ctypes.c_float * 16)(*[float(v) for v in pose.reshape(-1).tolist()])
+    C.check(C.lib().emap_rays_from_pixels(C.ptr(pixels_x.contiguous()), C.ptr(pixels_y.contiguous()),
+                                          C.ptr(edge_img), H, W, kinv, pm, B, C.ptr(rays_o), C.ptr(rays_v),
+                                          C.ptr(edge), C.ptr(ndc), C.ptr(p_cam), C.ptr(ds), C.stream()))
+    return {"rays_o": rays_o, "rays_v": rays_v, "edge": edge, "rays_ndc_uv": ndc,
+            "rays_norm_XYZ_cam": p_cam, "depth_scale": ds}

@@ -167,6 +167,22 @@ int emap_render_core_bwd(const float* rays_o, const float* rays_d, const float* 
                          const float* d_gerr_ns, const float* d_sparse, float* d_udf, float* d_grad,
                          double* partials, float* d_scalars, void* stream);
 
+/* ---- callers either side of the render path ------------------------------ */
+/* Line direction of edge extraction: grad [M,S,3] (S normalised UDF gradients sampled around each of
+ * M near-surface voxels) -> out [M,3] = unit right-singular vector of the smallest singular value of
+ * each [S,3] block (sign arbitrary, as with LAPACK).  replaces torch.linalg.svd + vh[:, -1, :] +
+ * F.normalize in src/edge_extraction/extract_pointcloud.py:75-89 and :176-187.                    */
+int emap_null_direction(const float* grad, int64_t M, int32_t S, float* out, void* stream);
+/* Deterministic half of the ray sampler: pixels (x,y) int64 [B] (device) of ONE image -> ndc uv
+ * [B,2], edge [B,1] gathered from edge_img [H,W] (device), p_cam = K^-1 (x,y,1) [B,3],
+ * depth_scale = normalised p_cam.z [B,1], rays_v = R p_cam/|p_cam| [B,3], rays_o = camera centre
+ * [B,3].  intr_inv3x3 (9 floats, row-major) and pose4x4 (16 floats) are HOST pointers.
+ * replaces src/dataset/dataset.py:268-290 (gen_random_rays_patches_at, after the pixel draw).      */
+int emap_rays_from_pixels(const int64_t* pixels_x, const int64_t* pixels_y, const float* edge_img,
+                          int32_t H, int32_t W, const float* intr_inv3x3, const float* pose4x4,
+                          int32_t B, float* rays_o, float* rays_v, float* edge, float* ndc_uv,
+                          float* p_cam, float* depth_scale, void* stream);
+
 /* ---- misc ------------------------------------------------------------------------------------ */
 /* options: "cluster" = 1|2|4 : width of the weight-stream multicast cluster of the MLP kernels.  */
 int emap_set_option(const char* name, int value);

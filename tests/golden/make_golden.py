@@ -238,6 +238,70 @@ def main():
     save("rendering_network", pts=pts, normals=nrm, view_dirs=vd, feat=feat,
          color=rn(pts, nrm, vd, feat), **{f"sd.{k}": v for k, v in rn.state_dict().items()})
 
+    # ------------------------------------------------------------------ §8f row 1: grid query of extract_edge
+    # the reference's own get_udf_normals_grid (loaded from its source file: the package __init__ pulls
+    # open3d), driven by the reference UDFNetwork exactly as runner_udf.py:520-526 does, on the CPU
+    import importlib.util
+    spec = importlib.util.spec_from_file_location(
+        "ref_extract_pointcloud", "/root/reference/src/edge_extraction/extract_pointcloud.py")
+    ref_ep = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(ref_ep)
+    net = build_net(perturbed=True)
+    func = net.udf
+
+    def func_grad(xyz):
+        gradients = net.gradient(xyz)
+        mag = torch.linalg.norm(gradients, ord=2, dim=-1, keepdim=True)
+        return gradients / (mag + 1e-5)
+
+    Ng, thr, SN = 14, 0.3, 50
+    torch.manual_seed(31)
+    df, ld, vecs, samples, vs = ref_ep.get_udf_normals_grid(func, func_grad, Ng, thr, is_linedirection=True,
+                                                            sampling_N=SN, sampling_delta=0.005,
+                                                            max_batch=4096, device="cpu")
+    M = int((samples[:, 3] < thr).sum())
+    torch.manual_seed(31)
+    offsets = torch.randn((M, SN, 3))          # the draw the reference made (M <= max_batch: one batch)
+    assert M <= 4096
+    save("extract_grid", N=Ng, udf_threshold=thr, sampling_N=SN, sampling_delta=0.005, df_values=df,
+         line_directions=ld, vecs=vecs, samples=samples.detach(), voxel_size=vs, offsets=offsets)
+
+    # ------------------------------------------------------------------ §8f row 2: ray sampler (deterministic half)
+    # gen_random_rays_patches_at is exec'd from the reference's dataset.py (the module itself imports cv2
+    # etc.) with a stand-in `self`; pixels are recovered from the returned ndc coordinates
+    import ast
+    import random
+    import types
+    src = open("/root/reference/src/dataset/dataset.py").read()
+    fn_node = None
+    for node in ast.walk(ast.parse(src)):
+        if isinstance(node, ast.FunctionDef) and node.name == "gen_random_rays_patches_at":
+            fn_node = node
+    mod = ast.Module(body=[fn_node], type_ignores=[])
+    ns = {"torch": torch, "np": np, "random": random}
+    exec(compile(mod, "dataset.py:gen_random_rays_patches_at", "exec"), ns)
+    H, W, n_img = 48, 64, 3
+    g = torch.Generator().manual_seed(41)
+    edges = (torch.rand(n_img, H, W, 1, generator=g) > 0.9).float() * torch.rand(n_img, H, W, 1, generator=g)
+    K = torch.eye(4).repeat(n_img, 1, 1)
+    K[:, 0, 0], K[:, 1, 1], K[:, 0, 2], K[:, 1, 2] = 70.0, 72.0, W / 2 - 0.3, H / 2 + 0.2
+    Kinv = torch.inverse(K)
+    pose = torch.eye(4).repeat(n_img, 1, 1)
+    for i in range(n_img):
+        q, _ = torch.linalg.qr(torch.randn(3, 3, generator=g))
+        pose[i, :3, :3] = q
+        pose[i, :3, 3] = torch.randn(3, generator=g)
+    fake = types.SimpleNamespace(W=W, H=H, edges=edges, intrinsics_all=K, intrinsics_all_inv=Kinv,
+                                 pose_all=pose, masks=None, device="cpu", image_pixels=H * W)
+    torch.manual_seed(43)
+    out = ns["gen_random_rays_patches_at"](fake, 1, 256, importance_sample=False)
+    uv = out["rays_ndc_uv"]
+    px = torch.round((uv[:, 0].double() + 1) / 2 * (W - 1)).long()
+    py = torch.round((uv[:, 1].double() + 1) / 2 * (H - 1)).long()
+    save("raygen", H=H, W=W, img_idx=1, edges=edges, intrinsics_inv=Kinv, pose=pose, pixels_x=px,
+         pixels_y=py, rays_o=out["rays"]["rays_o"], rays_v=out["rays"]["rays_v"], edge=out["rays"]["edge"],
+         rays_ndc_uv=uv, rays_norm_XYZ_cam=out["rays_norm_XYZ_cam"], depth_scale=out["depth_scale"])
+
     # ------------------------------------------------------------------ scalar nets
     var, beta = scalar_nets()
     save("scalars", inv_s=var(torch.zeros(1, 3)), beta=beta.get_beta(), gamma=beta.get_gamma(),

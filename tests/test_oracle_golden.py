@@ -181,3 +181,40 @@ def test_scalars(golden):
     assert torch.equal(s.inv_s().reshape(1, 1), g["inv_s"].clip(1e-6, 1e6))
     assert torch.equal(s.beta_val(), g["beta"].clip(1e-6, 1e6))
     assert torch.equal(s.gamma_val(), g["gamma"].clip(1e-6, 1e6))
+
+
+# ----------------------------------------------------------------------------- SURVEY §8f rows 1-2
+def test_extract_grid_oracle_matches_reference(golden):
+    """oracle/extract_oracle.py reproduces the reference's get_udf_normals_grid output (same seed ->
+    same randn offsets): df / coordinates / -sign(grad) "normals" bit-exactly, line directions up to the
+    SVD sign."""
+    from oracle import extract_oracle as E
+    from tests.helpers import oracle_params
+    g = golden("extract_grid")
+    p = oracle_params(True)
+    func = lambda x: (O.udf_forward(p, x)[0][:, :1], None, None)   # noqa: E731
+
+    def func_grad(xyz):
+        gr = O.udf_gradient(p, xyz).detach().reshape(-1, 1, 3)       # UDFNetwork.gradient -> [P,1,3]
+        return gr / (torch.linalg.norm(gr, ord=2, dim=-1, keepdim=True) + 1e-5)
+
+    N = int(g["N"])
+    df, ld, vecs, samples, vs = E.udf_normals_grid(func, func_grad, N, float(g["udf_threshold"]), True,
+                                                   int(g["sampling_N"]), float(g["sampling_delta"]),
+                                                   offsets=g["offsets"])
+    assert torch.equal(samples[:, :3], g["samples"][:, :3])
+    assert torch.equal(df, g["df_values"])
+    assert torch.equal(vecs, g["vecs"])
+    a, b = ld.reshape(-1, 3), g["line_directions"].reshape(-1, 3)
+    assert float(torch.minimum((a - b).abs().amax(1), (a + b).abs().amax(1)).max()) <= 1e-4
+    assert float(vs) == float(g["voxel_size"])
+
+
+def test_raygen_oracle_matches_reference(golden):
+    from oracle import extract_oracle as E
+    g = golden("raygen")
+    i = int(g["img_idx"])
+    out = E.rays_from_pixels(g["pixels_x"], g["pixels_y"], g["edges"][i], g["intrinsics_inv"][i], g["pose"][i],
+                             int(g["H"]), int(g["W"]))
+    for k in ("rays_o", "rays_v", "edge", "rays_ndc_uv", "rays_norm_XYZ_cam", "depth_scale"):
+        assert torch.equal(out[k], g[k]), k
