@@ -417,6 +417,8 @@ def null_direction(grad_ld: torch.Tensor) -> torch.Tensor:
         raise RuntimeError("grad_ld must be [M,S,3]")
     M, S, _ = grad_ld.shape
     out = torch.empty(M, 3, dtype=torch.float32, device=grad_ld.device)
+    if M == 0:
+        return out
     C.check(C.lib().emap_null_direction(C.ptr(grad_ld), M, S, C.ptr(out), C.stream()))
     return out
 
@@ -432,6 +434,9 @@ def rays_from_pixels(pixels_x, pixels_y, edge_img, intr_inv, pose):
     B = pixels_x.numel()
     f = lambda *s: torch.empty(*s, dtype=torch.float32, device=dev)  # noqa: E731
     rays_o, rays_v, edge, ndc, p_cam, ds = f(B, 3), f(B, 3), f(B, 1), f(B, 2), f(B, 3), f(B, 1)
+    if B == 0:
+        return {"rays_o": rays_o, "rays_v": rays_v, "edge": edge, "rays_ndc_uv": ndc,
+                "rays_norm_XYZ_cam": p_cam, "depth_scale": ds}
     kinv = (ctypes.c_float * 9)(*[float(v) for v in intr_inv[:3, :3].reshape(-1).tolist()])
     pm = (ctypes.c_float * 16)(*[float(v) for v in pose.reshape(-1).tolist()])
     C.check(C.lib().emap_rays_from_pixels(C.ptr(pixels_x.contiguous()), C.ptr(pixels_y.contiguous()),
