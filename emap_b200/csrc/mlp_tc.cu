@@ -517,6 +517,16 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_kernel(const MlpArgs args) {
           uint8_t* dst_hi = A_hi + chunk * kChunkBytes;
           uint8_t* dst_lo = A_lo + chunk * kChunkBytes;
           const int col0 = chunk * 64 + sub * 16;
+          // the bias words this lane needs, issued before the accumulator load so that their L1/L2
+          // latency hides under the tcgen05.ld wait (ncu: 8 % of the dual kernel's samples sat on it)
+          //   MODE 0: 16 columns; MODE 1: the lane's 4 value columns; MODE 2: the lane's 8 columns
+          constexpr int kBiasVec = (MODE == 0) ? 4 : ((MODE == 1) ? 1 : 2);
+          float4 bv[kBiasVec];
+          {
+            const int bofs = (MODE == 0) ? 0 : ((MODE == 1) ? 4 * ty : 8 * (lane & 1));
+#pragma unroll
+            for (int i = 0; i < kBiasVec; ++i) bv[i] = __ldg(reinterpret_cast<const float4*>(bl + col0 + bofs) + i);
+          }
           uint32_t r[16];
           tmem_ld_32x32b_x16(lane_taddr + (uint32_t)(buf * 256 + col0), r);
           tmem_wait_ld();
@@ -537,8 +547,7 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_kernel(const MlpArgs args) {
             const int t2 = lane & 1;
             const bool okp = (tile < args.num_tiles) && (pt < args.P);
             const long long rowg = (t2 ? args.P : 0) + pt;
-            const float4 bA = __ldg(reinterpret_cast<const float4*>(bl + col0 + t2 * 8));
-            const float4 bB = __ldg(reinterpret_cast<const float4*>(bl + col0 + t2 * 8 + 4));
+            const float4 bA = bv[0], bB = bv[kBiasVec - 1];
             const float bb[8] = {bA.x, bA.y, bA.z, bA.w, bB.x, bB.y, bB.z, bB.w};
             float hm[8], sm[8];
 #pragma unroll
@@ -573,8 +582,7 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_kernel(const MlpArgs args) {
           } else if (MODE == 0) {
 #pragma unroll
             for (int g = 0; g < 2; ++g) {
-              const float4 bA = __ldg(reinterpret_cast<const float4*>(bl + col0 + g * 8));
-              const float4 bB = __ldg(reinterpret_cast<const float4*>(bl + col0 + g * 8 + 4));
+              const float4 bA = bv[(2 * g) % kBiasVec], bB = bv[(2 * g + 1) % kBiasVec];
               const float bb[8] = {bA.x, bA.y, bA.z, bA.w, bB.x, bB.y, bB.z, bB.w};
               float h[8];
 #pragma unroll
@@ -611,7 +619,7 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_kernel(const MlpArgs args) {
               float4* my = slot(ty);
               const float4 vA = *my;
               const float va[4] = {vA.x, vA.y, vA.z, vA.w};
-              const float4 bA = __ldg(reinterpret_cast<const float4*>(bl + col0 + 4 * ty));
+              const float4 bA = bv[0];
               const float bb[4] = {bA.x, bA.y, bA.z, bA.w};
               float h[4], sg[4];
 #pragma unroll
