@@ -65,24 +65,28 @@ struct MlpArgs {
 
 constexpr int kRingStageBytes = 2 * kStageBytes;   // one part: [256 x 64] 16-bit SW128 image (N halves adjacent)
 
-template <int NTERMS, int MODE>
+template <int NTERMS, int MODE, bool PAIR = false>
 struct SmemPlan {
   // fp32x3: A_hi + A_lo = 128 KiB, ring 3 x 32 KiB; single-MMA modes: A = 64 KiB, ring 4 x 32 KiB.
+  // PAIR (cta_group::2): every CTA of a pair stages only ITS N half of each operand -> 16 KiB stages,
+  // twice as many of them in the same bytes.
   // (The PE chunk is not kept resident: it is written into activation chunk 0 for layer 0 and
   //  re-generated there for the skip term of layer 4.  The weight schedule is computed, not tabled.
   //  In fp32x3 MODE_GRAD the value->tangent exchange scratch aliases the destination chunk -- see the
   //  epilogue -- so that the third ring stage fits.)
-  static constexpr int kStages = (NTERMS == 3) ? 3 : 4;
+  static constexpr int kStageBytesP = PAIR ? kStageBytes : kRingStageBytes;
+  static constexpr int kStages = ((NTERMS == 3) ? 3 : 4) * (PAIR ? 2 : 1);
   static constexpr bool kOwnScratch = (MODE == 1 && NTERMS == 1);
   static constexpr int a_hi = 0;
   static constexpr int a_lo = a_hi + 4 * kChunkBytes;
   static constexpr int ring = a_lo + ((NTERMS == 3) ? 4 * kChunkBytes : 0);
-  static constexpr int scratch = ring + kStages * kRingStageBytes;
+  static constexpr int scratch = ring + kStages * kStageBytesP;
   static constexpr int bars = scratch + (kOwnScratch ? kEpiWarps * kScratchFloatsPerWarp * 4 : 0);
-  static constexpr int total = bars + 256 + 1024;   // +1 KiB slack to 1024-align the base
+  static constexpr int total = bars + 320 + 1024;   // +1 KiB slack to 1024-align the base
 };
 static_assert(SmemPlan<3, 1>::total <= 232448 && SmemPlan<3, 0>::total <= 232448 &&
-              SmemPlan<1, 1>::total <= 232448 && SmemPlan<3, 2>::total <= 232448, "shared memory plan exceeds 227 KiB");
+              SmemPlan<1, 1>::total <= 232448 && SmemPlan<3, 2>::total <= 232448 &&
+              SmemPlan<3, 1, true>::total <= 232448, "shared memory plan exceeds 227 KiB");
 
 // per-mode schedule constants (MODE 0 forward, 1 forward+grad (4 rows/point), 2 dual forward with
 // stashes for the backward (2 rows/point, layers 0..7 only -- the output layer is pulled back by a
@@ -305,9 +309,16 @@ __device__ __forceinline__ void pe_stage(const MlpArgs& args, const float (&x)[3
 
 template <int NTERMS, int MODE, typename T, int CL>
 __global__ void __launch_bounds__(kThreads, 1) mlp_kernel(const MlpArgs args) {
-  using Plan = SmemPlan<NTERMS, MODE>;
+  // CL = 1|2|4: weight-stream multicast width (cta_group::1).  CL = -2: PAIR mode -- clusters of two CTAs
+  // driven by ONE MMA issuer with tcgen05.mma.cta_group::2 (M = 256: each CTA's 128-row tile, N = 256 split
+  // as 128 weight rows per CTA): every SM stages and reads only half of each weight operand.
+  constexpr bool PAIR = (CL == -2);
+  constexpr int CLW = PAIR ? 2 : CL;             // cluster width
+  using Plan = SmemPlan<NTERMS, MODE, PAIR>;
   using MI = ModeInfo<MODE>;
   constexpr int kStages = Plan::kStages;
+  constexpr int kStageB = Plan::kStageBytesP;
+  constexpr int kArr = PAIR ? 2 : 1;             // epilogue arrivals per barrier: both CTAs of a pair
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
 
@@ -323,32 +334,44 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_kernel(const MlpArgs args) {
   uint64_t* full = bars;                  // [kStages]
   uint64_t* empty = bars + 8;             // [kStages]
   uint64_t* a_ready = bars + 16;          // [5]  (index 4 = PE written into chunk 0)
-  uint64_t* acc_full = bars + 21;         // [2]
+  uint64_t* acc_full = bars + 36;         // [2 buffers][2 N halves]: columns [0,128) / [128,256) complete
   uint64_t* acc_empty = bars + 23;        // [2]
   uint64_t* c0_free = bars + 25;          // layer 4 has consumed chunk 0 -> PE may be regenerated there
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 27);
+  uint64_t* peer_full = bars + 28;        // [kStages] PAIR, leader only: the peer's stage has landed
+  const uint32_t crank = (CLW > 1) ? cluster_ctarank() : 0;
 
   if (warp == kProducerWarp && lane == 0) {
-    for (int s = 0; s < kStages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], CL); }
-    for (int c = 0; c < 4; ++c) mbar_init(&a_ready[c], kEpiWarps);
-    mbar_init(&a_ready[4], 8);
-    for (int b = 0; b < 2; ++b) { mbar_init(&acc_full[b], 1); mbar_init(&acc_empty[b], kEpiWarps); }
+    for (int s = 0; s < kStages; ++s) {
+      mbar_init(&full[s], 1); mbar_init(&empty[s], PAIR ? 1 : CL); mbar_init(&peer_full[s], 1);
+    }
+    for (int c = 0; c < 4; ++c) mbar_init(&a_ready[c], kEpiWarps * kArr);
+    mbar_init(&a_ready[4], 8 * kArr);
+    for (int b = 0; b < 4; ++b) mbar_init(&acc_full[b], 1);
+    for (int b = 0; b < 2; ++b) mbar_init(&acc_empty[b], kEpiWarps * kArr);
     mbar_init(c0_free, 1);
     fence_barrier_init();
   }
-  if (warp == kMmaWarp) { tmem_alloc(tmem_slot, 512); tmem_relinquish(); }
+  if (warp == kMmaWarp) {
+    if (PAIR) { tmem_alloc_2sm(tmem_slot, 512); tmem_relinquish_2sm(); }
+    else { tmem_alloc(tmem_slot, 512); tmem_relinquish(); }
+  }
   tc_fence_before();
-  if (CL > 1) cluster_sync_all(); else __syncthreads();
+  if (CLW > 1) cluster_sync_all(); else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   constexpr int kParts = (NTERMS == 3) ? 2 : 1;
+  // epilogue -> MMA-issuer arrivals: in PAIR mode the issuer lives in the leader CTA (cluster rank 0)
+  auto arrive_issuer = [&](uint64_t* bar) {
+    if (!PAIR || crank == 0) mbar_arrive(bar); else mbar_arrive_cluster(bar, 0);
+  };
 
   if (warp == kProducerWarp) {
     // ===================================== producer =====================================
     // The weight stream of a tile is a fixed function of the schedule (pack.cu: layer -> K chunk ->
     // hi/lo part, both N halves of a part adjacent in memory): one 32 KiB bulk copy per part (2 KiB for
     // the N=16 output layer).  Uniform control flow, the copy itself issued by one elected lane.
-    const uint32_t rank = (CL > 1) ? cluster_ctarank() : 0;
+    const uint32_t rank = crank;
     const uint8_t* img = args.packed + hdr->images_off;
     uint8_t* ring = smem + Plan::ring;
     const bool no_copy = (args.dbg_flags & 2) != 0;
@@ -367,18 +390,42 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_kernel(const MlpArgs args) {
             if (no_copy) {
               mbar_arrive(&full[stage]);
             } else {
-              mbar_arrive_expect_tx(&full[stage], bytes);
-              uint8_t* dst = ring + stage * kRingStageBytes;
+              uint8_t* dst = ring + stage * kStageB;
               const uint8_t* src = img + off;
-              if (CL == 1) {
+              if (PAIR) {
+                // this CTA's N half of the operand (rows [128 rank, 128 rank + 128); 8 rows of the N=16 layer)
+                mbar_arrive_expect_tx(&full[stage], bytes / 2);
+                bulk_g2s(dst, src + rank * (bytes / 2), bytes / 2, &full[stage]);
+              } else if (CL == 1) {
+                mbar_arrive_expect_tx(&full[stage], bytes);
                 bulk_g2s(dst, src, bytes, &full[stage]);
               } else {
+                mbar_arrive_expect_tx(&full[stage], bytes);
                 const uint32_t slice = bytes / CL;
                 bulk_g2s_multicast(dst + rank * slice, src + rank * slice, slice, &full[stage],
-                                   (uint16_t)((1u << CL) - 1));
+                                   (uint16_t)((1u << CLW) - 1));
               }
             }
           }
+          __syncwarp();
+          if (++stage == (uint32_t)kStages) { stage = 0; ++round; }
+        }
+      }
+    }
+  } else if (warp == kMmaWarp && PAIR && crank != 0) {
+    // ===================================== peer CTA of a pair: relay =====================
+    // The leader issues every MMA; it must know that THIS CTA's half of a weight stage has landed.  Bulk
+    // copies can only signal a barrier of their destination CTA, so this otherwise idle warp forwards each
+    // `full` completion to the leader's `peer_full`.
+    uint32_t stage = 0, round = 0;
+    for (int iter = 0; iter < args.iters; ++iter) {
+#pragma unroll 1
+      for (int l = 0; l < MI::kLayers; ++l) {
+        const int nparts = ((l == 0) ? 1 : ((l == kSkipLayer) ? 5 : 4)) * kParts;
+#pragma unroll 1
+        for (int ip = 0; ip < nparts; ++ip) {
+          mbar_wait(&full[stage], round & 1, 450 + (int)stage, l * 16 + ip);
+          if (lane == 0) mbar_arrive_cluster(&peer_full[stage], 0);
           __syncwarp();
           if (++stage == (uint32_t)kStages) { stage = 0; ++round; }
         }
@@ -394,8 +441,16 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_kernel(const MlpArgs args) {
     const uint32_t a_hi_addr = smem_u32(smem + Plan::a_hi);
     const uint32_t a_lo_addr = smem_u32(smem + Plan::a_lo);
     const uint32_t ring_addr = smem_u32(smem + Plan::ring);
-    const uint32_t idesc256 = make_idesc_f16(128, 256, Elem<T>::fmt);
-    const uint32_t idesc16 = make_idesc_f16(128, 16, Elem<T>::fmt);
+    const uint32_t idesc256 = make_idesc_f16(PAIR ? 256 : 128, 256, Elem<T>::fmt);
+    const uint32_t idesc16 = make_idesc_f16(PAIR ? 256 : 128, 16, Elem<T>::fmt);
+    auto mma = [&](uint32_t d, uint64_t a, uint64_t b, uint32_t idesc, uint32_t acc) {
+      if (PAIR) umma_f16_2sm(d, a, b, idesc, acc); else umma_f16(d, a, b, idesc, acc);
+    };
+    auto commit = [&](uint64_t* bar, bool to_cluster) {
+      if (PAIR) umma_commit_2sm_multicast(bar, (uint16_t)3);
+      else if (to_cluster && CL > 1) umma_commit_multicast(bar, (uint16_t)((1u << CLW) - 1));
+      else umma_commit(bar);
+    };
     const bool no_mma = (args.dbg_flags & 1) != 0;
     uint32_t stage = 0, round = 0;
     for (int iter = 0; iter < args.iters; ++iter) {
@@ -406,60 +461,109 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_kernel(const MlpArgs args) {
         if (stamp) args.dbg_clk[72 + l * 8 + 0] = clock64();
         {
           const uint32_t started = (uint32_t)iter * (buf ? 4u : (uint32_t)MI::kUses0) + (uint32_t)(l >> 1);
-          if (started > 0) mbar_wait(&acc_empty[buf], (started - 1) & 1, 200 + buf, l);
+          if (started > 0) {
+            if (PAIR) mbar_wait_cluster(&acc_empty[buf], (started - 1) & 1, 200 + buf, l);
+            else mbar_wait(&acc_empty[buf], (started - 1) & 1, 200 + buf, l);
+          }
         }
         if (stamp) args.dbg_clk[72 + l * 8 + 1] = clock64();
         const int nkc = (l == 0) ? 1 : ((l == kSkipLayer) ? 5 : 4);
         const bool last = (l == kNumLinear - 1);
         const uint32_t idesc = last ? idesc16 : idesc256;
         const uint32_t d = tmem_base + (uint32_t)buf * 256u;
+        // N-split of the last K chunk (below).  Not for layers 0 and 4: their last K chunk is the PE chunk,
+        // which lives in activation chunk 0 -- the epilogue of accumulator half 0 would overwrite it under
+        // the still-running MMAs of half 1.
+        const bool split_tail = (NTERMS == 3) && !PAIR && !last && l != 0 && l != kSkipLayer;   // single-MMA modes: measured no gain
 #pragma unroll
         for (int ic = 0; ic < nkc; ++ic) {
           const int c = (l == 0) ? 4 : ((ic < 4) ? ic : 4);
           {
             const uint32_t uses = (c == 4) ? (uint32_t)iter * 2u + (l == kSkipLayer ? 1u : 0u)
                                            : (uint32_t)iter * (uint32_t)MI::kAPerTile + (uint32_t)(l - 1);
-            mbar_wait(&a_ready[c], uses & 1, 300 + c, l);
+            if (PAIR) mbar_wait_cluster(&a_ready[c], uses & 1, 300 + c, l);
+            else mbar_wait(&a_ready[c], uses & 1, 300 + c, l);
           }
           tc_fence_after();
           if (stamp && ic < 4) args.dbg_clk[72 + l * 8 + 2 + ic] = clock64();
           const uint32_t coff = (c == 4) ? 0u : (uint32_t)c * kChunkBytes;   // PE lives in chunk 0
           const uint64_t ahi = make_sw128_kmajor_desc(a_hi_addr + coff);
           const uint64_t alo = make_sw128_kmajor_desc(a_lo_addr + coff);
+          if (split_tail && ic == nkc - 1) {
+            // Last K chunk of the layer, N split in halves: the MMAs into accumulator columns [0,128) are
+            // issued (and committed to acc_full[buf][0]) first, so the epilogue starts on chunks 0-1 while
+            // the tensor pipe still works on columns [128,256) -- the accumulator tail (12 MMAs in fp32x3
+            // mode) is no longer serial with the first-chunk latency of the next layer.
+            uint32_t sidx[kParts];
+#pragma unroll
+            for (int part = 0; part < kParts; ++part) {
+              sidx[part] = stage;
+              mbar_wait(&full[stage], round & 1, 400 + (int)stage, l * 16 + ic * 2 + part);
+              if (++stage == (uint32_t)kStages) { stage = 0; ++round; }
+            }
+            tc_fence_after();
+            const uint32_t idesc128 = make_idesc_f16(128, 128, Elem<T>::fmt);
+            if (elect_one()) {
+#pragma unroll
+              for (int half = 0; half < 2; ++half) {
+                const uint32_t dh = d + (uint32_t)half * 128u;
+                const uint64_t b0 = make_sw128_kmajor_desc(ring_addr + sidx[0] * kStageB + half * kStageBytes);
+                if (!no_mma) {
+#pragma unroll
+                  for (int k = 0; k < 4; ++k)
+                    umma_f16(dh, ahi + 2 * k, b0 + 2 * k, idesc128, (ic == 0 && k == 0) ? 0u : 1u);
+                  if (NTERMS == 3) {
+                    const uint64_t b1 = make_sw128_kmajor_desc(ring_addr + sidx[kParts - 1] * kStageB + half * kStageBytes);
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) umma_f16(dh, alo + 2 * k, b0 + 2 * k, idesc128, 1u);
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) umma_f16(dh, ahi + 2 * k, b1 + 2 * k, idesc128, 1u);
+                  }
+                }
+                commit(&acc_full[buf * 2 + half], false);
+              }
+#pragma unroll
+              for (int part = 0; part < kParts; ++part) commit(&empty[sidx[part]], true);
+            }
+            __syncwarp();
+            continue;
+          }
 #pragma unroll
           for (int part = 0; part < kParts; ++part) {
             const bool st2 = stamp && l == 2 && ic == 1;
             if (st2) args.dbg_clk[144 + part * 4 + 0] = clock64();
             mbar_wait(&full[stage], round & 1, 400 + (int)stage, l * 16 + ic * 2 + part);
+            if (PAIR) mbar_wait_cluster(&peer_full[stage], round & 1, 420 + (int)stage, l * 16 + ic * 2 + part);
             tc_fence_after();
             if (st2) args.dbg_clk[144 + part * 4 + 1] = clock64();
-            const uint64_t bdesc = make_sw128_kmajor_desc(ring_addr + stage * kRingStageBytes);
+            const uint64_t bdesc = make_sw128_kmajor_desc(ring_addr + stage * kStageB);
             if (elect_one()) {
               if (!no_mma) {
                 if (part == 0) {
 #pragma unroll
                   for (int k = 0; k < 4; ++k)
-                    umma_f16(d, ahi + 2 * k, bdesc + 2 * k, idesc, (ic == 0 && k == 0) ? 0u : 1u);
+                    mma(d, ahi + 2 * k, bdesc + 2 * k, idesc, (ic == 0 && k == 0) ? 0u : 1u);
                   if (NTERMS == 3) {
 #pragma unroll
-                    for (int k = 0; k < 4; ++k) umma_f16(d, alo + 2 * k, bdesc + 2 * k, idesc, 1u);
+                    for (int k = 0; k < 4; ++k) mma(d, alo + 2 * k, bdesc + 2 * k, idesc, 1u);
                   }
                 } else {
 #pragma unroll
-                  for (int k = 0; k < 4; ++k) umma_f16(d, ahi + 2 * k, bdesc + 2 * k, idesc, 1u);
+                  for (int k = 0; k < 4; ++k) mma(d, ahi + 2 * k, bdesc + 2 * k, idesc, 1u);
                 }
               }
-              if (CL == 1) umma_commit(&empty[stage]);
-              else umma_commit_multicast(&empty[stage], (uint16_t)((1u << CL) - 1));
+              commit(&empty[stage], true);
             }
             __syncwarp();
             if (st2) args.dbg_clk[144 + part * 4 + 2] = clock64();
             if (++stage == (uint32_t)kStages) { stage = 0; ++round; }
           }
-          if (l == kSkipLayer && ic == 0) { if (elect_one()) umma_commit(c0_free); __syncwarp(); }
+          if (l == kSkipLayer && ic == 0) { if (elect_one()) commit(c0_free, false); __syncwarp(); }
         }
-        if (elect_one()) umma_commit(&acc_full[buf]);
-        __syncwarp();
+        if (!split_tail) {
+          if (elect_one()) { commit(&acc_full[buf * 2], false); commit(&acc_full[buf * 2 + 1], false); }
+          __syncwarp();
+        }
         if (stamp) args.dbg_clk[72 + l * 8 + 6] = clock64();
       }
     }
@@ -497,7 +601,7 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_kernel(const MlpArgs args) {
         else          pe_stage<NTERMS, MODE, T, 1>(args, x, multires, lane, row, pt, tile, true, A_hi, A_lo, gb);
         fence_proxy_async_smem();
         __syncwarp();
-        if (lane == 0) mbar_arrive(&a_ready[4]);
+        if (lane == 0) arrive_issuer(&a_ready[4]);
       }
 
       // ------------------------------------------------ hidden layers 0..7
@@ -505,7 +609,8 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_kernel(const MlpArgs args) {
         const int buf = l & 1;
         const bool stamp = args.dbg_clk && blockIdx.x == 0 && iter == 1 && warp == 0 && lane == 0;
         if (stamp) args.dbg_clk[l * 8 + 0] = clock64();
-        mbar_wait(&acc_full[buf], ((uint32_t)iter * (buf ? 4u : (uint32_t)MI::kUses0) + (uint32_t)(l >> 1)) & 1, 500 + buf, l);
+        const uint32_t acc_par = ((uint32_t)iter * (buf ? 4u : (uint32_t)MI::kUses0) + (uint32_t)(l >> 1)) & 1;
+        mbar_wait(&acc_full[buf * 2], acc_par, 500 + buf, l);
         tc_fence_after();
         if (stamp) args.dbg_clk[l * 8 + 1] = clock64();
         const float* bl = bias100 + l * kHidden;
@@ -517,6 +622,7 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_kernel(const MlpArgs args) {
           uint8_t* dst_hi = A_hi + chunk * kChunkBytes;
           uint8_t* dst_lo = A_lo + chunk * kChunkBytes;
           const int col0 = chunk * 64 + sub * 16;
+          if (chunk == 2) { mbar_wait(&acc_full[buf * 2 + 1], acc_par, 505 + buf, l); tc_fence_after(); }
           // the bias words this lane needs, issued before the accumulator load so that their L1/L2
           // latency hides under the tcgen05.ld wait (ncu: 8 % of the dual kernel's samples sat on it)
           //   MODE 0: 16 columns; MODE 1: the lane's 4 value columns; MODE 2: the lane's 8 columns
@@ -651,12 +757,12 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_kernel(const MlpArgs args) {
           if (stamp && chunk < 2) args.dbg_clk[l * 8 + 3 + 3 * chunk] = clock64();
           fence_proxy_async_smem();
           __syncwarp();
-          if (lane == 0 && !(MODE == 2 && l == 7)) mbar_arrive(&a_ready[chunk]);
+          if (lane == 0 && !(MODE == 2 && l == 7)) arrive_issuer(&a_ready[chunk]);
           if (stamp && chunk < 2) args.dbg_clk[l * 8 + 4 + 3 * chunk] = clock64();
         }
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(&acc_empty[buf]);
+        if (lane == 0) arrive_issuer(&acc_empty[buf]);
 
         if (l == kSkipLayer - 1 && sub < 2) {
           // skip connection: layer 4 = [h4 ; PE]/sqrt2.  Once its MMAs on chunk 0 are done, regenerate
@@ -666,7 +772,7 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_kernel(const MlpArgs args) {
           else          pe_stage<NTERMS, MODE, T, 1>(args, x, multires, lane, row, pt, tile, false, A_hi, A_lo, gb);
           fence_proxy_async_smem();
           __syncwarp();
-          if (lane == 0) mbar_arrive(&a_ready[4]);
+          if (lane == 0) arrive_issuer(&a_ready[4]);
         }
       }
 
@@ -699,14 +805,14 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_kernel(const MlpArgs args) {
       }
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&acc_empty[0]);
+      if (lane == 0) arrive_issuer(&acc_empty[0]);
     }
   }
 
   // ---- teardown
   tc_fence_before();
-  if (CL > 1) cluster_sync_all(); else __syncthreads();
-  if (warp == kMmaWarp) tmem_dealloc(tmem_base, 512);
+  if (CLW > 1) cluster_sync_all(); else __syncthreads();
+  if (warp == kMmaWarp) { if (PAIR) tmem_dealloc_2sm(tmem_base, 512); else tmem_dealloc(tmem_base, 512); }
 }
 
 static long long* g_dbg_clk = nullptr;   // emap_debug_set_clk_buffer
@@ -715,7 +821,9 @@ static int g_dbg_flags = 0;   // timing experiments (emap_set_option("dbg", flag
 // ---------------------------------------------------------------------------------------------
 template <int NTERMS, int MODE, typename T, int CL>
 static int launch(const MlpArgs& a_in, cudaStream_t stream) {
-  using Plan = SmemPlan<NTERMS, MODE>;
+  constexpr bool PAIR = (CL == -2);
+  constexpr int CLW = PAIR ? 2 : CL;
+  using Plan = SmemPlan<NTERMS, MODE, PAIR>;
   MlpArgs a = a_in;
   const int pts_per_tile = ModeInfo<MODE>::kPtsPerTile;
   const long long tiles = (a.P + pts_per_tile - 1) / pts_per_tile;
@@ -723,8 +831,8 @@ static int launch(const MlpArgs& a_in, cudaStream_t stream) {
   a.num_tiles = (int)tiles;
   a.dbg_flags = g_dbg_flags;
   int grid = sm_count();
-  grid = grid / CL * CL;
-  if (tiles < grid) grid = (int)((tiles + CL - 1) / CL * CL);
+  grid = grid / CLW * CLW;
+  if (tiles < grid) grid = (int)((tiles + CLW - 1) / CLW * CLW);
   a.iters = (int)((tiles + grid - 1) / grid);
   auto kern = mlp_kernel<NTERMS, MODE, T, CL>;
   static bool attr_done = false;   // per template instantiation
@@ -740,7 +848,7 @@ static int launch(const MlpArgs& a_in, cudaStream_t stream) {
   cfg.stream = stream;
   cudaLaunchAttribute attr[1];
   attr[0].id = cudaLaunchAttributeClusterDimension;
-  attr[0].val.clusterDim.x = CL;
+  attr[0].val.clusterDim.x = CLW;
   attr[0].val.clusterDim.y = 1;
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
@@ -749,21 +857,25 @@ static int launch(const MlpArgs& a_in, cudaStream_t stream) {
   return 0;
 }
 
-static int g_cluster = 1;   // weight-stream multicast width (1, 2 or 4); see emap_set_option
+// weight-stream organisation of the MLP kernels (emap_set_option("cluster", v)):
+//   1 = every CTA streams its own copy (default), 2 = multicast pairs (cta_group::1),
+//   -2 = CTA pairs driven by one cta_group::2 issuer (fp16 operand images only).
+static int g_cluster = 1;
 
 template <int MODE>
 static int dispatch(const emap_net_desc* net, int precision, const MlpArgs& a, cudaStream_t st) {
   const int cl = g_cluster;
 #define EMAP_LAUNCH(NT, TT)                                              \
   do {                                                                   \
-    if (cl == 4) return launch<NT, MODE, TT, 4>(a, st);                  \
     if (cl == 2) return launch<NT, MODE, TT, 2>(a, st);                  \
     return launch<NT, MODE, TT, 1>(a, st);                               \
   } while (0)
   if (precision == EMAP_PREC_FP32X3) {
-    if (net->elem_type == 0) EMAP_LAUNCH(3, __half); else EMAP_LAUNCH(3, __nv_bfloat16);
+    if (net->elem_type == 0) { if (cl == -2) return launch<3, MODE, __half, -2>(a, st); EMAP_LAUNCH(3, __half); }
+    else EMAP_LAUNCH(3, __nv_bfloat16);
   } else if (precision == EMAP_PREC_HALF) {
-    if (net->elem_type == 0) EMAP_LAUNCH(1, __half); else EMAP_LAUNCH(1, __nv_bfloat16);
+    if (net->elem_type == 0) { if (cl == -2) return launch<1, MODE, __half, -2>(a, st); EMAP_LAUNCH(1, __half); }
+    else EMAP_LAUNCH(1, __nv_bfloat16);
   }
 #undef EMAP_LAUNCH
   return set_error("precision must be EMAP_PREC_FP32X3 (3) or EMAP_PREC_HALF (1)");
@@ -780,7 +892,7 @@ static int check_points(const float* pts, const float* rays_o, const float* rays
 }
 
 int set_cluster_width(int v) {
-  if (v != 1 && v != 2 && v != 4) return set_error("cluster width must be 1, 2 or 4");
+  if (v != 1 && v != 2 && v != -2) return set_error("cluster must be 1, 2 (multicast) or -2 (cta_group::2 pairs)");
   g_cluster = v;
   return 0;
 }

@@ -24,7 +24,7 @@ for dbg in (0, 1, 2, 4, 3, 5, 6, 7):
         r.append(t(lambda: ops.udf_forward_grad(net, prec, pts=x[: P // 4])))
     print(f"dbg={dbg} (1=noMMA 2=noCopy 4=noEpiMath)  fwd3 {r[0]:.2f} ms  grad3(P/4) {r[1]:.2f} ms  fwd1 {r[2]:.2f} ms  grad1(P/4) {r[3]:.2f} ms", flush=True)
 C.set_option("dbg", 0)
-for cl in (1, 2, 4):
+for cl in (1, 2, -2):
     C.set_option("cluster", cl)
     r = []
     for prec in (3, 1):
