@@ -561,7 +561,7 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_kernel(const MlpArgs args) {
           if (l == kSkipLayer && ic == 0) { if (elect_one()) commit(c0_free, false); __syncwarp(); }
         }
         if (!split_tail) {
-          if (elect_one()) { commit(&acc_full[buf * 2], false); commit(&acc_full[buf * 2 + 1], false); }
+          if (elect_one()) { commit(&acc_full[buf * 2], false); if (NTERMS == 3) commit(&acc_full[buf * 2 + 1], false); }
           __syncwarp();
         }
         if (stamp) args.dbg_clk[72 + l * 8 + 6] = clock64();
@@ -622,7 +622,7 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_kernel(const MlpArgs args) {
           uint8_t* dst_hi = A_hi + chunk * kChunkBytes;
           uint8_t* dst_lo = A_lo + chunk * kChunkBytes;
           const int col0 = chunk * 64 + sub * 16;
-          if (chunk == 2) { mbar_wait(&acc_full[buf * 2 + 1], acc_par, 505 + buf, l); tc_fence_after(); }
+          if (NTERMS == 3 && chunk == 2) { mbar_wait(&acc_full[buf * 2 + 1], acc_par, 505 + buf, l); tc_fence_after(); }
           // the bias words this lane needs, issued before the accumulator load so that their L1/L2
           // latency hides under the tcgen05.ld wait (ncu: 8 % of the dual kernel's samples sat on it)
           //   MODE 0: 16 columns; MODE 1: the lane's 4 value columns; MODE 2: the lane's 8 columns
