@@ -54,6 +54,18 @@ def test_no_cpu_fallback():
         net(torch.zeros(4, 3))                       # CPU tensors: refuse, do not emulate
     with pytest.raises(NotImplementedError):
         UDFNetwork(3, 1, 128, 8, skip_in=[4], multires=10)
+    # SURVEY 8f modules: same rule
+    from emap_b200.extract_pointcloud import get_udf_normals_grid, get_udf_normals_slow
+    from emap_b200.ray_sampler import RaySampler
+    with pytest.raises(RuntimeError):
+        get_udf_normals_grid(net.udf, net.gradient, 4, 0.1, device="cpu")
+    with pytest.raises(RuntimeError):
+        get_udf_normals_slow(net.udf, net.gradient, 0.1, torch.zeros(2, 3), False, device="cpu")
+    with pytest.raises(RuntimeError):
+        RaySampler(torch.zeros(1, 4, 4, 1), torch.eye(4)[None], torch.eye(4)[None], device="cpu")
+    from emap_b200 import ops
+    with pytest.raises(RuntimeError):
+        ops.null_direction(torch.zeros(2, 5, 3))
 
 
 def test_state_dict_keys_and_init_match_reference(golden):

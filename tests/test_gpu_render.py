@@ -143,3 +143,33 @@ def test_properties_at_scale():
         assert torch.isfinite(v).all(), k
     assert torch.equal(a["weights"][perm.to(dev)], b["weights"])
     assert torch.equal(a["edge"][perm.to(dev)], b["edge"])
+
+
+def test_properties_c5_sweep_size():
+    """BASELINE config C5 (65536 rays x 256 flat samples, 16.8 M points per launch): size-independent
+    properties -- finite outputs, weights in [0,1] summing to <= 1, sorted samples, and shard invariance:
+    rendering the batch in two halves (what the multi-GPU path does with the rays) is bit-identical to
+    rendering it whole."""
+    from oracle import emap_oracle as O
+    net, var, beta, r = build(10, True, n_samples=256, n_importance=0, up_sample_steps=4)
+    r.perturb = 0
+    B = 65536
+    o, d = O.synthetic_rays(B)
+    near, far = torch.full((B, 1), 0.05).to(dev), torch.full((B, 1), 6.0).to(dev)
+    ds = torch.ones(B, 1).to(dev)
+    o, d = o.to(dev), d.to(dev)
+    with torch.no_grad():
+        full = r.render(o, d, near, far, ds, cos_anneal_ratio=1.0, flip_saturation=0.9)
+        h = B // 2
+        lo = r.render(o[:h], d[:h], near[:h], far[:h], ds[:h], cos_anneal_ratio=1.0, flip_saturation=0.9)
+        hi = r.render(o[h:], d[h:], near[h:], far[h:], ds[h:], cos_anneal_ratio=1.0, flip_saturation=0.9)
+    w = full["weights"]
+    assert w.shape == (B, 256)
+    for k in ("weights", "edge", "depth", "normals", "udf", "gradients", "gradient_mag"):
+        assert torch.isfinite(full[k]).all(), k
+    assert float(w.min()) >= 0.0 and float(w.max()) <= 1.0 + 1e-6
+    assert float(full["weight_sum"].max()) <= 1.0 + 1e-4
+    mz = full["mid_z_vals"]
+    assert bool((mz[:, 1:] >= mz[:, :-1]).all())
+    for k in ("weights", "edge", "depth", "normals", "udf", "gradients"):
+        assert torch.equal(full[k], torch.cat([lo[k], hi[k]])), k
