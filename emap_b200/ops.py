@@ -320,7 +320,9 @@ def udf_backward(net: PackedNet, precision: int, d_udf: Optional[torch.Tensor],
     dW, db = [None] * 9, [None] * 9
     dW[8] = torch.mm(coef.to(torch.float16).view(1, 2 * P), U8, out_dtype=torch.float32)
     db[8] = coef[:P].sum().reshape(1)
-    db_all = st_a[:, :P].sum(dim=1, dtype=torch.float32)                  # [8,256] in one pass
+    db_all = torch.empty(8, 256, dtype=torch.float32, device=dev)
+    db_part = torch.empty(8 * 296 * 256, dtype=torch.float32, device=dev)
+    C.check(L.emap_bwd_bias_sums(C.ptr(st_a), P, C.ptr(db_part), C.ptr(db_all), st))   # [8,256], one pass at HBM rate
     for l in range(8):
         A = st_a[l]
         db[l] = db_all[l]

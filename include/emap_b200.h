@@ -100,6 +100,10 @@ int emap_bwd_dual_forward(const emap_net_desc* net, const void* packed, int prec
                           void* stream);
 int emap_bwd_reverse_sweep(const emap_net_desc* net, const void* packed, const float* coef,
                            const void* st_u, void* st_a, int64_t P, void* stream);
+/* db_l[c] = sum over the value rows p < P of A_l[p, c], l = 0..7, from the reverse sweep's stash
+ * st_a [8][2P,256] fp16 -> db [8,256] fp32.  partial: scratch [8*296*256] floats.  Deterministic two-pass
+ * reduction (no atomics).  replaces the bias half of autograd's addmm backward (udf_model.py:102).      */
+int emap_bwd_bias_sums(const void* st_a, int64_t P, float* partial, float* db, void* stream);
 /* weight-norm backward + scatter into the flat gradient (same layout as the flat parameters).
  * dW[l]: fp32 [out_l, ldw[l]] (d/dW_eff, times mul[l]); db[l]: fp32 [out_l].                       */
 int emap_bwd_weight_norm(const emap_net_desc* net, const float* flat_params, const float* const* dW,
