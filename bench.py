@@ -219,6 +219,9 @@ def main():
     ap.add_argument("--rays", type=int, default=RAYS_PER_GPU)
     ap.add_argument("--ref-rays", type=int, default=128)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--grad-mode", default=os.environ.get("EMAP_GRAD_MODE", "forward"),
+                    choices=["forward", "reverse"],
+                    help="K1g forward-mode tangents (validated default) or K1r reverse-mode (mlp_rg.cu, opt-in)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
 
@@ -245,6 +248,8 @@ def main():
         dist.init_process_group("nccl", device_id=dev)
 
     from emap_b200 import _cabi as C
+    ops.set_grad_mode(args.grad_mode)
+    grad_call = "emap_udf_forward_grad_rev" if args.grad_mode == "reverse" else "emap_udf_forward_grad"
     net, var, beta, r = build_ours(dev, args.precision)
     B, n = args.rays, N0 + NI
     o, d, near, far, ds = synthetic_problem(B, seed_offset=rank)
@@ -288,7 +293,7 @@ def main():
         sampler.start()
     C.launch_count = 0
     C.timed_events.clear()
-    C.timed_call = "emap_udf_forward_grad"       # dominant kernel, timed live inside the timed region
+    C.timed_call = grad_call                     # dominant kernel, timed live inside the timed region
     evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
            for _ in range(args.steps)]
     barrier()
@@ -356,12 +361,14 @@ def main():
         P = B * n
         alg_flop = 2.0 * F_FWD * P                       # forward + reverse-mode d/dx
         nterms = 3 if args.precision == "fp32" else 1
-        exe_flop = 4.0 * F_FWD * P * nterms              # forward-mode: 4 rows per point, x MMA terms
+        rev = args.grad_mode == "reverse"
+        exe_flop = (2.0 if rev else 4.0) * F_FWD * P * nterms   # forward-mode: 4 rows per point; reverse: fwd + sweep
         achieved = alg_flop / (k_ms * 1e-3) / 1e12
-        roof = {"bound": "tensor", "kernel": "mlp_kernel<MODE_GRAD> (emap_udf_forward_grad)",
+        roof = {"bound": "tensor", "kernel": ("mlp_rgrad_kernel (emap_udf_forward_grad_rev)" if rev else
+                                              "mlp_kernel<MODE_GRAD> (emap_udf_forward_grad)"),
                 "achieved": achieved, "peak": pk["bf16_tflops"], "unit": "TFLOP/s",
                 "frac": achieved / pk["bf16_tflops"],
-                "traffic": NCU_DRAM_BYTES_PER_LAUNCH.get((args.precision, B, n)),
+                "traffic": None if rev else NCU_DRAM_BYTES_PER_LAUNCH.get((args.precision, B, n)),
                 "traffic_source": "profiles/r01_mlp_ncu_raw.csv (ncu --set full, dram__bytes_read.sum + "
                                   "dram__bytes_write.sum of one launch of this workload)",
                 "peak_source": pk_src + " burst bf16 (cuBLAS)",
@@ -369,8 +376,10 @@ def main():
                 "share_of_step": k_ms / ms,
                 "algorithmic_flop_per_point": 2.0 * F_FWD,
                 "executed_tflops": exe_flop / (k_ms * 1e-3) / 1e12,
-                "note": "algorithmic = 2F/point (fwd + reverse-mode grad); the kernel executes forward-mode "
-                        "(4 rows/point) and, in fp32 mode, 3 split-fp16 MMAs per product"}
+                "note": ("algorithmic = 2F/point (fwd + reverse-mode grad); the kernel executes exactly that, "
+                         "x3 split-fp16 MMAs per product in fp32 mode" if rev else
+                         "algorithmic = 2F/point (fwd + reverse-mode grad); the kernel executes forward-mode "
+                         "(4 rows/point) and, in fp32 mode, 3 split-fp16 MMAs per product")}
         cpu = None if args.no_cpu_baseline else cpu_baseline(args.mode)
         line = {
             "metric": "ray-samples/s through UDF render path", "value": value, "unit": "ray-samples/s",
@@ -381,7 +390,7 @@ def main():
             "data": "synthetic",
             "config": {"workload": f"replica-style synthetic cameras, {B} rays x {n} samples "
                                    f"({N0}+{NI}/{STEPS} hierarchical) per GPU, {args.mode}",
-                       "mode": args.mode, "rays_per_gpu": B, "samples_per_ray": n,
+                       "mode": args.mode, "grad_mode": args.grad_mode, "rays_per_gpu": B, "samples_per_ray": n,
                        "parallelism": f"rays sharded x{world}" + (", flat grad allreduce" if args.mode == "train" else ""),
                        "l2": "flushed (256 MiB write) between timed steps"},
             "clocks": clocks,

@@ -45,6 +45,18 @@ __host__ __device__ inline int pe_col_to_ref(int col, int multires) {
   return 3 + 6 * j + 3 * is_cos + c;
 }
 
+// PE row order of the REVERSE-mode gradient kernel (mlp_rg.cu): the adjoint of the positional encoding
+// comes out of two MMAs -- layer 4's skip input (accumulator columns out3-1+k) and layer 0 (columns k) --
+// and both use this order so that one contraction routine serves both.  It is the kernel column order
+// above with x_0 moved into the pad slot: slot 0 of the skip layer is the last hidden column out3-1, so
+//   k = 0 : not a PE entry (-1)      k = 1, 2 : x_1, x_2      k = 3 : x_0      k >= 4 : as pe_col_to_ref.
+__host__ __device__ inline int rg_pe_ref(int k, int multires) {
+  if (k <= 0) return -1;
+  if (k == 3) return 0;
+  if (k < 3) return k;
+  return pe_col_to_ref(k, multires);
+}
+
 // ----------------------------------------------------------------------------------------------
 // Ring items: the weight stream of one tile, in consumption order.  Built on the host by
 // build_item_table() (pack.cu), stored in the packed-weights buffer, copied to SMEM by the MLP

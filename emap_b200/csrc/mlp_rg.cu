@@ -1,0 +1,516 @@
+// K1r: fused PE + 9-layer MLP forward AND reverse-mode d udf / d x in one persistent kernel.
+//
+// Replaces (reference paths relative to /root/reference), like K1g in mlp_tc.cu:
+//   src/models/udf_model.py:90-110    UDFNetwork.forward
+//   src/models/udf_model.py:121-135   UDFNetwork.gradient  (autograd.grad of the output w.r.t. x)
+//   src/models/udf_renderer_blending.py:448-461  (the two calls in render_core)
+//
+// K1g carries three tangent rows per point through the network (forward mode: 4 rows x 3 split MMAs =
+// 12 F executed per point, F = one MLP forward).  This kernel does what autograd does instead: a value-
+// only forward (128 points per tile, 3 F) that keeps sigma_l = softplus'(a_l) of every hidden layer,
+// then the adjoint sweep
+//     alpha_7 = udf'(a_8) w_8 . sigma_7,      alpha_{l-1} = (alpha_l W_l) . sigma_{l-1},   l = 7..1,
+//     d udf / d x = J_gamma(x)^T [ alpha_0 W_0  +  PE columns of alpha_4 W_4 / sqrt2 ]
+// on the same tile with the W_l^T operand images (3 F): 6 F executed, half the epilogue conversions.
+// sigma (8 layers x 256 x fp32 = 8 KiB per point) does not fit on chip; every CTA owns a fixed 1 MiB
+// scratch slice in global memory that it rewrites tile after tile -- thread-private addresses (each
+// thread reads back exactly what it wrote), last written = first read, so the slice lives in the
+// 126 MB L2 and DRAM sees little of it.
+//
+// Skeleton = mlp_tc.cu (same roles, ring, barriers, A-tile format): 17 MMA "steps" per tile --
+// steps 0..8 = forward layers 0..8, steps 9..16 = reverse layers 7..0 -- ping-ponging the two
+// 256-column TMEM accumulators (buf = step & 1).  Adjoints are held in the A tile scaled by 2^4 so that
+// their fp16 lo parts stay normal; the scale rides through the sweep and is removed once at the end.
+#include "mlp_dev.cuh"
+
+namespace emap {
+namespace rg {
+
+constexpr int kSteps = 17;
+constexpr int kLastStep = kSteps - 1;
+constexpr uint32_t kUses0 = 9, kUses1 = 8;        // accumulator uses per tile: buf 0 (even steps) / buf 1
+constexpr uint32_t kAPerTile = 16;                // completions of a_ready[0..3] per tile (steps 0..15)
+constexpr float kAdjScale = 16.f;                 // power of two (headroom: |alpha| < 4095)
+constexpr int kSigmaFloatsPerCta = 8 * 4 * 16 * 512;   // [layer][chunk][warp][2 x 32 lanes x 8] = 1 MiB
+
+struct Args {
+  MlpArgs m;
+  float* scratch;        // [grid][kSigmaFloatsPerCta]
+  uint32_t rg_off;       // byte offset of the reverse image stream inside the packed buffer
+};
+
+template <int NTERMS>
+struct Plan {
+  static constexpr int kStages = (NTERMS == 3) ? 3 : 4;
+  static constexpr int a_hi = 0;
+  static constexpr int a_lo = a_hi + 4 * kChunkBytes;
+  static constexpr int ring = a_lo + ((NTERMS == 3) ? 4 * kChunkBytes : 0);
+  static constexpr int bars = ring + kStages * kRingStageBytes;
+  static constexpr int total = bars + 256 + 1024;   // +1 KiB slack to 1024-align the base
+};
+static_assert(Plan<3>::total <= 232448 && Plan<1>::total <= 232448, "shared memory plan exceeds 227 KiB");
+
+// schedule of step s: K chunks, bytes of one operand part, UMMA N
+__device__ __forceinline__ constexpr int step_nkc(int s) { return (s == 0) ? 1 : ((s == kSkipLayer) ? 5 : 4); }
+__device__ __forceinline__ constexpr uint32_t step_bytes(int s) {
+  return (s == 8) ? 2048u : ((s == kLastStep) ? 8192u : (uint32_t)kRingStageBytes);
+}
+
+// sigma scratch: plain (coherent) 256-bit accesses -- the data is rewritten by this kernel, so the
+// read-only path of ldg256 must not be used.
+__device__ __forceinline__ void ld_scratch8(const float* p, float (&v)[8]) {
+  uint32_t u[8];
+  asm volatile("ld.global.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=r"(u[0]), "=r"(u[1]), "=r"(u[2]), "=r"(u[3]), "=r"(u[4]), "=r"(u[5]), "=r"(u[6]), "=r"(u[7])
+               : "l"(p)
+               : "memory");
+#pragma unroll
+  for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(u[i]);
+}
+__device__ __forceinline__ void st_scratch8(float* p, const float (&v)[8]) {
+  uint32_t u[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) u[i] = __float_as_uint(v[i]);
+  stg256(p, u);
+}
+
+// J_gamma^T applied to 16 consecutive PE adjoints adj[i] <-> PE slot k = kbase + i (rg_pe_ref order,
+// common.cuh; kbase even, slots k < 1 are not PE entries): g += sum_k adj_k d gamma_k / d x.
+//   x_c: 1;   sin(f x_c): f cos(f x_c);   cos(f x_c): -f sin(f x_c),   f = 2^j   (embedder.py:26-35)
+__device__ __forceinline__ void pe_adjoint16(const float (&adj)[16], int kbase, const float (&x)[3],
+                                             int multires, float (&g)[3]) {
+#pragma unroll
+  for (int i = 0; i < 16; i += 2) {
+    const int k = kbase + i;                    // even; warp-uniform
+    if (k < 0) continue;
+    if (k == 0) { g[1] += adj[i + 1]; }                       // (not PE, x_1)
+    else if (k == 2) { g[2] += adj[i]; g[0] += adj[i + 1]; }  // (x_2, x_0)
+    else {
+      const int qq = (k - 4) >> 1, j = qq / 3, ax = qq - 3 * j;
+      if (j < multires) {
+        const float f = (float)(1 << j);
+        const float xa = (ax == 0) ? x[0] : (ax == 1 ? x[1] : x[2]);
+        float s, c;
+        sincosf(xa * f, &s, &c);
+        const float v = f * (adj[i] * c - adj[i + 1] * s);
+        if (ax == 0) g[0] += v; else if (ax == 1) g[1] += v; else g[2] += v;
+      }
+    }
+  }
+}
+
+__device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+
+template <int NTERMS, typename T>
+__global__ void __launch_bounds__(kThreads, 1) mlp_rgrad_kernel(const Args args) {
+  using P = Plan<NTERMS>;
+  constexpr int kStages = P::kStages;
+  constexpr int kParts = (NTERMS == 3) ? 2 : 1;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+
+  const MlpArgs& m = args.m;
+  const PackedHeader* hdr = reinterpret_cast<const PackedHeader*>(m.packed);
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int multires = (int)hdr->multires;
+  const float net_scale = hdr->scale;
+  const int udf_type = (int)hdr->udf_type;
+  const float* bias100 = reinterpret_cast<const float*>(m.packed + hdr->bias100_off);
+
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + P::bars);
+  uint64_t* full = bars;                  // [kStages]
+  uint64_t* empty = bars + 4;             // [kStages]
+  uint64_t* a_ready = bars + 8;           // [5]  (index 4 = PE written into chunk 0)
+  uint64_t* acc_full = bars + 13;         // [2]
+  uint64_t* acc_empty = bars + 15;        // [2]
+  uint64_t* c0_free = bars + 17;          // layer 4 has consumed chunk 0 -> PE may be regenerated there
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 18);
+
+  if (warp == kProducerWarp && lane == 0) {
+    for (int s = 0; s < kStages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+    for (int c = 0; c < 4; ++c) mbar_init(&a_ready[c], kEpiWarps);
+    mbar_init(&a_ready[4], 8);
+    for (int b = 0; b < 2; ++b) { mbar_init(&acc_full[b], 1); mbar_init(&acc_empty[b], kEpiWarps); }
+    mbar_init(c0_free, 1);
+    fence_barrier_init();
+  }
+  if (warp == kMmaWarp) { tmem_alloc(tmem_slot, 512); tmem_relinquish(); }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == kProducerWarp) {
+    // ===================================== producer =====================================
+    // forward images (pack.cu: layer -> K chunk -> hi/lo part) then the reverse stream (rg images, same
+    // order); one bulk copy per part, uniform control flow, issued by one elected lane.
+    const uint8_t* img_f = m.packed + hdr->images_off;
+    const uint8_t* img_r = m.packed + args.rg_off;
+    uint8_t* ring = smem + P::ring;
+    uint32_t stage = 0, round = 0;
+    for (int iter = 0; iter < m.iters; ++iter) {
+      uint32_t off = 0;
+#pragma unroll 1
+      for (int s = 0; s < kSteps; ++s) {
+        if (s == 9) off = 0;
+        const uint8_t* img = (s < 9) ? img_f : img_r;
+        const int nparts = step_nkc(s) * 2;
+        const uint32_t bytes = step_bytes(s);
+#pragma unroll 1
+        for (int ip = 0; ip < nparts; ++ip, off += bytes) {
+          if (NTERMS == 1 && (ip & 1)) continue;          // single-MMA mode streams the hi images only
+          if (round > 0) mbar_wait(&empty[stage], (round - 1) & 1, 100 + (int)stage, s * 16 + ip);
+          if (elect_one()) {
+            mbar_arrive_expect_tx(&full[stage], bytes);
+            bulk_g2s(ring + stage * kRingStageBytes, img + off, bytes, &full[stage]);
+          }
+          __syncwarp();
+          if (++stage == (uint32_t)kStages) { stage = 0; ++round; }
+        }
+      }
+    }
+  } else if (warp == kMmaWarp) {
+    // ===================================== MMA issuer ===================================
+    const uint32_t a_hi_addr = smem_u32(smem + P::a_hi);
+    const uint32_t a_lo_addr = smem_u32(smem + P::a_lo);
+    const uint32_t ring_addr = smem_u32(smem + P::ring);
+    const uint32_t idesc256 = make_idesc_f16(128, 256, Elem<T>::fmt);
+    const uint32_t idesc64 = make_idesc_f16(128, 64, Elem<T>::fmt);
+    const uint32_t idesc16 = make_idesc_f16(128, 16, Elem<T>::fmt);
+    uint32_t stage = 0, round = 0;
+    for (int iter = 0; iter < m.iters; ++iter) {
+#pragma unroll
+      for (int s = 0; s < kSteps; ++s) {
+        const int buf = s & 1;
+        {
+          const uint32_t started = (uint32_t)iter * (buf ? kUses1 : kUses0) + (uint32_t)(s >> 1);
+          if (started > 0) mbar_wait(&acc_empty[buf], (started - 1) & 1, 200 + buf, s);
+        }
+        const int nkc = step_nkc(s);
+        const uint32_t idesc = (s == 8) ? idesc16 : ((s == kLastStep) ? idesc64 : idesc256);
+        const uint32_t d = tmem_base + (uint32_t)buf * 256u;
+#pragma unroll
+        for (int ic = 0; ic < nkc; ++ic) {
+          const int c = (s == 0) ? 4 : ((ic < 4) ? ic : 4);
+          {
+            const uint32_t uses = (c == 4) ? (uint32_t)iter * 2u + (s == kSkipLayer ? 1u : 0u)
+                                           : (uint32_t)iter * kAPerTile + (uint32_t)(s - 1);
+            mbar_wait(&a_ready[c], uses & 1, 300 + c, s);
+          }
+          tc_fence_after();
+          const uint32_t coff = (c == 4) ? 0u : (uint32_t)c * kChunkBytes;   // PE lives in chunk 0
+          const uint64_t ahi = make_sw128_kmajor_desc(a_hi_addr + coff);
+          const uint64_t alo = make_sw128_kmajor_desc(a_lo_addr + coff);
+#pragma unroll
+          for (int part = 0; part < kParts; ++part) {
+            mbar_wait(&full[stage], round & 1, 400 + (int)stage, s * 16 + ic * 2 + part);
+            tc_fence_after();
+            const uint64_t bdesc = make_sw128_kmajor_desc(ring_addr + stage * kRingStageBytes);
+            if (elect_one()) {
+              if (part == 0) {
+#pragma unroll
+                for (int k = 0; k < 4; ++k)
+                  umma_f16(d, ahi + 2 * k, bdesc + 2 * k, idesc, (ic == 0 && k == 0) ? 0u : 1u);
+                if (NTERMS == 3) {
+#pragma unroll
+                  for (int k = 0; k < 4; ++k) umma_f16(d, alo + 2 * k, bdesc + 2 * k, idesc, 1u);
+                }
+              } else {
+#pragma unroll
+                for (int k = 0; k < 4; ++k) umma_f16(d, ahi + 2 * k, bdesc + 2 * k, idesc, 1u);
+              }
+              umma_commit(&empty[stage]);
+            }
+            __syncwarp();
+            if (++stage == (uint32_t)kStages) { stage = 0; ++round; }
+          }
+          if (s == kSkipLayer && ic == 0) { if (elect_one()) umma_commit(c0_free); __syncwarp(); }
+        }
+        if (elect_one()) umma_commit(&acc_full[buf]);
+        __syncwarp();
+      }
+    }
+  } else {
+    // ===================================== epilogue warps ================================
+    // warp = 4*sub + q: q = TMEM lane quarter (rows 32q..32q+31 = points), sub = 16-column slice of every
+    // 64-column chunk.  All 16 warps convert the same chunk, so chunk c of the next step's A tile is
+    // complete after (c+1)/4 of the epilogue and its MMAs start then.
+    const int q = warp & 3, sub = warp >> 2;
+    const int row = q * 32 + lane;
+    const uint32_t lane_taddr = tmem_base + ((uint32_t)(q * 32) << 16);
+    uint8_t* A_hi = smem + P::a_hi;
+    uint8_t* A_lo = smem + P::a_lo;
+    const float k1 = kSoftplusBeta * kInvWeightScale;
+    const float b8 = bias100[8 * kHidden];
+    const float* w8 = reinterpret_cast<const float*>(m.packed + hdr->weff_layer_off[8]);
+    const int out3 = (int)hdr->out_dim[kSkipLayer - 1];
+    // this thread's sigma words: ((l*4 + chunk)*16 + warp)*512 + g*256 + lane*8
+    float* sg_base = args.scratch + (size_t)blockIdx.x * kSigmaFloatsPerCta + (size_t)warp * 512 + lane * 8;
+    auto sg_ptr = [&](int l, int chunk) -> float* { return sg_base + (size_t)(l * 4 + chunk) * 8192; };
+    const float gz[3] = {0.f, 0.f, 0.f};
+
+    for (int iter = 0; iter < m.iters; ++iter) {
+      const long long tile = (long long)blockIdx.x + (long long)iter * gridDim.x;
+      const long long pt = tile * 128 + row;
+      const bool ok = (tile < m.num_tiles) && (pt < m.P);
+      float x[3];
+      load_point(m, pt, net_scale, x);
+      // ------------------------------------------------ input stage: positional encoding -> chunk 0
+      if (sub < 2) {
+        if (sub == 0) pe_stage<NTERMS, 0, T, 0>(m, x, multires, lane, row, pt, tile, false, A_hi, A_lo, gz);
+        else          pe_stage<NTERMS, 0, T, 1>(m, x, multires, lane, row, pt, tile, false, A_hi, A_lo, gz);
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&a_ready[4]);
+      }
+
+      // ------------------------------------------------ forward: hidden layers 0..7 (steps 0..7)
+#pragma unroll 1
+      for (int l = 0; l < 8; ++l) {
+        const int buf = l & 1;
+        const uint32_t acc_par = ((uint32_t)iter * (buf ? kUses1 : kUses0) + (uint32_t)(l >> 1)) & 1;
+        mbar_wait(&acc_full[buf], acc_par, 500 + buf, l);
+        tc_fence_after();
+        const float* bl = bias100 + l * kHidden;
+#pragma unroll 1
+        for (int chunk = 0; chunk < 4; ++chunk) {
+          uint8_t* dst_hi = A_hi + chunk * kChunkBytes;
+          uint8_t* dst_lo = A_lo + chunk * kChunkBytes;
+          const int col0 = chunk * 64 + sub * 16;
+          float4 bv[4];
+#pragma unroll
+          for (int i = 0; i < 4; ++i) bv[i] = __ldg(reinterpret_cast<const float4*>(bl + col0) + i);
+          uint32_t r[16];
+          tmem_ld_32x32b_x16(lane_taddr + (uint32_t)(buf * 256 + col0), r);
+          tmem_wait_ld();
+          float* sgp = sg_ptr(l, chunk);
+#pragma unroll
+          for (int g = 0; g < 2; ++g) {
+            const float4 bA = bv[2 * g], bB = bv[2 * g + 1];
+            const float bb[8] = {bA.x, bA.y, bA.z, bA.w, bB.x, bB.y, bB.z, bB.w};
+            float h[8], sg[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+              h[j] = softplus100<true>(fmaf(__uint_as_float(r[g * 8 + j]), k1, bb[j]), sg[j]);
+            store_group<NTERMS, T>(dst_hi, dst_lo, row, sub * 2 + g, h);
+            st_scratch8(sgp + g * 256, sg);
+          }
+          fence_proxy_async_smem();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&a_ready[chunk]);
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&acc_empty[buf]);
+
+        if (l == kSkipLayer - 1 && sub < 2) {
+          // skip connection: layer 4 = [h4 ; PE]/sqrt2.  Once its MMAs on chunk 0 are done, regenerate
+          // the PE there as the 5th K chunk of layer 4.
+          mbar_wait(c0_free, (uint32_t)iter & 1, 520);
+          if (sub == 0) pe_stage<NTERMS, 0, T, 0>(m, x, multires, lane, row, pt, tile, false, A_hi, A_lo, gz);
+          else          pe_stage<NTERMS, 0, T, 1>(m, x, multires, lane, row, pt, tile, false, A_hi, A_lo, gz);
+          fence_proxy_async_smem();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&a_ready[4]);
+        }
+      }
+
+      // ------------------------------------------------ step 8: output layer -> udf, and alpha_7
+      {
+        mbar_wait(&acc_full[0], ((uint32_t)iter * kUses0 + 4u) & 1, 510);
+        tc_fence_after();
+        const float accv = __uint_as_float(tmem_ld_32x32b_x1(lane_taddr)) * kInvWeightScale;
+        tmem_wait_ld();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&acc_empty[0]);
+        const float a = accv + b8;
+        float gmul = 1.f;
+        if (udf_type == 0) gmul = (a > 0.f) ? 1.f : (a < 0.f ? -1.f : 0.f);
+        else if (udf_type == 1) gmul = 2.f * a;
+        if (sub == 0 && ok) {
+          const float u = (udf_type == 0) ? fabsf(a) : (udf_type == 1 ? a * a : a);
+          m.udf_out[pt] = u / net_scale;
+        }
+        const float gS = gmul * kAdjScale;
+#pragma unroll 1
+        for (int chunk = 0; chunk < 4; ++chunk) {
+          const int col0 = chunk * 64 + sub * 16;
+          const float* sgp = sg_ptr(7, chunk);
+#pragma unroll
+          for (int g = 0; g < 2; ++g) {
+            float sg[8];
+            ld_scratch8(sgp + g * 256, sg);
+            const float4 wA = __ldg(reinterpret_cast<const float4*>(w8 + col0 + g * 8));
+            const float4 wB = __ldg(reinterpret_cast<const float4*>(w8 + col0 + g * 8 + 4));
+            const float ww[8] = {wA.x, wA.y, wA.z, wA.w, wB.x, wB.y, wB.z, wB.w};
+            float v[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) v[j] = gS * ww[j] * sg[j];
+            store_group<NTERMS, T>(A_hi + chunk * kChunkBytes, A_lo + chunk * kChunkBytes, row, sub * 2 + g, v);
+          }
+          fence_proxy_async_smem();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&a_ready[chunk]);
+        }
+      }
+
+      // ------------------------------------------------ reverse: steps 9..15 = layers 7..1
+      float gs[3] = {0.f, 0.f, 0.f};            // this thread's share of J_gamma^T (PE adjoint)
+      const float inv_adj = kInvWeightScale / kAdjScale;
+#pragma unroll 1
+      for (int s = 9; s < kLastStep; ++s) {
+        const int l = 16 - s;                   // accumulator = alpha_l W_l  -> alpha_{l-1} = acc . sigma_{l-1}
+        const int buf = s & 1;
+        // sigma of the current chunk; chunk 0 is fetched before the accumulator wait, chunk c+1 as soon as
+        // chunk c's values are consumed (its L2 latency then overlaps the conversions and stores of chunk c)
+        float sgc[16];
+        auto fetch_sigma = [&](int chunk) {
+          const float* sgp = sg_ptr(l - 1, chunk);
+          float t0[8], t1[8];
+          ld_scratch8(sgp, t0); ld_scratch8(sgp + 256, t1);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) { sgc[j] = t0[j]; sgc[8 + j] = t1[j]; }
+        };
+        fetch_sigma(0);
+        mbar_wait(&acc_full[buf], ((uint32_t)iter * (buf ? kUses1 : kUses0) + (uint32_t)(s >> 1)) & 1, 530 + buf, s);
+        tc_fence_after();
+#pragma unroll
+        for (int chunk = 0; chunk < 4; ++chunk) {
+          const int col0 = chunk * 64 + sub * 16;
+          uint32_t r[16];
+          tmem_ld_32x32b_x16(lane_taddr + (uint32_t)(buf * 256 + col0), r);
+          tmem_wait_ld();
+          float v[16];
+#pragma unroll
+          for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(r[j]) * kInvWeightScale * sgc[j];
+          if (chunk < 3) fetch_sigma(chunk + 1);
+          if (chunk == 3 && l == kSkipLayer) {
+            // columns n >= out3 of alpha_4 W_4 are the adjoint of the skip input's PE part (slot
+            // k = n - (out3-1) >= 1): contract them with J_gamma now; they are not inputs of layer 3.
+            const int kbase = col0 - (out3 - 1);
+            float adj[16];
+#pragma unroll
+            for (int j = 0; j < 16; ++j) adj[j] = __uint_as_float(r[j]) * inv_adj;
+            pe_adjoint16(adj, kbase, x, multires, gs);
+#pragma unroll
+            for (int j = 0; j < 16; ++j) if (kbase + j >= 1) v[j] = 0.f;
+          }
+#pragma unroll
+          for (int g = 0; g < 2; ++g) {
+            float v8[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) v8[j] = v[g * 8 + j];
+            store_group<NTERMS, T>(A_hi + chunk * kChunkBytes, A_lo + chunk * kChunkBytes, row, sub * 2 + g, v8);
+          }
+          fence_proxy_async_smem();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&a_ready[chunk]);
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&acc_empty[buf]);
+      }
+
+      // ------------------------------------------------ step 16: alpha_0 W_0 (64 PE slots) -> d udf / d x
+      {
+        mbar_wait(&acc_full[0], ((uint32_t)iter * kUses0 + 8u) & 1, 540);
+        tc_fence_after();
+        uint32_t r[16];
+        tmem_ld_32x32b_x16(lane_taddr + (uint32_t)(sub * 16), r);
+        tmem_wait_ld();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&acc_empty[0]);
+        float adj[16];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) adj[j] = __uint_as_float(r[j]) * inv_adj;
+        pe_adjoint16(adj, sub * 16, x, multires, gs);
+        // sum the four column slices of a point: the A tile is dead here (every MMA of the tile has
+        // completed), 16 bytes per (point, sub) serve as the exchange -- inside the chunk-3 rows of this
+        // lane quarter (rows 32q..32q+15), which only its own four warps write later; they meet on a named
+        // barrier before and after.
+        float4* slots = reinterpret_cast<float4*>(A_hi + 3 * kChunkBytes + (q * 32 + (lane >> 1)) * 128 + (lane & 1) * 64);
+        slots[sub] = make_float4(gs[0], gs[1], gs[2], 0.f);
+        named_bar_sync(1 + q, 128);
+        if (sub == 0 && ok) {
+          const float4 s0 = slots[0], s1 = slots[1], s2 = slots[2], s3 = slots[3];
+          m.grad_out[pt * 3 + 0] = (s0.x + s1.x) + (s2.x + s3.x);
+          m.grad_out[pt * 3 + 1] = (s0.y + s1.y) + (s2.y + s3.y);
+          m.grad_out[pt * 3 + 2] = (s0.z + s1.z) + (s2.z + s3.z);
+        }
+        named_bar_sync(1 + q, 128);
+      }
+    }
+  }
+
+  // ---- teardown
+  tc_fence_before();
+  __syncthreads();
+  if (warp == kMmaWarp) tmem_dealloc(tmem_base, 512);
+}
+
+template <int NTERMS, typename T>
+static int launch(const Args& a_in, size_t scratch_bytes, cudaStream_t stream) {
+  Args a = a_in;
+  const long long tiles = (a.m.P + 127) / 128;
+  if (tiles > 0x7fffffffLL) return set_error("too many points");
+  a.m.num_tiles = (int)tiles;
+  int grid = sm_count();
+  if (tiles < grid) grid = (int)tiles;
+  a.m.iters = (int)((tiles + grid - 1) / grid);
+  if (scratch_bytes < (size_t)grid * kSigmaFloatsPerCta * sizeof(float))
+    return set_error("emap_udf_forward_grad_rev: scratch too small (%zu bytes, need %zu)", scratch_bytes,
+                     (size_t)grid * kSigmaFloatsPerCta * sizeof(float));
+  auto kern = mlp_rgrad_kernel<NTERMS, T>;
+  static bool attr_done = false;   // per template instantiation
+  if (!attr_done) {
+    EMAP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Plan<NTERMS>::total));
+    attr_done = true;
+  }
+  kern<<<grid, kThreads, Plan<NTERMS>::total, stream>>>(a);
+  EMAP_CUDA(cudaGetLastError());
+  return 0;
+}
+
+}  // namespace rg
+}  // namespace emap
+
+using namespace emap;
+
+extern "C" size_t emap_rgrad_scratch_bytes(void) {
+  return (size_t)sm_count() * rg::kSigmaFloatsPerCta * sizeof(float);
+}
+
+extern "C" int emap_udf_forward_grad_rev(const emap_net_desc* net, const void* packed, int precision,
+                                         const float* pts, const float* rays_o, const float* rays_d,
+                                         const float* z, int32_t n_per_ray, int64_t P, float* udf_out,
+                                         float* grad_out, void* scratch, size_t scratch_bytes, void* stream) {
+  if (check_net(net)) return 1;
+  if (!packed || !udf_out || !grad_out || !scratch) return set_error("emap_udf_forward_grad_rev: NULL pointer");
+  if (P <= 0) return set_error("P must be > 0");
+  if (!pts) {
+    if (!rays_o || !rays_d || !z) return set_error("give either pts or (rays_o, rays_d, z)");
+    if (n_per_ray <= 0 || P % n_per_ray) return set_error("P must be a multiple of n_per_ray");
+  }
+  PackedHeader h; std::vector<RingItem> t1, t3;
+  build_layout(*net, h, t1, t3);
+  rg::Args a;
+  memset(&a, 0, sizeof(a));
+  a.m.packed = (const uint8_t*)packed; a.m.pts = pts; a.m.rays_o = rays_o; a.m.rays_d = rays_d; a.m.z = z;
+  a.m.n_per_ray = n_per_ray; a.m.P = P; a.m.udf_out = udf_out; a.m.grad_out = grad_out;
+  a.scratch = (float*)scratch;
+  a.rg_off = h.reserved[3];
+  cudaStream_t st = (cudaStream_t)stream;
+  if (precision == EMAP_PREC_FP32X3) {
+    if (net->elem_type == 0) return rg::launch<3, __half>(a, scratch_bytes, st);
+    return rg::launch<3, __nv_bfloat16>(a, scratch_bytes, st);
+  } else if (precision == EMAP_PREC_HALF) {
+    if (net->elem_type == 0) return rg::launch<1, __half>(a, scratch_bytes, st);
+    return rg::launch<1, __nv_bfloat16>(a, scratch_bytes, st);
+  }
+  return set_error("precision must be EMAP_PREC_FP32X3 (3) or EMAP_PREC_HALF (1)");
+}

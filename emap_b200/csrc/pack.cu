@@ -8,6 +8,8 @@
 //     of W * 16 (hi part) and of the residual (lo part) -- exactly the byte layout tcgen05.mma
 //     expects in shared memory, so the MLP kernel streams them with 1-D bulk copies.
 //   * the two "ring item" tables (1-term and 3-term MMA schedules) describing the stream order.
+//   * the W^T images of the backward's reverse sweep (hi only) and of the reverse-mode gradient
+//     kernel (hi and lo; mlp_rg.cu).
 #include <math.h>
 #include <string.h>
 #include <vector>
@@ -34,6 +36,11 @@ size_t flat_param_count(int multires) {
 }
 
 static inline uint32_t align_up(uint32_t x, uint32_t a) { return (x + a - 1) / a * a; }
+
+constexpr int kRgBigImages = 7 * 4 * 2;          // layers 7..1 x 4 K chunks x (hi, lo)
+constexpr int kRgSmallImages = 4 * 2;            // layer 0
+constexpr uint32_t kRgBigBytes = 256 * 128, kRgSmallBytes = 64 * 128;
+constexpr uint32_t kRgImageBytes = kRgBigImages * kRgBigBytes + kRgSmallImages * kRgSmallBytes;
 
 // Build header + item tables (host).  Deterministic function of (multires, elem_type).
 void build_layout(const emap_net_desc& net, PackedHeader& h, std::vector<RingItem>& t1,
@@ -117,7 +124,11 @@ void build_layout(const emap_net_desc& net, PackedHeader& h, std::vector<RingIte
   h.reserved[0] = roff;                                   // rev item table offset
   h.reserved[1] = 7 * 4 * 2;                              // number of rev items
   h.reserved[2] = align_up(roff + h.reserved[1] * (uint32_t)sizeof(RingItem), 1024);   // rev images offset
-  h.total_bytes = align_up(h.reserved[2] + h.reserved[1] * (uint32_t)kStageBytes, 1024);
+  // reverse-mode gradient stream (mlp_rg.cu): W_l^T images hi AND lo, l = 7..1 as [256 x 64] operands
+  // (32 KiB), then l = 0 as [64 x 64] operands (8 KiB), in consumption order (layer, K chunk, part).
+  h.reserved[3] = align_up(h.reserved[2] + h.reserved[1] * (uint32_t)kStageBytes, 1024);   // rg images offset
+  h.reserved[4] = kRgImageBytes;
+  h.total_bytes = align_up(h.reserved[3] + kRgImageBytes, 1024);
 }
 
 void build_rev_items(const PackedHeader& h, std::vector<RingItem>& tr) {
@@ -238,6 +249,56 @@ __global__ void pack_rev_images_kernel(uint8_t* __restrict__ packed) {
   }
 }
 
+// Reverse-mode gradient images (mlp_rg.cu).  Image b of the stream: b < 56: layer l = 7 - b/8, K chunk
+// kc = (b%8)/2, part b&1, [256 x 64]; b >= 56: layer 0, kc = (b-56)/2, part (b-56)&1, [64 x 64].
+//   value(n, kk) = 16 * W_l[out = 64 kc + kk][in = src(n)]        (x 1/sqrt2 for the skip layer)
+// i.e. the B operand of  eta_l[n] = sum_out alpha_l[out] W_l[out][n].  src(n) = n, except
+//   layer 4: n < out3 : hidden input n;  n >= out3 : PE entry rg_pe_ref(n - (out3-1)) of the skip input
+//   layer 0: PE entry rg_pe_ref(n)   (row 0 and rows past the PE width are zero).
+// Host-callable so that the CPU tests can build the very same images (emap_debug_rg_image).
+__host__ __device__ inline void rg_image_geom(int b, int& l, int& kc, int& part, int& rows, uint32_t& off) {
+  if (b < kRgBigImages) { l = 7 - b / 8; kc = (b % 8) / 2; part = b & 1; rows = 256; off = (uint32_t)b * kRgBigBytes; }
+  else {
+    const int b2 = b - kRgBigImages;
+    l = 0; kc = b2 / 2; part = b2 & 1; rows = 64; off = kRgBigImages * kRgBigBytes + (uint32_t)b2 * kRgSmallBytes;
+  }
+}
+__host__ __device__ inline float rg_image_value(const float* W, int l, int od, int id, int multires, int kc,
+                                                int n, int kk) {
+  const int pe = 3 + 6 * multires, out3 = kHidden - pe;
+  const int out_idx = kc * 64 + kk;
+  if (out_idx >= od) return 0.f;
+  int src;
+  float mul = 1.f;
+  if (l == 0) {
+    src = rg_pe_ref(n, multires);
+  } else if (l == kSkipLayer) {
+    mul = 0.70710678118654752440f;
+    if (n < out3) src = n;
+    else { const int r = rg_pe_ref(n - (out3 - 1), multires); src = (r >= 0) ? out3 + r : -1; }
+  } else {
+    src = n;
+  }
+  if (src < 0 || src >= id) return 0.f;
+  return W[(size_t)out_idx * id + src] * mul * kWeightScale;
+}
+
+template <typename T>
+__global__ void pack_rg_images_kernel(uint8_t* __restrict__ packed) {
+  const PackedHeader* h = reinterpret_cast<const PackedHeader*>(packed);
+  int l, kc, part, rows; uint32_t off;
+  rg_image_geom((int)blockIdx.x, l, kc, part, rows, off);
+  const int od = (int)h->out_dim[l], id = (int)h->in_dim[l];
+  const float* W = reinterpret_cast<const float*>(packed + h->weff_layer_off[l]);
+  T* img = reinterpret_cast<T*>(packed + h->reserved[3] + off);
+  for (int e = threadIdx.x; e < rows * 64; e += blockDim.x) {
+    const int n = e >> 6, kk = e & 63;
+    const float val = rg_image_value(W, l, od, id, (int)h->multires, kc, n, kk);
+    const T hi = to_elem<T>(val);
+    img[sw128_offset(n, kk) >> 1] = (part == 0) ? hi : to_elem<T>(val - from_elem<T>(hi));
+  }
+}
+
 // ---- host entry points -------------------------------------------------------------------------
 int check_net(const emap_net_desc* net) {
   if (!net) return set_error("net desc is NULL");
@@ -298,5 +359,30 @@ extern "C" int emap_wn_fold(const emap_net_desc* net, const float* flat_params, 
   else
     pack_rev_images_kernel<__nv_bfloat16><<<(unsigned)tr.size(), 256, 0, stream>>>(p);
   EMAP_CUDA(cudaGetLastError());
+  if (net->elem_type == 0)
+    pack_rg_images_kernel<__half><<<kRgBigImages + kRgSmallImages, 256, 0, stream>>>(p);
+  else
+    pack_rg_images_kernel<__nv_bfloat16><<<kRgBigImages + kRgSmallImages, 256, 0, stream>>>(p);
+  EMAP_CUDA(cudaGetLastError());
   return 0;
 }
+
+// Test hook (HOST memory, no GPU needed): the un-split fp32 value image b of the reverse-mode gradient
+// stream as the pack kernel computes it, from HOST W_eff matrices of the layer (row-major [out,in]).
+// out_host: [rows x 64] floats, row-major (n, kk) -- no swizzle.  Returns rows (256 or 64), or -1.
+extern "C" int emap_debug_rg_image(const emap_net_desc* net, int b, const float* W_host, float* out_host,
+                                   int32_t* layer_kc_part /*[3]*/) {
+  if (check_net(net)) return -1;
+  if (b < 0 || b >= kRgBigImages + kRgSmallImages || !W_host || !out_host) { set_error("emap_debug_rg_image: bad arguments"); return -1; }
+  int l, kc, part, rows; uint32_t off;
+  rg_image_geom(b, l, kc, part, rows, off);
+  int in_dim[kNumLinear], out_dim[kNumLinear];
+  net_dims(net->multires, in_dim, out_dim);
+  for (int n = 0; n < rows; ++n)
+    for (int kk = 0; kk < 64; ++kk)
+      out_host[n * 64 + kk] = rg_image_value(W_host, l, out_dim[l], in_dim[l], net->multires, kc, n, kk);
+  if (layer_kc_part) { layer_kc_part[0] = l; layer_kc_part[1] = kc; layer_kc_part[2] = part; }
+  return rows;
+}
+extern "C" int emap_debug_pe_col_to_ref(int col, int multires) { return pe_col_to_ref(col, multires); }
+extern "C" int emap_debug_rg_pe_ref(int k, int multires) { return rg_pe_ref(k, multires); }

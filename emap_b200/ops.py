@@ -6,6 +6,7 @@ CUDA stream.  Used by the drop-in classes in udf_model.py / udf_renderer_blendin
 from __future__ import annotations
 
 import ctypes
+import os
 from typing import Optional, Tuple
 
 import torch
@@ -71,12 +72,49 @@ def udf_forward(net: PackedNet, precision: int, pts=None, rays_o=None, rays_d=No
     return udf, pe
 
 
-def udf_forward_grad(net: PackedNet, precision: int, pts=None, rays_o=None, rays_d=None, z=None
-                     ) -> Tuple[torch.Tensor, torch.Tensor]:
+# How (udf, d udf/dx) is evaluated: "forward" = K1g, forward-mode tangent rows (validated on B200, the
+# default); "reverse" = K1r, value forward + adjoint sweep in one kernel (mlp_rg.cu; half the tensor-core
+# work -- built and CPU-emulated in round 1, not yet run on hardware, hence opt-in).
+_GRAD_MODE = os.environ.get("EMAP_GRAD_MODE", "forward")
+_RG_SCRATCH = {}
+
+
+def set_grad_mode(mode: str) -> None:
+    global _GRAD_MODE
+    if mode not in ("forward", "reverse"):
+        raise ValueError("grad mode must be 'forward' or 'reverse'")
+    _GRAD_MODE = mode
+
+
+def get_grad_mode() -> str:
+    return _GRAD_MODE
+
+
+def _rg_scratch(dev: torch.device) -> torch.Tensor:
+    """K1r's sigma scratch (1 MiB per SM), one per device; kernels on one stream reuse it in order."""
+    key = (dev.type, dev.index if dev.index is not None else torch.cuda.current_device())
+    buf = _RG_SCRATCH.get(key)
+    if buf is None:
+        with torch.cuda.device(dev):
+            nbytes = int(C.lib().emap_rgrad_scratch_bytes())
+        buf = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+        _RG_SCRATCH[key] = buf
+    return buf
+
+
+def udf_forward_grad(net: PackedNet, precision: int, pts=None, rays_o=None, rays_d=None, z=None,
+                     mode: Optional[str] = None) -> Tuple[torch.Tensor, torch.Tensor]:
     pts, ro, rd, zz, n, P = _points_args(pts, rays_o, rays_d, z)
     dev = net.packed.device
     udf = torch.empty(P, dtype=torch.float32, device=dev)
     grad = torch.empty(P, 3, dtype=torch.float32, device=dev)
+    if (mode or _GRAD_MODE) == "reverse":
+        scratch = _rg_scratch(dev)
+        C.check(C.lib().emap_udf_forward_grad_rev(ctypes.byref(net.desc), C.ptr(net.packed), precision,
+                                                  C.ptr(pts), C.ptr(ro), C.ptr(rd), C.ptr(zz), n, P,
+                                                  C.ptr(udf), C.ptr(grad), C.ptr(scratch), scratch.numel(),
+                                                  C.stream()))
+        return udf, grad
     C.check(C.lib().emap_udf_forward_grad(ctypes.byref(net.desc), C.ptr(net.packed), precision,
                                           C.ptr(pts), C.ptr(ro), C.ptr(rd), C.ptr(zz), n, P,
                                           C.ptr(udf), C.ptr(grad), C.stream()))

@@ -68,6 +68,17 @@ int emap_udf_forward_grad(const emap_net_desc* net, const void* packed, int prec
                           const float* z, int32_t n_per_ray, int64_t P, float* udf_out,
                           float* grad_out, void* stream);
 
+/* ---- K1r: the same result as K1g by REVERSE mode (value-only forward that keeps softplus' of every
+ * layer, then the adjoint sweep with the W^T operand images): 6 F executed per point instead of 12 F.
+ * replaces: the same reference lines as emap_udf_forward_grad.  `scratch` = emap_rgrad_scratch_bytes()
+ * bytes of device memory (1 MiB per SM, rewritten tile after tile -> L2-resident), reusable across
+ * calls on one stream.  Selected by the host shim with EMAP_GRAD_MODE=reverse / ops.set_grad_mode().  */
+size_t emap_rgrad_scratch_bytes(void);
+int emap_udf_forward_grad_rev(const emap_net_desc* net, const void* packed, int precision,
+                              const float* pts, const float* rays_o, const float* rays_d,
+                              const float* z, int32_t n_per_ray, int64_t P, float* udf_out,
+                              float* grad_out, void* scratch, size_t scratch_bytes, void* stream);
+
 /* ---- K1b: backward of (udf, d udf/dx) w.r.t. the 462,980 MLP parameters -------------------------
  * replaces: autograd through UDFNetwork.forward + .gradient(create_graph=True)
  * (udf_model.py:90-135; loss.backward() at runner_udf.py:167).  Round-1 structure: the element-wise
@@ -197,6 +208,14 @@ int emap_debug_set_clk_buffer(void* dev_buf_144_int64);
 int emap_debug_mlp(const emap_net_desc* net, const void* packed, int precision, int mode,
                    const float* pts, int64_t P, float* udf_out, float* grad_out, float* dbg_acc,
                    void* stream);
+/* test hooks on HOST memory (no GPU needed): the un-split fp32 value image `b` (0..63) of the K1r
+ * reverse stream from the HOST W_eff matrix of its layer -> out_host [rows x 64] (rows returned: 256 or
+ * 64; -1 on error), layer_kc_part[3] (optional) = {layer, K chunk, hi/lo part}; and the two PE column
+ * maps of the kernels (kernel column / K1r slot -> reference PE index, -1 = padding).              */
+int emap_debug_rg_image(const emap_net_desc* net, int b, const float* W_host, float* out_host,
+                        int32_t* layer_kc_part);
+int emap_debug_pe_col_to_ref(int col, int multires);
+int emap_debug_rg_pe_ref(int k, int multires);
 
 #ifdef __cplusplus
 }

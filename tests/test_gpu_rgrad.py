@@ -1,0 +1,125 @@
+"""GPU parity: K1r, forward + REVERSE-mode gradient in one tcgen05 kernel (emap_b200/csrc/mlp_rg.cu),
+against the reference-generated fixtures, the CPU oracle and the validated forward-mode kernel K1g.
+
+Status: written and compiled for sm_100a in round 1 after the round's GPU budget was spent; its
+algorithm, operand images and column maps are pinned on the CPU (tests/test_rg_emulation.py), its
+synchronisation has NOT run on hardware yet.  It is therefore opt-in in the product
+(EMAP_GRAD_MODE=reverse / ops.set_grad_mode) and these tests run only with EMAP_EXPERIMENTAL=1, so that
+the round-end GPU suite reports the state of the validated default path.  First GPU call of the next
+round: `EMAP_EXPERIMENTAL=1 python -m pytest tests/test_gpu_rgrad.py -x -q`.
+
+Tolerances: the ones K1g is held to (tests/test_gpu_mlp.py): fp32x3 5e-5 relative to max(1, |ref|max);
+fp16 3e-3 / 1e-2.
+"""
+import os
+
+import pytest
+import torch
+
+from tests.helpers import maxdiff, oracle_params
+
+pytestmark = [
+    pytest.mark.gpu,
+    pytest.mark.skipif(os.environ.get("EMAP_EXPERIMENTAL") != "1",
+                       reason="K1r not yet validated on hardware: set EMAP_EXPERIMENTAL=1 to run"),
+    pytest.mark.timeout(300),
+]
+
+
+def _net(pert, multires=10, elem="fp16", udf_type="abs", scale=1.0):
+    from emap_b200 import ops
+    p = oracle_params(pert, multires)
+    flat = torch.cat([t.reshape(-1) for t in p.tensors()]).cuda()
+    net = ops.PackedNet(multires, udf_type=udf_type, scale=scale, elem_type=elem)
+    net.fold(flat)
+    return net, p
+
+
+@pytest.mark.parametrize("pert", [False, True])
+@pytest.mark.parametrize("prec,tol_u,tol_g", [("fp32", 5e-5, 5e-5), ("fp16", 3e-3, 1e-2)])
+def test_reverse_mode_vs_reference(golden, pert, prec, tol_u, tol_g):
+    from emap_b200 import ops, _cabi as C
+    g = golden("mlp_pert" if pert else "mlp_init")
+    net, _ = _net(pert)
+    x = g["x"].cuda()
+    udf, grad = ops.udf_forward_grad(net, C.PRECISIONS[prec], pts=x, mode="reverse")
+    torch.cuda.synchronize()
+    ref_u, ref_g = g["udf"][:, 0], g["grad"][:, 0]
+    assert maxdiff(udf.cpu(), ref_u) <= tol_u * max(1.0, float(ref_u.abs().max()))
+    assert maxdiff(grad.cpu(), ref_g) <= tol_g * max(1.0, float(ref_g.abs().max()))
+
+
+def test_reverse_mode_multires6(golden):
+    from emap_b200 import ops, _cabi as C
+    g = golden("mlp_mr6_pert")
+    net, _ = _net(True, multires=6)
+    udf, grad = ops.udf_forward_grad(net, C.PREC_FP32X3, pts=g["x"].cuda(), mode="reverse")
+    assert maxdiff(udf.cpu(), g["out"][:, 0]) <= 5e-5 * max(1.0, float(g["out"].abs().max()))
+    assert maxdiff(grad.cpu(), g["grad"][:, 0]) <= 5e-5 * max(1.0, float(g["grad"].abs().max()))
+
+
+def test_reverse_mode_rays_ragged_many_tiles_and_repeatable():
+    """points given as rays, P not a multiple of 128, several tiles per CTA (the scratch slice and every
+    barrier phase are reused), two runs bit-identical, and agreement with K1g far below the tolerance."""
+    from emap_b200 import ops, _cabi as C
+    from oracle import emap_oracle as O
+    net, p = _net(True)
+    B, n = 6011, 11                                   # 66,121 points -> 517 tiles on 148 CTAs
+    o, d = O.synthetic_rays(B)
+    z = torch.rand(B, n) * 3 + 0.5
+    args = dict(rays_o=o.cuda(), rays_d=d.cuda(), z=z.cuda())
+    u1, g1 = ops.udf_forward_grad(net, C.PREC_FP32X3, mode="reverse", **args)
+    u2, g2 = ops.udf_forward_grad(net, C.PREC_FP32X3, mode="reverse", **args)
+    uf, gf = ops.udf_forward_grad(net, C.PREC_FP32X3, mode="forward", **args)
+    torch.cuda.synchronize()
+    assert torch.equal(u1, u2) and torch.equal(g1, g2)
+    assert maxdiff(u1, uf) <= 5e-5 and maxdiff(g1, gf) <= 5e-5
+    sel = torch.randperm(B * n)[:4096]
+    pts = (o[:, None, :] + d[:, None, :] * z[..., None]).reshape(-1, 3)[sel]
+    ref_u = O.udf_forward(p, pts)[0][:, 0]
+    ref_g = O.udf_gradient(p, pts).detach()
+    assert maxdiff(u1.cpu()[sel], ref_u) <= 5e-5 * max(1.0, float(ref_u.abs().max()))
+    assert maxdiff(g1.cpu()[sel], ref_g) <= 5e-5 * max(1.0, float(ref_g.abs().max()))
+
+
+@pytest.mark.parametrize("udf_type,scale", [("square", 1.0), ("sdf", 1.0), ("abs", 0.5)])
+def test_reverse_mode_udf_types_and_scale(udf_type, scale):
+    from emap_b200 import ops, _cabi as C
+    from oracle import emap_oracle as O
+    net, p = _net(True, udf_type=udf_type, scale=scale)
+    p.udf_type, p.scale = udf_type, scale
+    torch.manual_seed(11)
+    x = (torch.rand(700, 3) * 2 - 1) * 0.9
+    udf, grad = ops.udf_forward_grad(net, C.PREC_FP32X3, pts=x.cuda(), mode="reverse")
+    ref_u = O.udf_forward(p, x)[0][:, 0]
+    ref_g = O.udf_gradient(p, x).detach()
+    assert maxdiff(udf.cpu(), ref_u) <= 5e-5 * max(1.0, float(ref_u.abs().max()))
+    assert maxdiff(grad.cpu(), ref_g) <= 5e-5 * max(1.0, float(ref_g.abs().max()))
+
+
+def test_render_with_reverse_mode_matches_default():
+    """the drop-in renderer end to end with K1r selected: same outputs as with K1g within the MLP tolerance."""
+    from emap_b200 import ops
+    from emap_b200.udf_model import BetaNetwork, SingleVarianceNetwork, UDFNetwork
+    from emap_b200.udf_renderer_blending import UDFRendererBlending
+    from oracle import emap_oracle as O
+    torch.manual_seed(0)
+    net = UDFNetwork(3, 1, 256, 8, skip_in=[4], multires=10).cuda()
+    var, beta = SingleVarianceNetwork(0.3).cuda(), BetaNetwork(0.5, 0.3, 0.3, 5e-5, True, True, False).cuda()
+    r = UDFRendererBlending(None, net, var, beta, n_samples=64, n_importance=64, n_outside=0,
+                            up_sample_steps=4, perturb=1.0, device="cuda")
+    B = 256
+    o, d = O.synthetic_rays(B)
+    near, far, ds = torch.full((B, 1), 0.05), torch.full((B, 1), 6.0), torch.ones(B, 1)
+    outs = {}
+    for mode in ("forward", "reverse"):
+        ops.set_grad_mode(mode)
+        try:
+            torch.manual_seed(7)
+            with torch.no_grad():
+                outs[mode] = r.render(o.cuda(), d.cuda(), near.cuda(), far.cuda(), ds.cuda(),
+                                      cos_anneal_ratio=1.0, flip_saturation=0.9)
+        finally:
+            ops.set_grad_mode("forward")
+    for k in ("edge", "depth", "weights", "gradients", "udf"):
+        assert maxdiff(outs["forward"][k], outs["reverse"][k]) <= 2e-3, k

@@ -1,0 +1,207 @@
+"""CPU: the algorithm of the reverse-mode gradient kernel K1r (emap_b200/csrc/mlp_rg.cu), emulated step by
+step in float64 from the operand images the LIBRARY builds (emap_debug_rg_image: the same
+`rg_image_value` the pack kernel runs, on host memory), against autograd through the oracle.
+
+What this pins without a GPU: the image stream order (layer 7..1 then 0, K chunk, part), the W^T
+orientation, the skip layer's [hidden ; PE] row order and its 1/sqrt2, the PE slot order `rg_pe_ref` and
+the kernel's closed-form decoding of it in `pe_adjoint16`, the masks, and the adjoint recurrence itself.
+What it cannot pin: the kernel's synchronisation and its fp16 hi/lo arithmetic (GPU parity tests).
+"""
+import ctypes
+import math
+
+import numpy as np
+import pytest
+import torch
+
+from emap_b200 import _cabi as C
+from oracle import emap_oracle as O
+from tests.helpers import oracle_params
+
+KW = 16.0  # kWeightScale
+
+
+def _decode_ref(r, multires):
+    """reference PE index (embedder.py:26-35) -> ('x'|'sin'|'cos', j, axis)."""
+    if r < 3:
+        return ("x", 0, r)
+    j, rem = divmod(r - 3, 6)
+    assert j < multires
+    return ("cos" if rem >= 3 else "sin", j, rem % 3)
+
+
+def _decode_kernel(k, multires):
+    """pe_adjoint16's decoding of slot k (mlp_rg.cu), mirrored: None = not a PE entry."""
+    if k < 1:
+        return None
+    if k == 1:
+        return ("x", 0, 1)
+    if k == 2:
+        return ("x", 0, 2)
+    if k == 3:
+        return ("x", 0, 0)
+    qq = (k - 4) >> 1
+    j, ax = divmod(qq, 3)
+    if j >= multires:
+        return None
+    return ("cos" if (k & 1) else "sin", j, ax)
+
+
+@pytest.mark.parametrize("multires", [0, 1, 6, 10])
+def test_slot_decoding_matches_the_image_order(multires):
+    L = C.lib()
+    seen = set()
+    for k in range(-2, 64):
+        r = L.emap_debug_rg_pe_ref(k, multires)
+        dk = _decode_kernel(k, multires)
+        if r < 0:
+            assert dk is None, (k, dk)
+        else:
+            assert dk == _decode_ref(r, multires), (k, r, dk)
+            seen.add(r)
+    assert seen == set(range(3 + 6 * multires))          # every PE entry has exactly one slot
+    # kernel column order of the forward kernels: also a permutation of the reference order + padding
+    cols = [L.emap_debug_pe_col_to_ref(c, multires) for c in range(64)]
+    assert sorted(c for c in cols if c >= 0) == list(range(3 + 6 * multires))
+
+
+def _rg_matrices(p, W):
+    """B_l [n_rows, 256] = un-scaled W^T operand of reverse layer l, assembled from the library's images."""
+    L = C.lib()
+    desc = C.NetDesc(p.multires, 0, 1.0, 0)
+    mats = {}
+    order = []
+    for b in range(64):
+        lkp = (ctypes.c_int32 * 3)()
+        # the layer of image b is a fixed function of b; ask with a dummy call first
+        geom = np.zeros((256, 64), dtype=np.float32)
+        w_any = np.ascontiguousarray(W[1].numpy())
+        L.emap_debug_rg_image(ctypes.byref(desc), b, w_any.ctypes.data, geom.ctypes.data, lkp)
+        l, kc, part = int(lkp[0]), int(lkp[1]), int(lkp[2])
+        order.append((l, kc, part))
+        w = np.ascontiguousarray(W[l].numpy())
+        out = np.zeros((256, 64), dtype=np.float32)
+        rows = L.emap_debug_rg_image(ctypes.byref(desc), b, w.ctypes.data, out.ctypes.data, lkp)
+        assert rows == (64 if l == 0 else 256)
+        if part == 0:
+            mats.setdefault(l, np.zeros((rows, 256)))[:, kc * 64:(kc + 1) * 64] = out[:rows].astype(np.float64) / KW
+    # consumption order of the kernel's producer / issuer: layer 7..1, then 0; K chunk; (hi, lo)
+    expect = [(l, kc, part) for l in (7, 6, 5, 4, 3, 2, 1, 0) for kc in range(4) for part in (0, 1)]
+    assert order == expect
+    return mats
+
+
+def _split16(v):
+    """x = hi + lo with two fp16 numbers (store_group / the pack kernels), returned as float64."""
+    hi = v.astype(np.float16)
+    lo = (v - hi.astype(np.float64)).astype(np.float16)
+    return hi.astype(np.float64), lo.astype(np.float64)
+
+
+def _mm(A, Bt, split, a_scale=1.0):
+    """A @ Bt as the tensor cores form it: exact (split=False) or hi*hi + lo*hi + hi*lo of the fp16
+    splits of a_scale*A and 16*B (fp32 accumulation error not modelled)."""
+    if not split:
+        return A @ Bt
+    ah, al = _split16(A.astype(np.float32).astype(np.float64) * a_scale)
+    bh, bl = _split16(Bt * KW)
+    return ((ah + al) @ bh + ah @ bl) / (KW * a_scale)
+
+
+def _emulate(p, x, split=False, adj_scale=16.0):
+    """forward + adjoint sweep exactly as mlp_rgrad_kernel structures it (float64; split=True models the
+    fp16 hi/lo operands of the fp32x3 mode, fp32 activations / sigma / adjoints between the layers)."""
+    mr = p.multires
+    pe = 3 + 6 * mr
+    out3 = 256 - pe
+    W = [w.detach() for w in O.effective_weights(p)]
+    B = _rg_matrices(p, W)
+    Wd = [w.double().numpy() for w in W]
+    bd = [b.detach().double().numpy() for b in p.b]
+    xs = (x.double() * p.scale).numpy()
+    e = O.posenc(torch.from_numpy(xs), mr).numpy()
+    # ---- forward, keeping sigma_l = softplus'(a_l) = sigmoid(100 a_l)
+    h = e
+    sig = []
+    for l in range(8):
+        if l == 4:
+            h = np.concatenate([h, e], axis=1) / math.sqrt(2)
+        a = _mm(h, Wd[l].T, split) + bd[l]
+        t = 100.0 * a
+        h = np.where(t > 20, a, np.log1p(np.exp(np.minimum(t, 20))) / 100.0)
+        s = 1.0 / (1.0 + np.exp(-t))
+        if a.shape[1] < 256:                       # layer 3: padded accumulator columns (bias 0 -> sigma 0.5)
+            s = np.concatenate([s, np.full((a.shape[0], 256 - a.shape[1]), 0.5)], axis=1)
+        if split:
+            h, s = h.astype(np.float32).astype(np.float64), s.astype(np.float32).astype(np.float64)
+        sig.append(s)
+    a8 = (_mm(h, Wd[8].T, split) + bd[8])[:, 0]
+    udf = np.abs(a8) / p.scale
+    gmul = np.sign(a8)
+    # ---- step 8: alpha_7
+    alpha = gmul[:, None] * Wd[8][0][None, :] * sig[7]
+    g = np.zeros((x.shape[0], 3))
+
+    def contract(adj, kbase):
+        for i in range(adj.shape[1]):
+            d = _decode_kernel(kbase + i, mr)
+            if d is None:
+                continue
+            kind, j, ax = d
+            f = float(2 ** j)
+            if kind == "x":
+                g[:, ax] += adj[:, i]
+            elif kind == "sin":
+                g[:, ax] += adj[:, i] * f * np.cos(f * xs[:, ax])
+            else:
+                g[:, ax] -= adj[:, i] * f * np.sin(f * xs[:, ax])
+
+    # ---- steps 9..15: layers 7..1
+    for l in range(7, 0, -1):
+        acc = _mm(alpha, B[l].T, split, adj_scale)   # [P, 256 (n)]
+        v = acc * sig[l - 1]
+        if l == 4:
+            # chunk 3, per 16-column slice `sub` exactly as the epilogue warps see it
+            for sub in range(4):
+                col0 = 192 + 16 * sub
+                kbase = col0 - (out3 - 1)
+                contract(acc[:, col0:col0 + 16], kbase)
+                for j in range(16):
+                    if kbase + j >= 1:
+                        v[:, col0 + j] = 0.0
+        alpha = v
+    # ---- step 16: layer 0
+    acc = _mm(alpha, B[0].T, split, adj_scale)       # [P, 64]
+    for sub in range(4):
+        contract(acc[:, 16 * sub:16 * sub + 16], 16 * sub)
+    return udf, g
+
+
+@pytest.mark.parametrize("multires,pert", [(10, False), (10, True), (6, True)])
+def test_reverse_sweep_emulation_matches_autograd(multires, pert):
+    p = oracle_params(pert, multires).to(torch.float64)
+    torch.manual_seed(3)
+    x = (torch.rand(96, 3, dtype=torch.float64) * 2 - 1) * 0.9
+    ref_u = O.udf_forward(p, x)[0][:, 0].detach().numpy()
+    ref_g = O.udf_gradient(p, x, create_graph=False).detach().numpy()
+    # weights as the kernel sees them: fp32 W_eff (the images are built from the fp32 fold)
+    p32 = oracle_params(pert, multires)
+    udf, g = _emulate(p32, x.float())
+    assert np.abs(udf - ref_u).max() < 2e-6
+    assert np.abs(g - ref_g).max() < 2e-5 * max(1.0, np.abs(ref_g).max())
+
+
+def test_split_fp16_numerics_budget():
+    """fp32x3 arithmetic of K1r (fp16 hi/lo operands, adjoints scaled by 2^4 in the A tile), modelled on
+    the CPU: the gradient stays within the tolerance the GPU parity tests use for K1g (5e-5 abs)."""
+    p64 = oracle_params(True, 10).to(torch.float64)
+    torch.manual_seed(5)
+    x = (torch.rand(128, 3, dtype=torch.float64) * 2 - 1) * 0.9
+    ref_u = O.udf_forward(p64, x.float().double())[0][:, 0].detach().numpy()
+    ref_g = O.udf_gradient(p64, x.float().double(), create_graph=False).detach().numpy()
+    udf, g = _emulate(oracle_params(True, 10), x.float(), split=True)
+    assert np.abs(udf - ref_u).max() < 2e-5
+    assert np.abs(g - ref_g).max() < 5e-5
+    # without the 2^4 scale the lo parts of small adjoints go subnormal: must not be better than with it
+    _, g1 = _emulate(oracle_params(True, 10), x.float(), split=True, adj_scale=1.0)
+    print("grad err scaled", np.abs(g - ref_g).max(), "unscaled", np.abs(g1 - ref_g).max())
