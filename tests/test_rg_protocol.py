@@ -1,0 +1,333 @@
+"""CPU: discrete-event model of the synchronisation protocol of K1r (emap_b200/csrc/mlp_rg.cu).
+
+The kernel could not be run on hardware in the round it was written, so its barrier protocol is
+transcribed here role by role (producer warp, MMA-issuing warp, 16 epilogue warps) with the SAME barrier
+counts, wait parities and use-count formulas as the CUDA source, and executed under randomised latencies
+with mbarrier phase-parity semantics.  The model raises on
+  * deadlock (every role blocked, nothing in flight),
+  * a wait that passes on an aliased phase (detected through the data hazards below),
+  * ring stage overwritten while an MMA still reads it / consumed before its copy landed,
+  * A-tile chunk written while an MMA reading it is in flight, or an MMA reading the wrong version,
+  * TMEM accumulator overwritten before all 16 epilogue warps have read it, or read before complete.
+It does not model the arithmetic (tests/test_rg_emulation.py does) nor PTX memory-ordering fences.
+"""
+import heapq
+import random
+
+import pytest
+
+K_STAGES = {3: 3, 1: 4}
+K_STEPS = 17
+SKIP = 4
+USES = (9, 8)            # accumulator uses per tile: buf 0 / buf 1   (kUses0, kUses1)
+A_PER_TILE = 16          # kAPerTile
+EPI_WARPS = 16
+
+
+def step_nkc(s):
+    return 1 if s == 0 else (5 if s == SKIP else 4)
+
+
+class Hazard(AssertionError):
+    pass
+
+
+class MBar:
+    def __init__(self, name, count):
+        self.name, self.count, self.pending, self.completed, self.tx = name, count, count, 0, 0
+
+    def _maybe_complete(self):
+        if self.pending == 0 and self.tx == 0:
+            self.completed += 1
+            self.pending = self.count
+
+    def arrive(self, tx=0):
+        assert self.pending > 0, f"too many arrivals on {self.name}"
+        self.tx += tx
+        self.pending -= 1
+        self._maybe_complete()
+
+    def complete_tx(self, n):
+        self.tx -= n
+        assert self.tx >= 0
+        self._maybe_complete()
+
+    def test(self, parity):
+        """mbarrier.try_wait.parity: true iff the phase with this parity has completed, i.e. the phase in
+        progress has the other parity.  (A barrier two phases ahead of its waiter aliases -- on purpose.)"""
+        return (self.completed & 1) != (parity & 1)
+
+
+class Sim:
+    def __init__(self, nterms, iters, seed):
+        self.rng = random.Random(seed)
+        self.nterms, self.iters = nterms, iters
+        self.parts = 2 if nterms == 3 else 1
+        ns = K_STAGES[nterms]
+        self.ns = ns
+        self.full = [MBar(f"full{i}", 1) for i in range(ns)]
+        self.empty = [MBar(f"empty{i}", 1) for i in range(ns)]
+        self.a_ready = [MBar(f"a_ready{i}", EPI_WARPS) for i in range(4)] + [MBar("a_ready4", 8)]
+        self.acc_full = [MBar("acc_full0", 1), MBar("acc_full1", 1)]
+        self.acc_empty = [MBar("acc_empty0", EPI_WARPS), MBar("acc_empty1", EPI_WARPS)]
+        self.c0_free = MBar("c0_free", 1)
+        self.now = 0.0
+        self.events = []          # (time, seq, fn)
+        self.seq = 0
+        # ---- resource state for the hazard checks
+        self.stage_data = [None] * ns           # (iter, s, ic, part) landed in the stage
+        self.stage_copying = [False] * ns
+        self.stage_readers = [0] * ns           # MMAs in flight reading the stage
+        # A chunk c: per-warp version tags + MMAs in flight reading it
+        self.chunk_ver = [[None] * EPI_WARPS for _ in range(4)]
+        self.chunk_readers = [0] * 4
+        self.acc_ver = [None, None]             # (iter, s) once complete
+        self.acc_writing = [None, None]         # (iter, s) while MMAs in flight
+        self.acc_reads_left = [0, 0]            # epilogue warps that still have to read the current version
+        self.mma_queue = []                     # in-order completion of the tensor pipe
+        self.mma_busy_until = 0.0
+        self.blocked = {}
+        self.done = 0
+
+    # ------------------------------------------------------------------ event plumbing
+    def at(self, dt, fn):
+        self.seq += 1
+        heapq.heappush(self.events, (self.now + dt, self.seq, fn))
+
+    def lat(self, lo, hi):
+        return self.rng.uniform(lo, hi)
+
+    def run_role(self, name, gen):
+        """advance a role until it blocks on a barrier or finishes"""
+        try:
+            while True:
+                op = next(gen)
+                if op[0] == "wait":
+                    _, bar, parity = op
+                    if not bar.test(parity):
+                        self.blocked[name] = (gen, bar, parity)
+                        return
+                elif op[0] == "delay":
+                    self.at(op[1], lambda n=name, g=gen: self.run_role(n, g))
+                    return
+        except StopIteration:
+            self.done += 1
+
+    def wake(self):
+        for name in list(self.blocked):
+            gen, bar, parity = self.blocked[name]
+            if bar.test(parity):
+                del self.blocked[name]
+                # a woken role resumes after a small random latency (warp scheduling)
+                self.at(self.lat(0.0, 0.3), lambda n=name, g=gen: self.run_role(n, g))
+
+    def run(self):
+        roles = {"producer": self.producer(), "issuer": self.issuer()}
+        for w in range(EPI_WARPS):
+            roles[f"epi{w}"] = self.epilogue(w)
+        for name, gen in roles.items():
+            self.at(self.lat(0, 1), lambda n=name, g=gen: self.run_role(n, g))
+        nroles = len(roles)
+        while self.events:
+            t, _, fn = heapq.heappop(self.events)
+            self.now = t
+            fn()
+            self.wake()
+        if self.done != nroles:
+            state = {n: (b.name, p, b.completed) for n, (_, b, p) in self.blocked.items()}
+            raise Hazard(f"deadlock: {state}")
+
+    # ------------------------------------------------------------------ asynchronous agents
+    def bulk_copy(self, stage, tag):
+        if self.stage_readers[stage]:
+            raise Hazard(f"copy into ring stage {stage} while an MMA reads it ({tag})")
+        if self.stage_copying[stage]:
+            raise Hazard(f"two copies in flight into ring stage {stage}")
+        self.stage_copying[stage] = True
+        self.stage_data[stage] = None
+
+        def land():
+            self.stage_copying[stage] = False
+            self.stage_data[stage] = tag
+            self.full[stage].complete_tx(1)
+        self.at(self.lat(0.5, 6.0), land)
+
+    def mma_group(self, it, s, ic, part, stage, chunk, buf, first):
+        """the MMAs of one (K chunk, part): reads ring stage + A chunk, accumulates into TMEM buf"""
+        if self.stage_data[stage] != (it, s, ic, part):
+            raise Hazard(f"MMA {(it, s, ic, part)} reads ring stage {stage} holding {self.stage_data[stage]}")
+        want = ("PE", it, s) if chunk == 4 else (it, s)
+        phys = 0 if chunk == 4 else chunk
+        writers = range(8) if chunk == 4 else range(EPI_WARPS)      # warps sub<2 = warps 0..7 write the PE
+        for w in writers:
+            if self.chunk_ver[phys][w] != want:
+                raise Hazard(f"MMA {(it, s, ic, part)} reads chunk {phys}: warp {w} wrote {self.chunk_ver[phys][w]}, want {want}")
+        if first:
+            if self.acc_reads_left[buf]:
+                raise Hazard(f"step {(it, s)} overwrites TMEM buf {buf} with {self.acc_reads_left[buf]} reads outstanding")
+            self.acc_writing[buf] = (it, s)
+            self.acc_ver[buf] = None
+        elif self.acc_writing[buf] != (it, s):
+            raise Hazard(f"accumulating step {(it, s)} into buf {buf} owned by {self.acc_writing[buf]}")
+        self.stage_readers[stage] += 1
+        self.chunk_readers[phys] += 1
+        start = max(self.now, self.mma_busy_until)
+        self.mma_busy_until = start + self.lat(0.5, 2.0)
+
+        def fin():
+            self.stage_readers[stage] -= 1
+            self.chunk_readers[phys] -= 1
+        self.mma_queue.append((self.mma_busy_until, fin))
+        self.at(self.mma_busy_until - self.now, self._retire)
+
+    def _retire(self):
+        while self.mma_queue and self.mma_queue[0][0] <= self.now + 1e-12:
+            self.mma_queue.pop(0)[1]()
+
+    def commit(self, fn):
+        """tcgen05.commit: fires once every MMA issued so far has completed"""
+        t = max(self.mma_busy_until, self.now)
+        self.at(t - self.now + 1e-9, fn)
+
+    # ------------------------------------------------------------------ roles (mirroring mlp_rg.cu)
+    def producer(self):
+        stage, rnd = 0, 0
+        for it in range(self.iters):
+            for s in range(K_STEPS):
+                for ip in range(step_nkc(s) * 2):
+                    if self.nterms == 1 and (ip & 1):
+                        continue
+                    if rnd > 0:
+                        yield ("wait", self.empty[stage], (rnd - 1) & 1)
+                    self.full[stage].arrive(tx=1)                   # arrive.expect_tx
+                    self.bulk_copy(stage, (it, s, ip // 2, ip & 1))
+                    yield ("delay", self.lat(0.05, 0.3))
+                    stage += 1
+                    if stage == self.ns:
+                        stage, rnd = 0, rnd + 1
+
+    def issuer(self):
+        stage, rnd = 0, 0
+        for it in range(self.iters):
+            for s in range(K_STEPS):
+                buf = s & 1
+                started = it * USES[buf] + (s >> 1)
+                if started > 0:
+                    yield ("wait", self.acc_empty[buf], (started - 1) & 1)
+                for ic in range(step_nkc(s)):
+                    c = 4 if s == 0 else (ic if ic < 4 else 4)
+                    uses = (it * 2 + (1 if s == SKIP else 0)) if c == 4 else (it * A_PER_TILE + (s - 1))
+                    yield ("wait", self.a_ready[c], uses & 1)
+                    for part in range(self.parts):
+                        yield ("wait", self.full[stage], rnd & 1)
+                        self.mma_group(it, s, ic, part, stage, c, buf, first=(ic == 0 and part == 0))
+                        st = stage
+                        self.commit(lambda st=st: self.empty[st].arrive())
+                        yield ("delay", self.lat(0.05, 0.4))
+                        stage += 1
+                        if stage == self.ns:
+                            stage, rnd = 0, rnd + 1
+                    if s == SKIP and ic == 0:
+                        self.commit(self.c0_free.arrive)
+
+                def full_fn(buf=buf, it=it, s=s):
+                    self.acc_ver[buf] = (it, s)
+                    self.acc_writing[buf] = None
+                    self.acc_reads_left[buf] = EPI_WARPS
+                    self.acc_full[buf].arrive()
+                self.commit(full_fn)
+                yield ("delay", self.lat(0.02, 0.1))
+
+    def _write_chunk(self, w, phys, tag):
+        if self.chunk_readers[phys]:
+            raise Hazard(f"warp {w} writes chunk {phys} ({tag}) under {self.chunk_readers[phys]} MMAs in flight")
+        self.chunk_ver[phys][w] = tag
+
+    def _read_acc(self, w, buf, it, s):
+        if self.acc_ver[buf] != (it, s):
+            raise Hazard(f"warp {w} reads TMEM buf {buf}: holds {self.acc_ver[buf]} (writing {self.acc_writing[buf]}), want {(it, s)}")
+
+    def epilogue(self, w):
+        sub = w >> 2
+        for it in range(self.iters):
+            # input stage: PE -> chunk 0
+            if sub < 2:
+                yield ("delay", self.lat(0.2, 1.5))
+                self._write_chunk(w, 0, ("PE", it, 0))
+                self.a_ready[4].arrive()
+            # forward layers 0..7
+            for l in range(8):
+                buf = l & 1
+                yield ("wait", self.acc_full[buf], (it * USES[buf] + (l >> 1)) & 1)
+                for chunk in range(4):
+                    self._read_acc(w, buf, it, l)
+                    yield ("delay", self.lat(0.1, 1.0))
+                    self._write_chunk(w, chunk, (it, l + 1))
+                    self.a_ready[chunk].arrive()
+                self.acc_reads_left[buf] -= 1
+                self.acc_empty[buf].arrive()
+                if l == SKIP - 1 and sub < 2:
+                    yield ("wait", self.c0_free, it & 1)
+                    yield ("delay", self.lat(0.2, 1.5))
+                    self._write_chunk(w, 0, ("PE", it, SKIP))
+                    self.a_ready[4].arrive()
+            # step 8: output layer, alpha_7
+            yield ("wait", self.acc_full[0], (it * USES[0] + 4) & 1)
+            self._read_acc(w, 0, it, 8)
+            self.acc_reads_left[0] -= 1
+            self.acc_empty[0].arrive()
+            for chunk in range(4):
+                yield ("delay", self.lat(0.1, 1.0))
+                self._write_chunk(w, chunk, (it, 9))
+                self.a_ready[chunk].arrive()
+            # reverse steps 9..15
+            for s in range(9, 16):
+                buf = s & 1
+                yield ("wait", self.acc_full[buf], (it * USES[buf] + (s >> 1)) & 1)
+                for chunk in range(4):
+                    self._read_acc(w, buf, it, s)
+                    yield ("delay", self.lat(0.1, 1.0))
+                    self._write_chunk(w, chunk, (it, s + 1))
+                    self.a_ready[chunk].arrive()
+                self.acc_reads_left[buf] -= 1
+                self.acc_empty[buf].arrive()
+            # step 16: PE adjoint -> gradient; the exchange slots live in chunk 3 of the (dead) A tile
+            yield ("wait", self.acc_full[0], (it * USES[0] + 8) & 1)
+            self._read_acc(w, 0, it, 16)
+            self.acc_reads_left[0] -= 1
+            self.acc_empty[0].arrive()
+            yield ("delay", self.lat(0.1, 0.8))
+            self._write_chunk(w, 3, ("slots", it))
+            yield ("delay", self.lat(0.05, 0.5))     # (named barriers of the lane quarter: no mbarrier involved)
+
+
+@pytest.mark.parametrize("nterms", [3, 1])
+def test_protocol_no_deadlock_no_hazard(nterms):
+    for seed in range(40):
+        Sim(nterms, iters=3, seed=seed).run()
+
+
+def test_model_detects_a_wrong_parity():
+    """the model has teeth: an off-by-one in the a_ready use count must be caught"""
+    global A_PER_TILE
+    old = A_PER_TILE
+    A_PER_TILE = 15
+    try:
+        with pytest.raises(AssertionError):
+            for seed in range(10):
+                Sim(3, iters=3, seed=seed).run()
+    finally:
+        A_PER_TILE = old
+
+
+def test_model_detects_a_wrong_accumulator_count():
+    """buf 1 is used 8 times per tile, not 9: the wrong count must be caught from the second tile on"""
+    global USES
+    old = USES
+    USES = (9, 9)
+    try:
+        with pytest.raises(AssertionError):
+            for seed in range(10):
+                Sim(3, iters=3, seed=seed).run()
+    finally:
+        USES = old
