@@ -1,0 +1,44 @@
+"""K1r (reverse-mode gradient kernel) vs K1g (forward-mode): agreement + timing on 1 M points.
+usage: python tests/gpu_time_rgrad.py"""
+import os
+import sys
+
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from emap_b200 import ops, _cabi as C  # noqa: E402
+from tests.helpers import oracle_params  # noqa: E402
+
+p = oracle_params(True)
+flat = torch.cat([t.reshape(-1) for t in p.tensors()]).cuda()
+net = ops.PackedNet(10)
+net.fold(flat)
+P = 1 << 20
+x = (torch.rand(P, 3, device="cuda") * 2 - 1) * 1.5
+
+
+def t(fn, reps=5):
+    fn()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(True), torch.cuda.Event(True)
+    e0.record()
+    for _ in range(reps):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / reps
+
+
+for prec, name in ((3, "fp32x3"), (1, "fp16")):
+    uf, gf = ops.udf_forward_grad(net, prec, pts=x, mode="forward")
+    ur, gr = ops.udf_forward_grad(net, prec, pts=x, mode="reverse")
+    torch.cuda.synchronize()
+    print(f"{name}: |udf_rev - udf_fwd| max {float((ur - uf).abs().max()):.3e}   "
+          f"|grad_rev - grad_fwd| max {float((gr - gf).abs().max()):.3e}", flush=True)
+    tf = t(lambda: ops.udf_forward_grad(net, prec, pts=x, mode="forward"))
+    tr = t(lambda: ops.udf_forward_grad(net, prec, pts=x, mode="reverse"))
+    f0 = t(lambda: ops.udf_forward(net, prec, pts=x))
+    flop = 2 * 918016 * P
+    print(f"{name}: K1g {tf:.2f} ms ({flop / tf / 1e9:.0f} TF/s alg)   K1r {tr:.2f} ms ({flop / tr / 1e9:.0f} TF/s alg)   "
+          f"K1 forward only {f0:.2f} ms", flush=True)
