@@ -9,29 +9,33 @@
 // 12 F executed per point, F = one MLP forward).  This kernel does what autograd does instead: a value-
 // only forward (128 points per tile, 3 F) that keeps sigma_l = softplus'(a_l) of every hidden layer,
 // then the adjoint sweep
-//     alpha_7 = udf'(a_8) w_8 . sigma_7,      alpha_{l-1} = (alpha_l W_l) . sigma_{l-1},   l = 7..1,
-//     d udf / d x = J_gamma(x)^T [ alpha_0 W_0  +  PE columns of alpha_4 W_4 / sqrt2 ]
+//     alpha_7 = w_8 . sigma_7,      alpha_{l-1} = (alpha_l W_l) . sigma_{l-1},   l = 7..1,
+//     d udf / d x = udf'(a_8) J_gamma(x)^T [ alpha_0 W_0  +  PE columns of alpha_4 W_4 / sqrt2 ]
 // on the same tile with the W_l^T operand images (3 F): 6 F executed, half the epilogue conversions.
-// sigma (8 layers x 256 x fp32 = 8 KiB per point) does not fit on chip; every CTA owns a fixed 1 MiB
-// scratch slice in global memory that it rewrites tile after tile -- thread-private addresses (each
+// sigma (7 stashed layers x 256 x fp32 = 7 KiB per point) does not fit on chip; every CTA owns a fixed
+// 896 KiB scratch slice in global memory that it rewrites tile after tile -- thread-private addresses (each
 // thread reads back exactly what it wrote), last written = first read, so the slice lives in the
 // 126 MB L2 and DRAM sees little of it.
 //
-// Skeleton = mlp_tc.cu (same roles, ring, barriers, A-tile format): 17 MMA "steps" per tile --
-// steps 0..8 = forward layers 0..8, steps 9..16 = reverse layers 7..0 -- ping-ponging the two
-// 256-column TMEM accumulators (buf = step & 1).  Adjoints are held in the A tile scaled by 2^4 so that
-// their fp16 lo parts stay normal; the scale rides through the sweep and is removed once at the end.
+// Skeleton = mlp_tc.cu (same roles, ring, barriers, A-tile format): 16 MMA "steps" per tile --
+// steps 0..7 = forward layers 0..7, steps 8..15 = reverse layers 7..0 -- ping-ponging the two
+// 256-column TMEM accumulators (buf = step & 1).  The output layer is NOT an MMA step: the sweep is linear
+// in its seed, so it starts from the unsigned seed w_8 . sigma_7 straight out of layer 7's epilogue (which
+// also forms this thread's share of the dot product a_8 = w_8 . h_8 in fp32), and udf'(a_8) multiplies the
+// finished gradient.  Adjoints are held in the A tile scaled by 2^4 so that their fp16 lo parts stay
+// normal; the scale rides through the sweep and is removed once at the end.
 #include "mlp_dev.cuh"
 
 namespace emap {
 namespace rg {
 
-constexpr int kSteps = 17;
+constexpr int kSteps = 16;
 constexpr int kLastStep = kSteps - 1;
-constexpr uint32_t kUses0 = 9, kUses1 = 8;        // accumulator uses per tile: buf 0 (even steps) / buf 1
-constexpr uint32_t kAPerTile = 16;                // completions of a_ready[0..3] per tile (steps 0..15)
+constexpr uint32_t kUsesPerBuf = 8;               // accumulator uses per tile and buffer (buf = step & 1)
+constexpr uint32_t kAPerTile = 15;                // completions of a_ready[0..3] per tile (steps 0..14)
 constexpr float kAdjScale = 16.f;                 // power of two (headroom: |alpha| < 4095)
-constexpr int kSigmaFloatsPerCta = 8 * 4 * 16 * 512;   // [layer][chunk][warp][2 x 32 lanes x 8] = 1 MiB
+constexpr int kSigmaLayers = 7;                   // sigma_0..sigma_6 (sigma_7 is consumed in registers)
+constexpr int kSigmaFloatsPerCta = kSigmaLayers * 4 * 16 * 512;   // [layer][chunk][warp][2 x 32 lanes x 8] = 896 KiB
 
 struct Args {
   MlpArgs m;
@@ -53,7 +57,7 @@ static_assert(Plan<3>::total <= 232448 && Plan<1>::total <= 232448, "shared memo
 // schedule of step s: K chunks, bytes of one operand part, UMMA N
 __device__ __forceinline__ constexpr int step_nkc(int s) { return (s == 0) ? 1 : ((s == kSkipLayer) ? 5 : 4); }
 __device__ __forceinline__ constexpr uint32_t step_bytes(int s) {
-  return (s == 8) ? 2048u : ((s == kLastStep) ? 8192u : (uint32_t)kRingStageBytes);
+  return (s == kLastStep) ? 8192u : (uint32_t)kRingStageBytes;
 }
 
 // sigma scratch: plain (coherent) 256-bit accesses -- the data is rewritten by this kernel, so the
@@ -145,8 +149,9 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_rgrad_kernel(const Args args)
 
   if (warp == kProducerWarp) {
     // ===================================== producer =====================================
-    // forward images (pack.cu: layer -> K chunk -> hi/lo part) then the reverse stream (rg images, same
-    // order); one bulk copy per part, uniform control flow, issued by one elected lane.
+    // forward images of layers 0..7 (pack.cu: layer -> K chunk -> hi/lo part; they lead the forward stream)
+    // then the reverse stream (rg images, same order); one bulk copy per part, uniform control flow, issued
+    // by one elected lane.
     const uint8_t* img_f = m.packed + hdr->images_off;
     const uint8_t* img_r = m.packed + args.rg_off;
     uint8_t* ring = smem + P::ring;
@@ -155,8 +160,8 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_rgrad_kernel(const Args args)
       uint32_t off = 0;
 #pragma unroll 1
       for (int s = 0; s < kSteps; ++s) {
-        if (s == 9) off = 0;
-        const uint8_t* img = (s < 9) ? img_f : img_r;
+        if (s == 8) off = 0;
+        const uint8_t* img = (s < 8) ? img_f : img_r;
         const int nparts = step_nkc(s) * 2;
         const uint32_t bytes = step_bytes(s);
 #pragma unroll 1
@@ -179,18 +184,17 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_rgrad_kernel(const Args args)
     const uint32_t ring_addr = smem_u32(smem + P::ring);
     const uint32_t idesc256 = make_idesc_f16(128, 256, Elem<T>::fmt);
     const uint32_t idesc64 = make_idesc_f16(128, 64, Elem<T>::fmt);
-    const uint32_t idesc16 = make_idesc_f16(128, 16, Elem<T>::fmt);
     uint32_t stage = 0, round = 0;
     for (int iter = 0; iter < m.iters; ++iter) {
 #pragma unroll
       for (int s = 0; s < kSteps; ++s) {
         const int buf = s & 1;
         {
-          const uint32_t started = (uint32_t)iter * (buf ? kUses1 : kUses0) + (uint32_t)(s >> 1);
+          const uint32_t started = (uint32_t)iter * kUsesPerBuf + (uint32_t)(s >> 1);
           if (started > 0) mbar_wait(&acc_empty[buf], (started - 1) & 1, 200 + buf, s);
         }
         const int nkc = step_nkc(s);
-        const uint32_t idesc = (s == 8) ? idesc16 : ((s == kLastStep) ? idesc64 : idesc256);
+        const uint32_t idesc = (s == kLastStep) ? idesc64 : idesc256;
         const uint32_t d = tmem_base + (uint32_t)buf * 256u;
 #pragma unroll
         for (int ic = 0; ic < nkc; ++ic) {
@@ -247,7 +251,7 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_rgrad_kernel(const Args args)
     const float b8 = bias100[8 * kHidden];
     const float* w8 = reinterpret_cast<const float*>(m.packed + hdr->weff_layer_off[8]);
     const int out3 = (int)hdr->out_dim[kSkipLayer - 1];
-    // this thread's sigma words: ((l*4 + chunk)*16 + warp)*512 + g*256 + lane*8
+    // this thread's sigma words (l = 0..6): ((l*4 + chunk)*16 + warp)*512 + g*256 + lane*8
     float* sg_base = args.scratch + (size_t)blockIdx.x * kSigmaFloatsPerCta + (size_t)warp * 512 + lane * 8;
     auto sg_ptr = [&](int l, int chunk) -> float* { return sg_base + (size_t)(l * 4 + chunk) * 8192; };
     const float gz[3] = {0.f, 0.f, 0.f};
@@ -268,11 +272,12 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_rgrad_kernel(const Args args)
       }
 
       // ------------------------------------------------ forward: hidden layers 0..7 (steps 0..7)
+      float dot8 = 0.f;                         // this thread's share of a_8 = w_8 . h_8 (its 64 columns)
 #pragma unroll 1
       for (int l = 0; l < 8; ++l) {
         const int buf = l & 1;
-        const uint32_t acc_par = ((uint32_t)iter * (buf ? kUses1 : kUses0) + (uint32_t)(l >> 1)) & 1;
-        mbar_wait(&acc_full[buf], acc_par, 500 + buf, l);
+        const bool top = (l == 7);              // layer 7: h_8 feeds only the output layer; seed the sweep
+        mbar_wait(&acc_full[buf], ((uint32_t)iter * kUsesPerBuf + (uint32_t)(l >> 1)) & 1, 500 + buf, l);
         tc_fence_after();
         const float* bl = bias100 + l * kHidden;
 #pragma unroll 1
@@ -286,7 +291,7 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_rgrad_kernel(const Args args)
           uint32_t r[16];
           tmem_ld_32x32b_x16(lane_taddr + (uint32_t)(buf * 256 + col0), r);
           tmem_wait_ld();
-          float* sgp = sg_ptr(l, chunk);
+          float* sgp = sg_ptr(top ? 0 : l, chunk);
 #pragma unroll
           for (int g = 0; g < 2; ++g) {
             const float4 bA = bv[2 * g], bB = bv[2 * g + 1];
@@ -295,8 +300,19 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_rgrad_kernel(const Args args)
 #pragma unroll
             for (int j = 0; j < 8; ++j)
               h[j] = softplus100<true>(fmaf(__uint_as_float(r[g * 8 + j]), k1, bb[j]), sg[j]);
-            store_group<NTERMS, T>(dst_hi, dst_lo, row, sub * 2 + g, h);
-            st_scratch8(sgp + g * 256, sg);
+            if (!top) {
+              store_group<NTERMS, T>(dst_hi, dst_lo, row, sub * 2 + g, h);
+              st_scratch8(sgp + g * 256, sg);
+            } else {
+              // a_8 += w_8 . h_8;  unsigned seed of the sweep: alpha_7 = w_8 . sigma_7 (x 2^4)
+              const float4 wA = __ldg(reinterpret_cast<const float4*>(w8 + col0 + g * 8));
+              const float4 wB = __ldg(reinterpret_cast<const float4*>(w8 + col0 + g * 8 + 4));
+              const float ww[8] = {wA.x, wA.y, wA.z, wA.w, wB.x, wB.y, wB.z, wB.w};
+              float v[8];
+#pragma unroll
+              for (int j = 0; j < 8; ++j) { dot8 = fmaf(ww[j], h[j], dot8); v[j] = kAdjScale * ww[j] * sg[j]; }
+              store_group<NTERMS, T>(dst_hi, dst_lo, row, sub * 2 + g, v);
+            }
           }
           fence_proxy_async_smem();
           __syncwarp();
@@ -318,52 +334,12 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_rgrad_kernel(const Args args)
         }
       }
 
-      // ------------------------------------------------ step 8: output layer -> udf, and alpha_7
-      {
-        mbar_wait(&acc_full[0], ((uint32_t)iter * kUses0 + 4u) & 1, 510);
-        tc_fence_after();
-        const float accv = __uint_as_float(tmem_ld_32x32b_x1(lane_taddr)) * kInvWeightScale;
-        tmem_wait_ld();
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&acc_empty[0]);
-        const float a = accv + b8;
-        float gmul = 1.f;
-        if (udf_type == 0) gmul = (a > 0.f) ? 1.f : (a < 0.f ? -1.f : 0.f);
-        else if (udf_type == 1) gmul = 2.f * a;
-        if (sub == 0 && ok) {
-          const float u = (udf_type == 0) ? fabsf(a) : (udf_type == 1 ? a * a : a);
-          m.udf_out[pt] = u / net_scale;
-        }
-        const float gS = gmul * kAdjScale;
-#pragma unroll 1
-        for (int chunk = 0; chunk < 4; ++chunk) {
-          const int col0 = chunk * 64 + sub * 16;
-          const float* sgp = sg_ptr(7, chunk);
-#pragma unroll
-          for (int g = 0; g < 2; ++g) {
-            float sg[8];
-            ld_scratch8(sgp + g * 256, sg);
-            const float4 wA = __ldg(reinterpret_cast<const float4*>(w8 + col0 + g * 8));
-            const float4 wB = __ldg(reinterpret_cast<const float4*>(w8 + col0 + g * 8 + 4));
-            const float ww[8] = {wA.x, wA.y, wA.z, wA.w, wB.x, wB.y, wB.z, wB.w};
-            float v[8];
-#pragma unroll
-            for (int j = 0; j < 8; ++j) v[j] = gS * ww[j] * sg[j];
-            store_group<NTERMS, T>(A_hi + chunk * kChunkBytes, A_lo + chunk * kChunkBytes, row, sub * 2 + g, v);
-          }
-          fence_proxy_async_smem();
-          __syncwarp();
-          if (lane == 0) mbar_arrive(&a_ready[chunk]);
-        }
-      }
-
-      // ------------------------------------------------ reverse: steps 9..15 = layers 7..1
+      // ------------------------------------------------ reverse: steps 8..14 = layers 7..1
       float gs[3] = {0.f, 0.f, 0.f};            // this thread's share of J_gamma^T (PE adjoint)
       const float inv_adj = kInvWeightScale / kAdjScale;
 #pragma unroll 1
-      for (int s = 9; s < kLastStep; ++s) {
-        const int l = 16 - s;                   // accumulator = alpha_l W_l  -> alpha_{l-1} = acc . sigma_{l-1}
+      for (int s = 8; s < kLastStep; ++s) {
+        const int l = 15 - s;                   // accumulator = alpha_l W_l  -> alpha_{l-1} = acc . sigma_{l-1}
         const int buf = s & 1;
         // sigma of the current chunk; chunk 0 is fetched before the accumulator wait, chunk c+1 as soon as
         // chunk c's values are consumed (its L2 latency then overlaps the conversions and stores of chunk c)
@@ -376,7 +352,7 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_rgrad_kernel(const Args args)
           for (int j = 0; j < 8; ++j) { sgc[j] = t0[j]; sgc[8 + j] = t1[j]; }
         };
         fetch_sigma(0);
-        mbar_wait(&acc_full[buf], ((uint32_t)iter * (buf ? kUses1 : kUses0) + (uint32_t)(s >> 1)) & 1, 530 + buf, s);
+        mbar_wait(&acc_full[buf], ((uint32_t)iter * kUsesPerBuf + (uint32_t)(s >> 1)) & 1, 530 + buf, s);
         tc_fence_after();
 #pragma unroll
         for (int chunk = 0; chunk < 4; ++chunk) {
@@ -415,32 +391,38 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_rgrad_kernel(const Args args)
         if (lane == 0) mbar_arrive(&acc_empty[buf]);
       }
 
-      // ------------------------------------------------ step 16: alpha_0 W_0 (64 PE slots) -> d udf / d x
+      // ------------------------------------------------ step 15: alpha_0 W_0 (64 PE slots) -> d udf / d x
       {
-        mbar_wait(&acc_full[0], ((uint32_t)iter * kUses0 + 8u) & 1, 540);
+        mbar_wait(&acc_full[1], ((uint32_t)iter * kUsesPerBuf + 7u) & 1, 540);
         tc_fence_after();
         uint32_t r[16];
-        tmem_ld_32x32b_x16(lane_taddr + (uint32_t)(sub * 16), r);
+        tmem_ld_32x32b_x16(lane_taddr + (uint32_t)(256 + sub * 16), r);
         tmem_wait_ld();
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(&acc_empty[0]);
+        if (lane == 0) mbar_arrive(&acc_empty[1]);
         float adj[16];
 #pragma unroll
         for (int j = 0; j < 16; ++j) adj[j] = __uint_as_float(r[j]) * inv_adj;
         pe_adjoint16(adj, sub * 16, x, multires, gs);
-        // sum the four column slices of a point: the A tile is dead here (every MMA of the tile has
-        // completed), 16 bytes per (point, sub) serve as the exchange -- inside the chunk-3 rows of this
-        // lane quarter (rows 32q..32q+15), which only its own four warps write later; they meet on a named
-        // barrier before and after.
+        // sum the four column slices of a point (gradient shares and the a_8 shares): the A tile is dead
+        // here (every MMA of the tile has completed), 16 bytes per (point, sub) serve as the exchange --
+        // inside the chunk-3 rows of this lane quarter (rows 32q..32q+15), which only its own four warps
+        // write later; they meet on a named barrier before and after.
         float4* slots = reinterpret_cast<float4*>(A_hi + 3 * kChunkBytes + (q * 32 + (lane >> 1)) * 128 + (lane & 1) * 64);
-        slots[sub] = make_float4(gs[0], gs[1], gs[2], 0.f);
+        slots[sub] = make_float4(gs[0], gs[1], gs[2], dot8);
         named_bar_sync(1 + q, 128);
         if (sub == 0 && ok) {
           const float4 s0 = slots[0], s1 = slots[1], s2 = slots[2], s3 = slots[3];
-          m.grad_out[pt * 3 + 0] = (s0.x + s1.x) + (s2.x + s3.x);
-          m.grad_out[pt * 3 + 1] = (s0.y + s1.y) + (s2.y + s3.y);
-          m.grad_out[pt * 3 + 2] = (s0.z + s1.z) + (s2.z + s3.z);
+          const float a = ((s0.w + s1.w) + (s2.w + s3.w)) + b8;          // output layer (udf_model.py:102)
+          float u, gmul;                                                // udf_model.py:82-88 and its derivative
+          if (udf_type == 0) { u = fabsf(a); gmul = (a > 0.f) ? 1.f : (a < 0.f ? -1.f : 0.f); }
+          else if (udf_type == 1) { u = a * a; gmul = 2.f * a; }
+          else { u = a; gmul = 1.f; }
+          m.udf_out[pt] = u / net_scale;
+          m.grad_out[pt * 3 + 0] = gmul * ((s0.x + s1.x) + (s2.x + s3.x));
+          m.grad_out[pt * 3 + 1] = gmul * ((s0.y + s1.y) + (s2.y + s3.y));
+          m.grad_out[pt * 3 + 2] = gmul * ((s0.z + s1.z) + (s2.z + s3.z));
         }
         named_bar_sync(1 + q, 128);
       }

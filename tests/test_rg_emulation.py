@@ -135,11 +135,12 @@ def _emulate(p, x, split=False, adj_scale=16.0):
         if split:
             h, s = h.astype(np.float32).astype(np.float64), s.astype(np.float32).astype(np.float64)
         sig.append(s)
-    a8 = (_mm(h, Wd[8].T, split) + bd[8])[:, 0]
+    # output layer: fp32 dot product in layer 7's epilogue (no MMA); the sweep starts from the UNSIGNED
+    # seed w_8 . sigma_7 and udf'(a_8) multiplies the finished gradient
+    a8 = h @ Wd[8][0] + bd[8][0]
     udf = np.abs(a8) / p.scale
     gmul = np.sign(a8)
-    # ---- step 8: alpha_7
-    alpha = gmul[:, None] * Wd[8][0][None, :] * sig[7]
+    alpha = Wd[8][0][None, :] * sig[7]
     g = np.zeros((x.shape[0], 3))
 
     def contract(adj, kbase):
@@ -156,7 +157,7 @@ def _emulate(p, x, split=False, adj_scale=16.0):
             else:
                 g[:, ax] -= adj[:, i] * f * np.sin(f * xs[:, ax])
 
-    # ---- steps 9..15: layers 7..1
+    # ---- steps 8..14: layers 7..1
     for l in range(7, 0, -1):
         acc = _mm(alpha, B[l].T, split, adj_scale)   # [P, 256 (n)]
         v = acc * sig[l - 1]
@@ -170,11 +171,11 @@ def _emulate(p, x, split=False, adj_scale=16.0):
                     if kbase + j >= 1:
                         v[:, col0 + j] = 0.0
         alpha = v
-    # ---- step 16: layer 0
+    # ---- step 15: layer 0
     acc = _mm(alpha, B[0].T, split, adj_scale)       # [P, 64]
     for sub in range(4):
         contract(acc[:, 16 * sub:16 * sub + 16], 16 * sub)
-    return udf, g
+    return udf, g * gmul[:, None]
 
 
 @pytest.mark.parametrize("multires,pert", [(10, False), (10, True), (6, True)])

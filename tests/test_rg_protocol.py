@@ -17,10 +17,10 @@ import random
 import pytest
 
 K_STAGES = {3: 3, 1: 4}
-K_STEPS = 17
+K_STEPS = 16             # forward layers 0..7, reverse layers 7..0 (the output layer is not an MMA step)
 SKIP = 4
-USES = (9, 8)            # accumulator uses per tile: buf 0 / buf 1   (kUses0, kUses1)
-A_PER_TILE = 16          # kAPerTile
+USES = (8, 8)            # accumulator uses per tile: buf 0 / buf 1   (kUsesPerBuf)
+A_PER_TILE = 15          # kAPerTile
 EPI_WARPS = 16
 
 
@@ -271,17 +271,9 @@ class Sim:
                     yield ("delay", self.lat(0.2, 1.5))
                     self._write_chunk(w, 0, ("PE", it, SKIP))
                     self.a_ready[4].arrive()
-            # step 8: output layer, alpha_7
-            yield ("wait", self.acc_full[0], (it * USES[0] + 4) & 1)
-            self._read_acc(w, 0, it, 8)
-            self.acc_reads_left[0] -= 1
-            self.acc_empty[0].arrive()
-            for chunk in range(4):
-                yield ("delay", self.lat(0.1, 1.0))
-                self._write_chunk(w, chunk, (it, 9))
-                self.a_ready[chunk].arrive()
-            # reverse steps 9..15
-            for s in range(9, 16):
+            # (layer 7's epilogue above wrote the sweep's seed alpha_7 as the input of step 8)
+            # reverse steps 8..14
+            for s in range(8, 15):
                 buf = s & 1
                 yield ("wait", self.acc_full[buf], (it * USES[buf] + (s >> 1)) & 1)
                 for chunk in range(4):
@@ -291,11 +283,11 @@ class Sim:
                     self.a_ready[chunk].arrive()
                 self.acc_reads_left[buf] -= 1
                 self.acc_empty[buf].arrive()
-            # step 16: PE adjoint -> gradient; the exchange slots live in chunk 3 of the (dead) A tile
-            yield ("wait", self.acc_full[0], (it * USES[0] + 8) & 1)
-            self._read_acc(w, 0, it, 16)
-            self.acc_reads_left[0] -= 1
-            self.acc_empty[0].arrive()
+            # step 15: PE adjoint -> gradient; the exchange slots live in chunk 3 of the (dead) A tile
+            yield ("wait", self.acc_full[1], (it * USES[1] + 7) & 1)
+            self._read_acc(w, 1, it, 15)
+            self.acc_reads_left[1] -= 1
+            self.acc_empty[1].arrive()
             yield ("delay", self.lat(0.1, 0.8))
             self._write_chunk(w, 3, ("slots", it))
             yield ("delay", self.lat(0.05, 0.5))     # (named barriers of the lane quarter: no mbarrier involved)
@@ -311,7 +303,7 @@ def test_model_detects_a_wrong_parity():
     """the model has teeth: an off-by-one in the a_ready use count must be caught"""
     global A_PER_TILE
     old = A_PER_TILE
-    A_PER_TILE = 15
+    A_PER_TILE = 16
     try:
         with pytest.raises(AssertionError):
             for seed in range(10):
@@ -321,10 +313,10 @@ def test_model_detects_a_wrong_parity():
 
 
 def test_model_detects_a_wrong_accumulator_count():
-    """buf 1 is used 8 times per tile, not 9: the wrong count must be caught from the second tile on"""
+    """each buffer is used 8 times per tile, not 9: the wrong count must be caught from the second tile on"""
     global USES
     old = USES
-    USES = (9, 9)
+    USES = (9, 8)
     try:
         with pytest.raises(AssertionError):
             for seed in range(10):
