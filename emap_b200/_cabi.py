@@ -46,6 +46,8 @@ SIGNATURES = {
     "emap_rgrad_scratch_bytes": (ctypes.c_size_t, []),
     "emap_udf_forward_grad_rev": (ctypes.c_int, [_nd, _vp, _i32, _vp, _vp, _vp, _vp, _i32, _i64, _vp, _vp, _vp,
                                                  ctypes.c_size_t, _vp]),
+    "emap_debug_rgrad": (ctypes.c_int, [_nd, _vp, _i32, _vp, _vp, _vp, _vp, _i32, _i64, _vp, _vp, _vp,
+                                        ctypes.c_size_t, _vp, _vp]),
     "emap_debug_rg_image": (ctypes.c_int, [_nd, ctypes.c_int, _vp, _vp, _vp]),
     "emap_debug_pe_col_to_ref": (ctypes.c_int, [ctypes.c_int, ctypes.c_int]),
     "emap_debug_rg_pe_ref": (ctypes.c_int, [ctypes.c_int, ctypes.c_int]),
@@ -78,7 +80,7 @@ SIGNATURES = {
 
 # kernel launches issued by each entry point (for bench.py's `gpu_launches` claim)
 LAUNCHES_PER_CALL = {
-    "emap_wn_fold": 4, "emap_udf_forward": 1, "emap_udf_forward_grad": 1, "emap_udf_forward_grad_rev": 1, "emap_debug_mlp": 1,
+    "emap_wn_fold": 4, "emap_udf_forward": 1, "emap_udf_forward_grad": 1, "emap_udf_forward_grad_rev": 1, "emap_debug_rgrad": 1, "emap_debug_mlp": 1,
     "emap_coarse_z": 1, "emap_upsample_step": 1, "emap_render_prep": 1, "emap_render_core_fwd": 2,
     "emap_render_core_bwd": 2, "emap_bwd_pe_dual": 1, "emap_bwd_act_fwd": 1, "emap_bwd_top": 1,
     "emap_bwd_act_bwd": 1, "emap_bwd_weight_norm": 1, "emap_bwd_dual_forward": 1,

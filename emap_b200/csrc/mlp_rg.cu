@@ -291,6 +291,11 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_rgrad_kernel(const Args args)
           uint32_t r[16];
           tmem_ld_32x32b_x16(lane_taddr + (uint32_t)(buf * 256 + col0), r);
           tmem_wait_ld();
+          if (m.dbg_acc && tile == 0) {
+#pragma unroll
+            for (int k = 0; k < 16; ++k)
+              m.dbg_acc[((size_t)l * 128 + row) * 256 + col0 + k] = __uint_as_float(r[k]) * kInvWeightScale;
+          }
           float* sgp = sg_ptr(top ? 0 : l, chunk);
 #pragma unroll
           for (int g = 0; g < 2; ++g) {
@@ -360,6 +365,11 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_rgrad_kernel(const Args args)
           uint32_t r[16];
           tmem_ld_32x32b_x16(lane_taddr + (uint32_t)(buf * 256 + col0), r);
           tmem_wait_ld();
+          if (m.dbg_acc && tile == 0) {
+#pragma unroll
+            for (int k = 0; k < 16; ++k)
+              m.dbg_acc[((size_t)s * 128 + row) * 256 + col0 + k] = __uint_as_float(r[k]) * inv_adj;
+          }
           float v[16];
 #pragma unroll
           for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(r[j]) * kInvWeightScale * sgc[j];
@@ -404,6 +414,10 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_rgrad_kernel(const Args args)
         float adj[16];
 #pragma unroll
         for (int j = 0; j < 16; ++j) adj[j] = __uint_as_float(r[j]) * inv_adj;
+        if (m.dbg_acc && tile == 0) {
+#pragma unroll
+          for (int k = 0; k < 16; ++k) m.dbg_acc[((size_t)kLastStep * 128 + row) * 256 + sub * 16 + k] = adj[k];
+        }
         pe_adjoint16(adj, sub * 16, x, multires, gs);
         // sum the four column slices of a point (gradient shares and the a_8 shares): the A tile is dead
         // here (every MMA of the tile has completed), 16 bytes per (point, sub) serve as the exchange --
@@ -471,6 +485,18 @@ extern "C" int emap_udf_forward_grad_rev(const emap_net_desc* net, const void* p
                                          const float* pts, const float* rays_o, const float* rays_d,
                                          const float* z, int32_t n_per_ray, int64_t P, float* udf_out,
                                          float* grad_out, void* scratch, size_t scratch_bytes, void* stream) {
+  return emap_debug_rgrad(net, packed, precision, pts, rays_o, rays_d, z, n_per_ray, P, udf_out, grad_out,
+                          scratch, scratch_bytes, nullptr, stream);
+}
+
+// Test hook: the same launch, additionally dumping the accumulators of tile 0 after every MMA step,
+// dbg_acc[16][128][256] floats: steps 0..7 = W_l h_l (no bias), steps 8..14 = alpha_l W_l for l = 7..1 (the
+// adjoint of layer l's input, unsigned seed, de-scaled), step 15 = the 64 PE slots (columns 0..63).
+extern "C" int emap_debug_rgrad(const emap_net_desc* net, const void* packed, int precision,
+                                const float* pts, const float* rays_o, const float* rays_d,
+                                const float* z, int32_t n_per_ray, int64_t P, float* udf_out,
+                                float* grad_out, void* scratch, size_t scratch_bytes, float* dbg_acc,
+                                void* stream) {
   if (check_net(net)) return 1;
   if (!packed || !udf_out || !grad_out || !scratch) return set_error("emap_udf_forward_grad_rev: NULL pointer");
   if (P <= 0) return set_error("P must be > 0");
@@ -484,6 +510,7 @@ extern "C" int emap_udf_forward_grad_rev(const emap_net_desc* net, const void* p
   memset(&a, 0, sizeof(a));
   a.m.packed = (const uint8_t*)packed; a.m.pts = pts; a.m.rays_o = rays_o; a.m.rays_d = rays_d; a.m.z = z;
   a.m.n_per_ray = n_per_ray; a.m.P = P; a.m.udf_out = udf_out; a.m.grad_out = grad_out;
+  a.m.dbg_acc = dbg_acc;
   a.scratch = (float*)scratch;
   a.rg_off = h.reserved[3];
   cudaStream_t st = (cudaStream_t)stream;

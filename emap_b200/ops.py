@@ -134,6 +134,21 @@ def debug_mlp(net: PackedNet, precision: int, mode: int, pts: torch.Tensor):
     return udf, grad, dbg
 
 
+def debug_rgrad(net: PackedNet, precision: int, pts: torch.Tensor):
+    """Test hook: K1r plus the accumulators of tile 0 after each MMA step, [16,128,256]."""
+    pts = C.f32(pts)
+    P = pts.shape[0]
+    dev = net.packed.device
+    udf = torch.zeros(P, dtype=torch.float32, device=dev)
+    grad = torch.zeros(P, 3, dtype=torch.float32, device=dev)
+    dbg = torch.zeros(16, 128, 256, dtype=torch.float32, device=dev)
+    scratch = _rg_scratch(dev)
+    C.check(C.lib().emap_debug_rgrad(ctypes.byref(net.desc), C.ptr(net.packed), precision, C.ptr(pts), None,
+                                     None, None, 0, P, C.ptr(udf), C.ptr(grad), C.ptr(scratch),
+                                     scratch.numel(), C.ptr(dbg), C.stream()))
+    return udf, grad, dbg
+
+
 def positional_encoding(x: torch.Tensor, multires: int) -> torch.Tensor:
     """gamma(x) as computed by the MLP kernel's input stage (reference column order)."""
     x = C.f32(x.reshape(-1, 3))

@@ -208,6 +208,12 @@ int emap_debug_set_clk_buffer(void* dev_buf_144_int64);
 int emap_debug_mlp(const emap_net_desc* net, const void* packed, int precision, int mode,
                    const float* pts, int64_t P, float* udf_out, float* grad_out, float* dbg_acc,
                    void* stream);
+/* test hook: emap_udf_forward_grad_rev that also dumps the accumulators of tile 0 after each of its 16
+ * MMA steps, dbg_acc[16][128][256] (see mlp_rg.cu).                                                   */
+int emap_debug_rgrad(const emap_net_desc* net, const void* packed, int precision, const float* pts,
+                     const float* rays_o, const float* rays_d, const float* z, int32_t n_per_ray,
+                     int64_t P, float* udf_out, float* grad_out, void* scratch, size_t scratch_bytes,
+                     float* dbg_acc, void* stream);
 /* test hooks on HOST memory (no GPU needed): the un-split fp32 value image `b` (0..63) of the K1r
  * reverse stream from the HOST W_eff matrix of its layer -> out_host [rows x 64] (rows returned: 256 or
  * 64; -1 on error), layer_kc_part[3] (optional) = {layer, K chunk, hi/lo part}; and the two PE column

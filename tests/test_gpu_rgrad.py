@@ -35,6 +35,30 @@ def _net(pert, multires=10, elem="fp16", udf_type="abs", scale=1.0):
     return net, p
 
 
+def test_stepwise_accumulators_vs_emulation():
+    """bring-up diagnostic, run first: the accumulators of tile 0 after each of the 16 MMA steps against the
+    float64 emulation of the same algorithm (tests/test_rg_emulation.py) -- names the first step that
+    diverges instead of only reporting a wrong gradient."""
+    import numpy as np
+    from emap_b200 import ops, _cabi as C
+    from tests.test_rg_emulation import _emulate
+    net, p = _net(True)
+    torch.manual_seed(3)
+    x = (torch.rand(128, 3) * 2 - 1) * 0.9
+    udf, grad, dbg = ops.debug_rgrad(net, C.PREC_FP32X3, x.cuda())
+    torch.cuda.synchronize()
+    steps = []
+    eu, eg = _emulate(p, x, steps=steps)
+    assert len(steps) == 16
+    got = dbg.cpu().double().numpy()
+    for s_i, want in enumerate(steps):
+        scale = max(1.0, float(np.abs(want).max()))
+        err = float(np.abs(got[s_i] - want).max())
+        assert err <= 2e-4 * scale, f"MMA step {s_i}: max |acc - emulation| = {err:.3e} (scale {scale:.2e})"
+    assert float(np.abs(udf.cpu().numpy() - eu).max()) <= 5e-5
+    assert float(np.abs(grad.cpu().numpy() - eg).max()) <= 5e-5
+
+
 @pytest.mark.parametrize("pert", [False, True])
 @pytest.mark.parametrize("prec,tol_u,tol_g", [("fp32", 5e-5, 5e-5), ("fp16", 3e-3, 1e-2)])
 def test_reverse_mode_vs_reference(golden, pert, prec, tol_u, tol_g):

@@ -108,7 +108,7 @@ def _mm(A, Bt, split, a_scale=1.0):
     return ((ah + al) @ bh + ah @ bl) / (KW * a_scale)
 
 
-def _emulate(p, x, split=False, adj_scale=16.0):
+def _emulate(p, x, split=False, adj_scale=16.0, steps=None):
     """forward + adjoint sweep exactly as mlp_rgrad_kernel structures it (float64; split=True models the
     fp16 hi/lo operands of the fp32x3 mode, fp32 activations / sigma / adjoints between the layers)."""
     mr = p.multires
@@ -127,6 +127,8 @@ def _emulate(p, x, split=False, adj_scale=16.0):
         if l == 4:
             h = np.concatenate([h, e], axis=1) / math.sqrt(2)
         a = _mm(h, Wd[l].T, split) + bd[l]
+        if steps is not None:                      # what emap_debug_rgrad dumps: W_l h_l without the bias
+            steps.append(np.pad(a - bd[l], ((0, 0), (0, 256 - a.shape[1]))))
         t = 100.0 * a
         h = np.where(t > 20, a, np.log1p(np.exp(np.minimum(t, 20))) / 100.0)
         s = 1.0 / (1.0 + np.exp(-t))
@@ -160,6 +162,8 @@ def _emulate(p, x, split=False, adj_scale=16.0):
     # ---- steps 8..14: layers 7..1
     for l in range(7, 0, -1):
         acc = _mm(alpha, B[l].T, split, adj_scale)   # [P, 256 (n)]
+        if steps is not None:
+            steps.append(acc.copy())
         v = acc * sig[l - 1]
         if l == 4:
             # chunk 3, per 16-column slice `sub` exactly as the epilogue warps see it
@@ -173,6 +177,8 @@ def _emulate(p, x, split=False, adj_scale=16.0):
         alpha = v
     # ---- step 15: layer 0
     acc = _mm(alpha, B[0].T, split, adj_scale)       # [P, 64]
+    if steps is not None:
+        steps.append(np.pad(acc, ((0, 0), (0, 192))))
     for sub in range(4):
         contract(acc[:, 16 * sub:16 * sub + 16], 16 * sub)
     return udf, g * gmul[:, None]
