@@ -41,7 +41,9 @@ struct Args {
   MlpArgs m;
   float* scratch;        // [grid][kSigmaFloatsPerCta]
   uint32_t rg_off;       // byte offset of the reverse image stream inside the packed buffer
+  int flags;             // emap_set_option("rg_flags", bits): kFlagSplitTail
 };
+constexpr int kFlagSplitTail = 1;   // N-split of each step's last K chunk (as K1g does; A/B switch for bring-up)
 
 template <int NTERMS>
 struct Plan {
@@ -128,16 +130,17 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_rgrad_kernel(const Args args)
   uint64_t* full = bars;                  // [kStages]
   uint64_t* empty = bars + 4;             // [kStages]
   uint64_t* a_ready = bars + 8;           // [5]  (index 4 = PE written into chunk 0)
-  uint64_t* acc_full = bars + 13;         // [2]
-  uint64_t* acc_empty = bars + 15;        // [2]
-  uint64_t* c0_free = bars + 17;          // layer 4 has consumed chunk 0 -> PE may be regenerated there
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 18);
+  uint64_t* acc_full = bars + 13;         // [2 buffers][2 N halves]: columns [0,128) / [128,256) complete
+  uint64_t* acc_empty = bars + 17;        // [2]
+  uint64_t* c0_free = bars + 19;          // layer 4 has consumed chunk 0 -> PE may be regenerated there
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 20);
 
   if (warp == kProducerWarp && lane == 0) {
     for (int s = 0; s < kStages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
     for (int c = 0; c < 4; ++c) mbar_init(&a_ready[c], kEpiWarps);
     mbar_init(&a_ready[4], 8);
-    for (int b = 0; b < 2; ++b) { mbar_init(&acc_full[b], 1); mbar_init(&acc_empty[b], kEpiWarps); }
+    for (int b = 0; b < 4; ++b) mbar_init(&acc_full[b], 1);
+    for (int b = 0; b < 2; ++b) mbar_init(&acc_empty[b], kEpiWarps);
     mbar_init(c0_free, 1);
     fence_barrier_init();
   }
@@ -196,6 +199,13 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_rgrad_kernel(const Args args)
         const int nkc = step_nkc(s);
         const uint32_t idesc = (s == kLastStep) ? idesc64 : idesc256;
         const uint32_t d = tmem_base + (uint32_t)buf * 256u;
+        // N-split of the last K chunk (optional, mlp_tc.cu): its MMAs into accumulator columns [0,128) are
+        // issued and committed first, so the epilogue starts on chunks 0-1 while the tensor pipe finishes
+        // columns [128,256).  Not for steps 0 and 4 (their last K chunk is the PE chunk, which lives in
+        // activation chunk 0 -- the epilogue of half 0 would overwrite it under the running MMAs of half 1),
+        // not for the N=64 last step, not in single-MMA mode.
+        const bool split_tail = (NTERMS == 3) && (args.flags & kFlagSplitTail) && s != 0 && s != kSkipLayer &&
+                                s != kLastStep;
 #pragma unroll
         for (int ic = 0; ic < nkc; ++ic) {
           const int c = (s == 0) ? 4 : ((ic < 4) ? ic : 4);
@@ -208,6 +218,36 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_rgrad_kernel(const Args args)
           const uint32_t coff = (c == 4) ? 0u : (uint32_t)c * kChunkBytes;   // PE lives in chunk 0
           const uint64_t ahi = make_sw128_kmajor_desc(a_hi_addr + coff);
           const uint64_t alo = make_sw128_kmajor_desc(a_lo_addr + coff);
+          if (split_tail && ic == nkc - 1) {
+            uint32_t sidx[kParts];
+#pragma unroll
+            for (int part = 0; part < kParts; ++part) {
+              sidx[part] = stage;
+              mbar_wait(&full[stage], round & 1, 400 + (int)stage, s * 16 + ic * 2 + part);
+              if (++stage == (uint32_t)kStages) { stage = 0; ++round; }
+            }
+            tc_fence_after();
+            const uint32_t idesc128 = make_idesc_f16(128, 128, Elem<T>::fmt);
+            if (elect_one()) {
+#pragma unroll
+              for (int half = 0; half < 2; ++half) {
+                const uint32_t dh = d + (uint32_t)half * 128u;
+                const uint64_t b0 = make_sw128_kmajor_desc(ring_addr + sidx[0] * kRingStageBytes + half * kStageBytes);
+#pragma unroll
+                for (int k = 0; k < 4; ++k) umma_f16(dh, ahi + 2 * k, b0 + 2 * k, idesc128, 1u);
+#pragma unroll
+                for (int k = 0; k < 4; ++k) umma_f16(dh, alo + 2 * k, b0 + 2 * k, idesc128, 1u);
+                const uint64_t b1 = make_sw128_kmajor_desc(ring_addr + sidx[kParts - 1] * kRingStageBytes + half * kStageBytes);
+#pragma unroll
+                for (int k = 0; k < 4; ++k) umma_f16(dh, ahi + 2 * k, b1 + 2 * k, idesc128, 1u);
+                umma_commit(&acc_full[buf * 2 + half]);
+              }
+#pragma unroll
+              for (int part = 0; part < kParts; ++part) umma_commit(&empty[sidx[part]]);
+            }
+            __syncwarp();
+            continue;
+          }
 #pragma unroll
           for (int part = 0; part < kParts; ++part) {
             mbar_wait(&full[stage], round & 1, 400 + (int)stage, s * 16 + ic * 2 + part);
@@ -233,8 +273,10 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_rgrad_kernel(const Args args)
           }
           if (s == kSkipLayer && ic == 0) { if (elect_one()) umma_commit(c0_free); __syncwarp(); }
         }
-        if (elect_one()) umma_commit(&acc_full[buf]);
-        __syncwarp();
+        if (!split_tail) {
+          if (elect_one()) { umma_commit(&acc_full[buf * 2]); umma_commit(&acc_full[buf * 2 + 1]); }
+          __syncwarp();
+        }
       }
     }
   } else {
@@ -277,7 +319,8 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_rgrad_kernel(const Args args)
       for (int l = 0; l < 8; ++l) {
         const int buf = l & 1;
         const bool top = (l == 7);              // layer 7: h_8 feeds only the output layer; seed the sweep
-        mbar_wait(&acc_full[buf], ((uint32_t)iter * kUsesPerBuf + (uint32_t)(l >> 1)) & 1, 500 + buf, l);
+        const uint32_t acc_par = ((uint32_t)iter * kUsesPerBuf + (uint32_t)(l >> 1)) & 1;
+        mbar_wait(&acc_full[buf * 2], acc_par, 500 + buf, l);
         tc_fence_after();
         const float* bl = bias100 + l * kHidden;
 #pragma unroll 1
@@ -285,6 +328,7 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_rgrad_kernel(const Args args)
           uint8_t* dst_hi = A_hi + chunk * kChunkBytes;
           uint8_t* dst_lo = A_lo + chunk * kChunkBytes;
           const int col0 = chunk * 64 + sub * 16;
+          if (chunk == 2) { mbar_wait(&acc_full[buf * 2 + 1], acc_par, 505 + buf, l); tc_fence_after(); }
           float4 bv[4];
 #pragma unroll
           for (int i = 0; i < 4; ++i) bv[i] = __ldg(reinterpret_cast<const float4*>(bl + col0) + i);
@@ -357,11 +401,13 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_rgrad_kernel(const Args args)
           for (int j = 0; j < 8; ++j) { sgc[j] = t0[j]; sgc[8 + j] = t1[j]; }
         };
         fetch_sigma(0);
-        mbar_wait(&acc_full[buf], ((uint32_t)iter * kUsesPerBuf + (uint32_t)(s >> 1)) & 1, 530 + buf, s);
+        const uint32_t acc_par = ((uint32_t)iter * kUsesPerBuf + (uint32_t)(s >> 1)) & 1;
+        mbar_wait(&acc_full[buf * 2], acc_par, 530 + buf, s);
         tc_fence_after();
 #pragma unroll
         for (int chunk = 0; chunk < 4; ++chunk) {
           const int col0 = chunk * 64 + sub * 16;
+          if (chunk == 2) { mbar_wait(&acc_full[buf * 2 + 1], acc_par, 535 + buf, s); tc_fence_after(); }
           uint32_t r[16];
           tmem_ld_32x32b_x16(lane_taddr + (uint32_t)(buf * 256 + col0), r);
           tmem_wait_ld();
@@ -403,7 +449,7 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_rgrad_kernel(const Args args)
 
       // ------------------------------------------------ step 15: alpha_0 W_0 (64 PE slots) -> d udf / d x
       {
-        mbar_wait(&acc_full[1], ((uint32_t)iter * kUsesPerBuf + 7u) & 1, 540);
+        mbar_wait(&acc_full[2], ((uint32_t)iter * kUsesPerBuf + 7u) & 1, 540);   // buf 1 (both halves commit together)
         tc_fence_after();
         uint32_t r[16];
         tmem_ld_32x32b_x16(lane_taddr + (uint32_t)(256 + sub * 16), r);
@@ -449,9 +495,13 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_rgrad_kernel(const Args args)
   if (warp == kMmaWarp) tmem_dealloc(tmem_base, 512);
 }
 
+static int g_flags = 0;   // emap_set_option("rg_flags", bits)
+int set_flags(int v) { g_flags = v; return 0; }
+
 template <int NTERMS, typename T>
 static int launch(const Args& a_in, size_t scratch_bytes, cudaStream_t stream) {
   Args a = a_in;
+  a.flags = g_flags;
   const long long tiles = (a.m.P + 127) / 128;
   if (tiles > 0x7fffffffLL) return set_error("too many points");
   a.m.num_tiles = (int)tiles;

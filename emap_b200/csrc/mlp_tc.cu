@@ -31,6 +31,8 @@
 
 namespace emap {
 
+namespace rg { int set_flags(int v); }   // mlp_rg.cu
+
 template <int NTERMS, int MODE, typename T, int CL>
 __global__ void __launch_bounds__(kThreads, 1) mlp_kernel(const MlpArgs args) {
   // CL = 1|2|4: weight-stream multicast width (cta_group::1).  CL = -2: PAIR mode -- clusters of two CTAs
@@ -690,6 +692,7 @@ extern "C" int emap_set_option(const char* name, int value) {
   if (!name) return set_error("option name is NULL");
   if (!strcmp(name, "cluster")) return set_cluster_width(value);
   if (!strcmp(name, "dbg")) { emap::g_dbg_flags = value; return 0; }
+  if (!strcmp(name, "rg_flags")) return emap::rg::set_flags(value);   // K1r experiment switches (mlp_rg.cu)
   return set_error("unknown option '%s'", name);
 }
 

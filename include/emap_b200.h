@@ -199,7 +199,9 @@ int emap_rays_from_pixels(const int64_t* pixels_x, const int64_t* pixels_y, cons
                           float* p_cam, float* depth_scale, void* stream);
 
 /* ---- misc ------------------------------------------------------------------------------------ */
-/* options: "cluster" = 1|2|4 : width of the weight-stream multicast cluster of the MLP kernels.  */
+/* options: "cluster" = 1|2|-2 : weight-stream organisation of the K1/K1g/dual kernels (1 = default);
+ *          "rg_flags" : K1r experiment switches (bit 0: N-split of each step's last K chunk);
+ *          "dbg"      : timing experiments of mlp_tc.cu (0 in production).                            */
 int emap_set_option(const char* name, int value);
 /* test hook: MLP forward (mode 0) / forward+grad (mode 1) that also dumps the de-scaled
  * accumulators of tile 0, dbg_acc[9][128][256].                                                  */

@@ -106,6 +106,22 @@ def test_reverse_mode_rays_ragged_many_tiles_and_repeatable():
     assert maxdiff(g1.cpu()[sel], ref_g) <= 5e-5 * max(1.0, float(ref_g.abs().max()))
 
 
+def test_split_tail_variant_is_bit_identical(golden):
+    """rg_flags bit 0: N-split of each step's last K chunk (same MMA order per accumulator column)."""
+    from emap_b200 import ops, _cabi as C
+    g = golden("mlp_pert")
+    net, _ = _net(True)
+    x = g["x"].cuda().repeat(60, 1)           # 23,040 points -> 180 tiles: two tiles on some CTAs
+    u1, g1 = ops.udf_forward_grad(net, C.PREC_FP32X3, pts=x, mode="reverse")
+    try:
+        C.set_option("rg_flags", 1)
+        u2, g2 = ops.udf_forward_grad(net, C.PREC_FP32X3, pts=x, mode="reverse")
+        torch.cuda.synchronize()
+    finally:
+        C.set_option("rg_flags", 0)
+    assert torch.equal(u1, u2) and torch.equal(g1, g2)
+
+
 @pytest.mark.parametrize("udf_type,scale", [("square", 1.0), ("sdf", 1.0), ("abs", 0.5)])
 def test_reverse_mode_udf_types_and_scale(udf_type, scale):
     from emap_b200 import ops, _cabi as C

@@ -59,16 +59,17 @@ class MBar:
 
 
 class Sim:
-    def __init__(self, nterms, iters, seed):
+    def __init__(self, nterms, iters, seed, split_tail=False):
         self.rng = random.Random(seed)
         self.nterms, self.iters = nterms, iters
+        self.split_tail = split_tail and nterms == 3
         self.parts = 2 if nterms == 3 else 1
         ns = K_STAGES[nterms]
         self.ns = ns
         self.full = [MBar(f"full{i}", 1) for i in range(ns)]
         self.empty = [MBar(f"empty{i}", 1) for i in range(ns)]
         self.a_ready = [MBar(f"a_ready{i}", EPI_WARPS) for i in range(4)] + [MBar("a_ready4", 8)]
-        self.acc_full = [MBar("acc_full0", 1), MBar("acc_full1", 1)]
+        self.acc_full = [[MBar(f"acc_full{b}{h}", 1) for h in range(2)] for b in range(2)]   # [buf][N half]
         self.acc_empty = [MBar("acc_empty0", EPI_WARPS), MBar("acc_empty1", EPI_WARPS)]
         self.c0_free = MBar("c0_free", 1)
         self.now = 0.0
@@ -81,7 +82,7 @@ class Sim:
         # A chunk c: per-warp version tags + MMAs in flight reading it
         self.chunk_ver = [[None] * EPI_WARPS for _ in range(4)]
         self.chunk_readers = [0] * 4
-        self.acc_ver = [None, None]             # (iter, s) once complete
+        self.acc_ver = [[None, None], [None, None]]   # [buf][N half]: (iter, s) once complete
         self.acc_writing = [None, None]         # (iter, s) while MMAs in flight
         self.acc_reads_left = [0, 0]            # epilogue warps that still have to read the current version
         self.mma_queue = []                     # in-order completion of the tensor pipe
@@ -152,30 +153,34 @@ class Sim:
             self.full[stage].complete_tx(1)
         self.at(self.lat(0.5, 6.0), land)
 
-    def mma_group(self, it, s, ic, part, stage, chunk, buf, first):
-        """the MMAs of one (K chunk, part): reads ring stage + A chunk, accumulates into TMEM buf"""
-        if self.stage_data[stage] != (it, s, ic, part):
-            raise Hazard(f"MMA {(it, s, ic, part)} reads ring stage {stage} holding {self.stage_data[stage]}")
+    def mma_group(self, it, s, ic, parts, chunk, buf, first):
+        """the MMAs of one K chunk over the given [(part, ring stage)]: read ring stages + A chunk,
+        accumulate into TMEM buf"""
+        for part, stage in parts:
+            if self.stage_data[stage] != (it, s, ic, part):
+                raise Hazard(f"MMA {(it, s, ic, part)} reads ring stage {stage} holding {self.stage_data[stage]}")
         want = ("PE", it, s) if chunk == 4 else (it, s)
         phys = 0 if chunk == 4 else chunk
         writers = range(8) if chunk == 4 else range(EPI_WARPS)      # warps sub<2 = warps 0..7 write the PE
         for w in writers:
             if self.chunk_ver[phys][w] != want:
-                raise Hazard(f"MMA {(it, s, ic, part)} reads chunk {phys}: warp {w} wrote {self.chunk_ver[phys][w]}, want {want}")
+                raise Hazard(f"MMA {(it, s, ic)} reads chunk {phys}: warp {w} wrote {self.chunk_ver[phys][w]}, want {want}")
         if first:
             if self.acc_reads_left[buf]:
                 raise Hazard(f"step {(it, s)} overwrites TMEM buf {buf} with {self.acc_reads_left[buf]} reads outstanding")
             self.acc_writing[buf] = (it, s)
-            self.acc_ver[buf] = None
+            self.acc_ver[buf] = [None, None]
         elif self.acc_writing[buf] != (it, s):
             raise Hazard(f"accumulating step {(it, s)} into buf {buf} owned by {self.acc_writing[buf]}")
-        self.stage_readers[stage] += 1
+        for _, stage in parts:
+            self.stage_readers[stage] += 1
         self.chunk_readers[phys] += 1
         start = max(self.now, self.mma_busy_until)
         self.mma_busy_until = start + self.lat(0.5, 2.0)
 
         def fin():
-            self.stage_readers[stage] -= 1
+            for _, stage in parts:
+                self.stage_readers[stage] -= 1
             self.chunk_readers[phys] -= 1
         self.mma_queue.append((self.mma_busy_until, fin))
         self.at(self.mma_busy_until - self.now, self._retire)
@@ -214,13 +219,36 @@ class Sim:
                 started = it * USES[buf] + (s >> 1)
                 if started > 0:
                     yield ("wait", self.acc_empty[buf], (started - 1) & 1)
-                for ic in range(step_nkc(s)):
+                nkc = step_nkc(s)
+                split = self.split_tail and s not in (0, SKIP, K_STEPS - 1)
+
+                def half_done(buf=buf, it=it, s=s, half=0):
+                    self.acc_ver[buf][half] = (it, s)
+                    if self.acc_ver[buf][0] == (it, s) and self.acc_ver[buf][1] == (it, s):
+                        self.acc_writing[buf] = None
+                    self.acc_full[buf][half].arrive()
+                for ic in range(nkc):
                     c = 4 if s == 0 else (ic if ic < 4 else 4)
                     uses = (it * 2 + (1 if s == SKIP else 0)) if c == 4 else (it * A_PER_TILE + (s - 1))
                     yield ("wait", self.a_ready[c], uses & 1)
+                    if split and ic == nkc - 1:
+                        sidx = []
+                        for part in range(self.parts):
+                            yield ("wait", self.full[stage], rnd & 1)
+                            sidx.append((part, stage))
+                            stage += 1
+                            if stage == self.ns:
+                                stage, rnd = 0, rnd + 1
+                        for half in range(2):
+                            self.mma_group(it, s, ic, sidx, c, buf, first=False)
+                            self.commit(lambda h=half, f=half_done: f(half=h))
+                        for _, st in sidx:
+                            self.commit(lambda st=st: self.empty[st].arrive())
+                        yield ("delay", self.lat(0.05, 0.4))
+                        continue
                     for part in range(self.parts):
                         yield ("wait", self.full[stage], rnd & 1)
-                        self.mma_group(it, s, ic, part, stage, c, buf, first=(ic == 0 and part == 0))
+                        self.mma_group(it, s, ic, [(part, stage)], c, buf, first=(ic == 0 and part == 0))
                         st = stage
                         self.commit(lambda st=st: self.empty[st].arrive())
                         yield ("delay", self.lat(0.05, 0.4))
@@ -229,13 +257,10 @@ class Sim:
                             stage, rnd = 0, rnd + 1
                     if s == SKIP and ic == 0:
                         self.commit(self.c0_free.arrive)
-
-                def full_fn(buf=buf, it=it, s=s):
-                    self.acc_ver[buf] = (it, s)
-                    self.acc_writing[buf] = None
-                    self.acc_reads_left[buf] = EPI_WARPS
-                    self.acc_full[buf].arrive()
-                self.commit(full_fn)
+                if not split:
+                    self.commit(lambda f=half_done: (f(half=0), f(half=1)))
+                # the epilogue warps' read counter is armed when the step starts completing
+                self.commit(lambda buf=buf: self.acc_reads_left.__setitem__(buf, EPI_WARPS))
                 yield ("delay", self.lat(0.02, 0.1))
 
     def _write_chunk(self, w, phys, tag):
@@ -243,9 +268,10 @@ class Sim:
             raise Hazard(f"warp {w} writes chunk {phys} ({tag}) under {self.chunk_readers[phys]} MMAs in flight")
         self.chunk_ver[phys][w] = tag
 
-    def _read_acc(self, w, buf, it, s):
-        if self.acc_ver[buf] != (it, s):
-            raise Hazard(f"warp {w} reads TMEM buf {buf}: holds {self.acc_ver[buf]} (writing {self.acc_writing[buf]}), want {(it, s)}")
+    def _read_acc(self, w, buf, it, s, half):
+        if self.acc_ver[buf][half] != (it, s):
+            raise Hazard(f"warp {w} reads TMEM buf {buf} half {half}: holds {self.acc_ver[buf][half]} "
+                         f"(writing {self.acc_writing[buf]}), want {(it, s)}")
 
     def epilogue(self, w):
         sub = w >> 2
@@ -258,9 +284,12 @@ class Sim:
             # forward layers 0..7
             for l in range(8):
                 buf = l & 1
-                yield ("wait", self.acc_full[buf], (it * USES[buf] + (l >> 1)) & 1)
+                par = (it * USES[buf] + (l >> 1)) & 1
+                yield ("wait", self.acc_full[buf][0], par)
                 for chunk in range(4):
-                    self._read_acc(w, buf, it, l)
+                    if chunk == 2:
+                        yield ("wait", self.acc_full[buf][1], par)
+                    self._read_acc(w, buf, it, l, chunk >> 1)
                     yield ("delay", self.lat(0.1, 1.0))
                     self._write_chunk(w, chunk, (it, l + 1))
                     self.a_ready[chunk].arrive()
@@ -275,17 +304,20 @@ class Sim:
             # reverse steps 8..14
             for s in range(8, 15):
                 buf = s & 1
-                yield ("wait", self.acc_full[buf], (it * USES[buf] + (s >> 1)) & 1)
+                par = (it * USES[buf] + (s >> 1)) & 1
+                yield ("wait", self.acc_full[buf][0], par)
                 for chunk in range(4):
-                    self._read_acc(w, buf, it, s)
+                    if chunk == 2:
+                        yield ("wait", self.acc_full[buf][1], par)
+                    self._read_acc(w, buf, it, s, chunk >> 1)
                     yield ("delay", self.lat(0.1, 1.0))
                     self._write_chunk(w, chunk, (it, s + 1))
                     self.a_ready[chunk].arrive()
                 self.acc_reads_left[buf] -= 1
                 self.acc_empty[buf].arrive()
             # step 15: PE adjoint -> gradient; the exchange slots live in chunk 3 of the (dead) A tile
-            yield ("wait", self.acc_full[1], (it * USES[1] + 7) & 1)
-            self._read_acc(w, 1, it, 15)
+            yield ("wait", self.acc_full[1][0], (it * USES[1] + 7) & 1)
+            self._read_acc(w, 1, it, 15, 0)
             self.acc_reads_left[1] -= 1
             self.acc_empty[1].arrive()
             yield ("delay", self.lat(0.1, 0.8))
@@ -293,10 +325,10 @@ class Sim:
             yield ("delay", self.lat(0.05, 0.5))     # (named barriers of the lane quarter: no mbarrier involved)
 
 
-@pytest.mark.parametrize("nterms", [3, 1])
-def test_protocol_no_deadlock_no_hazard(nterms):
+@pytest.mark.parametrize("nterms,split", [(3, False), (3, True), (1, False)])
+def test_protocol_no_deadlock_no_hazard(nterms, split):
     for seed in range(40):
-        Sim(nterms, iters=3, seed=seed).run()
+        Sim(nterms, iters=3, seed=seed, split_tail=split).run()
 
 
 def test_model_detects_a_wrong_parity():
