@@ -222,6 +222,9 @@ def main():
     ap.add_argument("--grad-mode", default=os.environ.get("EMAP_GRAD_MODE", "forward"),
                     choices=["forward", "reverse"],
                     help="K1g forward-mode tangents (validated default) or K1r reverse-mode (mlp_rg.cu, opt-in)")
+    ap.add_argument("--bwd-stash", default=os.environ.get("EMAP_BWD_STASH", "dual"), choices=["dual", "shared"],
+                    help="backward: re-run the dual forward (validated default) or share the training forward's "
+                         "activations (needs --grad-mode reverse; opt-in)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
 
@@ -249,6 +252,9 @@ def main():
 
     from emap_b200 import _cabi as C
     ops.set_grad_mode(args.grad_mode)
+    ops.set_backward_mode(args.bwd_stash)
+    if args.bwd_stash == "shared" and args.grad_mode != "reverse":
+        raise SystemExit("--bwd-stash shared needs --grad-mode reverse")
     grad_call = "emap_udf_forward_grad_rev" if args.grad_mode == "reverse" else "emap_udf_forward_grad"
     net, var, beta, r = build_ours(dev, args.precision)
     B, n = args.rays, N0 + NI
@@ -390,7 +396,7 @@ def main():
             "data": "synthetic",
             "config": {"workload": f"replica-style synthetic cameras, {B} rays x {n} samples "
                                    f"({N0}+{NI}/{STEPS} hierarchical) per GPU, {args.mode}",
-                       "mode": args.mode, "grad_mode": args.grad_mode, "rays_per_gpu": B, "samples_per_ray": n,
+                       "mode": args.mode, "grad_mode": args.grad_mode, "bwd_stash": args.bwd_stash, "rays_per_gpu": B, "samples_per_ray": n,
                        "parallelism": f"rays sharded x{world}" + (", flat grad allreduce" if args.mode == "train" else ""),
                        "l2": "flushed (256 MiB write) between timed steps"},
             "clocks": clocks,

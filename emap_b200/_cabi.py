@@ -45,7 +45,8 @@ SIGNATURES = {
     "emap_udf_forward_grad": (ctypes.c_int, [_nd, _vp, _i32, _vp, _vp, _vp, _vp, _i32, _i64, _vp, _vp, _vp]),
     "emap_rgrad_scratch_bytes": (ctypes.c_size_t, []),
     "emap_udf_forward_grad_rev": (ctypes.c_int, [_nd, _vp, _i32, _vp, _vp, _vp, _vp, _i32, _i64, _vp, _vp, _vp,
-                                                 ctypes.c_size_t, _vp]),
+                                                 ctypes.c_size_t, _vp, _vp, _vp]),
+    "emap_bwd_tangent_forward": (ctypes.c_int, [_nd, _vp, _vp, _vp, _vp, _vp, _i32, _i64, _vp, _vp, _vp, _vp]),
     "emap_debug_rgrad": (ctypes.c_int, [_nd, _vp, _i32, _vp, _vp, _vp, _vp, _i32, _i64, _vp, _vp, _vp,
                                         ctypes.c_size_t, _vp, _vp]),
     "emap_debug_rg_image": (ctypes.c_int, [_nd, ctypes.c_int, _vp, _vp, _vp]),
@@ -84,7 +85,7 @@ LAUNCHES_PER_CALL = {
     "emap_coarse_z": 1, "emap_upsample_step": 1, "emap_render_prep": 1, "emap_render_core_fwd": 2,
     "emap_render_core_bwd": 2, "emap_bwd_pe_dual": 1, "emap_bwd_act_fwd": 1, "emap_bwd_top": 1,
     "emap_bwd_act_bwd": 1, "emap_bwd_weight_norm": 1, "emap_bwd_dual_forward": 1,
-    "emap_bwd_reverse_sweep": 1, "emap_bwd_bias_sums": 2, "emap_null_direction": 1, "emap_rays_from_pixels": 1,
+    "emap_bwd_reverse_sweep": 1, "emap_bwd_tangent_forward": 1, "emap_bwd_bias_sums": 2, "emap_null_direction": 1, "emap_rays_from_pixels": 1,
 }
 launch_count = 0
 # bench.py: name of ONE C-ABI entry point whose launches are bracketed by CUDA events on the current

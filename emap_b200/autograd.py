@@ -51,9 +51,18 @@ class _UDFForwardGrad(torch.autograd.Function):
     @staticmethod
     def forward(ctx, module, x, rays_o, rays_d, z, *params):
         net = module.packed()
-        udf, grad = ops.udf_forward_grad(net, module.prec_code, pts=x, rays_o=rays_o, rays_d=rays_d, z=z)
+        # shared-forward backward (opt-in, ops.set_backward_mode): when parameter gradients will be asked for,
+        # the reverse-mode forward also fills the value rows of the backward's stashes
+        stash = None
+        if ops.shared_backward() and net.desc.elem_type == 0 and any(ctx.needs_input_grad[5:]):
+            P = x.shape[0] if x is not None else z.numel()
+            stash = ops.alloc_backward_stash(P, net.packed.device)
+        udf, grad = ops.udf_forward_grad(net, module.prec_code, pts=x, rays_o=rays_o, rays_d=rays_d, z=z,
+                                         stash=stash)
         ctx.module = module
         ctx.pts = (x, rays_o, rays_d, z)
+        ctx.stash = stash
+        ctx.fold_id = getattr(net, "fold_id", None)
         return udf, grad
 
     @staticmethod
@@ -61,10 +70,14 @@ class _UDFForwardGrad(torch.autograd.Function):
         module = ctx.module
         x, ro, rd, z = ctx.pts
         net = module.packed()
+        stash = ctx.stash
+        if stash is not None and ctx.fold_id != getattr(net, "fold_id", None):
+            stash = None            # parameters changed between forward and backward: recompute (dual forward)
         flat_grad = ops.udf_backward(net, module.prec_code,
                                      None if d_udf is None else d_udf.contiguous(),
                                      None if d_grad is None else d_grad.contiguous(),
-                                     pts=x, rays_o=ro, rays_d=rd, z=z, flat_params=net.flat)
+                                     pts=x, rays_o=ro, rays_d=rd, z=z, flat_params=net.flat, stash=stash)
+        ctx.stash = None
         grads = _split_flat(flat_grad, module.flat_param_list())
         return (None, None, None, None, None, *grads)
 

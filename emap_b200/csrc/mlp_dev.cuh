@@ -65,12 +65,13 @@ static_assert(SmemPlan<3, 1>::total <= 232448 && SmemPlan<3, 0>::total <= 232448
 
 // per-mode schedule constants (MODE 0 forward, 1 forward+grad (4 rows/point), 2 dual forward with
 // stashes for the backward (2 rows/point, layers 0..7 only -- the output layer is pulled back by a
-// separate small kernel))
+// separate small kernel), 3 tangent-only forward of the backward (1 row/point, layers 0..7; the value rows
+// of the stash come from the training forward, mlp_rg.cu))
 template <int MODE> struct ModeInfo {
-  static constexpr int kLayers = (MODE == 2) ? 8 : 9;          // MMA layers per tile
-  static constexpr int kUses0 = (MODE == 2) ? 4 : 5;           // accumulator-0 uses per tile
-  static constexpr int kAPerTile = (MODE == 2) ? 7 : 8;        // a_ready[0..3] completions per tile
-  static constexpr int kPtsPerTile = (MODE == 0) ? 128 : ((MODE == 1) ? 32 : 64);
+  static constexpr int kLayers = (MODE >= 2) ? 8 : 9;          // MMA layers per tile
+  static constexpr int kUses0 = (MODE >= 2) ? 4 : 5;           // accumulator-0 uses per tile
+  static constexpr int kAPerTile = (MODE >= 2) ? 7 : 8;        // a_ready[0..3] completions per tile
+  static constexpr int kPtsPerTile = (MODE == 0 || MODE == 3) ? 128 : ((MODE == 1) ? 32 : 64);
 };
 
 template <typename T> struct Elem;
@@ -172,6 +173,8 @@ __device__ __forceinline__ void load_point(const MlpArgs& a, long long idx, floa
 // common.cuh), written as four 16-byte groups of the PE chunk.
 //   MODE 0: row = point:            [x, sin(2^j x_c), cos(2^j x_c)]          (embedder.py:26-35)
 //   MODE 1: row = (point, type):    type 0 as above; type c+1 = d/dx_c of it (the tangent seed).
+//   MODE 2: row = (point, value|tangent along gb);   MODE 3: row = point, tangent along gb only;
+//   MODE 4 (mlp_rg.cu): as MODE 0, and the values also go to the backward's U_0 stash when one is given.
 template <int NTERMS, int MODE, typename T, int HF>
 __device__ __forceinline__ void pe_stage(const MlpArgs& args, const float (&x)[3], int multires,
                                          int lane, int row, long long pt, long long tile,
@@ -182,7 +185,7 @@ __device__ __forceinline__ void pe_stage(const MlpArgs& args, const float (&x)[3
   constexpr int vofs = (HF == 0) ? 4 : 0;
   const int ty = lane & 3;
   float vals[32];
-  if (MODE == 0) {
+  if (MODE == 0 || MODE == 4) {
     if (HF == 0) { vals[0] = x[0]; vals[1] = x[1]; vals[2] = x[2]; vals[3] = 0.f; }
 #pragma unroll
     for (int i = 0; i < npairs; ++i) {
@@ -198,6 +201,17 @@ __device__ __forceinline__ void pe_stage(const MlpArgs& args, const float (&x)[3
         const int ref = pe_col_to_ref(HF * 32 + k, multires);
         if (ref >= 0) args.pe_out[pt * pe + ref] = vals[k];
       }
+    }
+  } else if (MODE == 3) {
+    // tangent of the PE along gb (one row per point): d/dt gamma(x + t gb)
+    if (HF == 0) { vals[0] = gb[0]; vals[1] = gb[1]; vals[2] = gb[2]; vals[3] = 0.f; }
+#pragma unroll
+    for (int i = 0; i < npairs; ++i) {
+      const int qq = qbase + i, j = qq / 3, ax = qq % 3;
+      float s = 0.f, c = 0.f;
+      const float f = (float)(1 << j);
+      if (j < multires) sincosf(x[ax] * f, &s, &c);
+      vals[vofs + 2 * i] = f * c * gb[ax]; vals[vofs + 2 * i + 1] = -f * s * gb[ax];
     }
   } else if (MODE == 2) {
     // dual rows: lane pair (value, tangent along gb); the two lanes split the sincos work
@@ -271,6 +285,20 @@ __device__ __forceinline__ void pe_stage(const MlpArgs& args, const float (&x)[3
       else if (ax == ty - 1 && j < multires) { vs = f * C; vc = -f * S; }
       else { vs = 0.f; vc = 0.f; }
       vals[vofs + 2 * i] = vs; vals[vofs + 2 * i + 1] = vc;
+    }
+  }
+  if ((MODE == 4 || MODE == 3) && emit_pe_out && args.st_u0 && pt < args.P && tile < args.num_tiles) {
+    // backward stash U_0 [2P,64], kernel column order: value rows [0,P) from the training forward (MODE 4 =
+    // MODE 0 values + this stash; mlp_rg.cu), tangent rows [P,2P) from the tangent-only forward (MODE 3)
+    __half* dst = args.st_u0 + ((MODE == 3 ? args.P : 0) + pt) * 64 + HF * 32;
+#pragma unroll
+    for (int g = 0; g < 4; ++g) {
+      uint4 v;
+      v.x = Elem<__half>::pack2(vals[g * 8 + 0], vals[g * 8 + 1]);
+      v.y = Elem<__half>::pack2(vals[g * 8 + 2], vals[g * 8 + 3]);
+      v.z = Elem<__half>::pack2(vals[g * 8 + 4], vals[g * 8 + 5]);
+      v.w = Elem<__half>::pack2(vals[g * 8 + 6], vals[g * 8 + 7]);
+      *reinterpret_cast<uint4*>(dst + g * 8) = v;
     }
   }
 #pragma unroll

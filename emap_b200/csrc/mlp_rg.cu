@@ -306,8 +306,9 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_rgrad_kernel(const Args args)
       load_point(m, pt, net_scale, x);
       // ------------------------------------------------ input stage: positional encoding -> chunk 0
       if (sub < 2) {
-        if (sub == 0) pe_stage<NTERMS, 0, T, 0>(m, x, multires, lane, row, pt, tile, false, A_hi, A_lo, gz);
-        else          pe_stage<NTERMS, 0, T, 1>(m, x, multires, lane, row, pt, tile, false, A_hi, A_lo, gz);
+        // (MODE 4 = the forward's PE values, also written to the backward's U_0 stash when one is given)
+        if (sub == 0) pe_stage<NTERMS, 4, T, 0>(m, x, multires, lane, row, pt, tile, true, A_hi, A_lo, gz);
+        else          pe_stage<NTERMS, 4, T, 1>(m, x, multires, lane, row, pt, tile, true, A_hi, A_lo, gz);
         fence_proxy_async_smem();
         __syncwarp();
         if (lane == 0) mbar_arrive(&a_ready[4]);
@@ -341,6 +342,7 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_rgrad_kernel(const Args args)
               m.dbg_acc[((size_t)l * 128 + row) * 256 + col0 + k] = __uint_as_float(r[k]) * kInvWeightScale;
           }
           float* sgp = sg_ptr(top ? 0 : l, chunk);
+          uint32_t pu[8];                     // h_{l+1} of this thread's 16 columns as fp16 (training stash)
 #pragma unroll
           for (int g = 0; g < 2; ++g) {
             const float4 bA = bv[2 * g], bB = bv[2 * g + 1];
@@ -349,6 +351,8 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_rgrad_kernel(const Args args)
 #pragma unroll
             for (int j = 0; j < 8; ++j)
               h[j] = softplus100<true>(fmaf(__uint_as_float(r[g * 8 + j]), k1, bb[j]), sg[j]);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) pu[g * 4 + j] = Elem<__half>::pack2(h[2 * j], h[2 * j + 1]);
             if (!top) {
               store_group<NTERMS, T>(dst_hi, dst_lo, row, sub * 2 + g, h);
               st_scratch8(sgp + g * 256, sg);
@@ -366,6 +370,9 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_rgrad_kernel(const Args args)
           fence_proxy_async_smem();
           __syncwarp();
           if (lane == 0) mbar_arrive(&a_ready[chunk]);
+          // training: value rows [0,P) of the backward's stash U_{l+1} (emap_bwd_tangent_forward adds the
+          // tangent rows later) -- after the hand-off, off the MMA's critical path
+          if (m.st_u && ok) stg256(m.st_u + (size_t)l * 2 * (size_t)m.P * 256 + (size_t)pt * 256 + col0, pu);
         }
         tc_fence_before();
         __syncwarp();
@@ -522,6 +529,10 @@ static int launch(const Args& a_in, size_t scratch_bytes, cudaStream_t stream) {
   return 0;
 }
 
+int run(const emap_net_desc* net, const void* packed, int precision, const float* pts, const float* rays_o,
+        const float* rays_d, const float* z, int32_t n_per_ray, int64_t P, float* udf_out, float* grad_out,
+        void* scratch, size_t scratch_bytes, void* st_u0, void* st_u, float* dbg_acc, void* stream);
+
 }  // namespace rg
 }  // namespace emap
 
@@ -534,9 +545,10 @@ extern "C" size_t emap_rgrad_scratch_bytes(void) {
 extern "C" int emap_udf_forward_grad_rev(const emap_net_desc* net, const void* packed, int precision,
                                          const float* pts, const float* rays_o, const float* rays_d,
                                          const float* z, int32_t n_per_ray, int64_t P, float* udf_out,
-                                         float* grad_out, void* scratch, size_t scratch_bytes, void* stream) {
-  return emap_debug_rgrad(net, packed, precision, pts, rays_o, rays_d, z, n_per_ray, P, udf_out, grad_out,
-                          scratch, scratch_bytes, nullptr, stream);
+                                         float* grad_out, void* scratch, size_t scratch_bytes, void* st_u0,
+                                         void* st_u, void* stream) {
+  return rg::run(net, packed, precision, pts, rays_o, rays_d, z, n_per_ray, P, udf_out, grad_out, scratch,
+                 scratch_bytes, st_u0, st_u, nullptr, stream);
 }
 
 // Test hook: the same launch, additionally dumping the accumulators of tile 0 after every MMA step,
@@ -547,7 +559,16 @@ extern "C" int emap_debug_rgrad(const emap_net_desc* net, const void* packed, in
                                 const float* z, int32_t n_per_ray, int64_t P, float* udf_out,
                                 float* grad_out, void* scratch, size_t scratch_bytes, float* dbg_acc,
                                 void* stream) {
+  return rg::run(net, packed, precision, pts, rays_o, rays_d, z, n_per_ray, P, udf_out, grad_out, scratch,
+                 scratch_bytes, nullptr, nullptr, dbg_acc, stream);
+}
+
+int emap::rg::run(const emap_net_desc* net, const void* packed, int precision, const float* pts,
+                  const float* rays_o, const float* rays_d, const float* z, int32_t n_per_ray, int64_t P,
+                  float* udf_out, float* grad_out, void* scratch, size_t scratch_bytes, void* st_u0,
+                  void* st_u, float* dbg_acc, void* stream) {
   if (check_net(net)) return 1;
+  if ((st_u0 == nullptr) != (st_u == nullptr)) return set_error("emap_udf_forward_grad_rev: give both stash pointers or none");
   if (!packed || !udf_out || !grad_out || !scratch) return set_error("emap_udf_forward_grad_rev: NULL pointer");
   if (P <= 0) return set_error("P must be > 0");
   if (!pts) {
@@ -561,6 +582,7 @@ extern "C" int emap_debug_rgrad(const emap_net_desc* net, const void* packed, in
   a.m.packed = (const uint8_t*)packed; a.m.pts = pts; a.m.rays_o = rays_o; a.m.rays_d = rays_d; a.m.z = z;
   a.m.n_per_ray = n_per_ray; a.m.P = P; a.m.udf_out = udf_out; a.m.grad_out = grad_out;
   a.m.dbg_acc = dbg_acc;
+  a.m.st_u0 = (__half*)st_u0; a.m.st_u = (__half*)st_u;
   a.scratch = (float*)scratch;
   a.rg_off = h.reserved[3];
   cudaStream_t st = (cudaStream_t)stream;

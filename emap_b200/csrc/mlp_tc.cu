@@ -312,13 +312,13 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_kernel(const MlpArgs args) {
       const long long tile = (long long)blockIdx.x + (long long)iter * gridDim.x;
       // ------------------------------------------------ input stage: positional encoding -> chunk 0
       long long pt;
-      if (MODE == 0) pt = tile * 128 + row;
+      if (MODE == 0 || MODE == 3) pt = tile * 128 + row;
       else if (MODE == 1) pt = tile * 32 + q * 8 + p8;
       else pt = tile * 64 + q * 16 + (lane >> 1);
       float x[3];
       load_point(args, pt, net_scale, x);
       float gb[3] = {0.f, 0.f, 0.f};
-      if (MODE == 2 && args.gbar) {
+      if (MODE >= 2 && args.gbar) {
         const long long pc = (pt < args.P) ? pt : args.P - 1;
         gb[0] = args.gbar[pc * 3]; gb[1] = args.gbar[pc * 3 + 1]; gb[2] = args.gbar[pc * 3 + 2];
       }
@@ -336,11 +336,20 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_kernel(const MlpArgs args) {
         const bool stamp = args.dbg_clk && blockIdx.x == 0 && iter == 1 && warp == 0 && lane == 0;
         if (stamp) args.dbg_clk[l * 8 + 0] = clock64();
         const uint32_t acc_par = ((uint32_t)iter * (buf ? 4u : (uint32_t)MI::kUses0) + (uint32_t)(l >> 1)) & 1;
+        // MODE 3: this row's h_{l+1} (value row of the stash, written by the training forward) for the
+        // thread's 16 columns of all four chunks -- independent of the MMA, fetched before waiting for it
+        uint32_t hw[(MODE == 3) ? 4 : 1][8];
+        if (MODE == 3) {
+          const long long pc = (pt < args.P) ? pt : args.P - 1;
+          const __half* hp = args.st_u + (size_t)l * 2 * (size_t)args.P * 256 + (size_t)pc * 256 + sub * 16;
+#pragma unroll
+          for (int c4 = 0; c4 < 4; ++c4) ldg256(hp + c4 * 64, hw[c4]);
+        }
         mbar_wait(&acc_full[buf * 2], acc_par, 500 + buf, l);
         tc_fence_after();
         if (stamp) args.dbg_clk[l * 8 + 1] = clock64();
         const float* bl = bias100 + l * kHidden;
-#pragma unroll 1
+#pragma unroll (MODE == 3 ? 4 : 1)
         for (int chunk = 0; chunk < 4; ++chunk) {
           // all 16 warps convert the same 64-column chunk (16 columns each), so chunk c of the next
           // layer's A tile is complete after (c+1)/4 of the epilogue and its MMAs start then
@@ -352,10 +361,10 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_kernel(const MlpArgs args) {
           // the bias words this lane needs, issued before the accumulator load so that their L1/L2
           // latency hides under the tcgen05.ld wait (ncu: 8 % of the dual kernel's samples sat on it)
           //   MODE 0: 16 columns; MODE 1: the lane's 4 value columns; MODE 2: the lane's 8 columns
-          constexpr int kBiasVec = (MODE == 0) ? 4 : ((MODE == 1) ? 1 : 2);
+          constexpr int kBiasVec = (MODE == 0) ? 4 : ((MODE == 1 || MODE == 3) ? 1 : 2);   // MODE 3: unused
           float4 bv[kBiasVec];
           {
-            const int bofs = (MODE == 0) ? 0 : ((MODE == 1) ? 4 * ty : 8 * (lane & 1));
+            const int bofs = (MODE == 0 || MODE == 3) ? 0 : ((MODE == 1) ? 4 * ty : 8 * (lane & 1));
 #pragma unroll
             for (int i = 0; i < kBiasVec; ++i) bv[i] = __ldg(reinterpret_cast<const float4*>(bl + col0 + bofs) + i);
           }
@@ -410,6 +419,30 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_kernel(const MlpArgs args) {
             if (okp && !(args.dbg_flags & 8)) {
               const size_t plane_u = (size_t)l * 2 * (size_t)args.P * 256;
               stg256(args.st_u + plane_u + (size_t)rowg * 256 + col0, pu);
+            }
+          } else if (MODE == 3) {
+            // tangent rows only: hdot_{l+1} = softplus'(a_l) . adot_l with softplus'(a_l) = 1 - exp(-100 h_{l+1})
+            // recovered from the value row of the stash (as the reverse sweep does); next layer's A tile +
+            // the tangent row of the stash.
+            const bool okp = (tile < args.num_tiles) && (pt < args.P);
+            uint32_t pu[8];
+#pragma unroll
+            for (int g = 0; g < 2; ++g) {
+              float v8[8];
+#pragma unroll
+              for (int w2 = 0; w2 < 4; ++w2) {
+                const float2 h2 = __half22float2(*reinterpret_cast<const __half2*>(&hw[chunk][g * 4 + w2]));
+                const float s0 = 1.0f - __expf(-kSoftplusBeta * h2.x), s1 = 1.0f - __expf(-kSoftplusBeta * h2.y);
+                v8[2 * w2] = s0 * (__uint_as_float(r[g * 8 + 2 * w2]) * kInvWeightScale);
+                v8[2 * w2 + 1] = s1 * (__uint_as_float(r[g * 8 + 2 * w2 + 1]) * kInvWeightScale);
+              }
+              if (l < 7) store_group<NTERMS, T>(dst_hi, dst_lo, row, sub * 2 + g, v8);
+#pragma unroll
+              for (int j = 0; j < 4; ++j) pu[g * 4 + j] = Elem<__half>::pack2(v8[2 * j], v8[2 * j + 1]);
+            }
+            if (okp) {
+              const size_t plane_u = (size_t)l * 2 * (size_t)args.P * 256;
+              stg256(args.st_u + plane_u + ((size_t)args.P + (size_t)pt) * 256 + col0, pu);
             }
           } else if (MODE == 0) {
 #pragma unroll
@@ -483,7 +516,7 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_kernel(const MlpArgs args) {
           if (stamp && chunk < 2) args.dbg_clk[l * 8 + 3 + 3 * chunk] = clock64();
           fence_proxy_async_smem();
           __syncwarp();
-          if (lane == 0 && !(MODE == 2 && l == 7)) arrive_issuer(&a_ready[chunk]);
+          if (lane == 0 && !(MODE >= 2 && l == 7)) arrive_issuer(&a_ready[chunk]);
           if (stamp && chunk < 2) args.dbg_clk[l * 8 + 4 + 3 * chunk] = clock64();
         }
         tc_fence_before();
@@ -503,7 +536,7 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_kernel(const MlpArgs args) {
       }
 
       // ------------------------------------------------ output layer (layer 8, accumulator buf 0, col 0)
-      if (MODE == 2) continue;        // dual forward stops at layer 7 (the output layer is pulled back separately)
+      if (MODE >= 2) continue;        // dual / tangent forward stop at layer 7 (the output layer is pulled back separately)
       mbar_wait(&acc_full[0], ((uint32_t)iter * 5u + 4u) & 1, 510);
       tc_fence_after();
       if (sub == 0) {
@@ -669,6 +702,26 @@ extern "C" int emap_bwd_dual_forward(const emap_net_desc* net, const void* packe
   a.n_per_ray = n_per_ray; a.P = P; a.gbar = d_grad;
   a.st_u0 = (__half*)st_u0; a.st_u = (__half*)st_u;
   return dispatch<2>(net, precision, a, (cudaStream_t)stream);
+}
+
+// K1b stage 1, shared-forward variant: when the training forward (emap_udf_forward_grad_rev with stash
+// pointers) has already written the VALUE rows of st_u0 / st_u, only the tangent rows along d_grad remain:
+// one row per point (128 points per tile), no softplus -- about half the work of the dual forward.
+extern "C" int emap_bwd_tangent_forward(const emap_net_desc* net, const void* packed, const float* pts,
+                                        const float* rays_o, const float* rays_d, const float* z,
+                                        int32_t n_per_ray, int64_t P, const float* d_grad, void* st_u0,
+                                        void* st_u, void* stream) {
+  if (check_net(net)) return 1;
+  if (!packed || !st_u0 || !st_u) return set_error("emap_bwd_tangent_forward: NULL pointer");
+  if (check_points(pts, rays_o, rays_d, z, n_per_ray, P)) return 1;
+  MlpArgs a;
+  memset(&a, 0, sizeof(a));
+  a.packed = (const uint8_t*)packed; a.pts = pts; a.rays_o = rays_o; a.rays_d = rays_d; a.z = z;
+  a.n_per_ray = n_per_ray; a.P = P; a.gbar = d_grad;
+  a.st_u0 = (__half*)st_u0; a.st_u = (__half*)st_u;
+  // single-MMA, one CTA per SM, no cluster variants: the only configuration this mode is built for
+  if (net->elem_type == 0) return launch<1, 3, __half, 1>(a, (cudaStream_t)stream);
+  return launch<1, 3, __nv_bfloat16, 1>(a, (cudaStream_t)stream);
 }
 
 // Debug / test hook: run the forward (mode 0) or forward+grad (mode 1) kernel and additionally dump

@@ -79,6 +79,30 @@ _GRAD_MODE = os.environ.get("EMAP_GRAD_MODE", "forward")
 _RG_SCRATCH = {}
 
 
+# How the backward obtains the dual activations U_l = (h_l ; hdot_l): "dual" = re-run the dual forward
+# (validated default); "shared" = the training forward (K1r) writes the value rows while it has them in
+# registers and the backward only adds the tangent rows (emap_bwd_tangent_forward, about half the work).
+# "shared" needs grad mode "reverse"; opt-in for the same reason as K1r.
+_BWD_MODE = os.environ.get("EMAP_BWD_STASH", "dual")
+
+
+def set_backward_mode(mode: str) -> None:
+    global _BWD_MODE
+    if mode not in ("dual", "shared"):
+        raise ValueError("backward mode must be 'dual' or 'shared'")
+    _BWD_MODE = mode
+
+
+def shared_backward() -> bool:
+    return _BWD_MODE == "shared" and _GRAD_MODE == "reverse"
+
+
+def alloc_backward_stash(P: int, device) -> Tuple[torch.Tensor, torch.Tensor]:
+    """(st_u0 [2P,64], st_u [8,2P,256]) fp16 -- the layout emap_bwd_dual_forward documents."""
+    return (torch.empty(2 * P, 64, dtype=torch.float16, device=device),
+            torch.empty(8, 2 * P, 256, dtype=torch.float16, device=device))
+
+
 def set_grad_mode(mode: str) -> None:
     global _GRAD_MODE
     if mode not in ("forward", "reverse"):
@@ -91,7 +115,7 @@ def get_grad_mode() -> str:
 
 
 def _rg_scratch(dev: torch.device) -> torch.Tensor:
-    """K1r's sigma scratch (1 MiB per SM), one per device; kernels on one stream reuse it in order."""
+    """K1r's sigma scratch (896 KiB per SM), one per device; kernels on one stream reuse it in order."""
     key = (dev.type, dev.index if dev.index is not None else torch.cuda.current_device())
     buf = _RG_SCRATCH.get(key)
     if buf is None:
@@ -103,18 +127,26 @@ def _rg_scratch(dev: torch.device) -> torch.Tensor:
 
 
 def udf_forward_grad(net: PackedNet, precision: int, pts=None, rays_o=None, rays_d=None, z=None,
-                     mode: Optional[str] = None) -> Tuple[torch.Tensor, torch.Tensor]:
+                     mode: Optional[str] = None, stash=None) -> Tuple[torch.Tensor, torch.Tensor]:
+    """stash = (st_u0, st_u) from alloc_backward_stash (reverse mode only): the forward also writes the
+    value rows of the backward's stashes."""
     pts, ro, rd, zz, n, P = _points_args(pts, rays_o, rays_d, z)
     dev = net.packed.device
     udf = torch.empty(P, dtype=torch.float32, device=dev)
     grad = torch.empty(P, 3, dtype=torch.float32, device=dev)
     if (mode or _GRAD_MODE) == "reverse":
         scratch = _rg_scratch(dev)
+        su0, su = (None, None) if stash is None else stash
+        if stash is not None and (su0.shape != (2 * P, 64) or su.shape != (8, 2 * P, 256)
+                                  or su0.dtype != torch.float16 or su.dtype != torch.float16):
+            raise RuntimeError("backward stash must be (fp16 [2P,64], fp16 [8,2P,256])")
         C.check(C.lib().emap_udf_forward_grad_rev(ctypes.byref(net.desc), C.ptr(net.packed), precision,
                                                   C.ptr(pts), C.ptr(ro), C.ptr(rd), C.ptr(zz), n, P,
                                                   C.ptr(udf), C.ptr(grad), C.ptr(scratch), scratch.numel(),
-                                                  C.stream()))
+                                                  C.ptr(su0), C.ptr(su), C.stream()))
         return udf, grad
+    if stash is not None:
+        raise RuntimeError("a backward stash can only be filled by the reverse-mode forward (K1r)")
     C.check(C.lib().emap_udf_forward_grad(ctypes.byref(net.desc), C.ptr(net.packed), precision,
                                           C.ptr(pts), C.ptr(ro), C.ptr(rd), C.ptr(zz), n, P,
                                           C.ptr(udf), C.ptr(grad), C.stream()))
@@ -334,7 +366,7 @@ def _pe_perm(multires: int, device):
 
 def udf_backward(net: PackedNet, precision: int, d_udf: Optional[torch.Tensor],
                  d_grad: Optional[torch.Tensor], pts=None, rays_o=None, rays_d=None, z=None,
-                 flat_params: Optional[torch.Tensor] = None) -> torch.Tensor:
+                 flat_params: Optional[torch.Tensor] = None, stash=None) -> torch.Tensor:
     """Pull the cotangents (d_udf[P], d_grad[P,3]) back to the flat parameter gradient.
 
     Fused path (default; fp16 operand images): dual forward with stashes and the reverse sweep are two
@@ -342,7 +374,7 @@ def udf_backward(net: PackedNet, precision: int, d_udf: Optional[torch.Tensor],
     library GEMMs.  EMAP_BWD=layerwise selects the round-1 layer-by-layer structure (kept as a
     cross-check: element-wise kernels + a library GEMM per layer and direction)."""
     import os
-    if net.desc.elem_type != 0 or os.environ.get("EMAP_BWD") == "layerwise":
+    if stash is None and (net.desc.elem_type != 0 or os.environ.get("EMAP_BWD") == "layerwise"):
         return udf_backward_layerwise(net, precision, d_udf, d_grad, pts, rays_o, rays_d, z, flat_params)
     L = C.lib()
     pts, ro, rd, zz, n, P = _points_args(pts, rays_o, rays_d, z)
@@ -360,10 +392,18 @@ def udf_backward(net: PackedNet, precision: int, d_udf: Optional[torch.Tensor],
         boff.append(off)
         off += out_dim[l] * (2 + in_dim[l])
 
-    st_u0, st_u, st_a = h16(2 * P, 64), h16(8, 2 * P, 256), h16(8, 2 * P, 256)
-    C.check(L.emap_bwd_dual_forward(desc, C.ptr(net.packed), C.PREC_HALF, C.ptr(pts), C.ptr(ro), C.ptr(rd),
-                                    C.ptr(zz), n, P, C.ptr(None if d_grad is None else C.f32(d_grad)),
-                                    C.ptr(st_u0), C.ptr(st_u), st))
+    st_a = h16(8, 2 * P, 256)
+    if stash is not None:
+        # value rows written by the training forward (K1r): add the tangent rows only
+        st_u0, st_u = stash
+        C.check(L.emap_bwd_tangent_forward(desc, C.ptr(net.packed), C.ptr(pts), C.ptr(ro), C.ptr(rd), C.ptr(zz),
+                                           n, P, C.ptr(None if d_grad is None else C.f32(d_grad)),
+                                           C.ptr(st_u0), C.ptr(st_u), st))
+    else:
+        st_u0, st_u = h16(2 * P, 64), h16(8, 2 * P, 256)
+        C.check(L.emap_bwd_dual_forward(desc, C.ptr(net.packed), C.PREC_HALF, C.ptr(pts), C.ptr(ro), C.ptr(rd),
+                                        C.ptr(zz), n, P, C.ptr(None if d_grad is None else C.f32(d_grad)),
+                                        C.ptr(st_u0), C.ptr(st_u), st))
     coef = torch.empty(2 * P, dtype=torch.float32, device=dev)
     U8 = st_u[7]
     C.check(L.emap_bwd_top(desc, C.ptr(U8), C.ptr(W[8].reshape(-1)), C.ptr(flat_params[boff[8]:boff[8] + 1]),

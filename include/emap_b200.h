@@ -74,10 +74,14 @@ int emap_udf_forward_grad(const emap_net_desc* net, const void* packed, int prec
  * bytes of device memory (896 KiB per SM, rewritten tile after tile -> L2-resident), reusable across
  * calls on one stream.  Selected by the host shim with EMAP_GRAD_MODE=reverse / ops.set_grad_mode().  */
 size_t emap_rgrad_scratch_bytes(void);
+/* st_u0 / st_u (both or neither; training only): the backward's stashes (see emap_bwd_dual_forward) --
+ * the forward then writes their VALUE rows [0,P) (PE and h_1..h_8 as fp16) and the backward only has to
+ * add the tangent rows with emap_bwd_tangent_forward instead of re-running the dual forward.        */
 int emap_udf_forward_grad_rev(const emap_net_desc* net, const void* packed, int precision,
                               const float* pts, const float* rays_o, const float* rays_d,
                               const float* z, int32_t n_per_ray, int64_t P, float* udf_out,
-                              float* grad_out, void* scratch, size_t scratch_bytes, void* stream);
+                              float* grad_out, void* scratch, size_t scratch_bytes, void* st_u0,
+                              void* st_u, void* stream);
 
 /* ---- K1b: backward of (udf, d udf/dx) w.r.t. the 462,980 MLP parameters -------------------------
  * replaces: autograd through UDFNetwork.forward + .gradient(create_graph=True)
@@ -111,6 +115,12 @@ int emap_bwd_dual_forward(const emap_net_desc* net, const void* packed, int prec
                           void* stream);
 int emap_bwd_reverse_sweep(const emap_net_desc* net, const void* packed, const float* coef,
                            const void* st_u, void* st_a, int64_t P, void* stream);
+/* Shared-forward variant of stage 1: the value rows of st_u0 / st_u were written by the training forward
+ * (emap_udf_forward_grad_rev with stash pointers); this adds the tangent rows [P,2P) along d_grad (NULL =
+ * zero tangent): one row per point, sigma_l recovered from the stashed h_{l+1}, single fp16 MMA.       */
+int emap_bwd_tangent_forward(const emap_net_desc* net, const void* packed, const float* pts,
+                             const float* rays_o, const float* rays_d, const float* z, int32_t n_per_ray,
+                             int64_t P, const float* d_grad, void* st_u0, void* st_u, void* stream);
 /* db_l[c] = sum over the value rows p < P of A_l[p, c], l = 0..7, from the reverse sweep's stash
  * st_a [8][2P,256] fp16 -> db [8,256] fp32.  partial: scratch [8*296*256] floats.  Deterministic two-pass
  * reduction (no atomics).  replaces the bias half of autograd's addmm backward (udf_model.py:102).      */

@@ -163,3 +163,92 @@ def test_render_with_reverse_mode_matches_default():
             ops.set_grad_mode("forward")
     for k in ("edge", "depth", "weights", "gradients", "udf"):
         assert maxdiff(outs["forward"][k], outs["reverse"][k]) <= 2e-3, k
+
+
+# ---------------------------------------------------------------------------------------------------
+# Shared-forward backward (opt-in, ops.set_backward_mode("shared")): K1r writes the value rows of the
+# backward's stashes in the training forward, emap_bwd_tangent_forward (mlp_kernel MODE 3) adds the tangent
+# rows; everything downstream (top, reverse sweep, dW GEMMs, weight-norm) is the validated path.
+# ---------------------------------------------------------------------------------------------------
+def test_shared_stash_matches_dual_forward_stash():
+    """diagnostic, ops level: (K1r value rows + tangent forward) vs the validated dual forward's stashes.
+    fp16 stashes; the value rows now come from the fp32x3 forward instead of a single-fp16-MMA recompute,
+    so they agree to the fp16 forward's own error (<= 4e-3 of the plane's max), not bit for bit."""
+    from emap_b200 import ops, _cabi as C
+    import ctypes
+    net, p = _net(True)
+    torch.manual_seed(5)
+    P = 1000                                           # ragged: 8 tiles of 128, 16 tiles of 64
+    x = ((torch.rand(P, 3) * 2 - 1) * 0.9).cuda()
+    gbar = torch.randn(P, 3).cuda() * 0.1
+    L, desc, st = C.lib(), ctypes.byref(net.desc), C.stream()
+    u0_d, u_d = ops.alloc_backward_stash(P, x.device)
+    C.check(L.emap_bwd_dual_forward(desc, C.ptr(net.packed), C.PREC_HALF, C.ptr(x), None, None, None, 0, P,
+                                    C.ptr(gbar), C.ptr(u0_d), C.ptr(u_d), st))
+    u0_s, u_s = ops.alloc_backward_stash(P, x.device)
+    u0_s.fill_(float("nan")); u_s.fill_(float("nan"))  # every row must be written by one of the two kernels
+    ops.udf_forward_grad(net, C.PREC_FP32X3, pts=x, mode="reverse", stash=(u0_s, u_s))
+    C.check(L.emap_bwd_tangent_forward(desc, C.ptr(net.packed), C.ptr(x), None, None, None, 0, P, C.ptr(gbar),
+                                       C.ptr(u0_s), C.ptr(u_s), st))
+    torch.cuda.synchronize()
+    assert torch.isfinite(u0_s).all() and torch.isfinite(u_s).all()
+    assert maxdiff(u0_s[:P], u0_d[:P]) <= 1e-3 * float(u0_d[:P].abs().max())   # PE value rows (same sincosf)
+    assert maxdiff(u0_s[P:], u0_d[P:]) <= 2e-3 * float(u0_d[P:].abs().max())   # PE tangent rows
+    for l in range(8):
+        for rows, name in ((slice(0, P), "value"), (slice(P, 2 * P), "tangent")):
+            ref = u_d[l][rows].float()
+            err = maxdiff(u_s[l][rows].float(), ref) / (float(ref.abs().max()) + 1e-12)
+            assert err <= 8e-3, (l, name, err)
+
+
+@pytest.mark.parametrize("tag,pert", [("init", False), ("pert", True)])
+def test_shared_backward_param_grads_vs_reference(golden, tag, pert):
+    """the double-backward fixture of tests/test_gpu_train.py with K1r + shared-forward backward selected"""
+    from emap_b200 import ops
+    from tests.test_gpu_render import build
+    from tests.test_gpu_train import _check
+    g = golden(f"mlp_{tag}")
+    ops.set_grad_mode("reverse"); ops.set_backward_mode("shared")
+    try:
+        net, var, beta, r = build(10, pert, n_samples=64, n_importance=0, up_sample_steps=5)
+        x = g["x"].cuda()
+        y, _ = net(x)
+        gg = net.gradient(x.clone()).squeeze(1)
+        loss = (g["cu"].cuda() * y).sum() + (g["cg"].cuda() * gg).sum()
+        assert abs(float(loss) - float(g["loss"])) <= 2e-3 * max(1.0, abs(float(g["loss"])))
+        net.zero_grad()
+        loss.backward()
+        torch.cuda.synchronize()
+    finally:
+        ops.set_grad_mode("forward"); ops.set_backward_mode("dual")
+    _check([(n, p.grad) for n, p in net.named_parameters()], g, "dgrad", 1e-2)
+
+
+def test_shared_backward_render_loss_matches_default():
+    """a full render() loss, backward through the drop-in classes: shared-forward vs the default path"""
+    from emap_b200 import ops
+    from tests.test_gpu_render import build
+    from oracle import emap_oracle as O
+    B = 300
+    o, d = O.synthetic_rays(B)
+    near, far, ds = torch.full((B, 1), 0.05), torch.full((B, 1), 6.0), torch.ones(B, 1)
+    te = torch.rand(B, 1, generator=torch.Generator().manual_seed(3)).cuda()
+    grads = {}
+    for mode in (("forward", "dual"), ("reverse", "shared")):
+        ops.set_grad_mode(mode[0]); ops.set_backward_mode(mode[1])
+        try:
+            net, var, beta, r = build(10, True, n_samples=64, n_importance=64, up_sample_steps=4)
+            torch.manual_seed(7)
+            out = r.render(o.cuda(), d.cuda(), near.cuda(), far.cuda(), ds.cuda(), cos_anneal_ratio=1.0,
+                           flip_saturation=0.9)
+            loss = (torch.nn.functional.mse_loss(out["edge"], te) + 0.01 * out["gradient_error_near_surface"]
+                    + 0.1 * out["gradient_error"])
+            loss.backward()
+            torch.cuda.synchronize()
+            grads[mode] = (float(loss), [p.grad.clone() for p in net.parameters()])
+        finally:
+            ops.set_grad_mode("forward"); ops.set_backward_mode("dual")
+    (l0, g0), (l1, g1) = grads[("forward", "dual")], grads[("reverse", "shared")]
+    assert abs(l0 - l1) <= 1e-3 * max(1.0, abs(l0))
+    for a, b in zip(g0, g1):
+        assert maxdiff(a, b) <= 2e-2 * (float(a.abs().max()) + 1e-12)
