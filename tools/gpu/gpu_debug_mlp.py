@@ -1,12 +1,12 @@
 """GPU diagnostic (not a pytest): layer-by-layer comparison of the tcgen05 MLP kernel against the
-fp64 oracle.  Run on the B200 box:  python tests/gpu_debug_mlp.py"""
+fp64 oracle.  Run on the B200 box:  python tools/gpu/gpu_debug_mlp.py"""
 import math
 import os
 import sys
 
 import torch
 
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
 
 from emap_b200 import ops, _cabi as C  # noqa: E402

@@ -1,6 +1,6 @@
 """cta_group::2 pair mode vs the default: bit-identity of every MLP mode, then timing."""
 import sys, os, torch, ctypes
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
 from emap_b200 import ops, _cabi as C
 from tests.helpers import oracle_params

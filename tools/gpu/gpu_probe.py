@@ -1,6 +1,6 @@
 """One experiment per process (a device trap kills the CUDA context).  usage: gpu_probe.py MODE PREC P [cluster]"""
 import sys, os, torch
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
 from emap_b200 import ops, _cabi as C
 from oracle import emap_oracle as O

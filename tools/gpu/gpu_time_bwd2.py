@@ -1,5 +1,5 @@
 import sys, os, torch, ctypes
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
 from emap_b200 import ops, _cabi as C
 from tests.helpers import oracle_params

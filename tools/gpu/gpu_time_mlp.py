@@ -1,6 +1,6 @@
 """timing experiments on the MLP kernels.  usage: gpu_time_mlp.py"""
 import sys, os, torch
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
 from emap_b200 import ops, _cabi as C
 from tests.helpers import oracle_params

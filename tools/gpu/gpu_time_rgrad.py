@@ -1,11 +1,11 @@
 """K1r (reverse-mode gradient kernel) vs K1g (forward-mode): agreement + timing on 1 M points.
-usage: python tests/gpu_time_rgrad.py"""
+usage: python tools/gpu/gpu_time_rgrad.py"""
 import os
 import sys
 
 import torch
 
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
 from emap_b200 import ops, _cabi as C  # noqa: E402
 from tests.helpers import oracle_params  # noqa: E402
