@@ -1,0 +1,139 @@
+"""CPU: every C-ABI call the host shim makes is checked against the declared ctypes signature.
+
+The GPU-only code paths of emap_b200/ops.py cannot execute here, and a call with one argument too many or
+a pointer where an int belongs would only surface on the B200 box.  This test swaps the library for a
+recorder that validates each call against `_cabi.SIGNATURES` (argument count + ctypes conversion of every
+argument) and returns success without touching memory, lets CPU tensors through `_cabi.ptr`, and then
+drives the shim's entry points -- including the opt-in K1r / shared-forward-backward paths -- end to end.
+Nothing is computed: outputs are whatever torch.empty returned.  (Host-only library functions -- sizes,
+parameter counts -- are forwarded to the real library.)
+"""
+import ctypes
+
+import pytest
+import torch
+
+from emap_b200 import _cabi as C
+
+HOST_ONLY = {"emap_flat_param_count", "emap_packed_size", "emap_last_error", "emap_abi_version",
+             "emap_packed_offsets", "emap_set_option"}
+
+
+class _Recorder:
+    def __init__(self, real):
+        self.real = real
+        self.calls = []
+
+    def __getattr__(self, name):
+        if name not in C.SIGNATURES:
+            raise AttributeError(f"{name} is not declared in _cabi.SIGNATURES")
+        restype, argtypes = C.SIGNATURES[name]
+        if name in HOST_ONLY:
+            return getattr(self.real, name)
+
+        def call(*args):
+            assert len(args) == len(argtypes), f"{name}: {len(args)} arguments, signature has {len(argtypes)}"
+            for i, (a, t) in enumerate(zip(args, argtypes)):
+                try:
+                    t.from_param(a)
+                except (TypeError, ctypes.ArgumentError) as e:     # pragma: no cover - failure path
+                    raise AssertionError(f"{name}: argument {i} ({a!r}) does not convert to {t}: {e}")
+            self.calls.append(name)
+            if name == "emap_rgrad_scratch_bytes":
+                return 4 * 7 * 4 * 16 * 512 * 4                    # pretend 4 SMs
+            return 0
+        return call
+
+
+@pytest.fixture()
+def shim(monkeypatch):
+    from emap_b200 import ops
+    rec = _Recorder(C.lib())
+    monkeypatch.setattr(C, "lib", lambda: rec)
+    monkeypatch.setattr(C, "ptr", lambda t: None if t is None else (t.contiguous().data_ptr() or 1))
+    monkeypatch.setattr(C, "stream", lambda: 0)
+    monkeypatch.setattr(ops, "_rg_scratch", lambda dev: torch.empty(1 << 20, dtype=torch.uint8))
+    # library GEMMs of the backward: fp16 x fp16 -> fp32 is a CUDA feature; shapes are what matters here
+    real_mm = torch.mm
+    monkeypatch.setattr(torch, "mm", lambda a, b, out_dtype=None: real_mm(a.float(), b.float()))
+    yield ops, rec
+    ops.set_grad_mode("forward")
+    ops.set_backward_mode("dual")
+
+
+def _packed(ops, multires=10):
+    net = ops.PackedNet(multires, device="cpu")
+    net.fold(torch.zeros(net.n_params))
+    net.flat = torch.zeros(net.n_params)
+    return net
+
+
+def test_forward_entry_points(shim):
+    ops, rec = shim
+    net = _packed(ops)
+    x = torch.zeros(37, 3)
+    o, d, z = torch.zeros(5, 3), torch.zeros(5, 3), torch.zeros(5, 7)
+    ops.udf_forward(net, C.PREC_FP32X3, pts=x, want_pe=True)
+    ops.udf_forward(net, C.PREC_HALF, rays_o=o, rays_d=d, z=z)
+    for mode in ("forward", "reverse"):
+        u, g = ops.udf_forward_grad(net, C.PREC_FP32X3, pts=x, mode=mode)
+        assert u.shape == (37,) and g.shape == (37, 3)
+        ops.udf_forward_grad(net, C.PREC_FP32X3, rays_o=o, rays_d=d, z=z, mode=mode)
+    stash = ops.alloc_backward_stash(37, "cpu")
+    ops.udf_forward_grad(net, C.PREC_FP32X3, pts=x, mode="reverse", stash=stash)
+    with pytest.raises(RuntimeError):
+        ops.udf_forward_grad(net, C.PREC_FP32X3, pts=x, mode="forward", stash=stash)    # only K1r fills a stash
+    with pytest.raises(RuntimeError):
+        ops.udf_forward_grad(net, C.PREC_FP32X3, pts=x, mode="reverse", stash=ops.alloc_backward_stash(36, "cpu"))
+    ops.debug_mlp(net, C.PREC_FP32X3, 1, x)
+    ops.debug_rgrad(net, C.PREC_FP32X3, x)
+    for name in ("emap_wn_fold", "emap_udf_forward", "emap_udf_forward_grad", "emap_udf_forward_grad_rev",
+                 "emap_debug_mlp", "emap_debug_rgrad"):
+        assert name in rec.calls, name
+
+
+@pytest.mark.parametrize("shared", [False, True])
+def test_backward_entry_points(shim, shared):
+    ops, rec = shim
+    net = _packed(ops)
+    P = 24
+    x = torch.zeros(P, 3)
+    stash = ops.alloc_backward_stash(P, "cpu") if shared else None
+    flat_grad = ops.udf_backward(net, C.PREC_FP32X3, torch.zeros(P), torch.zeros(P, 3), pts=x,
+                                 flat_params=net.flat, stash=stash)
+    assert flat_grad.shape == net.flat.shape
+    assert ("emap_bwd_tangent_forward" in rec.calls) == shared
+    assert ("emap_bwd_dual_forward" in rec.calls) == (not shared)
+    for name in ("emap_bwd_top", "emap_bwd_reverse_sweep", "emap_bwd_bias_sums", "emap_bwd_weight_norm"):
+        assert name in rec.calls, name
+
+
+def test_mode_switches_validate(shim):
+    ops, _ = shim
+    with pytest.raises(ValueError):
+        ops.set_grad_mode("sideways")
+    with pytest.raises(ValueError):
+        ops.set_backward_mode("borrowed")
+    ops.set_backward_mode("shared")
+    assert not ops.shared_backward()            # needs the reverse-mode forward
+    ops.set_grad_mode("reverse")
+    assert ops.shared_backward()
+
+
+def test_ray_kernels_and_callers(shim):
+    ops, rec = shim
+    B, n, k = 6, 16, 4
+    z = torch.zeros(B, n)
+    o = d = torch.zeros(B, 3)
+    lin = torch.linspace(0, 1, n)
+    ops.coarse_z(torch.zeros(1), torch.ones(1), False, lin, torch.zeros(B), B, n)
+    sd = torch.zeros(1)
+    u = torch.linspace(0.1, 0.9, k)
+    ops.upsample_step(o, d, z, torch.zeros(B, n), None, None, u, k, sd, 64.0, 128.0, 20.0, want_inds=True,
+                      want_weights=True)
+    ops.upsample_step(o, d, z, torch.zeros(B, n), torch.zeros(B, k), torch.zeros(B, k), u, k, sd, 64.0, 128.0, 20.0)
+    ops.sample_pdf_det(z, torch.zeros(B, n - 1), k)
+    ops.render_prep(z, sd)
+    ops.null_direction(torch.zeros(5, 50, 3))
+    for name in ("emap_coarse_z", "emap_upsample_step", "emap_render_prep", "emap_null_direction"):
+        assert name in rec.calls, name
