@@ -44,6 +44,7 @@ struct Args {
   int flags;             // emap_set_option("rg_flags", bits): kFlagSplitTail
 };
 constexpr int kFlagSplitTail = 1;   // N-split of each step's last K chunk (as K1g does; A/B switch for bring-up)
+constexpr int kFlagL2Persist = 2;   // host side: launch with the sigma scratch as a persisting-L2 access window
 
 template <int NTERMS>
 struct Plan {
@@ -524,8 +525,37 @@ static int launch(const Args& a_in, size_t scratch_bytes, cudaStream_t stream) {
     EMAP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Plan<NTERMS>::total));
     attr_done = true;
   }
+  // Optional: ask the L2 to keep the sigma scratch (rewritten tile after tile) resident instead of letting
+  // the weight/stash streams evict it: persisting access-policy window over the slices in use, hit ratio
+  // scaled to the carve-out the device grants.  A/B switch -- whether it pays is a measurement (ncu dram bytes).
+  const bool persist = (a.flags & kFlagL2Persist) != 0;
+  if (persist) {
+    int dev = 0, max_persist = 0, max_window = 0;
+    EMAP_CUDA(cudaGetDevice(&dev));
+    EMAP_CUDA(cudaDeviceGetAttribute(&max_persist, cudaDevAttrMaxPersistingL2CacheSize, dev));
+    EMAP_CUDA(cudaDeviceGetAttribute(&max_window, cudaDevAttrMaxAccessPolicyWindowSize, dev));
+    size_t bytes = (size_t)grid * kSigmaFloatsPerCta * sizeof(float);
+    if (max_persist > 0 && max_window > 0) {
+      static bool limit_set = false;
+      if (!limit_set) { EMAP_CUDA(cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, (size_t)max_persist)); limit_set = true; }
+      if (bytes > (size_t)max_window) bytes = (size_t)max_window;
+      cudaStreamAttrValue v;
+      memset(&v, 0, sizeof(v));
+      v.accessPolicyWindow.base_ptr = a.scratch;
+      v.accessPolicyWindow.num_bytes = bytes;
+      v.accessPolicyWindow.hitRatio = (bytes <= (size_t)max_persist) ? 1.0f : (float)max_persist / (float)bytes;
+      v.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+      v.accessPolicyWindow.missProp = cudaAccessPropertyNormal;
+      EMAP_CUDA(cudaStreamSetAttribute(stream, cudaStreamAttributeAccessPolicyWindow, &v));
+    }
+  }
   kern<<<grid, kThreads, Plan<NTERMS>::total, stream>>>(a);
   EMAP_CUDA(cudaGetLastError());
+  if (persist) {
+    cudaStreamAttrValue v;
+    memset(&v, 0, sizeof(v));                       // num_bytes = 0 disables the window for later launches
+    EMAP_CUDA(cudaStreamSetAttribute(stream, cudaStreamAttributeAccessPolicyWindow, &v));
+  }
   return 0;
 }
 

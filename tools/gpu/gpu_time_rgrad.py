@@ -42,6 +42,10 @@ for prec, name in ((3, "fp32x3"), (1, "fp16")):
     tr1 = t(lambda: ops.udf_forward_grad(net, prec, pts=x, mode="reverse"))
     C.set_option("rg_flags", 0)
     print(f"{name}: K1r with the N-split tail (rg_flags=1): {tr1:.2f} ms", flush=True)
+    C.set_option("rg_flags", 2)
+    tr2 = t(lambda: ops.udf_forward_grad(net, prec, pts=x, mode="reverse"))
+    C.set_option("rg_flags", 0)
+    print(f"{name}: K1r with the persisting-L2 window on the sigma scratch (rg_flags=2): {tr2:.2f} ms", flush=True)
     f0 = t(lambda: ops.udf_forward(net, prec, pts=x))
     flop = 2 * 918016 * P
     print(f"{name}: K1g {tf:.2f} ms ({flop / tf / 1e9:.0f} TF/s alg)   K1r {tr:.2f} ms ({flop / tr / 1e9:.0f} TF/s alg)   "
