@@ -50,6 +50,7 @@ SIGNATURES = {
     "emap_debug_rgrad": (ctypes.c_int, [_nd, _vp, _i32, _vp, _vp, _vp, _vp, _i32, _i64, _vp, _vp, _vp,
                                         ctypes.c_size_t, _vp, _vp]),
     "emap_debug_rg_image": (ctypes.c_int, [_nd, ctypes.c_int, _vp, _vp, _vp]),
+    "emap_debug_pe_adjoint": (ctypes.c_int, [_vp, ctypes.c_int, _vp, ctypes.c_int, _vp]),
     "emap_debug_pe_col_to_ref": (ctypes.c_int, [ctypes.c_int, ctypes.c_int]),
     "emap_debug_rg_pe_ref": (ctypes.c_int, [ctypes.c_int, ctypes.c_int]),
     "emap_debug_mlp": (ctypes.c_int, [_nd, _vp, _i32, _i32, _vp, _i64, _vp, _vp, _vp, _vp]),

@@ -84,8 +84,8 @@ __device__ __forceinline__ void st_scratch8(float* p, const float (&v)[8]) {
 // J_gamma^T applied to 16 consecutive PE adjoints adj[i] <-> PE slot k = kbase + i (rg_pe_ref order,
 // common.cuh; kbase even, slots k < 1 are not PE entries): g += sum_k adj_k d gamma_k / d x.
 //   x_c: 1;   sin(f x_c): f cos(f x_c);   cos(f x_c): -f sin(f x_c),   f = 2^j   (embedder.py:26-35)
-__device__ __forceinline__ void pe_adjoint16(const float (&adj)[16], int kbase, const float (&x)[3],
-                                             int multires, float (&g)[3]) {
+__host__ __device__ __forceinline__ void pe_adjoint16(const float (&adj)[16], int kbase, const float (&x)[3],
+                                                      int multires, float (&g)[3]) {
 #pragma unroll
   for (int i = 0; i < 16; i += 2) {
     const int k = kbase + i;                    // even; warp-uniform
@@ -567,6 +567,17 @@ int run(const emap_net_desc* net, const void* packed, int precision, const float
 }  // namespace emap
 
 using namespace emap;
+
+// Test hook on HOST memory (no GPU needed): the kernel's own PE-adjoint contraction (pe_adjoint16) applied to
+// 16 adjoints of the slots kbase..kbase+15; g3 is accumulated into.
+extern "C" int emap_debug_pe_adjoint(const float* adj16, int kbase, const float* x3, int multires, float* g3) {
+  if (!adj16 || !x3 || !g3 || (kbase & 1)) return set_error("emap_debug_pe_adjoint: bad arguments (kbase must be even)");
+  float adj[16], x[3] = {x3[0], x3[1], x3[2]}, g[3] = {g3[0], g3[1], g3[2]};
+  for (int i = 0; i < 16; ++i) adj[i] = adj16[i];
+  rg::pe_adjoint16(adj, kbase, x, multires, g);
+  g3[0] = g[0]; g3[1] = g[1]; g3[2] = g[2];
+  return 0;
+}
 
 extern "C" size_t emap_rgrad_scratch_bytes(void) {
   return (size_t)sm_count() * rg::kSigmaFloatsPerCta * sizeof(float);

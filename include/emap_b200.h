@@ -229,10 +229,13 @@ int emap_debug_rgrad(const emap_net_desc* net, const void* packed, int precision
                      float* dbg_acc, void* stream);
 /* test hooks on HOST memory (no GPU needed): the un-split fp32 value image `b` (0..63) of the K1r
  * reverse stream from the HOST W_eff matrix of its layer -> out_host [rows x 64] (rows returned: 256 or
- * 64; -1 on error), layer_kc_part[3] (optional) = {layer, K chunk, hi/lo part}; and the two PE column
- * maps of the kernels (kernel column / K1r slot -> reference PE index, -1 = padding).              */
+ * 64; -1 on error), layer_kc_part[3] (optional) = {layer, K chunk, hi/lo part}; K1r's PE-adjoint
+ * contraction itself (J_gamma^T over 16 slots, the device function compiled for the host); and the two PE
+ * column maps of the kernels (kernel column / K1r slot -> reference PE index, -1 = padding).        */
 int emap_debug_rg_image(const emap_net_desc* net, int b, const float* W_host, float* out_host,
                         int32_t* layer_kc_part);
+int emap_debug_pe_adjoint(const float* adj16_host, int kbase, const float* x3_host, int multires,
+                          float* g3_host /* accumulated into */);
 int emap_debug_pe_col_to_ref(int col, int multires);
 int emap_debug_rg_pe_ref(int k, int multires);
 

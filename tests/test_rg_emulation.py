@@ -65,6 +65,40 @@ def test_slot_decoding_matches_the_image_order(multires):
     assert sorted(c for c in cols if c >= 0) == list(range(3 + 6 * multires))
 
 
+@pytest.mark.parametrize("multires", [0, 6, 10])
+def test_kernel_pe_adjoint_is_jacobian_transpose(multires):
+    """the kernel's OWN contraction routine (pe_adjoint16, compiled for the host) over the four 16-slot
+    slices equals J_gamma(x)^T applied to the adjoint vector in reference order (autograd through posenc)."""
+    L = C.lib()
+    rng = np.random.default_rng(multires)
+    pe = 3 + 6 * multires
+    for trial in range(4):
+        x = (rng.random(3) * 2 - 1).astype(np.float32)
+        adj_ref = rng.standard_normal(pe).astype(np.float32)          # adjoint per reference PE entry
+        slots = np.zeros(64, dtype=np.float32)                         # the same, laid out in K1r slot order
+        for k in range(64):
+            r = L.emap_debug_rg_pe_ref(k, multires)
+            if r >= 0:
+                slots[k] = adj_ref[r]
+        g = np.zeros(3, dtype=np.float32)
+        for sub in range(4):
+            a16 = np.ascontiguousarray(slots[16 * sub:16 * sub + 16])
+            assert L.emap_debug_pe_adjoint(a16.ctypes.data, 16 * sub, x.ctypes.data, multires, g.ctypes.data) == 0
+        # shifted window as the skip layer sees it (kbase negative / not a multiple of 16): same result
+        g2 = np.zeros(3, dtype=np.float32)
+        padded = np.concatenate([np.full(8, 7.0, np.float32), slots, np.zeros(8, np.float32)])   # slots k = -8..71
+        padded[8] = 123.0                                              # slot 0 is not a PE entry: must be ignored
+        for w in range(5):
+            a16 = np.ascontiguousarray(padded[16 * w:16 * w + 16])
+            assert L.emap_debug_pe_adjoint(a16.ctypes.data, -8 + 16 * w, x.ctypes.data, multires, g2.ctypes.data) == 0
+        xt = torch.tensor(x, dtype=torch.float64, requires_grad=True)
+        e = O.posenc(xt[None, :], multires)[0]
+        (want,) = torch.autograd.grad((e * torch.tensor(adj_ref, dtype=torch.float64)).sum(), xt)
+        scale = max(1.0, float(want.abs().max()))
+        assert np.abs(g - want.numpy()).max() <= 2e-5 * scale
+        assert np.abs(g2 - want.numpy()).max() <= 2e-5 * scale
+
+
 def _rg_matrices(p, W):
     """B_l [n_rows, 256] = un-scaled W^T operand of reverse layer l, assembled from the library's images."""
     L = C.lib()
