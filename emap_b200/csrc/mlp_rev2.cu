@@ -1,40 +1,41 @@
-// K1b stage 2: fused reverse sweep of the dual network on the tensor cores.
+// K1b stage 2, two tiles in flight per CTA ("rev2"; opt-in, emap_set_option("rev_tiles", 2)).
 //
-// Given the stash of the dual forward (emap_bwd_dual_forward: U_{l+1} = (h_{l+1} ; hdot_{l+1}), from which
-// sigma_l = 1 - exp(-100 h_{l+1}) and adot_l softplus''(a_l) = 100 hdot_{l+1} (1 - sigma_l) follow) and the
-// output-layer pull-back (emap_bwd_top: alpha_8, alphadot_8 per point), one persistent kernel walks the
-// layers 7 -> 0 per tile of 64 points x {alpha, alphadot} rows:
-//     alpha_l    = eta_{l+1} sigma_l + etadot_{l+1} adot_l softplus''(a_l)      (value row)
-//     alphadot_l = etadot_{l+1} sigma_l                                        (tangent row)
-//     [eta_l ; etadot_l] = [alpha_l ; alphadot_l] W_l                           (tcgen05.mma, W_l^T images)
-// and stashes A_l = [alpha_l ; alphadot_l] (fp16, row-major) for the weight-gradient GEMMs
-// dW_l = A_l^T U_l.  Same skeleton as mlp_tc.cu (bulk-copy weight ring, one MMA-issuing warp, 16
-// epilogue warps converting 64-column chunks in order so the next layer's MMA overlaps); single-MMA
-// fp16 arithmetic with fp32 accumulation.  Replaces the autograd reverse pass through
-// src/models/udf_model.py:90-135 (loss.backward(), runner_udf.py:167).
+// Same arithmetic, same stash formats and the same per-tile instruction sequence as mlp_rev.cu (see there for
+// the recurrences) -- outputs are bit-identical -- but every CTA works on TWO tiles X, Y of 64 points at a
+// time.  ncu on mlp_rev_kernel (profiles/r01_mlp_stalls.txt): 18 % of the warp samples are the 16 epilogue
+// warps waiting for `acc_full`, because with one tile in flight the MMAs of layer l can only start when the
+// epilogue of layer l+1 has produced their first K chunk.  Here the epilogue warps alternate
+//     X(j) , Y(j) , X(j+1) , Y(j+1) , ...
+// and while they convert Y(j) the tensor pipe runs X(j+1) (whose inputs they have just written), so neither
+// side waits for the other.  Each tile owns one 256-column TMEM accumulator (no ping-pong inside a tile: the
+// other tile fills that gap) and one 64 KiB A tile; the ring shrinks to 3 stages (224 KiB in all).  Weights
+// are streamed per (tile, layer) exactly as before -- no sharing between X and Y -- so the L2 -> SMEM traffic
+// per point is unchanged.  Protocol modelled in tests/test_rev2_protocol.py.
 #include "common.cuh"
 #include "host.h"
 
 namespace emap {
 
-namespace rev {
+namespace rev2 {
 
 constexpr int kEpiWarps = 16;
 constexpr int kProducerWarp = kEpiWarps;
 constexpr int kMmaWarp = kEpiWarps + 1;
 constexpr int kThreads = (kEpiWarps + 2) * 32;
 constexpr int kChunkBytes = 16384;
-constexpr int kStages = 4;             // ring stages of 32 KiB: one [256 x 64] W^T operand (both N halves)
+constexpr int kStages = 3;             // ring stages of 32 KiB: one [256 x 64] W^T operand (both N halves)
+constexpr int kTiles = 2;              // tiles in flight per CTA
 constexpr int kRingStageBytes = 2 * kStageBytes;
 constexpr int kRevLayers = 7;          // MMA layers l = 7..1
 constexpr int kRevParts = kRevLayers * 4;
 
 struct Smem {
-  static constexpr int a = 0;                                   // [4 chunks][128 x 64] fp16 SW128
-  static constexpr int ring = a + 4 * kChunkBytes;
+  static constexpr int a = 0;                                   // [2 tiles][4 chunks][128 x 64] fp16 SW128
+  static constexpr int ring = a + kTiles * 4 * kChunkBytes;
   static constexpr int bars = ring + kStages * kRingStageBytes;
   static constexpr int total = bars + 256 + 1024;
 };
+static_assert(Smem::total <= 232448, "shared memory plan exceeds 227 KiB");
 
 struct Args {
   const uint8_t* packed;
@@ -50,7 +51,7 @@ __device__ __forceinline__ uint32_t pack2h(float a, float b) {
   return *reinterpret_cast<uint32_t*>(&h);
 }
 
-__global__ void __launch_bounds__(kThreads, 1) mlp_rev_kernel(const Args args) {
+__global__ void __launch_bounds__(kThreads, 1) mlp_rev2_kernel(const Args args) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   const PackedHeader* hdr = reinterpret_cast<const PackedHeader*>(args.packed);
@@ -58,17 +59,17 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_rev_kernel(const Args args) {
   const int out3 = (int)hdr->out_dim[kSkipLayer - 1];          // 256 - pe: valid columns of alpha_3
 
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Smem::bars);
-  uint64_t* full = bars;            // [8]
-  uint64_t* empty = bars + 8;       // [8]
-  uint64_t* a_ready = bars + 16;    // [4]
-  uint64_t* acc_full = bars + 20;   // [2]
-  uint64_t* acc_empty = bars + 22;  // [2]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 25);
+  uint64_t* full = bars;            // [kStages]
+  uint64_t* empty = bars + 4;       // [kStages]
+  uint64_t* a_ready = bars + 8;     // [2 tiles][4 chunks]
+  uint64_t* acc_full = bars + 16;   // [2 tiles]
+  uint64_t* acc_empty = bars + 18;  // [2 tiles]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 20);
 
   if (warp == kProducerWarp && lane == 0) {
     for (int s = 0; s < kStages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
-    for (int c = 0; c < 4; ++c) mbar_init(&a_ready[c], kEpiWarps);
-    for (int b = 0; b < 2; ++b) { mbar_init(&acc_full[b], 1); mbar_init(&acc_empty[b], kEpiWarps); }
+    for (int c = 0; c < kTiles * 4; ++c) mbar_init(&a_ready[c], kEpiWarps);
+    for (int b = 0; b < kTiles; ++b) { mbar_init(&acc_full[b], 1); mbar_init(&acc_empty[b], kEpiWarps); }
     fence_barrier_init();
   }
   if (warp == kMmaWarp) { tmem_alloc(tmem_slot, 512); tmem_relinquish(); }
@@ -85,14 +86,19 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_rev_kernel(const Args args) {
     uint32_t stage = 0, round = 0;
     for (int iter = 0; iter < args.iters; ++iter) {
 #pragma unroll 1
-      for (int i = 0; i < kRevParts; ++i) {
-        if (round > 0) mbar_wait(&empty[stage], (round - 1) & 1, 100 + (int)stage, i);
-        if (elect_one()) {
-          mbar_arrive_expect_tx(&full[stage], kRingStageBytes);
-          bulk_g2s(ring + stage * kRingStageBytes, img + (size_t)i * kRingStageBytes, kRingStageBytes, &full[stage]);
+      for (int jt = 0; jt < kRevLayers * kTiles; ++jt) {
+        const int j = jt >> 1;                       // layer step; tile = jt & 1 consumes the same four images
+#pragma unroll 1
+        for (int kc = 0; kc < 4; ++kc) {
+          const int i = j * 4 + kc;
+          if (round > 0) mbar_wait(&empty[stage], (round - 1) & 1, 100 + (int)stage, jt * 4 + kc);
+          if (elect_one()) {
+            mbar_arrive_expect_tx(&full[stage], kRingStageBytes);
+            bulk_g2s(ring + stage * kRingStageBytes, img + (size_t)i * kRingStageBytes, kRingStageBytes, &full[stage]);
+          }
+          __syncwarp();
+          if (++stage == (uint32_t)kStages) { stage = 0; ++round; }
         }
-        __syncwarp();
-        if (++stage == (uint32_t)kStages) { stage = 0; ++round; }
       }
     }
   } else if (warp == kMmaWarp) {
@@ -102,19 +108,21 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_rev_kernel(const Args args) {
     uint32_t stage = 0, round = 0;
     for (int iter = 0; iter < args.iters; ++iter) {
 #pragma unroll
-      for (int j = 0; j < kRevLayers; ++j) {
-        const int buf = j & 1;
+      for (int jt = 0; jt < kRevLayers * kTiles; ++jt) {
+        const int j = jt >> 1, t = jt & 1;             // X(j), Y(j), X(j+1), ...
+        const int buf = t;                             // one accumulator per tile
         {
-          const uint32_t started = (uint32_t)iter * (buf ? 3u : 4u) + (uint32_t)(j >> 1);
+          // the epilogue of this tile's previous layer (or of the previous tile pair's last) has drained it
+          const uint32_t started = (uint32_t)iter * 7u + (uint32_t)j;
           if (started > 0) mbar_wait(&acc_empty[buf], (started - 1) & 1, 200 + buf, j);
         }
         const uint32_t d = tmem_base + (uint32_t)buf * 256u;
 #pragma unroll
         for (int kc = 0; kc < 4; ++kc) {
-          mbar_wait(&a_ready[kc], ((uint32_t)iter * 7u + (uint32_t)j) & 1, 300 + kc, j);
-          mbar_wait(&full[stage], round & 1, 400 + (int)stage, j * 4 + kc);
+          mbar_wait(&a_ready[t * 4 + kc], ((uint32_t)iter * 7u + (uint32_t)j) & 1, 300 + t * 4 + kc, j);
+          mbar_wait(&full[stage], round & 1, 400 + (int)stage, jt * 4 + kc);
           tc_fence_after();
-          const uint64_t adesc = make_sw128_kmajor_desc(a_addr + kc * kChunkBytes);
+          const uint64_t adesc = make_sw128_kmajor_desc(a_addr + (t * 4 + kc) * kChunkBytes);
           const uint64_t bdesc = make_sw128_kmajor_desc(ring_addr + stage * kRingStageBytes);
           if (elect_one()) {
 #pragma unroll
@@ -135,25 +143,40 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_rev_kernel(const Args args) {
     const int row = q * 32 + lane;
     const int t2 = lane & 1;                                  // 0: alpha (value) row, 1: alphadot row
     const uint32_t lane_taddr = tmem_base + ((uint32_t)(q * 32) << 16);
-    uint8_t* A = smem + Smem::a;
+    uint8_t* A_base = smem + Smem::a;
     const float* w8 = reinterpret_cast<const float*>(args.packed + hdr->weff_layer_off[8]);
     const size_t P = (size_t)args.P;
 
     for (int iter = 0; iter < args.iters; ++iter) {
-      const long long tile = (long long)blockIdx.x + (long long)iter * gridDim.x;
-      const long long pt = tile * 64 + q * 16 + (lane >> 1);
-      const bool ok = (tile < args.num_tiles) && (pt < args.P);
-      const size_t pc = ok ? (size_t)pt : 0;
-      const size_t rowg = (t2 ? P : 0) + pc;
-      // cotangents of a8 / adot8 for this point
-      const float c_v = ok ? args.coef[pc] : 0.f;
-      const float c_t = ok ? args.coef[P + pc] : 0.f;
+      // the two tiles of this iteration: X = 2*pair, Y = 2*pair + 1
+      const long long pair = (long long)blockIdx.x + (long long)iter * gridDim.x;
+      bool ok_[kTiles];
+      size_t rowg_[kTiles];
+      float cv_[kTiles], ct_[kTiles];
+#pragma unroll
+      for (int t = 0; t < kTiles; ++t) {
+        const long long tile = pair * kTiles + t;
+        const long long pt = tile * 64 + q * 16 + (lane >> 1);
+        ok_[t] = (tile < args.num_tiles) && (pt < args.P);
+        const size_t pc = ok_[t] ? (size_t)pt : 0;
+        rowg_[t] = (t2 ? P : 0) + pc;
+        // cotangents of a8 / adot8 for this point
+        cv_[t] = ok_[t] ? args.coef[pc] : 0.f;
+        ct_[t] = ok_[t] ? args.coef[P + pc] : 0.f;
+      }
 
-      // stage j = -1 builds A_7 from the output-layer pull-back; stages j = 0..6 from the accumulators
+      // stage j = -1 builds A_7 from the output-layer pull-back; stages j = 0..6 from the accumulators;
+      // X and Y alternate inside every stage (the t loop is unrolled: per-tile state stays in registers)
 #pragma unroll 1
       for (int j = -1; j < kRevLayers; ++j) {
+#pragma unroll
+       for (int t = 0; t < kTiles; ++t) {
+        const bool ok = ok_[t];
+        const size_t rowg = rowg_[t];
+        const float c_v = cv_[t], c_t = ct_[t];
         const int lt = 6 - j;                   // layer whose A_l = [alpha ; alphadot] this stage produces
-        const int buf = j & 1;
+        const int buf = t;                      // one accumulator and one A tile per tile slot
+        uint8_t* A = A_base + t * 4 * kChunkBytes;
         // the stash reads of this stage do not depend on the MMA: issue them before waiting for it
         uint32_t uw_all[4][8];
         {
@@ -162,7 +185,7 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_rev_kernel(const Args args) {
           for (int c4 = 0; c4 < 4; ++c4) ldg256(u_pre + c4 * 64, uw_all[c4]);
         }
         if (j >= 0) {
-          mbar_wait(&acc_full[buf], ((uint32_t)iter * (buf ? 3u : 4u) + (uint32_t)(j >> 1)) & 1, 500 + buf, j);
+          mbar_wait(&acc_full[buf], ((uint32_t)iter * 7u + (uint32_t)j) & 1, 500 + buf, j);
           tc_fence_after();
         }
         // own row of U_{lt+1}: h (value lane) or hdot (tangent lane); the partner's comes by shuffle
@@ -241,7 +264,7 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_rev_kernel(const Args args) {
           if (lt >= 1) {
             fence_proxy_async_smem();
             __syncwarp();
-            if (lane == 0) mbar_arrive(&a_ready[chunk]);
+            if (lane == 0) mbar_arrive(&a_ready[t * 4 + chunk]);
           }
         }
         if (j >= 0) {
@@ -249,6 +272,7 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_rev_kernel(const Args args) {
           __syncwarp();
           if (lane == 0) mbar_arrive(&acc_empty[buf]);
         }
+       }
       }
     }
   }
@@ -258,39 +282,38 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_rev_kernel(const Args args) {
   if (warp == kMmaWarp) tmem_dealloc(tmem_base, 512);
 }
 
-}  // namespace rev
-}  // namespace emap
-
-namespace emap {
-namespace rev2 {   // mlp_rev2.cu: the same sweep with two tiles in flight per CTA (opt-in)
-bool enabled();
-int launch(const emap_net_desc* net, const void* packed, const float* coef, const void* st_u, void* st_a,
-           int64_t P, void* stream);
 }  // namespace rev2
 }  // namespace emap
 
-using namespace emap;
+namespace emap {
+namespace rev2 {
+static int g_tiles = 1;   // emap_set_option("rev_tiles", 1|2)
+int set_tiles(int v) {
+  if (v != 1 && v != 2) return set_error("rev_tiles must be 1 (default kernel) or 2 (two tiles in flight)");
+  g_tiles = v;
+  return 0;
+}
+bool enabled() { return g_tiles == 2; }
 
-extern "C" int emap_bwd_reverse_sweep(const emap_net_desc* net, const void* packed, const float* coef,
-                                      const void* st_u, void* st_a, int64_t P, void* stream) {
-  if (check_net(net)) return 1;
-  if (net->elem_type != 0) return set_error("emap_bwd_reverse_sweep: fp16 operand images required");
-  if (!packed || !coef || !st_u || !st_a || P <= 0) return set_error("emap_bwd_reverse_sweep: bad arguments");
-  if (rev2::enabled()) return rev2::launch(net, packed, coef, st_u, st_a, P, stream);
-  rev::Args a;
+int launch(const emap_net_desc* net, const void* packed, const float* coef, const void* st_u, void* st_a,
+           int64_t P, void* stream) {
+  Args a;
   a.packed = (const uint8_t*)packed; a.coef = coef; a.st_u = (const __half*)st_u;
   a.st_a = (__half*)st_a; a.P = P;
   const long long tiles = (P + 63) / 64;
+  const long long pairs = (tiles + kTiles - 1) / kTiles;
   a.num_tiles = (int)tiles;
   int grid = sm_count();
-  if (tiles < grid) grid = (int)tiles;
-  a.iters = (int)((tiles + grid - 1) / grid);
+  if (pairs < grid) grid = (int)pairs;
+  a.iters = (int)((pairs + grid - 1) / grid);
   static bool attr_done = false;
   if (!attr_done) {
-    EMAP_CUDA(cudaFuncSetAttribute(rev::mlp_rev_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, rev::Smem::total));
+    EMAP_CUDA(cudaFuncSetAttribute(mlp_rev2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, Smem::total));
     attr_done = true;
   }
-  rev::mlp_rev_kernel<<<grid, rev::kThreads, rev::Smem::total, (cudaStream_t)stream>>>(a);
+  mlp_rev2_kernel<<<grid, kThreads, Smem::total, (cudaStream_t)stream>>>(a);
   EMAP_CUDA(cudaGetLastError());
   return 0;
 }
+}  // namespace rev2
+}  // namespace emap

@@ -32,6 +32,7 @@
 namespace emap {
 
 namespace rg { int set_flags(int v); }   // mlp_rg.cu
+namespace rev2 { int set_tiles(int v); } // mlp_rev2.cu
 
 template <int NTERMS, int MODE, typename T, int CL>
 __global__ void __launch_bounds__(kThreads, 1) mlp_kernel(const MlpArgs args) {
@@ -746,6 +747,7 @@ extern "C" int emap_set_option(const char* name, int value) {
   if (!strcmp(name, "cluster")) return set_cluster_width(value);
   if (!strcmp(name, "dbg")) { emap::g_dbg_flags = value; return 0; }
   if (!strcmp(name, "rg_flags")) return emap::rg::set_flags(value);   // K1r experiment switches (mlp_rg.cu)
+  if (!strcmp(name, "rev_tiles")) return emap::rev2::set_tiles(value); // reverse sweep: tiles in flight per CTA
   return set_error("unknown option '%s'", name);
 }
 
