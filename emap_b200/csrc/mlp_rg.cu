@@ -40,7 +40,6 @@ constexpr int kSigmaFloatsPerCta = kSigmaLayers * 4 * 16 * 512;   // [layer][chu
 struct Args {
   MlpArgs m;
   float* scratch;        // [grid][kSigmaFloatsPerCta]
-  uint32_t rg_off;       // byte offset of the reverse image stream inside the packed buffer
   int flags;             // emap_set_option("rg_flags", bits): kFlagSplitTail
 };
 constexpr int kFlagSplitTail = 1;   // N-split of each step's last K chunk (as K1g does; A/B switch for bring-up)
@@ -157,7 +156,7 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_rgrad_kernel(const Args args)
     // then the reverse stream (rg images, same order); one bulk copy per part, uniform control flow, issued
     // by one elected lane.
     const uint8_t* img_f = m.packed + hdr->images_off;
-    const uint8_t* img_r = m.packed + args.rg_off;
+    const uint8_t* img_r = m.packed + hdr->reserved[3];      // reverse image stream (pack.cu: build_layout)
     uint8_t* ring = smem + P::ring;
     uint32_t stage = 0, round = 0;
     for (int iter = 0; iter < m.iters; ++iter) {
@@ -616,8 +615,6 @@ int emap::rg::run(const emap_net_desc* net, const void* packed, int precision, c
     if (!rays_o || !rays_d || !z) return set_error("give either pts or (rays_o, rays_d, z)");
     if (n_per_ray <= 0 || P % n_per_ray) return set_error("P must be a multiple of n_per_ray");
   }
-  PackedHeader h; std::vector<RingItem> t1, t3;
-  build_layout(*net, h, t1, t3);
   rg::Args a;
   memset(&a, 0, sizeof(a));
   a.m.packed = (const uint8_t*)packed; a.m.pts = pts; a.m.rays_o = rays_o; a.m.rays_d = rays_d; a.m.z = z;
@@ -625,7 +622,6 @@ int emap::rg::run(const emap_net_desc* net, const void* packed, int precision, c
   a.m.dbg_acc = dbg_acc;
   a.m.st_u0 = (__half*)st_u0; a.m.st_u = (__half*)st_u;
   a.scratch = (float*)scratch;
-  a.rg_off = h.reserved[3];
   cudaStream_t st = (cudaStream_t)stream;
   if (precision == EMAP_PREC_FP32X3) {
     if (net->elem_type == 0) return rg::launch<3, __half>(a, scratch_bytes, st);
