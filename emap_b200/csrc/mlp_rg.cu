@@ -12,8 +12,8 @@
 //     alpha_7 = w_8 . sigma_7,      alpha_{l-1} = (alpha_l W_l) . sigma_{l-1},   l = 7..1,
 //     d udf / d x = udf'(a_8) J_gamma(x)^T [ alpha_0 W_0  +  PE columns of alpha_4 W_4 / sqrt2 ]
 // on the same tile with the W_l^T operand images (3 F): 6 F executed, half the epilogue conversions.
-// sigma (7 stashed layers x 256 x fp32 = 7 KiB per point) does not fit on chip; every CTA owns a fixed
-// 896 KiB scratch slice in global memory that it rewrites tile after tile -- thread-private addresses (each
+// sigma (7 stashed layers x 256 x 16-bit fixed point = 3.5 KiB per point) does not fit on chip; every CTA
+// owns a fixed 448 KiB scratch slice in global memory that it rewrites tile after tile -- thread-private addresses (each
 // thread reads back exactly what it wrote), last written = first read, so the slice lives in the
 // 126 MB L2 and DRAM sees little of it.
 //
@@ -35,11 +35,16 @@ constexpr uint32_t kUsesPerBuf = 8;               // accumulator uses per tile a
 constexpr uint32_t kAPerTile = 15;                // completions of a_ready[0..3] per tile (steps 0..14)
 constexpr float kAdjScale = 16.f;                 // power of two (headroom: |alpha| < 4095)
 constexpr int kSigmaLayers = 7;                   // sigma_0..sigma_6 (sigma_7 is consumed in registers)
-constexpr int kSigmaFloatsPerCta = kSigmaLayers * 4 * 16 * 512;   // [layer][chunk][warp][2 x 32 lanes x 8] = 896 KiB
+// sigma in [0,1] is stashed as 16-bit FIXED point (round(sigma * 65535)): what matters for the gradient is
+// its absolute error (2^-17), not its relative one -- modelled in tests/test_rg_emulation.py: 1e-5 on the
+// gradient against 5e-6 with fp32 sigma and 1.7e-4 with fp16 sigma.  Half the L2 traffic of an fp32 stash,
+// and 148 slices (66 MB) fit the 126 MB L2 together with the weights.
+constexpr float kSigmaQ = 65535.f;
+constexpr int kSigmaWordsPerCta = kSigmaLayers * 4 * 16 * 256;   // [layer][chunk][warp][32 lanes x 8 words] = 448 KiB
 
 struct Args {
   MlpArgs m;
-  float* scratch;        // [grid][kSigmaFloatsPerCta]
+  uint32_t* scratch;     // [grid][kSigmaWordsPerCta]
   int flags;             // emap_set_option("rg_flags", bits): kFlagSplitTail
 };
 constexpr int kFlagSplitTail = 1;   // N-split of each step's last K chunk (as K1g does; A/B switch for bring-up)
@@ -63,21 +68,21 @@ __device__ __forceinline__ constexpr uint32_t step_bytes(int s) {
 }
 
 // sigma scratch: plain (coherent) 256-bit accesses -- the data is rewritten by this kernel, so the
-// read-only path of ldg256 must not be used.
-__device__ __forceinline__ void ld_scratch8(const float* p, float (&v)[8]) {
+// read-only path of ldg256 must not be used.  16 sigmas of one thread = 8 words (column 2i in the low half).
+__device__ __forceinline__ void ld_sigma16(const uint32_t* p, float (&v)[16]) {
   uint32_t u[8];
   asm volatile("ld.global.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
                : "=r"(u[0]), "=r"(u[1]), "=r"(u[2]), "=r"(u[3]), "=r"(u[4]), "=r"(u[5]), "=r"(u[6]), "=r"(u[7])
                : "l"(p)
                : "memory");
 #pragma unroll
-  for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(u[i]);
+  for (int i = 0; i < 8; ++i) {          // kept as integers-in-float: the 1/65535 is folded into the caller's scale
+    v[2 * i] = (float)(u[i] & 0xffffu);
+    v[2 * i + 1] = (float)(u[i] >> 16);
+  }
 }
-__device__ __forceinline__ void st_scratch8(float* p, const float (&v)[8]) {
-  uint32_t u[8];
-#pragma unroll
-  for (int i = 0; i < 8; ++i) u[i] = __float_as_uint(v[i]);
-  stg256(p, u);
+__device__ __forceinline__ uint32_t pack_sigma2(float a, float b) {
+  return __float2uint_rn(a * kSigmaQ) | (__float2uint_rn(b * kSigmaQ) << 16);
 }
 
 // J_gamma^T applied to 16 consecutive PE adjoints adj[i] <-> PE slot k = kbase + i (rg_pe_ref order,
@@ -293,9 +298,9 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_rgrad_kernel(const Args args)
     const float b8 = bias100[8 * kHidden];
     const float* w8 = reinterpret_cast<const float*>(m.packed + hdr->weff_layer_off[8]);
     const int out3 = (int)hdr->out_dim[kSkipLayer - 1];
-    // this thread's sigma words (l = 0..6): ((l*4 + chunk)*16 + warp)*512 + g*256 + lane*8
-    float* sg_base = args.scratch + (size_t)blockIdx.x * kSigmaFloatsPerCta + (size_t)warp * 512 + lane * 8;
-    auto sg_ptr = [&](int l, int chunk) -> float* { return sg_base + (size_t)(l * 4 + chunk) * 8192; };
+    // this thread's sigma words (l = 0..6): ((l*4 + chunk)*16 + warp)*256 + lane*8
+    uint32_t* sg_base = args.scratch + (size_t)blockIdx.x * kSigmaWordsPerCta + (size_t)warp * 256 + lane * 8;
+    auto sg_ptr = [&](int l, int chunk) -> uint32_t* { return sg_base + (size_t)(l * 4 + chunk) * 4096; };
     const float gz[3] = {0.f, 0.f, 0.f};
 
     for (int iter = 0; iter < m.iters; ++iter) {
@@ -341,7 +346,8 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_rgrad_kernel(const Args args)
             for (int k = 0; k < 16; ++k)
               m.dbg_acc[((size_t)l * 128 + row) * 256 + col0 + k] = __uint_as_float(r[k]) * kInvWeightScale;
           }
-          float* sgp = sg_ptr(top ? 0 : l, chunk);
+          uint32_t* sgp = sg_ptr(top ? 0 : l, chunk);
+          uint32_t sw[8];                     // sigma_l of this thread's 16 columns, 16-bit fixed point
           uint32_t pu[8];                     // h_{l+1} of this thread's 16 columns as fp16 (training stash)
 #pragma unroll
           for (int g = 0; g < 2; ++g) {
@@ -355,7 +361,8 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_rgrad_kernel(const Args args)
             for (int j = 0; j < 4; ++j) pu[g * 4 + j] = Elem<__half>::pack2(h[2 * j], h[2 * j + 1]);
             if (!top) {
               store_group<NTERMS, T>(dst_hi, dst_lo, row, sub * 2 + g, h);
-              st_scratch8(sgp + g * 256, sg);
+#pragma unroll
+              for (int j = 0; j < 4; ++j) sw[g * 4 + j] = pack_sigma2(sg[2 * j], sg[2 * j + 1]);
             } else {
               // a_8 += w_8 . h_8;  unsigned seed of the sweep: alpha_7 = w_8 . sigma_7 (x 2^4)
               const float4 wA = __ldg(reinterpret_cast<const float4*>(w8 + col0 + g * 8));
@@ -370,6 +377,7 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_rgrad_kernel(const Args args)
           fence_proxy_async_smem();
           __syncwarp();
           if (lane == 0) mbar_arrive(&a_ready[chunk]);
+          if (!top) stg256(sgp, sw);          // after the hand-off: off the MMA's critical path
           // training: value rows [0,P) of the backward's stash U_{l+1} (emap_bwd_tangent_forward adds the
           // tangent rows later) -- after the hand-off, off the MMA's critical path
           if (m.st_u && ok) stg256(m.st_u + (size_t)l * 2 * (size_t)m.P * 256 + (size_t)pt * 256 + col0, pu);
@@ -399,14 +407,8 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_rgrad_kernel(const Args args)
         const int buf = s & 1;
         // sigma of the current chunk; chunk 0 is fetched before the accumulator wait, chunk c+1 as soon as
         // chunk c's values are consumed (its L2 latency then overlaps the conversions and stores of chunk c)
-        float sgc[16];
-        auto fetch_sigma = [&](int chunk) {
-          const float* sgp = sg_ptr(l - 1, chunk);
-          float t0[8], t1[8];
-          ld_scratch8(sgp, t0); ld_scratch8(sgp + 256, t1);
-#pragma unroll
-          for (int j = 0; j < 8; ++j) { sgc[j] = t0[j]; sgc[8 + j] = t1[j]; }
-        };
+        float sgc[16];                          // 65535 * sigma
+        auto fetch_sigma = [&](int chunk) { ld_sigma16(sg_ptr(l - 1, chunk), sgc); };
         fetch_sigma(0);
         const uint32_t acc_par = ((uint32_t)iter * kUsesPerBuf + (uint32_t)(s >> 1)) & 1;
         mbar_wait(&acc_full[buf * 2], acc_par, 530 + buf, s);
@@ -425,7 +427,7 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_rgrad_kernel(const Args args)
           }
           float v[16];
 #pragma unroll
-          for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(r[j]) * kInvWeightScale * sgc[j];
+          for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(r[j]) * (kInvWeightScale / kSigmaQ) * sgc[j];
           if (chunk < 3) fetch_sigma(chunk + 1);
           if (chunk == 3 && l == kSkipLayer) {
             // columns n >= out3 of alpha_4 W_4 are the adjoint of the skip input's PE part (slot
@@ -515,9 +517,9 @@ static int launch(const Args& a_in, size_t scratch_bytes, cudaStream_t stream) {
   int grid = sm_count();
   if (tiles < grid) grid = (int)tiles;
   a.m.iters = (int)((tiles + grid - 1) / grid);
-  if (scratch_bytes < (size_t)grid * kSigmaFloatsPerCta * sizeof(float))
+  if (scratch_bytes < (size_t)grid * kSigmaWordsPerCta * sizeof(uint32_t))
     return set_error("emap_udf_forward_grad_rev: scratch too small (%zu bytes, need %zu)", scratch_bytes,
-                     (size_t)grid * kSigmaFloatsPerCta * sizeof(float));
+                     (size_t)grid * kSigmaWordsPerCta * sizeof(uint32_t));
   auto kern = mlp_rgrad_kernel<NTERMS, T>;
   static bool attr_done = false;   // per template instantiation
   if (!attr_done) {
@@ -533,7 +535,7 @@ static int launch(const Args& a_in, size_t scratch_bytes, cudaStream_t stream) {
     EMAP_CUDA(cudaGetDevice(&dev));
     EMAP_CUDA(cudaDeviceGetAttribute(&max_persist, cudaDevAttrMaxPersistingL2CacheSize, dev));
     EMAP_CUDA(cudaDeviceGetAttribute(&max_window, cudaDevAttrMaxAccessPolicyWindowSize, dev));
-    size_t bytes = (size_t)grid * kSigmaFloatsPerCta * sizeof(float);
+    size_t bytes = (size_t)grid * kSigmaWordsPerCta * sizeof(uint32_t);
     if (max_persist > 0 && max_window > 0) {
       static bool limit_set = false;
       if (!limit_set) { EMAP_CUDA(cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, (size_t)max_persist)); limit_set = true; }
@@ -579,7 +581,7 @@ extern "C" int emap_debug_pe_adjoint(const float* adj16, int kbase, const float*
 }
 
 extern "C" size_t emap_rgrad_scratch_bytes(void) {
-  return (size_t)sm_count() * rg::kSigmaFloatsPerCta * sizeof(float);
+  return (size_t)sm_count() * rg::kSigmaWordsPerCta * sizeof(uint32_t);
 }
 
 extern "C" int emap_udf_forward_grad_rev(const emap_net_desc* net, const void* packed, int precision,
@@ -621,7 +623,7 @@ int emap::rg::run(const emap_net_desc* net, const void* packed, int precision, c
   a.m.n_per_ray = n_per_ray; a.m.P = P; a.m.udf_out = udf_out; a.m.grad_out = grad_out;
   a.m.dbg_acc = dbg_acc;
   a.m.st_u0 = (__half*)st_u0; a.m.st_u = (__half*)st_u;
-  a.scratch = (float*)scratch;
+  a.scratch = (uint32_t*)scratch;
   cudaStream_t st = (cudaStream_t)stream;
   if (precision == EMAP_PREC_FP32X3) {
     if (net->elem_type == 0) return rg::launch<3, __half>(a, scratch_bytes, st);

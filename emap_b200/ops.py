@@ -115,7 +115,7 @@ def get_grad_mode() -> str:
 
 
 def _rg_scratch(dev: torch.device) -> torch.Tensor:
-    """K1r's sigma scratch (896 KiB per SM), one per device; kernels on one stream reuse it in order."""
+    """K1r's sigma scratch (448 KiB per SM), one per device; kernels on one stream reuse it in order."""
     key = (dev.type, dev.index if dev.index is not None else torch.cuda.current_device())
     buf = _RG_SCRATCH.get(key)
     if buf is None:

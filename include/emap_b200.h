@@ -71,7 +71,7 @@ int emap_udf_forward_grad(const emap_net_desc* net, const void* packed, int prec
 /* ---- K1r: the same result as K1g by REVERSE mode (value-only forward that keeps softplus' of every
  * layer, then the adjoint sweep with the W^T operand images): 6 F executed per point instead of 12 F.
  * replaces: the same reference lines as emap_udf_forward_grad.  `scratch` = emap_rgrad_scratch_bytes()
- * bytes of device memory (896 KiB per SM, rewritten tile after tile -> L2-resident), reusable across
+ * bytes of device memory (448 KiB per SM, rewritten tile after tile -> L2-resident), reusable across
  * calls on one stream.  Selected by the host shim with EMAP_GRAD_MODE=reverse / ops.set_grad_mode().  */
 size_t emap_rgrad_scratch_bytes(void);
 /* st_u0 / st_u (both or neither; training only): the backward's stashes (see emap_bwd_dual_forward) --

@@ -144,7 +144,8 @@ def _mm(A, Bt, split, a_scale=1.0):
 
 def _emulate(p, x, split=False, adj_scale=16.0, steps=None):
     """forward + adjoint sweep exactly as mlp_rgrad_kernel structures it (float64; split=True models the
-    fp16 hi/lo operands of the fp32x3 mode, fp32 activations / sigma / adjoints between the layers)."""
+    fp16 hi/lo operands of the fp32x3 mode, fp32 activations / adjoints between the layers and the 16-bit
+    fixed-point sigma stash)."""
     mr = p.multires
     pe = 3 + 6 * mr
     out3 = 256 - pe
@@ -168,8 +169,8 @@ def _emulate(p, x, split=False, adj_scale=16.0, steps=None):
         s = 1.0 / (1.0 + np.exp(-t))
         if a.shape[1] < 256:                       # layer 3: padded accumulator columns (bias 0 -> sigma 0.5)
             s = np.concatenate([s, np.full((a.shape[0], 256 - a.shape[1]), 0.5)], axis=1)
-        if split:
-            h, s = h.astype(np.float32).astype(np.float64), s.astype(np.float32).astype(np.float64)
+        if split:                                  # fp32 activations; sigma stashed as 16-bit fixed point
+            h, s = h.astype(np.float32).astype(np.float64), np.round(s * 65535.0) / 65535.0
         sig.append(s)
     # output layer: fp32 dot product in layer 7's epilogue (no MMA); the sweep starts from the UNSIGNED
     # seed w_8 . sigma_7 and udf'(a_8) multiplies the finished gradient
@@ -233,8 +234,9 @@ def test_reverse_sweep_emulation_matches_autograd(multires, pert):
 
 
 def test_split_fp16_numerics_budget():
-    """fp32x3 arithmetic of K1r (fp16 hi/lo operands, adjoints scaled by 2^4 in the A tile), modelled on
-    the CPU: the gradient stays within the tolerance the GPU parity tests use for K1g (5e-5 abs)."""
+    """fp32x3 arithmetic of K1r (fp16 hi/lo operands, adjoints scaled by 2^4 in the A tile, sigma stashed as
+    round(sigma * 65535)), modelled on the CPU: the gradient stays within the tolerance the GPU parity tests
+    use for K1g (5e-5 abs) -- measured here: 1e-5 (5e-6 with an fp32 sigma stash, 1.7e-4 with fp16)."""
     p64 = oracle_params(True, 10).to(torch.float64)
     torch.manual_seed(5)
     x = (torch.rand(128, 3, dtype=torch.float64) * 2 - 1) * 0.9
@@ -242,7 +244,7 @@ def test_split_fp16_numerics_budget():
     ref_g = O.udf_gradient(p64, x.float().double(), create_graph=False).detach().numpy()
     udf, g = _emulate(oracle_params(True, 10), x.float(), split=True)
     assert np.abs(udf - ref_u).max() < 2e-5
-    assert np.abs(g - ref_g).max() < 5e-5
+    assert np.abs(g - ref_g).max() < 2.5e-5
     # without the 2^4 scale the lo parts of small adjoints go subnormal: must not be better than with it
     _, g1 = _emulate(oracle_params(True, 10), x.float(), split=True, adj_scale=1.0)
     print("grad err scaled", np.abs(g - ref_g).max(), "unscaled", np.abs(g1 - ref_g).max())
