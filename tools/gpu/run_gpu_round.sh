@@ -10,6 +10,7 @@ timeout 300 python bench.py > $O/bench_train_fp32.json 2> $O/bench_train.err; ec
 timeout 200 python bench.py --mode infer --no-cpu-baseline > $O/bench_infer_fp32.json 2> $O/bench_infer.err; echo "bench infer rc=$?"; cut -c1-200 $O/bench_infer_fp32.json
 timeout 200 python bench.py --mode infer --precision fp16 --no-cpu-baseline > $O/bench_infer_fp16.json 2>/dev/null
 timeout 200 python bench.py --precision fp16 --no-cpu-baseline > $O/bench_train_fp16.json 2>/dev/null
+for wl in c2 c3 c5; do timeout 300 python bench.py --workload $wl --no-cpu-baseline --steps 10 > $O/bench_$wl.json 2> $O/bench_$wl.err; echo "bench $wl rc=$?"; cut -c1-200 $O/bench_$wl.json; done
 timeout 200 python bench.py --impl reference --steps 2 --warmup 1 > $O/bench_reference.json 2>/dev/null; echo "ref rc=$?"; cut -c1-200 $O/bench_reference.json
 timeout 120 python tools/gpu/gpu_time_mlp.py > $O/time_mlp.txt 2>&1; echo "time_mlp rc=$?"
 timeout 120 python tools/gpu/gpu_time_bwd.py > $O/time_bwd.txt 2>&1; echo "time_bwd rc=$?"
