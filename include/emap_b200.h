@@ -212,6 +212,8 @@ int emap_rays_from_pixels(const int64_t* pixels_x, const int64_t* pixels_y, cons
 /* options: "cluster" = 1|2|-2 : weight-stream organisation of the K1/K1g/dual kernels (1 = default);
  *          "rg_flags" : K1r experiment switches (bit 0: N-split of each step's last K chunk; bit 1: launch
  *                       with the sigma scratch as a persisting-L2 access-policy window);
+ *          "k1_dot"   : 1 = emap_udf_forward (without pe_out) runs the output layer as an fp32 dot product
+ *                       in layer 7's epilogue instead of a ninth MMA step (opt-in until measured);
  *          "rev_tiles": 1 = default reverse sweep, 2 = two tiles in flight per CTA (mlp_rev2.cu,
  *                       bit-identical output; opt-in until measured);
  *          "dbg"      : timing experiments of mlp_tc.cu (0 in production).                            */
