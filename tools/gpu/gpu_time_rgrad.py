@@ -31,6 +31,12 @@ def t(fn, reps=5):
 
 
 for prec, name in ((3, "fp32x3"), (1, "fp16")):
+    # (independent of K1r: first, so that a K1r failure does not lose it)
+    f0 = t(lambda: ops.udf_forward(net, prec, pts=x))
+    C.set_option("k1_dot", 1)
+    f1 = t(lambda: ops.udf_forward(net, prec, pts=x))
+    C.set_option("k1_dot", 0)
+    print(f"{name}: K1 forward with the dot-product output layer (k1_dot=1): {f1:.2f} ms (default {f0:.2f} ms)", flush=True)
     uf, gf = ops.udf_forward_grad(net, prec, pts=x, mode="forward")
     ur, gr = ops.udf_forward_grad(net, prec, pts=x, mode="reverse")
     torch.cuda.synchronize()
@@ -46,11 +52,6 @@ for prec, name in ((3, "fp32x3"), (1, "fp16")):
     tr2 = t(lambda: ops.udf_forward_grad(net, prec, pts=x, mode="reverse"))
     C.set_option("rg_flags", 0)
     print(f"{name}: K1r with the persisting-L2 window on the sigma scratch (rg_flags=2): {tr2:.2f} ms", flush=True)
-    f0 = t(lambda: ops.udf_forward(net, prec, pts=x))
-    C.set_option("k1_dot", 1)
-    f1 = t(lambda: ops.udf_forward(net, prec, pts=x))
-    C.set_option("k1_dot", 0)
-    print(f"{name}: K1 forward with the dot-product output layer (k1_dot=1): {f1:.2f} ms (default {f0:.2f} ms)", flush=True)
     flop = 2 * 918016 * P
     print(f"{name}: K1g {tf:.2f} ms ({flop / tf / 1e9:.0f} TF/s alg)   K1r {tr:.2f} ms ({flop / tr / 1e9:.0f} TF/s alg)   "
           f"K1 forward only {f0:.2f} ms", flush=True)
