@@ -5,7 +5,9 @@
 mkdir -p gpurun_out
 O=gpurun_out
 timeout 300 python tools/gpu/gpu_debug_rgrad.py > $O/k1r_debug.txt 2>&1; echo "k1r debug rc=$?"; tail -60 $O/k1r_debug.txt
-EMAP_EXPERIMENTAL=1 timeout 900 python -m pytest tests/test_gpu_rgrad.py -x -q > $O/k1r_pytest.log 2>&1; echo "k1r pytest rc=$?"; tail -15 $O/k1r_pytest.log
+EMAP_EXPERIMENTAL=1 timeout 900 python -m pytest tests/test_gpu_rgrad.py -x -q -k "not k1_dot and not shared" > $O/k1r_pytest.log 2>&1; echo "k1r pytest rc=$?"; tail -15 $O/k1r_pytest.log
+EMAP_EXPERIMENTAL=1 timeout 600 python -m pytest tests/test_gpu_rgrad.py -x -q -k "shared" > $O/shared_pytest.log 2>&1; echo "shared-backward pytest rc=$?"; tail -15 $O/shared_pytest.log
+EMAP_EXPERIMENTAL=1 timeout 300 python -m pytest tests/test_gpu_rgrad.py -x -q -k "k1_dot" > $O/k1dot_pytest.log 2>&1; echo "k1_dot pytest rc=$?"; tail -5 $O/k1dot_pytest.log
 EMAP_EXPERIMENTAL=1 timeout 600 python -m pytest tests/test_gpu_rev2.py -x -q > $O/rev2_pytest.log 2>&1; echo "rev2 pytest rc=$?"; tail -5 $O/rev2_pytest.log
 timeout 200 python tools/gpu/gpu_time_rev2.py > $O/rev2_time.txt 2>&1; echo "rev2 time rc=$?"; cat $O/rev2_time.txt
 timeout 600 python -m pytest tests -q -m gpu > $O/pytest_gpu.log 2>&1; echo "pytest rc=$?"; tail -3 $O/pytest_gpu.log
