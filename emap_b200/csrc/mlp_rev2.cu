@@ -27,7 +27,6 @@ constexpr int kStages = 3;             // ring stages of 32 KiB: one [256 x 64] 
 constexpr int kTiles = 2;              // tiles in flight per CTA
 constexpr int kRingStageBytes = 2 * kStageBytes;
 constexpr int kRevLayers = 7;          // MMA layers l = 7..1
-constexpr int kRevParts = kRevLayers * 4;
 
 struct Smem {
   static constexpr int a = 0;                                   // [2 tiles][4 chunks][128 x 64] fp16 SW128

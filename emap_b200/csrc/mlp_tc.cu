@@ -128,7 +128,7 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_kernel(const MlpArgs args) {
                 bulk_g2s(dst, src, bytes, &full[stage]);
               } else {
                 mbar_arrive_expect_tx(&full[stage], bytes);
-                const uint32_t slice = bytes / CL;
+                const uint32_t slice = bytes / (uint32_t)CLW;
                 bulk_g2s_multicast(dst + rank * slice, src + rank * slice, slice, &full[stage],
                                    (uint16_t)((1u << CLW) - 1));
               }
