@@ -27,6 +27,7 @@
 #include "mlp_dev.cuh"
 
 namespace emap {
+long long* dbg_clk_buffer();   // mlp_tc.cu (emap_debug_set_clk_buffer)
 namespace rg {
 
 constexpr int kSteps = 16;
@@ -197,10 +198,15 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_rgrad_kernel(const Args args)
 #pragma unroll
       for (int s = 0; s < kSteps; ++s) {
         const int buf = s & 1;
+        // timeline of block 0's second tile (emap_debug_rgrad + emap_debug_set_clk_buffer): issuer stamps at
+        // dbg_clk[64 + 4 s + {0: step start, 1: accumulator free, 2: first K chunk ready, 3: all MMAs issued}]
+        const bool stamp = m.dbg_clk && blockIdx.x == 0 && iter == 1 && lane == 0;
+        if (stamp) m.dbg_clk[64 + 4 * s + 0] = clock64();
         {
           const uint32_t started = (uint32_t)iter * kUsesPerBuf + (uint32_t)(s >> 1);
           if (started > 0) mbar_wait(&acc_empty[buf], (started - 1) & 1, 200 + buf, s);
         }
+        if (stamp) m.dbg_clk[64 + 4 * s + 1] = clock64();
         const int nkc = step_nkc(s);
         const uint32_t idesc = (s == kLastStep) ? idesc64 : idesc256;
         const uint32_t d = tmem_base + (uint32_t)buf * 256u;
@@ -219,6 +225,7 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_rgrad_kernel(const Args args)
                                            : (uint32_t)iter * kAPerTile + (uint32_t)(s - 1);
             mbar_wait(&a_ready[c], uses & 1, 300 + c, s);
           }
+          if (stamp && ic == 0) m.dbg_clk[64 + 4 * s + 2] = clock64();
           tc_fence_after();
           const uint32_t coff = (c == 4) ? 0u : (uint32_t)c * kChunkBytes;   // PE lives in chunk 0
           const uint64_t ahi = make_sw128_kmajor_desc(a_hi_addr + coff);
@@ -282,6 +289,7 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_rgrad_kernel(const Args args)
           if (elect_one()) { umma_commit(&acc_full[buf * 2]); umma_commit(&acc_full[buf * 2 + 1]); }
           __syncwarp();
         }
+        if (stamp) m.dbg_clk[64 + 4 * s + 3] = clock64();
       }
     }
   } else {
@@ -326,8 +334,12 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_rgrad_kernel(const Args args)
         const int buf = l & 1;
         const bool top = (l == 7);              // layer 7: h_8 feeds only the output layer; seed the sweep
         const uint32_t acc_par = ((uint32_t)iter * kUsesPerBuf + (uint32_t)(l >> 1)) & 1;
+        // epilogue warp 0 stamps at dbg_clk[4 s + {0: waiting, 1: accumulator complete, 2: chunk 0 handed off, 3: done}]
+        const bool stamp = m.dbg_clk && blockIdx.x == 0 && iter == 1 && warp == 0 && lane == 0;
+        if (stamp) m.dbg_clk[4 * l + 0] = clock64();
         mbar_wait(&acc_full[buf * 2], acc_par, 500 + buf, l);
         tc_fence_after();
+        if (stamp) m.dbg_clk[4 * l + 1] = clock64();
         const float* bl = bias100 + l * kHidden;
 #pragma unroll 1
         for (int chunk = 0; chunk < 4; ++chunk) {
@@ -377,6 +389,7 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_rgrad_kernel(const Args args)
           fence_proxy_async_smem();
           __syncwarp();
           if (lane == 0) mbar_arrive(&a_ready[chunk]);
+          if (stamp && chunk == 0) m.dbg_clk[4 * l + 2] = clock64();
           if (!top) stg256(sgp, sw);          // after the hand-off: off the MMA's critical path
           // training: value rows [0,P) of the backward's stash U_{l+1} (emap_bwd_tangent_forward adds the
           // tangent rows later) -- after the hand-off, off the MMA's critical path
@@ -385,6 +398,7 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_rgrad_kernel(const Args args)
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(&acc_empty[buf]);
+        if (stamp) m.dbg_clk[4 * l + 3] = clock64();
 
         if (l == kSkipLayer - 1 && sub < 2) {
           // skip connection: layer 4 = [h4 ; PE]/sqrt2.  Once its MMAs on chunk 0 are done, regenerate
@@ -411,8 +425,11 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_rgrad_kernel(const Args args)
         auto fetch_sigma = [&](int chunk) { ld_sigma16(sg_ptr(l - 1, chunk), sgc); };
         fetch_sigma(0);
         const uint32_t acc_par = ((uint32_t)iter * kUsesPerBuf + (uint32_t)(s >> 1)) & 1;
+        const bool stamp = m.dbg_clk && blockIdx.x == 0 && iter == 1 && warp == 0 && lane == 0;
+        if (stamp) m.dbg_clk[4 * s + 0] = clock64();
         mbar_wait(&acc_full[buf * 2], acc_par, 530 + buf, s);
         tc_fence_after();
+        if (stamp) m.dbg_clk[4 * s + 1] = clock64();
 #pragma unroll
         for (int chunk = 0; chunk < 4; ++chunk) {
           const int col0 = chunk * 64 + sub * 16;
@@ -450,10 +467,12 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_rgrad_kernel(const Args args)
           fence_proxy_async_smem();
           __syncwarp();
           if (lane == 0) mbar_arrive(&a_ready[chunk]);
+          if (stamp && chunk == 0) m.dbg_clk[4 * s + 2] = clock64();
         }
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(&acc_empty[buf]);
+        if (stamp) m.dbg_clk[4 * s + 3] = clock64();
       }
 
       // ------------------------------------------------ step 15: alpha_0 W_0 (64 PE slots) -> d udf / d x
@@ -622,6 +641,7 @@ int emap::rg::run(const emap_net_desc* net, const void* packed, int precision, c
   a.m.packed = (const uint8_t*)packed; a.m.pts = pts; a.m.rays_o = rays_o; a.m.rays_d = rays_d; a.m.z = z;
   a.m.n_per_ray = n_per_ray; a.m.P = P; a.m.udf_out = udf_out; a.m.grad_out = grad_out;
   a.m.dbg_acc = dbg_acc;
+  a.m.dbg_clk = dbg_acc ? dbg_clk_buffer() : nullptr;      // timeline stamps only through emap_debug_rgrad
   a.m.st_u0 = (__half*)st_u0; a.m.st_u = (__half*)st_u;
   a.scratch = (uint32_t*)scratch;
   cudaStream_t st = (cudaStream_t)stream;

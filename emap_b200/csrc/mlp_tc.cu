@@ -602,6 +602,7 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_kernel(const MlpArgs args) {
 }
 
 static long long* g_dbg_clk = nullptr;   // emap_debug_set_clk_buffer
+long long* dbg_clk_buffer() { return g_dbg_clk; }   // (mlp_rg.cu's debug entry stamps into the same buffer)
 static int g_dbg_flags = 0;   // timing experiments (emap_set_option("dbg", flags)); 0 in production
 
 // ---------------------------------------------------------------------------------------------

@@ -12,6 +12,7 @@ EMAP_EXPERIMENTAL=1 timeout 600 python -m pytest tests/test_gpu_rev2.py -x -q > 
 timeout 200 python tools/gpu/gpu_time_rev2.py > $O/rev2_time.txt 2>&1; echo "rev2 time rc=$?"; cat $O/rev2_time.txt
 timeout 600 python -m pytest tests -q -m gpu > $O/pytest_gpu.log 2>&1; echo "pytest rc=$?"; tail -3 $O/pytest_gpu.log
 timeout 200 python tools/gpu/gpu_time_rgrad.py > $O/k1r_time.txt 2>&1; echo "time rc=$?"; cat $O/k1r_time.txt
+timeout 120 python tools/gpu/gpu_clk_rgrad.py > $O/k1r_clk.txt 2>&1; echo "clk rc=$?"
 for gm in forward reverse; do
   timeout 200 python bench.py --mode infer --no-cpu-baseline --grad-mode $gm > $O/bench_infer_fp32_$gm.json 2> $O/bench_infer_$gm.err; echo "bench infer $gm rc=$?"; cut -c1-200 $O/bench_infer_fp32_$gm.json
   timeout 300 python bench.py --no-cpu-baseline --grad-mode $gm > $O/bench_train_fp32_$gm.json 2> $O/bench_train_$gm.err; echo "bench train $gm rc=$?"; cut -c1-200 $O/bench_train_fp32_$gm.json
