@@ -10,7 +10,7 @@ EMAP_EXPERIMENTAL=1 timeout 600 python -m pytest tests/test_gpu_rgrad.py -x -q -
 EMAP_EXPERIMENTAL=1 timeout 300 python -m pytest tests/test_gpu_rgrad.py -x -q -k "k1_dot" > $O/k1dot_pytest.log 2>&1; echo "k1_dot pytest rc=$?"; tail -5 $O/k1dot_pytest.log
 EMAP_EXPERIMENTAL=1 timeout 600 python -m pytest tests/test_gpu_rev2.py -x -q > $O/rev2_pytest.log 2>&1; echo "rev2 pytest rc=$?"; tail -5 $O/rev2_pytest.log
 timeout 200 python tools/gpu/gpu_time_rev2.py > $O/rev2_time.txt 2>&1; echo "rev2 time rc=$?"; cat $O/rev2_time.txt
-timeout 600 python -m pytest tests -q -m gpu > $O/pytest_gpu.log 2>&1; echo "pytest rc=$?"; tail -3 $O/pytest_gpu.log
+timeout 600 python -m pytest tests -q -m gpu --deselect tests/test_gpu_zz_experimental.py > $O/pytest_gpu.log 2>&1; echo "pytest rc=$?"; tail -3 $O/pytest_gpu.log
 timeout 200 python tools/gpu/gpu_time_rgrad.py > $O/k1r_time.txt 2>&1; echo "time rc=$?"; cat $O/k1r_time.txt
 timeout 120 python tools/gpu/gpu_clk_rgrad.py > $O/k1r_clk.txt 2>&1; echo "clk rc=$?"
 for gm in forward reverse; do
