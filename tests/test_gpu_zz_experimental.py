@@ -33,7 +33,7 @@ def test_experimental_group_in_child_process(name, args, capsys):
     if os.environ.get("EMAP_EXPERIMENTAL") == "1":
         pytest.skip("the experimental tests are running directly in this session")
     env = dict(os.environ, EMAP_EXPERIMENTAL="1")
-    cmd = [sys.executable, "-m", "pytest", "-q", "-x", "-p", "no:cacheprovider"] + args
+    cmd = [sys.executable, "-m", "pytest", "-q", "-rfEs", "-p", "no:cacheprovider"] + args
     try:
         res = subprocess.run(cmd, cwd=ROOT, env=env, capture_output=True, text=True, timeout=600)
         out, rc = res.stdout + res.stderr, res.returncode
