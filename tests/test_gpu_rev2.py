@@ -15,7 +15,7 @@ pytestmark = [
     pytest.mark.gpu,
     pytest.mark.skipif(os.environ.get("EMAP_EXPERIMENTAL") != "1",
                        reason="rev2 not yet validated on hardware: set EMAP_EXPERIMENTAL=1 to run"),
-    pytest.mark.timeout(300),
+    pytest.mark.timeout(120),
 ]
 
 

@@ -27,7 +27,7 @@ GROUPS = [
 
 
 @pytest.mark.gpu
-@pytest.mark.timeout(900)
+@pytest.mark.timeout(300)
 @pytest.mark.parametrize("name,args", GROUPS, ids=[g[0] for g in GROUPS])
 def test_experimental_group_in_child_process(name, args, capsys):
     if os.environ.get("EMAP_EXPERIMENTAL") == "1":
@@ -35,7 +35,7 @@ def test_experimental_group_in_child_process(name, args, capsys):
     env = dict(os.environ, EMAP_EXPERIMENTAL="1")
     cmd = [sys.executable, "-m", "pytest", "-q", "-rfEs", "-p", "no:cacheprovider"] + args
     try:
-        res = subprocess.run(cmd, cwd=ROOT, env=env, capture_output=True, text=True, timeout=600)
+        res = subprocess.run(cmd, cwd=ROOT, env=env, capture_output=True, text=True, timeout=240)
         out, rc = res.stdout + res.stderr, res.returncode
     except subprocess.TimeoutExpired as e:
         out = (e.stdout or b"").decode(errors="replace") if isinstance(e.stdout, bytes) else (e.stdout or "")
