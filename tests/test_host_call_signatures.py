@@ -137,3 +137,51 @@ def test_ray_kernels_and_callers(shim):
     ops.null_direction(torch.zeros(5, 50, 3))
     for name in ("emap_coarse_z", "emap_upsample_step", "emap_render_prep", "emap_null_direction"):
         assert name in rec.calls, name
+
+
+class _FakeModule:
+    """just enough of emap_b200.UDFNetwork for the autograd Functions: a CPU PackedNet behind the recorder"""
+
+    def __init__(self, ops):
+        self.net = _packed(ops)
+        self.params = [torch.zeros(n, requires_grad=True) for n in (self.net.n_params - 10, 10)]
+        self.prec_code = C.PREC_FP32X3
+        self.net.fold_id = 1
+
+    def packed(self):
+        return self.net
+
+    def flat_param_list(self):
+        return self.params
+
+
+@pytest.mark.parametrize("grad_mode,bwd_mode,expect_shared", [("forward", "dual", False), ("reverse", "dual", False),
+                                                              ("reverse", "shared", True), ("forward", "shared", False)])
+def test_autograd_wiring_of_the_backward_modes(shim, grad_mode, bwd_mode, expect_shared):
+    """_UDFForwardGrad end to end on the recorder: which forward / stage-1 kernels each mode combination calls,
+    that the stash made in forward reaches backward, and that every parameter gets a gradient of its shape."""
+    ops, rec = shim
+    from emap_b200.autograd import udf_forward_grad_fn
+    ops.set_grad_mode(grad_mode)
+    ops.set_backward_mode(bwd_mode)
+    mod = _FakeModule(ops)
+    x = torch.zeros(40, 3)
+    udf, grad = udf_forward_grad_fn(mod, x)
+    assert ("emap_udf_forward_grad_rev" in rec.calls) == (grad_mode == "reverse")
+    (udf.sum() + grad.sum()).backward()
+    assert ("emap_bwd_tangent_forward" in rec.calls) == expect_shared
+    assert ("emap_bwd_dual_forward" in rec.calls) == (not expect_shared)
+    for p in mod.params:
+        assert p.grad is not None and p.grad.shape == p.shape
+    # parameters re-folded between forward and backward: the stash is stale -> fall back to the dual forward
+    if expect_shared:
+        rec.calls.clear()
+        udf, grad = udf_forward_grad_fn(mod, x)
+        mod.net.fold_id += 1
+        (udf.sum() + grad.sum()).backward()
+        assert "emap_bwd_dual_forward" in rec.calls and "emap_bwd_tangent_forward" not in rec.calls
+    # no parameter gradient requested -> no stash is allocated / filled
+    rec.calls.clear()
+    with torch.no_grad():
+        udf_forward_grad_fn(mod, x)
+    assert rec.calls.count("emap_udf_forward_grad_rev") + rec.calls.count("emap_udf_forward_grad") == 1
