@@ -130,6 +130,13 @@ def test_rev2_protocol_no_deadlock_no_hazard():
         Rev2Sim(iters=3, seed=seed).run()
 
 
+def test_rev2_protocol_under_heavy_tailed_latencies(monkeypatch):
+    from tests.test_rg_protocol import _heavy_tailed
+    monkeypatch.setattr(Sim, "lat", _heavy_tailed)
+    for seed in range(300, 340):
+        Rev2Sim(iters=4, seed=seed).run()
+
+
 def test_rev2_model_detects_a_wrong_parity():
     with pytest.raises(AssertionError):
         for seed in range(10):
