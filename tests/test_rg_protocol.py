@@ -367,3 +367,30 @@ def test_model_detects_a_wrong_accumulator_count():
                 Sim(3, iters=3, seed=seed).run()
     finally:
         USES = old
+
+
+def test_model_constants_match_the_cuda_source():
+    """the model is a transcription: at least its constants are read back from mlp_rg.cu / mlp_rev2.cu"""
+    import os
+    import re
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    src = open(os.path.join(root, "emap_b200", "csrc", "mlp_rg.cu")).read()
+
+    def const(name):
+        m = re.search(rf"constexpr\s+\w+\s+{name}\s*=\s*(\d+)", src)
+        assert m, name
+        return int(m.group(1))
+    assert const("kSteps") == K_STEPS
+    assert const("kUsesPerBuf") == USES[0] == USES[1]
+    assert const("kAPerTile") == A_PER_TILE
+    assert re.search(r"kStages = \(NTERMS == 3\) \? 3 : 4;", src) and K_STAGES == {3: 3, 1: 4}
+    assert re.search(r"mbar_init\(&a_ready\[c\], kEpiWarps\)", src) and re.search(r"mbar_init\(&a_ready\[4\], 8\)", src)
+    assert re.search(r"mbar_init\(&acc_empty\[b\], kEpiWarps\)", src)
+    assert "uses & 1" in src and "(uint32_t)iter * kAPerTile + (uint32_t)(s - 1)" in src
+    assert "(uint32_t)iter * 2u + (s == kSkipLayer ? 1u : 0u)" in src
+    assert "(uint32_t)iter * kUsesPerBuf + (uint32_t)(s >> 1)" in src
+    dev = open(os.path.join(root, "emap_b200", "csrc", "mlp_dev.cuh")).read()
+    assert re.search(r"constexpr int kEpiWarps = (\d+);", dev).group(1) == str(EPI_WARPS)
+    rev2 = open(os.path.join(root, "emap_b200", "csrc", "mlp_rev2.cu")).read()
+    assert re.search(r"constexpr int kStages = 3;", rev2) and re.search(r"constexpr int kTiles = 2;", rev2)
+    assert "(uint32_t)iter * 7u + (uint32_t)j" in rev2
