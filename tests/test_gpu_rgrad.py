@@ -4,9 +4,10 @@ against the reference-generated fixtures, the CPU oracle and the validated forwa
 Status: written and compiled for sm_100a in round 1 after the round's GPU budget was spent; its
 algorithm, operand images and column maps are pinned on the CPU (tests/test_rg_emulation.py), its
 synchronisation has NOT run on hardware yet.  It is therefore opt-in in the product
-(EMAP_GRAD_MODE=reverse / ops.set_grad_mode) and these tests run only with EMAP_EXPERIMENTAL=1, so that
-the round-end GPU suite reports the state of the validated default path.  First GPU call of the next
-round: `EMAP_EXPERIMENTAL=1 python -m pytest tests/test_gpu_rgrad.py -x -q`.
+(EMAP_GRAD_MODE=reverse / ops.set_grad_mode) and these tests run directly only with EMAP_EXPERIMENTAL=1;
+in a regular `pytest -m gpu` session they are executed by tests/test_gpu_zz_experimental.py in child
+processes, non-gating (a red group is reported as xfail), so that the suite's verdict stays that of the
+validated default path.  Bring-up: `tools/gpu/run_gpu_k1r.sh`.
 
 Tolerances: the ones K1g is held to (tests/test_gpu_mlp.py): fp32x3 5e-5 relative to max(1, |ref|max);
 fp16 3e-3 / 1e-2.
