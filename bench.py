@@ -187,6 +187,33 @@ def cpu_baseline(mode, sample_rays=1024, reps=1):
             f"{mode}, torch CPU fp32 oracle (port of the reference), {reps} rep(s), {dt:.2f} s each"}
 
 
+def experimental_probes(points):
+    """Informational, never part of `value` / `e2e`: the opt-in kernels (K1r, K1 without the output
+    MMA, tangent-only forward, two-tile reverse sweep) against the validated kernels they would replace --
+    parity on the same inputs and time, one child process per item so that a trapped launch cannot take this
+    process (or the next item) down.  Bounded: 150 s per item."""
+    probe = os.path.join(ROOT, "tools", "gpu", "experimental_probe.py")
+    out = {"note": "opt-in kernels, not yet the default path; NOT included in value / e2e / roofline"}
+    for item in ("k1r", "k1_dot", "shared_backward", "rev2"):
+        try:
+            res = subprocess.run([sys.executable, probe, "--item", item, "--points", str(points)], cwd=ROOT,
+                                 capture_output=True, text=True, timeout=150)
+            lines = [ln for ln in res.stdout.strip().splitlines() if ln.startswith("{")]
+            if res.returncode == 0 and lines:
+                out[item] = json.loads(lines[-1])
+            else:
+                err = [ln for ln in (res.stderr + res.stdout).strip().splitlines() if ln.strip()]
+                out[item] = {"error": (err[-1] if err else f"rc={res.returncode}")[:300]}
+                traps = [ln[:160] for ln in res.stdout.splitlines() if ln.startswith("emap:")][:4]
+                if traps:                                         # the kernels' own diagnostics (barrier tags)
+                    out[item]["device_messages"] = traps
+        except subprocess.TimeoutExpired:
+            out[item] = {"error": "timeout (150 s)"}
+        except Exception as e:                                    # never let the probe break the bench line
+            out[item] = {"error": repr(e)[:300]}
+    return out
+
+
 def run_reference(args, rank, world):
     """--impl reference: the reference's CPU implementation of the path (oracle port), rank 0 only."""
     if rank != 0:
@@ -230,6 +257,8 @@ def main():
                     help="BASELINE.json config (default c4 = 4096 rays x 256 samples, the one the metric is quoted on)")
     ap.add_argument("--ref-rays", type=int, default=128)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-experimental", action="store_true",
+                    help="skip the informational probes of the opt-in kernels (child processes, N=1 only)")
     ap.add_argument("--grad-mode", default=os.environ.get("EMAP_GRAD_MODE", "forward"),
                     choices=["forward", "reverse"],
                     help="K1g forward-mode tangents (validated default) or K1r reverse-mode (mlp_rg.cu, opt-in)")
@@ -404,6 +433,10 @@ def main():
                          "algorithmic = 2F/point (fwd + reverse-mode grad); the kernel executes forward-mode "
                          "(4 rows/point) and, in fp32 mode, 3 split-fp16 MMAs per product")}
         cpu = None if args.no_cpu_baseline else cpu_baseline(args.mode)
+        experimental = None
+        if world == 1 and not args.no_experimental:
+            torch.cuda.empty_cache()
+            experimental = experimental_probes(min(B * n, 1 << 20))
         line = {
             "metric": "ray-samples/s through UDF render path", "value": value, "unit": "ray-samples/s",
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms,
@@ -423,6 +456,8 @@ def main():
             "roofline": roof,
             "cpu_baseline": cpu,
         }
+        if experimental is not None:
+            line["experimental"] = experimental
         print(json.dumps(line))
     if world > 1:
         torch.distributed.barrier()
