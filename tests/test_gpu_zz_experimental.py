@@ -32,6 +32,8 @@ GROUPS = [
 def test_experimental_group_in_child_process(name, args, capsys):
     if os.environ.get("EMAP_EXPERIMENTAL") == "1":
         pytest.skip("the experimental tests are running directly in this session")
+    import torch
+    torch.cuda.empty_cache()                       # hand this process's cached blocks back before the child allocates
     env = dict(os.environ, EMAP_EXPERIMENTAL="1")
     cmd = [sys.executable, "-m", "pytest", "-q", "-rfEs", "-p", "no:cacheprovider"] + args
     try:
