@@ -191,17 +191,17 @@ def experimental_probes(points):
     """Informational, never part of `value` / `e2e`: the opt-in kernels (K1r, K1 without the output
     MMA, tangent-only forward, two-tile reverse sweep) against the validated kernels they would replace --
     parity on the same inputs and time, one child process per item so that a trapped launch cannot take this
-    process (or the next item) down.  Bounded: 45 s per item (a protocol bug traps within ~4 s), 150 s in all."""
+    process (or the next item) down.  Bounded: 35 s per item (a protocol bug traps within ~4 s), 100 s in all."""
     probe = os.path.join(ROOT, "tools", "gpu", "experimental_probe.py")
     out = {"note": "opt-in kernels, not yet the default path; NOT included in value / e2e / roofline"}
-    deadline = time.perf_counter() + 150.0
+    deadline = time.perf_counter() + 100.0
     for item in ("k1r", "k1_dot", "shared_backward", "rev2"):
-        if time.perf_counter() > deadline - 20.0:
+        if time.perf_counter() > deadline - 15.0:
             out[item] = {"error": "skipped: time budget of the probes used up"}
             continue
         try:
             res = subprocess.run([sys.executable, probe, "--item", item, "--points", str(points)], cwd=ROOT,
-                                 capture_output=True, text=True, timeout=45)
+                                 capture_output=True, text=True, timeout=35)
             lines = [ln for ln in res.stdout.strip().splitlines() if ln.startswith("{")]
             if res.returncode == 0 and lines:
                 out[item] = json.loads(lines[-1])
@@ -212,7 +212,7 @@ def experimental_probes(points):
                 if traps:                                         # the kernels' own diagnostics (barrier tags)
                     out[item]["device_messages"] = traps
         except subprocess.TimeoutExpired:
-            out[item] = {"error": "timeout (45 s)"}
+            out[item] = {"error": "timeout (35 s)"}
         except Exception as e:                                    # never let the probe break the bench line
             out[item] = {"error": repr(e)[:300]}
     return out
