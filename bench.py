@@ -261,6 +261,9 @@ def main():
                     help="BASELINE.json config (default c4 = 4096 rays x 256 samples, the one the metric is quoted on)")
     ap.add_argument("--ref-rays", type=int, default=128)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--all-optins", action="store_true",
+                    help="measure with every opt-in kernel selected: --grad-mode reverse --bwd-stash shared, "
+                         "rev_tiles=2, k1_dot=1 (DESIGN §8; the combined step the next default would be)")
     ap.add_argument("--no-experimental", action="store_true",
                     help="skip the informational probes of the opt-in kernels (child processes, N=1 only)")
     ap.add_argument("--grad-mode", default=os.environ.get("EMAP_GRAD_MODE", "forward"),
@@ -301,6 +304,10 @@ def main():
         dist.init_process_group("nccl", device_id=dev)
 
     from emap_b200 import _cabi as C
+    if args.all_optins:
+        args.grad_mode, args.bwd_stash = "reverse", "shared"
+        C.set_option("rev_tiles", 2)
+        C.set_option("k1_dot", 1)
     ops.set_grad_mode(args.grad_mode)
     ops.set_backward_mode(args.bwd_stash)
     if args.bwd_stash == "shared" and args.grad_mode != "reverse":
@@ -450,7 +457,8 @@ def main():
             "data": "synthetic",
             "config": {"workload": f"replica-style synthetic cameras, {B} rays x {n} samples "
                                    f"({N0}+{NI}/{STEPS} hierarchical) per GPU, {args.mode}",
-                       "mode": args.mode, "grad_mode": args.grad_mode, "bwd_stash": args.bwd_stash, "rays_per_gpu": B, "samples_per_ray": n,
+                       "mode": args.mode, "grad_mode": args.grad_mode, "bwd_stash": args.bwd_stash,
+                       "all_optins": bool(args.all_optins), "rays_per_gpu": B, "samples_per_ray": n,
                        "parallelism": f"rays sharded x{world}" + (", flat grad allreduce" if args.mode == "train" else ""),
                        "l2": "flushed (256 MiB write) between timed steps"},
             "clocks": clocks,

@@ -18,6 +18,8 @@ for gm in forward reverse; do
   timeout 300 python bench.py --no-cpu-baseline --no-experimental --grad-mode $gm > $O/bench_train_fp32_$gm.json 2> $O/bench_train_$gm.err; echo "bench train $gm rc=$?"; cut -c1-200 $O/bench_train_fp32_$gm.json
 done
 timeout 300 python bench.py --no-cpu-baseline --no-experimental --grad-mode reverse --bwd-stash shared > $O/bench_train_fp32_reverse_shared.json 2> $O/bench_train_shared.err; echo "bench train reverse+shared rc=$?"; cut -c1-200 $O/bench_train_fp32_reverse_shared.json
+timeout 300 python bench.py --no-cpu-baseline --no-experimental --all-optins > $O/bench_train_fp32_all_optins.json 2> $O/bench_train_all.err; echo "bench train all opt-ins rc=$?"; cut -c1-200 $O/bench_train_fp32_all_optins.json
+timeout 200 python bench.py --mode infer --no-cpu-baseline --no-experimental --all-optins > $O/bench_infer_fp32_all_optins.json 2>/dev/null; echo "bench infer all opt-ins rc=$?"; cut -c1-200 $O/bench_infer_fp32_all_optins.json
 timeout 500 ncu --set full --clock-control none --import-source on -k regex:"mlp_rgrad" -s 3 -c 1 -o /tmp/prof_k1r python bench.py --mode infer --steps 1 --warmup 3 --no-cpu-baseline --no-experimental --grad-mode reverse > $O/ncu_k1r.log 2>&1; echo "ncu rc=$?"
 ncu -i /tmp/prof_k1r.ncu-rep --page raw --csv > $O/prof_k1r_raw.csv 2>/dev/null
 ncu -i /tmp/prof_k1r.ncu-rep --page source --csv 2>/dev/null | python tools/gpu/ncu_stalls.py > $O/prof_k1r_stalls.txt
