@@ -191,10 +191,10 @@ def experimental_probes(points):
     """Informational, never part of `value` / `e2e`: the opt-in kernels (K1r, K1 without the output
     MMA, tangent-only forward, two-tile reverse sweep) against the validated kernels they would replace --
     parity on the same inputs and time, one child process per item so that a trapped launch cannot take this
-    process (or the next item) down.  Bounded: 35 s per item (a protocol bug traps within ~4 s), 100 s in all."""
+    process (or the next item) down.  Bounded: 35 s per item (a protocol bug traps within ~4 s), 130 s in all."""
     probe = os.path.join(ROOT, "tools", "gpu", "experimental_probe.py")
     out = {"note": "opt-in kernels, not yet the default path; NOT included in value / e2e / roofline"}
-    deadline = time.perf_counter() + 100.0
+    deadline = time.perf_counter() + 130.0
     for item in ("k1r", "k1_dot", "shared_backward", "rev2"):
         if time.perf_counter() > deadline - 15.0:
             out[item] = {"error": "skipped: time budget of the probes used up"}
@@ -215,6 +215,28 @@ def experimental_probes(points):
             out[item] = {"error": "timeout (35 s)"}
         except Exception as e:                                    # never let the probe break the bench line
             out[item] = {"error": repr(e)[:300]}
+    # if the two kernels the combined step depends on came out clean, also time that step (a short run of this
+    # very script with every opt-in selected) -- again informational
+    clean = all("error" not in out.get(k, {"error": 1}) for k in ("k1r", "shared_backward", "rev2", "k1_dot"))
+    parity = clean and out["k1r"].get("max_abs_diff_grad_vs_k1g", 1.0) < 1e-3 and out["rev2"].get("rev2_bit_identical")
+    if parity and time.perf_counter() < deadline - 30.0:
+        for mode in ("train", "infer"):
+            try:
+                res = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--all-optins", "--no-experimental",
+                                      "--no-cpu-baseline", "--mode", mode, "--steps", "5", "--warmup", "3"], cwd=ROOT,
+                                     capture_output=True, text=True, timeout=max(10.0, deadline - time.perf_counter()))
+                lines = [ln for ln in res.stdout.strip().splitlines() if ln.startswith("{")]
+                if res.returncode == 0 and lines:
+                    j = json.loads(lines[-1])
+                    out[f"all_optins_{mode}"] = {"ms_per_step": j["ms_per_step"], "value": j["value"], "unit": j["unit"],
+                                                 "roofline_frac": j["roofline"]["frac"],
+                                                 "kernel_ms": j["roofline"]["ms_per_launch"], "steps": j["steps"]}
+                else:
+                    out[f"all_optins_{mode}"] = {"error": f"rc={res.returncode}"}
+            except subprocess.TimeoutExpired:
+                out[f"all_optins_{mode}"] = {"error": "timeout"}
+            except Exception as e:
+                out[f"all_optins_{mode}"] = {"error": repr(e)[:300]}
     return out
 
 
