@@ -61,15 +61,15 @@ def main():
         C.set_option("rg_flags", 0)
         out["k1r_algorithmic_tflops"] = 2 * F * P / (out["k1r_ms"] * 1e-3) / 1e12
         try:                                                      # extras: must not cost the results above
-            C.set_option("rg_flags", 2)
-            out["k1r_l2_persist_ms"] = timed(lambda: ops.udf_forward_grad(net, C.PREC_FP32X3, pts=x, mode="reverse"), 3)
-            C.set_option("rg_flags", 0)
             uf16, gf16 = ops.udf_forward_grad(net, C.PREC_HALF, pts=x, mode="forward")
             ur16, gr16 = ops.udf_forward_grad(net, C.PREC_HALF, pts=x, mode="reverse")
             torch.cuda.synchronize()
             out["fp16_max_abs_diff_grad_vs_k1g"] = float((gr16 - gf16).abs().max())
             out["fp16_k1g_ms"] = timed(lambda: ops.udf_forward_grad(net, C.PREC_HALF, pts=x, mode="forward"), 3)
             out["fp16_k1r_ms"] = timed(lambda: ops.udf_forward_grad(net, C.PREC_HALF, pts=x, mode="reverse"), 3)
+            C.set_option("rg_flags", 2)
+            out["k1r_l2_persist_ms"] = timed(lambda: ops.udf_forward_grad(net, C.PREC_FP32X3, pts=x, mode="reverse"), 3)
+            C.set_option("rg_flags", 0)
         except Exception as e:
             out["extras_error"] = repr(e)[:200]
             C.set_option("rg_flags", 0)
