@@ -187,59 +187,6 @@ def cpu_baseline(mode, sample_rays=1024, reps=1):
             f"{mode}, torch CPU fp32 oracle (port of the reference), {reps} rep(s), {dt:.2f} s each"}
 
 
-def experimental_probes(points):
-    """Informational, never part of `value` / `e2e`: the opt-in kernels (K1r, K1 without the output
-    MMA, tangent-only forward, two-tile reverse sweep) against the validated kernels they would replace --
-    parity on the same inputs and time, one child process per item so that a trapped launch cannot take this
-    process (or the next item) down.  Bounded: 35 s per item (a protocol bug traps within ~4 s), 130 s in all."""
-    probe = os.path.join(ROOT, "tools", "gpu", "experimental_probe.py")
-    out = {"note": "opt-in kernels, not yet the default path; NOT included in value / e2e / roofline"}
-    deadline = time.perf_counter() + 130.0
-    for item in ("k1r", "k1_dot", "shared_backward", "rev2"):
-        if time.perf_counter() > deadline - 15.0:
-            out[item] = {"error": "skipped: time budget of the probes used up"}
-            continue
-        try:
-            res = subprocess.run([sys.executable, probe, "--item", item, "--points", str(points)], cwd=ROOT,
-                                 capture_output=True, text=True, timeout=35)
-            lines = [ln for ln in res.stdout.strip().splitlines() if ln.startswith("{")]
-            if res.returncode == 0 and lines:
-                out[item] = json.loads(lines[-1])
-            else:
-                err = [ln for ln in (res.stderr + res.stdout).strip().splitlines() if ln.strip()]
-                out[item] = {"error": (err[-1] if err else f"rc={res.returncode}")[:300]}
-                traps = [ln[:160] for ln in res.stdout.splitlines() if ln.startswith("emap:")][:4]
-                if traps:                                         # the kernels' own diagnostics (barrier tags)
-                    out[item]["device_messages"] = traps
-        except subprocess.TimeoutExpired:
-            out[item] = {"error": "timeout (35 s)"}
-        except Exception as e:                                    # never let the probe break the bench line
-            out[item] = {"error": repr(e)[:300]}
-    # if the two kernels the combined step depends on came out clean, also time that step (a short run of this
-    # very script with every opt-in selected) -- again informational
-    clean = all("error" not in out.get(k, {"error": 1}) for k in ("k1r", "shared_backward", "rev2", "k1_dot"))
-    parity = clean and out["k1r"].get("max_abs_diff_grad_vs_k1g", 1.0) < 1e-3 and out["rev2"].get("rev2_bit_identical")
-    if parity and time.perf_counter() < deadline - 30.0:
-        for mode in ("train", "infer"):
-            try:
-                res = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--all-optins", "--no-experimental",
-                                      "--no-cpu-baseline", "--mode", mode, "--steps", "5", "--warmup", "3"], cwd=ROOT,
-                                     capture_output=True, text=True, timeout=max(10.0, deadline - time.perf_counter()))
-                lines = [ln for ln in res.stdout.strip().splitlines() if ln.startswith("{")]
-                if res.returncode == 0 and lines:
-                    j = json.loads(lines[-1])
-                    out[f"all_optins_{mode}"] = {"ms_per_step": j["ms_per_step"], "value": j["value"], "unit": j["unit"],
-                                                 "roofline_frac": j["roofline"]["frac"],
-                                                 "kernel_ms": j["roofline"]["ms_per_launch"], "steps": j["steps"]}
-                else:
-                    out[f"all_optins_{mode}"] = {"error": f"rc={res.returncode}"}
-            except subprocess.TimeoutExpired:
-                out[f"all_optins_{mode}"] = {"error": "timeout"}
-            except Exception as e:
-                out[f"all_optins_{mode}"] = {"error": repr(e)[:300]}
-    return out
-
-
 def run_reference(args, rank, world):
     """--impl reference: the reference's CPU implementation of the path (oracle port), rank 0 only."""
     if rank != 0:
@@ -283,17 +230,12 @@ def main():
                     help="BASELINE.json config (default c4 = 4096 rays x 256 samples, the one the metric is quoted on)")
     ap.add_argument("--ref-rays", type=int, default=128)
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--all-optins", action="store_true",
-                    help="measure with every opt-in kernel selected: --grad-mode reverse --bwd-stash shared, "
-                         "rev_tiles=2, k1_dot=1 (DESIGN §8; the combined step the next default would be)")
-    ap.add_argument("--no-experimental", action="store_true",
-                    help="skip the informational probes of the opt-in kernels (child processes, N=1 only)")
-    ap.add_argument("--grad-mode", default=os.environ.get("EMAP_GRAD_MODE", "forward"),
+    ap.add_argument("--grad-mode", default=os.environ.get("EMAP_GRAD_MODE", "reverse"),
                     choices=["forward", "reverse"],
-                    help="K1g forward-mode tangents (validated default) or K1r reverse-mode (mlp_rg.cu, opt-in)")
-    ap.add_argument("--bwd-stash", default=os.environ.get("EMAP_BWD_STASH", "dual"), choices=["dual", "shared"],
-                    help="backward: re-run the dual forward (validated default) or share the training forward's "
-                         "activations (needs --grad-mode reverse; opt-in)")
+                    help="K1r reverse-mode (mlp_rg.cu, default) or K1g forward-mode tangents (cross-check)")
+    ap.add_argument("--bwd-stash", default=None, choices=["dual", "shared"],
+                    help="backward: share the training forward's activations (default with --grad-mode reverse) "
+                         "or re-run the dual forward")
     args = ap.parse_args()
     global N0, NI, STEPS, RAYS_PER_GPU
     wl = WORKLOADS[args.workload]
@@ -326,10 +268,8 @@ def main():
         dist.init_process_group("nccl", device_id=dev)
 
     from emap_b200 import _cabi as C
-    if args.all_optins:
-        args.grad_mode, args.bwd_stash = "reverse", "shared"
-        C.set_option("rev_tiles", 2)
-        C.set_option("k1_dot", 1)
+    if args.bwd_stash is None:
+        args.bwd_stash = "shared" if args.grad_mode == "reverse" else "dual"
     ops.set_grad_mode(args.grad_mode)
     ops.set_backward_mode(args.bwd_stash)
     if args.bwd_stash == "shared" and args.grad_mode != "reverse":
@@ -466,10 +406,6 @@ def main():
                          "algorithmic = 2F/point (fwd + reverse-mode grad); the kernel executes forward-mode "
                          "(4 rows/point) and, in fp32 mode, 3 split-fp16 MMAs per product")}
         cpu = None if args.no_cpu_baseline else cpu_baseline(args.mode)
-        experimental = None
-        if world == 1 and not args.no_experimental:
-            torch.cuda.empty_cache()
-            experimental = experimental_probes(min(B * n, 1 << 20))
         line = {
             "metric": "ray-samples/s through UDF render path", "value": value, "unit": "ray-samples/s",
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms,
@@ -480,7 +416,7 @@ def main():
             "config": {"workload": f"replica-style synthetic cameras, {B} rays x {n} samples "
                                    f"({N0}+{NI}/{STEPS} hierarchical) per GPU, {args.mode}",
                        "mode": args.mode, "grad_mode": args.grad_mode, "bwd_stash": args.bwd_stash,
-                       "all_optins": bool(args.all_optins), "rays_per_gpu": B, "samples_per_ray": n,
+                       "rays_per_gpu": B, "samples_per_ray": n,
                        "parallelism": f"rays sharded x{world}" + (", flat grad allreduce" if args.mode == "train" else ""),
                        "l2": "flushed (256 MiB write) between timed steps"},
             "clocks": clocks,
@@ -490,8 +426,6 @@ def main():
             "roofline": roof,
             "cpu_baseline": cpu,
         }
-        if experimental is not None:
-            line["experimental"] = experimental
         print(json.dumps(line))
     if world > 1:
         torch.distributed.barrier()

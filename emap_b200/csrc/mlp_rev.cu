@@ -261,14 +261,6 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_rev_kernel(const Args args) {
 }  // namespace rev
 }  // namespace emap
 
-namespace emap {
-namespace rev2 {   // mlp_rev2.cu: the same sweep with two tiles in flight per CTA (opt-in)
-bool enabled();
-int launch(const emap_net_desc* net, const void* packed, const float* coef, const void* st_u, void* st_a,
-           int64_t P, void* stream);
-}  // namespace rev2
-}  // namespace emap
-
 using namespace emap;
 
 extern "C" int emap_bwd_reverse_sweep(const emap_net_desc* net, const void* packed, const float* coef,
@@ -276,7 +268,6 @@ extern "C" int emap_bwd_reverse_sweep(const emap_net_desc* net, const void* pack
   if (check_net(net)) return 1;
   if (net->elem_type != 0) return set_error("emap_bwd_reverse_sweep: fp16 operand images required");
   if (!packed || !coef || !st_u || !st_a || P <= 0) return set_error("emap_bwd_reverse_sweep: bad arguments");
-  if (rev2::enabled()) return rev2::launch(net, packed, coef, st_u, st_a, P, stream);
   rev::Args a;
   a.packed = (const uint8_t*)packed; a.coef = coef; a.st_u = (const __half*)st_u;
   a.st_a = (__half*)st_a; a.P = P;

@@ -32,7 +32,6 @@
 namespace emap {
 
 namespace rg { int set_flags(int v); }   // mlp_rg.cu
-namespace rev2 { int set_tiles(int v); } // mlp_rev2.cu
 
 template <int NTERMS, int MODE, typename T, int CL>
 __global__ void __launch_bounds__(kThreads, 1) mlp_kernel(const MlpArgs args) {
@@ -785,7 +784,6 @@ extern "C" int emap_set_option(const char* name, int value) {
   if (!strcmp(name, "dbg")) { emap::g_dbg_flags = value; return 0; }
   if (!strcmp(name, "k1_dot")) { emap::g_k1_dot = (value != 0); return 0; }
   if (!strcmp(name, "rg_flags")) return emap::rg::set_flags(value);   // K1r experiment switches (mlp_rg.cu)
-  if (!strcmp(name, "rev_tiles")) return emap::rev2::set_tiles(value); // reverse sweep: tiles in flight per CTA
   return set_error("unknown option '%s'", name);
 }
 

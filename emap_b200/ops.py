@@ -72,18 +72,20 @@ def udf_forward(net: PackedNet, precision: int, pts=None, rays_o=None, rays_d=No
     return udf, pe
 
 
-# How (udf, d udf/dx) is evaluated: "forward" = K1g, forward-mode tangent rows (validated on B200, the
-# default); "reverse" = K1r, value forward + adjoint sweep in one kernel (mlp_rg.cu; half the tensor-core
-# work -- built and CPU-emulated in round 1, not yet run on hardware, hence opt-in).
-_GRAD_MODE = os.environ.get("EMAP_GRAD_MODE", "forward")
+# How (udf, d udf/dx) is evaluated: "reverse" = K1r, value forward + adjoint sweep in one kernel (mlp_rg.cu;
+# what autograd does, half the tensor-core work of forward mode -- the default since it was validated on
+# B200); "forward" = K1g, forward-mode tangent rows (mlp_tc.cu MODE 1; kept as an independent cross-check).
+DEFAULT_GRAD_MODE = os.environ.get("EMAP_GRAD_MODE", "reverse")
+_GRAD_MODE = DEFAULT_GRAD_MODE
 _RG_SCRATCH = {}
 
 
-# How the backward obtains the dual activations U_l = (h_l ; hdot_l): "dual" = re-run the dual forward
-# (validated default); "shared" = the training forward (K1r) writes the value rows while it has them in
-# registers and the backward only adds the tangent rows (emap_bwd_tangent_forward, about half the work).
-# "shared" needs grad mode "reverse"; opt-in for the same reason as K1r.
-_BWD_MODE = os.environ.get("EMAP_BWD_STASH", "dual")
+# How the backward obtains the dual activations U_l = (h_l ; hdot_l): "shared" (default) = the training
+# forward (K1r) writes the value rows while it has them in registers and the backward only adds the tangent
+# rows (emap_bwd_tangent_forward, about half the work); "dual" = re-run the dual forward (cross-check, and
+# what grad mode "forward" uses).  "shared" needs grad mode "reverse".
+DEFAULT_BWD_MODE = os.environ.get("EMAP_BWD_STASH", "shared")
+_BWD_MODE = DEFAULT_BWD_MODE
 
 
 def set_backward_mode(mode: str) -> None:

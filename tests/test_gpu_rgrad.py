@@ -1,19 +1,13 @@
 """GPU parity: K1r, forward + REVERSE-mode gradient in one tcgen05 kernel (emap_b200/csrc/mlp_rg.cu),
 against the reference-generated fixtures, the CPU oracle and the validated forward-mode kernel K1g.
 
-Status: written and compiled for sm_100a in round 1 after the round's GPU budget was spent; its
-algorithm, operand images and column maps are pinned on the CPU (tests/test_rg_emulation.py), its
-synchronisation has NOT run on hardware yet.  It is therefore opt-in in the product
-(EMAP_GRAD_MODE=reverse / ops.set_grad_mode) and these tests run directly only with EMAP_EXPERIMENTAL=1;
-in a regular `pytest -m gpu` session they are executed by tests/test_gpu_zz_experimental.py in child
-processes, non-gating (a red group is reported as xfail), so that the suite's verdict stays that of the
-validated default path.  Bring-up: `tools/gpu/run_gpu_k1r.sh`.
+Status: validated on B200 (round 2); K1r + the shared-forward backward are the product default
+(ops._GRAD_MODE = "reverse", ops._BWD_MODE = "shared").  The forward-mode kernel K1g and the dual-forward
+backward remain as independent cross-checks.
 
 Tolerances: the ones K1g is held to (tests/test_gpu_mlp.py): fp32x3 5e-5 relative to max(1, |ref|max);
 fp16 3e-3 / 1e-2.
 """
-import os
-
 import pytest
 import torch
 
@@ -21,8 +15,6 @@ from tests.helpers import maxdiff, oracle_params
 
 pytestmark = [
     pytest.mark.gpu,
-    pytest.mark.skipif(os.environ.get("EMAP_EXPERIMENTAL") != "1",
-                       reason="K1r not yet validated on hardware: set EMAP_EXPERIMENTAL=1 to run"),
     pytest.mark.timeout(120),
 ]
 
@@ -161,7 +153,7 @@ def test_render_with_reverse_mode_matches_default():
                 outs[mode] = r.render(o.cuda(), d.cuda(), near.cuda(), far.cuda(), ds.cuda(),
                                       cos_anneal_ratio=1.0, flip_saturation=0.9)
         finally:
-            ops.set_grad_mode("forward")
+            ops.set_grad_mode(ops.DEFAULT_GRAD_MODE)
     for k in ("edge", "depth", "weights", "gradients", "udf"):
         assert maxdiff(outs["forward"][k], outs["reverse"][k]) <= 2e-3, k
 
@@ -221,7 +213,7 @@ def test_shared_backward_param_grads_vs_reference(golden, tag, pert):
         loss.backward()
         torch.cuda.synchronize()
     finally:
-        ops.set_grad_mode("forward"); ops.set_backward_mode("dual")
+        ops.set_grad_mode(ops.DEFAULT_GRAD_MODE); ops.set_backward_mode(ops.DEFAULT_BWD_MODE)
     _check([(n, p.grad) for n, p in net.named_parameters()], g, "dgrad", 1e-2)
 
 
@@ -248,7 +240,7 @@ def test_shared_backward_render_loss_matches_default():
             torch.cuda.synchronize()
             grads[mode] = (float(loss), [p.grad.clone() for p in net.parameters()])
         finally:
-            ops.set_grad_mode("forward"); ops.set_backward_mode("dual")
+            ops.set_grad_mode(ops.DEFAULT_GRAD_MODE); ops.set_backward_mode(ops.DEFAULT_BWD_MODE)
     (l0, g0), (l1, g1) = grads[("forward", "dual")], grads[("reverse", "shared")]
     assert abs(l0 - l1) <= 1e-3 * max(1.0, abs(l0))
     for a, b in zip(g0, g1):

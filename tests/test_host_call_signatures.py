@@ -57,8 +57,8 @@ def shim(monkeypatch):
     real_mm = torch.mm
     monkeypatch.setattr(torch, "mm", lambda a, b, out_dtype=None: real_mm(a.float(), b.float()))
     yield ops, rec
-    ops.set_grad_mode("forward")
-    ops.set_backward_mode("dual")
+    ops.set_grad_mode(ops.DEFAULT_GRAD_MODE)
+    ops.set_backward_mode(ops.DEFAULT_BWD_MODE)
 
 
 def _packed(ops, multires=10):
@@ -114,6 +114,7 @@ def test_mode_switches_validate(shim):
         ops.set_grad_mode("sideways")
     with pytest.raises(ValueError):
         ops.set_backward_mode("borrowed")
+    ops.set_grad_mode("forward")
     ops.set_backward_mode("shared")
     assert not ops.shared_backward()            # needs the reverse-mode forward
     ops.set_grad_mode("reverse")

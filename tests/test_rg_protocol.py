@@ -370,7 +370,7 @@ def test_model_detects_a_wrong_accumulator_count():
 
 
 def test_model_constants_match_the_cuda_source():
-    """the model is a transcription: at least its constants are read back from mlp_rg.cu / mlp_rev2.cu"""
+    """the model is a transcription: at least its constants are read back from mlp_rg.cu"""
     import os
     import re
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -391,6 +391,3 @@ def test_model_constants_match_the_cuda_source():
     assert "(uint32_t)iter * kUsesPerBuf + (uint32_t)(s >> 1)" in src
     dev = open(os.path.join(root, "emap_b200", "csrc", "mlp_dev.cuh")).read()
     assert re.search(r"constexpr int kEpiWarps = (\d+);", dev).group(1) == str(EPI_WARPS)
-    rev2 = open(os.path.join(root, "emap_b200", "csrc", "mlp_rev2.cu")).read()
-    assert re.search(r"constexpr int kStages = 3;", rev2) and re.search(r"constexpr int kTiles = 2;", rev2)
-    assert "(uint32_t)iter * 7u + (uint32_t)j" in rev2

@@ -6,8 +6,8 @@ timeout 200 python bench.py --steps 10 --warmup 3 --mode infer --no-cpu-baseline
 timeout 200 python bench.py --steps 10 --warmup 3 --mode infer --precision fp16 --no-cpu-baseline > gpurun_out/bench_infer_fp16.json 2>/dev/null
 timeout 200 python bench.py --steps 10 --warmup 3 --precision fp16 --no-cpu-baseline > gpurun_out/bench_train_fp16.json 2>/dev/null
 timeout 120 python bench.py --impl reference --steps 2 --warmup 1 > gpurun_out/bench_reference.json 2>/dev/null; echo "ref rc=$?"
-timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none -s 400 -c 160 --csv --log-file gpurun_out/launches_train.csv python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-experimental > gpurun_out/ncu_launches.log 2>&1; echo "ncu list rc=$?"
-timeout 500 ncu --set full --clock-control none --import-source on -k regex:"mlp_kernel<3, 1|mlp_kernel<1, 2|mlp_rev" -s 3 -c 3 -o /tmp/prof_mlp2 python bench.py --steps 1 --warmup 3 --no-cpu-baseline --no-experimental > gpurun_out/ncu_full.log 2>&1; echo "ncu full rc=$?"
+timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none -s 400 -c 160 --csv --log-file gpurun_out/launches_train.csv python bench.py --steps 2 --warmup 3 --no-cpu-baseline > gpurun_out/ncu_launches.log 2>&1; echo "ncu list rc=$?"
+timeout 500 ncu --set full --clock-control none --import-source on -k regex:"mlp_kernel<3, 1|mlp_kernel<1, 2|mlp_rev" -s 3 -c 3 -o /tmp/prof_mlp2 python bench.py --steps 1 --warmup 3 --no-cpu-baseline > gpurun_out/ncu_full.log 2>&1; echo "ncu full rc=$?"
 ncu -i /tmp/prof_mlp2.ncu-rep --page raw --csv > gpurun_out/prof_mlp2_raw.csv 2>/dev/null
 ncu -i /tmp/prof_mlp2.ncu-rep --page source --csv 2>/dev/null | python - <<'PY' > gpurun_out/prof_mlp2_stalls.txt
 import sys, csv, re, collections
