@@ -17,7 +17,10 @@ max over ranks, L2 flushed between steps); `e2e` = same through the public API w
 inputs, H2D and D2H inside the timed region; `roofline` = the dominant kernel (fused MLP
 forward+gradient) timed alone, algorithmic FLOPs / measured duration vs the measured bf16 GEMM peak;
 `cpu_baseline` = the CPU oracle (port of the reference, torch CPU fp32, all host threads) on a
-bounded sample of the same workload.  `--impl reference` prints the CPU arm as the headline.
+bounded sample of the same workload; `gpu_incumbent` = the same port in eager PyTorch on cuda:0 (fp32, TF32
+off: what the reference's authors ran, runner_base.py:27), whole batch, forward and forward+backward.
+`--impl reference` prints the CPU arm as the headline.  `--scaling strong` splits ONE batch of --rays rays
+over the ranks (BASELINE configs[3]: 4096 rays sharded over 8 GPUs) instead of giving every rank --rays rays.
 """
 import argparse
 import json
@@ -46,7 +49,9 @@ WORKLOADS = {
 }
 # DRAM bytes of ONE launch of the dominant kernel (ncu --set full capture of this workload, see profiles/):
 # (precision, rays, samples) -> dram__bytes_read.sum + dram__bytes_write.sum.  None = not captured.
-NCU_DRAM_BYTES_PER_LAUNCH = {("fp32", 4096, 256): 6.490e6}
+NCU_DRAM_BYTES_PER_LAUNCH = {("forward", "train", "fp32", 4096, 256): 6.490e6,     # K1g (round 1)
+                             ("forward", "infer", "fp32", 4096, 256): 6.490e6,
+                             ("reverse", "train", "fp32", 4096, 256): 10.953e9}    # K1r + value stash (round 2)
 
 
 def peaks():
@@ -125,8 +130,9 @@ def build_ours(dev, precision):
     return net, var, beta, r
 
 
-def oracle_step_fn(mode, B):
-    """CPU oracle (port of the reference) on B rays of the same workload; returns a callable."""
+def oracle_step_fn(mode, B, device="cpu"):
+    """The oracle (port of the reference, plain PyTorch ops) on B rays of the same workload; returns a
+    callable.  device="cpu": the CPU arm; device="cuda": the eager-CUDA incumbent."""
     from oracle import emap_oracle as O
     p = O.perturbed_params(O.geometric_init(generator=torch.Generator().manual_seed(0)))
     s = O.ScalarParams(torch.tensor([0.3]), torch.tensor([0.5]), torch.tensor([0.3]))
@@ -134,6 +140,11 @@ def oracle_step_fn(mode, B):
     o, d, near, far, ds = synthetic_problem(B)
     t_rand = O.synthetic_t_rand(B)
     true_edge = torch.rand(B, 1, generator=torch.Generator().manual_seed(21))
+    if device != "cpu":
+        p = O.UDFParams([t.to(device) for t in p.v], [t.to(device) for t in p.g], [t.to(device) for t in p.b],
+                        p.multires, p.skip_in, p.scale, p.udf_type)
+        s = O.ScalarParams(s.variance.to(device), s.beta.to(device), s.gamma.to(device))
+        o, d, near, far, ds, t_rand, true_edge = (t.to(device) for t in (o, d, near, far, ds, t_rand, true_edge))
     if mode == "train":
         p.requires_grad_(True)
         for t in (s.variance, s.beta, s.gamma):
@@ -187,6 +198,46 @@ def cpu_baseline(mode, sample_rays=1024, reps=1):
             f"{mode}, torch CPU fp32 oracle (port of the reference), {reps} rep(s), {dt:.2f} s each"}
 
 
+def gpu_incumbent(dev, B):
+    """The reference path as its authors ran it: plain PyTorch modules/ops in eager mode on the GPU (fp32,
+    TF32 off -- torch's default), here on the whole B-ray batch of the bench workload.  The reference package
+    itself cannot travel to the GPU box (its runner needs pyhocon/open3d/...), so this is the oracle port of its
+    modules -- pinned bit-exactly to the reference on the CPU (tests/test_oracle_golden.py)."""
+    assert not torch.backends.cuda.matmul.allow_tf32
+    n = N0 + NI
+    res = {"kind": "port", "what": "oracle restatement of the reference modules, eager PyTorch on cuda, fp32 "
+                                    "(TF32 off), whole batch per step", "rays": B, "samples_per_ray": n}
+    for mode in ("infer", "train"):
+        try:
+            step = oracle_step_fn(mode, B, device=dev)
+            step()
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            reps = 2
+            e0.record()
+            for _ in range(reps):
+                step()
+            e1.record()
+            torch.cuda.synchronize()
+            ms = e0.elapsed_time(e1) / reps
+            res[mode] = {"ms_per_step": ms, "value": B * n / (ms * 1e-3), "unit": "ray-samples/s",
+                         "peak_mem_gb": torch.cuda.max_memory_allocated() / 2**30}
+            del step
+        except Exception as e:  # noqa: BLE001  (e.g. out of memory on a smaller part: report, do not fail the bench)
+            res[mode] = {"error": repr(e)[:200]}
+        torch.cuda.empty_cache()
+    return res
+
+
+def workload_config(args, world):
+    """The keys that define WHAT is measured -- identical in both arms (ours / --impl reference)."""
+    n = N0 + NI
+    per_gpu = args.rays // world if args.scaling == "strong" else args.rays
+    return {"workload": f"replica-style synthetic cameras, {per_gpu} rays x {n} samples "
+                        f"({N0}+{NI}/{STEPS} hierarchical) per GPU, {args.mode}",
+            "mode": args.mode, "rays_per_gpu": per_gpu, "samples_per_ray": n, "scaling": args.scaling}
+
+
 def run_reference(args, rank, world):
     """--impl reference: the reference's CPU implementation of the path (oracle port), rank 0 only."""
     if rank != 0:
@@ -204,13 +255,13 @@ def run_reference(args, rank, world):
     line = {
         "impl": "reference", "metric": "ray-samples/s through UDF render path", "value": val,
         "unit": "ray-samples/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"replica-style synthetic cameras, {RAYS_PER_GPU} rays x {n} samples "
-                               f"({N0}+{NI}/{STEPS} hierarchical) per GPU, {args.mode}",
-                   "step_sample": f"{args.ref_rays} rays x {n} samples per step (bounded CPU sample)"},
+        "config": workload_config(args, world),
         "cpu_baseline": {"value": val, "unit": "ray-samples/s", "cores": torch.get_num_threads(),
-                         "kind": "port", "sample": f"{args.ref_rays} rays x {n} samples per step"},
+                         "kind": "port", "sample": f"{args.ref_rays} rays x {n} samples per step (a bounded "
+                         "chunk of the batch; the reference processes rays independently, chunk by chunk in "
+                         "its own validate loop), torch CPU fp32 oracle port of the reference"},
         "e2e": {"value": val, "unit": "ray-samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -228,7 +279,12 @@ def main():
     ap.add_argument("--rays", type=int, default=None)
     ap.add_argument("--workload", default="c4", choices=sorted(WORKLOADS),
                     help="BASELINE.json config (default c4 = 4096 rays x 256 samples, the one the metric is quoted on)")
-    ap.add_argument("--ref-rays", type=int, default=128)
+    ap.add_argument("--ref-rays", type=int, default=1024,
+                    help="rays per step of the CPU arm (a bounded chunk of the batch; ~5 s per step)")
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
+                    help="weak: --rays rays per GPU (default); strong: --rays rays in total, sharded over the ranks")
+    ap.add_argument("--no-gpu-incumbent", action="store_true",
+                    help="skip timing the eager-PyTorch-on-CUDA port of the reference (N=1, after the timed region)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--grad-mode", default=os.environ.get("EMAP_GRAD_MODE", "reverse"),
                     choices=["forward", "reverse"],
@@ -276,10 +332,23 @@ def main():
         raise SystemExit("--bwd-stash shared needs --grad-mode reverse")
     grad_call = "emap_udf_forward_grad_rev" if args.grad_mode == "reverse" else "emap_udf_forward_grad"
     net, var, beta, r = build_ours(dev, args.precision)
-    B, n = args.rays, N0 + NI
-    o, d, near, far, ds = synthetic_problem(B, seed_offset=rank)
+    n = N0 + NI
+    if args.scaling == "strong":
+        # ONE batch of --rays rays, contiguous shards (parallel.shard_rays); the two eikonal means are those of
+        # the whole batch (2-float all-reduce in the forward, parallel.globalize_eikonal)
+        from emap_b200.parallel import shard_rays
+        if args.rays % world:
+            raise SystemExit("--scaling strong needs --rays divisible by the number of ranks")
+        o, d, near, far, ds = synthetic_problem(args.rays)
+        te_all = torch.rand(args.rays, 1, generator=torch.Generator().manual_seed(21))
+        o, d, ds, true_edge = shard_rays([o, d, ds, te_all], rank, world)
+        true_edge = true_edge.to(dev)
+        r.global_batch_stats = world > 1
+    else:
+        o, d, near, far, ds = synthetic_problem(args.rays, seed_offset=rank)
+        true_edge = torch.rand(args.rays, 1, generator=torch.Generator().manual_seed(21 + rank)).to(dev)
+    B = o.shape[0]
     o_d, d_d, ds_d = o.to(dev), d.to(dev), ds.to(dev)
-    true_edge = torch.rand(B, 1, generator=torch.Generator().manual_seed(21 + rank)).to(dev)
     near_f, far_f = 0.05, 6.0
     opt = None
     if args.mode == "train":
@@ -393,9 +462,11 @@ def main():
                                               "mlp_kernel<MODE_GRAD> (emap_udf_forward_grad)"),
                 "achieved": achieved, "peak": pk["bf16_tflops"], "unit": "TFLOP/s",
                 "frac": achieved / pk["bf16_tflops"],
-                "traffic": None if rev else NCU_DRAM_BYTES_PER_LAUNCH.get((args.precision, B, n)),
-                "traffic_source": "profiles/r01_mlp_ncu_raw.csv (ncu --set full, dram__bytes_read.sum + "
-                                  "dram__bytes_write.sum of one launch of this workload)",
+                "traffic": NCU_DRAM_BYTES_PER_LAUNCH.get((args.grad_mode, args.mode, args.precision, B, n)),
+                "traffic_source": "ncu --set full capture of one launch of this workload (dram__bytes_read.sum + "
+                                  "dram__bytes_write.sum; profiles/r02_k1r_ncu_raw.csv, r01_mlp_ncu_raw.csv); in "
+                                  "train mode the kernel also writes the backward's fp16 value stash, "
+                                  "8 x P x 256 x 2 B = 4.3 GB at P = 1 M",
                 "peak_source": pk_src + " burst bf16 (cuBLAS)",
                 "ms_per_launch": k_ms, "launches_timed": len(k_live), "points_per_launch": P,
                 "share_of_step": k_ms / ms,
@@ -406,25 +477,34 @@ def main():
                          "algorithmic = 2F/point (fwd + reverse-mode grad); the kernel executes forward-mode "
                          "(4 rows/point) and, in fp32 mode, 3 split-fp16 MMAs per product")}
         cpu = None if args.no_cpu_baseline else cpu_baseline(args.mode)
+        incumbent = None
+        if world == 1 and not args.no_gpu_incumbent:
+            del flush
+            torch.cuda.empty_cache()
+            incumbent = gpu_incumbent(dev, B)
+            if "value" in incumbent.get(args.mode, {}):
+                incumbent["this_repo_over_incumbent"] = value / incumbent[args.mode]["value"]
         line = {
             "metric": "ray-samples/s through UDF render path", "value": value, "unit": "ray-samples/s",
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms,
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": {"fp32": "f32 (3x split-fp16 tcgen05 MMA, fp32 accumulate)", "fp16": "f16",
-                      "bf16": "bf16"}[args.precision],
+            "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None,
+            "dtype": {"fp32": "f32 forward (3x split-fp16 tcgen05 MMA, fp32 accumulate)", "fp16": "f16 forward",
+                      "bf16": "bf16 forward"}[args.precision] + (
+                "; backward: fp16 tcgen05 MMA operands and fp16 stashes, fp32 accumulate, loss-scaled on the device"
+                if args.mode == "train" else ""),
             "data": "synthetic",
-            "config": {"workload": f"replica-style synthetic cameras, {B} rays x {n} samples "
-                                   f"({N0}+{NI}/{STEPS} hierarchical) per GPU, {args.mode}",
-                       "mode": args.mode, "grad_mode": args.grad_mode, "bwd_stash": args.bwd_stash,
-                       "rays_per_gpu": B, "samples_per_ray": n,
-                       "parallelism": f"rays sharded x{world}" + (", flat grad allreduce" if args.mode == "train" else ""),
-                       "l2": "flushed (256 MiB write) between timed steps"},
+            "config": workload_config(args, world),
+            "impl_config": {"grad_mode": args.grad_mode, "bwd_stash": args.bwd_stash, "precision": args.precision,
+                            "parallelism": f"rays sharded x{world}" + (", one in-place flat grad all-reduce"
+                                                                       if args.mode == "train" else ""),
+                            "l2": "flushed (256 MiB write) between timed steps"},
             "clocks": clocks,
             "e2e": {"value": world * B * n / (e2e_ms * 1e-3), "unit": "ray-samples/s",
                     "ms_per_step": e2e_ms, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
             "gpu_launches": launches,
             "roofline": roof,
             "cpu_baseline": cpu,
+            "gpu_incumbent": incumbent,
         }
         print(json.dumps(line))
     if world > 1:

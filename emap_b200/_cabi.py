@@ -46,7 +46,7 @@ SIGNATURES = {
     "emap_rgrad_scratch_bytes": (ctypes.c_size_t, []),
     "emap_udf_forward_grad_rev": (ctypes.c_int, [_nd, _vp, _i32, _vp, _vp, _vp, _vp, _i32, _i64, _vp, _vp, _vp,
                                                  ctypes.c_size_t, _vp, _vp, _vp]),
-    "emap_bwd_tangent_forward": (ctypes.c_int, [_nd, _vp, _vp, _vp, _vp, _vp, _i32, _i64, _vp, _vp, _vp, _vp]),
+    "emap_bwd_tangent_forward": (ctypes.c_int, [_nd, _vp, _vp, _vp, _vp, _vp, _i32, _i64, _vp, _vp, _vp, _vp, _vp]),
     "emap_debug_rgrad": (ctypes.c_int, [_nd, _vp, _i32, _vp, _vp, _vp, _vp, _i32, _i64, _vp, _vp, _vp,
                                         ctypes.c_size_t, _vp, _vp]),
     "emap_debug_rg_image": (ctypes.c_int, [_nd, ctypes.c_int, _vp, _vp, _vp]),
@@ -57,19 +57,17 @@ SIGNATURES = {
     "emap_debug_set_clk_buffer": (ctypes.c_int, [_vp]),
     "emap_coarse_z": (ctypes.c_int, [_vp, _vp, _i32, _vp, _vp, _i32, _i32, _vp, _vp]),
     "emap_upsample_step": (ctypes.c_int, [_vp, _vp, _vp, _vp, _i32, _vp, _vp, _i32, _vp, _vp, _vp, _i32,
-                                          _vp, _vp, _vp, _vp, _i32, _f32, _f32, _f32, _vp, _i32, _i32, _vp]),
+                                          _vp, _vp, _vp, _vp, _i32, _f32, _f32, _f32, _vp, _i32, _i32, _vp, _vp]),
     "emap_render_prep": (ctypes.c_int, [_vp, _vp, _i32, _i32, _vp, _vp, _vp]),
     "emap_render_core_fwd": (ctypes.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _i32, _f32, _f32,
                                             _f32, _f32, _i32, _i32, _i32, _vp, _vp, _vp, _vp, _vp, _vp,
-                                            _vp, _vp, _vp, _vp, _vp]),
-    "emap_bwd_dual_forward": (ctypes.c_int, [_nd, _vp, _i32, _vp, _vp, _vp, _vp, _i32, _i64, _vp, _vp, _vp, _vp]),
+                                            _vp, _vp, _vp, _vp, _vp, _vp]),
+    "emap_bwd_cotangent_scales": (ctypes.c_int, [_vp, _vp, _i64, _vp, _vp]),
+    "emap_bwd_dual_forward": (ctypes.c_int, [_nd, _vp, _i32, _vp, _vp, _vp, _vp, _i32, _i64, _vp, _vp, _vp, _vp, _vp]),
     "emap_bwd_reverse_sweep": (ctypes.c_int, [_nd, _vp, _vp, _vp, _vp, _i64, _vp]),
     "emap_bwd_bias_sums": (ctypes.c_int, [_vp, _i64, _vp, _vp, _vp]),
-    "emap_bwd_pe_dual": (ctypes.c_int, [_nd, _vp, _vp, _vp, _vp, _i32, _i64, _vp, _vp, _vp]),
-    "emap_bwd_act_fwd": (ctypes.c_int, [_vp, _i32, _vp, _i64, _i32, _vp, _i32, _vp, _vp, _vp, _vp]),
-    "emap_bwd_top": (ctypes.c_int, [_nd, _vp, _vp, _vp, _vp, _i64, _vp, _vp, _vp]),
-    "emap_bwd_act_bwd": (ctypes.c_int, [_vp, _i32, _f32, _i64, _i32, _vp, _vp, _vp, _vp]),
-    "emap_bwd_weight_norm": (ctypes.c_int, [_nd, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "emap_bwd_top": (ctypes.c_int, [_nd, _vp, _vp, _vp, _vp, _vp, _i64, _vp, _vp]),
+    "emap_bwd_weight_norm": (ctypes.c_int, [_nd, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "emap_packed_offsets": (ctypes.c_int, [_nd, _vp]),
     "emap_null_direction": (ctypes.c_int, [_vp, _i64, _i32, _vp, _vp]),
     "emap_rays_from_pixels": (ctypes.c_int, [_vp, _vp, _vp, _i32, _i32, _vp, _vp, _i32, _vp, _vp, _vp, _vp,
@@ -84,8 +82,8 @@ SIGNATURES = {
 LAUNCHES_PER_CALL = {
     "emap_wn_fold": 4, "emap_udf_forward": 1, "emap_udf_forward_grad": 1, "emap_udf_forward_grad_rev": 1, "emap_debug_rgrad": 1, "emap_debug_mlp": 1,
     "emap_coarse_z": 1, "emap_upsample_step": 1, "emap_render_prep": 1, "emap_render_core_fwd": 2,
-    "emap_render_core_bwd": 2, "emap_bwd_pe_dual": 1, "emap_bwd_act_fwd": 1, "emap_bwd_top": 1,
-    "emap_bwd_act_bwd": 1, "emap_bwd_weight_norm": 1, "emap_bwd_dual_forward": 1,
+    "emap_render_core_bwd": 2, "emap_bwd_top": 1, "emap_bwd_cotangent_scales": 2,
+    "emap_bwd_weight_norm": 1, "emap_bwd_dual_forward": 1,
     "emap_bwd_reverse_sweep": 1, "emap_bwd_tangent_forward": 1, "emap_bwd_bias_sums": 2, "emap_null_direction": 1, "emap_rays_from_pixels": 1,
 }
 launch_count = 0
@@ -138,7 +136,7 @@ def lib():
             fn = getattr(L, name)
             fn.restype = res
             fn.argtypes = args
-        if L.emap_abi_version() != 1:
+        if L.emap_abi_version() != 2:
             raise RuntimeError("emap_b200: ABI version mismatch between _cabi.py and the library")
         _lib = _Counting(L)
         if os.environ.get("EMAP_CLUSTER"):

@@ -54,7 +54,7 @@ class _UDFForwardGrad(torch.autograd.Function):
         # shared-forward backward (opt-in, ops.set_backward_mode): when parameter gradients will be asked for,
         # the reverse-mode forward also fills the value rows of the backward's stashes
         stash = None
-        if ops.shared_backward() and net.desc.elem_type == 0 and any(ctx.needs_input_grad[5:]):
+        if ops.shared_backward() and any(ctx.needs_input_grad[5:]):
             P = x.shape[0] if x is not None else z.numel()
             stash = ops.alloc_backward_stash(P, net.packed.device)
         udf, grad = ops.udf_forward_grad(net, module.prec_code, pts=x, rays_o=rays_o, rays_d=rays_d, z=z,

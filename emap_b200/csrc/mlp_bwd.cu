@@ -10,11 +10,9 @@
 //     alphadot_l = etadot_{l+1} * sigma_l
 //     dW_l = sum_p alpha_l u_l^T + alphadot_l udot_l^T,   db_l = sum_p alpha_l,
 //     [eta_l ; etadot_l] = [alpha_l ; alphadot_l] W_l
-// Round-1 structure: the per-layer GEMMs ([2P,in]x[in,256], [2P,256]x[256,in], [256,2P]x[2P,in])
-// are plain library GEMMs (cuBLAS through torch.mm, fp16 operands, fp32 accumulate/output), and
-// everything between them -- dual positional encoding, softplus / sigmoid / softplus'' stages with
-// their stashes, the output-layer pull-back, the weight-norm backward -- is the kernels below.
-// (DESIGN.md "backward" lists the fused tcgen05 version of this sweep as the next step.)
+// The dual forward / tangent forward (mlp_tc.cu) and the reverse sweep (mlp_rev.cu) are tcgen05 kernels; this
+// file holds the small stages around them: the cotangent scales (loss scaling of the fp16 arithmetic), the
+// output-layer pull-back, the bias-gradient sums and the weight-norm backward.
 #include <math.h>
 
 #include "common.cuh"
@@ -22,100 +20,58 @@
 
 namespace emap {
 
-__device__ __forceinline__ void bwd_load_point(const float* pts, const float* rays_o, const float* rays_d,
-                                               const float* z, int n_per_ray, long long idx, float scale,
-                                               float (&x)[3]) {
-  if (pts) { x[0] = pts[idx * 3]; x[1] = pts[idx * 3 + 1]; x[2] = pts[idx * 3 + 2]; }
-  else {
-    const long long ray = idx / n_per_ray;
-    const float zz = z[idx];
-    for (int c = 0; c < 3; ++c) x[c] = __fadd_rn(rays_o[ray * 3 + c], __fmul_rn(rays_d[ray * 3 + c], zz));
+// Cotangent scales (loss scaling of the fp16 backward).  The pull-back is jointly linear in
+// (ubar = dL/dudf, Gbar = dL/dgrad), but raw loss cotangents at production batch sizes sit far below the
+// fp16 range the stashes and MMA operands of the backward are held in (|Gbar| ~ 1e-8: the eikonal term would
+// flush to zero).  Two powers of two, computed on the device from the tensors' maxima (no host sync):
+//   S_g : the tangent DIRECTION is S_g Gbar (max |S_g Gbar| in [0.5,1)) -- tangent rows hdot ~ O(J);
+//   S_u : everything the reverse sweep accumulates is S_u dL/dtheta; the adjoint seed of the tangent output is
+//         S_u/S_g, that of the value output S_u ubar;  max(S_u |ubar|, S_u |Gbar|) in [1/8, 1/4).
+// scales[0..3] = {S_g, S_u, S_u/S_g, 1/S_u};  scales[4..5] = bit patterns of max|ubar|, max|Gbar| (scratch).
+__global__ void __launch_bounds__(256) cotangent_amax_kernel(const float* __restrict__ ubar,
+                                                             const float* __restrict__ gbar, long long P,
+                                                             unsigned int* __restrict__ amax_bits) {
+  float mu = 0.f, mg = 0.f;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < 3 * P; i += stride) {
+    if (gbar) mg = fmaxf(mg, fabsf(gbar[i]));      // fmaxf drops NaN: a NaN cotangent surfaces in the result
+    if (ubar && i < P) mu = fmaxf(mu, fabsf(ubar[i]));
   }
-  if (scale != 1.f) for (int c = 0; c < 3; ++c) x[c] = __fmul_rn(x[c], scale);
-}
-
-// U0[2P,64] fp16, reference PE column order (embedder.py:26-35), col >= pe zero.
-// rows [0,P): gamma(x);   rows [P,2P): J_gamma(x) . Gbar  (Gbar NULL -> zeros)
-__global__ void pe_dual_kernel(const float* pts, const float* rays_o, const float* rays_d, const float* z,
-                               int n_per_ray, long long P, float scale, int multires,
-                               const float* __restrict__ gbar, __half* __restrict__ U0) {
-  const long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (p >= P) return;
-  float x[3];
-  bwd_load_point(pts, rays_o, rays_d, z, n_per_ray, p, scale, x);
-  float g[3] = {0.f, 0.f, 0.f};
-  if (gbar) { g[0] = gbar[p * 3]; g[1] = gbar[p * 3 + 1]; g[2] = gbar[p * 3 + 2]; }
-  __half* rv = U0 + p * 64;
-  __half* rt = U0 + (P + p) * 64;
-  for (int c = 0; c < 3; ++c) { rv[c] = __float2half_rn(x[c]); rt[c] = __float2half_rn(g[c]); }
-  for (int j = 0; j < kMaxFreq; ++j) {
-    const float f = (float)(1 << j);
-    for (int c = 0; c < 3; ++c) {
-      float s = 0.f, co = 0.f, ts = 0.f, tc = 0.f;
-      if (j < multires) {
-        sincosf(x[c] * f, &s, &co);
-        ts = f * co * g[c];
-        tc = -f * s * g[c];
-      }
-      rv[3 + 6 * j + c] = __float2half_rn(s);      rt[3 + 6 * j + c] = __float2half_rn(ts);
-      rv[3 + 6 * j + 3 + c] = __float2half_rn(co); rt[3 + 6 * j + 3 + c] = __float2half_rn(tc);
-    }
+  for (int o = 16; o; o >>= 1) {
+    mu = fmaxf(mu, __shfl_xor_sync(0xffffffffu, mu, o));
+    mg = fmaxf(mg, __shfl_xor_sync(0xffffffffu, mg, o));
   }
-  rv[63] = __float2half_rn(0.f); rt[63] = __float2half_rn(0.f);
-}
-
-__device__ __forceinline__ float sp100(float a, float& sig) {
-  const float t = kSoftplusBeta * a;
-  const float e = __expf(-fabsf(t));
-  const float r = 1.0f / (1.0f + e);
-  sig = (t >= 0.f) ? r : e * r;
-  return (fmaxf(t, 0.f) + log1pf(e)) * 0.01f;
-}
-
-// Dual activation stage of layer l (l = 0..7):
-//   acc[2P, ld] fp32 = [U_l ; Udot_l] W_l^T   (rows [0,P) value, [P,2P) tangent), n_out valid columns
-//   -> Unext[2P,256] fp16 (h ; sigma*adot), sig[P,256] fp16, adot[P,256] fp16
-// For the skip layer (l == 3) columns [n_out, 256) of Unext receive the PE (U0 cols [0,pe)), and the
-// whole row is NOT scaled: the 1/sqrt(2) lives in the fp16 copy of W_4.
-__global__ void dual_act_fwd_kernel(const float* __restrict__ acc, int ld, const float* __restrict__ bias,
-                                    long long P, int n_out, const __half* __restrict__ U0, int pe,
-                                    __half* __restrict__ Unext, __half* __restrict__ sig_out,
-                                    __half* __restrict__ adot_out) {
-  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;   // over P*128 (2 cols each)
-  if (idx >= P * 128) return;
-  const long long p = idx >> 7;
-  const int c = (int)(idx & 127) * 2;
-  float hv[2], ht[2], sg[2], ad[2];
-#pragma unroll
-  for (int k = 0; k < 2; ++k) {
-    const int cc = c + k;
-    if (cc < n_out) {
-      const float a = acc[p * ld + cc] + bias[cc];
-      const float adot = acc[(P + p) * ld + cc];
-      float s;
-      hv[k] = sp100(a, s);
-      sg[k] = s; ad[k] = adot; ht[k] = s * adot;
-    } else {
-      const int q = cc - n_out;
-      hv[k] = (U0 && q < pe) ? __half2float(U0[p * 64 + q]) : 0.f;
-      ht[k] = (U0 && q < pe) ? __half2float(U0[(P + p) * 64 + q]) : 0.f;
-      sg[k] = 0.f; ad[k] = 0.f;
-    }
+  if ((threadIdx.x & 31) == 0) {                   // non-negative floats order like their bit patterns
+    atomicMax(amax_bits + 0, __float_as_uint(mu));
+    atomicMax(amax_bits + 1, __float_as_uint(mg));
   }
-  *reinterpret_cast<__half2*>(Unext + p * 256 + c) = __floats2half2_rn(hv[0], hv[1]);
-  *reinterpret_cast<__half2*>(Unext + (P + p) * 256 + c) = __floats2half2_rn(ht[0], ht[1]);
-  *reinterpret_cast<__half2*>(sig_out + p * 256 + c) = __floats2half2_rn(sg[0], sg[1]);
-  *reinterpret_cast<__half2*>(adot_out + p * 256 + c) = __floats2half2_rn(ad[0], ad[1]);
+}
+__host__ __device__ inline float pow2_scale(float amax, int target_exp) {
+  // power of two S with S * amax in [2^(target_exp-1), 2^target_exp); 1 for 0 / non-finite maxima
+  if (!(amax > 0.f) || !(amax < 3.0e38f)) return 1.f;
+  int e;
+  frexpf(amax, &e);                                // amax = m 2^e, m in [0.5, 1)
+  int k = target_exp - e;
+  if (k > 100) k = 100;
+  if (k < -100) k = -100;
+  return ldexpf(1.f, k);
+}
+__global__ void cotangent_scales_kernel(float* __restrict__ scales) {
+  const unsigned int* bits = reinterpret_cast<const unsigned int*>(scales + 4);
+  const float au = __uint_as_float(bits[0]), ag = __uint_as_float(bits[1]);
+  const float sg = pow2_scale(ag, 0);
+  const float su = pow2_scale(fmaxf(au, ag), -2);
+  scales[0] = sg; scales[1] = su; scales[2] = su / sg; scales[3] = 1.f / su;
 }
 
 // Output layer pull-back.  One warp per point:
-//   a8 = U8[p].w8 + b8, adot8 = U8[P+p].w8;  udf = f(a8)/scale, f in {abs, square, identity}
-//   alpha8 = ubar f'(a8)/scale + f''(a8) adot8 ;  alphadot8 = f'(a8)
-//   Eta8[p] = alpha8 * w8 ; Eta8[P+p] = alphadot8 * w8 ; coef[p] = alpha8 ; coef[P+p] = alphadot8
+//   a8 = U8[p].w8 + b8, adot8 = U8[P+p].w8 (tangent along S_g Gbar);  udf = f(a8)/scale, f in {abs, square, id}
+//   alpha8 = S_u ubar f'(a8)/scale + (S_u/S_g) f''(a8) adot8 ;  alphadot8 = (S_u/S_g) f'(a8)
+//   coef[p] = alpha8 ; coef[P+p] = alphadot8          (scales NULL: S_g = S_u = 1)
 __global__ void dual_top_kernel(const __half* __restrict__ U8, const float* __restrict__ w8,
-                                const float* __restrict__ b8p,
-                                const float* __restrict__ ubar, long long P, int udf_type, float scale,
-                                float* __restrict__ Eta8, float* __restrict__ coef) {
+                                const float* __restrict__ b8p, const float* __restrict__ ubar,
+                                const float* __restrict__ scales, long long P, int udf_type, float scale,
+                                float* __restrict__ coef) {
   const long long p = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   if (p >= P) return;
@@ -131,46 +87,9 @@ __global__ void dual_top_kernel(const __half* __restrict__ U8, const float* __re
   if (udf_type == 0) { f1 = (a > 0.f) ? 1.f : ((a < 0.f) ? -1.f : 0.f); f2 = 0.f; }
   else if (udf_type == 1) { f1 = 2.f * a; f2 = 2.f; }
   else { f1 = 1.f; f2 = 0.f; }
+  const float su = scales ? scales[1] : 1.f, sr = scales ? scales[2] : 1.f;
   const float ub = ubar ? ubar[p] : 0.f;
-  const float alpha = ub * f1 / scale + f2 * adot;
-  const float alphadot = f1;
-  if (Eta8) {
-    for (int c = lane; c < 256; c += 32) {
-      const float w = w8[c];
-      Eta8[p * 256 + c] = alpha * w;
-      Eta8[(P + p) * 256 + c] = alphadot * w;
-    }
-  }
-  if (lane == 0) { coef[p] = alpha; coef[P + p] = alphadot; }
-}
-
-// Reverse activation stage of layer l (l = 7..0):
-//   eta[2P, ld] fp32 (adjoints of h_{l+1}, hdot_{l+1}; `mul` folds the skip 1/sqrt(2)), n valid cols
-//   -> A[2P,256] fp16 = [alpha_l ; alphadot_l]   (columns >= n zero)
-__global__ void dual_act_bwd_kernel(const float* __restrict__ eta, int ld, float mul, long long P, int n,
-                                    const __half* __restrict__ sig, const __half* __restrict__ adot,
-                                    __half* __restrict__ A) {
-  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= P * 128) return;
-  const long long p = idx >> 7;
-  const int c = (int)(idx & 127) * 2;
-  float al[2] = {0.f, 0.f}, ad[2] = {0.f, 0.f};
-  const float2 sg = __half22float2(*reinterpret_cast<const __half2*>(sig + p * 256 + c));
-  const float2 at = __half22float2(*reinterpret_cast<const __half2*>(adot + p * 256 + c));
-  const float sgv[2] = {sg.x, sg.y}, atv[2] = {at.x, at.y};
-#pragma unroll
-  for (int k = 0; k < 2; ++k) {
-    const int cc = c + k;
-    if (cc < n) {
-      const float e = eta[p * ld + cc] * mul, ed = eta[(P + p) * ld + cc] * mul;
-      const float s = sgv[k];
-      const float sp2 = kSoftplusBeta * s * (1.0f - s);
-      al[k] = e * s + ed * atv[k] * sp2;
-      ad[k] = ed * s;
-    }
-  }
-  *reinterpret_cast<__half2*>(A + p * 256 + c) = __floats2half2_rn(al[0], al[1]);
-  *reinterpret_cast<__half2*>(A + (P + p) * 256 + c) = __floats2half2_rn(ad[0], ad[1]);
+  if (lane == 0) { coef[p] = su * ub * f1 / scale + sr * f2 * adot; coef[P + p] = sr * f1; }
 }
 
 // Weight-norm backward + scatter into the flat gradient (parameters() order: bias, g, v per layer):
@@ -184,6 +103,8 @@ struct WnBwdArgs {
   int ldw[kNumLinear];
   float mul[kNumLinear];
   int in_dim[kNumLinear], out_dim[kNumLinear];
+  const float* scales;        // cotangent scales of the sweep (scales[3] = 1/S_u) or NULL
+  int* status;                // optional: bit EMAP_STATUS_NONFINITE_GRAD is set when a gradient is not finite
 };
 __global__ void wn_bwd_kernel(const WnBwdArgs a) {
   int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -203,7 +124,8 @@ __global__ void wn_bwd_kernel(const WnBwdArgs a) {
   float* gg = gb + od;
   float* gv = gg + od + (size_t)row * id;
   const float* dW = a.dW[l] + (size_t)row * a.ldw[l];
-  const float mul = a.mul[l];
+  const float inv = a.scales ? a.scales[3] : 1.f;
+  const float mul = a.mul[l] * inv;
   double ss = 0.0, dot = 0.0;
   for (int k = lane; k < id; k += 32) { const double vv = v[k]; ss += vv * vv; dot += (double)(dW[k] * mul) * vv; }
   for (int o = 16; o; o >>= 1) {
@@ -212,9 +134,18 @@ __global__ void wn_bwd_kernel(const WnBwdArgs a) {
   }
   const double nrm = sqrt(ss);
   const float gi = g[row];
-  for (int k = lane; k < id; k += 32)
-    gv[k] = (float)((double)gi / nrm * ((double)(dW[k] * mul) - dot * (double)v[k] / ss));
-  if (lane == 0) { gg[row] = (float)(dot / nrm); gb[row] = a.db[l][row]; }
+  bool bad = false;
+  for (int k = lane; k < id; k += 32) {
+    const float o = (float)((double)gi / nrm * ((double)(dW[k] * mul) - dot * (double)v[k] / ss));
+    gv[k] = o;
+    bad |= !isfinite(o);
+  }
+  if (lane == 0) {
+    const float og = (float)(dot / nrm), ob = a.db[l][row] * inv;
+    gg[row] = og; gb[row] = ob;
+    bad |= !isfinite(og) || !isfinite(ob);
+  }
+  if (a.status && __any_sync(0xffffffffu, bad) && lane == 0) atomicOr(a.status, EMAP_STATUS_NONFINITE_GRAD);
 }
 
 // Bias gradients db_l[c] = sum_{p < P} A_l[p, c] over the VALUE rows of the eight [2P,256] fp16 stashes the
@@ -263,35 +194,27 @@ using namespace emap;
 
 static inline unsigned nblk(long long n, int t) { return (unsigned)((n + t - 1) / t); }
 
-extern "C" int emap_bwd_pe_dual(const emap_net_desc* net, const float* pts, const float* rays_o,
-                                const float* rays_d, const float* z, int32_t n_per_ray, int64_t P,
-                                const float* d_grad, void* U0_half, void* stream) {
-  if (check_net(net)) return 1;
-  if (!U0_half || P <= 0) return set_error("emap_bwd_pe_dual: bad arguments");
-  if (!pts && (!rays_o || !rays_d || !z || n_per_ray <= 0)) return set_error("emap_bwd_pe_dual: no points");
-  pe_dual_kernel<<<nblk(P, 128), 128, 0, (cudaStream_t)stream>>>(pts, rays_o, rays_d, z, n_per_ray, P,
-                                                                 net->scale, net->multires, d_grad,
-                                                                 (__half*)U0_half);
+extern "C" int emap_bwd_cotangent_scales(const float* d_udf, const float* d_grad, int64_t P, float* scales8,
+                                         void* stream) {
+  if (!scales8 || P <= 0) return set_error("emap_bwd_cotangent_scales: bad arguments");
+  cudaStream_t st = (cudaStream_t)stream;
+  EMAP_CUDA(cudaMemsetAsync(scales8 + 4, 0, 2 * sizeof(float), st));
+  int grid = 2 * sm_count();
+  const long long need = (3 * P + 255) / 256;
+  if (need < grid) grid = (int)need;
+  cotangent_amax_kernel<<<grid, 256, 0, st>>>(d_udf, d_grad, P, reinterpret_cast<unsigned int*>(scales8 + 4));
   EMAP_CUDA(cudaGetLastError());
-  return 0;
-}
-
-extern "C" int emap_bwd_act_fwd(const float* acc, int32_t ld, const float* bias, int64_t P, int32_t n_out,
-                                const void* U0_half, int32_t pe, void* Unext_half, void* sig_half,
-                                void* adot_half, void* stream) {
-  if (!acc || !bias || !Unext_half || !sig_half || !adot_half || P <= 0) return set_error("emap_bwd_act_fwd: bad arguments");
-  dual_act_fwd_kernel<<<nblk(P * 128, 256), 256, 0, (cudaStream_t)stream>>>(
-      acc, ld, bias, P, n_out, (const __half*)U0_half, pe, (__half*)Unext_half, (__half*)sig_half, (__half*)adot_half);
+  cotangent_scales_kernel<<<1, 1, 0, st>>>(scales8);
   EMAP_CUDA(cudaGetLastError());
   return 0;
 }
 
 extern "C" int emap_bwd_top(const emap_net_desc* net, const void* U8_half, const float* w8, const float* b8,
-                            const float* d_udf, int64_t P, float* Eta8, float* coef, void* stream) {
+                            const float* d_udf, const float* scales, int64_t P, float* coef, void* stream) {
   if (check_net(net)) return 1;
   if (!U8_half || !w8 || !b8 || !coef || P <= 0) return set_error("emap_bwd_top: bad arguments");
-  dual_top_kernel<<<nblk(P * 32, 256), 256, 0, (cudaStream_t)stream>>>((const __half*)U8_half, w8, b8, d_udf, P,
-                                                                       net->udf_type, net->scale, Eta8, coef);
+  dual_top_kernel<<<nblk(P * 32, 256), 256, 0, (cudaStream_t)stream>>>((const __half*)U8_half, w8, b8, d_udf, scales,
+                                                                       P, net->udf_type, net->scale, coef);
   EMAP_CUDA(cudaGetLastError());
   return 0;
 }
@@ -305,22 +228,14 @@ extern "C" int emap_bwd_bias_sums(const void* st_a_half, int64_t P, float* parti
   return 0;
 }
 
-extern "C" int emap_bwd_act_bwd(const float* eta, int32_t ld, float mul, int64_t P, int32_t n,
-                                const void* sig_half, const void* adot_half, void* A_half, void* stream) {
-  if (!eta || !sig_half || !adot_half || !A_half || P <= 0 || n > 256 || ld < n) return set_error("emap_bwd_act_bwd: bad arguments");
-  dual_act_bwd_kernel<<<nblk(P * 128, 256), 256, 0, (cudaStream_t)stream>>>(
-      eta, ld, mul, P, n, (const __half*)sig_half, (const __half*)adot_half, (__half*)A_half);
-  EMAP_CUDA(cudaGetLastError());
-  return 0;
-}
-
 extern "C" int emap_bwd_weight_norm(const emap_net_desc* net, const float* flat_params,
                                     const float* const* dW, const int32_t* ldw, const float* mul,
-                                    const float* const* db, float* flat_grad, void* stream) {
+                                    const float* const* db, const float* scales, float* flat_grad,
+                                    int32_t* status, void* stream) {
   if (check_net(net)) return 1;
   if (!flat_params || !dW || !ldw || !mul || !db || !flat_grad) return set_error("emap_bwd_weight_norm: NULL pointer");
   WnBwdArgs a;
-  a.flat = flat_params; a.flat_grad = flat_grad;
+  a.flat = flat_params; a.flat_grad = flat_grad; a.scales = scales; a.status = status;
   net_dims(net->multires, a.in_dim, a.out_dim);
   int rows = 0;
   for (int l = 0; l < kNumLinear; ++l) {

@@ -27,6 +27,7 @@ struct MlpArgs {
   float* pe_out;
   // MODE_DUAL (backward recompute): cotangent direction + fp16 stashes for the reverse sweep / dW GEMMs
   const float* gbar;    // [P,3] dL/d(grad udf) or NULL (zero tangent)
+  const float* bwd_scales;   // cotangent scales (emap_bwd_cotangent_scales) or NULL: tangent direction = scales[0] * gbar
   __half* st_u0;        // [2P,64]  dual PE in kernel column order (rows [0,P) value, [P,2P) tangent)
   __half* st_u;         // [8][2P,256] inputs of layers 1..8 (h ; hdot).  This is the ONLY per-layer stash:
                         // sigma_l = 1 - exp(-100 h_{l+1}) and adot_l * softplus''(a_l) = 100 hdot_{l+1} (1 - sigma_l)

@@ -320,7 +320,8 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_kernel(const MlpArgs args) {
       float gb[3] = {0.f, 0.f, 0.f};
       if (MODE >= 2 && args.gbar) {
         const long long pc = (pt < args.P) ? pt : args.P - 1;
-        gb[0] = args.gbar[pc * 3]; gb[1] = args.gbar[pc * 3 + 1]; gb[2] = args.gbar[pc * 3 + 2];
+        const float sg = args.bwd_scales ? __ldg(args.bwd_scales) : 1.f;     // power of two (loss scaling)
+        gb[0] = sg * args.gbar[pc * 3]; gb[1] = sg * args.gbar[pc * 3 + 1]; gb[2] = sg * args.gbar[pc * 3 + 2];
       }
       if (sub < 2) {
         if (sub == 0) pe_stage<NTERMS, MODE, T, 0>(args, x, multires, lane, row, pt, tile, true, A_hi, A_lo, gb);
@@ -729,14 +730,14 @@ extern "C" int emap_udf_forward_grad(const emap_net_desc* net, const void* packe
 extern "C" int emap_bwd_dual_forward(const emap_net_desc* net, const void* packed, int precision,
                                      const float* pts, const float* rays_o, const float* rays_d,
                                      const float* z, int32_t n_per_ray, int64_t P, const float* d_grad,
-                                     void* st_u0, void* st_u, void* stream) {
+                                     const float* scales, void* st_u0, void* st_u, void* stream) {
   if (check_net(net)) return 1;
   if (!packed || !st_u0 || !st_u) return set_error("emap_bwd_dual_forward: NULL pointer");
   if (check_points(pts, rays_o, rays_d, z, n_per_ray, P)) return 1;
   MlpArgs a;
   memset(&a, 0, sizeof(a));
   a.packed = (const uint8_t*)packed; a.pts = pts; a.rays_o = rays_o; a.rays_d = rays_d; a.z = z;
-  a.n_per_ray = n_per_ray; a.P = P; a.gbar = d_grad;
+  a.n_per_ray = n_per_ray; a.P = P; a.gbar = d_grad; a.bwd_scales = scales;
   a.st_u0 = (__half*)st_u0; a.st_u = (__half*)st_u;
   return dispatch<2>(net, precision, a, (cudaStream_t)stream);
 }
@@ -746,15 +747,15 @@ extern "C" int emap_bwd_dual_forward(const emap_net_desc* net, const void* packe
 // one row per point (128 points per tile), no softplus -- about half the work of the dual forward.
 extern "C" int emap_bwd_tangent_forward(const emap_net_desc* net, const void* packed, const float* pts,
                                         const float* rays_o, const float* rays_d, const float* z,
-                                        int32_t n_per_ray, int64_t P, const float* d_grad, void* st_u0,
-                                        void* st_u, void* stream) {
+                                        int32_t n_per_ray, int64_t P, const float* d_grad,
+                                        const float* scales, void* st_u0, void* st_u, void* stream) {
   if (check_net(net)) return 1;
   if (!packed || !st_u0 || !st_u) return set_error("emap_bwd_tangent_forward: NULL pointer");
   if (check_points(pts, rays_o, rays_d, z, n_per_ray, P)) return 1;
   MlpArgs a;
   memset(&a, 0, sizeof(a));
   a.packed = (const uint8_t*)packed; a.pts = pts; a.rays_o = rays_o; a.rays_d = rays_d; a.z = z;
-  a.n_per_ray = n_per_ray; a.P = P; a.gbar = d_grad;
+  a.n_per_ray = n_per_ray; a.P = P; a.gbar = d_grad; a.bwd_scales = scales;
   a.st_u0 = (__half*)st_u0; a.st_u = (__half*)st_u;
   // single-MMA, one CTA per SM, no cluster variants: the only configuration this mode is built for
   if (net->elem_type == 0) return launch<1, 3, __half, 1>(a, (cudaStream_t)stream);

@@ -125,6 +125,7 @@ struct UpsampleArgs {
   float inv_s, beta, gamma;
   int mode;        // 0 unbias (occlusion aware), 1 no_occ_aware, 2 weights given (sample_pdf only)
   int alpha_type;  // 0 numerical, 1 theorical
+  int* status;     // optional device status word: EMAP_STATUS_NAN_SAMPLES when a new sample is NaN (:102, :346)
 };
 
 __global__ void __launch_bounds__(kRayWarps * 32) upsample_step_kernel(const UpsampleArgs a) {
@@ -280,6 +281,9 @@ __global__ void __launch_bounds__(kRayWarps * 32) upsample_step_kernel(const Ups
     int rank = 0;
     for (int t = 0; t < k; ++t) { const float o = zn[t]; rank += (o < v || (o == v && t < j)) ? 1 : 0; }
     a.z_new[(size_t)ray * k + rank] = v;
+    // the reference's NaN guard on the new samples (pdb.set_trace() at :102-107 and :346-351): a device flag
+    // the host polls once per step.  (A NaN ranks 0 like every NaN here; the flag is what matters.)
+    if (a.status && v != v) atomicOr(a.status, EMAP_STATUS_NAN_SAMPLES);
   }
 }
 
@@ -409,7 +413,8 @@ __global__ void __launch_bounds__(kRayWarps * 32) render_core_fwd_kernel(const C
 
 // Deterministic reduction of the per-ray partial sums -> [gradient_error, gradient_error_near_surface,
 // sparse_error, sum_relax, sum_near]                                             (:618-625, :642-644)
-__global__ void render_reduce_kernel(const double* __restrict__ partials, int B, float* __restrict__ out) {
+__global__ void render_reduce_kernel(const double* __restrict__ partials, int B, float* __restrict__ out,
+                                     int* __restrict__ status) {
   __shared__ double sh[5][32];
   double acc[5] = {0, 0, 0, 0, 0};
   for (int r = threadIdx.x; r < B; r += blockDim.x)
@@ -429,6 +434,8 @@ __global__ void render_reduce_kernel(const double* __restrict__ partials, int B,
     out[2] = (float)(t[4] / (double)B);
     out[3] = sr;
     out[4] = sn;
+    // the reference's guard on gradient_error (:632-633)
+    if (status && out[0] != out[0]) atomicOr(status, EMAP_STATUS_NAN_EIKONAL);
   }
 }
 
@@ -740,7 +747,7 @@ extern "C" int emap_upsample_step(const float* rays_o, const float* rays_d, cons
                                   const float* u, int32_t k, float* z_new, int64_t* inds_out,
                                   float* weights_out, const float* sample_dist, int32_t B, float inv_s,
                                   float beta, float gamma, const float* gamma_dev, int32_t mode,
-                                  int32_t alpha_type, void* stream) {
+                                  int32_t alpha_type, int32_t* status, void* stream) {
   if (!z_in || B <= 0 || n <= 0) return set_error("emap_upsample_step: bad arguments");
   if (n + ka > kMaxSamples) return set_error("emap_upsample_step: more than %d samples per ray", kMaxSamples);
   if (k > kMaxNew || ka > kMaxNew) return set_error("emap_upsample_step: more than %d new samples per step", kMaxNew);
@@ -755,7 +762,7 @@ extern "C" int emap_upsample_step(const float* rays_o, const float* rays_d, cons
   a.z_add = z_add; a.udf_add = udf_add; a.ka = ka; a.z_out = z_out; a.udf_out = udf_out;
   a.u = u; a.z_new = z_new; a.inds = (long long*)inds_out; a.w_out = weights_out;
   a.sample_dist = sample_dist; a.gamma_ptr = gamma_dev; a.B = B; a.k = k; a.inv_s = inv_s; a.beta = beta; a.gamma = gamma;
-  a.mode = mode; a.alpha_type = alpha_type;
+  a.mode = mode; a.alpha_type = alpha_type; a.status = status;
   upsample_step_kernel<<<(B + kRayWarps - 1) / kRayWarps, kRayWarps * 32, 0, (cudaStream_t)stream>>>(a);
   EMAP_CUDA(cudaGetLastError());
   return 0;
@@ -777,7 +784,7 @@ extern "C" int emap_render_core_fwd(const float* rays_o, const float* rays_d, co
                                     int32_t use_unbias, int32_t use_norm_grad, int32_t alpha_type,
                                     float* weights, float* alpha, float* grad_flip, float* inside_sphere,
                                     float* grad_mag, float* edge, float* depth, float* normals,
-                                    double* partials, float* reduced, void* stream) {
+                                    double* partials, float* reduced, int32_t* status, void* stream) {
   if (!rays_o || !rays_d || !mid_z || !dists || !udf || !grad || !scalars || !weights || !grad_flip ||
       !inside_sphere || !grad_mag || !edge || !depth || !normals || !partials || !reduced)
     return set_error("emap_render_core_fwd: NULL pointer");
@@ -792,7 +799,7 @@ extern "C" int emap_render_core_fwd(const float* rays_o, const float* rays_d, co
   cudaStream_t st = (cudaStream_t)stream;
   render_core_fwd_kernel<<<(B + kRayWarps - 1) / kRayWarps, kRayWarps * 32, 0, st>>>(a);
   EMAP_CUDA(cudaGetLastError());
-  render_reduce_kernel<<<1, 1024, 0, st>>>(partials, B, reduced);
+  render_reduce_kernel<<<1, 1024, 0, st>>>(partials, B, reduced, status);
   EMAP_CUDA(cudaGetLastError());
   return 0;
 }

@@ -14,6 +14,72 @@ import torch
 from . import _cabi as C
 
 
+# ----------------------------------------------------------------------------- device status word
+# The reference guards its hot path with NaN checks that drop into pdb (udf_renderer_blending.py:102-107,
+# :346-351, :632-633) -- each a device->host sync.  Here the kernels OR bits into one int32 per device
+# (include/emap_b200.h: EMAP_STATUS_*) and the host polls it lazily: poll_status() never blocks (it reads the
+# copy enqueued by the previous poll once that has landed), check_status() synchronises.  Both raise
+# FloatingPointError naming the stage and clear the word.
+STATUS_BITS = {1: "NaN among the new z samples of an up-sampling step (sample_pdf / up_sample)",
+               2: "NaN gradient_error in render_core",
+               4: "non-finite parameter gradient out of the MLP backward"}
+_STATUS = {}
+
+
+class _Status:
+    def __init__(self, dev):
+        self.word = torch.zeros(1, dtype=torch.int32, device=dev)
+        self.host = None                      # pinned landing buffer of the lazy poll, made on first use
+        self.event = None
+
+
+def _status(dev) -> _Status:
+    dev = torch.device(dev)
+    key = (dev.type, dev.index if (dev.index is not None or dev.type != "cuda") else torch.cuda.current_device())
+    st = _STATUS.get(key)
+    if st is None:
+        st = _STATUS[key] = _Status(dev)
+    return st
+
+
+def status_word(dev) -> torch.Tensor:
+    return _status(dev).word
+
+
+def _raise_status(st: _Status, bits: int):
+    st.word.zero_()
+    st.event = None
+    what = "; ".join(msg for b, msg in STATUS_BITS.items() if bits & b) or f"status {bits}"
+    raise FloatingPointError("emap_b200: " + what)
+
+
+def poll_status(dev) -> None:
+    """Non-blocking: raise if the copy enqueued by the previous poll has landed with a bit set, then enqueue
+    the next copy (4 bytes, pinned, on the current stream)."""
+    st = _status(dev)
+    if torch.cuda.is_current_stream_capturing():
+        return
+    if st.event is not None and st.event.query():
+        bits = int(st.host[0])
+        st.event = None
+        if bits:
+            _raise_status(st, bits)
+    if st.event is None:
+        if st.host is None:
+            st.host = torch.zeros(1, dtype=torch.int32).pin_memory()
+        st.host.copy_(st.word, non_blocking=True)
+        st.event = torch.cuda.Event()
+        st.event.record()
+
+
+def check_status(dev) -> None:
+    """Blocking check (one 4-byte device->host read)."""
+    st = _status(dev)
+    bits = int(st.word.item())
+    if bits:
+        _raise_status(st, bits)
+
+
 def net_dims(multires: int):
     pe = 3 + 6 * multires
     in_dim = [pe] + [256] * 8
@@ -37,6 +103,21 @@ class PackedNet:
             C.check(1)
         self.packed = torch.empty(nbytes, dtype=torch.uint8, device=self.device)
 
+    def backward_net(self) -> "PackedNet":
+        """The operand pack the backward kernels use: fp16 images.  A bf16 network keeps a second, fp16 pack of
+        the same parameters for it (re-folded when the parameters change): bf16 forward, fp16 backward."""
+        if self.desc.elem_type == 0:
+            return self
+        bn = getattr(self, "_bwd_net", None)
+        if bn is None:
+            bn = PackedNet(self.multires, [k for k, v in C.UDF_TYPES.items() if v == self.desc.udf_type][0],
+                           float(self.desc.scale), "fp16", self.device)
+            self._bwd_net = bn
+        if getattr(bn, "src_fold_id", None) != self.fold_id:
+            bn.fold(self.flat)
+            bn.src_fold_id = self.fold_id
+        return bn
+
     def fold(self, flat_params: torch.Tensor) -> None:
         """K0: W = g v/||v||, split/pack into tcgen05 operand images (once per optimizer step)."""
         flat_params = C.f32(flat_params)
@@ -45,6 +126,8 @@ class PackedNet:
                                f"expected {self.n_params}")
         C.check(C.lib().emap_wn_fold(ctypes.byref(self.desc), C.ptr(flat_params), C.ptr(self.packed),
                                      C.stream()))
+        self.flat = flat_params                         # kept for the backward (bias / g / v reads)
+        self.fold_id = getattr(self, "fold_id", 0) + 1
 
 
 def _points_args(pts, rays_o, rays_d, z):
@@ -234,7 +317,8 @@ def upsample_step(rays_o, rays_d, z_in, udf_in, z_add, udf_add, u, k, sample_dis
         C.ptr(None if z_add is None else C.f32(z_add)), C.ptr(None if udf_add is None else C.f32(udf_add)),
         ka, C.ptr(z_out), C.ptr(udf_out), C.ptr(u), k, C.ptr(z_new), C.ptr(inds), C.ptr(w),
         C.ptr(sample_dist), B, float(inv_s), float(beta), float(gamma),
-        C.ptr(None if gamma_dev is None else C.f32(gamma_dev)), int(mode), int(alpha_type), C.stream()))
+        C.ptr(None if gamma_dev is None else C.f32(gamma_dev)), int(mode), int(alpha_type),
+        C.ptr(status_word(dev)), C.stream()))
     z_cur = z_out if ka > 0 else z_in
     udf_cur = udf_out if ka > 0 else udf_in
     return z_cur, udf_cur, z_new, inds, w
@@ -278,7 +362,7 @@ def render_core_fwd(rays_o, rays_d, mid_z, dists, udf, grad, scalars, B, n, cfg,
         cfg["near_surface"], cfg["sparse_scale"], cfg["use_unbias"], cfg["use_norm_grad"],
         cfg["alpha_type"], C.ptr(weights), C.ptr(alpha), C.ptr(grad_flip), C.ptr(inside),
         C.ptr(grad_mag), C.ptr(edge), C.ptr(depth), C.ptr(normals), C.ptr(partials), C.ptr(reduced),
-        C.stream()))
+        C.ptr(status_word(dev)), C.stream()))
     return weights, alpha, grad_flip, inside, grad_mag, edge, depth, normals, reduced
 
 
@@ -319,26 +403,6 @@ def _weff_views(net: PackedNet):
     return W, in_dim, out_dim
 
 
-def _half_weights(net: PackedNet, fold_id):
-    """fp16 copies of W_eff for the library GEMMs of the backward (re-made after each fold):
-    layer 0 padded to K=64, layer 3 padded to 256 rows, layer 4 carries the skip 1/sqrt(2)."""
-    if getattr(net, "_wh_id", None) == fold_id and getattr(net, "_wh", None) is not None:
-        return net._wh
-    W, in_dim, out_dim = _weff_views(net)
-    dev = net.packed.device
-    wh = []
-    for l in range(8):
-        w = W[l]
-        if l == 4:
-            w = w * (1.0 / (2.0 ** 0.5))
-        k = 64 if l == 0 else 256
-        t = torch.zeros(256, k, dtype=torch.float16, device=dev)
-        t[:out_dim[l], :in_dim[l]] = w.to(torch.float16)
-        wh.append(t)
-    net._wh, net._wh_id = wh, fold_id
-    return wh
-
-
 _PE_PERM = {}
 
 
@@ -371,14 +435,12 @@ def udf_backward(net: PackedNet, precision: int, d_udf: Optional[torch.Tensor],
                  flat_params: Optional[torch.Tensor] = None, stash=None) -> torch.Tensor:
     """Pull the cotangents (d_udf[P], d_grad[P,3]) back to the flat parameter gradient.
 
-    Fused path (default; fp16 operand images): dual forward with stashes and the reverse sweep are two
-    tcgen05 kernels on the K1 skeleton; the 9 weight-gradient contractions dW_l = A_l^T U_l are plain
-    library GEMMs.  EMAP_BWD=layerwise selects the round-1 layer-by-layer structure (kept as a
-    cross-check: element-wise kernels + a library GEMM per layer and direction)."""
-    import os
-    if stash is None and (net.desc.elem_type != 0 or os.environ.get("EMAP_BWD") == "layerwise"):
-        return udf_backward_layerwise(net, precision, d_udf, d_grad, pts, rays_o, rays_d, z, flat_params)
+    fp16 operand images and stashes, fp32 accumulation, loss-scaled on the device
+    (emap_bwd_cotangent_scales): [tangent forward | dual forward] -> output-layer pull-back -> reverse sweep
+    (tcgen05 kernels on the K1 skeleton) -> the nine weight-gradient contractions dW_l = A_l^T U_l -> bias
+    sums -> weight-norm backward, which removes the loss scale and flags non-finite gradients."""
     L = C.lib()
+    net = net.backward_net()
     pts, ro, rd, zz, n, P = _points_args(pts, rays_o, rays_d, z)
     dev = net.packed.device
     if flat_params is None:
@@ -393,23 +455,28 @@ def udf_backward(net: PackedNet, precision: int, d_udf: Optional[torch.Tensor],
     for l in range(9):
         boff.append(off)
         off += out_dim[l] * (2 + in_dim[l])
+    d_udf = None if d_udf is None else C.f32(d_udf)
+    d_grad = None if d_grad is None else C.f32(d_grad)
 
+    scales = None
+    if os.environ.get("EMAP_BWD_NOSCALE") != "1":          # (diagnostic switch: what round 1 did, raw cotangents)
+        scales = torch.empty(8, dtype=torch.float32, device=dev)
+        C.check(L.emap_bwd_cotangent_scales(C.ptr(d_udf), C.ptr(d_grad), P, C.ptr(scales), st))
     st_a = h16(8, 2 * P, 256)
     if stash is not None:
         # value rows written by the training forward (K1r): add the tangent rows only
         st_u0, st_u = stash
         C.check(L.emap_bwd_tangent_forward(desc, C.ptr(net.packed), C.ptr(pts), C.ptr(ro), C.ptr(rd), C.ptr(zz),
-                                           n, P, C.ptr(None if d_grad is None else C.f32(d_grad)),
-                                           C.ptr(st_u0), C.ptr(st_u), st))
+                                           n, P, C.ptr(d_grad), C.ptr(scales), C.ptr(st_u0), C.ptr(st_u), st))
     else:
         st_u0, st_u = h16(2 * P, 64), h16(8, 2 * P, 256)
         C.check(L.emap_bwd_dual_forward(desc, C.ptr(net.packed), C.PREC_HALF, C.ptr(pts), C.ptr(ro), C.ptr(rd),
-                                        C.ptr(zz), n, P, C.ptr(None if d_grad is None else C.f32(d_grad)),
-                                        C.ptr(st_u0), C.ptr(st_u), st))
+                                        C.ptr(zz), n, P, C.ptr(d_grad), C.ptr(scales), C.ptr(st_u0),
+                                        C.ptr(st_u), st))
     coef = torch.empty(2 * P, dtype=torch.float32, device=dev)
     U8 = st_u[7]
     C.check(L.emap_bwd_top(desc, C.ptr(U8), C.ptr(W[8].reshape(-1)), C.ptr(flat_params[boff[8]:boff[8] + 1]),
-                           C.ptr(None if d_udf is None else C.f32(d_udf)), P, None, C.ptr(coef), st))
+                           C.ptr(d_udf), C.ptr(scales), P, C.ptr(coef), st))
     C.check(L.emap_bwd_reverse_sweep(desc, C.ptr(net.packed), C.ptr(coef), C.ptr(st_u), C.ptr(st_a), P, st))
     cols, refs = _pe_perm(net.multires, dev)
     dW, db = [None] * 9, [None] * 9
@@ -435,73 +502,14 @@ def udf_backward(net: PackedNet, precision: int, d_udf: Optional[torch.Tensor],
             dW[4] = d4
         else:
             dW[l] = torch.mm(A.t(), st_u[l - 1], out_dtype=torch.float32)
-    flat_grad = torch.empty_like(flat_params)
+    # (+ spare tail: parallel.FlatGradAllReduce parks the few foreign gradients there and all-reduces in place)
+    flat_grad = torch.empty(flat_params.numel() + 32, dtype=torch.float32, device=dev)[:flat_params.numel()]
     dW_p = (ctypes.c_void_p * 9)(*[t.data_ptr() for t in dW])
     db_p = (ctypes.c_void_p * 9)(*[t.data_ptr() for t in db])
     ldw = (ctypes.c_int32 * 9)(*[t.shape[1] for t in dW])
     mul = (ctypes.c_float * 9)(*[(2.0 ** -0.5) if l == 4 else 1.0 for l in range(9)])
-    C.check(L.emap_bwd_weight_norm(desc, C.ptr(flat_params), dW_p, ldw, mul, db_p, C.ptr(flat_grad), st))
-    return flat_grad
-
-
-def udf_backward_layerwise(net: PackedNet, precision: int, d_udf: Optional[torch.Tensor],
-                           d_grad: Optional[torch.Tensor], pts=None, rays_o=None, rays_d=None, z=None,
-                           flat_params: Optional[torch.Tensor] = None) -> torch.Tensor:
-    """Round-1 structure of the backward (see udf_backward)."""
-    L = C.lib()
-    pts, ro, rd, zz, n, P = _points_args(pts, rays_o, rays_d, z)
-    dev = net.packed.device
-    if flat_params is None:
-        raise RuntimeError("udf_backward needs the flat parameter buffer")
-    flat_params = C.f32(flat_params)
-    W, in_dim, out_dim = _weff_views(net)
-    wh = _half_weights(net, getattr(net, "fold_id", 0))
-    pe = 3 + 6 * net.multires
-    h16 = lambda *s: torch.empty(*s, dtype=torch.float16, device=dev)  # noqa: E731
-    st = C.stream()
-    desc = ctypes.byref(net.desc)
-    # bias views inside the flat parameter buffer
-    boff, off = [], 0
-    for l in range(9):
-        boff.append(off)
-        off += out_dim[l] * (2 + in_dim[l])
-
-    U = [h16(2 * P, 64)]
-    C.check(L.emap_bwd_pe_dual(desc, C.ptr(pts), C.ptr(ro), C.ptr(rd), C.ptr(zz), n, P,
-                               C.ptr(None if d_grad is None else C.f32(d_grad)), C.ptr(U[0]), st))
-    sig, adot = [], []
-    for l in range(8):
-        acc = torch.mm(U[l], wh[l].t(), out_dtype=torch.float32)            # library GEMM [2P,256]
-        un, sg, ad = h16(2 * P, 256), h16(P, 256), h16(P, 256)
-        bias = flat_params[boff[l]:boff[l] + out_dim[l]]
-        C.check(L.emap_bwd_act_fwd(C.ptr(acc), 256, C.ptr(bias), P, out_dim[l],
-                                   C.ptr(U[0]) if l == 3 else None, pe, C.ptr(un), C.ptr(sg), C.ptr(ad), st))
-        U.append(un); sig.append(sg); adot.append(ad)
-        del acc
-    eta = torch.empty(2 * P, 256, dtype=torch.float32, device=dev)
-    coef = torch.empty(2 * P, dtype=torch.float32, device=dev)
-    w8 = W[8].reshape(-1)
-    b8 = flat_params[boff[8]:boff[8] + 1]
-    C.check(L.emap_bwd_top(desc, C.ptr(U[8]), C.ptr(w8), C.ptr(b8),
-                           C.ptr(None if d_udf is None else C.f32(d_udf)), P, C.ptr(eta), C.ptr(coef), st))
-    dW = [None] * 9
-    db = [None] * 9
-    dW[8] = torch.mm(coef.to(torch.float16).view(1, 2 * P), U[8], out_dtype=torch.float32)   # [1,256]
-    db[8] = coef[:P].sum().reshape(1)
-    A = h16(2 * P, 256)
-    for l in range(7, -1, -1):
-        C.check(L.emap_bwd_act_bwd(C.ptr(eta), 256, 1.0, P, out_dim[l], C.ptr(sig[l]), C.ptr(adot[l]),
-                                   C.ptr(A), st))
-        dW[l] = torch.mm(A.t(), U[l], out_dtype=torch.float32)                 # [256, 64|256]
-        db[l] = A[:P].sum(dim=0, dtype=torch.float32)
-        if l > 0:
-            eta = torch.mm(A, wh[l], out_dtype=torch.float32)                  # [2P,256]
-    flat_grad = torch.empty_like(flat_params)
-    dW_p = (ctypes.c_void_p * 9)(*[t.data_ptr() for t in dW])
-    db_p = (ctypes.c_void_p * 9)(*[t.data_ptr() for t in db])
-    ldw = (ctypes.c_int32 * 9)(*[t.shape[1] for t in dW])
-    mul = (ctypes.c_float * 9)(*[(2.0 ** -0.5) if l == 4 else 1.0 for l in range(9)])
-    C.check(L.emap_bwd_weight_norm(desc, C.ptr(flat_params), dW_p, ldw, mul, db_p, C.ptr(flat_grad), st))
+    C.check(L.emap_bwd_weight_norm(desc, C.ptr(flat_params), dW_p, ldw, mul, db_p, C.ptr(scales),
+                                   C.ptr(flat_grad), C.ptr(status_word(dev)), st))
     return flat_grad
 
 

@@ -43,8 +43,18 @@ def shard_rays(tensors: Sequence[torch.Tensor], rank: Optional[int] = None,
     return [t[lo:hi].contiguous() for t in tensors]
 
 
+GRAD_ARENA_SLACK = 32     # spare floats ops.udf_backward leaves behind its flat gradient for foreign gradients
+
+
 class FlatGradAllReduce:
-    """Average the gradients of ``params`` across ranks with ONE all-reduce of one flat buffer."""
+    """Average the gradients of ``params`` across ranks with ONE all-reduce of one flat buffer.
+
+    The MLP backward (ops.udf_backward) returns all 462,980 gradients as ONE flat buffer and autograd hands the
+    per-parameter views of it to ``p.grad`` without copying, so that buffer (the "arena") is all-reduced IN
+    PLACE: the few gradients that live elsewhere (variance, beta, gamma, ...: 5 floats) are copied into the
+    arena's spare tail with one batched copy and back with another.  Parameters whose gradients do not share
+    an arena (any other model) fall back to packing into an own flat buffer with batched copies.  Either way:
+    one collective, no per-parameter launches."""
 
     def __init__(self, params: Iterable[torch.nn.Parameter], group=None):
         self.params = [p for p in params]
@@ -52,39 +62,103 @@ class FlatGradAllReduce:
         self.numel = sum(p.numel() for p in self.params)
         self._flat: Optional[torch.Tensor] = None
 
+    # -- layout -------------------------------------------------------------------------------
+    def _arena(self, grads: List[Optional[torch.Tensor]]):
+        """(k, n): grads[0..k) tile one storage back to back (n elements from its storage offset 0..)."""
+        g0 = grads[0] if grads else None
+        if g0 is None or not g0.is_contiguous():
+            return 0, 0
+        base = g0.untyped_storage().data_ptr()
+        start = g0.storage_offset()
+        k, n = 0, 0
+        for g in grads:
+            if (g is None or not g.is_contiguous() or g.dtype != g0.dtype
+                    or g.untyped_storage().data_ptr() != base or g.storage_offset() != start + n):
+                break
+            k += 1
+            n += g.numel()
+        return (k, n) if k > 1 else (0, 0)
+
     def flat_grads(self) -> torch.Tensor:
+        """All gradients packed into an own flat buffer (missing ones as zeros) -- the fallback layout."""
         ps = self.params
         dev, dt = ps[0].device, ps[0].dtype
         if self._flat is None or self._flat.device != dev:
             self._flat = torch.zeros(self.numel, dtype=dt, device=dev)
-        off = 0
+        views, srcs, off = [], [], 0
         for p in ps:
             n = p.numel()
             if p.grad is None:
                 self._flat[off:off + n].zero_()
             else:
-                self._flat[off:off + n].copy_(p.grad.reshape(-1))
+                views.append(self._flat[off:off + n].view_as(p))
+                srcs.append(p.grad)
             off += n
+        if views:
+            torch._foreach_copy_(views, srcs)
         return self._flat
 
     def scatter_(self, flat: torch.Tensor) -> None:
-        off = 0
+        dsts, srcs, off = [], [], 0
         for p in self.params:
             n = p.numel()
             if p.grad is not None:
-                p.grad.copy_(flat[off:off + n].view_as(p))
+                dsts.append(p.grad)
+                srcs.append(flat[off:off + n].view_as(p))
             elif p.requires_grad:
                 p.grad = flat[off:off + n].view_as(p).clone()
             off += n
+        if dsts:
+            torch._foreach_copy_(dsts, srcs)
 
-    def allreduce_(self) -> None:
+    # -- the exchange step -------------------------------------------------------------------
+    def allreduce_(self, local_weight: float = 1.0) -> None:
+        """SUM over ranks of local_weight * grad, divided by the world size.  local_weight = 1 is the plain
+        average (equal shards); for unequal ray shards pass B_local * W / B_global (``shard_weight``) so that
+        per-shard means (mse, sparse error) combine to the mean over the whole batch."""
         _, w = world()
-        if w == 1:
+        if w == 1 and local_weight == 1.0:
             return
+        grads = [p.grad for p in self.params]
+        k, n = self._arena(grads)
+        if k:
+            g0 = grads[0]
+            rest = [g for g in grads[k:] if g is not None]
+            extra = sum(g.numel() for g in rest)
+            cap = g0.untyped_storage().nbytes() // g0.element_size() - g0.storage_offset()
+            if n + extra <= cap and all(g.dtype == g0.dtype and g.device == g0.device for g in rest):
+                buf = torch.empty(0, dtype=g0.dtype, device=g0.device).set_(
+                    g0.untyped_storage(), g0.storage_offset(), (n + extra,))
+                tails, off = [], n
+                for g in rest:
+                    tails.append(buf[off:off + g.numel()].view_as(g))
+                    off += g.numel()
+                if rest:
+                    torch._foreach_copy_(tails, rest)
+                if local_weight != 1.0:
+                    buf.mul_(float(local_weight))
+                if w > 1:
+                    dist.all_reduce(buf, op=dist.ReduceOp.SUM, group=self.group)
+                    buf.div_(w)
+                if rest:
+                    torch._foreach_copy_(rest, tails)
+                return
         flat = self.flat_grads()
-        dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=self.group)
-        flat.div_(w)
+        if local_weight != 1.0:
+            flat.mul_(float(local_weight))
+        if w > 1:
+            dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=self.group)
+            flat.div_(w)
         self.scatter_(flat)
+
+
+def shard_weight(local_rays: int, global_rays: int, world_size: Optional[int] = None) -> float:
+    """Weight of this rank's gradient for exact whole-batch means with unequal ray shards: per-shard means
+    (mse, sparse_error: / B_local) averaged over W ranks equal the batch mean iff each is weighted by
+    B_local * W / B_global (1.0 for equal shards)."""
+    _, w = world()
+    w = w if world_size is None else world_size
+    return float(local_rays) * w / float(global_rays)
 
 
 def global_denominators(local_sums: torch.Tensor, group=None) -> torch.Tensor:

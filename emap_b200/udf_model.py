@@ -115,9 +115,7 @@ class UDFNetwork(nn.Module):
         if ver != self._folded_version:
             with torch.no_grad():
                 flat = torch.cat([p.detach().reshape(-1) for p in ps])
-            self._net.fold(flat)
-            self._net.flat = flat                      # kept for the backward (bias / g / v reads)
-            self._net.fold_id = getattr(self._net, "fold_id", 0) + 1
+            self._net.fold(flat)                       # (keeps `flat` for the backward, bumps fold_id)
             self._folded_version = ver
         return self._net
 

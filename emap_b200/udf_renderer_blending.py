@@ -10,7 +10,10 @@ CUDA kernel behind the C ABI:
     render_core         emap_render_prep -> emap_udf_forward_grad -> emap_render_core_fwd (:418-677)
 
 The reference's 12 host syncs per call (NaN checks that drop into pdb, ``.item()``) are gone: nothing
-in ``render()`` synchronises with the device.
+in ``render()`` synchronises with the device.  Its NaN guards (:102-107, :346-351, :632-633) became a device
+status word the kernels OR into: ``render()`` polls it without blocking (a NaN raises ``FloatingPointError``
+at the next call at the latest), ``check_numerics()`` is the blocking check for callers that synchronise
+anyway (the reference runner does, once per iteration: ``runner_udf.py:164``).
 """
 from __future__ import annotations
 
@@ -65,6 +68,11 @@ class UDFRendererBlending:
         self._const_cache: Dict = {}
         # multi-GPU: make the two eikonal means those of the whole (sharded) batch (parallel.py)
         self.global_batch_stats = False
+
+    def check_numerics(self):
+        """Blocking check of the device status word (one 4-byte read); raises FloatingPointError where the
+        reference would have dropped into pdb, and after a non-finite parameter gradient."""
+        ops.check_status(self.device)
 
     # ------------------------------------------------------------------ cached device constants
     def _const(self, key, make):
@@ -186,6 +194,7 @@ class UDFRendererBlending:
                perturb_overwrite=-1, background_rgb=None, flip_saturation=0, color_maps=None, pose=None,
                fx=None, fy=None, img_index=None, rays_uv=None):
         dev = self.device
+        ops.poll_status(dev)                       # non-blocking NaN guard (see module docstring)
         rays_o = rays_o.to(dev, torch.float32).contiguous()
         rays_d = rays_d.to(dev, torch.float32).contiguous()
         B = len(rays_o)

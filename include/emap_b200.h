@@ -20,7 +20,7 @@
 extern "C" {
 #endif
 
-#define EMAP_ABI_VERSION 1
+#define EMAP_ABI_VERSION 2
 
 /* Network description == the `model.udf_network` conf block (confs/ABC.conf:65-77) restricted
  * to the topology the kernels are built for: d_in=3, d_hidden=256, n_layers=8, skip_in=[4],
@@ -35,6 +35,13 @@ typedef struct emap_net_desc {
 /* MLP arithmetic mode */
 #define EMAP_PREC_FP32X3 3 /* fp32-faithful: 3 split-fp16 tcgen05 MMAs (hi*hi + lo*hi + hi*lo), fp32 accum */
 #define EMAP_PREC_HALF   1 /* one fp16 (or bf16) tcgen05 MMA, fp32 accumulate                              */
+
+/* Device-side status word (an int32 in device memory owned by the caller, zeroed by the caller): kernels OR
+ * bits into it instead of the reference's `pdb.set_trace()` NaN guards; the host shim polls it once per step
+ * and raises (udf_renderer_blending.py:102-107, :346-351, :632-633).                                        */
+#define EMAP_STATUS_NAN_SAMPLES     1 /* NaN among the new z samples of an up-sampling step (:102, :346)      */
+#define EMAP_STATUS_NAN_EIKONAL     2 /* NaN gradient_error in render_core (:632)                             */
+#define EMAP_STATUS_NONFINITE_GRAD  4 /* non-finite parameter gradient out of the backward                    */
 
 /* Flat parameter buffer layout (fp32), identical to list(UDFNetwork.parameters()) order:
  *   for l in 0..8: bias[out_l], g[out_l] ("original0"), v[out_l*in_l] ("original1")
@@ -85,22 +92,21 @@ int emap_udf_forward_grad_rev(const emap_net_desc* net, const void* packed, int 
 
 /* ---- K1b: backward of (udf, d udf/dx) w.r.t. the 462,980 MLP parameters -------------------------
  * replaces: autograd through UDFNetwork.forward + .gradient(create_graph=True)
- * (udf_model.py:90-135; loss.backward() at runner_udf.py:167).  Round-1 structure: the element-wise
- * stages are the kernels below; the per-layer GEMMs between them are plain library GEMMs issued by
- * the host shim (emap_b200/ops.py: udf_backward).  All *_half pointers are fp16 device buffers;
- * "dual" tensors hold value rows [0,P) and tangent rows [P,2P).                                    */
-int emap_bwd_pe_dual(const emap_net_desc* net, const float* pts, const float* rays_o,
-                     const float* rays_d, const float* z, int32_t n_per_ray, int64_t P,
-                     const float* d_grad /*[P,3] or NULL*/, void* U0_half /*[2P,64]*/, void* stream);
-int emap_bwd_act_fwd(const float* acc /*[2P,ld]*/, int32_t ld, const float* bias, int64_t P,
-                     int32_t n_out, const void* U0_half /*skip layer only, else NULL*/, int32_t pe,
-                     void* Unext_half /*[2P,256]*/, void* sig_half /*[P,256]*/, void* adot_half /*[P,256]*/,
-                     void* stream);
+ * (udf_model.py:90-135; loss.backward() at runner_udf.py:167).  All *_half pointers are fp16 device buffers;
+ * "dual" tensors hold value rows [0,P) and tangent rows [P,2P).
+ *
+ * Loss scaling: the stashes and MMA operands of the backward are fp16, raw loss cotangents are not in its
+ * range (|dL/dgrad| ~ 1e-8 at production batch sizes).  emap_bwd_cotangent_scales derives two powers of two
+ * from the maxima of the cotangents on the device (no host sync): scales[0] = S_g (the tangent direction is
+ * S_g d_grad, max in [0.5,1)), scales[1] = S_u (what the sweep accumulates is S_u dL/dtheta; max(S_u |d_udf|,
+ * S_u |d_grad|) in [1/8,1/4)), scales[2] = S_u/S_g, scales[3] = 1/S_u; scales[4..7] scratch.  The stages
+ * below take that buffer (NULL = all ones); emap_bwd_weight_norm removes S_u.                          */
+int emap_bwd_cotangent_scales(const float* d_udf /*[P] or NULL*/, const float* d_grad /*[P,3] or NULL*/,
+                              int64_t P, float* scales8, void* stream);
+/* output-layer pull-back: coef[p] = S_u d_udf f'(a8)/scale + (S_u/S_g) f''(a8) adot8, coef[P+p] = (S_u/S_g) f'(a8) */
 int emap_bwd_top(const emap_net_desc* net, const void* U8_half, const float* w8, const float* b8,
-                 const float* d_udf /*[P] or NULL*/, int64_t P, float* Eta8 /*[2P,256] or NULL*/,
-                 float* coef /*[2P]*/, void* stream);
-int emap_bwd_act_bwd(const float* eta /*[2P,ld]*/, int32_t ld, float mul, int64_t P, int32_t n,
-                     const void* sig_half, const void* adot_half, void* A_half /*[2P,256]*/, void* stream);
+                 const float* d_udf /*[P] or NULL*/, const float* scales, int64_t P, float* coef /*[2P]*/,
+                 void* stream);
 /* Fused tensor-core stages of K1b (hand-written tcgen05 kernels on the K1 skeleton):
  *  emap_bwd_dual_forward : layers 0..7 of the dual network (value + ONE tangent along d_grad) with
  *     fp16 stashes  st_u0[2P,64] (dual PE, kernel column order), st_u[8][2P,256] (inputs of layers 1..8:
@@ -111,8 +117,8 @@ int emap_bwd_act_bwd(const float* eta /*[2P,ld]*/, int32_t ld, float mul, int64_
  *     dW_l = A_l^T U_l (library) and emap_bwd_weight_norm.                                            */
 int emap_bwd_dual_forward(const emap_net_desc* net, const void* packed, int precision,
                           const float* pts, const float* rays_o, const float* rays_d, const float* z,
-                          int32_t n_per_ray, int64_t P, const float* d_grad, void* st_u0, void* st_u,
-                          void* stream);
+                          int32_t n_per_ray, int64_t P, const float* d_grad, const float* scales,
+                          void* st_u0, void* st_u, void* stream);
 int emap_bwd_reverse_sweep(const emap_net_desc* net, const void* packed, const float* coef,
                            const void* st_u, void* st_a, int64_t P, void* stream);
 /* Shared-forward variant of stage 1: the value rows of st_u0 / st_u were written by the training forward
@@ -120,16 +126,19 @@ int emap_bwd_reverse_sweep(const emap_net_desc* net, const void* packed, const f
  * zero tangent): one row per point, sigma_l recovered from the stashed h_{l+1}, single fp16 MMA.       */
 int emap_bwd_tangent_forward(const emap_net_desc* net, const void* packed, const float* pts,
                              const float* rays_o, const float* rays_d, const float* z, int32_t n_per_ray,
-                             int64_t P, const float* d_grad, void* st_u0, void* st_u, void* stream);
+                             int64_t P, const float* d_grad, const float* scales, void* st_u0, void* st_u,
+                             void* stream);
 /* db_l[c] = sum over the value rows p < P of A_l[p, c], l = 0..7, from the reverse sweep's stash
  * st_a [8][2P,256] fp16 -> db [8,256] fp32.  partial: scratch [8*296*256] floats.  Deterministic two-pass
  * reduction (no atomics).  replaces the bias half of autograd's addmm backward (udf_model.py:102).      */
 int emap_bwd_bias_sums(const void* st_a, int64_t P, float* partial, float* db, void* stream);
 /* weight-norm backward + scatter into the flat gradient (same layout as the flat parameters).
- * dW[l]: fp32 [out_l, ldw[l]] (d/dW_eff, times mul[l]); db[l]: fp32 [out_l].                       */
+ * dW[l]: fp32 [out_l, ldw[l]] (d/dW_eff, times mul[l]); db[l]: fp32 [out_l]; both still carry the loss scale
+ * S_u, removed here (scales[3]; NULL = 1).  status (optional, device int32): bit EMAP_STATUS_NONFINITE_GRAD
+ * is set when a parameter gradient is not finite (e.g. an fp16 overflow of the scaled sweep).       */
 int emap_bwd_weight_norm(const emap_net_desc* net, const float* flat_params, const float* const* dW,
                          const int32_t* ldw, const float* mul, const float* const* db,
-                         float* flat_grad, void* stream);
+                         const float* scales, float* flat_grad, int32_t* status, void* stream);
 /* byte offsets inside the packed buffer: out[0] = 100*bias table, out[1..9] = W_eff of layer 0..8. */
 int emap_packed_offsets(const emap_net_desc* net, uint32_t* out10);
 
@@ -156,7 +165,8 @@ int emap_upsample_step(const float* rays_o, const float* rays_d, const float* z_
                        int32_t ka, float* z_out, float* udf_out, const float* u, int32_t k,
                        float* z_new, int64_t* inds_out, float* weights_out, const float* sample_dist,
                        int32_t B, float inv_s, float beta, float gamma, const float* gamma_dev,
-                       int32_t mode, int32_t alpha_type, void* stream);
+                       int32_t mode, int32_t alpha_type, int32_t* status /* optional, EMAP_STATUS_* */,
+                       void* stream);
 
 /* render_core before the MLP: dists, mid_z_vals          (udf_renderer_blending.py:435-446)     */
 int emap_render_prep(const float* z, const float* sample_dist, int32_t B, int32_t n, float* dists,
@@ -175,7 +185,7 @@ int emap_render_core_fwd(const float* rays_o, const float* rays_d, const float* 
                          int32_t use_unbias, int32_t use_norm_grad, int32_t alpha_type,
                          float* weights, float* alpha, float* grad_flip, float* inside_sphere,
                          float* grad_mag, float* edge, float* depth, float* normals,
-                         double* partials, float* reduced, void* stream);
+                         double* partials, float* reduced, int32_t* status /* optional */, void* stream);
 
 /* backward of emap_render_core_fwd: cotangents (any may be NULL = zero) of weights[B,n], edge[B],
  * depth[B], normals[B,3] and of the three scalar reductions (device scalars) -> d_udf[B*n],

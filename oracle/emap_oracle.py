@@ -254,7 +254,7 @@ def sample_pdf_det(bins: torch.Tensor, weights: torch.Tensor, k: int,
     pdf = w / torch.sum(w, -1, keepdim=True)
     cdf = torch.cumsum(pdf, -1)
     cdf = torch.cat([torch.zeros_like(cdf[..., :1]), cdf], -1)  # [B,n]
-    u = torch.linspace(0.0 + 0.5 / k, 1.0 - 0.5 / k, steps=k, dtype=cdf.dtype)
+    u = torch.linspace(0.0 + 0.5 / k, 1.0 - 0.5 / k, steps=k, dtype=cdf.dtype).to(cdf.device)
     u = u.expand(cdf.shape[0], k).contiguous()
     inds = torch.searchsorted(cdf, u, right=True)
     below = (inds - 1).clamp_min(0)
@@ -498,7 +498,7 @@ class RenderConfig:
 def coarse_z(near: torch.Tensor, far: torch.Tensor, n_samples: int,
              t_rand: Optional[torch.Tensor]) -> torch.Tensor:
     """udf_renderer_blending.py:705-720.  ``t_rand`` = rand([B,1]) - 0.5 or None."""
-    lin = torch.linspace(0.0, 1.0, n_samples, dtype=near.dtype)
+    lin = torch.linspace(0.0, 1.0, n_samples, dtype=near.dtype).to(near.device)
     z = near + (far - near) * lin[None, :]
     if t_rand is not None:
         z = z + t_rand * 2.0 / n_samples

@@ -216,7 +216,7 @@ def main():
     run_render("init_64_50_5", False, 64, 50, 5, 16, 0.0, 1.0)
     run_render("pert_64_64_4", True, 64, 64, 4, 16, 0.9, 0.6)
     run_render("pert_64_0", True, 64, 0, 5, 16, 0.9, None)
-    run_render("pert_128_128_4", True, 128, 128, 4, 6, 1.0, 1.0, grads=False)
+    run_render("pert_128_128_4", True, 128, 128, 4, 6, 1.0, 1.0)      # the bench configuration (BASELINE configs[3])
     # Replica-style: multires=6, far=2.5
     run_render("mr6_64_50_5", True, 64, 50, 5, 8, 0.9, 1.0, multires=6, far_v=2.5, grads=False)
     # off-default variants

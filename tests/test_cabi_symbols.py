@@ -31,7 +31,7 @@ def test_header_symbols_exported_and_bound():
 
 def test_host_only_entry_points():
     L = C.lib()
-    assert L.emap_abi_version() == 1
+    assert L.emap_abi_version() == 2
     for mr, expect in ((10, 462980), (6, 462980 - 256 * 24 + 0), (0, None)):
         d = C.NetDesc(mr, 0, 1.0, 0)
         n = L.emap_flat_param_count(ctypes.byref(d))

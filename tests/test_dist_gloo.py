@@ -49,6 +49,34 @@ def _worker(rank, world, port, ret):
             else:
                 assert torch.allclose(p.grad, torch.full_like(p, mean_rank * (i + 1)))
 
+        # the production layout: the MLP backward hands out views of ONE flat buffer (with a spare tail) -- it is
+        # all-reduced in place, the foreign gradients (scalar networks) ride in its tail; still one collective
+        arena = torch.empty(20 + parallel.GRAD_ARENA_SLACK)[:20]
+        arena.copy_(torch.arange(20.0) * (rank + 1))
+        ps = [torch.nn.Parameter(torch.zeros(4, 3)), torch.nn.Parameter(torch.zeros(8)), torch.nn.Parameter(torch.zeros(1)),
+              torch.nn.Parameter(torch.zeros(2))]
+        ps[0].grad, ps[1].grad = arena[0:12].view(4, 3), arena[12:20]
+        ps[2].grad, ps[3].grad = torch.tensor([7.0 * (rank + 1)]), torch.tensor([1.0, 2.0]) * (rank + 1)
+        ptr0 = ps[0].grad.data_ptr()
+        red2 = parallel.FlatGradAllReduce(ps)
+        calls["n"] = 0
+        dist.all_reduce = counting
+        red2.allreduce_()
+        dist.all_reduce = orig
+        assert calls["n"] == 1
+        assert ps[0].grad.data_ptr() == ptr0                    # reduced in place, no re-pack
+        assert torch.allclose(torch.cat([ps[0].grad.reshape(-1), ps[1].grad]), torch.arange(20.0) * mean_rank)
+        assert torch.allclose(ps[2].grad, torch.tensor([7.0 * mean_rank]))
+        assert torch.allclose(ps[3].grad, torch.tensor([1.0, 2.0]) * mean_rank)
+        # unequal ray shards: weights B_local * W / B_global make per-shard means combine to the batch mean
+        lo_, hi_ = parallel.shard_bounds(11, rank, world)
+        wgt = parallel.shard_weight(hi_ - lo_, 11)
+        vals = torch.arange(11.0)
+        pp = torch.nn.Parameter(torch.zeros(1))
+        pp.grad = vals[lo_:hi_].mean().reshape(1)               # a per-shard mean
+        parallel.FlatGradAllReduce([pp]).allreduce_(local_weight=wgt)
+        assert torch.allclose(pp.grad, vals.mean().reshape(1))
+
         den = parallel.global_denominators(torch.tensor([float(rank + 1), 10.0 * (rank + 1)]))
         assert torch.allclose(den, torch.tensor([3.0, 30.0]))
 
