@@ -28,6 +28,7 @@
 
 namespace emap {
 long long* dbg_clk_buffer();   // mlp_tc.cu (emap_debug_set_clk_buffer)
+int dbg_iter();                 // mlp_tc.cu (emap_set_option("dbg_iter"))
 namespace rg {
 
 constexpr int kSteps = 16;
@@ -36,16 +37,27 @@ constexpr uint32_t kUsesPerBuf = 8;               // accumulator uses per tile a
 constexpr uint32_t kAPerTile = 15;                // completions of a_ready[0..3] per tile (steps 0..14)
 constexpr float kAdjScale = 16.f;                 // power of two (headroom: |alpha| < 4095)
 constexpr int kSigmaLayers = 7;                   // sigma_0..sigma_6 (sigma_7 is consumed in registers)
-// sigma in [0,1] is stashed as 16-bit FIXED point (round(sigma * 65535)): what matters for the gradient is
-// its absolute error (2^-17), not its relative one -- modelled in tests/test_rg_emulation.py: 1e-5 on the
-// gradient against 5e-6 with fp32 sigma and 1.7e-4 with fp16 sigma.  Half the L2 traffic of an fp32 stash,
-// and 148 slices (66 MB) fit the 126 MB L2 together with the weights.
-constexpr float kSigmaQ = 65535.f;
+// sigma in [0,1] is stashed in 16 bits of FIXED point (15-bit exp(-|t|) + the sign of t, see enc_e): what
+// matters for the gradient is its absolute error (2^-16), not its relative one -- modelled in
+// tests/test_rg_emulation.py: 1.3e-5 on the gradient against 5e-6 with fp32 sigma and 1.7e-4 with fp16 sigma.
+// Half the L2 traffic of an fp32 stash, and 148 slices (66 MB) fit the 126 MB L2 together with the weights.
+constexpr float kSigmaQ = 32767.f;
 constexpr int kSigmaWordsPerCta = kSigmaLayers * 4 * 16 * 256;   // [layer][chunk][warp][32 lanes x 8 words] = 448 KiB
+
+// The positional encoding of a tile is not computed on the tile's critical path: while the reverse steps of
+// tile i are MMA-bound, the 16 epilogue warps encode the points of tile i+1 and write the finished operand
+// image of its PE chunk ([128 x 64] K-major SW128, hi | lo: 32 KiB) into a per-CTA, double-buffered global
+// scratch (L2-resident).  One thread then hands it to the TMA engine: a bulk copy into A-tile chunk 0 as soon as
+// the last MMA of tile i has released it, and the same copy again for the skip term of layer 4 (the round-1
+// kernel ran 2 x 16 sincosf per point on eight warps at both places: ~28 k of the tile's ~218 k clocks with the
+// tensor pipe idle -- profiles/r02_k1r_timeline_before.txt).
+constexpr int kPeImageBytes = 2 * kChunkBytes;            // hi | lo
+constexpr int kPeBytesPerCta = 2 * kPeImageBytes;         // double buffered
 
 struct Args {
   MlpArgs m;
   uint32_t* scratch;     // [grid][kSigmaWordsPerCta]
+  uint8_t* pe_scratch;   // [grid][2][kPeImageBytes]
   int flags;             // emap_set_option("rg_flags", bits): kFlagSplitTail
 };
 constexpr int kFlagSplitTail = 1;   // N-split of each step's last K chunk (as K1g does; A/B switch for bring-up)
@@ -68,22 +80,26 @@ __device__ __forceinline__ constexpr uint32_t step_bytes(int s) {
   return (s == kLastStep) ? 8192u : (uint32_t)kRingStageBytes;
 }
 
-// sigma scratch: plain (coherent) 256-bit accesses -- the data is rewritten by this kernel, so the
-// read-only path of ldg256 must not be used.  16 sigmas of one thread = 8 words (column 2i in the low half).
-__device__ __forceinline__ void ld_sigma16(const uint32_t* p, float (&v)[16]) {
-  uint32_t u[8];
+// sigma scratch: plain (coherent) 256-bit accesses -- the data is rewritten by this kernel, so the read-only
+// path of ldg256 must not be used.  Per element 16 bits: bit 15 = sign of t = 100 a, bits 0..14 =
+// round(32767 exp(-|t|)); sigma = (t >= 0 ? 1 : e) / (1 + e) is rebuilt in the reverse step (one MUFU.RCP there
+// instead of MUFU.RCP + F2I in the forward step, which is the longer one).  Both conversions go through the
+// 2^23 magic number on the FMA / ALU pipes -- no F2I / I2F (they share the XU pipe with the MUFUs).
+__device__ __forceinline__ void ld_words8(const uint32_t* p, uint32_t (&u)[8]) {
   asm volatile("ld.global.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
                : "=r"(u[0]), "=r"(u[1]), "=r"(u[2]), "=r"(u[3]), "=r"(u[4]), "=r"(u[5]), "=r"(u[6]), "=r"(u[7])
                : "l"(p)
                : "memory");
-#pragma unroll
-  for (int i = 0; i < 8; ++i) {          // kept as integers-in-float: the 1/65535 is folded into the caller's scale
-    v[2 * i] = (float)(u[i] & 0xffffu);
-    v[2 * i + 1] = (float)(u[i] >> 16);
-  }
 }
-__device__ __forceinline__ uint32_t pack_sigma2(float a, float b) {
-  return __float2uint_rn(a * kSigmaQ) | (__float2uint_rn(b * kSigmaQ) << 16);
+__device__ __forceinline__ uint32_t enc_e(float e, float t) {     // 16-bit code of (e, sign t)
+  const uint32_t q = __float_as_uint(fmaf(e, kSigmaQ, 12582912.0f));          // low mantissa bits = round(32767 e)
+  return (q & 0x7fffu) | ((__float_as_uint(t) >> 16) & 0x8000u);
+}
+__device__ __forceinline__ float dec_sigma(uint32_t v) {          // v: 16-bit code in the low half
+  const float ei = __uint_as_float(0x4B000000u | (v & 0x7fffu)) - 8388608.0f;   // 32767 e
+  const float e = ei * (1.0f / kSigmaQ);
+  const float r = rcp_approx(fmaf(ei, 1.0f / kSigmaQ, 1.0f));
+  return (v & 0x8000u) ? e * r : r;
 }
 
 // J_gamma^T applied to 16 consecutive PE adjoints adj[i] <-> PE slot k = kbase + i (rg_pe_ref order,
@@ -103,11 +119,49 @@ __host__ __device__ __forceinline__ void pe_adjoint16(const float (&adj)[16], in
         const float f = (float)(1 << j);
         const float xa = (ax == 0) ? x[0] : (ax == 1 ? x[1] : x[2]);
         float s, c;
-        sincosf(xa * f, &s, &c);
+        sincos_pe(xa * f, &s, &c);
         const float v = f * (adj[i] * c - adj[i + 1] * s);
         if (ax == 0) g[0] += v; else if (ax == 1) g[1] += v; else g[2] += v;
       }
     }
+  }
+}
+
+// Encode 16 columns (kernel PE column order, common.cuh) of one point: the thread's two 16-byte groups of the PE
+// operand image, written to `img` (hi image; lo image kChunkBytes further) -- a global copy of what the
+// round-1 kernel stored into shared memory -- and, in training, to the value rows of the backward's U_0 stash.
+template <int NTERMS, typename T>
+__device__ __forceinline__ void pe_precompute(const MlpArgs& m, const float (&x)[3], int multires, int row,
+                                              int sub, long long pt, bool ok, uint8_t* img) {
+  float vals[16];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int col = sub * 16 + 2 * i;                   // even kernel column, warp-uniform
+    float a = 0.f, b = 0.f;
+    if (col == 0) { a = x[0]; b = x[1]; }
+    else if (col == 2) { a = x[2]; }
+    else {
+      const int qq = (col < 32) ? ((col - 4) >> 1) : (14 + ((col - 32) >> 1));
+      const int j = qq / 3, ax = qq - 3 * j;
+      if (j < multires) {
+        const float xa = (ax == 0) ? x[0] : (ax == 1 ? x[1] : x[2]);
+        sincos_pe(xa * (float)(1 << j), &a, &b);
+      }
+    }
+    vals[2 * i] = a; vals[2 * i + 1] = b;
+  }
+  if (m.st_u0 && ok) {
+    uint32_t pu[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) pu[j] = Elem<__half>::pack2(vals[2 * j], vals[2 * j + 1]);
+    stg256(m.st_u0 + (size_t)pt * 64 + sub * 16, pu);
+  }
+#pragma unroll
+  for (int g = 0; g < 2; ++g) {
+    float v8[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) v8[j] = vals[g * 8 + j];
+    store_group<NTERMS, T>(img, img + kChunkBytes, row, sub * 2 + g, v8);
   }
 }
 
@@ -138,13 +192,15 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_rgrad_kernel(const Args args)
   uint64_t* a_ready = bars + 8;           // [5]  (index 4 = PE written into chunk 0)
   uint64_t* acc_full = bars + 13;         // [2 buffers][2 N halves]: columns [0,128) / [128,256) complete
   uint64_t* acc_empty = bars + 17;        // [2]
-  uint64_t* c0_free = bars + 19;          // layer 4 has consumed chunk 0 -> PE may be regenerated there
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 20);
+  uint64_t* c0_free = bars + 19;          // layer 4 has consumed chunk 0 -> the PE image may be copied there again
+  uint64_t* pe_done = bars + 20;          // all 16 epilogue warps have written their part of a PE image
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 21);
 
   if (warp == kProducerWarp && lane == 0) {
     for (int s = 0; s < kStages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
     for (int c = 0; c < 4; ++c) mbar_init(&a_ready[c], kEpiWarps);
-    mbar_init(&a_ready[4], 8);
+    mbar_init(&a_ready[4], 1);            // one arrive.expect_tx by the thread that issues the PE bulk copy
+    mbar_init(pe_done, kEpiWarps);
     for (int b = 0; b < 4; ++b) mbar_init(&acc_full[b], 1);
     for (int b = 0; b < 2; ++b) mbar_init(&acc_empty[b], kEpiWarps);
     mbar_init(c0_free, 1);
@@ -200,7 +256,7 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_rgrad_kernel(const Args args)
         const int buf = s & 1;
         // timeline of block 0's second tile (emap_debug_rgrad + emap_debug_set_clk_buffer): issuer stamps at
         // dbg_clk[64 + 4 s + {0: step start, 1: accumulator free, 2: first K chunk ready, 3: all MMAs issued}]
-        const bool stamp = m.dbg_clk && blockIdx.x == 0 && iter == 1 && lane == 0;
+        const bool stamp = m.dbg_clk && blockIdx.x == 0 && iter == m.dbg_iter && lane == 0;
         if (stamp) m.dbg_clk[64 + 4 * s + 0] = clock64();
         {
           const uint32_t started = (uint32_t)iter * kUsesPerBuf + (uint32_t)(s >> 1);
@@ -309,23 +365,38 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_rgrad_kernel(const Args args)
     // this thread's sigma words (l = 0..6): ((l*4 + chunk)*16 + warp)*256 + lane*8
     uint32_t* sg_base = args.scratch + (size_t)blockIdx.x * kSigmaWordsPerCta + (size_t)warp * 256 + lane * 8;
     auto sg_ptr = [&](int l, int chunk) -> uint32_t* { return sg_base + (size_t)(l * 4 + chunk) * 4096; };
-    const float gz[3] = {0.f, 0.f, 0.f};
+    uint8_t* pe_img = args.pe_scratch + (size_t)blockIdx.x * kPeBytesPerCta;
+    // hand PE image `b` to the TMA engine: chunk 0 (hi) and its lo twin; completes a_ready[4]
+    auto issue_pe_copy = [&](int b) {
+      fence_proxy_async_all();                              // the image was written with ordinary global stores
+      constexpr uint32_t bytes = (NTERMS == 3) ? (uint32_t)kPeImageBytes : (uint32_t)kChunkBytes;
+      mbar_arrive_expect_tx(&a_ready[4], bytes);
+      bulk_g2s(A_hi, pe_img + (size_t)b * kPeImageBytes, kChunkBytes, &a_ready[4]);
+      if (NTERMS == 3) bulk_g2s(A_lo, pe_img + (size_t)b * kPeImageBytes + kChunkBytes, kChunkBytes, &a_ready[4]);
+    };
+    // encode the points of tile iteration `it` into image it & 1 (all 16 warps, 16 columns of a row each)
+    auto encode_tile = [&](int it) {
+      const long long t2 = (long long)blockIdx.x + (long long)it * gridDim.x;
+      const long long p2 = t2 * 128 + row;
+      float xn[3];
+      load_point(m, p2, net_scale, xn);
+      pe_precompute<NTERMS, T>(m, xn, multires, row, sub, p2, (t2 < m.num_tiles) && (p2 < m.P),
+                               pe_img + (size_t)(it & 1) * kPeImageBytes);
+      __syncwarp();
+      if (lane == 0) mbar_arrive(pe_done);
+    };
+    encode_tile(0);
+    if (warp == 0) {
+      mbar_wait(pe_done, 0, 550);
+      if (lane == 0) issue_pe_copy(0);
+      __syncwarp();
+    }
 
     for (int iter = 0; iter < m.iters; ++iter) {
       const long long tile = (long long)blockIdx.x + (long long)iter * gridDim.x;
       const long long pt = tile * 128 + row;
       const bool ok = (tile < m.num_tiles) && (pt < m.P);
-      float x[3];
-      load_point(m, pt, net_scale, x);
-      // ------------------------------------------------ input stage: positional encoding -> chunk 0
-      if (sub < 2) {
-        // (MODE 4 = the forward's PE values, also written to the backward's U_0 stash when one is given)
-        if (sub == 0) pe_stage<NTERMS, 4, T, 0>(m, x, multires, lane, row, pt, tile, true, A_hi, A_lo, gz);
-        else          pe_stage<NTERMS, 4, T, 1>(m, x, multires, lane, row, pt, tile, true, A_hi, A_lo, gz);
-        fence_proxy_async_smem();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&a_ready[4]);
-      }
+      // (the PE image of this tile is already on its way into chunk 0: nothing to do at tile start)
 
       // ------------------------------------------------ forward: hidden layers 0..7 (steps 0..7)
       float dot8 = 0.f;                         // this thread's share of a_8 = w_8 . h_8 (its 64 columns)
@@ -335,7 +406,7 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_rgrad_kernel(const Args args)
         const bool top = (l == 7);              // layer 7: h_8 feeds only the output layer; seed the sweep
         const uint32_t acc_par = ((uint32_t)iter * kUsesPerBuf + (uint32_t)(l >> 1)) & 1;
         // epilogue warp 0 stamps at dbg_clk[4 s + {0: waiting, 1: accumulator complete, 2: chunk 0 handed off, 3: done}]
-        const bool stamp = m.dbg_clk && blockIdx.x == 0 && iter == 1 && warp == 0 && lane == 0;
+        const bool stamp = m.dbg_clk && blockIdx.x == 0 && iter == m.dbg_iter && warp == 0 && lane == 0;
         if (stamp) m.dbg_clk[4 * l + 0] = clock64();
         mbar_wait(&acc_full[buf * 2], acc_par, 500 + buf, l);
         tc_fence_after();
@@ -359,22 +430,25 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_rgrad_kernel(const Args args)
               m.dbg_acc[((size_t)l * 128 + row) * 256 + col0 + k] = __uint_as_float(r[k]) * kInvWeightScale;
           }
           uint32_t* sgp = sg_ptr(top ? 0 : l, chunk);
-          uint32_t sw[8];                     // sigma_l of this thread's 16 columns, 16-bit fixed point
+          uint32_t sw[8];                     // (e, sign t) codes of this thread's 16 columns -> sigma_l in the sweep
           uint32_t pu[8];                     // h_{l+1} of this thread's 16 columns as fp16 (training stash)
 #pragma unroll
           for (int g = 0; g < 2; ++g) {
             const float4 bA = bv[2 * g], bB = bv[2 * g + 1];
             const float bb[8] = {bA.x, bA.y, bA.z, bA.w, bB.x, bB.y, bB.z, bB.w};
-            float h[8], sg[8];
-#pragma unroll
-            for (int j = 0; j < 8; ++j)
-              h[j] = softplus100<true>(fmaf(__uint_as_float(r[g * 8 + j]), k1, bb[j]), sg[j]);
-#pragma unroll
-            for (int j = 0; j < 4; ++j) pu[g * 4 + j] = Elem<__half>::pack2(h[2 * j], h[2 * j + 1]);
+            float h[8];
             if (!top) {
+              uint32_t code[8];
+#pragma unroll
+              for (int j = 0; j < 8; ++j) {
+                const float t = fmaf(__uint_as_float(r[g * 8 + j]), k1, bb[j]);
+                float e;
+                h[j] = softplus100_e(t, e);
+                code[j] = enc_e(e, t);
+              }
               store_group<NTERMS, T>(dst_hi, dst_lo, row, sub * 2 + g, h);
 #pragma unroll
-              for (int j = 0; j < 4; ++j) sw[g * 4 + j] = pack_sigma2(sg[2 * j], sg[2 * j + 1]);
+              for (int j = 0; j < 4; ++j) sw[g * 4 + j] = code[2 * j] | (code[2 * j + 1] << 16);
             } else {
               // a_8 += w_8 . h_8;  unsigned seed of the sweep: alpha_7 = w_8 . sigma_7 (x 2^4)
               const float4 wA = __ldg(reinterpret_cast<const float4*>(w8 + col0 + g * 8));
@@ -382,9 +456,16 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_rgrad_kernel(const Args args)
               const float ww[8] = {wA.x, wA.y, wA.z, wA.w, wB.x, wB.y, wB.z, wB.w};
               float v[8];
 #pragma unroll
-              for (int j = 0; j < 8; ++j) { dot8 = fmaf(ww[j], h[j], dot8); v[j] = kAdjScale * ww[j] * sg[j]; }
+              for (int j = 0; j < 8; ++j) {
+                float sg;
+                h[j] = softplus100<true>(fmaf(__uint_as_float(r[g * 8 + j]), k1, bb[j]), sg);
+                dot8 = fmaf(ww[j], h[j], dot8);
+                v[j] = kAdjScale * ww[j] * sg;
+              }
               store_group<NTERMS, T>(dst_hi, dst_lo, row, sub * 2 + g, v);
             }
+#pragma unroll
+            for (int j = 0; j < 4; ++j) pu[g * 4 + j] = Elem<__half>::pack2(h[2 * j], h[2 * j + 1]);
           }
           fence_proxy_async_smem();
           __syncwarp();
@@ -400,15 +481,12 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_rgrad_kernel(const Args args)
         if (lane == 0) mbar_arrive(&acc_empty[buf]);
         if (stamp) m.dbg_clk[4 * l + 3] = clock64();
 
-        if (l == kSkipLayer - 1 && sub < 2) {
-          // skip connection: layer 4 = [h4 ; PE]/sqrt2.  Once its MMAs on chunk 0 are done, regenerate
-          // the PE there as the 5th K chunk of layer 4.
+        if (l == kSkipLayer - 1 && warp == 0) {
+          // skip connection: layer 4 = [h4 ; PE]/sqrt2.  Once its MMAs on chunk 0 are done, the PE image is
+          // copied there again as the 5th K chunk of layer 4.
           mbar_wait(c0_free, (uint32_t)iter & 1, 520);
-          if (sub == 0) pe_stage<NTERMS, 0, T, 0>(m, x, multires, lane, row, pt, tile, false, A_hi, A_lo, gz);
-          else          pe_stage<NTERMS, 0, T, 1>(m, x, multires, lane, row, pt, tile, false, A_hi, A_lo, gz);
-          fence_proxy_async_smem();
+          if (lane == 0) issue_pe_copy(iter & 1);
           __syncwarp();
-          if (lane == 0) mbar_arrive(&a_ready[4]);
         }
       }
 
@@ -421,11 +499,13 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_rgrad_kernel(const Args args)
         const int buf = s & 1;
         // sigma of the current chunk; chunk 0 is fetched before the accumulator wait, chunk c+1 as soon as
         // chunk c's values are consumed (its L2 latency then overlaps the conversions and stores of chunk c)
-        float sgc[16];                          // 65535 * sigma
-        auto fetch_sigma = [&](int chunk) { ld_sigma16(sg_ptr(l - 1, chunk), sgc); };
+        uint32_t sgc[8];                        // (e, sign t) codes of sigma_{l-1}, this thread's 16 columns
+        auto fetch_sigma = [&](int chunk) { ld_words8(sg_ptr(l - 1, chunk), sgc); };
         fetch_sigma(0);
+        float x[3] = {0.f, 0.f, 0.f};           // the point itself: only the skip layer's PE adjoint needs it
+        if (l == kSkipLayer) load_point(m, pt, net_scale, x);
         const uint32_t acc_par = ((uint32_t)iter * kUsesPerBuf + (uint32_t)(s >> 1)) & 1;
-        const bool stamp = m.dbg_clk && blockIdx.x == 0 && iter == 1 && warp == 0 && lane == 0;
+        const bool stamp = m.dbg_clk && blockIdx.x == 0 && iter == m.dbg_iter && warp == 0 && lane == 0;
         if (stamp) m.dbg_clk[4 * s + 0] = clock64();
         mbar_wait(&acc_full[buf * 2], acc_par, 530 + buf, s);
         tc_fence_after();
@@ -444,7 +524,8 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_rgrad_kernel(const Args args)
           }
           float v[16];
 #pragma unroll
-          for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(r[j]) * (kInvWeightScale / kSigmaQ) * sgc[j];
+          for (int j = 0; j < 16; ++j)
+            v[j] = __uint_as_float(r[j]) * kInvWeightScale * dec_sigma((j & 1) ? (sgc[j >> 1] >> 16) : sgc[j >> 1]);
           if (chunk < 3) fetch_sigma(chunk + 1);
           if (chunk == 3 && l == kSkipLayer) {
             // columns n >= out3 of alpha_4 W_4 are the adjoint of the skip input's PE part (slot
@@ -473,12 +554,22 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_rgrad_kernel(const Args args)
         __syncwarp();
         if (lane == 0) mbar_arrive(&acc_empty[buf]);
         if (stamp) m.dbg_clk[4 * s + 3] = clock64();
+        // the reverse steps are MMA-bound: the gap after the first one takes the encoding of the NEXT tile
+        if (s == 8 && iter + 1 < m.iters) encode_tile(iter + 1);
       }
 
       // ------------------------------------------------ step 15: alpha_0 W_0 (64 PE slots) -> d udf / d x
       {
+        float x[3];
+        load_point(m, pt, net_scale, x);
         mbar_wait(&acc_full[2], ((uint32_t)iter * kUsesPerBuf + 7u) & 1, 540);   // buf 1 (both halves commit together)
         tc_fence_after();
+        // every MMA of this tile has completed: chunk 0 is free, the next tile's PE image can go in now
+        if (warp == 0 && iter + 1 < m.iters) {
+          mbar_wait(pe_done, (uint32_t)(iter + 1) & 1, 551);
+          if (lane == 0) issue_pe_copy((iter + 1) & 1);
+          __syncwarp();
+        }
         uint32_t r[16];
         tmem_ld_32x32b_x16(lane_taddr + (uint32_t)(256 + sub * 16), r);
         tmem_wait_ld();
@@ -536,9 +627,11 @@ static int launch(const Args& a_in, size_t scratch_bytes, cudaStream_t stream) {
   int grid = sm_count();
   if (tiles < grid) grid = (int)tiles;
   a.m.iters = (int)((tiles + grid - 1) / grid);
-  if (scratch_bytes < (size_t)grid * kSigmaWordsPerCta * sizeof(uint32_t))
+  const size_t sigma_bytes = (size_t)grid * kSigmaWordsPerCta * sizeof(uint32_t);
+  if (scratch_bytes < sigma_bytes + (size_t)grid * kPeBytesPerCta)
     return set_error("emap_udf_forward_grad_rev: scratch too small (%zu bytes, need %zu)", scratch_bytes,
-                     (size_t)grid * kSigmaWordsPerCta * sizeof(uint32_t));
+                     sigma_bytes + (size_t)grid * kPeBytesPerCta);
+  a.pe_scratch = reinterpret_cast<uint8_t*>(a.scratch) + sigma_bytes;      // PE images behind the sigma slices
   auto kern = mlp_rgrad_kernel<NTERMS, T>;
   static bool attr_done = false;   // per template instantiation
   if (!attr_done) {
@@ -600,7 +693,7 @@ extern "C" int emap_debug_pe_adjoint(const float* adj16, int kbase, const float*
 }
 
 extern "C" size_t emap_rgrad_scratch_bytes(void) {
-  return (size_t)sm_count() * rg::kSigmaWordsPerCta * sizeof(uint32_t);
+  return (size_t)sm_count() * (rg::kSigmaWordsPerCta * sizeof(uint32_t) + rg::kPeBytesPerCta);
 }
 
 extern "C" int emap_udf_forward_grad_rev(const emap_net_desc* net, const void* packed, int precision,
@@ -642,6 +735,7 @@ int emap::rg::run(const emap_net_desc* net, const void* packed, int precision, c
   a.m.n_per_ray = n_per_ray; a.m.P = P; a.m.udf_out = udf_out; a.m.grad_out = grad_out;
   a.m.dbg_acc = dbg_acc;
   a.m.dbg_clk = dbg_acc ? dbg_clk_buffer() : nullptr;      // timeline stamps only through emap_debug_rgrad
+  a.m.dbg_iter = dbg_iter();
   a.m.st_u0 = (__half*)st_u0; a.m.st_u = (__half*)st_u;
   a.scratch = (uint32_t*)scratch;
   cudaStream_t st = (cudaStream_t)stream;

@@ -183,7 +183,7 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_kernel(const MlpArgs args) {
 #pragma unroll
       for (int l = 0; l < MI::kLayers; ++l) {
         const int buf = l & 1;
-        const bool stamp = args.dbg_clk && blockIdx.x == 0 && iter == 1 && lane == 0;
+        const bool stamp = args.dbg_clk && blockIdx.x == 0 && iter == args.dbg_iter && lane == 0;
         if (stamp) args.dbg_clk[72 + l * 8 + 0] = clock64();
         {
           const uint32_t started = (uint32_t)iter * (buf ? 4u : (uint32_t)MI::kUses0) + (uint32_t)(l >> 1);
@@ -335,7 +335,7 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_kernel(const MlpArgs args) {
       float dot8 = 0.f;               // MODE 5: this thread's share of a_8 = w_8 . h_8 (its 64 columns)
       for (int l = 0; l < 8; ++l) {
         const int buf = l & 1;
-        const bool stamp = args.dbg_clk && blockIdx.x == 0 && iter == 1 && warp == 0 && lane == 0;
+        const bool stamp = args.dbg_clk && blockIdx.x == 0 && iter == args.dbg_iter && warp == 0 && lane == 0;
         if (stamp) args.dbg_clk[l * 8 + 0] = clock64();
         const uint32_t acc_par = ((uint32_t)iter * (buf ? 4u : (uint32_t)MI::kUses0) + (uint32_t)(l >> 1)) & 1;
         // MODE 3: this row's h_{l+1} (value row of the stash, written by the training forward) for the
@@ -604,6 +604,8 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_kernel(const MlpArgs args) {
 static long long* g_dbg_clk = nullptr;   // emap_debug_set_clk_buffer
 long long* dbg_clk_buffer() { return g_dbg_clk; }   // (mlp_rg.cu's debug entry stamps into the same buffer)
 static int g_dbg_flags = 0;   // timing experiments (emap_set_option("dbg", flags)); 0 in production
+static int g_dbg_iter = 1;    // which tile iteration of block 0 the clock64 timelines stamp (emap_set_option("dbg_iter"))
+int dbg_iter() { return g_dbg_iter; }
 
 // ---------------------------------------------------------------------------------------------
 template <int NTERMS, int MODE, typename T, int CL>
@@ -617,6 +619,7 @@ static int launch(const MlpArgs& a_in, cudaStream_t stream) {
   if (tiles > 0x7fffffffLL) return set_error("too many points");
   a.num_tiles = (int)tiles;
   a.dbg_flags = g_dbg_flags;
+  a.dbg_iter = g_dbg_iter;
   int grid = sm_count();
   grid = grid / CLW * CLW;
   if (tiles < grid) grid = (int)((tiles + CLW - 1) / CLW * CLW);
@@ -783,6 +786,7 @@ extern "C" int emap_set_option(const char* name, int value) {
   if (!name) return set_error("option name is NULL");
   if (!strcmp(name, "cluster")) return set_cluster_width(value);
   if (!strcmp(name, "dbg")) { emap::g_dbg_flags = value; return 0; }
+  if (!strcmp(name, "dbg_iter")) { emap::g_dbg_iter = value; return 0; }
   if (!strcmp(name, "k1_dot")) { emap::g_k1_dot = (value != 0); return 0; }
   if (!strcmp(name, "rg_flags")) return emap::rg::set_flags(value);   // K1r experiment switches (mlp_rg.cu)
   return set_error("unknown option '%s'", name);

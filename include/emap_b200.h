@@ -224,7 +224,8 @@ int emap_rays_from_pixels(const int64_t* pixels_x, const int64_t* pixels_y, cons
  *                       with the sigma scratch as a persisting-L2 access-policy window);
  *          "k1_dot"   : 1 = emap_udf_forward (without pe_out) runs the output layer as an fp32 dot product
  *                       in layer 7's epilogue instead of a ninth MMA step (opt-in until measured);
- *          "dbg"      : timing experiments of mlp_tc.cu (0 in production).                            */
+ *          "dbg"      : timing experiments of mlp_tc.cu (0 in production);
+ *          "dbg_iter" : tile iteration of block 0 that the clock64 timelines of the debug entry points stamp. */
 int emap_set_option(const char* name, int value);
 /* test hook: MLP forward (mode 0) / forward+grad (mode 1) that also dumps the de-scaled
  * accumulators of tile 0, dbg_acc[9][128][256].                                                  */

@@ -129,4 +129,4 @@ def test_perturb_overwrite_background_and_bf16(golden):
     nb = build(10, True, precision="bf16", n_samples=64, n_importance=0, up_sample_steps=5)[3]
     c = nb.render(*args, cos_anneal_ratio=None, perturb_overwrite=0, flip_saturation=0.9)
     assert torch.isfinite(c["weights"]).all()
-    assert maxdiff(c["edge"].cpu(), ref["edge"]) <= 0.15
+    assert maxdiff(c["edge"].cpu(), ref["edge"]) <= 5e-3        # flat sampling; hierarchical: tests/test_gpu_parity_r2.py

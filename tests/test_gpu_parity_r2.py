@@ -48,13 +48,14 @@ def test_render_core_per_sample_at_reference_positions(golden, tag, pert, multir
     c = {k: v.detach().cpu() for k, v in c.items()}
     assert maxdiff(c["mid_z_vals"], g["out.mid_z_vals"]) <= 2e-6
     assert maxdiff(c["dists"], g["out.dists"]) <= 2e-6
-    assert maxdiff(c["udf"], g["out.udf"]) <= 1e-4                       # measured <= 3e-5
-    assert maxdiff(c["gradients"], g["out.gradients"]) <= 2e-4           # measured <= 6e-5
-    assert maxdiff(c["gradient_mag"], g["out.gradient_mag"]) <= 2e-4
-    assert maxdiff(c["weights"], g["out.weights"]) <= 1e-3               # sigmoid(inv_s udf) amplifies udf's 3e-5
-    assert maxdiff(c["gradients_flip"], g["out.gradients_flip"]) <= 2e-3
-    assert maxdiff(c["edge"], g["out.edge"]) <= 1e-3
-    assert maxdiff(c["normals"], g["out.normals"]) <= 2e-3
+    # measured worst case over the nine fixtures (profiles/r02_parity.json) in brackets; bound = 2x
+    assert maxdiff(c["udf"], g["out.udf"]) <= 6e-5                       # [2.7e-5]
+    assert maxdiff(c["gradients"], g["out.gradients"]) <= 8e-5           # [3.7e-5]
+    assert maxdiff(c["gradient_mag"], g["out.gradient_mag"]) <= 8e-5     # [3.2e-5]
+    assert maxdiff(c["weights"], g["out.weights"]) <= 1.2e-5             # [5.6e-6]
+    assert maxdiff(c["gradients_flip"], g["out.gradients_flip"]) <= 8e-5  # [3.7e-5]
+    assert maxdiff(c["edge"], g["out.edge"]) <= 2e-4                     # [9.0e-5] (sum of up to 256 weights)
+    assert maxdiff(c["normals"], g["out.normals"]) <= 1.5e-4             # [6.8e-5]
     assert torch.equal(c["inside_sphere"], g["out.inside_sphere"])
     ge = float(g["out.gradient_error"])
     assert abs(float(c["gradient_error"]) - ge) <= 5e-4 * max(1.0, ge)
@@ -62,25 +63,34 @@ def test_render_core_per_sample_at_reference_positions(golden, tag, pert, multir
 
 @pytest.mark.parametrize("tag,pert,multires,rkw", CASES)
 def test_render_end_to_end_measured_bounds(golden, tag, pert, multires, rkw):
-    """render() end to end (own up-sampling): the hierarchical sampler amplifies the MLP's fp32-class rounding
-    (last step: sigmoid(1024 udf)); bounds = 2x the worst measured case."""
+    """render() end to end (own up-sampling).  Bounds = 2x the worst measured case (profiles/r02_parity.json):
+    edge / weight_sum 8.6e-5, depth 4.9e-4 everywhere.  Sample positions: 7.4e-4 on the eight perturbed-network
+    fixtures; 9.4e-3 on the pristine geometric initialisation (init_64_50_5: an exact sphere, whose rays carry
+    long stretches of ~1e-5 weight where the inverse CDF is flat and a rounding-level change of the cdf moves a
+    sample along the ray without changing any rendered quantity -- edge still agrees to 8.6e-5 there)."""
     g = golden(f"render_{tag}")
     net, var, beta, r = build(multires, pert, **rkw)
     with torch.no_grad():
         o = run_render(g, r)
     o = {k: v.detach().cpu() for k, v in o.items()}
     flat = rkw["n_importance"] == 0
-    assert maxdiff(o["mid_z_vals"], g["out.mid_z_vals"]) <= (2e-6 if flat else 5e-3)
-    assert maxdiff(o["edge"], g["out.edge"]) <= (2e-4 if flat else 2e-3)
-    assert maxdiff(o["weight_sum"], g["out.weight_sum"]) <= (2e-4 if flat else 2e-3)
-    assert maxdiff(o["depth"], g["out.depth"]) <= (1e-3 if flat else 1.2e-2)
+    dz = (o["mid_z_vals"] - g["out.mid_z_vals"]).abs()
+    assert float(dz.max()) <= (2e-6 if flat else (2e-2 if not pert else 1.5e-3))
+    assert float((dz > 1e-4).double().mean()) <= (0.0 if flat else 0.02)
+    assert maxdiff(o["edge"], g["out.edge"]) <= 2e-4
+    assert maxdiff(o["weight_sum"], g["out.weight_sum"]) <= 2e-4
+    assert maxdiff(o["depth"], g["out.depth"]) <= 1e-3
 
 
 @pytest.mark.parametrize("tag,n0,ni,steps", [("init_64_50_5", 64, 50, 5), ("pert_64_64_4", 64, 64, 4),
                                              ("pert_128_128_4", 128, 128, 4)])
 def test_upsample_index_flips_are_knife_edges(golden, tag, n0, ni, steps):
     """each up-sampling step fed the reference's own (z, udf): an index may differ from the reference's only
-    where a cdf entry sits within 2e-6 of the quantile (searchsorted on a knife edge: libm ulps decide)."""
+    where a cdf entry sits within 2e-6 of the quantile (searchsorted on a knife edge: libm ulps decide).
+    Measured on B200: ZERO flips on all three fixtures (13 steps, 18,624 look-ups) -- asserted exactly; the
+    knife-edge proof stays in place for other hardware / libm versions.  New samples: <= 1.5e-6 from the
+    reference's on the perturbed networks; on the pristine sphere initialisation (flat ~1e-5 weight stretches,
+    see test_render_end_to_end_measured_bounds) 1.3e-3 in step 0 and 2.6e-5 in step 2."""
     from emap_b200 import ops
     from oracle import emap_oracle as O
     g = golden(f"upsample_{tag}")
@@ -106,7 +116,10 @@ def test_upsample_index_flips_are_knife_edges(golden, tag, n0, ni, steps):
             edge = float((cdf[ray, min(a, b)] - float(u[j])).abs())
             assert edge <= 2e-6, (i, ray, j, edge)
             flips += 1
-    assert flips <= 2, flips            # measured: see profiles/r02_parity.json
+        dz = maxdiff(z_new.cpu(), torch.sort(g[f"z_new{i}"], -1)[0])
+        assert dz <= (3e-3 if tag.startswith("init") else 5e-6), (i, dz)
+        assert maxdiff(w.cpu(), wr) <= 2e-6 * max(1e-3, float(wr.abs().max())), i      # measured 5.4e-7
+    assert flips == 0, flips
 
 
 NAMES = []
@@ -130,11 +143,11 @@ def test_param_grads_at_bench_config(golden):
     loss.backward()
     for n, p in net.named_parameters():
         ref = g[f"dloss.{n}"]
-        assert maxdiff(p.grad.cpu(), ref) <= 1e-2 * (float(ref.abs().max()) + 1e-12), n
-        assert l2rel(p.grad, ref) <= 1e-2, n
+        assert maxdiff(p.grad.cpu(), ref) <= 2e-3 * (float(ref.abs().max()) + 1e-12), n      # measured 8.3e-4
+        assert l2rel(p.grad, ref) <= 1.5e-3, n                                               # measured 6.0e-4
     for name, p in (("variance", var.variance), ("beta", beta.beta), ("gamma", beta.gamma)):
         ref = g[f"dloss.{name}"]
-        assert maxdiff(p.grad.cpu(), ref) <= 1e-2 * (float(ref.abs().max()) + 1e-9) + 1e-9, name
+        assert maxdiff(p.grad.cpu(), ref) <= 2e-3 * (float(ref.abs().max()) + 1e-9) + 1e-9, name
 
 
 @pytest.mark.timeout(300)
@@ -164,7 +177,9 @@ def test_eikonal_gradient_at_production_scale():
     loss.backward()
     r.check_numerics()
     for (name, prm), gr in zip(net.named_parameters(), ref):
-        assert l2rel(prm.grad, gr) <= 2e-2, (name, l2rel(prm.grad, gr))       # measured: profiles/r02_parity.json
+        # measured on B200: 7.1e-4 worst (max norm 9.0e-4); the unscaled backward of round 1: 1.0 (all lost)
+        assert l2rel(prm.grad, gr) <= 2e-3, (name, l2rel(prm.grad, gr))
+        assert maxdiff(prm.grad.cpu(), gr) <= 2e-3 * float(gr.abs().max()), name
 
 
 def test_bf16_network_forward_and_gradients(golden):
@@ -174,13 +189,26 @@ def test_bf16_network_forward_and_gradients(golden):
     x = g["x"].to(dev)
     y, _ = net(x)
     gg = net.gradient(x.clone()).squeeze(1)
-    assert maxdiff(y.detach().cpu(), g["out"]) <= 3e-2
-    assert maxdiff(gg.detach().cpu(), g["grad"]) <= 6e-2
+    assert maxdiff(y.detach().cpu(), g["out"]) <= 2e-2                   # measured 8.7e-3 (bf16: 8-bit mantissa)
+    # d udf/dx = sign(a_8) J: where |udf| is below the bf16 error the sign -- and with it the whole gradient --
+    # may flip; compared away from the zero level set, where it is well conditioned
+    away = (g["out"].abs() > 3e-2).reshape(-1)
+    assert float(away.double().mean()) > 0.8
+    assert maxdiff(gg.detach().cpu()[away], g["grad"][away]) <= 0.1
     loss = (g["cu"].to(dev) * y).sum() + (g["cg"].to(dev) * gg).sum()
     loss.backward()
     for n, p in net.named_parameters():
         ref = g[f"dgrad.{n}"]
-        assert l2rel(p.grad, ref) <= 5e-2, (n, l2rel(p.grad, ref))
+        assert l2rel(p.grad, ref) <= 6e-2, (n, l2rel(p.grad, ref))         # measured 2.9e-2
+    # render(): BASELINE config C2's sizes, end to end (measured: z 4.1e-4, edge 7.4e-4, depth 1.3e-3)
+    gr = golden("render_pert_64_64_4")
+    netb, varb, betab, rb = build(10, True, precision="bf16", n_samples=64, n_importance=64, up_sample_steps=4)
+    with torch.no_grad():
+        ob = run_render(gr, rb)
+    assert maxdiff(ob["edge"].cpu(), gr["out.edge"]) <= 2e-3
+    assert maxdiff(ob["weight_sum"].cpu(), gr["out.weight_sum"]) <= 2e-3
+    assert maxdiff(ob["mid_z_vals"].cpu(), gr["out.mid_z_vals"]) <= 2e-3
+    assert maxdiff(ob["depth"].cpu(), gr["out.depth"]) <= 5e-3
 
 
 def test_status_word_replaces_pdb_nan_guards():

@@ -58,10 +58,12 @@ def test_upsample_steps_in_isolation(golden, tag, n0, ni, steps):
         flips += int((inds.cpu() != ir).sum())
         # measured 1.3e-3 worst case (flat, tiny-pdf region: alpha there is (sigmoid difference + 1e-5),
         # i.e. fp32 cancellation noise that differs between CUDA expf and the CPU's)
-        assert maxdiff(z_new.cpu(), torch.sort(g[f"z_new{i}"], -1)[0]) <= 5e-3, i
+        assert maxdiff(z_new.cpu(), torch.sort(g[f"z_new{i}"], -1)[0]) <= (3e-3 if tag.startswith("init") else 5e-6), i
     # the weights differ by libm ulps, so a bin boundary within ~1e-6 of a quantile may flip;
     # the inverse CDF is continuous across bins, hence the tight bound on z_new above.
-    assert flips <= 2, flips
+    # measured on B200: no flip on any fixture (tests/test_gpu_parity_r2.py proves that a flip, should one ever
+    # appear on other hardware, is a knife edge: a cdf entry within 2e-6 of the quantile)
+    assert flips == 0, flips
 
 
 def test_merge_matches_sort(golden):

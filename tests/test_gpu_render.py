@@ -3,9 +3,10 @@ generated from the reference, end to end through the C ABI.
 
 End-to-end tolerances are looser than the per-stage ones because the hierarchical sampler amplifies
 MLP rounding: the last up-sampling step evaluates sigmoid(1024*udf) and a 2048-sharp logistic, so
-an fp32-class udf error of 2e-5 moves a few new samples by up to ~1e-3 in z.  Stated bounds
-(fp32x3 mode, vs the fp32 CPU reference): z within 5e-3, per-ray edge/weight_sum within 2e-2
-absolute (weights in [0,1]); the per-stage tests (test_gpu_rays.py) pin each stage to 1e-5.
+an fp32-class udf error of 2e-5 moves a few new samples in z.  Bounds here (fp32x3 mode, vs the fp32 CPU
+reference) = 2x the values measured on B200 (profiles/r02_parity.json): per-ray edge / weight_sum 2e-4
+absolute, depth 1e-3, z 1.5e-3 (2e-2 on the pristine sphere initialisation, see
+tests/test_gpu_parity_r2.py, which also compares every per-sample tensor at the reference's positions).
 """
 import pytest
 import torch
@@ -84,12 +85,11 @@ def test_render_matches_reference(golden, tag, pert, multires, rkw):
         assert out[k].dtype == torch.float32 and out[k].is_cuda
     o = {k: v.detach().cpu() for k, v in out.items()}
     flat = rkw["n_importance"] == 0
-    ztol = 1e-6 if flat else 5e-3
-    assert maxdiff(o["mid_z_vals"], g["out.mid_z_vals"]) <= ztol * 6, maxdiff(o["mid_z_vals"], g["out.mid_z_vals"])
-    wtol = 2e-4 if flat else 2e-2
-    assert maxdiff(o["edge"], g["out.edge"]) <= wtol
-    assert maxdiff(o["weight_sum"], g["out.weight_sum"]) <= wtol
-    assert maxdiff(o["depth"], g["out.depth"]) <= wtol * 6
+    ztol = 2e-6 if flat else (1.5e-3 if pert else 2e-2)
+    assert maxdiff(o["mid_z_vals"], g["out.mid_z_vals"]) <= ztol, maxdiff(o["mid_z_vals"], g["out.mid_z_vals"])
+    assert maxdiff(o["edge"], g["out.edge"]) <= 2e-4
+    assert maxdiff(o["weight_sum"], g["out.weight_sum"]) <= 2e-4
+    assert maxdiff(o["depth"], g["out.depth"]) <= 1e-3
     assert abs(float(o["gradient_error"]) - float(g["out.gradient_error"])) <= 2e-3 * max(1, float(g["out.gradient_error"]))
     assert float(o["beta"]) == pytest.approx(float(g["out.beta"]), rel=1e-6)
     assert float(o["gamma"]) == pytest.approx(float(g["out.gamma"]), rel=1e-6)
@@ -108,7 +108,7 @@ def test_importance_sampling_positions(golden):
     z = r.importance_sample(g["rays_o"].to(dev), g["rays_d"].to(dev), g["z0"].to(dev), sd)
     assert z.shape == g["z_final"].shape
     assert bool((z[:, 1:] >= z[:, :-1]).all())
-    assert maxdiff(z.cpu(), g["z_final"]) <= 5e-3 * 6
+    assert maxdiff(z.cpu(), g["z_final"]) <= 1.5e-3
 
 
 def test_properties_at_scale():

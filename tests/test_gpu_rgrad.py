@@ -177,12 +177,12 @@ def test_shared_stash_matches_dual_forward_stash():
     L, desc, st = C.lib(), ctypes.byref(net.desc), C.stream()
     u0_d, u_d = ops.alloc_backward_stash(P, x.device)
     C.check(L.emap_bwd_dual_forward(desc, C.ptr(net.packed), C.PREC_HALF, C.ptr(x), None, None, None, 0, P,
-                                    C.ptr(gbar), C.ptr(u0_d), C.ptr(u_d), st))
+                                    C.ptr(gbar), None, C.ptr(u0_d), C.ptr(u_d), st))
     u0_s, u_s = ops.alloc_backward_stash(P, x.device)
     u0_s.fill_(float("nan")); u_s.fill_(float("nan"))  # every row must be written by one of the two kernels
     ops.udf_forward_grad(net, C.PREC_FP32X3, pts=x, mode="reverse", stash=(u0_s, u_s))
     C.check(L.emap_bwd_tangent_forward(desc, C.ptr(net.packed), C.ptr(x), None, None, None, 0, P, C.ptr(gbar),
-                                       C.ptr(u0_s), C.ptr(u_s), st))
+                                       None, C.ptr(u0_s), C.ptr(u_s), st))
     torch.cuda.synchronize()
     assert torch.isfinite(u0_s).all() and torch.isfinite(u_s).all()
     assert maxdiff(u0_s[:P], u0_d[:P]) <= 1e-3 * float(u0_d[:P].abs().max())   # PE value rows (same sincosf)
@@ -214,7 +214,7 @@ def test_shared_backward_param_grads_vs_reference(golden, tag, pert):
         torch.cuda.synchronize()
     finally:
         ops.set_grad_mode(ops.DEFAULT_GRAD_MODE); ops.set_backward_mode(ops.DEFAULT_BWD_MODE)
-    _check([(n, p.grad) for n, p in net.named_parameters()], g, "dgrad", 1e-2)
+    _check([(n, p.grad) for n, p in net.named_parameters()], g, "dgrad", 3e-3)     # measured 1.65e-3
 
 
 def test_shared_backward_render_loss_matches_default():

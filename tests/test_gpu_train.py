@@ -2,9 +2,11 @@
 reference gets from autograd.grad(create_graph=True)) and of a full render() loss, against the
 fixtures generated from the reference.
 
-Tolerance: the backward's dual forward / reverse sweep run with fp16 GEMM operands and fp16 stashes
-(fp32 accumulation), so per-tensor gradients are compared at 1e-2 of the tensor's max |grad|
-(measured ~2e-3); the loss value itself follows the forward's fp32-class accuracy.
+Tolerance: the backward runs with fp16 MMA operands and fp16 stashes (fp32 accumulation), loss-scaled on the
+device; the value rows of its stash come from the fp32x3 forward.  Per-tensor gradients are compared in the
+max norm relative to the tensor's max |grad|: 2e-3 for the render losses (measured <= 8.3e-4 on B200,
+profiles/r02_parity.json), 3e-3 for the raw MLP double backward with O(1) random cotangents (measured
+1.65e-3); the loss value itself follows the forward's fp32-class accuracy.
 """
 import pytest
 import torch
@@ -43,7 +45,7 @@ def test_mlp_double_backward_vs_reference(golden, tag, pert):
     assert abs(float(loss) - float(g["loss"])) <= 2e-3 * max(1.0, abs(float(g["loss"])))
     net.zero_grad()
     loss.backward()
-    _check([(n, p.grad) for n, p in net.named_parameters()], g, "dgrad", 1e-2)
+    _check([(n, p.grad) for n, p in net.named_parameters()], g, "dgrad", 3e-3)
 
 
 @pytest.mark.parametrize("tag,pert,rkw", [
@@ -83,7 +85,7 @@ def test_render_loss_param_grads_vs_reference(golden, tag, pert, rkw):
     for m in (net, var, beta):
         m.zero_grad()
     loss.backward()
-    rel = 1e-2
+    rel = 2e-3
     _check([(n, p.grad) for n, p in net.named_parameters()], g, "dloss", rel)
     for name, p in (("variance", var.variance), ("beta", beta.beta), ("gamma", beta.gamma)):
         ref = g[f"dloss.{name}"]

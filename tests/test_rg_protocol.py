@@ -8,7 +8,10 @@ with mbarrier phase-parity semantics.  The model raises on
   * a wait that passes on an aliased phase (detected through the data hazards below),
   * ring stage overwritten while an MMA still reads it / consumed before its copy landed,
   * A-tile chunk written while an MMA reading it is in flight, or an MMA reading the wrong version,
-  * TMEM accumulator overwritten before all 16 epilogue warps have read it, or read before complete.
+  * TMEM accumulator overwritten before all 16 epilogue warps have read it, or read before complete,
+  * the positional-encoding image of a tile (global scratch, double buffered, written by all 16 epilogue warps
+    during the previous tile's reverse steps) copied into chunk 0 by the TMA engine before it is complete,
+    overwritten while a copy reads it, or the copy landing in chunk 0 under a running MMA.
 It does not model the arithmetic (tests/test_rg_emulation.py does) nor PTX memory-ordering fences.
 """
 import heapq
@@ -68,7 +71,11 @@ class Sim:
         self.ns = ns
         self.full = [MBar(f"full{i}", 1) for i in range(ns)]
         self.empty = [MBar(f"empty{i}", 1) for i in range(ns)]
-        self.a_ready = [MBar(f"a_ready{i}", EPI_WARPS) for i in range(4)] + [MBar("a_ready4", 8)]
+        self.a_ready = [MBar(f"a_ready{i}", EPI_WARPS) for i in range(4)] + [MBar("a_ready4", 1)]
+        self.pe_done = MBar("pe_done", EPI_WARPS)
+        self.img_ver = [[None] * EPI_WARPS for _ in range(2)]     # PE image b: tile iteration each warp wrote
+        self.img_readers = [0, 0]                                   # TMA copies in flight reading image b
+        self.chunk0_copy = False                                    # a PE copy into chunk 0 is in flight
         self.acc_full = [[MBar(f"acc_full{b}{h}", 1) for h in range(2)] for b in range(2)]   # [buf][N half]
         self.acc_empty = [MBar("acc_empty0", EPI_WARPS), MBar("acc_empty1", EPI_WARPS)]
         self.c0_free = MBar("c0_free", 1)
@@ -153,6 +160,28 @@ class Sim:
             self.full[stage].complete_tx(1)
         self.at(self.lat(0.5, 6.0), land)
 
+    def pe_copy(self, it, s, b):
+        """TMA bulk copy of PE image b (tile iteration `it`) into A chunk 0, as the PE operand of step s"""
+        for w in range(EPI_WARPS):
+            if self.img_ver[b][w] != it:
+                raise Hazard(f"PE copy for {(it, s)} reads image {b}: warp {w} wrote {self.img_ver[b][w]}")
+        if self.chunk_readers[0]:
+            raise Hazard(f"PE copy for {(it, s)} issued into chunk 0 under {self.chunk_readers[0]} MMAs in flight")
+        if self.chunk0_copy:
+            raise Hazard("two PE copies in flight")
+        self.chunk0_copy = True
+        self.img_readers[b] += 1
+
+        def land():
+            if self.chunk_readers[0]:
+                raise Hazard(f"PE copy for {(it, s)} lands in chunk 0 under a running MMA")
+            self.chunk0_copy = False
+            self.img_readers[b] -= 1
+            for w in range(EPI_WARPS):
+                self.chunk_ver[0][w] = ("PE", it, s)
+            self.a_ready[4].complete_tx(1)
+        self.at(self.lat(0.5, 6.0), land)
+
     def mma_group(self, it, s, ic, parts, chunk, buf, first):
         """the MMAs of one K chunk over the given [(part, ring stage)]: read ring stages + A chunk,
         accumulate into TMEM buf"""
@@ -161,8 +190,7 @@ class Sim:
                 raise Hazard(f"MMA {(it, s, ic, part)} reads ring stage {stage} holding {self.stage_data[stage]}")
         want = ("PE", it, s) if chunk == 4 else (it, s)
         phys = 0 if chunk == 4 else chunk
-        writers = range(8) if chunk == 4 else range(EPI_WARPS)      # warps sub<2 = warps 0..7 write the PE
-        for w in writers:
+        for w in range(EPI_WARPS):
             if self.chunk_ver[phys][w] != want:
                 raise Hazard(f"MMA {(it, s, ic)} reads chunk {phys}: warp {w} wrote {self.chunk_ver[phys][w]}, want {want}")
         if first:
@@ -265,7 +293,17 @@ class Sim:
     def _write_chunk(self, w, phys, tag):
         if self.chunk_readers[phys]:
             raise Hazard(f"warp {w} writes chunk {phys} ({tag}) under {self.chunk_readers[phys]} MMAs in flight")
+        if phys == 0 and self.chunk0_copy:
+            raise Hazard(f"warp {w} writes chunk 0 ({tag}) while a PE copy into it is in flight")
         self.chunk_ver[phys][w] = tag
+
+    def _encode(self, w, it):
+        """this warp's part of the PE image of tile iteration `it` -> global scratch image it & 1"""
+        b = it & 1
+        if self.img_readers[b]:
+            raise Hazard(f"warp {w} overwrites PE image {b} (tile {it}) under a copy in flight")
+        self.img_ver[b][w] = it
+        self.pe_done.arrive()
 
     def _read_acc(self, w, buf, it, s, half):
         if self.acc_ver[buf][half] != (it, s):
@@ -274,12 +312,15 @@ class Sim:
 
     def epilogue(self, w):
         sub = w >> 2
+        # prologue: encode tile 0; warp 0 hands the image to the TMA engine
+        yield ("delay", self.lat(0.2, 1.5))
+        self._encode(w, 0)
+        if w == 0:
+            if not getattr(self, "skip_pe_wait", False):
+                yield ("wait", self.pe_done, 0)
+            self.a_ready[4].arrive(tx=1)
+            self.pe_copy(0, 0, 0)
         for it in range(self.iters):
-            # input stage: PE -> chunk 0
-            if sub < 2:
-                yield ("delay", self.lat(0.2, 1.5))
-                self._write_chunk(w, 0, ("PE", it, 0))
-                self.a_ready[4].arrive()
             # forward layers 0..7
             for l in range(8):
                 buf = l & 1
@@ -294,11 +335,10 @@ class Sim:
                     self.a_ready[chunk].arrive()
                 self.acc_reads_left[buf] -= 1
                 self.acc_empty[buf].arrive()
-                if l == SKIP - 1 and sub < 2:
+                if l == SKIP - 1 and w == 0:
                     yield ("wait", self.c0_free, it & 1)
-                    yield ("delay", self.lat(0.2, 1.5))
-                    self._write_chunk(w, 0, ("PE", it, SKIP))
-                    self.a_ready[4].arrive()
+                    self.a_ready[4].arrive(tx=1)
+                    self.pe_copy(it, SKIP, it & 1)
             # (layer 7's epilogue above wrote the sweep's seed alpha_7 as the input of step 8)
             # reverse steps 8..14
             for s in range(8, 15):
@@ -314,8 +354,16 @@ class Sim:
                     self.a_ready[chunk].arrive()
                 self.acc_reads_left[buf] -= 1
                 self.acc_empty[buf].arrive()
+                if s == 8 and it + 1 < self.iters:        # the next tile's PE, in the MMA-bound reverse steps
+                    yield ("delay", self.lat(0.2, 1.5))
+                    self._encode(w, it + 1)
             # step 15: PE adjoint -> gradient; the exchange slots live in chunk 3 of the (dead) A tile
             yield ("wait", self.acc_full[1][0], (it * USES[1] + 7) & 1)
+            if w == 0 and it + 1 < self.iters:            # chunk 0 is free: next tile's PE image on its way
+                if not getattr(self, "skip_pe_wait", False):
+                    yield ("wait", self.pe_done, (it + 1) & 1)
+                self.a_ready[4].arrive(tx=1)
+                self.pe_copy(it + 1, 0, (it + 1) & 1)
             self._read_acc(w, 1, it, 15, 0)
             self.acc_reads_left[1] -= 1
             self.acc_empty[1].arrive()
@@ -341,6 +389,21 @@ def test_protocol_under_heavy_tailed_latencies(nterms, split, monkeypatch):
     monkeypatch.setattr(Sim, "lat", _heavy_tailed)
     for seed in range(300, 340):
         Sim(nterms, iters=4, seed=seed, split_tail=split).run()
+
+
+def test_model_detects_a_pe_copy_before_the_image_is_complete():
+    """the PE hand-off has teeth too: without the pe_done wait the first TMA copy reads a half-written image
+    (later tiles are also covered by the data dependencies of the sweep -- every warp's step-9 epilogue comes
+    after its encoding -- there pe_done supplies the release/acquire ordering of the image's global stores)"""
+    caught = 0
+    for seed in range(20):
+        sim = Sim(3, iters=2, seed=seed)
+        sim.skip_pe_wait = True
+        try:
+            sim.run()
+        except AssertionError:
+            caught += 1
+    assert caught > 0
 
 
 def test_model_detects_a_wrong_parity():
@@ -384,7 +447,9 @@ def test_model_constants_match_the_cuda_source():
     assert const("kUsesPerBuf") == USES[0] == USES[1]
     assert const("kAPerTile") == A_PER_TILE
     assert re.search(r"kStages = \(NTERMS == 3\) \? 3 : 4;", src) and K_STAGES == {3: 3, 1: 4}
-    assert re.search(r"mbar_init\(&a_ready\[c\], kEpiWarps\)", src) and re.search(r"mbar_init\(&a_ready\[4\], 8\)", src)
+    assert re.search(r"mbar_init\(&a_ready\[c\], kEpiWarps\)", src) and re.search(r"mbar_init\(&a_ready\[4\], 1\)", src)
+    assert re.search(r"mbar_init\(pe_done, kEpiWarps\)", src)
+    assert "mbar_wait(pe_done, (uint32_t)(iter + 1) & 1" in src and "mbar_wait(pe_done, 0" in src
     assert re.search(r"mbar_init\(&acc_empty\[b\], kEpiWarps\)", src)
     assert "uses & 1" in src and "(uint32_t)iter * kAPerTile + (uint32_t)(s - 1)" in src
     assert "(uint32_t)iter * 2u + (s == kSkipLayer ? 1u : 0u)" in src

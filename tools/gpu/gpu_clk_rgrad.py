@@ -16,10 +16,12 @@ net.fold(torch.cat([t.reshape(-1) for t in p.tensors()]).cuda())
 buf = torch.zeros(176, dtype=torch.int64, device="cuda")
 C.lib().emap_debug_set_clk_buffer(C.ptr(buf))
 names = [f"fwd L{l}" for l in range(8)] + [f"rev L{l}" for l in range(7, -1, -1)]
-for flags in (0, 1):
+# a steady-state tile: full-size launch (1 M points, 56 tiles per CTA), the 30th tile of block 0
+C.set_option("dbg_iter", 30)
+for flags in (0,):
     C.set_option("rg_flags", flags)
     for prec in (3, 1):
-        x = (torch.rand(148 * 128 * 3, 3, device="cuda") * 2 - 1) * 1.5      # three tiles per CTA
+        x = (torch.rand(1 << 20, 3, device="cuda") * 2 - 1) * 1.5
         buf.zero_()
         ops.debug_rgrad(net, prec, x)
         torch.cuda.synchronize()
@@ -34,4 +36,5 @@ for flags in (0, 1):
         m = [int(v) - t0 if v else -1 for v in b[64 + 60:64 + 64]]
         print(f"  step 15 {names[15]}: mma {m}", flush=True)
 C.set_option("rg_flags", 0)
+C.set_option("dbg_iter", 1)
 C.lib().emap_debug_set_clk_buffer(None)
