@@ -58,10 +58,13 @@ struct Args {
   MlpArgs m;
   uint32_t* scratch;     // [grid][kSigmaWordsPerCta]
   uint8_t* pe_scratch;   // [grid][2][kPeImageBytes]
+  unsigned int* tile_counter;   // dynamic scheduling: tiles grid, grid+1, ... are handed out in arrival order
   int flags;             // emap_set_option("rg_flags", bits): kFlagSplitTail
 };
 constexpr int kFlagSplitTail = 1;   // N-split of each step's last K chunk (as K1g does; A/B switch for bring-up)
 constexpr int kFlagL2Persist = 2;   // host side: launch with the sigma scratch as a persisting-L2 access window
+constexpr int kFlagDynamic = 8;     // tiles handed out by a global atomic counter instead of the static round robin
+constexpr int kFlagPipeLd = 4;      // host side: select the PIPE instantiation (tcgen05.ld one chunk ahead)
 
 template <int NTERMS>
 struct Plan {
@@ -169,7 +172,8 @@ __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
 
-template <int NTERMS, typename T>
+// PIPE: the accumulator chunk c+1 is fetched from TMEM (tcgen05.ld) while chunk c is being converted.
+template <int NTERMS, typename T, bool PIPE>
 __global__ void __launch_bounds__(kThreads, 1) mlp_rgrad_kernel(const Args args) {
   using P = Plan<NTERMS>;
   constexpr int kStages = P::kStages;
@@ -195,22 +199,31 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_rgrad_kernel(const Args args)
   uint64_t* c0_free = bars + 19;          // layer 4 has consumed chunk 0 -> the PE image may be copied there again
   uint64_t* pe_done = bars + 20;          // all 16 epilogue warps have written their part of a PE image
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 21);
+  // Tile schedule: the tile of iteration k is published in sched_tile[k & 1] by completion k of sched_ready
+  // (one thread of epilogue warp 0, during step 2 of iteration k-1: every role has consumed completion k-1 by
+  // then, so the parity wait cannot alias).  A tile index >= num_tiles ends every role's loop.
+  uint64_t* sched_ready = bars + 22;
+  volatile int* sched_tile = reinterpret_cast<volatile int*>(bars + 23);
 
   if (warp == kProducerWarp && lane == 0) {
     for (int s = 0; s < kStages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
     for (int c = 0; c < 4; ++c) mbar_init(&a_ready[c], kEpiWarps);
     mbar_init(&a_ready[4], 1);            // one arrive.expect_tx by the thread that issues the PE bulk copy
     mbar_init(pe_done, kEpiWarps);
+    mbar_init(sched_ready, 1);
+    sched_tile[0] = (int)blockIdx.x;
     for (int b = 0; b < 4; ++b) mbar_init(&acc_full[b], 1);
     for (int b = 0; b < 2; ++b) mbar_init(&acc_empty[b], kEpiWarps);
     mbar_init(c0_free, 1);
     fence_barrier_init();
+    mbar_arrive(sched_ready);             // completion 0: iteration 0 runs tile blockIdx.x
   }
   if (warp == kMmaWarp) { tmem_alloc(tmem_slot, 512); tmem_relinquish(); }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  const long long t_block0 = m.dbg_clk ? clock64() : 0;     // debug entry only: per-block elapsed cycles
 
   if (warp == kProducerWarp) {
     // ===================================== producer =====================================
@@ -221,7 +234,9 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_rgrad_kernel(const Args args)
     const uint8_t* img_r = m.packed + hdr->reserved[3];      // reverse image stream (pack.cu: build_layout)
     uint8_t* ring = smem + P::ring;
     uint32_t stage = 0, round = 0;
-    for (int iter = 0; iter < m.iters; ++iter) {
+    for (int iter = 0;; ++iter) {
+      mbar_wait(sched_ready, (uint32_t)iter & 1, 560);
+      if (sched_tile[iter & 1] >= m.num_tiles) break;
       uint32_t off = 0;
 #pragma unroll 1
       for (int s = 0; s < kSteps; ++s) {
@@ -250,7 +265,9 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_rgrad_kernel(const Args args)
     const uint32_t idesc256 = make_idesc_f16(128, 256, Elem<T>::fmt);
     const uint32_t idesc64 = make_idesc_f16(128, 64, Elem<T>::fmt);
     uint32_t stage = 0, round = 0;
-    for (int iter = 0; iter < m.iters; ++iter) {
+    for (int iter = 0;; ++iter) {
+      mbar_wait(sched_ready, (uint32_t)iter & 1, 561);
+      if (sched_tile[iter & 1] >= m.num_tiles) break;
 #pragma unroll
       for (int s = 0; s < kSteps; ++s) {
         const int buf = s & 1;
@@ -375,8 +392,7 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_rgrad_kernel(const Args args)
       if (NTERMS == 3) bulk_g2s(A_lo, pe_img + (size_t)b * kPeImageBytes + kChunkBytes, kChunkBytes, &a_ready[4]);
     };
     // encode the points of tile iteration `it` into image it & 1 (all 16 warps, 16 columns of a row each)
-    auto encode_tile = [&](int it) {
-      const long long t2 = (long long)blockIdx.x + (long long)it * gridDim.x;
+    auto encode_tile = [&](int it, long long t2) {
       const long long p2 = t2 * 128 + row;
       float xn[3];
       load_point(m, p2, net_scale, xn);
@@ -385,15 +401,26 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_rgrad_kernel(const Args args)
       __syncwarp();
       if (lane == 0) mbar_arrive(pe_done);
     };
-    encode_tile(0);
+    encode_tile(0, (long long)blockIdx.x);
     if (warp == 0) {
       mbar_wait(pe_done, 0, 550);
       if (lane == 0) issue_pe_copy(0);
       __syncwarp();
     }
+    const bool scheduler = (warp == 0 && lane == 0);
+    const bool dynamic = (args.flags & kFlagDynamic) != 0;
 
-    for (int iter = 0; iter < m.iters; ++iter) {
-      const long long tile = (long long)blockIdx.x + (long long)iter * gridDim.x;
+    for (int iter = 0;; ++iter) {
+      mbar_wait(sched_ready, (uint32_t)iter & 1, 562);
+      const long long tile = (long long)sched_tile[iter & 1];
+      if (tile >= m.num_tiles) break;
+      // the tile after this one: fetched now (an L2 atomic in dynamic mode), published during step 2
+      int next_tile = 0;
+      if (scheduler) {
+        const long long nt = dynamic ? (long long)gridDim.x + (long long)atomicAdd(args.tile_counter, 1u)
+                                     : tile + (long long)gridDim.x;
+        next_tile = (nt < (long long)m.num_tiles) ? (int)nt : m.num_tiles;
+      }
       const long long pt = tile * 128 + row;
       const bool ok = (tile < m.num_tiles) && (pt < m.P);
       // (the PE image of this tile is already on its way into chunk 0: nothing to do at tile start)
@@ -411,19 +438,35 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_rgrad_kernel(const Args args)
         mbar_wait(&acc_full[buf * 2], acc_par, 500 + buf, l);
         tc_fence_after();
         if (stamp) m.dbg_clk[4 * l + 1] = clock64();
+        if (l == 2 && scheduler) {              // all 16 warps are past step 1 of this tile, i.e. past its schedule wait
+          sched_tile[(iter + 1) & 1] = next_tile;
+          mbar_arrive(sched_ready);
+        }
         const float* bl = bias100 + l * kHidden;
+        uint32_t rn[16];                        // PIPE: the chunk in flight
+        if (PIPE) tmem_ld_32x32b_x16(lane_taddr + (uint32_t)(buf * 256 + sub * 16), rn);
 #pragma unroll 1
         for (int chunk = 0; chunk < 4; ++chunk) {
           uint8_t* dst_hi = A_hi + chunk * kChunkBytes;
           uint8_t* dst_lo = A_lo + chunk * kChunkBytes;
           const int col0 = chunk * 64 + sub * 16;
-          if (chunk == 2) { mbar_wait(&acc_full[buf * 2 + 1], acc_par, 505 + buf, l); tc_fence_after(); }
+          if (!PIPE && chunk == 2) { mbar_wait(&acc_full[buf * 2 + 1], acc_par, 505 + buf, l); tc_fence_after(); }
           float4 bv[4];
 #pragma unroll
           for (int i = 0; i < 4; ++i) bv[i] = __ldg(reinterpret_cast<const float4*>(bl + col0) + i);
           uint32_t r[16];
-          tmem_ld_32x32b_x16(lane_taddr + (uint32_t)(buf * 256 + col0), r);
-          tmem_wait_ld();
+          if (PIPE) {
+            tmem_wait_ld_regs(rn);
+#pragma unroll
+            for (int k = 0; k < 16; ++k) r[k] = rn[k];
+            if (chunk < 3) {
+              if (chunk == 1) { mbar_wait(&acc_full[buf * 2 + 1], acc_par, 505 + buf, l); tc_fence_after(); }
+              tmem_ld_32x32b_x16(lane_taddr + (uint32_t)(buf * 256 + col0 + 64), rn);
+            }
+          } else {
+            tmem_ld_32x32b_x16(lane_taddr + (uint32_t)(buf * 256 + col0), r);
+            tmem_wait_ld();
+          }
           if (m.dbg_acc && tile == 0) {
 #pragma unroll
             for (int k = 0; k < 16; ++k)
@@ -510,13 +553,25 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_rgrad_kernel(const Args args)
         mbar_wait(&acc_full[buf * 2], acc_par, 530 + buf, s);
         tc_fence_after();
         if (stamp) m.dbg_clk[4 * s + 1] = clock64();
+        uint32_t rn[16];                        // PIPE: the chunk in flight
+        if (PIPE) tmem_ld_32x32b_x16(lane_taddr + (uint32_t)(buf * 256 + sub * 16), rn);
 #pragma unroll
         for (int chunk = 0; chunk < 4; ++chunk) {
           const int col0 = chunk * 64 + sub * 16;
-          if (chunk == 2) { mbar_wait(&acc_full[buf * 2 + 1], acc_par, 535 + buf, s); tc_fence_after(); }
+          if (!PIPE && chunk == 2) { mbar_wait(&acc_full[buf * 2 + 1], acc_par, 535 + buf, s); tc_fence_after(); }
           uint32_t r[16];
-          tmem_ld_32x32b_x16(lane_taddr + (uint32_t)(buf * 256 + col0), r);
-          tmem_wait_ld();
+          if (PIPE) {
+            tmem_wait_ld_regs(rn);
+#pragma unroll
+            for (int k = 0; k < 16; ++k) r[k] = rn[k];
+            if (chunk < 3) {
+              if (chunk == 1) { mbar_wait(&acc_full[buf * 2 + 1], acc_par, 535 + buf, s); tc_fence_after(); }
+              tmem_ld_32x32b_x16(lane_taddr + (uint32_t)(buf * 256 + col0 + 64), rn);
+            }
+          } else {
+            tmem_ld_32x32b_x16(lane_taddr + (uint32_t)(buf * 256 + col0), r);
+            tmem_wait_ld();
+          }
           if (m.dbg_acc && tile == 0) {
 #pragma unroll
             for (int k = 0; k < 16; ++k)
@@ -555,7 +610,11 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_rgrad_kernel(const Args args)
         if (lane == 0) mbar_arrive(&acc_empty[buf]);
         if (stamp) m.dbg_clk[4 * s + 3] = clock64();
         // the reverse steps are MMA-bound: the gap after the first one takes the encoding of the NEXT tile
-        if (s == 8 && iter + 1 < m.iters) encode_tile(iter + 1);
+        if (s == 8) {
+          mbar_wait(sched_ready, (uint32_t)(iter + 1) & 1, 563);      // published in step 2: immediate
+          const long long nt = (long long)sched_tile[(iter + 1) & 1];
+          if (nt < m.num_tiles) encode_tile(iter + 1, nt);
+        }
       }
 
       // ------------------------------------------------ step 15: alpha_0 W_0 (64 PE slots) -> d udf / d x
@@ -565,7 +624,7 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_rgrad_kernel(const Args args)
         mbar_wait(&acc_full[2], ((uint32_t)iter * kUsesPerBuf + 7u) & 1, 540);   // buf 1 (both halves commit together)
         tc_fence_after();
         // every MMA of this tile has completed: chunk 0 is free, the next tile's PE image can go in now
-        if (warp == 0 && iter + 1 < m.iters) {
+        if (warp == 0 && sched_tile[(iter + 1) & 1] < m.num_tiles) {
           mbar_wait(pe_done, (uint32_t)(iter + 1) & 1, 551);
           if (lane == 0) issue_pe_copy((iter + 1) & 1);
           __syncwarp();
@@ -612,13 +671,28 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_rgrad_kernel(const Args args)
   tc_fence_before();
   __syncthreads();
   if (warp == kMmaWarp) tmem_dealloc(tmem_base, 512);
+  if (m.dbg_clk && threadIdx.x == 0) {                      // load-balance diagnostic: dbg_clk[256 + 2 b + {0,1}]
+    uint32_t smid;
+    asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+    m.dbg_clk[256 + 2 * blockIdx.x] = clock64() - t_block0;
+    m.dbg_clk[256 + 2 * blockIdx.x + 1] = (long long)smid;
+  }
 }
 
 static int g_flags = 0;   // emap_set_option("rg_flags", bits)
 int set_flags(int v) { g_flags = v; return 0; }
 
+template <int NTERMS, typename T, bool PIPE>
+static int launch_p(const Args& a_in, size_t scratch_bytes, cudaStream_t stream);
+
 template <int NTERMS, typename T>
 static int launch(const Args& a_in, size_t scratch_bytes, cudaStream_t stream) {
+  if (g_flags & kFlagPipeLd) return launch_p<NTERMS, T, true>(a_in, scratch_bytes, stream);
+  return launch_p<NTERMS, T, false>(a_in, scratch_bytes, stream);
+}
+
+template <int NTERMS, typename T, bool PIPE>
+static int launch_p(const Args& a_in, size_t scratch_bytes, cudaStream_t stream) {
   Args a = a_in;
   a.flags = g_flags;
   const long long tiles = (a.m.P + 127) / 128;
@@ -628,11 +702,13 @@ static int launch(const Args& a_in, size_t scratch_bytes, cudaStream_t stream) {
   if (tiles < grid) grid = (int)tiles;
   a.m.iters = (int)((tiles + grid - 1) / grid);
   const size_t sigma_bytes = (size_t)grid * kSigmaWordsPerCta * sizeof(uint32_t);
-  if (scratch_bytes < sigma_bytes + (size_t)grid * kPeBytesPerCta)
+  if (scratch_bytes < sigma_bytes + (size_t)grid * kPeBytesPerCta + 256)
     return set_error("emap_udf_forward_grad_rev: scratch too small (%zu bytes, need %zu)", scratch_bytes,
-                     sigma_bytes + (size_t)grid * kPeBytesPerCta);
+                     sigma_bytes + (size_t)grid * kPeBytesPerCta + 256);
   a.pe_scratch = reinterpret_cast<uint8_t*>(a.scratch) + sigma_bytes;      // PE images behind the sigma slices
-  auto kern = mlp_rgrad_kernel<NTERMS, T>;
+  a.tile_counter = reinterpret_cast<unsigned int*>(a.pe_scratch + (size_t)grid * kPeBytesPerCta);
+  if (a.flags & kFlagDynamic) EMAP_CUDA(cudaMemsetAsync(a.tile_counter, 0, sizeof(unsigned int), stream));
+  auto kern = mlp_rgrad_kernel<NTERMS, T, PIPE>;
   static bool attr_done = false;   // per template instantiation
   if (!attr_done) {
     EMAP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Plan<NTERMS>::total));
@@ -693,7 +769,7 @@ extern "C" int emap_debug_pe_adjoint(const float* adj16, int kbase, const float*
 }
 
 extern "C" size_t emap_rgrad_scratch_bytes(void) {
-  return (size_t)sm_count() * (rg::kSigmaWordsPerCta * sizeof(uint32_t) + rg::kPeBytesPerCta);
+  return (size_t)sm_count() * (rg::kSigmaWordsPerCta * sizeof(uint32_t) + rg::kPeBytesPerCta) + 256;
 }
 
 extern "C" int emap_udf_forward_grad_rev(const emap_net_desc* net, const void* packed, int precision,

@@ -73,6 +73,11 @@ class Sim:
         self.empty = [MBar(f"empty{i}", 1) for i in range(ns)]
         self.a_ready = [MBar(f"a_ready{i}", EPI_WARPS) for i in range(4)] + [MBar("a_ready4", 1)]
         self.pe_done = MBar("pe_done", EPI_WARPS)
+        # tile schedule: completion k of sched_ready publishes the tile of iteration k in sched_tile[k & 1]
+        # (True = a tile, False = past the end); completion 0 is made at barrier initialisation
+        self.sched_ready = MBar("sched_ready", 1)
+        self.sched_tile = [True, None]
+        self.sched_ready.arrive()
         self.img_ver = [[None] * EPI_WARPS for _ in range(2)]     # PE image b: tile iteration each warp wrote
         self.img_readers = [0, 0]                                   # TMA copies in flight reading image b
         self.chunk0_copy = False                                    # a PE copy into chunk 0 is in flight
@@ -223,9 +228,21 @@ class Sim:
         self.at(t - self.now + 1e-9, fn)
 
     # ------------------------------------------------------------------ roles (mirroring mlp_rg.cu)
+    def _schedule(self, it):
+        """what every role does at the top of iteration `it` (after the wait): read the published slot"""
+        v = self.sched_tile[it & 1]
+        if v is None:
+            raise Hazard(f"iteration {it}: schedule slot read before it was published")
+        return v
+
     def producer(self):
         stage, rnd = 0, 0
-        for it in range(self.iters):
+        it = -1
+        while True:
+            it += 1
+            yield ("wait", self.sched_ready, it & 1)
+            if not self._schedule(it):
+                return
             for s in range(K_STEPS):
                 for ip in range(step_nkc(s) * 2):
                     if self.nterms == 1 and (ip & 1):
@@ -241,7 +258,12 @@ class Sim:
 
     def issuer(self):
         stage, rnd = 0, 0
-        for it in range(self.iters):
+        it = -1
+        while True:
+            it += 1
+            yield ("wait", self.sched_ready, it & 1)
+            if not self._schedule(it):
+                return
             for s in range(K_STEPS):
                 buf = s & 1
                 started = it * USES[buf] + (s >> 1)
@@ -320,12 +342,20 @@ class Sim:
                 yield ("wait", self.pe_done, 0)
             self.a_ready[4].arrive(tx=1)
             self.pe_copy(0, 0, 0)
-        for it in range(self.iters):
+        it = -1
+        while True:
+            it += 1
+            yield ("wait", self.sched_ready, it & 1)
+            if not self._schedule(it):
+                return
             # forward layers 0..7
             for l in range(8):
                 buf = l & 1
                 par = (it * USES[buf] + (l >> 1)) & 1
                 yield ("wait", self.acc_full[buf][0], par)
+                if l == getattr(self, "publish_layer", 2) and w == 0:   # the scheduler thread publishes iteration it + 1
+                    self.sched_tile[(it + 1) & 1] = (it + 1 < self.iters)
+                    self.sched_ready.arrive()
                 for chunk in range(4):
                     if chunk == 2:
                         yield ("wait", self.acc_full[buf][1], par)
@@ -354,12 +384,14 @@ class Sim:
                     self.a_ready[chunk].arrive()
                 self.acc_reads_left[buf] -= 1
                 self.acc_empty[buf].arrive()
-                if s == 8 and it + 1 < self.iters:        # the next tile's PE, in the MMA-bound reverse steps
-                    yield ("delay", self.lat(0.2, 1.5))
-                    self._encode(w, it + 1)
+                if s == 8:                                # the next tile's PE, in the MMA-bound reverse steps
+                    yield ("wait", self.sched_ready, (it + 1) & 1)
+                    if self._schedule(it + 1):
+                        yield ("delay", self.lat(0.2, 1.5))
+                        self._encode(w, it + 1)
             # step 15: PE adjoint -> gradient; the exchange slots live in chunk 3 of the (dead) A tile
             yield ("wait", self.acc_full[1][0], (it * USES[1] + 7) & 1)
-            if w == 0 and it + 1 < self.iters:            # chunk 0 is free: next tile's PE image on its way
+            if w == 0 and self._schedule(it + 1):         # chunk 0 is free: next tile's PE image on its way
                 if not getattr(self, "skip_pe_wait", False):
                     yield ("wait", self.pe_done, (it + 1) & 1)
                 self.a_ready[4].arrive(tx=1)
@@ -399,6 +431,21 @@ def test_model_detects_a_pe_copy_before_the_image_is_complete():
     for seed in range(20):
         sim = Sim(3, iters=2, seed=seed)
         sim.skip_pe_wait = True
+        try:
+            sim.run()
+        except AssertionError:
+            caught += 1
+    assert caught > 0
+
+
+def test_model_detects_a_schedule_published_too_early(monkeypatch):
+    """publishing the next tile before every role has consumed the current completion (during step 0 instead of
+    step 2) lets a straggler wait on an aliased parity: caught as a deadlock"""
+    monkeypatch.setattr(Sim, "lat", _heavy_tailed)
+    caught = 0
+    for seed in range(60):
+        sim = Sim(3, iters=4, seed=seed)
+        sim.publish_layer = 0
         try:
             sim.run()
         except AssertionError:
@@ -450,6 +497,8 @@ def test_model_constants_match_the_cuda_source():
     assert re.search(r"mbar_init\(&a_ready\[c\], kEpiWarps\)", src) and re.search(r"mbar_init\(&a_ready\[4\], 1\)", src)
     assert re.search(r"mbar_init\(pe_done, kEpiWarps\)", src)
     assert "mbar_wait(pe_done, (uint32_t)(iter + 1) & 1" in src and "mbar_wait(pe_done, 0" in src
+    assert re.search(r"mbar_init\(sched_ready, 1\)", src) and src.count("mbar_wait(sched_ready, (uint32_t)iter & 1") == 3
+    assert "if (l == 2 && scheduler)" in src and "mbar_wait(sched_ready, (uint32_t)(iter + 1) & 1" in src
     assert re.search(r"mbar_init\(&acc_empty\[b\], kEpiWarps\)", src)
     assert "uses & 1" in src and "(uint32_t)iter * kAPerTile + (uint32_t)(s - 1)" in src
     assert "(uint32_t)iter * 2u + (s == kSkipLayer ? 1u : 0u)" in src

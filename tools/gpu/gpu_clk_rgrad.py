@@ -13,7 +13,7 @@ from tests.helpers import oracle_params  # noqa: E402
 p = oracle_params(True)
 net = ops.PackedNet(10)
 net.fold(torch.cat([t.reshape(-1) for t in p.tensors()]).cuda())
-buf = torch.zeros(176, dtype=torch.int64, device="cuda")
+buf = torch.zeros(1024, dtype=torch.int64, device="cuda")
 C.lib().emap_debug_set_clk_buffer(C.ptr(buf))
 names = [f"fwd L{l}" for l in range(8)] + [f"rev L{l}" for l in range(7, -1, -1)]
 # a steady-state tile: full-size launch (1 M points, 56 tiles per CTA), the 30th tile of block 0
@@ -35,6 +35,13 @@ for flags in (0,):
             print(f"  step {s:2d} {names[s]}: epi {e}   mma {m}", flush=True)
         m = [int(v) - t0 if v else -1 for v in b[64 + 60:64 + 64]]
         print(f"  step 15 {names[15]}: mma {m}", flush=True)
+        per = b[256:256 + 2 * 148].reshape(148, 2)
+        cyc = per[:, 0].double()
+        order = torch.argsort(cyc)
+        print(f"  per-block elapsed cycles: min {cyc.min():.0f} median {cyc.median():.0f} max {cyc.max():.0f} "
+              f"(max/min {cyc.max() / cyc.min():.3f}); slowest blocks (block, smid, Mclk): "
+              f"{[(int(i), int(per[i, 1]), round(float(cyc[i]) / 1e6, 2)) for i in order[-6:]]}; fastest: "
+              f"{[(int(i), int(per[i, 1]), round(float(cyc[i]) / 1e6, 2)) for i in order[:6]]}", flush=True)
 C.set_option("rg_flags", 0)
 C.set_option("dbg_iter", 1)
 C.lib().emap_debug_set_clk_buffer(None)
