@@ -65,9 +65,10 @@ SIGNATURES = {
     "emap_bwd_cotangent_scales": (ctypes.c_int, [_vp, _vp, _i64, _vp, _vp]),
     "emap_bwd_dual_forward": (ctypes.c_int, [_nd, _vp, _i32, _vp, _vp, _vp, _vp, _i32, _i64, _vp, _vp, _vp, _vp, _vp]),
     "emap_bwd_reverse_sweep": (ctypes.c_int, [_nd, _vp, _vp, _vp, _vp, _i64, _vp]),
-    "emap_bwd_bias_sums": (ctypes.c_int, [_vp, _i64, _vp, _vp, _vp]),
-    "emap_bwd_top": (ctypes.c_int, [_nd, _vp, _vp, _vp, _vp, _vp, _i64, _vp, _vp]),
-    "emap_bwd_weight_norm": (ctypes.c_int, [_nd, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "emap_bwd_workspace_bytes": (ctypes.c_size_t, []),
+    "emap_bwd_weight_grads": (ctypes.c_int, [_nd, _vp, _vp, _vp, _i64, _vp, ctypes.c_size_t, _vp]),
+    "emap_bwd_finish": (ctypes.c_int, [_nd, _vp, _vp, _i32, _vp, _vp, _vp, _vp]),
+    "emap_bwd_top": (ctypes.c_int, [_nd, _vp, _vp, _vp, _vp, _vp, _i64, _vp, _vp, _vp]),
     "emap_packed_offsets": (ctypes.c_int, [_nd, _vp]),
     "emap_null_direction": (ctypes.c_int, [_vp, _i64, _i32, _vp, _vp]),
     "emap_rays_from_pixels": (ctypes.c_int, [_vp, _vp, _vp, _i32, _i32, _vp, _vp, _i32, _vp, _vp, _vp, _vp,
@@ -83,8 +84,8 @@ LAUNCHES_PER_CALL = {
     "emap_wn_fold": 4, "emap_udf_forward": 1, "emap_udf_forward_grad": 1, "emap_udf_forward_grad_rev": 1, "emap_debug_rgrad": 1, "emap_debug_mlp": 1,
     "emap_coarse_z": 1, "emap_upsample_step": 1, "emap_render_prep": 1, "emap_render_core_fwd": 2,
     "emap_render_core_bwd": 2, "emap_bwd_top": 1, "emap_bwd_cotangent_scales": 2,
-    "emap_bwd_weight_norm": 1, "emap_bwd_dual_forward": 1,
-    "emap_bwd_reverse_sweep": 1, "emap_bwd_tangent_forward": 1, "emap_bwd_bias_sums": 2, "emap_null_direction": 1, "emap_rays_from_pixels": 1,
+    "emap_bwd_weight_grads": 1, "emap_bwd_finish": 1, "emap_bwd_dual_forward": 1,
+    "emap_bwd_reverse_sweep": 1, "emap_bwd_tangent_forward": 1, "emap_null_direction": 1, "emap_rays_from_pixels": 1,
 }
 launch_count = 0
 # bench.py: name of ONE C-ABI entry point whose launches are bracketed by CUDA events on the current

@@ -345,17 +345,6 @@ __device__ __forceinline__ void tmem_ld_32x32b_x16(uint32_t taddr, uint32_t (&r)
       : "r"(taddr)
       : "memory");
 }
-// tcgen05.wait::ld that also names the destination registers of an earlier, still outstanding tcgen05.ld as
-// read-write operands: their consumers then depend on the wait (a load issued one chunk ahead must not have its
-// registers read before this point, and nothing else ties plain register reads to the wait instruction).
-__device__ __forceinline__ void tmem_wait_ld_regs(uint32_t (&r)[16]) {
-  asm volatile("tcgen05.wait::ld.sync.aligned;"
-               : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]),
-                 "+r"(r[8]), "+r"(r[9]), "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]),
-                 "+r"(r[15])
-               :
-               : "memory");
-}
 __device__ __forceinline__ uint32_t tmem_ld_32x32b_x1(uint32_t taddr) {
   uint32_t r;
   asm volatile("tcgen05.ld.sync.aligned.32x32b.x1.b32 {%0}, [%1];" : "=r"(r) : "r"(taddr) : "memory");

@@ -17,6 +17,14 @@ void build_layout(const emap_net_desc& net, PackedHeader& h, std::vector<RingIte
                   std::vector<RingItem>& t3);
 int sm_count();
 
+// Workspace of the backward's weight-gradient stage (emap_bwd_workspace_bytes), in floats:
+//   [sm_count][kDwPartialFloats]  per-CTA partial dW of the nine contraction jobs (mlp_dw.cu: c_jobs offsets)
+//   [sm_count][8][256]            per-CTA partial db_0..7
+//   [kTopBlocks][kTopStride]      per-block partial dW_8[256], db_8 of the output-layer pull-back (mlp_bwd.cu)
+constexpr int kDwPartialFloats = 2 * 256 * 64 + 7 * 256 * 256;
+constexpr int kTopBlocks = 592;
+constexpr int kTopStride = 260;
+
 #define EMAP_CUDA(expr)                                                                          \
   do {                                                                                           \
     cudaError_t _e = (expr);                                                                     \

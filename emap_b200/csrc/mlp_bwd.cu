@@ -12,7 +12,8 @@
 //     [eta_l ; etadot_l] = [alpha_l ; alphadot_l] W_l
 // The dual forward / tangent forward (mlp_tc.cu) and the reverse sweep (mlp_rev.cu) are tcgen05 kernels; this
 // file holds the small stages around them: the cotangent scales (loss scaling of the fp16 arithmetic), the
-// output-layer pull-back, the bias-gradient sums and the weight-norm backward.
+// output-layer pull-back (with dW_8 / db_8) and the final stage -- fixed-order sum of the per-CTA partial
+// gradients of mlp_dw.cu + weight-norm backward.
 #include <math.h>
 
 #include "common.cuh"
@@ -64,49 +65,91 @@ __global__ void cotangent_scales_kernel(float* __restrict__ scales) {
   scales[0] = sg; scales[1] = su; scales[2] = su / sg; scales[3] = 1.f / su;
 }
 
-// Output layer pull-back.  One warp per point:
+// Output layer pull-back, with its own weight gradient.  One warp per point (persistent grid of kTopBlocks
+// blocks), lane = 8 consecutive columns:
 //   a8 = U8[p].w8 + b8, adot8 = U8[P+p].w8 (tangent along S_g Gbar);  udf = f(a8)/scale, f in {abs, square, id}
 //   alpha8 = S_u ubar f'(a8)/scale + (S_u/S_g) f''(a8) adot8 ;  alphadot8 = (S_u/S_g) f'(a8)
 //   coef[p] = alpha8 ; coef[P+p] = alphadot8          (scales NULL: S_g = S_u = 1)
-__global__ void dual_top_kernel(const __half* __restrict__ U8, const float* __restrict__ w8,
-                                const float* __restrict__ b8p, const float* __restrict__ ubar,
-                                const float* __restrict__ scales, long long P, int udf_type, float scale,
-                                float* __restrict__ coef) {
-  const long long p = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  const int lane = threadIdx.x & 31;
-  if (p >= P) return;
-  float dv = 0.f, dt = 0.f;
-  for (int c = lane; c < 256; c += 32) {
-    const float w = w8[c];
-    dv += __half2float(U8[p * 256 + c]) * w;
-    dt += __half2float(U8[(P + p) * 256 + c]) * w;
+//   dW_8 += alpha8 U8[p] + alphadot8 U8[P+p] ;  db_8 += alpha8     -> top_partial[block][kTopStride] (fp32, summed
+//   over the blocks in a fixed order by emap_bwd_finish)
+__global__ void __launch_bounds__(256) dual_top_kernel(const __half* __restrict__ U8, const float* __restrict__ w8,
+                                                       const float* __restrict__ b8p, const float* __restrict__ ubar,
+                                                       const float* __restrict__ scales, long long P, int udf_type,
+                                                       float scale, float* __restrict__ coef,
+                                                       float* __restrict__ top_partial) {
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const long long warps_total = (long long)gridDim.x * 8;
+  float wv[8], accw[8], accb = 0.f;
+  {
+    const float4 a = __ldg(reinterpret_cast<const float4*>(w8 + lane * 8));
+    const float4 b = __ldg(reinterpret_cast<const float4*>(w8 + lane * 8 + 4));
+    wv[0] = a.x; wv[1] = a.y; wv[2] = a.z; wv[3] = a.w; wv[4] = b.x; wv[5] = b.y; wv[6] = b.z; wv[7] = b.w;
   }
-  for (int o = 16; o; o >>= 1) { dv += __shfl_xor_sync(0xffffffffu, dv, o); dt += __shfl_xor_sync(0xffffffffu, dt, o); }
-  const float a = dv + b8p[0], adot = dt;
-  float f1, f2;
-  if (udf_type == 0) { f1 = (a > 0.f) ? 1.f : ((a < 0.f) ? -1.f : 0.f); f2 = 0.f; }
-  else if (udf_type == 1) { f1 = 2.f * a; f2 = 2.f; }
-  else { f1 = 1.f; f2 = 0.f; }
-  const float su = scales ? scales[1] : 1.f, sr = scales ? scales[2] : 1.f;
-  const float ub = ubar ? ubar[p] : 0.f;
-  if (lane == 0) { coef[p] = su * ub * f1 / scale + sr * f2 * adot; coef[P + p] = sr * f1; }
+#pragma unroll
+  for (int j = 0; j < 8; ++j) accw[j] = 0.f;
+  const float su = scales ? scales[1] : 1.f, sr = scales ? scales[2] : 1.f, b8 = b8p[0];
+  for (long long p = (long long)blockIdx.x * 8 + w; p < P; p += warps_total) {
+    const uint4 qv = __ldg(reinterpret_cast<const uint4*>(U8 + p * 256 + lane * 8));
+    const uint4 qt = __ldg(reinterpret_cast<const uint4*>(U8 + (P + p) * 256 + lane * 8));
+    const __half2* hv = reinterpret_cast<const __half2*>(&qv);
+    const __half2* ht = reinterpret_cast<const __half2*>(&qt);
+    float u[8], ud[8], dv = 0.f, dt = 0.f;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float2 a = __half22float2(hv[j]), b = __half22float2(ht[j]);
+      u[2 * j] = a.x; u[2 * j + 1] = a.y; ud[2 * j] = b.x; ud[2 * j + 1] = b.y;
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { dv = fmaf(u[j], wv[j], dv); dt = fmaf(ud[j], wv[j], dt); }
+    for (int o = 16; o; o >>= 1) { dv += __shfl_xor_sync(0xffffffffu, dv, o); dt += __shfl_xor_sync(0xffffffffu, dt, o); }
+    const float a = dv + b8, adot = dt;
+    float f1, f2;
+    if (udf_type == 0) { f1 = (a > 0.f) ? 1.f : ((a < 0.f) ? -1.f : 0.f); f2 = 0.f; }
+    else if (udf_type == 1) { f1 = 2.f * a; f2 = 2.f; }
+    else { f1 = 1.f; f2 = 0.f; }
+    const float ub = ubar ? ubar[p] : 0.f;
+    const float alpha = su * ub * f1 / scale + sr * f2 * adot, alphadot = sr * f1;
+    if (lane == 0) { coef[p] = alpha; coef[P + p] = alphadot; }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) accw[j] = fmaf(alpha, u[j], fmaf(alphadot, ud[j], accw[j]));
+    accb += alpha;
+  }
+  __shared__ float red[8][kTopStride];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) red[w][lane * 8 + j] = accw[j];
+  if (lane == 0) red[w][256] = accb;
+  __syncthreads();
+  for (int c = threadIdx.x; c < 257; c += 256) {
+    float s = 0.f;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) s += red[k][c];
+    top_partial[(size_t)blockIdx.x * kTopStride + c] = s;
+  }
 }
 
-// Weight-norm backward + scatter into the flat gradient (parameters() order: bias, g, v per layer):
+// Last stage: add the per-CTA partial weight / bias gradients (mlp_dw.cu, dual_top_kernel) in a fixed order,
+// undo the kernels' PE column order, then the weight-norm backward, scattered into the flat gradient
+// (parameters() order: bias, g, v per layer) with the loss scale removed:
 //   W = g v/||v||:  dg = <dW, v>/||v|| ;  dv = g/||v|| (dW - <dW, v> v/||v||^2)
-// One warp per (layer,row).  dW rows are [out, ldw] fp32 with `col_mul` folded (skip layer 1/sqrt2).
-struct WnBwdArgs {
+// One warp per (layer, output row); a row of dW (<= 256 entries) lives in registers between the two passes.
+struct FinishArgs {
   const float* flat;          // parameters
   float* flat_grad;           // out
-  const float* dW[kNumLinear];
-  const float* db[kNumLinear];
-  int ldw[kNumLinear];
-  float mul[kNumLinear];
+  const float* partial;       // [n_parts][kDwPartialFloats]
+  const float* dbp;           // [n_parts][8][256]
+  const float* top;           // [kTopBlocks][kTopStride]
+  int n_parts;
+  int multires;
   int in_dim[kNumLinear], out_dim[kNumLinear];
   const float* scales;        // cotangent scales of the sweep (scales[3] = 1/S_u) or NULL
   int* status;                // optional: bit EMAP_STATUS_NONFINITE_GRAD is set when a gradient is not finite
 };
-__global__ void wn_bwd_kernel(const WnBwdArgs a) {
+__device__ __forceinline__ int ref_to_pe_col(int k, int multires) {     // inverse of pe_col_to_ref (common.cuh)
+  for (int col = 0; col < 64; ++col)
+    if (pe_col_to_ref(col, multires) == k) return col;
+  return 0;
+}
+__global__ void __launch_bounds__(256) finish_kernel(const FinishArgs a) {
   int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   int l = 0, row = warp;
@@ -123,11 +166,44 @@ __global__ void wn_bwd_kernel(const WnBwdArgs a) {
   float* gb = a.flat_grad + poff;
   float* gg = gb + od;
   float* gv = gg + od + (size_t)row * id;
-  const float* dW = a.dW[l] + (size_t)row * a.ldw[l];
   const float inv = a.scales ? a.scales[3] : 1.f;
-  const float mul = a.mul[l] * inv;
+  const float mul = ((l == kSkipLayer) ? 0.70710678118654752f : 1.f) * inv;     // the skip layer's input is [h ; PE]/sqrt2
+  const int pe = 3 + 6 * a.multires, hid = kHidden - pe;
+  float dwv[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const int k = lane + 32 * j;
+    float s = 0.f;
+    if (k < id) {
+      if (l == kNumLinear - 1) {
+        for (int b = 0; b < kTopBlocks; ++b) s += a.top[(size_t)b * kTopStride + k];
+      } else {
+        int off, n, col = k;
+        if (l == 0) { off = 0; n = 64; col = ref_to_pe_col(k, a.multires); }
+        else if (l < kSkipLayer) { off = 16384 + (l - 1) * 65536; n = 256; }
+        else if (l == kSkipLayer) {
+          if (k < hid) { off = 16384 + 3 * 65536; n = 256; }
+          else { off = 16384 + 4 * 65536; n = 64; col = ref_to_pe_col(k - hid, a.multires); }
+        } else { off = 32768 + (l - 1) * 65536; n = 256; }
+        const float* src = a.partial + off + (size_t)row * n + col;
+#pragma unroll 4
+        for (int p = 0; p < a.n_parts; ++p) s += src[(size_t)p * kDwPartialFloats];
+      }
+    }
+    dwv[j] = s * mul;
+  }
+  float dbv = 0.f;
+  if (lane == 0) {
+    if (l == kNumLinear - 1) { for (int b = 0; b < kTopBlocks; ++b) dbv += a.top[(size_t)b * kTopStride + 256]; }
+    else { for (int p = 0; p < a.n_parts; ++p) dbv += a.dbp[((size_t)p * 8 + l) * 256 + row]; }
+    dbv *= inv;
+  }
   double ss = 0.0, dot = 0.0;
-  for (int k = lane; k < id; k += 32) { const double vv = v[k]; ss += vv * vv; dot += (double)(dW[k] * mul) * vv; }
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const int k = lane + 32 * j;
+    if (k < id) { const double vv = v[k]; ss += vv * vv; dot += (double)dwv[j] * vv; }
+  }
   for (int o = 16; o; o >>= 1) {
     ss += __shfl_xor_sync(0xffffffffu, ss, o);
     dot += __shfl_xor_sync(0xffffffffu, dot, o);
@@ -135,57 +211,21 @@ __global__ void wn_bwd_kernel(const WnBwdArgs a) {
   const double nrm = sqrt(ss);
   const float gi = g[row];
   bool bad = false;
-  for (int k = lane; k < id; k += 32) {
-    const float o = (float)((double)gi / nrm * ((double)(dW[k] * mul) - dot * (double)v[k] / ss));
-    gv[k] = o;
-    bad |= !isfinite(o);
-  }
-  if (lane == 0) {
-    const float og = (float)(dot / nrm), ob = a.db[l][row] * inv;
-    gg[row] = og; gb[row] = ob;
-    bad |= !isfinite(og) || !isfinite(ob);
-  }
-  if (a.status && __any_sync(0xffffffffu, bad) && lane == 0) atomicOr(a.status, EMAP_STATUS_NONFINITE_GRAD);
-}
-
-// Bias gradients db_l[c] = sum_{p < P} A_l[p, c] over the VALUE rows of the eight [2P,256] fp16 stashes the
-// reverse sweep wrote (replaces a library reduction that ran at half the HBM rate).  HBM-bound: 4.3 GB at
-// P = 1 M.  Pass 1: block b of layer l sums a slab of rows -- a row is 32 lanes x 16 B, a block covers 8 rows
-// per step, fp32 accumulation -- into partial[l][b][256]; pass 2 adds the partials in a fixed order:
-// deterministic, no atomics.
-constexpr int kDbBlocks = 296;          // 2 x 148 slabs per layer
-__global__ void __launch_bounds__(256) db_partial_kernel(const __half* __restrict__ st_a, long long P,
-                                                         float* __restrict__ partial) {
-  const int l = blockIdx.y, b = blockIdx.x;
-  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-  const long long rows_per = (P + kDbBlocks - 1) / kDbBlocks;
-  const long long r0 = (long long)b * rows_per, r1 = min(P, r0 + rows_per);
-  const __half* base = st_a + (size_t)l * 2 * (size_t)P * 256 + lane * 8;
-  float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-#pragma unroll 4
-  for (long long r = r0 + w; r < r1; r += 8) {
-    const uint4 v = __ldg(reinterpret_cast<const uint4*>(base + (size_t)r * 256));
-    const __half2* h = reinterpret_cast<const __half2*>(&v);
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      const float2 f = __half22float2(h[i]);
-      acc[2 * i] += f.x; acc[2 * i + 1] += f.y;
+  for (int j = 0; j < 8; ++j) {
+    const int k = lane + 32 * j;
+    if (k < id) {
+      const float o = (float)((double)gi / nrm * ((double)dwv[j] - dot * (double)v[k] / ss));
+      gv[k] = o;
+      bad |= !isfinite(o);
     }
   }
-  __shared__ float red[8][256];
-#pragma unroll
-  for (int i = 0; i < 8; ++i) red[w][lane * 8 + i] = acc[i];
-  __syncthreads();
-  float s = 0.f;
-#pragma unroll
-  for (int k = 0; k < 8; ++k) s += red[k][threadIdx.x];
-  partial[((size_t)l * kDbBlocks + b) * 256 + threadIdx.x] = s;
-}
-__global__ void __launch_bounds__(256) db_final_kernel(const float* __restrict__ partial, float* __restrict__ db) {
-  const int l = blockIdx.x;
-  float s = 0.f;
-  for (int b = 0; b < kDbBlocks; ++b) s += partial[((size_t)l * kDbBlocks + b) * 256 + threadIdx.x];
-  db[l * 256 + threadIdx.x] = s;
+  if (lane == 0) {
+    const float og = (float)(dot / nrm);
+    gg[row] = og; gb[row] = dbv;
+    bad |= !isfinite(og) || !isfinite(dbv);
+  }
+  if (a.status && __any_sync(0xffffffffu, bad) && lane == 0) atomicOr(a.status, EMAP_STATUS_NONFINITE_GRAD);
 }
 
 }  // namespace emap
@@ -210,40 +250,33 @@ extern "C" int emap_bwd_cotangent_scales(const float* d_udf, const float* d_grad
 }
 
 extern "C" int emap_bwd_top(const emap_net_desc* net, const void* U8_half, const float* w8, const float* b8,
-                            const float* d_udf, const float* scales, int64_t P, float* coef, void* stream) {
+                            const float* d_udf, const float* scales, int64_t P, float* coef, void* workspace,
+                            void* stream) {
   if (check_net(net)) return 1;
-  if (!U8_half || !w8 || !b8 || !coef || P <= 0) return set_error("emap_bwd_top: bad arguments");
-  dual_top_kernel<<<nblk(P * 32, 256), 256, 0, (cudaStream_t)stream>>>((const __half*)U8_half, w8, b8, d_udf, scales,
-                                                                       P, net->udf_type, net->scale, coef);
+  if (!U8_half || !w8 || !b8 || !coef || !workspace || P <= 0) return set_error("emap_bwd_top: bad arguments");
+  float* top = (float*)workspace + (size_t)sm_count() * (kDwPartialFloats + 8 * 256);
+  dual_top_kernel<<<kTopBlocks, 256, 0, (cudaStream_t)stream>>>((const __half*)U8_half, w8, b8, d_udf, scales, P,
+                                                               net->udf_type, net->scale, coef, top);
   EMAP_CUDA(cudaGetLastError());
   return 0;
 }
 
-extern "C" int emap_bwd_bias_sums(const void* st_a_half, int64_t P, float* partial, float* db, void* stream) {
-  if (!st_a_half || !partial || !db || P <= 0) return set_error("emap_bwd_bias_sums: bad arguments");
-  db_partial_kernel<<<dim3(kDbBlocks, 8), 256, 0, (cudaStream_t)stream>>>((const __half*)st_a_half, P, partial);
-  EMAP_CUDA(cudaGetLastError());
-  db_final_kernel<<<8, 256, 0, (cudaStream_t)stream>>>(partial, db);
-  EMAP_CUDA(cudaGetLastError());
-  return 0;
-}
-
-extern "C" int emap_bwd_weight_norm(const emap_net_desc* net, const float* flat_params,
-                                    const float* const* dW, const int32_t* ldw, const float* mul,
-                                    const float* const* db, const float* scales, float* flat_grad,
-                                    int32_t* status, void* stream) {
+extern "C" int emap_bwd_finish(const emap_net_desc* net, const float* flat_params, const void* workspace,
+                               int32_t n_parts, const float* scales, float* flat_grad, int32_t* status,
+                               void* stream) {
   if (check_net(net)) return 1;
-  if (!flat_params || !dW || !ldw || !mul || !db || !flat_grad) return set_error("emap_bwd_weight_norm: NULL pointer");
-  WnBwdArgs a;
+  if (!flat_params || !workspace || !flat_grad || n_parts <= 0 || n_parts > sm_count())
+    return set_error("emap_bwd_finish: bad arguments");
+  FinishArgs a;
   a.flat = flat_params; a.flat_grad = flat_grad; a.scales = scales; a.status = status;
+  a.partial = (const float*)workspace;
+  a.dbp = a.partial + (size_t)sm_count() * kDwPartialFloats;
+  a.top = a.dbp + (size_t)sm_count() * 8 * 256;
+  a.n_parts = n_parts; a.multires = net->multires;
   net_dims(net->multires, a.in_dim, a.out_dim);
   int rows = 0;
-  for (int l = 0; l < kNumLinear; ++l) {
-    if (!dW[l] || !db[l]) return set_error("emap_bwd_weight_norm: NULL layer pointer");
-    a.dW[l] = dW[l]; a.db[l] = db[l]; a.ldw[l] = ldw[l]; a.mul[l] = mul[l];
-    rows += a.out_dim[l];
-  }
-  wn_bwd_kernel<<<nblk((long long)rows * 32, 256), 256, 0, (cudaStream_t)stream>>>(a);
+  for (int l = 0; l < kNumLinear; ++l) rows += a.out_dim[l];
+  finish_kernel<<<nblk((long long)rows * 32, 256), 256, 0, (cudaStream_t)stream>>>(a);
   EMAP_CUDA(cudaGetLastError());
   return 0;
 }

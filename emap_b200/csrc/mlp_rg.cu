@@ -64,7 +64,6 @@ struct Args {
 constexpr int kFlagSplitTail = 1;   // N-split of each step's last K chunk (as K1g does; A/B switch for bring-up)
 constexpr int kFlagL2Persist = 2;   // host side: launch with the sigma scratch as a persisting-L2 access window
 constexpr int kFlagDynamic = 8;     // tiles handed out by a global atomic counter instead of the static round robin
-constexpr int kFlagPipeLd = 4;      // host side: select the PIPE instantiation (tcgen05.ld one chunk ahead)
 
 template <int NTERMS>
 struct Plan {
@@ -172,8 +171,7 @@ __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
 
-// PIPE: the accumulator chunk c+1 is fetched from TMEM (tcgen05.ld) while chunk c is being converted.
-template <int NTERMS, typename T, bool PIPE>
+template <int NTERMS, typename T>
 __global__ void __launch_bounds__(kThreads, 1) mlp_rgrad_kernel(const Args args) {
   using P = Plan<NTERMS>;
   constexpr int kStages = P::kStages;
@@ -443,30 +441,20 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_rgrad_kernel(const Args args)
           mbar_arrive(sched_ready);
         }
         const float* bl = bias100 + l * kHidden;
-        uint32_t rn[16];                        // PIPE: the chunk in flight
-        if (PIPE) tmem_ld_32x32b_x16(lane_taddr + (uint32_t)(buf * 256 + sub * 16), rn);
 #pragma unroll 1
         for (int chunk = 0; chunk < 4; ++chunk) {
           uint8_t* dst_hi = A_hi + chunk * kChunkBytes;
           uint8_t* dst_lo = A_lo + chunk * kChunkBytes;
           const int col0 = chunk * 64 + sub * 16;
-          if (!PIPE && chunk == 2) { mbar_wait(&acc_full[buf * 2 + 1], acc_par, 505 + buf, l); tc_fence_after(); }
+          if (chunk == 2) { mbar_wait(&acc_full[buf * 2 + 1], acc_par, 505 + buf, l); tc_fence_after(); }
           float4 bv[4];
 #pragma unroll
           for (int i = 0; i < 4; ++i) bv[i] = __ldg(reinterpret_cast<const float4*>(bl + col0) + i);
+          // (fetching chunk c+1 from TMEM while chunk c is converted was measured twice -- round 1 on K1g, round 2
+          //  here: 6.68 vs 6.05 ms -- and lost both times: the 16 extra live registers cost more than the latency)
           uint32_t r[16];
-          if (PIPE) {
-            tmem_wait_ld_regs(rn);
-#pragma unroll
-            for (int k = 0; k < 16; ++k) r[k] = rn[k];
-            if (chunk < 3) {
-              if (chunk == 1) { mbar_wait(&acc_full[buf * 2 + 1], acc_par, 505 + buf, l); tc_fence_after(); }
-              tmem_ld_32x32b_x16(lane_taddr + (uint32_t)(buf * 256 + col0 + 64), rn);
-            }
-          } else {
-            tmem_ld_32x32b_x16(lane_taddr + (uint32_t)(buf * 256 + col0), r);
-            tmem_wait_ld();
-          }
+          tmem_ld_32x32b_x16(lane_taddr + (uint32_t)(buf * 256 + col0), r);
+          tmem_wait_ld();
           if (m.dbg_acc && tile == 0) {
 #pragma unroll
             for (int k = 0; k < 16; ++k)
@@ -553,25 +541,13 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_rgrad_kernel(const Args args)
         mbar_wait(&acc_full[buf * 2], acc_par, 530 + buf, s);
         tc_fence_after();
         if (stamp) m.dbg_clk[4 * s + 1] = clock64();
-        uint32_t rn[16];                        // PIPE: the chunk in flight
-        if (PIPE) tmem_ld_32x32b_x16(lane_taddr + (uint32_t)(buf * 256 + sub * 16), rn);
 #pragma unroll
         for (int chunk = 0; chunk < 4; ++chunk) {
           const int col0 = chunk * 64 + sub * 16;
-          if (!PIPE && chunk == 2) { mbar_wait(&acc_full[buf * 2 + 1], acc_par, 535 + buf, s); tc_fence_after(); }
+          if (chunk == 2) { mbar_wait(&acc_full[buf * 2 + 1], acc_par, 535 + buf, s); tc_fence_after(); }
           uint32_t r[16];
-          if (PIPE) {
-            tmem_wait_ld_regs(rn);
-#pragma unroll
-            for (int k = 0; k < 16; ++k) r[k] = rn[k];
-            if (chunk < 3) {
-              if (chunk == 1) { mbar_wait(&acc_full[buf * 2 + 1], acc_par, 535 + buf, s); tc_fence_after(); }
-              tmem_ld_32x32b_x16(lane_taddr + (uint32_t)(buf * 256 + col0 + 64), rn);
-            }
-          } else {
-            tmem_ld_32x32b_x16(lane_taddr + (uint32_t)(buf * 256 + col0), r);
-            tmem_wait_ld();
-          }
+          tmem_ld_32x32b_x16(lane_taddr + (uint32_t)(buf * 256 + col0), r);
+          tmem_wait_ld();
           if (m.dbg_acc && tile == 0) {
 #pragma unroll
             for (int k = 0; k < 16; ++k)
@@ -679,20 +655,11 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_rgrad_kernel(const Args args)
   }
 }
 
-static int g_flags = 0;   // emap_set_option("rg_flags", bits)
+static int g_flags = kFlagDynamic;   // emap_set_option("rg_flags", bits); dynamic tiles: 5.24 vs 6.05 ms per 1 M points (B200)
 int set_flags(int v) { g_flags = v; return 0; }
-
-template <int NTERMS, typename T, bool PIPE>
-static int launch_p(const Args& a_in, size_t scratch_bytes, cudaStream_t stream);
 
 template <int NTERMS, typename T>
 static int launch(const Args& a_in, size_t scratch_bytes, cudaStream_t stream) {
-  if (g_flags & kFlagPipeLd) return launch_p<NTERMS, T, true>(a_in, scratch_bytes, stream);
-  return launch_p<NTERMS, T, false>(a_in, scratch_bytes, stream);
-}
-
-template <int NTERMS, typename T, bool PIPE>
-static int launch_p(const Args& a_in, size_t scratch_bytes, cudaStream_t stream) {
   Args a = a_in;
   a.flags = g_flags;
   const long long tiles = (a.m.P + 127) / 128;
@@ -708,7 +675,7 @@ static int launch_p(const Args& a_in, size_t scratch_bytes, cudaStream_t stream)
   a.pe_scratch = reinterpret_cast<uint8_t*>(a.scratch) + sigma_bytes;      // PE images behind the sigma slices
   a.tile_counter = reinterpret_cast<unsigned int*>(a.pe_scratch + (size_t)grid * kPeBytesPerCta);
   if (a.flags & kFlagDynamic) EMAP_CUDA(cudaMemsetAsync(a.tile_counter, 0, sizeof(unsigned int), stream));
-  auto kern = mlp_rgrad_kernel<NTERMS, T, PIPE>;
+  auto kern = mlp_rgrad_kernel<NTERMS, T>;
   static bool attr_done = false;   // per template instantiation
   if (!attr_done) {
     EMAP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Plan<NTERMS>::total));

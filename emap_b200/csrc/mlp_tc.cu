@@ -32,6 +32,7 @@
 namespace emap {
 
 namespace rg { int set_flags(int v); }   // mlp_rg.cu
+namespace dw { int set_desc_strides(int which, int v); }   // mlp_dw.cu
 
 template <int NTERMS, int MODE, typename T, int CL>
 __global__ void __launch_bounds__(kThreads, 1) mlp_kernel(const MlpArgs args) {
@@ -787,6 +788,8 @@ extern "C" int emap_set_option(const char* name, int value) {
   if (!strcmp(name, "cluster")) return set_cluster_width(value);
   if (!strcmp(name, "dbg")) { emap::g_dbg_flags = value; return 0; }
   if (!strcmp(name, "dbg_iter")) { emap::g_dbg_iter = value; return 0; }
+  if (!strcmp(name, "dw_lbo")) return emap::dw::set_desc_strides(0, value);      // bring-up of mlp_dw.cu's descriptors
+  if (!strcmp(name, "dw_sbo")) return emap::dw::set_desc_strides(1, value);
   if (!strcmp(name, "k1_dot")) { emap::g_k1_dot = (value != 0); return 0; }
   if (!strcmp(name, "rg_flags")) return emap::rg::set_flags(value);   // K1r experiment switches (mlp_rg.cu)
   return set_error("unknown option '%s'", name);

@@ -211,6 +211,26 @@ def _rg_scratch(dev: torch.device) -> torch.Tensor:
     return buf
 
 
+_BWD_WS = {}
+
+
+def _bwd_workspace(dev: torch.device) -> torch.Tensor:
+    """Partial-gradient workspace of the backward's weight-gradient stage (~290 MB), one per device; calls on
+    one stream reuse it in order."""
+    dev = torch.device(dev)
+    key = (dev.type, dev.index if (dev.index is not None or dev.type != "cuda") else torch.cuda.current_device())
+    buf = _BWD_WS.get(key)
+    if buf is None:
+        if dev.type == "cuda":
+            with torch.cuda.device(dev):
+                nbytes = int(C.lib().emap_bwd_workspace_bytes())
+        else:
+            nbytes = int(C.lib().emap_bwd_workspace_bytes())
+        buf = torch.empty(max(nbytes, 16), dtype=torch.uint8, device=dev)
+        _BWD_WS[key] = buf
+    return buf
+
+
 def udf_forward_grad(net: PackedNet, precision: int, pts=None, rays_o=None, rays_d=None, z=None,
                      mode: Optional[str] = None, stash=None) -> Tuple[torch.Tensor, torch.Tensor]:
     """stash = (st_u0, st_u) from alloc_backward_stash (reverse mode only): the forward also writes the
@@ -403,42 +423,16 @@ def _weff_views(net: PackedNet):
     return W, in_dim, out_dim
 
 
-_PE_PERM = {}
-
-
-def _pe_perm(multires: int, device):
-    """kernel PE column -> reference PE index (common.cuh: pe_col_to_ref); -1 = padding."""
-    key = (multires, str(device))
-    if key not in _PE_PERM:
-        ref = []
-        for col in range(64):
-            if col < 3:
-                r = col
-            elif col == 3:
-                r = -1
-            else:
-                if col < 32:
-                    qq, is_cos = (col - 4) >> 1, (col - 4) & 1
-                else:
-                    qq, is_cos = 14 + ((col - 32) >> 1), (col - 32) & 1
-                j, c = qq // 3, qq % 3
-                r = -1 if j >= multires else 3 + 6 * j + 3 * is_cos + c
-            ref.append(r)
-        cols = [c for c, r in enumerate(ref) if r >= 0]
-        refs = [r for r in ref if r >= 0]
-        _PE_PERM[key] = (torch.tensor(cols, device=device), torch.tensor(refs, device=device))
-    return _PE_PERM[key]
-
-
 def udf_backward(net: PackedNet, precision: int, d_udf: Optional[torch.Tensor],
                  d_grad: Optional[torch.Tensor], pts=None, rays_o=None, rays_d=None, z=None,
                  flat_params: Optional[torch.Tensor] = None, stash=None) -> torch.Tensor:
     """Pull the cotangents (d_udf[P], d_grad[P,3]) back to the flat parameter gradient.
 
     fp16 operand images and stashes, fp32 accumulation, loss-scaled on the device
-    (emap_bwd_cotangent_scales): [tangent forward | dual forward] -> output-layer pull-back -> reverse sweep
-    (tcgen05 kernels on the K1 skeleton) -> the nine weight-gradient contractions dW_l = A_l^T U_l -> bias
-    sums -> weight-norm backward, which removes the loss scale and flags non-finite gradients."""
+    (emap_bwd_cotangent_scales): [tangent forward | dual forward] -> output-layer pull-back (with dW_8, db_8)
+    -> reverse sweep -> the weight-gradient contractions dW_l = A_l^T U_l with the bias sums (all tcgen05 kernels)
+    -> fixed-order sum of the partials + weight-norm backward, which removes the loss scale and flags non-finite
+    gradients.  No library GEMM anywhere."""
     L = C.lib()
     net = net.backward_net()
     pts, ro, rd, zz, n, P = _points_args(pts, rays_o, rays_d, z)
@@ -447,7 +441,6 @@ def udf_backward(net: PackedNet, precision: int, d_udf: Optional[torch.Tensor],
         raise RuntimeError("udf_backward needs the flat parameter buffer")
     flat_params = C.f32(flat_params)
     W, in_dim, out_dim = _weff_views(net)
-    pe = 3 + 6 * net.multires
     st = C.stream()
     desc = ctypes.byref(net.desc)
     h16 = lambda *s: torch.empty(*s, dtype=torch.float16, device=dev)  # noqa: E731
@@ -474,42 +467,19 @@ def udf_backward(net: PackedNet, precision: int, d_udf: Optional[torch.Tensor],
                                         C.ptr(zz), n, P, C.ptr(d_grad), C.ptr(scales), C.ptr(st_u0),
                                         C.ptr(st_u), st))
     coef = torch.empty(2 * P, dtype=torch.float32, device=dev)
-    U8 = st_u[7]
-    C.check(L.emap_bwd_top(desc, C.ptr(U8), C.ptr(W[8].reshape(-1)), C.ptr(flat_params[boff[8]:boff[8] + 1]),
-                           C.ptr(d_udf), C.ptr(scales), P, C.ptr(coef), st))
+    ws = _bwd_workspace(dev)
+    C.check(L.emap_bwd_top(desc, C.ptr(st_u[7]), C.ptr(W[8].reshape(-1)), C.ptr(flat_params[boff[8]:boff[8] + 1]),
+                           C.ptr(d_udf), C.ptr(scales), P, C.ptr(coef), C.ptr(ws), st))
     C.check(L.emap_bwd_reverse_sweep(desc, C.ptr(net.packed), C.ptr(coef), C.ptr(st_u), C.ptr(st_a), P, st))
-    cols, refs = _pe_perm(net.multires, dev)
-    dW, db = [None] * 9, [None] * 9
-    dW[8] = torch.mm(coef.to(torch.float16).view(1, 2 * P), U8, out_dtype=torch.float32)
-    db[8] = coef[:P].sum().reshape(1)
-    db_all = torch.empty(8, 256, dtype=torch.float32, device=dev)
-    db_part = torch.empty(8 * 296 * 256, dtype=torch.float32, device=dev)
-    C.check(L.emap_bwd_bias_sums(C.ptr(st_a), P, C.ptr(db_part), C.ptr(db_all), st))   # [8,256], one pass at HBM rate
-    for l in range(8):
-        A = st_a[l]
-        db[l] = db_all[l]
-        if l == 0:
-            dk = torch.mm(A.t(), st_u0, out_dtype=torch.float32)              # [256,64] kernel PE order
-            d0 = torch.zeros(256, pe, dtype=torch.float32, device=dev)
-            d0[:, refs] = dk[:, cols]
-            dW[0] = d0
-        elif l == 4:
-            dh = torch.mm(A.t(), st_u[3], out_dtype=torch.float32)            # [256,256]; cols < 256-pe real
-            dk = torch.mm(A.t(), st_u0, out_dtype=torch.float32)
-            d4 = torch.empty(256, 256, dtype=torch.float32, device=dev)
-            d4[:, :256 - pe] = dh[:, :256 - pe]
-            d4[:, (256 - pe) + refs] = dk[:, cols]
-            dW[4] = d4
-        else:
-            dW[l] = torch.mm(A.t(), st_u[l - 1], out_dtype=torch.float32)
+    # dW_l = A_l^T U_l and db_l on the tensor cores (mlp_dw.cu), per-CTA partials; summed in a fixed order by the
+    # final stage, which also undoes the PE column order, applies the weight-norm backward and removes the scale
+    n_parts = int(L.emap_bwd_weight_grads(desc, C.ptr(st_a), C.ptr(st_u0), C.ptr(st_u), P, C.ptr(ws), ws.numel(), st))
+    if n_parts <= 0:
+        C.check(1)
     # (+ spare tail: parallel.FlatGradAllReduce parks the few foreign gradients there and all-reduces in place)
     flat_grad = torch.empty(flat_params.numel() + 32, dtype=torch.float32, device=dev)[:flat_params.numel()]
-    dW_p = (ctypes.c_void_p * 9)(*[t.data_ptr() for t in dW])
-    db_p = (ctypes.c_void_p * 9)(*[t.data_ptr() for t in db])
-    ldw = (ctypes.c_int32 * 9)(*[t.shape[1] for t in dW])
-    mul = (ctypes.c_float * 9)(*[(2.0 ** -0.5) if l == 4 else 1.0 for l in range(9)])
-    C.check(L.emap_bwd_weight_norm(desc, C.ptr(flat_params), dW_p, ldw, mul, db_p, C.ptr(scales),
-                                   C.ptr(flat_grad), C.ptr(status_word(dev)), st))
+    C.check(L.emap_bwd_finish(desc, C.ptr(flat_params), C.ptr(ws), n_parts, C.ptr(scales), C.ptr(flat_grad),
+                              C.ptr(status_word(dev)), st))
     return flat_grad
 
 

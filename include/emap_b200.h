@@ -100,21 +100,26 @@ int emap_udf_forward_grad_rev(const emap_net_desc* net, const void* packed, int 
  * from the maxima of the cotangents on the device (no host sync): scales[0] = S_g (the tangent direction is
  * S_g d_grad, max in [0.5,1)), scales[1] = S_u (what the sweep accumulates is S_u dL/dtheta; max(S_u |d_udf|,
  * S_u |d_grad|) in [1/8,1/4)), scales[2] = S_u/S_g, scales[3] = 1/S_u; scales[4..7] scratch.  The stages
- * below take that buffer (NULL = all ones); emap_bwd_weight_norm removes S_u.                          */
+ * below take that buffer (NULL = all ones); emap_bwd_finish removes S_u.                                  */
 int emap_bwd_cotangent_scales(const float* d_udf /*[P] or NULL*/, const float* d_grad /*[P,3] or NULL*/,
                               int64_t P, float* scales8, void* stream);
-/* output-layer pull-back: coef[p] = S_u d_udf f'(a8)/scale + (S_u/S_g) f''(a8) adot8, coef[P+p] = (S_u/S_g) f'(a8) */
+/* Workspace of the weight-gradient stage: per-CTA partial dW / db of emap_bwd_weight_grads and the per-block
+ * partial dW_8 / db_8 of emap_bwd_top (~290 MB, independent of P; reusable across calls on one stream).      */
+size_t emap_bwd_workspace_bytes(void);
+/* output-layer pull-back: coef[p] = S_u d_udf f'(a8)/scale + (S_u/S_g) f''(a8) adot8, coef[P+p] = (S_u/S_g) f'(a8);
+ * also the output layer's own gradient dW_8 = sum_p coef[p] U8[p] + coef[P+p] U8[P+p], db_8 = sum_p coef[p] as
+ * per-block partials in the workspace (replaces a library GEMV + two reductions).                          */
 int emap_bwd_top(const emap_net_desc* net, const void* U8_half, const float* w8, const float* b8,
                  const float* d_udf /*[P] or NULL*/, const float* scales, int64_t P, float* coef /*[2P]*/,
-                 void* stream);
+                 void* workspace, void* stream);
 /* Fused tensor-core stages of K1b (hand-written tcgen05 kernels on the K1 skeleton):
  *  emap_bwd_dual_forward : layers 0..7 of the dual network (value + ONE tangent along d_grad) with
  *     fp16 stashes  st_u0[2P,64] (dual PE, kernel column order), st_u[8][2P,256] (inputs of layers 1..8:
  *     h_{l+1} in rows [0,P), hdot_{l+1} in rows [P,2P)).  No sigma / adot stash is needed:
  *     softplus'(a_l) = 1 - exp(-100 h_{l+1}) and adot_l softplus''(a_l) = 100 hdot_{l+1} (1 - sigma_l).
  *  emap_bwd_reverse_sweep: layers 7..0 of the reverse sweep from coef[2P] (emap_bwd_top) and st_u;
- *     writes st_a[8][2P,256] = [alpha_l ; alphadot_l].  The weight gradients are then the plain GEMMs
- *     dW_l = A_l^T U_l (library) and emap_bwd_weight_norm.                                            */
+ *     writes st_a[8][2P,256] = [alpha_l ; alphadot_l].  The weight gradients are then the contractions
+ *     dW_l = A_l^T U_l of emap_bwd_weight_grads, finished by emap_bwd_finish.                         */
 int emap_bwd_dual_forward(const emap_net_desc* net, const void* packed, int precision,
                           const float* pts, const float* rays_o, const float* rays_d, const float* z,
                           int32_t n_per_ray, int64_t P, const float* d_grad, const float* scales,
@@ -128,17 +133,19 @@ int emap_bwd_tangent_forward(const emap_net_desc* net, const void* packed, const
                              const float* rays_o, const float* rays_d, const float* z, int32_t n_per_ray,
                              int64_t P, const float* d_grad, const float* scales, void* st_u0, void* st_u,
                              void* stream);
-/* db_l[c] = sum over the value rows p < P of A_l[p, c], l = 0..7, from the reverse sweep's stash
- * st_a [8][2P,256] fp16 -> db [8,256] fp32.  partial: scratch [8*296*256] floats.  Deterministic two-pass
- * reduction (no atomics).  replaces the bias half of autograd's addmm backward (udf_model.py:102).      */
-int emap_bwd_bias_sums(const void* st_a, int64_t P, float* partial, float* db, void* stream);
-/* weight-norm backward + scatter into the flat gradient (same layout as the flat parameters).
- * dW[l]: fp32 [out_l, ldw[l]] (d/dW_eff, times mul[l]); db[l]: fp32 [out_l]; both still carry the loss scale
- * S_u, removed here (scales[3]; NULL = 1).  status (optional, device int32): bit EMAP_STATUS_NONFINITE_GRAD
- * is set when a parameter gradient is not finite (e.g. an fp16 overflow of the scaled sweep).       */
-int emap_bwd_weight_norm(const emap_net_desc* net, const float* flat_params, const float* const* dW,
-                         const int32_t* ldw, const float* mul, const float* const* db,
-                         const float* scales, float* flat_grad, int32_t* status, void* stream);
+/* The weight-gradient contractions dW_l = A_l^T U_l, l = 0..7, and the bias sums db_l = sum_{p<P} A_l[p,:], on the
+ * tensor cores (mlp_dw.cu: TMA-staged row tiles as MN-major tcgen05 operands, one [256 x 256] fp32 accumulator
+ * per CTA in TMEM): st_a [8][2P,256], st_u0 [2P,64], st_u [8][2P,256] fp16 -> per-CTA partials in the workspace.
+ * replaces the `mm` chain of autograd's addmm backward (udf_model.py:102 under loss.backward()).
+ * Returns the number of partials (> 0) for emap_bwd_finish, or -1 with emap_last_error() set.                */
+int emap_bwd_weight_grads(const emap_net_desc* net, const void* st_a, const void* st_u0, const void* st_u,
+                          int64_t P, void* workspace, size_t workspace_bytes, void* stream);
+/* Final stage: fixed-order sum of the partials (deterministic, no atomics), the kernels' PE column order undone,
+ * weight-norm backward, scatter into the flat gradient (same layout as the flat parameters), loss scale S_u
+ * removed (scales[3]; NULL = 1).  status (optional, device int32): bit EMAP_STATUS_NONFINITE_GRAD is set when a
+ * parameter gradient is not finite (e.g. an fp16 overflow of the scaled sweep).                              */
+int emap_bwd_finish(const emap_net_desc* net, const float* flat_params, const void* workspace, int32_t n_parts,
+                    const float* scales, float* flat_grad, int32_t* status, void* stream);
 /* byte offsets inside the packed buffer: out[0] = 100*bias table, out[1..9] = W_eff of layer 0..8. */
 int emap_packed_offsets(const emap_net_desc* net, uint32_t* out10);
 
@@ -220,12 +227,14 @@ int emap_rays_from_pixels(const int64_t* pixels_x, const int64_t* pixels_y, cons
 
 /* ---- misc ------------------------------------------------------------------------------------ */
 /* options: "cluster" = 1|2|-2 : weight-stream organisation of the K1/K1g/dual kernels (1 = default);
- *          "rg_flags" : K1r experiment switches (bit 0: N-split of each step's last K chunk; bit 1: launch
- *                       with the sigma scratch as a persisting-L2 access-policy window);
+ *          "rg_flags" : K1r switches, default 8 (bit 3: tiles handed out by a global atomic counter -- 5.24 vs
+ *                       6.05 ms per 1 M points on B200; bit 0: N-split of each step's last K chunk; bit 1: launch
+ *                       with the sigma scratch as a persisting-L2 access-policy window -- both measured, no gain);
  *          "k1_dot"   : 1 = emap_udf_forward (without pe_out) runs the output layer as an fp32 dot product
  *                       in layer 7's epilogue instead of a ninth MMA step (opt-in until measured);
  *          "dbg"      : timing experiments of mlp_tc.cu (0 in production);
- *          "dbg_iter" : tile iteration of block 0 that the clock64 timelines of the debug entry points stamp. */
+ *          "dbg_iter" : tile iteration of block 0 that the clock64 timelines of the debug entry points stamp;
+ *          "dw_lbo" / "dw_sbo" : byte strides of mlp_dw.cu's MN-major operand descriptors (8192 / 1024).      */
 int emap_set_option(const char* name, int value);
 /* test hook: MLP forward (mode 0) / forward+grad (mode 1) that also dumps the de-scaled
  * accumulators of tile 0, dbg_acc[9][128][256].                                                  */

@@ -1,0 +1,47 @@
+"""GPU: the weight-gradient contraction kernel (emap_b200/csrc/mlp_dw.cu) in isolation -- random fp16 stashes,
+per-CTA partials read back from the workspace and summed, against fp32 matmuls of the same fp16 data.  Row counts
+that are not multiples of the 64-row stage (TMA zero fill), fewer stages than SMs, and value/tangent boundaries
+inside a stage (bias sums count value rows only)."""
+import ctypes
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+PART = 2 * 256 * 64 + 7 * 256 * 256
+# (job offset, n, A plane, U source) in the order of mlp_dw.cu: c_jobs
+JOBS = [(0, 64, 0, "u0"), (16384, 256, 1, 0), (16384 + 65536, 256, 2, 1), (16384 + 2 * 65536, 256, 3, 2),
+        (16384 + 3 * 65536, 256, 4, 3), (16384 + 4 * 65536, 64, 4, "u0"),
+        (32768 + 4 * 65536, 256, 5, 4), (32768 + 5 * 65536, 256, 6, 5), (32768 + 6 * 65536, 256, 7, 6)]
+
+
+@pytest.mark.parametrize("P", [1000, 70, 4096 * 3 + 17])
+def test_weight_grad_partials_match_matmul(P):
+    from emap_b200 import ops, _cabi as C
+    torch.manual_seed(P)
+    dev = "cuda"
+    st_a = (torch.randn(8, 2 * P, 256, device=dev) * 0.5).half()
+    st_u = (torch.randn(8, 2 * P, 256, device=dev) * 0.5).half()
+    st_u0 = (torch.randn(2 * P, 64, device=dev) * 0.5).half()
+    net = ops.PackedNet(10)
+    ws = ops._bwd_workspace(torch.device(dev))
+    ws.zero_()
+    n_parts = int(C.lib().emap_bwd_weight_grads(ctypes.byref(net.desc), C.ptr(st_a), C.ptr(st_u0), C.ptr(st_u), P,
+                                                C.ptr(ws), ws.numel(), C.stream()))
+    torch.cuda.synchronize()
+    assert n_parts > 0, C.lib().emap_last_error()
+    sms = torch.cuda.get_device_properties(0).multi_processor_count
+    wsf = ws.view(torch.float32)
+    parts = wsf[:sms * PART].view(sms, PART)[:n_parts].double().sum(0)
+    dbp = wsf[sms * PART:sms * PART + sms * 2048].view(sms, 8, 256)[:n_parts].double().sum(0)
+    for off, n, la, lu in JOBS:
+        A = st_a[la].double()
+        U = (st_u0 if lu == "u0" else st_u[lu]).double()
+        ref = A.t() @ U                                               # [256, n]
+        got = parts[off:off + 256 * n].view(256, n)
+        err = float((got - ref).abs().max()) / float(ref.abs().max())
+        assert err <= 1e-5, (off, n, la, lu, err)                     # fp32 accumulation of exact fp16 products
+    for l in range(8):
+        ref = st_a[l][:P].double().sum(0)
+        assert float((dbp[l] - ref).abs().max()) <= 1e-4 * max(1.0, float(ref.abs().max())), l

@@ -99,20 +99,22 @@ def test_reverse_mode_rays_ragged_many_tiles_and_repeatable():
     assert maxdiff(g1.cpu()[sel], ref_g) <= 5e-5 * max(1.0, float(ref_g.abs().max()))
 
 
-def test_split_tail_variant_is_bit_identical(golden):
-    """rg_flags bit 0: N-split of each step's last K chunk (same MMA order per accumulator column)."""
+def test_split_tail_and_static_schedule_variants_are_bit_identical(golden):
+    """rg_flags bit 0: N-split of each step's last K chunk (same MMA order per accumulator column); bit 3 off:
+    static round-robin tiles instead of the dynamic counter (the default) -- which CTA runs a tile must not matter."""
     from emap_b200 import ops, _cabi as C
     g = golden("mlp_pert")
     net, _ = _net(True)
     x = g["x"].cuda().repeat(60, 1)           # 23,040 points -> 180 tiles: two tiles on some CTAs
     u1, g1 = ops.udf_forward_grad(net, C.PREC_FP32X3, pts=x, mode="reverse")
-    try:
-        C.set_option("rg_flags", 1)
-        u2, g2 = ops.udf_forward_grad(net, C.PREC_FP32X3, pts=x, mode="reverse")
-        torch.cuda.synchronize()
-    finally:
-        C.set_option("rg_flags", 0)
-    assert torch.equal(u1, u2) and torch.equal(g1, g2)
+    for flags in (9, 0, 1):
+        try:
+            C.set_option("rg_flags", flags)
+            u2, g2 = ops.udf_forward_grad(net, C.PREC_FP32X3, pts=x, mode="reverse")
+            torch.cuda.synchronize()
+        finally:
+            C.set_option("rg_flags", 8)
+        assert torch.equal(u1, u2) and torch.equal(g1, g2), flags
 
 
 @pytest.mark.parametrize("udf_type,scale", [("square", 1.0), ("sdf", 1.0), ("abs", 0.5)])

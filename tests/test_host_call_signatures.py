@@ -41,6 +41,10 @@ class _Recorder:
             self.calls.append(name)
             if name == "emap_rgrad_scratch_bytes":
                 return 4 * 7 * 4 * 16 * 512 * 4                    # pretend 4 SMs
+            if name == "emap_bwd_workspace_bytes":
+                return 1 << 16
+            if name == "emap_bwd_weight_grads":
+                return 4                                           # number of partials
             return 0
         return call
 
@@ -104,7 +108,8 @@ def test_backward_entry_points(shim, shared):
     assert flat_grad.shape == net.flat.shape
     assert ("emap_bwd_tangent_forward" in rec.calls) == shared
     assert ("emap_bwd_dual_forward" in rec.calls) == (not shared)
-    for name in ("emap_bwd_top", "emap_bwd_reverse_sweep", "emap_bwd_bias_sums", "emap_bwd_weight_norm"):
+    for name in ("emap_bwd_cotangent_scales", "emap_bwd_top", "emap_bwd_reverse_sweep", "emap_bwd_weight_grads",
+                 "emap_bwd_finish"):
         assert name in rec.calls, name
 
 

@@ -18,7 +18,7 @@ C.lib().emap_debug_set_clk_buffer(C.ptr(buf))
 names = [f"fwd L{l}" for l in range(8)] + [f"rev L{l}" for l in range(7, -1, -1)]
 # a steady-state tile: full-size launch (1 M points, 56 tiles per CTA), the 30th tile of block 0
 C.set_option("dbg_iter", 30)
-for flags in (0,):
+for flags in (8,):
     C.set_option("rg_flags", flags)
     for prec in (3, 1):
         x = (torch.rand(1 << 20, 3, device="cuda") * 2 - 1) * 1.5
@@ -42,6 +42,6 @@ for flags in (0,):
               f"(max/min {cyc.max() / cyc.min():.3f}); slowest blocks (block, smid, Mclk): "
               f"{[(int(i), int(per[i, 1]), round(float(cyc[i]) / 1e6, 2)) for i in order[-6:]]}; fastest: "
               f"{[(int(i), int(per[i, 1]), round(float(cyc[i]) / 1e6, 2)) for i in order[:6]]}", flush=True)
-C.set_option("rg_flags", 0)
+C.set_option("rg_flags", 8)
 C.set_option("dbg_iter", 1)
 C.lib().emap_debug_set_clk_buffer(None)
