@@ -38,6 +38,7 @@ struct MlpArgs {
   long long* dbg_clk;   // optional [2][9][8] clock64 stamps of block 0, tile iteration 1 (epilogue warp 0 / MMA role 0)
   int dbg_flags;        // timing experiments only: 1 = no MMA issue, 2 = no weight copies, 4 = no epilogue math
   int dbg_iter;         // tile iteration of block 0 whose timeline is stamped into dbg_clk (emap_set_option("dbg_iter"))
+  unsigned int* tile_counter;   // single-CTA launches: tiles grid, grid+1, ... are handed out in arrival order (NULL = static)
 };
 
 constexpr int kRingStageBytes = 2 * kStageBytes;   // one part: [256 x 64] 16-bit SW128 image (N halves adjacent)

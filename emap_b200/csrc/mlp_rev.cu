@@ -43,6 +43,7 @@ struct Args {
   __half* st_a;             // [8][2P,256]  out: A_l, l = 0..7
   long long P;
   int num_tiles, iters;
+  unsigned int* tile_counter;   // dynamic tile scheduling (as in mlp_rg.cu / mlp_tc.cu); NULL = static round robin
 };
 
 __device__ __forceinline__ uint32_t pack2h(float a, float b) {
@@ -64,12 +65,19 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_rev_kernel(const Args args) {
   uint64_t* acc_full = bars + 20;   // [2]
   uint64_t* acc_empty = bars + 22;  // [2]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 25);
+  // tile schedule: completion k of sched_ready publishes the tile of iteration k in sched_tile[k & 1] (one thread
+  // of epilogue warp 0, during stage 1 of iteration k-1); a tile index >= num_tiles ends every role's loop
+  uint64_t* sched_ready = bars + 26;
+  volatile int* sched_tile = reinterpret_cast<volatile int*>(bars + 27);
 
   if (warp == kProducerWarp && lane == 0) {
     for (int s = 0; s < kStages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
     for (int c = 0; c < 4; ++c) mbar_init(&a_ready[c], kEpiWarps);
     for (int b = 0; b < 2; ++b) { mbar_init(&acc_full[b], 1); mbar_init(&acc_empty[b], kEpiWarps); }
+    mbar_init(sched_ready, 1);
+    sched_tile[0] = (int)blockIdx.x;
     fence_barrier_init();
+    mbar_arrive(sched_ready);             // completion 0: iteration 0 runs tile blockIdx.x
   }
   if (warp == kMmaWarp) { tmem_alloc(tmem_slot, 512); tmem_relinquish(); }
   tc_fence_before();
@@ -83,7 +91,9 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_rev_kernel(const Args args) {
     const uint8_t* img = args.packed + hdr->reserved[2];
     uint8_t* ring = smem + Smem::ring;
     uint32_t stage = 0, round = 0;
-    for (int iter = 0; iter < args.iters; ++iter) {
+    for (int iter = 0;; ++iter) {
+      mbar_wait(sched_ready, (uint32_t)iter & 1, 560);
+      if (sched_tile[iter & 1] >= args.num_tiles) break;
 #pragma unroll 1
       for (int i = 0; i < kRevParts; ++i) {
         if (round > 0) mbar_wait(&empty[stage], (round - 1) & 1, 100 + (int)stage, i);
@@ -100,7 +110,9 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_rev_kernel(const Args args) {
     const uint32_t ring_addr = smem_u32(smem + Smem::ring);
     const uint32_t idesc = make_idesc_f16(128, 256, 0);
     uint32_t stage = 0, round = 0;
-    for (int iter = 0; iter < args.iters; ++iter) {
+    for (int iter = 0;; ++iter) {
+      mbar_wait(sched_ready, (uint32_t)iter & 1, 561);
+      if (sched_tile[iter & 1] >= args.num_tiles) break;
 #pragma unroll
       for (int j = 0; j < kRevLayers; ++j) {
         const int buf = j & 1;
@@ -139,8 +151,17 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_rev_kernel(const Args args) {
     const float* w8 = reinterpret_cast<const float*>(args.packed + hdr->weff_layer_off[8]);
     const size_t P = (size_t)args.P;
 
-    for (int iter = 0; iter < args.iters; ++iter) {
-      const long long tile = (long long)blockIdx.x + (long long)iter * gridDim.x;
+    const bool scheduler = (warp == 0 && lane == 0);
+    for (int iter = 0;; ++iter) {
+      mbar_wait(sched_ready, (uint32_t)iter & 1, 562);
+      const long long tile = (long long)sched_tile[iter & 1];
+      if (tile >= args.num_tiles) break;
+      int next_tile = 0;
+      if (scheduler) {
+        const long long nt = args.tile_counter ? (long long)gridDim.x + (long long)atomicAdd(args.tile_counter, 1u)
+                                               : tile + (long long)gridDim.x;
+        next_tile = (nt < (long long)args.num_tiles) ? (int)nt : args.num_tiles;
+      }
       const long long pt = tile * 64 + q * 16 + (lane >> 1);
       const bool ok = (tile < args.num_tiles) && (pt < args.P);
       const size_t pc = ok ? (size_t)pt : 0;
@@ -164,6 +185,10 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_rev_kernel(const Args args) {
         if (j >= 0) {
           mbar_wait(&acc_full[buf], ((uint32_t)iter * (buf ? 3u : 4u) + (uint32_t)(j >> 1)) & 1, 500 + buf, j);
           tc_fence_after();
+          if (j == 1 && scheduler) {        // all 16 warps are past stage 0 of this tile, i.e. past its schedule wait
+            sched_tile[(iter + 1) & 1] = next_tile;
+            mbar_arrive(sched_ready);
+          }
         }
         // own row of U_{lt+1}: h (value lane) or hdot (tangent lane); the partner's comes by shuffle
         __half* a_out = args.st_a + (size_t)lt * 2 * P * 256 + rowg * 256;
@@ -258,6 +283,9 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_rev_kernel(const Args args) {
   if (warp == kMmaWarp) tmem_dealloc(tmem_base, 512);
 }
 
+static int g_dynamic = 1;
+int set_dynamic(int v) { g_dynamic = v; return 0; }
+
 }  // namespace rev
 }  // namespace emap
 
@@ -276,6 +304,7 @@ extern "C" int emap_bwd_reverse_sweep(const emap_net_desc* net, const void* pack
   int grid = sm_count();
   if (tiles < grid) grid = (int)tiles;
   a.iters = (int)((tiles + grid - 1) / grid);
+  a.tile_counter = rev::g_dynamic ? tile_counter((cudaStream_t)stream) : nullptr;
   static bool attr_done = false;
   if (!attr_done) {
     EMAP_CUDA(cudaFuncSetAttribute(rev::mlp_rev_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, rev::Smem::total));

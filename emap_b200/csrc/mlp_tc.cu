@@ -33,6 +33,7 @@ namespace emap {
 
 namespace rg { int set_flags(int v); }   // mlp_rg.cu
 namespace dw { int set_desc_strides(int which, int v); }   // mlp_dw.cu
+namespace rev { int set_dynamic(int v); }                  // mlp_rev.cu
 
 template <int NTERMS, int MODE, typename T, int CL>
 __global__ void __launch_bounds__(kThreads, 1) mlp_kernel(const MlpArgs args) {
@@ -66,6 +67,14 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_kernel(const MlpArgs args) {
   uint64_t* c0_free = bars + 25;          // layer 4 has consumed chunk 0 -> PE may be regenerated there
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 27);
   uint64_t* peer_full = bars + 28;        // [kStages] PAIR, leader only: the peer's stage has landed
+  // Tile schedule of the single-CTA configuration (as in mlp_rg.cu): the tile of iteration k is published in
+  // sched_tile[k & 1] by completion k of sched_ready -- one thread of epilogue warp 0, during layer 2 of
+  // iteration k-1, when every role has consumed completion k-1 -- either the static round robin or the next
+  // value of a global atomic counter (SM-to-SM speed differences of ~10 % otherwise idle the fast SMs at the
+  // end).  A tile index >= num_tiles ends every role's loop.  Cluster configurations keep the static loop.
+  constexpr bool kSched = (CL == 1);
+  uint64_t* sched_ready = bars + 21;
+  volatile int* sched_tile = reinterpret_cast<volatile int*>(bars + 22);
   const uint32_t crank = (CLW > 1) ? cluster_ctarank() : 0;
 
   if (warp == kProducerWarp && lane == 0) {
@@ -77,7 +86,9 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_kernel(const MlpArgs args) {
     for (int b = 0; b < 4; ++b) mbar_init(&acc_full[b], 1);
     for (int b = 0; b < 2; ++b) mbar_init(&acc_empty[b], kEpiWarps * kArr);
     mbar_init(c0_free, 1);
+    if (kSched) { mbar_init(sched_ready, 1); sched_tile[0] = (int)blockIdx.x; }
     fence_barrier_init();
+    if (kSched) mbar_arrive(sched_ready);          // completion 0: iteration 0 runs tile blockIdx.x
   }
   if (warp == kMmaWarp) {
     if (PAIR) { tmem_alloc_2sm(tmem_slot, 512); tmem_relinquish_2sm(); }
@@ -103,7 +114,11 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_kernel(const MlpArgs args) {
     uint8_t* ring = smem + Plan::ring;
     const bool no_copy = (args.dbg_flags & 2) != 0;
     uint32_t stage = 0, round = 0;
-    for (int iter = 0; iter < args.iters; ++iter) {
+    for (int iter = 0; kSched || iter < args.iters; ++iter) {
+      if (kSched) {
+        mbar_wait(sched_ready, (uint32_t)iter & 1, 560);
+        if (sched_tile[iter & 1] >= args.num_tiles) break;
+      }
       uint32_t off = 0;
 #pragma unroll 1
       for (int l = 0; l < MI::kLayers; ++l) {
@@ -180,7 +195,11 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_kernel(const MlpArgs args) {
     };
     const bool no_mma = (args.dbg_flags & 1) != 0;
     uint32_t stage = 0, round = 0;
-    for (int iter = 0; iter < args.iters; ++iter) {
+    for (int iter = 0; kSched || iter < args.iters; ++iter) {
+      if (kSched) {
+        mbar_wait(sched_ready, (uint32_t)iter & 1, 561);
+        if (sched_tile[iter & 1] >= args.num_tiles) break;
+      }
 #pragma unroll
       for (int l = 0; l < MI::kLayers; ++l) {
         const int buf = l & 1;
@@ -309,8 +328,20 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_kernel(const MlpArgs args) {
     const int p8 = lane >> 2, ty = lane & 3;       // MODE_GRAD: point-in-warp, row type
     const float b8 = bias100[8 * kHidden];
 
-    for (int iter = 0; iter < args.iters; ++iter) {
-      const long long tile = (long long)blockIdx.x + (long long)iter * gridDim.x;
+    const bool scheduler = kSched && warp == 0 && lane == 0;
+    for (int iter = 0; kSched || iter < args.iters; ++iter) {
+      long long tile = (long long)blockIdx.x + (long long)iter * gridDim.x;
+      int next_tile = 0;
+      if (kSched) {
+        mbar_wait(sched_ready, (uint32_t)iter & 1, 562);
+        tile = (long long)sched_tile[iter & 1];
+        if (tile >= args.num_tiles) break;
+        if (scheduler) {       // the tile after this one: fetched now (an L2 atomic in dynamic mode), published in layer 2
+          const long long nt = args.tile_counter ? (long long)gridDim.x + (long long)atomicAdd(args.tile_counter, 1u)
+                                                 : tile + (long long)gridDim.x;
+          next_tile = (nt < (long long)args.num_tiles) ? (int)nt : args.num_tiles;
+        }
+      }
       // ------------------------------------------------ input stage: positional encoding -> chunk 0
       long long pt;
       if (MODE == 0 || MODE == 3 || MODE == 5) pt = tile * 128 + row;
@@ -351,6 +382,10 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_kernel(const MlpArgs args) {
         mbar_wait(&acc_full[buf * 2], acc_par, 500 + buf, l);
         tc_fence_after();
         if (stamp) args.dbg_clk[l * 8 + 1] = clock64();
+        if (l == 2 && scheduler) {      // all 16 warps are past layer 1 of this tile, i.e. past its schedule wait
+          sched_tile[(iter + 1) & 1] = next_tile;
+          mbar_arrive(sched_ready);
+        }
         const float* bl = bias100 + l * kHidden;
 #pragma unroll (MODE == 3 ? 4 : 1)
         for (int chunk = 0; chunk < 4; ++chunk) {
@@ -605,6 +640,7 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_kernel(const MlpArgs args) {
 static long long* g_dbg_clk = nullptr;   // emap_debug_set_clk_buffer
 long long* dbg_clk_buffer() { return g_dbg_clk; }   // (mlp_rg.cu's debug entry stamps into the same buffer)
 static int g_dbg_flags = 0;   // timing experiments (emap_set_option("dbg", flags)); 0 in production
+static int g_dynamic_tiles = 1;   // emap_set_option("dynamic_tiles", 0): static round-robin tiles (A/B switch)
 static int g_dbg_iter = 1;    // which tile iteration of block 0 the clock64 timelines stamp (emap_set_option("dbg_iter"))
 int dbg_iter() { return g_dbg_iter; }
 
@@ -621,6 +657,7 @@ static int launch(const MlpArgs& a_in, cudaStream_t stream) {
   a.num_tiles = (int)tiles;
   a.dbg_flags = g_dbg_flags;
   a.dbg_iter = g_dbg_iter;
+  a.tile_counter = (CL == 1 && g_dynamic_tiles) ? tile_counter(stream) : nullptr;
   int grid = sm_count();
   grid = grid / CLW * CLW;
   if (tiles < grid) grid = (int)((tiles + CLW - 1) / CLW * CLW);
@@ -788,6 +825,7 @@ extern "C" int emap_set_option(const char* name, int value) {
   if (!strcmp(name, "cluster")) return set_cluster_width(value);
   if (!strcmp(name, "dbg")) { emap::g_dbg_flags = value; return 0; }
   if (!strcmp(name, "dbg_iter")) { emap::g_dbg_iter = value; return 0; }
+  if (!strcmp(name, "dynamic_tiles")) { emap::g_dynamic_tiles = value; emap::rev::set_dynamic(value); return 0; }
   if (!strcmp(name, "dw_lbo")) return emap::dw::set_desc_strides(0, value);      // bring-up of mlp_dw.cu's descriptors
   if (!strcmp(name, "dw_sbo")) return emap::dw::set_desc_strides(1, value);
   if (!strcmp(name, "k1_dot")) { emap::g_k1_dot = (value != 0); return 0; }

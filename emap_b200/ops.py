@@ -80,6 +80,26 @@ def check_status(dev) -> None:
         _raise_status(st, bits)
 
 
+# ----------------------------------------------------------------------------- NVTX ranges
+# EMAP_NVTX=1 brackets the stages of the path (render, importance sampling, render_core, the backward's stages)
+# with NVTX ranges for Nsight timelines; off by default (the reference has no tracing at all).
+_NVTX = os.environ.get("EMAP_NVTX") == "1"
+
+
+class nvtx_range:
+    def __init__(self, name: str):
+        self.name = name
+
+    def __enter__(self):
+        if _NVTX:
+            torch.cuda.nvtx.range_push(self.name)
+
+    def __exit__(self, *exc):
+        if _NVTX:
+            torch.cuda.nvtx.range_pop()
+        return False
+
+
 def net_dims(multires: int):
     pe = 3 + 6 * multires
     in_dim = [pe] + [256] * 8
@@ -459,8 +479,9 @@ def udf_backward(net: PackedNet, precision: int, d_udf: Optional[torch.Tensor],
     if stash is not None:
         # value rows written by the training forward (K1r): add the tangent rows only
         st_u0, st_u = stash
-        C.check(L.emap_bwd_tangent_forward(desc, C.ptr(net.packed), C.ptr(pts), C.ptr(ro), C.ptr(rd), C.ptr(zz),
-                                           n, P, C.ptr(d_grad), C.ptr(scales), C.ptr(st_u0), C.ptr(st_u), st))
+        with nvtx_range("emap.bwd.tangent_forward"):
+            C.check(L.emap_bwd_tangent_forward(desc, C.ptr(net.packed), C.ptr(pts), C.ptr(ro), C.ptr(rd), C.ptr(zz),
+                                               n, P, C.ptr(d_grad), C.ptr(scales), C.ptr(st_u0), C.ptr(st_u), st))
     else:
         st_u0, st_u = h16(2 * P, 64), h16(8, 2 * P, 256)
         C.check(L.emap_bwd_dual_forward(desc, C.ptr(net.packed), C.PREC_HALF, C.ptr(pts), C.ptr(ro), C.ptr(rd),
@@ -470,10 +491,13 @@ def udf_backward(net: PackedNet, precision: int, d_udf: Optional[torch.Tensor],
     ws = _bwd_workspace(dev)
     C.check(L.emap_bwd_top(desc, C.ptr(st_u[7]), C.ptr(W[8].reshape(-1)), C.ptr(flat_params[boff[8]:boff[8] + 1]),
                            C.ptr(d_udf), C.ptr(scales), P, C.ptr(coef), C.ptr(ws), st))
-    C.check(L.emap_bwd_reverse_sweep(desc, C.ptr(net.packed), C.ptr(coef), C.ptr(st_u), C.ptr(st_a), P, st))
+    with nvtx_range("emap.bwd.reverse_sweep"):
+        C.check(L.emap_bwd_reverse_sweep(desc, C.ptr(net.packed), C.ptr(coef), C.ptr(st_u), C.ptr(st_a), P, st))
     # dW_l = A_l^T U_l and db_l on the tensor cores (mlp_dw.cu), per-CTA partials; summed in a fixed order by the
     # final stage, which also undoes the PE column order, applies the weight-norm backward and removes the scale
-    n_parts = int(L.emap_bwd_weight_grads(desc, C.ptr(st_a), C.ptr(st_u0), C.ptr(st_u), P, C.ptr(ws), ws.numel(), st))
+    with nvtx_range("emap.bwd.weight_grads"):
+        n_parts = int(L.emap_bwd_weight_grads(desc, C.ptr(st_a), C.ptr(st_u0), C.ptr(st_u), P, C.ptr(ws),
+                                              ws.numel(), st))
     if n_parts <= 0:
         C.check(1)
     # (+ spare tail: parallel.FlatGradAllReduce parks the few foreign gradients there and all-reduces in place)

@@ -230,15 +230,17 @@ class UDFRendererBlending:
 
         n_samples = n0
         if self.n_importance > 0:
-            if self.upsampling_type == "classical":
-                z_vals = self.importance_sample(rays_o, rays_d, z_vals, sd_t)
-            else:
-                z_vals = self.importance_sample_mix(rays_o, rays_d, z_vals, sd_t)
+            with ops.nvtx_range("emap.importance_sample"):
+                if self.upsampling_type == "classical":
+                    z_vals = self.importance_sample(rays_o, rays_d, z_vals, sd_t)
+                else:
+                    z_vals = self.importance_sample_mix(rays_o, rays_d, z_vals, sd_t)
             n_samples = n0 + self.n_importance
 
-        r = self.render_core(rays_o, rays_d, z_vals, sd_t, self.udf_network, self.deviation_network,
-                             beta_network=self.beta_network, cos_anneal_ratio=cos_anneal_ratio,
-                             background_rgb=background_rgb, flip_saturation=flip_saturation)
+        with ops.nvtx_range("emap.render_core"):
+            r = self.render_core(rays_o, rays_d, z_vals, sd_t, self.udf_network, self.deviation_network,
+                                 beta_network=self.beta_network, cos_anneal_ratio=cos_anneal_ratio,
+                                 background_rgb=background_rgb, flip_saturation=flip_saturation)
         w = r["weights"]
         return {
             "udf": r["udf"], "edge": r["edge"],

@@ -189,14 +189,12 @@ def test_bf16_network_forward_and_gradients(golden):
     y, _ = net(x)
     gg = net.gradient(x.clone()).squeeze(1)
     assert maxdiff(y.detach().cpu(), g["out"]) <= 2e-2                   # measured 8.7e-3 (bf16: 8-bit mantissa)
-    # d udf/dx is not pointwise stable under an 8-bit mantissa: softplus(beta = 100) switches a hidden unit
-    # within |a| < ~0.02, a bf16-sized pre-activation error flips sigma between 0 and 1 there (and sign(a_8) near
-    # the zero level set), so single points move by O(1) (measured max 2.3).  The field as a whole is held:
-    dg = (gg.detach().cpu() - g["grad"]).abs().max(dim=1)[0]
-    print("bf16 grad error: median %.3e  p90 %.3e  p99 %.3e  max %.3e" % tuple(
-        float(torch.quantile(dg, q)) for q in (0.5, 0.9, 0.99, 1.0)))
-    assert float(torch.quantile(dg, 0.5)) <= 3e-2
-    assert float(torch.quantile(dg, 0.9)) <= 0.3
+    # d udf/dx: a CPU emulation of single-bf16-MMA arithmetic (weights and layer inputs rounded to bf16) gives
+    # 2.5e-3 median / 9e-3 max against fp32 on these points
+    dg = (gg.detach().cpu() - g["grad"].reshape(-1, 3)).abs().max(dim=1)[0]
+    print("bf16 grad error: median %.3e  p90 %.3e  max %.3e" % tuple(float(torch.quantile(dg, q)) for q in (0.5, 0.9, 1.0)))
+    assert float(dg.median()) <= 1e-2
+    assert float(dg.max()) <= 6e-2
     loss = (g["cu"].to(dev) * y).sum() + (g["cg"].to(dev) * gg).sum()
     loss.backward()
     for n, p in net.named_parameters():

@@ -198,7 +198,7 @@ x = g["x"].to(dev)
 y, _ = netb(x)
 gg = netb.gradient(x.clone()).squeeze(1)
 res["udf_abs"] = maxdiff(y.detach().cpu(), g["out"])
-res["grad_abs"] = maxdiff(gg.detach().cpu(), g["grad"])
+res["grad_abs"] = maxdiff(gg.detach().cpu(), g["grad"].reshape(-1, 3))
 loss = (g["cu"].to(dev) * y).sum() + (g["cg"].to(dev) * gg).sum()
 netb.zero_grad()
 loss.backward()
