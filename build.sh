@@ -11,7 +11,7 @@ FLAGS="-gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -std=c++17 -Xcompil
 objs=""
 pids=""
 names=""
-for f in cabi pack mlp_tc mlp_rg mlp_rev mlp_dw rays mlp_bwd extract; do
+for f in cabi pack mlp_tc mlp_rg mlp_rev mlp_dw rays mlp_bwd extract rendering; do
   [ -f $SRC/$f.cu ] || continue
   if [ ! -f build/$f.o ] || [ $SRC/$f.cu -nt build/$f.o ] || [ $SRC/common.cuh -nt build/$f.o ] || [ $SRC/mlp_dev.cuh -nt build/$f.o ] || [ $SRC/host.h -nt build/$f.o ] || [ include/emap_b200.h -nt build/$f.o ]; then
     extra=""

@@ -70,6 +70,8 @@ SIGNATURES = {
     "emap_bwd_finish": (ctypes.c_int, [_nd, _vp, _vp, _i32, _vp, _vp, _vp, _vp]),
     "emap_bwd_top": (ctypes.c_int, [_nd, _vp, _vp, _vp, _vp, _vp, _i64, _vp, _vp, _vp]),
     "emap_packed_offsets": (ctypes.c_int, [_nd, _vp]),
+    "emap_rendering_network_forward": (ctypes.c_int, [_vp, _vp, _vp, _i32, _i32, _i32, _i32, _i32, _i32, _vp, _vp,
+                                                      _vp, _vp, _i64, _vp, _vp]),
     "emap_null_direction": (ctypes.c_int, [_vp, _i64, _i32, _vp, _vp]),
     "emap_rays_from_pixels": (ctypes.c_int, [_vp, _vp, _vp, _i32, _i32, _vp, _vp, _i32, _vp, _vp, _vp, _vp,
                                              _vp, _vp, _vp]),
@@ -85,7 +87,7 @@ LAUNCHES_PER_CALL = {
     "emap_coarse_z": 1, "emap_upsample_step": 1, "emap_render_prep": 1, "emap_render_core_fwd": 2,
     "emap_render_core_bwd": 2, "emap_bwd_top": 1, "emap_bwd_cotangent_scales": 2,
     "emap_bwd_weight_grads": 1, "emap_bwd_finish": 1, "emap_bwd_dual_forward": 1,
-    "emap_bwd_reverse_sweep": 1, "emap_bwd_tangent_forward": 1, "emap_null_direction": 1, "emap_rays_from_pixels": 1,
+    "emap_bwd_reverse_sweep": 1, "emap_bwd_tangent_forward": 1, "emap_null_direction": 1, "emap_rendering_network_forward": 1, "emap_rays_from_pixels": 1,
 }
 launch_count = 0
 # bench.py: name of ONE C-ABI entry point whose launches are bracketed by CUDA events on the current

@@ -159,6 +159,64 @@ class UDFNetwork(nn.Module):
         return udf_forward_grad_fn(self, x, rays_o, rays_d, z)
 
 
+class RenderingNetwork(nn.Module):
+    """Standalone operator for the reference's ``RenderingNetwork`` (udf_model.py:138-209): same constructor
+    kwargs, parameter creation order (a given seed gives the reference's weights) and ``state_dict`` keys.
+
+    The reference defines and configures this class but never instantiates or calls it -- ``render_core`` uses a
+    constant edge of ones (udf_renderer_blending.py:561) -- so it is NOT wired into ``UDFRendererBlending``.
+    ``forward`` runs one fused CUDA kernel (``emap_rendering_network_forward``: input assembly, view-direction
+    encoding, all Linear + ReLU layers, sigmoid) in fp32.  Forward only: the output carries no autograd graph."""
+
+    MODES = {"idr": 0, "no_view_dir": 1, "no_normal": 2}
+
+    def __init__(self, d_feature, mode, d_in, d_out, d_hidden, n_layers, weight_norm=True, multires_view=0,
+                 squeeze_out=True):
+        super().__init__()
+        if mode not in self.MODES:
+            raise ValueError(f"unknown mode {mode!r}")
+        self.mode = mode
+        self.squeeze_out = squeeze_out
+        self.d_out = d_out
+        self.d_feature = d_feature
+        self.multires_view = multires_view if mode != "no_view_dir" else 0
+        dims = [d_in + d_feature] + [d_hidden for _ in range(n_layers)] + [d_out]
+        self.embedview_fn = None
+        if multires_view > 0 and mode != "no_view_dir":
+            self.embedview_fn, input_ch = get_embedder(multires_view)
+            dims[0] += input_ch - 3
+        self.dims = dims
+        self.num_layers = len(dims)
+        for l in range(self.num_layers - 1):
+            lin = nn.Linear(dims[l], dims[l + 1])
+            if weight_norm:
+                lin = nn.utils.parametrizations.weight_norm(lin)
+            setattr(self, "lin" + str(l), lin)
+        self.relu = nn.ReLU()
+
+    @torch.no_grad()
+    def forward(self, points, normals, view_dirs, feature_vectors):
+        import ctypes
+        dev = points.device
+        n = self.num_layers - 1
+        # weight-norm folded by torch's own parametrization; transposed so that the kernel reads W^T rows coalesced
+        wts = [getattr(self, f"lin{l}").weight.detach().t().contiguous().float() for l in range(n)]
+        bs = [getattr(self, f"lin{l}").bias.detach().contiguous().float() for l in range(n)]
+        pts = C.f32(points.reshape(-1, 3))
+        P = pts.shape[0]
+        nrm = None if normals is None else C.f32(normals.reshape(-1, 3))
+        vdr = None if view_dirs is None else C.f32(view_dirs.reshape(-1, 3))
+        feat = C.f32(feature_vectors.reshape(P, -1))
+        out = torch.empty(P, self.d_out, dtype=torch.float32, device=dev)
+        wt_p = (ctypes.c_void_p * n)(*[C.ptr(t) for t in wts])
+        b_p = (ctypes.c_void_p * n)(*[C.ptr(t) for t in bs])
+        dims = (ctypes.c_int32 * (n + 1))(*self.dims)
+        C.check(C.lib().emap_rendering_network_forward(
+            wt_p, b_p, dims, n, self.MODES[self.mode], int(self.multires_view), int(feat.shape[1]), int(self.d_out),
+            int(bool(self.squeeze_out)), C.ptr(pts), C.ptr(nrm), C.ptr(vdr), C.ptr(feat), P, C.ptr(out), C.stream()))
+        return out
+
+
 class SingleVarianceNetwork(nn.Module):
     """inv_s = exp(10 * variance)   (udf_model.py:212-232)."""
 

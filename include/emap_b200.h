@@ -225,6 +225,18 @@ int emap_rays_from_pixels(const int64_t* pixels_x, const int64_t* pixels_y, cons
                           int32_t B, float* rays_o, float* rays_v, float* edge, float* ndc_uv,
                           float* p_cam, float* depth_scale, void* stream);
 
+/* ---- RenderingNetwork.forward as a standalone operator (src/models/udf_model.py:177-209).
+ * Defined and configured in the reference but never called (render_core uses a constant edge of ones,
+ * udf_renderer_blending.py:561): NOT part of render().  Fused fp32 forward: input assembly for mode 0 "idr" /
+ * 1 "no_view_dir" / 2 "no_normal" incl. the view-direction encoding, n_layers Linear (+ReLU), sigmoid if
+ * squeeze_out.  wt[l] = W_l^T [dims[l], dims[l+1]] row-major with weight-norm folded, bias[l] [dims[l+1]]
+ * (host arrays of device pointers); out [P, d_out].  Forward only.                                          */
+int emap_rendering_network_forward(const float* const* wt, const float* const* bias, const int32_t* dims,
+                                   int32_t n_layers, int32_t mode, int32_t multires_view, int32_t d_feature,
+                                   int32_t d_out, int32_t squeeze_out, const float* points, const float* normals,
+                                   const float* view_dirs, const float* feats, int64_t P, float* out,
+                                   void* stream);
+
 /* ---- misc ------------------------------------------------------------------------------------ */
 /* options: "cluster" = 1|2|-2 : weight-stream organisation of the K1/K1g/dual kernels (1 = default);
  *          "rg_flags" : K1r switches, default 8 (bit 3: tiles handed out by a global atomic counter -- 5.24 vs

@@ -130,3 +130,34 @@ def test_perturb_overwrite_background_and_bf16(golden):
     c = nb.render(*args, cos_anneal_ratio=None, perturb_overwrite=0, flip_saturation=0.9)
     assert torch.isfinite(c["weights"]).all()
     assert maxdiff(c["edge"].cpu(), ref["edge"]) <= 5e-3        # flat sampling; hierarchical: tests/test_gpu_parity_r2.py
+
+
+def test_rendering_network_standalone_operator(golden):
+    """RenderingNetwork.forward (dead code in the reference, built as a standalone operator):
+    same seed -> the reference's own initial weights and state_dict keys; output vs the reference fixture."""
+    from emap_b200.udf_model import RenderingNetwork
+    g = golden("rendering_network")
+    torch.manual_seed(3)
+    rn = RenderingNetwork(d_feature=256, mode="no_normal", d_in=6, d_out=1, d_hidden=128, n_layers=4,
+                          weight_norm=True, multires_view=4, squeeze_out=True)
+    sd = rn.state_dict()
+    ref_sd = {k[3:]: v for k, v in g.items() if k.startswith("sd.")}
+    assert set(sd.keys()) == set(ref_sd.keys())
+    for k in sd:
+        assert torch.equal(sd[k], ref_sd[k]), k                    # bit-identical initialisation
+    rn = rn.to(dev)
+    c = rn(g["pts"].to(dev), g["normals"].to(dev), g["view_dirs"].to(dev), g["feat"].to(dev))
+    assert c.shape == g["color"].shape and c.dtype == torch.float32
+    assert maxdiff(c.cpu(), g["color"]) <= 2e-6                    # fp32 sums in a different order than the CPU GEMM
+    # the other two input modes against the oracle restatement
+    for mode, d_in in (("idr", 9), ("no_view_dir", 9)):
+        torch.manual_seed(4)
+        r2 = RenderingNetwork(d_feature=256, mode=mode, d_in=d_in, d_out=3, d_hidden=64, n_layers=2,
+                              weight_norm=True, multires_view=4 if mode == "idr" else 0, squeeze_out=False)
+        W = [getattr(r2, f"lin{l}").weight.detach() for l in range(3)]
+        b = [getattr(r2, f"lin{l}").bias.detach() for l in range(3)]
+        ref = O.rendering_network_forward(W, b, mode, g["pts"], g["normals"], g["view_dirs"], g["feat"],
+                                          multires_view=4 if mode == "idr" else 0, squeeze_out=False, d_out=3)
+        r2 = r2.to(dev)
+        got = r2(g["pts"].to(dev), g["normals"].to(dev), g["view_dirs"].to(dev), g["feat"].to(dev))
+        assert maxdiff(got.cpu(), ref) <= 1e-5 * max(1.0, float(ref.abs().max())), mode
