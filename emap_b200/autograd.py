@@ -51,14 +51,17 @@ class _UDFForwardGrad(torch.autograd.Function):
     @staticmethod
     def forward(ctx, module, x, rays_o, rays_d, z, *params):
         net = module.packed()
-        # shared-forward backward (opt-in, ops.set_backward_mode): when parameter gradients will be asked for,
-        # the reverse-mode forward also fills the value rows of the backward's stashes
+        # shared-forward backward: when parameter gradients will be asked for, the reverse-mode forward also fills
+        # the value rows of the backward's stashes.  (needs_input_grad ignores torch.no_grad(): without the
+        # is_grad_enabled test every inference render() wrote -- and allocated -- the 4.4 GB stash too; found in the
+        # round-2 ncu capture as 8.8 GB of stores by an "inference" launch.)
         stash = None
-        if ops.shared_backward() and any(ctx.needs_input_grad[5:]):
+        if ops.shared_backward() and torch.is_grad_enabled() and any(ctx.needs_input_grad[5:]):
             P = x.shape[0] if x is not None else z.numel()
             stash = ops.alloc_backward_stash(P, net.packed.device)
         udf, grad = ops.udf_forward_grad(net, module.prec_code, pts=x, rays_o=rays_o, rays_d=rays_d, z=z,
                                          stash=stash)
+        ctx.set_materialize_grads(False)
         ctx.module = module
         ctx.pts = (x, rays_o, rays_d, z)
         ctx.stash = stash
@@ -67,6 +70,8 @@ class _UDFForwardGrad(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, d_udf, d_grad):
+        if d_udf is None and d_grad is None:
+            return (None,) * (5 + len(ctx.module.flat_param_list()))
         module = ctx.module
         x, ro, rd, z = ctx.pts
         net = module.packed()

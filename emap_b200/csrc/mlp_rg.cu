@@ -156,7 +156,7 @@ __device__ __forceinline__ void pe_precompute(const MlpArgs& m, const float (&x)
     uint32_t pu[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) pu[j] = Elem<__half>::pack2(vals[2 * j], vals[2 * j + 1]);
-    stg256(m.st_u0 + (size_t)pt * 64 + sub * 16, pu);
+    stg256_cs(m.st_u0 + (size_t)pt * 64 + sub * 16, pu);
   }
 #pragma unroll
   for (int g = 0; g < 2; ++g) {
@@ -505,7 +505,7 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_rgrad_kernel(const Args args)
           if (!top) stg256(sgp, sw);          // after the hand-off: off the MMA's critical path
           // training: value rows [0,P) of the backward's stash U_{l+1} (emap_bwd_tangent_forward adds the
           // tangent rows later) -- after the hand-off, off the MMA's critical path
-          if (m.st_u && ok) stg256(m.st_u + (size_t)l * 2 * (size_t)m.P * 256 + (size_t)pt * 256 + col0, pu);
+          if (m.st_u && ok) stg256_cs(m.st_u + (size_t)l * 2 * (size_t)m.P * 256 + (size_t)pt * 256 + col0, pu);
         }
         tc_fence_before();
         __syncwarp();

@@ -20,6 +20,7 @@ class _RenderCore(torch.autograd.Function):
         if cfg.get("global_stats"):
             from .parallel import globalize_eikonal
             reduced = globalize_eikonal(reduced)       # exact full-batch eikonal means across ray shards
+        ctx.set_materialize_grads(False)      # unused outputs arrive as None (a NULL cotangent), not as zero tensors
         ctx.save_for_backward(udf, grad, scalars, rays_o, rays_d, mid_z, dists, reduced)
         ctx.cfg, ctx.B, ctx.n = cfg, B, n
         gerr, gerr_ns, sparse = reduced[0], reduced[1], reduced[2]

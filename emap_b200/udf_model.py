@@ -100,6 +100,11 @@ class UDFNetwork(nn.Module):
         ps = self.flat_param_list()
         return (tuple(p._version for p in ps), tuple(p.data_ptr() for p in ps), self.precision)
 
+    def invalidate(self) -> None:
+        """Force a re-fold at the next call.  The fold cache is keyed on the parameters' ``_version`` (bumped by
+        optimizers, ``load_state_dict``, in-place ops) -- writes through ``p.data`` do not bump it."""
+        self._folded_version = None
+
     def packed(self) -> ops.PackedNet:
         """Fold weight-norm and (re)pack the tensor-core operands iff a parameter changed."""
         ps = self.flat_param_list()
