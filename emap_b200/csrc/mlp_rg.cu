@@ -461,7 +461,8 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_rgrad_kernel(const Args args)
               m.dbg_acc[((size_t)l * 128 + row) * 256 + col0 + k] = __uint_as_float(r[k]) * kInvWeightScale;
           }
           uint32_t* sgp = sg_ptr(top ? 0 : l, chunk);
-          uint32_t sw[8];                     // (e, sign t) codes of this thread's 16 columns -> sigma_l in the sweep
+          float ev[16];                       // e = exp(-|t|) of this thread's 16 columns ...
+          uint32_t tneg = 0;                  // ... and the sign bits of t: sigma_l is rebuilt from them in the sweep
           uint32_t pu[8];                     // h_{l+1} of this thread's 16 columns as fp16 (training stash)
 #pragma unroll
           for (int g = 0; g < 2; ++g) {
@@ -469,17 +470,13 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_rgrad_kernel(const Args args)
             const float bb[8] = {bA.x, bA.y, bA.z, bA.w, bB.x, bB.y, bB.z, bB.w};
             float h[8];
             if (!top) {
-              uint32_t code[8];
 #pragma unroll
               for (int j = 0; j < 8; ++j) {
                 const float t = fmaf(__uint_as_float(r[g * 8 + j]), k1, bb[j]);
-                float e;
-                h[j] = softplus100_e(t, e);
-                code[j] = enc_e(e, t);
+                h[j] = softplus100_e(t, ev[g * 8 + j]);
+                tneg |= (__float_as_uint(t) >> 31) << (g * 8 + j);
               }
               store_group<NTERMS, T>(dst_hi, dst_lo, row, sub * 2 + g, h);
-#pragma unroll
-              for (int j = 0; j < 4; ++j) sw[g * 4 + j] = code[2 * j] | (code[2 * j + 1] << 16);
             } else {
               // a_8 += w_8 . h_8;  unsigned seed of the sweep: alpha_7 = w_8 . sigma_7 (x 2^4)
               const float4 wA = __ldg(reinterpret_cast<const float4*>(w8 + col0 + g * 8));
@@ -502,7 +499,16 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_rgrad_kernel(const Args args)
           __syncwarp();
           if (lane == 0) mbar_arrive(&a_ready[chunk]);
           if (stamp && chunk == 0) m.dbg_clk[4 * l + 2] = clock64();
-          if (!top) stg256(sgp, sw);          // after the hand-off: off the MMA's critical path
+          if (!top) {                         // after the hand-off, off the MMA's critical path: encode and stash
+            uint32_t sw[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const uint32_t c0 = (__float_as_uint(fmaf(ev[2 * j], kSigmaQ, 12582912.0f)) & 0x7fffu) | (((tneg >> (2 * j)) & 1u) << 15);
+              const uint32_t c1 = (__float_as_uint(fmaf(ev[2 * j + 1], kSigmaQ, 12582912.0f)) & 0x7fffu) | (((tneg >> (2 * j + 1)) & 1u) << 15);
+              sw[j] = c0 | (c1 << 16);
+            }
+            stg256(sgp, sw);
+          }
           // training: value rows [0,P) of the backward's stash U_{l+1} (emap_bwd_tangent_forward adds the
           // tangent rows later) -- after the hand-off, off the MMA's critical path
           if (m.st_u && ok) stg256_cs(m.st_u + (size_t)l * 2 * (size_t)m.P * 256 + (size_t)pt * 256 + col0, pu);

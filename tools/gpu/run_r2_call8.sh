@@ -2,6 +2,7 @@
 # round 2, call 8: inference without the training stash, fewer ATen launches, RenderingNetwork op; ncu of K1r in both modes.
 mkdir -p gpurun_out
 O=gpurun_out
+timeout 300 python tools/gpu/gpu_time_stages.py > $O/stages_time.txt 2>&1; cat $O/stages_time.txt | cut -c1-300
 timeout 900 python -m pytest tests -q -m gpu > $O/pytest_gpu.log 2>&1; echo "pytest rc=$?"; tail -6 $O/pytest_gpu.log
 timeout 300 python bench.py --no-cpu-baseline --no-gpu-incumbent > $O/bench_train_fp32.json 2> $O/bench_train.err; echo "bench train rc=$?"; cut -c1-200 $O/bench_train_fp32.json; tail -3 $O/bench_train.err
 timeout 300 python bench.py --mode infer --no-cpu-baseline --no-gpu-incumbent > $O/bench_infer_fp32.json 2> $O/bench_infer.err; echo "bench infer rc=$?"; cut -c1-200 $O/bench_infer_fp32.json
