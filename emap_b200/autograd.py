@@ -49,14 +49,15 @@ class _UDFForward(torch.autograd.Function):
 
 class _UDFForwardGrad(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, module, x, rays_o, rays_d, z, *params):
+    def forward(ctx, module, x, rays_o, rays_d, z, grad_mode_on, *params):
         net = module.packed()
         # shared-forward backward: when parameter gradients will be asked for, the reverse-mode forward also fills
-        # the value rows of the backward's stashes.  (needs_input_grad ignores torch.no_grad(): without the
-        # is_grad_enabled test every inference render() wrote -- and allocated -- the 4.4 GB stash too; found in the
-        # round-2 ncu capture as 8.8 GB of stores by an "inference" launch.)
+        # the value rows of the backward's stashes.  needs_input_grad ignores torch.no_grad() (without the grad-mode
+        # test every inference render() wrote -- and allocated -- the 4.4 GB stash too; found in the round-2 ncu
+        # capture as 8.8 GB of stores by an "inference" launch), and grad mode is always OFF inside
+        # Function.forward, so the caller samples it (udf_forward_grad_fn) and passes it in.
         stash = None
-        if ops.shared_backward() and torch.is_grad_enabled() and any(ctx.needs_input_grad[5:]):
+        if ops.shared_backward() and grad_mode_on and any(ctx.needs_input_grad[6:]):
             P = x.shape[0] if x is not None else z.numel()
             stash = ops.alloc_backward_stash(P, net.packed.device)
         udf, grad = ops.udf_forward_grad(net, module.prec_code, pts=x, rays_o=rays_o, rays_d=rays_d, z=z,
@@ -71,7 +72,7 @@ class _UDFForwardGrad(torch.autograd.Function):
     @staticmethod
     def backward(ctx, d_udf, d_grad):
         if d_udf is None and d_grad is None:
-            return (None,) * (5 + len(ctx.module.flat_param_list()))
+            return (None,) * (6 + len(ctx.module.flat_param_list()))
         module = ctx.module
         x, ro, rd, z = ctx.pts
         net = module.packed()
@@ -84,7 +85,7 @@ class _UDFForwardGrad(torch.autograd.Function):
                                      pts=x, rays_o=ro, rays_d=rd, z=z, flat_params=net.flat, stash=stash)
         ctx.stash = None
         grads = _split_flat(flat_grad, module.flat_param_list())
-        return (None, None, None, None, None, *grads)
+        return (None, None, None, None, None, None, *grads)
 
 
 def _detach(t):
@@ -100,4 +101,5 @@ def udf_forward_fn(module, x=None, rays_o=None, rays_d=None, z=None, want_pe=Fal
 
 def udf_forward_grad_fn(module, x=None, rays_o=None, rays_d=None, z=None):
     params = module.flat_param_list()
-    return _UDFForwardGrad.apply(module, _detach(x), _detach(rays_o), _detach(rays_d), _detach(z), *params)
+    return _UDFForwardGrad.apply(module, _detach(x), _detach(rays_o), _detach(rays_d), _detach(z),
+                                 torch.is_grad_enabled(), *params)

@@ -80,6 +80,15 @@ def check_status(dev) -> None:
         _raise_status(st, bits)
 
 
+# set by graph.GraphedStep while it warms up / captures an iteration: host-side draws and other things that a CUDA
+# graph would freeze are refused already in the warm-up, before any capture has begun
+graph_prepare = False
+
+
+def graph_capturing() -> bool:
+    return graph_prepare or torch.cuda.is_current_stream_capturing()
+
+
 # ----------------------------------------------------------------------------- NVTX ranges
 # EMAP_NVTX=1 brackets the stages of the path (render, importance sampling, render_core, the backward's stages)
 # with NVTX ranges for Nsight timelines; off by default (the reference has no tracing at all).

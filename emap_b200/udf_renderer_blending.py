@@ -68,6 +68,10 @@ class UDFRendererBlending:
         self._const_cache: Dict = {}
         # multi-GPU: make the two eikonal means those of the whole (sharded) batch (parallel.py)
         self.global_batch_stats = False
+        # False: the stratified offsets come from the global CPU generator exactly like the reference (:719: same
+        # seed -> same samples).  True: drawn on the device -- same distribution, another stream, no host->device
+        # copy; required inside a CUDA-graph capture (graph.GraphedStep), where a host draw would be frozen.
+        self.perturb_on_device = False
 
     def check_numerics(self):
         """Blocking check of the device status word (one 4-byte read); raises FloatingPointError where the
@@ -240,8 +244,14 @@ class UDFRendererBlending:
         perturb = self.perturb if perturb_overwrite < 0 else perturb_overwrite
         t_rand = None
         if perturb > 0:
-            # one draw from the GLOBAL CPU generator, exactly like the reference (:719) -> same seeds
-            t_rand = (torch.rand([B, 1]) - 0.5).to(dev, non_blocking=True)
+            if self.perturb_on_device:
+                t_rand = torch.rand([B, 1], device=dev) - 0.5
+            elif ops.graph_capturing():
+                raise RuntimeError("render() under CUDA-graph capture: set renderer.perturb_on_device = True "
+                                   "(a host-side draw would be frozen into the graph)")
+            else:
+                # one draw from the GLOBAL CPU generator, exactly like the reference (:719) -> same seeds
+                t_rand = (torch.rand([B, 1]) - 0.5).to(dev, non_blocking=True)
         elif not per_ray:
             raise ValueError("perturb == 0 with scalar near/far: the reference crashes here too "
                              "(z stays [1,n]); pass near/far as [B,1] tensors")

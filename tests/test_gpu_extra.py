@@ -150,7 +150,7 @@ def test_rendering_network_standalone_operator(golden):
     assert c.shape == g["color"].shape and c.dtype == torch.float32
     assert maxdiff(c.cpu(), g["color"]) <= 2e-6                    # fp32 sums in a different order than the CPU GEMM
     # the other two input modes against the oracle restatement
-    for mode, d_in in (("idr", 9), ("no_view_dir", 9)):
+    for mode, d_in in (("idr", 12), ("no_view_dir", 9)):       # d_in counts points, view, normals, -normals
         torch.manual_seed(4)
         r2 = RenderingNetwork(d_feature=256, mode=mode, d_in=d_in, d_out=3, d_hidden=64, n_layers=2,
                               weight_norm=True, multires_view=4 if mode == "idr" else 0, squeeze_out=False)

@@ -101,13 +101,14 @@ def test_reverse_mode_rays_ragged_many_tiles_and_repeatable():
 
 def test_split_tail_and_static_schedule_variants_are_bit_identical(golden):
     """rg_flags bit 0: N-split of each step's last K chunk (same MMA order per accumulator column); bit 3 off:
-    static round-robin tiles instead of the dynamic counter (the default) -- which CTA runs a tile must not matter."""
+    static round-robin tiles instead of the dynamic counter (the default) -- which CTA runs a tile must not matter;
+    bit 2: the instantiation whose MMA issuer walks the 16 steps in a rolled loop (same instruction stream)."""
     from emap_b200 import ops, _cabi as C
     g = golden("mlp_pert")
     net, _ = _net(True)
     x = g["x"].cuda().repeat(60, 1)           # 23,040 points -> 180 tiles: two tiles on some CTAs
     u1, g1 = ops.udf_forward_grad(net, C.PREC_FP32X3, pts=x, mode="reverse")
-    for flags in (9, 0, 1):
+    for flags in (9, 0, 1, 12, 4):
         try:
             C.set_option("rg_flags", flags)
             u2, g2 = ops.udf_forward_grad(net, C.PREC_FP32X3, pts=x, mode="reverse")

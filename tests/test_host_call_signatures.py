@@ -186,8 +186,18 @@ def test_autograd_wiring_of_the_backward_modes(shim, grad_mode, bwd_mode, expect
         mod.net.fold_id += 1
         (udf.sum() + grad.sum()).backward()
         assert "emap_bwd_dual_forward" in rec.calls and "emap_bwd_tangent_forward" not in rec.calls
-    # no parameter gradient requested -> no stash is allocated / filled
-    rec.calls.clear()
-    with torch.no_grad():
+    # no parameter gradient requested (inference under no_grad) -> no stash is allocated / filled;
+    # with grad mode on it is, exactly when the shared backward is selected
+    allocs = []
+    real_alloc = ops.alloc_backward_stash
+    ops.alloc_backward_stash = lambda *a, **k: (allocs.append(a), real_alloc(*a, **k))[1]
+    try:
+        rec.calls.clear()
+        with torch.no_grad():
+            udf_forward_grad_fn(mod, x)
+        assert rec.calls.count("emap_udf_forward_grad_rev") + rec.calls.count("emap_udf_forward_grad") == 1
+        assert allocs == []
         udf_forward_grad_fn(mod, x)
-    assert rec.calls.count("emap_udf_forward_grad_rev") + rec.calls.count("emap_udf_forward_grad") == 1
+        assert (len(allocs) == 1) == expect_shared
+    finally:
+        ops.alloc_backward_stash = real_alloc

@@ -52,14 +52,14 @@ for prec, name in ((3, "fp32x3"), (1, "fp16")):
     tr2 = t(lambda: ops.udf_forward_grad(net, prec, pts=x, mode="reverse"))
     C.set_option("rg_flags", 8)
     print(f"{name}: K1r with the persisting-L2 window on the sigma scratch (rg_flags=2): {tr2:.2f} ms", flush=True)
-    for fl in (0, 10):
+    for fl in (0, 10, 12, 4):
         C.set_option("rg_flags", fl)
         ud, gd = ops.udf_forward_grad(net, prec, pts=x, mode="reverse")
         torch.cuda.synchronize()
         same = bool(torch.equal(ud, ur) and torch.equal(gd, gr))
         trd = t(lambda: ops.udf_forward_grad(net, prec, pts=x, mode="reverse"))
         C.set_option("rg_flags", 8)
-        print(f"{name}: K1r rg_flags={fl} (default 8 = dynamic tiles; 0 = static round robin, 2 = persisting L2): {trd:.2f} ms, bit-identical to the default: {same}", flush=True)
+        print(f"{name}: K1r rg_flags={fl} (default 8 = dynamic tiles; 0 = static round robin, 2 = persisting L2, 4 = rolled issuer loop): {trd:.2f} ms, bit-identical to the default: {same}", flush=True)
     flop = 2 * 918016 * P
     print(f"{name}: K1g {tf:.2f} ms ({flop / tf / 1e9:.0f} TF/s alg)   K1r {tr:.2f} ms ({flop / tr / 1e9:.0f} TF/s alg)   "
           f"K1 forward only {f0:.2f} ms", flush=True)
