@@ -11,7 +11,11 @@
 //   * the W^T images of the backward's reverse sweep (hi only) and of the reverse-mode gradient
 //     kernel (hi and lo; mlp_rg.cu).
 #include <math.h>
+#include <stdlib.h>
 #include <string.h>
+#include <map>
+#include <mutex>
+#include <tuple>
 #include <vector>
 
 #include "common.cuh"
@@ -309,6 +313,46 @@ int check_net(const emap_net_desc* net) {
   return 0;
 }
 
+// Immortal per-descriptor host copy of the packed buffer's header and item tables (see emap_wn_fold).
+struct LayoutBlob {
+  PackedHeader h;
+  RingItem *t1, *t3, *tr;
+  size_t n1, n3, nr;
+};
+static const LayoutBlob* layout_blob(const emap_net_desc& net) {
+  static std::mutex mu;
+  static std::map<std::tuple<int, int, int, uint32_t>, LayoutBlob*> cache;
+  uint32_t sbits;
+  memcpy(&sbits, &net.scale, sizeof(sbits));
+  const auto key = std::make_tuple((int)net.multires, (int)net.udf_type, (int)net.elem_type, sbits);
+  std::lock_guard<std::mutex> lock(mu);
+  auto it = cache.find(key);
+  if (it != cache.end()) return it->second;
+  PackedHeader h; std::vector<RingItem> t1, t3, tr;
+  build_layout(net, h, t1, t3);
+  build_rev_items(h, tr);
+  const size_t items = t1.size() + t3.size() + tr.size();
+  const size_t bytes = sizeof(LayoutBlob) + items * sizeof(RingItem) + 64;
+  void* mem = nullptr;
+  if (cudaHostAlloc(&mem, bytes, cudaHostAllocDefault) != cudaSuccess) {
+    cudaGetLastError();
+    mem = malloc(bytes);            // pageable: still immortal, only not capturable / not asynchronous
+    if (!mem) return nullptr;
+  }
+  LayoutBlob* lb = new (mem) LayoutBlob();
+  lb->h = h;
+  uintptr_t q = (reinterpret_cast<uintptr_t>(lb + 1) + 15) & ~(uintptr_t)15;
+  lb->t1 = reinterpret_cast<RingItem*>(q);
+  lb->t3 = lb->t1 + t1.size();
+  lb->tr = lb->t3 + t3.size();
+  lb->n1 = t1.size(); lb->n3 = t3.size(); lb->nr = tr.size();
+  if (lb->n1) memcpy(lb->t1, t1.data(), lb->n1 * sizeof(RingItem));
+  if (lb->n3) memcpy(lb->t3, t3.data(), lb->n3 * sizeof(RingItem));
+  if (lb->nr) memcpy(lb->tr, tr.data(), lb->nr * sizeof(RingItem));
+  cache[key] = lb;
+  return lb;
+}
+
 }  // namespace emap
 
 using namespace emap;
@@ -330,34 +374,32 @@ extern "C" int emap_wn_fold(const emap_net_desc* net, const float* flat_params, 
   if (check_net(net)) return 1;
   if (!flat_params || !packed) return set_error("emap_wn_fold: NULL pointer");
   cudaStream_t stream = (cudaStream_t)stream_;
-  PackedHeader h; std::vector<RingItem> t1, t3;
-  build_layout(*net, h, t1, t3);
-  if (t3.size() > (size_t)kMaxItems) return set_error("internal: item table overflow");
-  // header + tables: small pageable H2D copies (stream-ordered; contents are a pure function of net)
+  const LayoutBlob* lb = layout_blob(*net);
+  if (!lb) return set_error("emap_wn_fold: cannot allocate the layout tables");
+  const PackedHeader& h = lb->h;
+  if (lb->n3 > (size_t)kMaxItems) return set_error("internal: item table overflow");
+  // header + tables: a pure function of net, kept in an immortal PINNED host blob per descriptor, so that the four
+  // small H2D copies are truly asynchronous and stay valid when the call is captured into a CUDA graph (a copy
+  // from a stack/vector temporary would be replayed from a dead address)
   uint8_t* p = reinterpret_cast<uint8_t*>(packed);
-  EMAP_CUDA(cudaMemcpyAsync(p, &h, sizeof(h), cudaMemcpyHostToDevice, stream));
-  EMAP_CUDA(cudaMemcpyAsync(p + h.items_off[0], t1.data(), t1.size() * sizeof(RingItem),
-                            cudaMemcpyHostToDevice, stream));
-  EMAP_CUDA(cudaMemcpyAsync(p + h.items_off[1], t3.data(), t3.size() * sizeof(RingItem),
-                            cudaMemcpyHostToDevice, stream));
-  std::vector<RingItem> tr;
-  build_rev_items(h, tr);
-  EMAP_CUDA(cudaMemcpyAsync(p + h.reserved[0], tr.data(), tr.size() * sizeof(RingItem),
-                            cudaMemcpyHostToDevice, stream));
+  EMAP_CUDA(cudaMemcpyAsync(p, &lb->h, sizeof(PackedHeader), cudaMemcpyHostToDevice, stream));
+  EMAP_CUDA(cudaMemcpyAsync(p + h.items_off[0], lb->t1, lb->n1 * sizeof(RingItem), cudaMemcpyHostToDevice, stream));
+  EMAP_CUDA(cudaMemcpyAsync(p + h.items_off[1], lb->t3, lb->n3 * sizeof(RingItem), cudaMemcpyHostToDevice, stream));
+  EMAP_CUDA(cudaMemcpyAsync(p + h.reserved[0], lb->tr, lb->nr * sizeof(RingItem), cudaMemcpyHostToDevice, stream));
   int rows = 0;
   for (int l = 0; l < kNumLinear; ++l) rows += (int)h.out_dim[l];
   const int threads = 256, wpb = threads / 32;
   wn_fold_kernel<<<(rows + wpb - 1) / wpb, threads, 0, stream>>>(flat_params, p, net->multires);
   EMAP_CUDA(cudaGetLastError());
   if (net->elem_type == 0)
-    pack_images_kernel<__half><<<(unsigned)t3.size(), 256, 0, stream>>>(p);
+    pack_images_kernel<__half><<<(unsigned)lb->n3, 256, 0, stream>>>(p);
   else
-    pack_images_kernel<__nv_bfloat16><<<(unsigned)t3.size(), 256, 0, stream>>>(p);
+    pack_images_kernel<__nv_bfloat16><<<(unsigned)lb->n3, 256, 0, stream>>>(p);
   EMAP_CUDA(cudaGetLastError());
   if (net->elem_type == 0)
-    pack_rev_images_kernel<__half><<<(unsigned)tr.size(), 256, 0, stream>>>(p);
+    pack_rev_images_kernel<__half><<<(unsigned)lb->nr, 256, 0, stream>>>(p);
   else
-    pack_rev_images_kernel<__nv_bfloat16><<<(unsigned)tr.size(), 256, 0, stream>>>(p);
+    pack_rev_images_kernel<__nv_bfloat16><<<(unsigned)lb->nr, 256, 0, stream>>>(p);
   EMAP_CUDA(cudaGetLastError());
   if (net->elem_type == 0)
     pack_rg_images_kernel<__half><<<kRgBigImages + kRgSmallImages, 256, 0, stream>>>(p);

@@ -66,3 +66,12 @@ for dyn in (1, 0):
 C.set_option("dynamic_tiles", 1)
 C.set_option("rg_flags", 8)
 print("bit-identical static vs dynamic:", [bool(torch.equal(a, b)) for a, b in zip(res[0], res[1])])
+# K1r in training mode (writes the backward's value stash): variants, two interleaved rounds against order effects
+# (rg_flags: 8 = default, +2 = persisting-L2 window on the sigma scratch, +4 = rolled issuer loop)
+for rnd in range(2):
+    line = []
+    for fl in (8, 10, 12, 14):
+        C.set_option("rg_flags", fl)
+        line.append(f"flags {fl}: {t(lambda: ops.udf_forward_grad(net, 3, pts=x, mode='reverse', stash=stash), reps=6):.2f}")
+    C.set_option("rg_flags", 8)
+    print(f"K1r+stash round {rnd}: " + "   ".join(line) + "  ms", flush=True)
