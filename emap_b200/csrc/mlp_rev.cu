@@ -51,6 +51,8 @@ __device__ __forceinline__ uint32_t pack2h(float a, float b) {
   return *reinterpret_cast<uint32_t*>(&h);
 }
 
+// ROLL: the issuer's layer loop rolled (instruction-cache footprint, see mlp_tc.cu / mlp_rg.cu)
+template <bool ROLL>
 __global__ void __launch_bounds__(kThreads, 1) mlp_rev_kernel(const Args args) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
@@ -113,7 +115,7 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_rev_kernel(const Args args) {
     for (int iter = 0;; ++iter) {
       mbar_wait(sched_ready, (uint32_t)iter & 1, 561);
       if (sched_tile[iter & 1] >= args.num_tiles) break;
-#pragma unroll
+#pragma unroll (ROLL ? 1 : kRevLayers)
       for (int j = 0; j < kRevLayers; ++j) {
         const int buf = j & 1;
         {
@@ -285,6 +287,8 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_rev_kernel(const Args args) {
 
 static int g_dynamic = 1;
 int set_dynamic(int v) { g_dynamic = v; return 0; }
+static int g_rolled = 0;         // emap_set_option("rev_rolled", 1)
+int set_rolled(int v) { g_rolled = v; return 0; }
 
 }  // namespace rev
 }  // namespace emap
@@ -307,10 +311,12 @@ extern "C" int emap_bwd_reverse_sweep(const emap_net_desc* net, const void* pack
   a.tile_counter = rev::g_dynamic ? tile_counter((cudaStream_t)stream) : nullptr;
   static bool attr_done = false;
   if (!attr_done) {
-    EMAP_CUDA(cudaFuncSetAttribute(rev::mlp_rev_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, rev::Smem::total));
+    EMAP_CUDA(cudaFuncSetAttribute(rev::mlp_rev_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, rev::Smem::total));
+    EMAP_CUDA(cudaFuncSetAttribute(rev::mlp_rev_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, rev::Smem::total));
     attr_done = true;
   }
-  rev::mlp_rev_kernel<<<grid, rev::kThreads, rev::Smem::total, (cudaStream_t)stream>>>(a);
+  if (rev::g_rolled) rev::mlp_rev_kernel<true><<<grid, rev::kThreads, rev::Smem::total, (cudaStream_t)stream>>>(a);
+  else rev::mlp_rev_kernel<false><<<grid, rev::kThreads, rev::Smem::total, (cudaStream_t)stream>>>(a);
   EMAP_CUDA(cudaGetLastError());
   return 0;
 }

@@ -65,6 +65,7 @@ constexpr int kFlagSplitTail = 1;   // N-split of each step's last K chunk (as K
 constexpr int kFlagL2Persist = 2;   // host side: launch with the sigma scratch as a persisting-L2 access window
 constexpr int kFlagDynamic = 8;     // tiles handed out by a global atomic counter instead of the static round robin
 constexpr int kFlagRolled = 4;      // host side: select the instantiation with the rolled issuer loop
+constexpr int kFlagRolledEpi = 16;  // host side: ... and with the reverse steps' chunk loop rolled as well
 
 template <int NTERMS>
 struct Plan {
@@ -172,9 +173,12 @@ __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
 
-// ROLL: the issuer walks the 16 steps in a rolled loop (schedule computed at run time) instead of 16 unrolled
-// copies of its body -- 11.8 k of the kernel's 19.5 k SASS instructions were the unrolled issuer.
-template <int NTERMS, typename T, bool ROLL>
+// ROLL >= 1: the issuer walks the 16 steps in a rolled loop (schedule computed at run time) instead of 16 unrolled
+// copies of its body -- 11.8 k of the kernel's 19.5 k SASS instructions were the unrolled issuer, executed by ONE
+// thread but competing with the 16 epilogue warps for the SM's instruction cache (stall_no_inst 8.5 % in the ncu
+// source view): 7.26 -> 6.35 ms in training mode (profiles/r02_stages_time.txt).  ROLL = 2 also rolls the chunk
+// loop of the reverse steps' epilogue.
+template <int NTERMS, typename T, int ROLL>
 __global__ void __launch_bounds__(kThreads, 1) mlp_rgrad_kernel(const Args args) {
   using P = Plan<NTERMS>;
   constexpr int kStages = P::kStages;
@@ -269,7 +273,7 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_rgrad_kernel(const Args args)
     for (int iter = 0;; ++iter) {
       mbar_wait(sched_ready, (uint32_t)iter & 1, 561);
       if (sched_tile[iter & 1] >= m.num_tiles) break;
-#pragma unroll (ROLL ? 1 : kSteps)
+#pragma unroll (ROLL >= 1 ? 1 : kSteps)
       for (int s = 0; s < kSteps; ++s) {
         const int buf = s & 1;
         // timeline of block 0's second tile (emap_debug_rgrad + emap_debug_set_clk_buffer): issuer stamps at
@@ -550,7 +554,7 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_rgrad_kernel(const Args args)
         mbar_wait(&acc_full[buf * 2], acc_par, 530 + buf, s);
         tc_fence_after();
         if (stamp) m.dbg_clk[4 * s + 1] = clock64();
-#pragma unroll
+#pragma unroll (ROLL >= 2 ? 1 : 4)
         for (int chunk = 0; chunk < 4; ++chunk) {
           const int col0 = chunk * 64 + sub * 16;
           if (chunk == 2) { mbar_wait(&acc_full[buf * 2 + 1], acc_par, 535 + buf, s); tc_fence_after(); }
@@ -664,19 +668,20 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_rgrad_kernel(const Args args)
   }
 }
 
-static int g_flags = kFlagDynamic;   // emap_set_option("rg_flags", bits); dynamic tiles: 5.24 vs 6.05 ms per 1 M points (B200)
+static int g_flags = kFlagDynamic | kFlagRolled;   // emap_set_option("rg_flags", bits); both measured (B200): dynamic tiles 5.24 vs 6.05 ms, rolled issuer 6.35 vs 7.26 ms with the training stash
 int set_flags(int v) { g_flags = v; return 0; }
 
-template <int NTERMS, typename T, bool ROLL>
+template <int NTERMS, typename T, int ROLL>
 static int launch_r(const Args& a_in, size_t scratch_bytes, cudaStream_t stream);
 
 template <int NTERMS, typename T>
 static int launch(const Args& a_in, size_t scratch_bytes, cudaStream_t stream) {
-  if (g_flags & kFlagRolled) return launch_r<NTERMS, T, true>(a_in, scratch_bytes, stream);
-  return launch_r<NTERMS, T, false>(a_in, scratch_bytes, stream);
+  if (g_flags & kFlagRolledEpi) return launch_r<NTERMS, T, 2>(a_in, scratch_bytes, stream);
+  if (g_flags & kFlagRolled) return launch_r<NTERMS, T, 1>(a_in, scratch_bytes, stream);
+  return launch_r<NTERMS, T, 0>(a_in, scratch_bytes, stream);
 }
 
-template <int NTERMS, typename T, bool ROLL>
+template <int NTERMS, typename T, int ROLL>
 static int launch_r(const Args& a_in, size_t scratch_bytes, cudaStream_t stream) {
   Args a = a_in;
   a.flags = g_flags;

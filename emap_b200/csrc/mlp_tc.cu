@@ -33,13 +33,18 @@ namespace emap {
 
 namespace rg { int set_flags(int v); }   // mlp_rg.cu
 namespace dw { int set_desc_strides(int which, int v); }   // mlp_dw.cu
-namespace rev { int set_dynamic(int v); }                  // mlp_rev.cu
+namespace rev { int set_dynamic(int v); int set_rolled(int v); }   // mlp_rev.cu
 
-template <int NTERMS, int MODE, typename T, int CL>
+template <int NTERMS, int MODE, typename T, int CL_>
 __global__ void __launch_bounds__(kThreads, 1) mlp_kernel(const MlpArgs args) {
   // CL = 1|2|4: weight-stream multicast width (cta_group::1).  CL = -2: PAIR mode -- clusters of two CTAs
   // driven by ONE MMA issuer with tcgen05.mma.cta_group::2 (M = 256: each CTA's 128-row tile, N = 256 split
   // as 128 weight rows per CTA): every SM stages and reads only half of each weight operand.
+  // CL_ = 3: CL = 1 with the issuer's layer loop ROLLED (schedule computed at run time): the unrolled issuer is
+  // ~half of the kernel's SASS and is executed by one thread -- it only costs instruction-cache capacity that
+  // the 16 epilogue warps need (K1r: 7.26 -> 6.35 ms in training mode from this alone, profiles/r02_*).
+  constexpr bool ROLLI = (CL_ == 3);
+  constexpr int CL = ROLLI ? 1 : CL_;
   constexpr bool PAIR = (CL == -2);
   constexpr int CLW = PAIR ? 2 : CL;             // cluster width
   using Plan = SmemPlan<NTERMS, MODE, PAIR>;
@@ -200,7 +205,7 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_kernel(const MlpArgs args) {
         mbar_wait(sched_ready, (uint32_t)iter & 1, 561);
         if (sched_tile[iter & 1] >= args.num_tiles) break;
       }
-#pragma unroll
+#pragma unroll (ROLLI ? 1 : MI::kLayers)
       for (int l = 0; l < MI::kLayers; ++l) {
         const int buf = l & 1;
         const bool stamp = args.dbg_clk && blockIdx.x == 0 && iter == args.dbg_iter && lane == 0;
@@ -645,8 +650,9 @@ static int g_dbg_iter = 1;    // which tile iteration of block 0 the clock64 tim
 int dbg_iter() { return g_dbg_iter; }
 
 // ---------------------------------------------------------------------------------------------
-template <int NTERMS, int MODE, typename T, int CL>
+template <int NTERMS, int MODE, typename T, int CL_>
 static int launch(const MlpArgs& a_in, cudaStream_t stream) {
+  constexpr int CL = (CL_ == 3) ? 1 : CL_;       // 3 = width 1 with the rolled issuer loop
   constexpr bool PAIR = (CL == -2);
   constexpr int CLW = PAIR ? 2 : CL;
   using Plan = SmemPlan<NTERMS, MODE, PAIR>;
@@ -662,7 +668,7 @@ static int launch(const MlpArgs& a_in, cudaStream_t stream) {
   grid = grid / CLW * CLW;
   if (tiles < grid) grid = (int)((tiles + CLW - 1) / CLW * CLW);
   a.iters = (int)((tiles + grid - 1) / grid);
-  auto kern = mlp_kernel<NTERMS, MODE, T, CL>;
+  auto kern = mlp_kernel<NTERMS, MODE, T, CL_>;
   static bool attr_done = false;   // per template instantiation
   if (!attr_done) {
     EMAP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Plan::total));
@@ -699,6 +705,7 @@ static int dispatch(const emap_net_desc* net, int precision, const MlpArgs& a, c
 #define EMAP_LAUNCH(NT, TT)                                              \
   do {                                                                   \
     if (cl == 2) return launch<NT, MODE, TT, 2>(a, st);                  \
+    if (cl == 3) return launch<NT, MODE, TT, 3>(a, st);                  \
     return launch<NT, MODE, TT, 1>(a, st);                               \
   } while (0)
   if (precision == EMAP_PREC_FP32X3) {
@@ -723,7 +730,8 @@ static int check_points(const float* pts, const float* rays_o, const float* rays
 }
 
 int set_cluster_width(int v) {
-  if (v != 1 && v != 2 && v != -2) return set_error("cluster must be 1, 2 (multicast) or -2 (cta_group::2 pairs)");
+  if (v != 1 && v != 2 && v != 3 && v != -2)
+    return set_error("cluster must be 1, 2 (multicast), 3 (1 with the rolled issuer loop) or -2 (cta_group::2 pairs)");
   g_cluster = v;
   return 0;
 }
@@ -799,6 +807,9 @@ extern "C" int emap_bwd_tangent_forward(const emap_net_desc* net, const void* pa
   a.n_per_ray = n_per_ray; a.P = P; a.gbar = d_grad; a.bwd_scales = scales;
   a.st_u0 = (__half*)st_u0; a.st_u = (__half*)st_u;
   // single-MMA, one CTA per SM, no cluster variants: the only configuration this mode is built for
+  if (g_cluster == 3)
+    return net->elem_type == 0 ? launch<1, 3, __half, 3>(a, (cudaStream_t)stream)
+                               : launch<1, 3, __nv_bfloat16, 3>(a, (cudaStream_t)stream);
   if (net->elem_type == 0) return launch<1, 3, __half, 1>(a, (cudaStream_t)stream);
   return launch<1, 3, __nv_bfloat16, 1>(a, (cudaStream_t)stream);
 }
@@ -829,6 +840,7 @@ extern "C" int emap_set_option(const char* name, int value) {
   if (!strcmp(name, "dw_lbo")) return emap::dw::set_desc_strides(0, value);      // bring-up of mlp_dw.cu's descriptors
   if (!strcmp(name, "dw_sbo")) return emap::dw::set_desc_strides(1, value);
   if (!strcmp(name, "k1_dot")) { emap::g_k1_dot = (value != 0); return 0; }
+  if (!strcmp(name, "rev_rolled")) return emap::rev::set_rolled(value);
   if (!strcmp(name, "rg_flags")) return emap::rg::set_flags(value);   // K1r experiment switches (mlp_rg.cu)
   return set_error("unknown option '%s'", name);
 }

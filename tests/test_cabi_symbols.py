@@ -42,7 +42,7 @@ def test_host_only_entry_points():
     bad = C.NetDesc(11, 0, 1.0, 0)
     assert L.emap_flat_param_count(ctypes.byref(bad)) == 0
     assert b"multires" in L.emap_last_error()
-    assert L.emap_set_option(b"cluster", 3) != 0
+    assert L.emap_set_option(b"cluster", 4) != 0
     assert L.emap_set_option(b"cluster", 1) == 0
 
 

@@ -91,20 +91,21 @@ def test_ray_addressing_and_ragged_sizes():
     assert maxdiff(gr.cpu(), refg) <= 5e-5 * max(1.0, float(refg.abs().max()))
 
 
-@pytest.mark.parametrize("cl", [2, -2])
+@pytest.mark.parametrize("cl", [2, -2, 3])
 def test_cluster_weight_stream_variants(golden, cl):
     """cluster=2: multicast pairs (cta_group::1); cluster=-2: CTA pairs driven by one cta_group::2 issuer
-    (M=256 MMAs, each CTA stages half of every weight operand).  Both must be bit-identical to the default."""
+    (M=256 MMAs, each CTA stages half of every weight operand); cluster=3: width 1 with the issuer's layer loop
+    rolled.  All must be bit-identical to the default."""
     from emap_b200 import ops, _cabi as C
     g = golden("mlp_pert")
     net, _ = _net(True)
     x = g["x"].cuda().repeat(40, 1)           # 15360 points -> 120 / 480 tiles
     C.set_option("cluster", 1)
-    u1, g1 = ops.udf_forward_grad(net, C.PREC_FP32X3, pts=x)
+    u1, g1 = ops.udf_forward_grad(net, C.PREC_FP32X3, pts=x, mode="forward")
     f1, _ = ops.udf_forward(net, C.PREC_HALF, pts=x)
     try:
         C.set_option("cluster", cl)
-        u2, g2 = ops.udf_forward_grad(net, C.PREC_FP32X3, pts=x)
+        u2, g2 = ops.udf_forward_grad(net, C.PREC_FP32X3, pts=x, mode="forward")
         f2, _ = ops.udf_forward(net, C.PREC_HALF, pts=x)
         torch.cuda.synchronize()
     finally:

@@ -108,13 +108,13 @@ def test_split_tail_and_static_schedule_variants_are_bit_identical(golden):
     net, _ = _net(True)
     x = g["x"].cuda().repeat(60, 1)           # 23,040 points -> 180 tiles: two tiles on some CTAs
     u1, g1 = ops.udf_forward_grad(net, C.PREC_FP32X3, pts=x, mode="reverse")
-    for flags in (9, 0, 1, 12, 4):
+    for flags in (9, 0, 1, 8, 4, 28):
         try:
             C.set_option("rg_flags", flags)
             u2, g2 = ops.udf_forward_grad(net, C.PREC_FP32X3, pts=x, mode="reverse")
             torch.cuda.synchronize()
         finally:
-            C.set_option("rg_flags", 8)
+            C.set_option("rg_flags", 12)
         assert torch.equal(u1, u2) and torch.equal(g1, g2), flags
 
 
@@ -280,3 +280,31 @@ def test_k1_dot_output_layer(golden, prec, tol):
     ref2 = O.udf_forward(p, pts)[0][:, 0]
     assert maxdiff(u2.cpu(), ref2) <= tol * max(1.0, float(ref2.abs().max()))
     assert maxdiff(pe.cpu(), g["pe"]) <= 5e-7
+
+
+def test_rolled_issuer_variants_of_the_backward_are_bit_identical(golden):
+    """A/B switches that only change code layout (rolled MMA-issuer loops: cluster=3 for the K1 family incl. the
+    tangent forward, rev_rolled=1 for the reverse sweep, rg_flags bit 4 for K1r's reverse epilogue) must not change
+    a single bit of the parameter gradients."""
+    from emap_b200 import _cabi as C
+    from tests.test_gpu_render import build
+    g = golden("mlp_pert")
+
+    def grads():
+        net, var, beta, r = build(10, True, n_samples=64, n_importance=0, up_sample_steps=5)
+        x = g["x"].cuda().repeat(20, 1)
+        y, _ = net(x)
+        gg = net.gradient(x.clone()).squeeze(1)
+        loss = (g["cu"].cuda().repeat(20, 1) * y).sum() + (g["cg"].cuda().repeat(20, 1) * gg).sum()
+        loss.backward()
+        torch.cuda.synchronize()
+        return [p.grad.clone() for p in net.parameters()]
+
+    ref = grads()
+    try:
+        C.set_option("cluster", 3); C.set_option("rev_rolled", 1); C.set_option("rg_flags", 28)
+        got = grads()
+    finally:
+        C.set_option("cluster", 1); C.set_option("rev_rolled", 0); C.set_option("rg_flags", 12)
+    for a, b in zip(ref, got):
+        assert torch.equal(a, b)
