@@ -668,7 +668,7 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_rgrad_kernel(const Args args)
   }
 }
 
-static int g_flags = kFlagDynamic | kFlagRolled;   // emap_set_option("rg_flags", bits); both measured (B200): dynamic tiles 5.24 vs 6.05 ms, rolled issuer 6.35 vs 7.26 ms with the training stash
+static int g_flags = kFlagDynamic | kFlagRolled | kFlagRolledEpi;   // (28) emap_set_option("rg_flags", bits); both measured (B200): dynamic tiles 5.24 vs 6.05 ms, rolled issuer 6.35 vs 7.26 ms with the training stash
 int set_flags(int v) { g_flags = v; return 0; }
 
 template <int NTERMS, typename T, int ROLL>

@@ -40,11 +40,12 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_kernel(const MlpArgs args) {
   // CL = 1|2|4: weight-stream multicast width (cta_group::1).  CL = -2: PAIR mode -- clusters of two CTAs
   // driven by ONE MMA issuer with tcgen05.mma.cta_group::2 (M = 256: each CTA's 128-row tile, N = 256 split
   // as 128 weight rows per CTA): every SM stages and reads only half of each weight operand.
-  // CL_ = 3: CL = 1 with the issuer's layer loop ROLLED (schedule computed at run time): the unrolled issuer is
-  // ~half of the kernel's SASS and is executed by one thread -- it only costs instruction-cache capacity that
-  // the 16 epilogue warps need (K1r: 7.26 -> 6.35 ms in training mode from this alone, profiles/r02_*).
-  constexpr bool ROLLI = (CL_ == 3);
-  constexpr int CL = ROLLI ? 1 : CL_;
+  // CL_ = 1 (default) runs the issuer's layer loop ROLLED (schedule computed at run time); CL_ = 3 is the same
+  // kernel with the loop unrolled (the round-1 form, kept as A/B switch): the unrolled issuer is ~half of the
+  // kernel's SASS and is executed by one thread -- it only costs instruction-cache capacity that the 16 epilogue
+  // warps need (measured: K1 forward 2.70 vs 3.04 ms, K1r 6.35 vs 7.26 ms in training mode; profiles/r02_*).
+  constexpr bool ROLLI = (CL_ == 1);
+  constexpr int CL = (CL_ == 3) ? 1 : CL_;
   constexpr bool PAIR = (CL == -2);
   constexpr int CLW = PAIR ? 2 : CL;             // cluster width
   using Plan = SmemPlan<NTERMS, MODE, PAIR>;
@@ -652,7 +653,7 @@ int dbg_iter() { return g_dbg_iter; }
 // ---------------------------------------------------------------------------------------------
 template <int NTERMS, int MODE, typename T, int CL_>
 static int launch(const MlpArgs& a_in, cudaStream_t stream) {
-  constexpr int CL = (CL_ == 3) ? 1 : CL_;       // 3 = width 1 with the rolled issuer loop
+  constexpr int CL = (CL_ == 3) ? 1 : CL_;       // 3 = width 1 with the UNROLLED issuer loop (A/B switch)
   constexpr bool PAIR = (CL == -2);
   constexpr int CLW = PAIR ? 2 : CL;
   using Plan = SmemPlan<NTERMS, MODE, PAIR>;
@@ -731,7 +732,7 @@ static int check_points(const float* pts, const float* rays_o, const float* rays
 
 int set_cluster_width(int v) {
   if (v != 1 && v != 2 && v != 3 && v != -2)
-    return set_error("cluster must be 1, 2 (multicast), 3 (1 with the rolled issuer loop) or -2 (cta_group::2 pairs)");
+    return set_error("cluster must be 1, 2 (multicast), 3 (1 with the unrolled issuer loop) or -2 (cta_group::2 pairs)");
   g_cluster = v;
   return 0;
 }

@@ -95,7 +95,7 @@ def test_ray_addressing_and_ragged_sizes():
 def test_cluster_weight_stream_variants(golden, cl):
     """cluster=2: multicast pairs (cta_group::1); cluster=-2: CTA pairs driven by one cta_group::2 issuer
     (M=256 MMAs, each CTA stages half of every weight operand); cluster=3: width 1 with the issuer's layer loop
-    rolled.  All must be bit-identical to the default."""
+    unrolled (the round-1 form; the default rolls it).  All must be bit-identical to the default."""
     from emap_b200 import ops, _cabi as C
     g = golden("mlp_pert")
     net, _ = _net(True)

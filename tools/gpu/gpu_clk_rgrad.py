@@ -42,6 +42,6 @@ for flags in (8,):
               f"(max/min {cyc.max() / cyc.min():.3f}); slowest blocks (block, smid, Mclk): "
               f"{[(int(i), int(per[i, 1]), round(float(cyc[i]) / 1e6, 2)) for i in order[-6:]]}; fastest: "
               f"{[(int(i), int(per[i, 1]), round(float(cyc[i]) / 1e6, 2)) for i in order[:6]]}", flush=True)
-C.set_option("rg_flags", 12)
+C.set_option("rg_flags", 28)
 C.set_option("dbg_iter", 1)
 C.lib().emap_debug_set_clk_buffer(None)

@@ -61,4 +61,4 @@ for flags in (0, 1, 2):
         print(f"rg_flags={flags}: launch failed: {e}", flush=True)
         sys.exit(1)
     finally:
-        C.set_option("rg_flags", 12)
+        C.set_option("rg_flags", 28)

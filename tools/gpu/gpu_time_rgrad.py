@@ -46,11 +46,11 @@ for prec, name in ((3, "fp32x3"), (1, "fp16")):
     tr = t(lambda: ops.udf_forward_grad(net, prec, pts=x, mode="reverse"))
     C.set_option("rg_flags", 1)
     tr1 = t(lambda: ops.udf_forward_grad(net, prec, pts=x, mode="reverse"))
-    C.set_option("rg_flags", 12)
+    C.set_option("rg_flags", 28)
     print(f"{name}: K1r with the N-split tail (rg_flags=1): {tr1:.2f} ms", flush=True)
     C.set_option("rg_flags", 2)
     tr2 = t(lambda: ops.udf_forward_grad(net, prec, pts=x, mode="reverse"))
-    C.set_option("rg_flags", 12)
+    C.set_option("rg_flags", 28)
     print(f"{name}: K1r with the persisting-L2 window on the sigma scratch (rg_flags=2): {tr2:.2f} ms", flush=True)
     for fl in (0, 10, 12, 4):
         C.set_option("rg_flags", fl)
@@ -58,7 +58,7 @@ for prec, name in ((3, "fp32x3"), (1, "fp16")):
         torch.cuda.synchronize()
         same = bool(torch.equal(ud, ur) and torch.equal(gd, gr))
         trd = t(lambda: ops.udf_forward_grad(net, prec, pts=x, mode="reverse"))
-        C.set_option("rg_flags", 12)
+        C.set_option("rg_flags", 28)
         print(f"{name}: K1r rg_flags={fl} (default 8 = dynamic tiles; 0 = static round robin, 2 = persisting L2, 4 = rolled issuer loop): {trd:.2f} ms, bit-identical to the default: {same}", flush=True)
     flop = 2 * 918016 * P
     print(f"{name}: K1g {tf:.2f} ms ({flop / tf / 1e9:.0f} TF/s alg)   K1r {tr:.2f} ms ({flop / tr / 1e9:.0f} TF/s alg)   "

@@ -44,7 +44,7 @@ W, _, _ = ops._weff_views(net)
 res = {}
 for dyn in (1, 0):
     C.set_option("dynamic_tiles", dyn)
-    C.set_option("rg_flags", 12 if dyn else 4)
+    C.set_option("rg_flags", 28 if dyn else 20)
     tag = "dynamic" if dyn else "static "
     fwd = t(lambda: ops.udf_forward(net, 3, pts=x))
     u0, _ = ops.udf_forward(net, 3, pts=x)
@@ -64,22 +64,23 @@ for dyn in (1, 0):
     print(f"{tag}: K1 forward {fwd:.2f}  K1r {k1r:.2f}  K1r+stash {k1rs:.2f}  tangent fwd {tan:.2f}  top {top:.2f}  "
           f"reverse sweep {rev:.2f}  weight grads {dw:.2f}  (dual forward {dual:.2f})  ms", flush=True)
 C.set_option("dynamic_tiles", 1)
-C.set_option("rg_flags", 12)
+C.set_option("rg_flags", 28)
 print("bit-identical static vs dynamic:", [bool(torch.equal(a, b)) for a, b in zip(res[0], res[1])])
 # code-layout variants (rolled MMA-issuer loops), two interleaved rounds against order effects.
-# rg_flags: 8 = dynamic tiles, +4 = rolled issuer (default 12), +16 = rolled reverse-epilogue chunk loop, +2 = persisting L2
+# rg_flags: 8 = dynamic tiles, +4 = rolled issuer, +16 = rolled reverse-epilogue chunk loop (default 28), +2 = persisting L2;
+# cluster 3 / rev_rolled 0 = the unrolled issuer loops of round 1
 for rnd in range(2):
     line = []
-    for fl in (12, 8, 28, 14):
+    for fl in (28, 12, 8, 30):
         C.set_option("rg_flags", fl)
         line.append(f"flags {fl}: {t(lambda: ops.udf_forward_grad(net, 3, pts=x, mode='reverse', stash=stash), reps=6):.2f}")
-    C.set_option("rg_flags", 12)
+    C.set_option("rg_flags", 28)
     print(f"K1r+stash round {rnd}: " + "   ".join(line) + "  ms", flush=True)
     line = []
-    for fl in (12, 8, 28):
+    for fl in (28, 12, 8):
         C.set_option("rg_flags", fl)
         line.append(f"flags {fl}: {t(lambda: ops.udf_forward_grad(net, 3, pts=x, mode='reverse'), reps=6):.2f}")
-    C.set_option("rg_flags", 12)
+    C.set_option("rg_flags", 28)
     print(f"K1r (inference) round {rnd}: " + "   ".join(line) + "  ms", flush=True)
     line = []
     for cl in (1, 3):
@@ -93,5 +94,5 @@ for rnd in range(2):
         C.set_option("rev_rolled", rr)
         rv = t(lambda: L.emap_bwd_reverse_sweep(desc, C.ptr(net.packed), C.ptr(coef), C.ptr(stash[1]), C.ptr(st_a), P, st), reps=6)
         line.append(f"rev_rolled {rr}: reverse sweep {rv:.2f}")
-    C.set_option("rev_rolled", 0)
+    C.set_option("rev_rolled", 1)
     print(f"issuer variants round {rnd}: " + "   ".join(line) + "  ms", flush=True)
