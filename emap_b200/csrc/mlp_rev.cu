@@ -44,6 +44,7 @@ struct Args {
   long long P;
   int num_tiles, iters;
   unsigned int* tile_counter;   // dynamic tile scheduling (as in mlp_rg.cu / mlp_tc.cu); NULL = static round robin
+  int no_prefetch;              // A/B switch: skip the L2 prefetch of the next stage's stash rows
 };
 
 __device__ __forceinline__ uint32_t pack2h(float a, float b) {
@@ -183,6 +184,8 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_rev_kernel(const Args args) {
           const __half* u_pre = args.st_u + (size_t)lt * 2 * P * 256 + rowg * 256 + sub * 16;
 #pragma unroll
           for (int c4 = 0; c4 < 4; ++c4) ldg256(u_pre + c4 * 64, uw_all[c4]);
+          // the same row of the next stage's plane (layer lt-1) goes into L2 now: one 128-byte line per thread
+          if (lt >= 1 && !args.no_prefetch) prefetch_l2(args.st_u + (size_t)(lt - 1) * 2 * P * 256 + rowg * 256 + sub * 64);
         }
         if (j >= 0) {
           mbar_wait(&acc_full[buf], ((uint32_t)iter * (buf ? 3u : 4u) + (uint32_t)(j >> 1)) & 1, 500 + buf, j);
@@ -219,43 +222,52 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_rev_kernel(const Args args) {
           // columns, 4 more return the packed results to the row that owns them.
           uint32_t outp[8];
           const uint32_t (&uw)[8] = uw_all[chunk];
-          float oacc[8];
-          uint32_t ou[4];
+          // (selects are kept to the exchange itself: what is sent, and which of {kept, received} is the value /
+          //  tangent row -- the arithmetic below is the same instruction stream for both lanes of a pair)
+          float eta[8], etad[8];                                   // adjoints of the value / tangent row, my 8 columns
 #pragma unroll
-          for (int k = 0; k < 8; ++k) oacc[k] = __shfl_xor_sync(0xffffffffu, t2 ? own[k] : own[8 + k], 1);
-#pragma unroll
-          for (int w = 0; w < 4; ++w) ou[w] = __shfl_xor_sync(0xffffffffu, t2 ? uw[w] : uw[4 + w], 1);
-          uint32_t mine_p[4], send_p[4];
+          for (int k = 0; k < 8; ++k) {
+            const float got = __shfl_xor_sync(0xffffffffu, t2 ? own[k] : own[8 + k], 1);
+            const float kept = t2 ? own[8 + k] : own[k];
+            eta[k] = t2 ? got : kept;
+            etad[k] = t2 ? kept : got;
+          }
+          uint32_t hvw[4], hdw[4];                                 // h (value row) / hdot (tangent row), my 8 columns
 #pragma unroll
           for (int w = 0; w < 4; ++w) {
-            const uint32_t um = t2 ? uw[4 + w] : uw[w];            // own row, my columns
-            const float2 m2 = __half22float2(*reinterpret_cast<const __half2*>(&um));
-            const float2 o2 = __half22float2(*reinterpret_cast<const __half2*>(&ou[w]));
-            const float hv[2] = {t2 ? o2.x : m2.x, t2 ? o2.y : m2.y};   // h of the value row
-            const float hd[2] = {t2 ? m2.x : o2.x, t2 ? m2.y : o2.y};   // hdot of the tangent row
+            const uint32_t got = __shfl_xor_sync(0xffffffffu, t2 ? uw[w] : uw[4 + w], 1);
+            const uint32_t kept = t2 ? uw[4 + w] : uw[w];
+            hvw[w] = t2 ? got : kept;
+            hdw[w] = t2 ? kept : got;
+          }
+          uint32_t pa[4], pd[4];                                   // packed alpha / alphadot of my 8 columns
+          // only layer 3 has fewer than 256 outputs (its last columns are the skip input's PE part)
+          const bool partial = (ncols != 256);                     // uniform over the CTA
+          const int nlive = ncols - (col0 + t2 * 8);               // live columns of my half (>= 8: all)
+#pragma unroll
+          for (int w = 0; w < 4; ++w) {
+            const float2 hv = __half22float2(*reinterpret_cast<const __half2*>(&hvw[w]));
+            const float2 hd = __half22float2(*reinterpret_cast<const __half2*>(&hdw[w]));
+            const float hve[2] = {hv.x, hv.y}, hde[2] = {hd.x, hd.y};
             float al[2], ad[2];
 #pragma unroll
             for (int e = 0; e < 2; ++e) {
               const int k = 2 * w + e;                             // column inside my half
-              const float mine = t2 ? own[8 + k] : own[k];
-              const float eta = t2 ? oacc[k] : mine;               // adjoint of the value row
-              const float etad = t2 ? mine : oacc[k];              // adjoint of the tangent row
               // sigma = softplus'(a) = 1 - exp(-100 h);  adot * softplus''(a) = 100 * hdot * (1 - sigma)
-              const float one_m_s = __expf(-kSoftplusBeta * hv[e]);
+              const float one_m_s = __expf(-kSoftplusBeta * hve[e]);
               const float sg = 1.0f - one_m_s;
-              const bool live = (col0 + t2 * 8 + k < ncols) && ok;
-              al[e] = live ? fmaf(etad, kSoftplusBeta * hd[e] * one_m_s, eta * sg) : 0.f;   // alpha
-              ad[e] = live ? etad * sg : 0.f;                                                // alphadot
+              al[e] = fmaf(etad[k], kSoftplusBeta * hde[e] * one_m_s, eta[k] * sg);       // alpha
+              ad[e] = etad[k] * sg;                                                       // alphadot
+              if (partial && k >= nlive) { al[e] = 0.f; ad[e] = 0.f; }
             }
-            const uint32_t pa = pack2h(al[0], al[1]), pd = pack2h(ad[0], ad[1]);
-            mine_p[w] = t2 ? pd : pa;                              // stays in my row
-            send_p[w] = t2 ? pa : pd;                              // belongs to the partner's row
+            pa[w] = pack2h(al[0], al[1]);
+            pd[w] = pack2h(ad[0], ad[1]);
           }
 #pragma unroll
           for (int w = 0; w < 4; ++w) {
-            const uint32_t got = __shfl_xor_sync(0xffffffffu, send_p[w], 1);
-            outp[w] = t2 ? got : mine_p[w];                        // columns 0-7 of my row
-            outp[4 + w] = t2 ? mine_p[w] : got;                    // columns 8-15
+            const uint32_t got = __shfl_xor_sync(0xffffffffu, t2 ? pa[w] : pd[w], 1);   // the partner row's share
+            outp[w] = t2 ? got : pa[w];                            // columns 0-7 of my row
+            outp[4 + w] = t2 ? pd[w] : got;                        // columns 8-15
           }
           if (lt >= 1) {
 #pragma unroll
@@ -287,7 +299,9 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_rev_kernel(const Args args) {
 
 static int g_dynamic = 1;
 int set_dynamic(int v) { g_dynamic = v; return 0; }
-static int g_rolled = 1;         // emap_set_option("rev_rolled", 0): the unrolled issuer loop (A/B switch; 7.1 vs 7.2 ms)
+// emap_set_option("rev_rolled", bits): bit 0 = rolled issuer loop (default; 0 = the unrolled round-1 form, 7.2 vs
+// 7.1 ms), bit 1 = no L2 prefetch of the next stage's stash rows (A/B switch)
+static int g_rolled = 1;
 int set_rolled(int v) { g_rolled = v; return 0; }
 
 }  // namespace rev
@@ -309,13 +323,14 @@ extern "C" int emap_bwd_reverse_sweep(const emap_net_desc* net, const void* pack
   if (tiles < grid) grid = (int)tiles;
   a.iters = (int)((tiles + grid - 1) / grid);
   a.tile_counter = rev::g_dynamic ? tile_counter((cudaStream_t)stream) : nullptr;
+  a.no_prefetch = (rev::g_rolled & 2) ? 1 : 0;
   static bool attr_done = false;
   if (!attr_done) {
     EMAP_CUDA(cudaFuncSetAttribute(rev::mlp_rev_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, rev::Smem::total));
     EMAP_CUDA(cudaFuncSetAttribute(rev::mlp_rev_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, rev::Smem::total));
     attr_done = true;
   }
-  if (rev::g_rolled) rev::mlp_rev_kernel<true><<<grid, rev::kThreads, rev::Smem::total, (cudaStream_t)stream>>>(a);
+  if (rev::g_rolled & 1) rev::mlp_rev_kernel<true><<<grid, rev::kThreads, rev::Smem::total, (cudaStream_t)stream>>>(a);
   else rev::mlp_rev_kernel<false><<<grid, rev::kThreads, rev::Smem::total, (cudaStream_t)stream>>>(a);
   EMAP_CUDA(cudaGetLastError());
   return 0;
