@@ -381,10 +381,6 @@ __device__ __forceinline__ void stg256(void* p, const uint32_t (&v)[8]) {
                "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7])
                : "memory");
 }
-// pull one 128-byte line into L2 ahead of its use (no register, no scoreboard)
-__device__ __forceinline__ void prefetch_l2(const void* p) {
-  asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
-}
 // streaming variant: written once, read by a later kernel -- do not let it push the L2-resident scratch out
 __device__ __forceinline__ void stg256_cs(void* p, const uint32_t (&v)[8]) {
   asm volatile("st.global.cs.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p), "r"(v[0]), "r"(v[1]), "r"(v[2]),

@@ -44,7 +44,6 @@ struct Args {
   long long P;
   int num_tiles, iters;
   unsigned int* tile_counter;   // dynamic tile scheduling (as in mlp_rg.cu / mlp_tc.cu); NULL = static round robin
-  int no_prefetch;              // A/B switch: skip the L2 prefetch of the next stage's stash rows
 };
 
 __device__ __forceinline__ uint32_t pack2h(float a, float b) {
@@ -184,8 +183,7 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_rev_kernel(const Args args) {
           const __half* u_pre = args.st_u + (size_t)lt * 2 * P * 256 + rowg * 256 + sub * 16;
 #pragma unroll
           for (int c4 = 0; c4 < 4; ++c4) ldg256(u_pre + c4 * 64, uw_all[c4]);
-          // the same row of the next stage's plane (layer lt-1) goes into L2 now: one 128-byte line per thread
-          if (lt >= 1 && !args.no_prefetch) prefetch_l2(args.st_u + (size_t)(lt - 1) * 2 * P * 256 + rowg * 256 + sub * 64);
+          // (an L2 prefetch of the next stage's rows from here was measured: 7.5 vs 7.15 ms -- slower, removed)
         }
         if (j >= 0) {
           mbar_wait(&acc_full[buf], ((uint32_t)iter * (buf ? 3u : 4u) + (uint32_t)(j >> 1)) & 1, 500 + buf, j);
@@ -299,8 +297,7 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_rev_kernel(const Args args) {
 
 static int g_dynamic = 1;
 int set_dynamic(int v) { g_dynamic = v; return 0; }
-// emap_set_option("rev_rolled", bits): bit 0 = rolled issuer loop (default; 0 = the unrolled round-1 form, 7.2 vs
-// 7.1 ms), bit 1 = no L2 prefetch of the next stage's stash rows (A/B switch)
+// emap_set_option("rev_rolled", 0): the unrolled issuer loop of round 1 (A/B switch; 7.2 vs 7.1 ms rolled)
 static int g_rolled = 1;
 int set_rolled(int v) { g_rolled = v; return 0; }
 
@@ -323,7 +320,6 @@ extern "C" int emap_bwd_reverse_sweep(const emap_net_desc* net, const void* pack
   if (tiles < grid) grid = (int)tiles;
   a.iters = (int)((tiles + grid - 1) / grid);
   a.tile_counter = rev::g_dynamic ? tile_counter((cudaStream_t)stream) : nullptr;
-  a.no_prefetch = (rev::g_rolled & 2) ? 1 : 0;
   static bool attr_done = false;
   if (!attr_done) {
     EMAP_CUDA(cudaFuncSetAttribute(rev::mlp_rev_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, rev::Smem::total));

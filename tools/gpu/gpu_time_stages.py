@@ -90,14 +90,9 @@ for rnd in range(2):
                                                   C.ptr(scales), C.ptr(stash[0]), C.ptr(stash[1]), st), reps=6)
         line.append(f"cluster {cl}: K1 forward {f:.2f}  tangent fwd {tn:.2f}")
     C.set_option("cluster", 1)
-    C.set_option("dbg", 16)
-    tn = t(lambda: L.emap_bwd_tangent_forward(desc, C.ptr(net.packed), C.ptr(x), None, None, None, 0, P, C.ptr(gbar),
-                                              C.ptr(scales), C.ptr(stash[0]), C.ptr(stash[1]), st), reps=6)
-    C.set_option("dbg", 0)
-    line.append(f"tangent fwd without the L2 prefetch {tn:.2f}")
-    for rr in (0, 1, 3):
+    for rr in (0, 1):
         C.set_option("rev_rolled", rr)
         rv = t(lambda: L.emap_bwd_reverse_sweep(desc, C.ptr(net.packed), C.ptr(coef), C.ptr(stash[1]), C.ptr(st_a), P, st), reps=6)
-        line.append(f"rev_rolled {rr}{' (no prefetch)' if rr & 2 else ''}: reverse sweep {rv:.2f}")
+        line.append(f"rev_rolled {rr}: reverse sweep {rv:.2f}")
     C.set_option("rev_rolled", 1)
     print(f"issuer variants round {rnd}: " + "   ".join(line) + "  ms", flush=True)
