@@ -274,12 +274,14 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_rev_kernel(const Args args) {
                                         (uint32_t)((((sub * 2 + g) ^ (row & 7)) & 7) << 4)) =
                   make_uint4(outp[g * 4], outp[g * 4 + 1], outp[g * 4 + 2], outp[g * 4 + 3]);
           }
-          if (ok) stg256(a_out + col0, outp);
           if (lt >= 1) {
             fence_proxy_async_smem();
             __syncwarp();
             if (lane == 0) mbar_arrive(&a_ready[chunk]);
           }
+          // the stash row goes out AFTER the hand-off: a global store in front of the fence (MEMBAR.ALL.CTA +
+          // FENCE.VIEW.ASYNC) makes every hand-off wait for an L2 round trip
+          if (ok) stg256(a_out + col0, outp);
         }
         if (j >= 0) {
           tc_fence_before();

@@ -422,6 +422,12 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_kernel(const MlpArgs args) {
             for (int k = 0; k < 16; ++k)
               args.dbg_acc[((size_t)l * 128 + row) * 256 + col0 + k] = __uint_as_float(r[k]) * kInvWeightScale;
           }
+          // MODE 2 / 3: this thread's 32 bytes of the stash row.  Stored AFTER the chunk's hand-off: the
+          // fence.proxy.async in front of the hand-off compiles to MEMBAR.ALL.CTA + FENCE.VIEW.ASYNC, and a global
+          // store issued before it makes every hand-off wait for an L2 round trip (ncu: 8 % of the tangent
+          // forward's samples sat on that fence)
+          uint32_t pu[8];
+          __half* st_dst = nullptr;
           if (args.dbg_flags & 4) {
             // timing experiment: no epilogue math / stores
           } else if (MODE == 2) {
@@ -451,7 +457,6 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_kernel(const MlpArgs args) {
               outv[j] = t2 ? y * ad_lo : hm[j];
               outv[8 + j] = t2 ? sm[j] * ad_hi : y;
             }
-            uint32_t pu[8];                              // 16 columns = 32 B per stash row
 #pragma unroll
             for (int g = 0; g < 2; ++g) {
               float v8[8];
@@ -459,18 +464,15 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_kernel(const MlpArgs args) {
               for (int j = 0; j < 8; ++j) v8[j] = outv[g * 8 + j];
               if (l < 7) store_group<NTERMS, T>(dst_hi, dst_lo, row, sub * 2 + g, v8);
 #pragma unroll
-              for (int j = 0; j < 4; ++j) pu[g * 4 + j] = Elem<__half>::pack2(v8[2 * j], v8[2 * j + 1]);
+              for (int j = 0; j < 4; ++j) pu[g * 4 + j] = Elem<__half>::pack2(v8[2 * j], v8[2 * j + 1]);   // 16 columns = 32 B per stash row
             }
-            if (okp && !(args.dbg_flags & 8)) {
-              const size_t plane_u = (size_t)l * 2 * (size_t)args.P * 256;
-              stg256(args.st_u + plane_u + (size_t)rowg * 256 + col0, pu);
-            }
+            if (okp && !(args.dbg_flags & 8))
+              st_dst = args.st_u + (size_t)l * 2 * (size_t)args.P * 256 + (size_t)rowg * 256 + col0;
           } else if (MODE == 3) {
             // tangent rows only: hdot_{l+1} = softplus'(a_l) . adot_l with softplus'(a_l) = 1 - exp(-100 h_{l+1})
             // recovered from the value row of the stash (as the reverse sweep does); next layer's A tile +
             // the tangent row of the stash.
             const bool okp = (tile < args.num_tiles) && (pt < args.P);
-            uint32_t pu[8];
 #pragma unroll
             for (int g = 0; g < 2; ++g) {
               float v8[8];
@@ -485,10 +487,7 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_kernel(const MlpArgs args) {
 #pragma unroll
               for (int j = 0; j < 4; ++j) pu[g * 4 + j] = Elem<__half>::pack2(v8[2 * j], v8[2 * j + 1]);
             }
-            if (okp) {
-              const size_t plane_u = (size_t)l * 2 * (size_t)args.P * 256;
-              stg256(args.st_u + plane_u + ((size_t)args.P + (size_t)pt) * 256 + col0, pu);
-            }
+            if (okp) st_dst = args.st_u + (size_t)l * 2 * (size_t)args.P * 256 + ((size_t)args.P + (size_t)pt) * 256 + col0;
           } else if (MODE == 0 || MODE == 5) {
 #pragma unroll
             for (int g = 0; g < 2; ++g) {
@@ -573,6 +572,7 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_kernel(const MlpArgs args) {
           __syncwarp();
           if (lane == 0 && !(MODE >= 2 && l == 7)) arrive_issuer(&a_ready[chunk]);
           if (stamp && chunk < 2) args.dbg_clk[l * 8 + 4 + 3 * chunk] = clock64();
+          if ((MODE == 2 || MODE == 3) && st_dst) stg256(st_dst, pu);
         }
         tc_fence_before();
         __syncwarp();
