@@ -44,6 +44,7 @@ struct Args {
   long long P;
   int num_tiles, iters;
   unsigned int* tile_counter;   // dynamic tile scheduling (as in mlp_rg.cu / mlp_tc.cu); NULL = static round robin
+  int dbg;                      // timing experiments (rev_rolled bits 1, 2): 1 = no stash stores, 2 = no stash loads
 };
 
 __device__ __forceinline__ uint32_t pack2h(float a, float b) {
@@ -181,8 +182,15 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_rev_kernel(const Args args) {
         uint32_t uw_all[4][8];
         {
           const __half* u_pre = args.st_u + (size_t)lt * 2 * P * 256 + rowg * 256 + sub * 16;
+          if (args.dbg & 2) {
 #pragma unroll
-          for (int c4 = 0; c4 < 4; ++c4) ldg256(u_pre + c4 * 64, uw_all[c4]);
+            for (int c4 = 0; c4 < 4; ++c4)
+#pragma unroll
+              for (int k = 0; k < 8; ++k) uw_all[c4][k] = 0x1c001c00u;
+          } else {
+#pragma unroll
+            for (int c4 = 0; c4 < 4; ++c4) ldg256(u_pre + c4 * 64, uw_all[c4]);
+          }
           // (an L2 prefetch of the next stage's rows from here was measured: 7.5 vs 7.15 ms -- slower, removed)
         }
         if (j >= 0) {
@@ -281,7 +289,7 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_rev_kernel(const Args args) {
           }
           // the stash row goes out AFTER the hand-off: a global store in front of the fence (MEMBAR.ALL.CTA +
           // FENCE.VIEW.ASYNC) makes every hand-off wait for an L2 round trip
-          if (ok) stg256(a_out + col0, outp);
+          if (ok && !(args.dbg & 1)) stg256(a_out + col0, outp);
         }
         if (j >= 0) {
           tc_fence_before();
@@ -297,8 +305,336 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_rev_kernel(const Args args) {
   if (warp == kMmaWarp) tmem_dealloc(tmem_base, 512);
 }
 
+// =====================================================================================================
+// Variant with both stashes staged through shared memory by the TMA engine ("rev_tma", the default).
+//
+// Measured on the kernel above (tools/gpu/gpu_probe_stash_io.py, 1 M points): 5.6 ms, of which 2.6 ms are its
+// global loads and stores -- exactly the HBM time of the 17.2 GB it moves, but ADDED to the 3.0 ms of the epilogue
+// instead of hidden under them: the 16 epilogue warps issue the stash reads of a stage, wait for them, and store
+// 32-byte pieces of rows from registers (4 warps per scheduler cannot cover a DRAM round trip).  Here a 19th warp
+// owns the global traffic: per 64-column chunk a 16 KiB slot of shared memory (value-row box | tangent-row box of
+// the tile's 64 points, 128-byte swizzle) is filled with U_{l+1} by two TMA loads a whole stage ahead of its use,
+// overwritten IN PLACE by the epilogue with A_l (each thread rewrites exactly the 16-byte units it read), written
+// to the A stash by two TMA stores, and refilled with the next stage's U as soon as the store has read it.
+// What the epilogue gains besides: no partner-row shuffles for the activations (a thread reads both rows of its
+// point from the slot), no result exchange (it writes alpha / alphadot of its 8 columns to both rows of the A tile
+// and both boxes of the slot itself), 32 fewer live registers.  Same arithmetic in the same order: bit-identical
+// to the kernel above (tests/test_gpu_rgrad.py).
+namespace t {
+
+constexpr int kIoWarp = kEpiWarps + 2;
+constexpr int kThreadsT = (kEpiWarps + 3) * 32;
+constexpr int kStagesT = 3;            // ring stages of 32 KiB (one less than above: the slots need the room)
+constexpr int kSlotBytes = 16384;      // [64 points x 64 columns] value rows | the same of the tangent rows
+
+struct Smem {
+  static constexpr int a = 0;                                   // [4 chunks][128 x 64] fp16 SW128 (MMA operand)
+  static constexpr int slots = a + 4 * kChunkBytes;             // [4 chunks][2][64 x 64] fp16 SW128 (TMA boxes)
+  static constexpr int ring = slots + 4 * kSlotBytes;
+  static constexpr int bars = ring + kStagesT * kRingStageBytes;
+  static constexpr int total = bars + 512 + 1024;
+};
+static_assert(Smem::total <= 232448, "shared memory plan exceeds 227 KiB");
+
+struct alignas(64) Maps { uint8_t u[128]; uint8_t a[128]; };     // two CUtensorMap (host.h: make_stash_map)
+
+__device__ __forceinline__ void tma_load_3d(void* smem_dst, const void* map, int c0, int c1, int c2, uint64_t* bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];" ::
+          "r"(smem_u32(smem_dst)),
+      "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
+__device__ __forceinline__ void tma_store_3d(const void* smem_src, const void* map, int c0, int c1, int c2) {
+  asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.tile.bulk_group [%0, {%2, %3, %4}], [%1];" ::
+                   "l"(reinterpret_cast<uint64_t>(map)),
+               "r"(smem_u32(smem_src)), "r"(c0), "r"(c1), "r"(c2)
+               : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read1() { asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+
+__global__ void __launch_bounds__(kThreadsT, 1) mlp_revt_kernel(const __grid_constant__ Maps maps, const Args args) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  const PackedHeader* hdr = reinterpret_cast<const PackedHeader*>(args.packed);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int out3 = (int)hdr->out_dim[kSkipLayer - 1];          // 256 - pe: valid columns of alpha_3
+
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Smem::bars);
+  uint64_t* full = bars;             // [3]  weight ring
+  uint64_t* empty = bars + 3;        // [3]
+  uint64_t* a_ready = bars + 6;      // [4]  A-tile chunk written (7 completions per tile)
+  uint64_t* acc_full = bars + 10;    // [2]
+  uint64_t* acc_empty = bars + 12;   // [2]
+  uint64_t* u_full = bars + 14;      // [4]  slot c holds U of the coming stage (8 completions per tile)
+  uint64_t* slot_done = bars + 18;   // [4]  slot c holds A of the finished stage (8 completions per tile)
+  uint64_t* sched_ready = bars + 22;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 23);
+  volatile int* sched_tile = reinterpret_cast<volatile int*>(bars + 24);
+
+  if (warp == kProducerWarp && lane == 0) {
+    for (int s = 0; s < kStagesT; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+    for (int c = 0; c < 4; ++c) {
+      mbar_init(&a_ready[c], kEpiWarps);
+      mbar_init(&u_full[c], 1);
+      mbar_init(&slot_done[c], kEpiWarps);
+    }
+    for (int b = 0; b < 2; ++b) { mbar_init(&acc_full[b], 1); mbar_init(&acc_empty[b], kEpiWarps); }
+    mbar_init(sched_ready, 1);
+    sched_tile[0] = (int)blockIdx.x;
+    fence_barrier_init();
+    mbar_arrive(sched_ready);             // completion 0: iteration 0 runs tile blockIdx.x
+  }
+  if (warp == kMmaWarp) { tmem_alloc(tmem_slot, 512); tmem_relinquish(); }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == kProducerWarp) {
+    const uint8_t* img = args.packed + hdr->reserved[2];
+    uint8_t* ring = smem + Smem::ring;
+    uint32_t stage = 0, round = 0;
+    for (int iter = 0;; ++iter) {
+      mbar_wait(sched_ready, (uint32_t)iter & 1, 560);
+      if (sched_tile[iter & 1] >= args.num_tiles) break;
+#pragma unroll 1
+      for (int i = 0; i < kRevParts; ++i) {
+        if (round > 0) mbar_wait(&empty[stage], (round - 1) & 1, 100 + (int)stage, i);
+        if (elect_one()) {
+          mbar_arrive_expect_tx(&full[stage], kRingStageBytes);
+          bulk_g2s(ring + stage * kRingStageBytes, img + (size_t)i * kRingStageBytes, kRingStageBytes, &full[stage]);
+        }
+        __syncwarp();
+        if (++stage == (uint32_t)kStagesT) { stage = 0; ++round; }
+      }
+    }
+  } else if (warp == kMmaWarp) {
+    const uint32_t a_addr = smem_u32(smem + Smem::a);
+    const uint32_t ring_addr = smem_u32(smem + Smem::ring);
+    const uint32_t idesc = make_idesc_f16(128, 256, 0);
+    uint32_t stage = 0, round = 0;
+    for (int iter = 0;; ++iter) {
+      mbar_wait(sched_ready, (uint32_t)iter & 1, 561);
+      if (sched_tile[iter & 1] >= args.num_tiles) break;
+#pragma unroll 1
+      for (int j = 0; j < kRevLayers; ++j) {
+        const int buf = j & 1;
+        {
+          const uint32_t started = (uint32_t)iter * (buf ? 3u : 4u) + (uint32_t)(j >> 1);
+          if (started > 0) mbar_wait(&acc_empty[buf], (started - 1) & 1, 200 + buf, j);
+        }
+        const uint32_t d = tmem_base + (uint32_t)buf * 256u;
+#pragma unroll
+        for (int kc = 0; kc < 4; ++kc) {
+          mbar_wait(&a_ready[kc], ((uint32_t)iter * 7u + (uint32_t)j) & 1, 300 + kc, j);
+          mbar_wait(&full[stage], round & 1, 400 + (int)stage, j * 4 + kc);
+          tc_fence_after();
+          const uint64_t adesc = make_sw128_kmajor_desc(a_addr + kc * kChunkBytes);
+          const uint64_t bdesc = make_sw128_kmajor_desc(ring_addr + stage * kRingStageBytes);
+          if (elect_one()) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+              umma_f16(d, adesc + 2 * k, bdesc + 2 * k, idesc, (kc == 0 && k == 0) ? 0u : 1u);
+            umma_commit(&empty[stage]);
+          }
+          __syncwarp();
+          if (++stage == (uint32_t)kStagesT) { stage = 0; ++round; }
+        }
+        if (elect_one()) umma_commit(&acc_full[buf]);
+        __syncwarp();
+      }
+    }
+  } else if (warp == kIoWarp) {
+    // ===================================== global I/O: one thread ======================================
+    if (lane == 0) {
+      uint8_t* slots = smem + Smem::slots;
+      auto load_u = [&](int c, int plane, int pt0) {            // U_{plane+1} rows of the tile, chunk c -> slot c
+        mbar_arrive_expect_tx(&u_full[c], kSlotBytes);
+        tma_load_3d(slots + c * kSlotBytes, maps.u, c * 64, pt0, plane * 2, &u_full[c]);
+        tma_load_3d(slots + c * kSlotBytes + kSlotBytes / 2, maps.u, c * 64, pt0, plane * 2 + 1, &u_full[c]);
+      };
+      for (int iter = 0;; ++iter) {
+        mbar_wait(sched_ready, (uint32_t)iter & 1, 563);
+        const int tile = sched_tile[iter & 1];
+        if (tile >= args.num_tiles) break;
+        const int pt0 = tile * 64;
+        if (iter == 0) {
+          for (int c = 0; c < 4; ++c) load_u(c, 7, pt0);
+        }
+        int next_tile = args.num_tiles;
+#pragma unroll 1
+        for (int s = 0; s < 8; ++s) {
+          const int lt = 7 - s;
+          // slot c after its store has read it: U of the next stage (same tile, plane lt-1) or of the next tile
+          auto refill = [&](int c) {
+            if (s < 7) load_u(c, lt - 1, pt0);
+            else if (next_tile < args.num_tiles) load_u(c, 7, next_tile * 64);
+          };
+          if (s == 7) {                                         // the next tile: published during stage 2 of this one
+            mbar_wait(sched_ready, (uint32_t)(iter + 1) & 1, 564);
+            next_tile = sched_tile[(iter + 1) & 1];
+          }
+#pragma unroll 1
+          for (int c = 0; c < 4; ++c) {
+            mbar_wait(&slot_done[c], ((uint32_t)iter * 8u + (uint32_t)s) & 1, 600 + c, s);
+            tma_store_3d(slots + c * kSlotBytes, maps.a, c * 64, pt0, lt * 2);
+            tma_store_3d(slots + c * kSlotBytes + kSlotBytes / 2, maps.a, c * 64, pt0, lt * 2 + 1);
+            bulk_commit();
+            if (c > 0) {                                        // one store stays in flight: refill the slot before
+              bulk_wait_read1();
+              refill(c - 1);
+            }
+          }
+          bulk_wait_read0();
+          refill(3);
+        }
+      }
+      bulk_wait0();                                             // every store has left before the CTA exits
+    }
+    __syncwarp();
+  } else {
+    // ===================================== epilogue warps ================================
+    const int q = warp & 3, sub = warp >> 2;
+    const int row = q * 32 + lane;
+    const int t2 = lane & 1;                                  // 0: alpha (value) row, 1: alphadot row
+    const int pi = row >> 1;                                  // point of the tile
+    const uint32_t lane_taddr = tmem_base + ((uint32_t)(q * 32) << 16);
+    uint8_t* A = smem + Smem::a;
+    uint8_t* slots = smem + Smem::slots;
+    const float* w8 = reinterpret_cast<const float*>(args.packed + hdr->weff_layer_off[8]);
+    const size_t P = (size_t)args.P;
+    // this thread's 16-byte unit (8 columns: unit 2 sub + t2 of the chunk's eight) in its point's row of a box,
+    // and in the two rows of its point in the A tile
+    const uint32_t unit = (uint32_t)(sub * 2 + t2);
+    const uint32_t box_off = (uint32_t)pi * 128u + ((unit ^ (uint32_t)(pi & 7)) << 4);
+    const uint32_t a_off_v = (uint32_t)(2 * pi) * 128u + ((unit ^ (uint32_t)((2 * pi) & 7)) << 4);
+    const uint32_t a_off_t = (uint32_t)(2 * pi + 1) * 128u + ((unit ^ (uint32_t)((2 * pi + 1) & 7)) << 4);
+
+    const bool scheduler = (warp == 0 && lane == 0);
+    for (int iter = 0;; ++iter) {
+      mbar_wait(sched_ready, (uint32_t)iter & 1, 562);
+      const long long tile = (long long)sched_tile[iter & 1];
+      if (tile >= args.num_tiles) break;
+      int next_tile = 0;
+      if (scheduler) {
+        const long long nt = args.tile_counter ? (long long)gridDim.x + (long long)atomicAdd(args.tile_counter, 1u)
+                                               : tile + (long long)gridDim.x;
+        next_tile = (nt < (long long)args.num_tiles) ? (int)nt : args.num_tiles;
+      }
+      const long long pt = tile * 64 + pi;
+      const bool ok = (pt < args.P);
+      const size_t pc = ok ? (size_t)pt : 0;
+      const float c_v = ok ? args.coef[pc] : 0.f;
+      const float c_t = ok ? args.coef[P + pc] : 0.f;
+
+#pragma unroll 1
+      for (int j = -1; j < kRevLayers; ++j) {
+        const int lt = 6 - j;                   // layer whose A_l = [alpha ; alphadot] this stage produces
+        const int buf = j & 1;
+        const uint32_t io_par = ((uint32_t)iter * 8u + (uint32_t)(j + 1)) & 1;
+        if (j >= 0) {
+          mbar_wait(&acc_full[buf], ((uint32_t)iter * (buf ? 3u : 4u) + (uint32_t)(j >> 1)) & 1, 500 + buf, j);
+          tc_fence_after();
+          if (j == 1 && scheduler) {        // all 16 warps are past stage 0 of this tile, i.e. past its schedule wait
+            sched_tile[(iter + 1) & 1] = next_tile;
+            mbar_arrive(sched_ready);
+          }
+        }
+        const int ncols = (lt == kSkipLayer - 1) ? out3 : 256;
+        const bool partial = (ncols != 256);                     // uniform over the CTA
+#pragma unroll 1
+        for (int chunk = 0; chunk < 4; ++chunk) {
+          const int col0 = chunk * 64 + sub * 16;
+          float own[16];
+          if (j >= 0) {
+            uint32_t r[16];
+            tmem_ld_32x32b_x16(lane_taddr + (uint32_t)(buf * 256 + col0), r);
+            tmem_wait_ld();
+#pragma unroll
+            for (int k = 0; k < 16; ++k) own[k] = __uint_as_float(r[k]) * kInvWeightScale;
+          } else {
+            const float cf = t2 ? c_t : c_v;
+#pragma unroll
+            for (int k = 0; k < 16; k += 4) {
+              const float4 w = __ldg(reinterpret_cast<const float4*>(w8 + col0 + k));
+              own[k] = cf * w.x; own[k + 1] = cf * w.y; own[k + 2] = cf * w.z; own[k + 3] = cf * w.w;
+            }
+          }
+          // adjoints of the value / tangent row for my 8 columns (the value lane takes columns 0-7 of the pair's
+          // 16, the tangent lane columns 8-15): one exchange with the partner lane
+          float eta[8], etad[8];
+#pragma unroll
+          for (int k = 0; k < 8; ++k) {
+            const float got = __shfl_xor_sync(0xffffffffu, t2 ? own[k] : own[8 + k], 1);
+            const float kept = t2 ? own[8 + k] : own[k];
+            eta[k] = t2 ? got : kept;
+            etad[k] = t2 ? kept : got;
+          }
+          // h (value row) and hdot (tangent row) of my 8 columns: straight from the slot
+          uint8_t* slot = slots + chunk * kSlotBytes;
+          mbar_wait(&u_full[chunk], io_par, 610 + chunk, j);
+          const uint4 hv4 = *reinterpret_cast<const uint4*>(slot + box_off);
+          const uint4 hd4 = *reinterpret_cast<const uint4*>(slot + kSlotBytes / 2 + box_off);
+          const uint32_t hvw[4] = {hv4.x, hv4.y, hv4.z, hv4.w}, hdw[4] = {hd4.x, hd4.y, hd4.z, hd4.w};
+          uint32_t pa[4], pd[4];                                   // packed alpha / alphadot of my 8 columns
+          const int nlive = ncols - (col0 + t2 * 8);               // live columns of my half (>= 8: all)
+#pragma unroll
+          for (int w = 0; w < 4; ++w) {
+            const float2 hv = __half22float2(*reinterpret_cast<const __half2*>(&hvw[w]));
+            const float2 hd = __half22float2(*reinterpret_cast<const __half2*>(&hdw[w]));
+            const float hve[2] = {hv.x, hv.y}, hde[2] = {hd.x, hd.y};
+            float al[2], ad[2];
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+              const int k = 2 * w + e;
+              // sigma = softplus'(a) = 1 - exp(-100 h);  adot * softplus''(a) = 100 * hdot * (1 - sigma)
+              const float one_m_s = __expf(-kSoftplusBeta * hve[e]);
+              const float sg = 1.0f - one_m_s;
+              al[e] = fmaf(etad[k], kSoftplusBeta * hde[e] * one_m_s, eta[k] * sg);       // alpha
+              ad[e] = etad[k] * sg;                                                       // alphadot
+              if (partial && k >= nlive) { al[e] = 0.f; ad[e] = 0.f; }
+            }
+            pa[w] = pack2h(al[0], al[1]);
+            pd[w] = pack2h(ad[0], ad[1]);
+          }
+          const uint4 pa4 = make_uint4(pa[0], pa[1], pa[2], pa[3]), pd4 = make_uint4(pd[0], pd[1], pd[2], pd[3]);
+          if (lt >= 1) {                                          // next MMA's operand: both rows of my point
+            *reinterpret_cast<uint4*>(A + chunk * kChunkBytes + a_off_v) = pa4;
+            *reinterpret_cast<uint4*>(A + chunk * kChunkBytes + a_off_t) = pd4;
+          }
+          *reinterpret_cast<uint4*>(slot + box_off) = pa4;        // A stash: in place of what was read
+          *reinterpret_cast<uint4*>(slot + kSlotBytes / 2 + box_off) = pd4;
+          fence_proxy_async_smem();
+          __syncwarp();
+          if (lane == 0) {
+            if (lt >= 1) mbar_arrive(&a_ready[chunk]);
+            mbar_arrive(&slot_done[chunk]);
+          }
+        }
+        if (j >= 0) {
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&acc_empty[buf]);
+        }
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == kMmaWarp) tmem_dealloc(tmem_base, 512);
+}
+
+}  // namespace t
+
 static int g_dynamic = 1;
 int set_dynamic(int v) { g_dynamic = v; return 0; }
+static int g_tma = 1;            // emap_set_option("rev_tma", 0): the register-staged kernel above (A/B switch)
+int set_tma(int v) { g_tma = v; return 0; }
 // emap_set_option("rev_rolled", 0): the unrolled issuer loop of round 1 (A/B switch; 7.2 vs 7.1 ms rolled)
 static int g_rolled = 1;
 int set_rolled(int v) { g_rolled = v; return 0; }
@@ -322,6 +658,19 @@ extern "C" int emap_bwd_reverse_sweep(const emap_net_desc* net, const void* pack
   if (tiles < grid) grid = (int)tiles;
   a.iters = (int)((tiles + grid - 1) / grid);
   a.tile_counter = rev::g_dynamic ? tile_counter((cudaStream_t)stream) : nullptr;
+  a.dbg = (rev::g_rolled >> 1) & 3;
+  if (rev::g_tma) {
+    rev::t::Maps maps;
+    if (make_stash_map(maps.u, st_u, P) || make_stash_map(maps.a, st_a, P)) return 1;
+    static bool attr_done_t = false;
+    if (!attr_done_t) {
+      EMAP_CUDA(cudaFuncSetAttribute(rev::t::mlp_revt_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, rev::t::Smem::total));
+      attr_done_t = true;
+    }
+    rev::t::mlp_revt_kernel<<<grid, rev::t::kThreadsT, rev::t::Smem::total, (cudaStream_t)stream>>>(maps, a);
+    EMAP_CUDA(cudaGetLastError());
+    return 0;
+  }
   static bool attr_done = false;
   if (!attr_done) {
     EMAP_CUDA(cudaFuncSetAttribute(rev::mlp_rev_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, rev::Smem::total));

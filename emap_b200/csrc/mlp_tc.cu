@@ -33,7 +33,7 @@ namespace emap {
 
 namespace rg { int set_flags(int v); }   // mlp_rg.cu
 namespace dw { int set_desc_strides(int which, int v); }   // mlp_dw.cu
-namespace rev { int set_dynamic(int v); int set_rolled(int v); }   // mlp_rev.cu
+namespace rev { int set_dynamic(int v); int set_rolled(int v); int set_tma(int v); }   // mlp_rev.cu
 
 template <int NTERMS, int MODE, typename T, int CL_>
 __global__ void __launch_bounds__(kThreads, 1) mlp_kernel(const MlpArgs args) {
@@ -382,8 +382,15 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_kernel(const MlpArgs args) {
         if (MODE == 3) {
           const long long pc = (pt < args.P) ? pt : args.P - 1;
           const __half* hp = args.st_u + (size_t)l * 2 * (size_t)args.P * 256 + (size_t)pc * 256 + sub * 16;
+          if (args.dbg_flags & 32) {            // (dbg 32: timing experiment without the stash loads)
 #pragma unroll
-          for (int c4 = 0; c4 < 4; ++c4) ldg256(hp + c4 * 64, hw[c4]);
+            for (int c4 = 0; c4 < 4; ++c4)
+#pragma unroll
+              for (int k = 0; k < 8; ++k) hw[c4][k] = 0x3c003c00u;
+          } else {
+#pragma unroll
+            for (int c4 = 0; c4 < 4; ++c4) ldg256(hp + c4 * 64, hw[c4]);
+          }
           // (an L2 prefetch of the next layer's rows from here was measured: 4.30 vs 4.04 ms -- slower, removed)
         }
         mbar_wait(&acc_full[buf * 2], acc_par, 500 + buf, l);
@@ -487,7 +494,8 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_kernel(const MlpArgs args) {
 #pragma unroll
               for (int j = 0; j < 4; ++j) pu[g * 4 + j] = Elem<__half>::pack2(v8[2 * j], v8[2 * j + 1]);
             }
-            if (okp) st_dst = args.st_u + (size_t)l * 2 * (size_t)args.P * 256 + ((size_t)args.P + (size_t)pt) * 256 + col0;
+            if (okp && !(args.dbg_flags & 8))      // (dbg 8: timing experiment without the stash stores)
+              st_dst = args.st_u + (size_t)l * 2 * (size_t)args.P * 256 + ((size_t)args.P + (size_t)pt) * 256 + col0;
           } else if (MODE == 0 || MODE == 5) {
 #pragma unroll
             for (int g = 0; g < 2; ++g) {
@@ -808,6 +816,7 @@ extern "C" int emap_bwd_tangent_forward(const emap_net_desc* net, const void* pa
   a.packed = (const uint8_t*)packed; a.pts = pts; a.rays_o = rays_o; a.rays_d = rays_d; a.z = z;
   a.n_per_ray = n_per_ray; a.P = P; a.gbar = d_grad; a.bwd_scales = scales;
   a.st_u0 = (__half*)st_u0; a.st_u = (__half*)st_u;
+  a.dbg_clk = g_dbg_clk;          // (NULL unless emap_debug_set_clk_buffer: clock64 timeline of block 0)
   // single-MMA, one CTA per SM, no cluster variants: the only configuration this mode is built for
   if (g_cluster == 3)
     return net->elem_type == 0 ? launch<1, 3, __half, 3>(a, (cudaStream_t)stream)
@@ -843,6 +852,7 @@ extern "C" int emap_set_option(const char* name, int value) {
   if (!strcmp(name, "dw_sbo")) return emap::dw::set_desc_strides(1, value);
   if (!strcmp(name, "k1_dot")) { emap::g_k1_dot = (value != 0); return 0; }
   if (!strcmp(name, "rev_rolled")) return emap::rev::set_rolled(value);
+  if (!strcmp(name, "rev_tma")) return emap::rev::set_tma(value);
   if (!strcmp(name, "rg_flags")) return emap::rg::set_flags(value);   // K1r experiment switches (mlp_rg.cu)
   return set_error("unknown option '%s'", name);
 }

@@ -45,3 +45,36 @@ def test_weight_grad_partials_match_matmul(P):
     for l in range(8):
         ref = st_a[l][:P].double().sum(0)
         assert float((dbp[l] - ref).abs().max()) <= 1e-4 * max(1.0, float(ref.abs().max())), l
+
+
+@pytest.mark.parametrize("P", [37, 64, 1000, 25600, 25613])
+def test_reverse_sweep_tma_staged_is_bit_identical_to_register_staged(P):
+    """The default reverse sweep stages both stashes through shared memory with the TMA engine (boxes of 64 points,
+    zero fill / clipping past P); the register-staged kernel of round 1 (rev_tma = 0) is the same arithmetic.  Random
+    but realistic stashes (h >= 0), every stored row compared bit for bit: fewer points than a tile, exact tiles,
+    ragged tails, several tiles per CTA."""
+    from emap_b200 import ops, _cabi as C
+    torch.manual_seed(P)
+    dev = "cuda"
+    net = ops.PackedNet(10)
+    from tests.helpers import oracle_params
+    p = oracle_params(True)
+    net.fold(torch.cat([t.reshape(-1) for t in p.tensors()]).to(dev))
+    st_u = torch.empty(8, 2 * P, 256, device=dev, dtype=torch.float16)
+    st_u[:, :P] = (torch.rand(8, P, 256, device=dev) * 0.08).half()          # h: softplus outputs, sigma in (0, 1)
+    st_u[:, P:] = (torch.randn(8, P, 256, device=dev) * 0.5).half()           # hdot
+    coef = torch.randn(2 * P, device=dev) * 0.3
+    L, desc = C.lib(), ctypes.byref(net.desc)
+    outs = []
+    for tma in (1, 0):
+        st_a = torch.full((8, 2 * P, 256), float("nan"), device=dev, dtype=torch.float16)
+        try:
+            C.set_option("rev_tma", tma)
+            C.check(L.emap_bwd_reverse_sweep(desc, C.ptr(net.packed), C.ptr(coef), C.ptr(st_u), C.ptr(st_a), P,
+                                             C.stream()))
+            torch.cuda.synchronize()
+        finally:
+            C.set_option("rev_tma", 1)
+        outs.append(st_a)
+    assert torch.isfinite(outs[0].float()).all()                             # every row of every plane was written
+    assert torch.equal(outs[0].view(torch.int16), outs[1].view(torch.int16))
