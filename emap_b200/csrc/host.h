@@ -16,7 +16,7 @@ size_t flat_param_count(int multires);
 void build_layout(const emap_net_desc& net, PackedHeader& h, std::vector<RingItem>& t1,
                   std::vector<RingItem>& t3);
 int sm_count();
-int make_stash_map(void* map_out_128B, const void* base, long long P);   // mlp_dw.cu: TMA view of st_u / st_a
+int make_stash_map(void* map_out_128B, const void* base, long long P, int box_points);   // mlp_dw.cu: TMA view of st_u / st_a
 unsigned int* tile_counter(cudaStream_t stream);   // zeroed per-launch counter for dynamic tile scheduling (or NULL)
 
 // Workspace of the backward's weight-gradient stage (emap_bwd_workspace_bytes), in floats:

@@ -39,11 +39,14 @@ struct MlpArgs {
   int dbg_flags;        // timing experiments only: 1 = no MMA issue, 2 = no weight copies, 4 = no epilogue math
   int dbg_iter;         // tile iteration of block 0 whose timeline is stamped into dbg_clk (emap_set_option("dbg_iter"))
   unsigned int* tile_counter;   // single-CTA launches: tiles grid, grid+1, ... are handed out in arrival order (NULL = static)
+  // MODE 3 (tangent forward) with fp16 stashes: CUtensorMap over st_u as [16 half-planes][P][256], boxes of
+  // [128 points x 64 columns] (host.h: make_stash_map) -- the stash rows travel through shared memory by TMA
+  alignas(64) unsigned char stash_map[128];
 };
 
 constexpr int kRingStageBytes = 2 * kStageBytes;   // one part: [256 x 64] 16-bit SW128 image (N halves adjacent)
 
-template <int NTERMS, int MODE, bool PAIR = false>
+template <int NTERMS, int MODE, bool PAIR = false, bool SLOTS = false>
 struct SmemPlan {
   // fp32x3: A_hi + A_lo = 128 KiB, ring 3 x 32 KiB; single-MMA modes: A = 64 KiB, ring 4 x 32 KiB.
   // PAIR (cta_group::2): every CTA of a pair stages only ITS N half of each operand -> 16 KiB stages,
@@ -53,18 +56,23 @@ struct SmemPlan {
   //  In fp32x3 MODE_GRAD the value->tangent exchange scratch aliases the destination chunk -- see the
   //  epilogue -- so that the third ring stage fits.)
   static constexpr int kStageBytesP = PAIR ? kStageBytes : kRingStageBytes;
-  static constexpr int kStages = ((NTERMS == 3) ? 3 : 4) * (PAIR ? 2 : 1);
+  // MODE 3 (tangent forward, single MMA): four 16 KiB slots through which the TMA engine moves the stash rows
+  // (value rows in, tangent rows out, see mlp_tc.cu), paid for with one ring stage.
+  static constexpr bool kSlots = SLOTS;
+  static constexpr int kStages = ((NTERMS == 3 || kSlots) ? 3 : 4) * (PAIR ? 2 : 1);
   static constexpr bool kOwnScratch = (MODE == 1 && NTERMS == 1);
   static constexpr int a_hi = 0;
   static constexpr int a_lo = a_hi + 4 * kChunkBytes;
   static constexpr int ring = a_lo + ((NTERMS == 3) ? 4 * kChunkBytes : 0);
-  static constexpr int scratch = ring + kStages * kStageBytesP;
+  static constexpr int slots = ring + kStages * kStageBytesP;
+  static constexpr int scratch = slots + (kSlots ? 4 * kChunkBytes : 0);
   static constexpr int bars = scratch + (kOwnScratch ? kEpiWarps * kScratchFloatsPerWarp * 4 : 0);
-  static constexpr int total = bars + 320 + 1024;   // +1 KiB slack to 1024-align the base
+  static constexpr int total = bars + 384 + 1024;   // +1 KiB slack to 1024-align the base
 };
 static_assert(SmemPlan<3, 1>::total <= 232448 && SmemPlan<3, 0>::total <= 232448 &&
               SmemPlan<1, 1>::total <= 232448 && SmemPlan<3, 2>::total <= 232448 &&
-              SmemPlan<3, 1, true>::total <= 232448, "shared memory plan exceeds 227 KiB");
+              SmemPlan<3, 1, true>::total <= 232448 && SmemPlan<1, 3, false, true>::total <= 232448,
+              "shared memory plan exceeds 227 KiB");
 
 // per-mode schedule constants (MODE 0 forward, 1 forward+grad (4 rows/point), 2 dual forward with
 // stashes for the backward (2 rows/point, layers 0..7 only -- the output layer is pulled back by a

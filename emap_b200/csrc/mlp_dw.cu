@@ -267,15 +267,15 @@ static int make_map(CUtensorMap* m, const void* base, long long rows, int cols) 
 }  // namespace dw
 
 // Tensor map over one stash of the backward (st_u or st_a: fp16 [8][2P][256], value rows [0,P) and tangent rows
-// [P,2P) of each plane) seen as [16 half-planes][P points][256 columns]: boxes of [64 points x 64 columns] with the
+// [P,2P) of each plane) seen as [16 half-planes][P points][256 columns]: boxes of [box_points x 64 columns] with the
 // 128-byte swizzle; points beyond P are zero-filled on load and dropped on store (ragged last tile).  Used by the
 // reverse sweep (mlp_rev.cu), which stages both stashes through shared memory with the TMA engine.
-int make_stash_map(void* map_out, const void* base, long long P) {
+int make_stash_map(void* map_out, const void* base, long long P, int box_points) {
   auto enc = dw::encode_fn();
   if (!enc) return set_error("cuTensorMapEncodeTiled is not available from the driver");
   cuuint64_t dims[3] = {256, (cuuint64_t)P, 16};
   cuuint64_t strides[2] = {512, (cuuint64_t)P * 512};
-  cuuint32_t box[3] = {64, 64, 1};
+  cuuint32_t box[3] = {64, (cuuint32_t)box_points, 1};
   cuuint32_t estr[3] = {1, 1, 1};
   CUresult r = enc(reinterpret_cast<CUtensorMap*>(map_out), CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 3,
                    const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,

@@ -661,7 +661,7 @@ extern "C" int emap_bwd_reverse_sweep(const emap_net_desc* net, const void* pack
   a.dbg = (rev::g_rolled >> 1) & 3;
   if (rev::g_tma) {
     rev::t::Maps maps;
-    if (make_stash_map(maps.u, st_u, P) || make_stash_map(maps.a, st_a, P)) return 1;
+    if (make_stash_map(maps.u, st_u, P, 64) || make_stash_map(maps.a, st_a, P, 64)) return 1;
     static bool attr_done_t = false;
     if (!attr_done_t) {
       EMAP_CUDA(cudaFuncSetAttribute(rev::t::mlp_revt_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, rev::t::Smem::total));

@@ -35,8 +35,33 @@ namespace rg { int set_flags(int v); }   // mlp_rg.cu
 namespace dw { int set_desc_strides(int which, int v); }   // mlp_dw.cu
 namespace rev { int set_dynamic(int v); int set_rolled(int v); int set_tma(int v); }   // mlp_rev.cu
 
+// TMA helpers of the tangent forward's stash traffic (same scheme as mlp_rev.cu)
+__device__ __forceinline__ void tma_load_3d(void* smem_dst, const void* map, int c0, int c1, int c2, uint64_t* bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];" ::
+          "r"(smem_u32(smem_dst)),
+      "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
+__device__ __forceinline__ void tma_store_3d(const void* smem_src, const void* map, int c0, int c1, int c2) {
+  asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.tile.bulk_group [%0, {%2, %3, %4}], [%1];" ::
+                   "l"(reinterpret_cast<uint64_t>(map)),
+               "r"(smem_u32(smem_src)), "r"(c0), "r"(c1), "r"(c2)
+               : "memory");
+}
+template <typename T> struct IsFp16 { static constexpr bool value = false; };
+template <> struct IsFp16<__half> { static constexpr bool value = true; };
+// The tangent forward with TMA-staged stash rows: MODE 3, single fp16 MMA, CL_ = 1 (CL_ = 3 keeps the
+// register-staged round-1 form as A/B switch).  It runs a 19th warp that owns the stash traffic.
+template <int NTERMS, int MODE, typename T, int CL_> struct TmaStash {
+  static constexpr bool value = (MODE == 3 && NTERMS == 1 && IsFp16<T>::value && CL_ == 1);
+};
+template <int NTERMS, int MODE, typename T, int CL_> struct ThreadsOf {
+  static constexpr int value = kThreads + (TmaStash<NTERMS, MODE, T, CL_>::value ? 32 : 0);
+};
+
 template <int NTERMS, int MODE, typename T, int CL_>
-__global__ void __launch_bounds__(kThreads, 1) mlp_kernel(const MlpArgs args) {
+__global__ void __launch_bounds__(ThreadsOf<NTERMS, MODE, T, CL_>::value, 1) mlp_kernel(const __grid_constant__ MlpArgs args) {
   // CL = 1|2|4: weight-stream multicast width (cta_group::1).  CL = -2: PAIR mode -- clusters of two CTAs
   // driven by ONE MMA issuer with tcgen05.mma.cta_group::2 (M = 256: each CTA's 128-row tile, N = 256 split
   // as 128 weight rows per CTA): every SM stages and reads only half of each weight operand.
@@ -48,7 +73,8 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_kernel(const MlpArgs args) {
   constexpr int CL = (CL_ == 3) ? 1 : CL_;
   constexpr bool PAIR = (CL == -2);
   constexpr int CLW = PAIR ? 2 : CL;             // cluster width
-  using Plan = SmemPlan<NTERMS, MODE, PAIR>;
+  constexpr bool kTmaC = TmaStash<NTERMS, MODE, T, CL_>::value;
+  using Plan = SmemPlan<NTERMS, MODE, PAIR, kTmaC>;
   using MI = ModeInfo<MODE>;
   constexpr int kStages = Plan::kStages;
   constexpr int kStageB = Plan::kStageBytesP;
@@ -79,6 +105,12 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_kernel(const MlpArgs args) {
   // value of a global atomic counter (SM-to-SM speed differences of ~10 % otherwise idle the fast SMs at the
   // end).  A tile index >= num_tiles ends every role's loop.  Cluster configurations keep the static loop.
   constexpr bool kSched = (CL == 1);
+  // MODE 3, fp16 stashes (the only kind the backward makes): the value rows h_{l+1} the epilogue needs and the
+  // tangent rows it produces move through four 16 KiB slots by TMA, issued by a 19th warp -- see the I/O role below
+  constexpr bool tma = kTmaC;
+  uint64_t* u_full = bars + 40;           // [4] slot c holds h_{l+1} of the coming layer (8 completions per tile)
+  uint64_t* out_done = bars + 44;         // [4] slot c holds hdot_{l+1} of the finished layer (8 per tile)
+  constexpr int kIoWarp = kEpiWarps + 2;
   uint64_t* sched_ready = bars + 21;
   volatile int* sched_tile = reinterpret_cast<volatile int*>(bars + 22);
   const uint32_t crank = (CLW > 1) ? cluster_ctarank() : 0;
@@ -92,6 +124,7 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_kernel(const MlpArgs args) {
     for (int b = 0; b < 4; ++b) mbar_init(&acc_full[b], 1);
     for (int b = 0; b < 2; ++b) mbar_init(&acc_empty[b], kEpiWarps * kArr);
     mbar_init(c0_free, 1);
+    if (kTmaC) { for (int c = 0; c < 4; ++c) { mbar_init(&u_full[c], 1); mbar_init(&out_done[c], kEpiWarps); } }
     if (kSched) { mbar_init(sched_ready, 1); sched_tile[0] = (int)blockIdx.x; }
     fence_barrier_init();
     if (kSched) mbar_arrive(sched_ready);          // completion 0: iteration 0 runs tile blockIdx.x
@@ -319,6 +352,54 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_kernel(const MlpArgs args) {
         if (stamp) args.dbg_clk[72 + l * 8 + 6] = clock64();
       }
     }
+  } else if (kTmaC && warp == kIoWarp) {
+    // ===================================== stash I/O (MODE 3): one thread ================
+    // Slot c (16 KiB: [128 points x 64 columns], 128-byte swizzle) is filled with the value rows h_{l+1} of the
+    // tile a whole layer ahead of their use, overwritten in place by the epilogue with the tangent rows
+    // hdot_{l+1}, written to the stash by a TMA store, and refilled as soon as the store has read it.
+    if (lane == 0) {
+      uint8_t* slots = smem + Plan::slots;
+      const void* map = args.stash_map;
+      auto load_h = [&](int c, int plane, int pt0) {
+        mbar_arrive_expect_tx(&u_full[c], kChunkBytes);
+        tma_load_3d(slots + c * kChunkBytes, map, c * 64, pt0, plane * 2, &u_full[c]);
+      };
+      for (int iter = 0;; ++iter) {
+        mbar_wait(sched_ready, (uint32_t)iter & 1, 563);
+        const int tile = sched_tile[iter & 1];
+        if (tile >= args.num_tiles) break;
+        const int pt0 = tile * 128;
+        if (iter == 0) {
+          for (int c = 0; c < 4; ++c) load_h(c, 0, pt0);
+        }
+        int next_tile = args.num_tiles;
+#pragma unroll 1
+        for (int l = 0; l < 8; ++l) {
+          auto refill = [&](int c) {
+            if (l < 7) load_h(c, l + 1, pt0);
+            else if (next_tile < args.num_tiles) load_h(c, 0, next_tile * 128);
+          };
+          if (l == 7) {                                         // the next tile: published during layer 2 of this one
+            mbar_wait(sched_ready, (uint32_t)(iter + 1) & 1, 564);
+            next_tile = sched_tile[(iter + 1) & 1];
+          }
+#pragma unroll 1
+          for (int c = 0; c < 4; ++c) {
+            mbar_wait(&out_done[c], ((uint32_t)iter * 8u + (uint32_t)l) & 1, 600 + c, l);
+            tma_store_3d(slots + c * kChunkBytes, map, c * 64, pt0, l * 2 + 1);
+            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+            if (c > 0) {                                        // one store stays in flight
+              asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+              refill(c - 1);
+            }
+          }
+          asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+          refill(3);
+        }
+      }
+      asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");   // every store has left before the CTA exits
+    }
+    __syncwarp();
   } else {
     // ===================================== epilogue warps ================================
     // warp = 4*sub + q: q = TMEM lane quarter; per layer each warp converts two 32-column pieces:
@@ -379,7 +460,7 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_kernel(const MlpArgs args) {
         // MODE 3: this row's h_{l+1} (value row of the stash, written by the training forward) for the
         // thread's 16 columns of all four chunks -- independent of the MMA, fetched before waiting for it
         uint32_t hw[(MODE == 3) ? 4 : 1][8];
-        if (MODE == 3) {
+        if (MODE == 3 && !tma) {
           const long long pc = (pt < args.P) ? pt : args.P - 1;
           const __half* hp = args.st_u + (size_t)l * 2 * (size_t)args.P * 256 + (size_t)pc * 256 + sub * 16;
           if (args.dbg_flags & 32) {            // (dbg 32: timing experiment without the stash loads)
@@ -480,6 +561,16 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_kernel(const MlpArgs args) {
             // recovered from the value row of the stash (as the reverse sweep does); next layer's A tile +
             // the tangent row of the stash.
             const bool okp = (tile < args.num_tiles) && (pt < args.P);
+            // TMA path: this row's 16 columns of h_{l+1} are two 16-byte units of the slot (row = point)
+            uint8_t* srow = smem + Plan::slots + chunk * kChunkBytes + (uint32_t)row * 128u;
+            if (kTmaC) {
+              mbar_wait(&u_full[chunk], ((uint32_t)iter * 8u + (uint32_t)l) & 1, 610 + chunk, l);
+#pragma unroll
+              for (int g = 0; g < 2; ++g) {
+                const uint4 v = *reinterpret_cast<const uint4*>(srow + ((((uint32_t)(sub * 2 + g)) ^ (uint32_t)(row & 7)) << 4));
+                hw[chunk][g * 4] = v.x; hw[chunk][g * 4 + 1] = v.y; hw[chunk][g * 4 + 2] = v.z; hw[chunk][g * 4 + 3] = v.w;
+              }
+            }
 #pragma unroll
             for (int g = 0; g < 2; ++g) {
               float v8[8];
@@ -493,8 +584,11 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_kernel(const MlpArgs args) {
               if (l < 7) store_group<NTERMS, T>(dst_hi, dst_lo, row, sub * 2 + g, v8);
 #pragma unroll
               for (int j = 0; j < 4; ++j) pu[g * 4 + j] = Elem<__half>::pack2(v8[2 * j], v8[2 * j + 1]);
+              if (kTmaC)                           // the stash row: in place of what was read
+                *reinterpret_cast<uint4*>(srow + ((((uint32_t)(sub * 2 + g)) ^ (uint32_t)(row & 7)) << 4)) =
+                    make_uint4(pu[g * 4], pu[g * 4 + 1], pu[g * 4 + 2], pu[g * 4 + 3]);
             }
-            if (okp && !(args.dbg_flags & 8))      // (dbg 8: timing experiment without the stash stores)
+            if (okp && !(args.dbg_flags & 8) && !tma)      // (dbg 8: timing experiment without the stash stores)
               st_dst = args.st_u + (size_t)l * 2 * (size_t)args.P * 256 + ((size_t)args.P + (size_t)pt) * 256 + col0;
           } else if (MODE == 0 || MODE == 5) {
 #pragma unroll
@@ -579,6 +673,7 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_kernel(const MlpArgs args) {
           fence_proxy_async_smem();
           __syncwarp();
           if (lane == 0 && !(MODE >= 2 && l == 7)) arrive_issuer(&a_ready[chunk]);
+          if (kTmaC && lane == 0) mbar_arrive(&out_done[chunk]);
           if (stamp && chunk < 2) args.dbg_clk[l * 8 + 4 + 3 * chunk] = clock64();
           if ((MODE == 2 || MODE == 3) && st_dst) stg256(st_dst, pu);
         }
@@ -665,7 +760,7 @@ static int launch(const MlpArgs& a_in, cudaStream_t stream) {
   constexpr int CL = (CL_ == 3) ? 1 : CL_;       // 3 = width 1 with the UNROLLED issuer loop (A/B switch)
   constexpr bool PAIR = (CL == -2);
   constexpr int CLW = PAIR ? 2 : CL;
-  using Plan = SmemPlan<NTERMS, MODE, PAIR>;
+  using Plan = SmemPlan<NTERMS, MODE, PAIR, TmaStash<NTERMS, MODE, T, CL_>::value>;
   MlpArgs a = a_in;
   const int pts_per_tile = ModeInfo<MODE>::kPtsPerTile;
   const long long tiles = (a.P + pts_per_tile - 1) / pts_per_tile;
@@ -687,7 +782,7 @@ static int launch(const MlpArgs& a_in, cudaStream_t stream) {
   cudaLaunchConfig_t cfg;
   memset(&cfg, 0, sizeof(cfg));
   cfg.gridDim = dim3(grid);
-  cfg.blockDim = dim3(kThreads);
+  cfg.blockDim = dim3(ThreadsOf<NTERMS, MODE, T, CL_>::value);
   cfg.dynamicSmemBytes = Plan::total;
   cfg.stream = stream;
   cudaLaunchAttribute attr[1];
@@ -708,6 +803,7 @@ static int g_cluster = 1;
 // emap_set_option("k1_dot", 1): emap_udf_forward runs MODE 5 (output layer as a dot product in layer 7's
 // epilogue, 8 MMA steps per tile instead of 9) when no PE output is requested.  Opt-in until measured.
 static int g_k1_dot = 0;
+static int g_tan_tma = 1;     // emap_set_option("tan_tma", 0): tangent forward with register-staged stash rows
 
 template <int MODE>
 static int dispatch(const emap_net_desc* net, int precision, const MlpArgs& a, cudaStream_t st) {
@@ -817,11 +913,12 @@ extern "C" int emap_bwd_tangent_forward(const emap_net_desc* net, const void* pa
   a.n_per_ray = n_per_ray; a.P = P; a.gbar = d_grad; a.bwd_scales = scales;
   a.st_u0 = (__half*)st_u0; a.st_u = (__half*)st_u;
   a.dbg_clk = g_dbg_clk;          // (NULL unless emap_debug_set_clk_buffer: clock64 timeline of block 0)
-  // single-MMA, one CTA per SM, no cluster variants: the only configuration this mode is built for
-  if (g_cluster == 3)
-    return net->elem_type == 0 ? launch<1, 3, __half, 3>(a, (cudaStream_t)stream)
-                               : launch<1, 3, __nv_bfloat16, 3>(a, (cudaStream_t)stream);
-  if (net->elem_type == 0) return launch<1, 3, __half, 1>(a, (cudaStream_t)stream);
+  // fp16 packs: stash rows through shared memory by TMA ("tan_tma" 0 or "cluster" 3: the register-staged form)
+  if (net->elem_type == 0 && g_tan_tma && g_cluster != 3) {
+    if (make_stash_map(a.stash_map, st_u, P, 128)) return 1;
+    return launch<1, 3, __half, 1>(a, (cudaStream_t)stream);
+  }
+  if (net->elem_type == 0) return launch<1, 3, __half, 3>(a, (cudaStream_t)stream);
   return launch<1, 3, __nv_bfloat16, 1>(a, (cudaStream_t)stream);
 }
 
@@ -853,6 +950,7 @@ extern "C" int emap_set_option(const char* name, int value) {
   if (!strcmp(name, "k1_dot")) { emap::g_k1_dot = (value != 0); return 0; }
   if (!strcmp(name, "rev_rolled")) return emap::rev::set_rolled(value);
   if (!strcmp(name, "rev_tma")) return emap::rev::set_tma(value);
+  if (!strcmp(name, "tan_tma")) { emap::g_tan_tma = value; return 0; }
   if (!strcmp(name, "rg_flags")) return emap::rg::set_flags(value);   // K1r experiment switches (mlp_rg.cu)
   return set_error("unknown option '%s'", name);
 }

@@ -78,3 +78,41 @@ def test_reverse_sweep_tma_staged_is_bit_identical_to_register_staged(P):
         outs.append(st_a)
     assert torch.isfinite(outs[0].float()).all()                             # every row of every plane was written
     assert torch.equal(outs[0].view(torch.int16), outs[1].view(torch.int16))
+
+
+@pytest.mark.parametrize("P", [50, 128, 1000, 51200, 51277])
+def test_tangent_forward_tma_staged_is_bit_identical_to_register_staged(P):
+    """The tangent forward moves the stash rows (value rows in, tangent rows out) through shared memory with the TMA
+    engine by default; tan_tma = 0 is the register-staged form of the same arithmetic.  Real value rows (written by the
+    training forward K1r), random cotangent direction; the tangent rows of all eight planes and of the PE stash are
+    compared bit for bit; the value rows must be untouched."""
+    from emap_b200 import ops, _cabi as C
+    from tests.helpers import oracle_params
+    torch.manual_seed(P)
+    dev = torch.device("cuda")
+    p = oracle_params(True)
+    net = ops.PackedNet(10)
+    net.fold(torch.cat([t.reshape(-1) for t in p.tensors()]).to(dev))
+    x = (torch.rand(P, 3, device=dev) * 2 - 1) * 1.2
+    gbar = torch.randn(P, 3, device=dev) * 1e-4
+    L, desc, st = C.lib(), ctypes.byref(net.desc), C.stream()
+    scales = torch.empty(8, device=dev)
+    C.check(L.emap_bwd_cotangent_scales(None, C.ptr(gbar), P, C.ptr(scales), st))
+    outs = []
+    for tma in (1, 0):
+        stash = ops.alloc_backward_stash(P, dev)
+        stash[0].fill_(float("nan")); stash[1].fill_(float("nan"))
+        ops.udf_forward_grad(net, C.PREC_FP32X3, pts=x, mode="reverse", stash=stash)
+        values = stash[1][:, :P].clone()
+        try:
+            C.set_option("tan_tma", tma)
+            C.check(L.emap_bwd_tangent_forward(desc, C.ptr(net.packed), C.ptr(x), None, None, None, 0, P, C.ptr(gbar),
+                                               C.ptr(scales), C.ptr(stash[0]), C.ptr(stash[1]), st))
+            torch.cuda.synchronize()
+        finally:
+            C.set_option("tan_tma", 1)
+        assert torch.equal(stash[1][:, :P].view(torch.int16), values.view(torch.int16))
+        outs.append((stash[0].clone(), stash[1].clone()))
+    assert torch.isfinite(outs[0][1].float()).all() and torch.isfinite(outs[0][0].float()).all()
+    assert torch.equal(outs[0][0].view(torch.int16), outs[1][0].view(torch.int16))
+    assert torch.equal(outs[0][1].view(torch.int16), outs[1][1].view(torch.int16))

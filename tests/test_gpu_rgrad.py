@@ -302,9 +302,9 @@ def test_rolled_issuer_variants_of_the_backward_are_bit_identical(golden):
 
     ref = grads()
     try:
-        C.set_option("cluster", 3); C.set_option("rev_rolled", 0); C.set_option("rev_tma", 0); C.set_option("rg_flags", 8)
+        C.set_option("cluster", 3); C.set_option("rev_rolled", 0); C.set_option("rev_tma", 0); C.set_option("tan_tma", 0); C.set_option("rg_flags", 8)
         got = grads()
     finally:
-        C.set_option("cluster", 1); C.set_option("rev_rolled", 1); C.set_option("rev_tma", 1); C.set_option("rg_flags", 28)
+        C.set_option("cluster", 1); C.set_option("rev_rolled", 1); C.set_option("rev_tma", 1); C.set_option("tan_tma", 1); C.set_option("rg_flags", 28)
     for a, b in zip(ref, got):
         assert torch.equal(a, b)

@@ -43,11 +43,14 @@ tan = lambda: L.emap_bwd_tangent_forward(desc, C.ptr(net.packed), C.ptr(x), None
                                          C.ptr(scales), C.ptr(stash[0]), C.ptr(stash[1]), st)
 rev = lambda: L.emap_bwd_reverse_sweep(desc, C.ptr(net.packed), C.ptr(coef), C.ptr(stash[1]), C.ptr(st_a), P, st)  # noqa: E731
 for rnd in range(2):
-    out = []
-    for d, name in ((0, "full"), (8, "no stores"), (32, "no loads"), (40, "no loads, no stores"), (44, "no epilogue math either")):
+    C.set_option("tan_tma", 1)
+    out = [f"TMA-staged {t(tan):.2f} |"]
+    C.set_option("tan_tma", 0)
+    for d, name in ((0, "register-staged: full"), (8, "no stores"), (32, "no loads"), (40, "no loads, no stores"), (44, "no epilogue math either")):
         C.set_option("dbg", d)
         out.append(f"{name} {t(tan):.2f}")
     C.set_option("dbg", 0)
+    C.set_option("tan_tma", 1)
     print(f"tangent forward round {rnd}: " + "   ".join(out) + "  ms", flush=True)
     C.set_option("rev_tma", 1)
     out = [f"TMA-staged {t(rev):.2f} |"]
