@@ -44,6 +44,24 @@ struct MlpArgs {
   alignas(64) unsigned char stash_map[128];
 };
 
+template <typename T> struct IsFp16 { static constexpr bool value = false; };
+template <> struct IsFp16<__half> { static constexpr bool value = true; };
+
+// TMA helpers of the stash traffic (tangent forward in mlp_tc.cu, training forward in mlp_rg.cu; mlp_rev.cu has its own)
+__device__ __forceinline__ void tma_load_3d(void* smem_dst, const void* map, int c0, int c1, int c2, uint64_t* bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];" ::
+          "r"(smem_u32(smem_dst)),
+      "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
+__device__ __forceinline__ void tma_store_3d(const void* smem_src, const void* map, int c0, int c1, int c2) {
+  asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.tile.bulk_group [%0, {%2, %3, %4}], [%1];" ::
+                   "l"(reinterpret_cast<uint64_t>(map)),
+               "r"(smem_u32(smem_src)), "r"(c0), "r"(c1), "r"(c2)
+               : "memory");
+}
+
 constexpr int kRingStageBytes = 2 * kStageBytes;   // one part: [256 x 64] 16-bit SW128 image (N halves adjacent)
 
 template <int NTERMS, int MODE, bool PAIR = false, bool SLOTS = false>

@@ -31,6 +31,8 @@ long long* dbg_clk_buffer();   // mlp_tc.cu (emap_debug_set_clk_buffer)
 int dbg_iter();                 // mlp_tc.cu (emap_set_option("dbg_iter"))
 namespace rg {
 
+constexpr int kIoWarp = kEpiWarps + 2;            // 19th warp: TMA stores of the training stash (idle in inference)
+constexpr int kThreadsRg = kThreads + 32;
 constexpr int kSteps = 16;
 constexpr int kLastStep = kSteps - 1;
 constexpr uint32_t kUsesPerBuf = 8;               // accumulator uses per tile and buffer (buf = step & 1)
@@ -65,6 +67,7 @@ constexpr int kFlagSplitTail = 1;   // N-split of each step's last K chunk (as K
 constexpr int kFlagL2Persist = 2;   // host side: launch with the sigma scratch as a persisting-L2 access window
 constexpr int kFlagDynamic = 8;     // tiles handed out by a global atomic counter instead of the static round robin
 constexpr int kFlagRolled = 4;      // host side: select the instantiation with the rolled issuer loop
+constexpr int kFlagRegStash = 32;   // A/B switch: training stash stored from registers (round-2 form) instead of by TMA
 constexpr int kFlagRolledEpi = 16;  // host side: ... and with the reverse steps' chunk loop rolled as well
 
 template <int NTERMS>
@@ -179,7 +182,7 @@ __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
 // source view): 7.26 -> 6.35 ms in training mode (profiles/r02_stages_time.txt).  ROLL = 2 also rolls the chunk
 // loop of the reverse steps' epilogue.
 template <int NTERMS, typename T, int ROLL>
-__global__ void __launch_bounds__(kThreads, 1) mlp_rgrad_kernel(const Args args) {
+__global__ void __launch_bounds__(kThreadsRg, 1) mlp_rgrad_kernel(const __grid_constant__ Args args) {
   using P = Plan<NTERMS>;
   constexpr int kStages = P::kStages;
   constexpr int kParts = (NTERMS == 3) ? 2 : 1;
@@ -209,6 +212,16 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_rgrad_kernel(const Args args)
   // then, so the parity wait cannot alias).  A tile index >= num_tiles ends every role's loop.
   uint64_t* sched_ready = bars + 22;
   volatile int* sched_tile = reinterpret_cast<volatile int*>(bars + 23);
+  // Training stash (value rows of the backward's U_{l+1}, fp16 = the hi half of the next step's A tile): with fp16
+  // operand images the I/O warp writes chunk c of h_{l+1} from the A tile to the stash with ONE TMA store as soon
+  // as the 16 epilogue warps have handed it off (st_ready), and the epilogue waits for that store to have read the
+  // chunk (st_done) before it overwrites it a step later -- instead of 32-byte register stores per thread and chunk.
+  constexpr bool kTmaSt = IsFp16<T>::value;
+  const bool tma_st = kTmaSt && m.st_u != nullptr && !(args.flags & kFlagRegStash);
+  // (L2 eviction hints -- evict_last on the sigma scratch, evict_first on the stash stores -- were measured: 6.7-6.8
+  //  against 6.0-6.6 ms in training mode, slower; so was a persisting-L2 window on the scratch.  Removed.)
+  uint64_t* st_ready = bars + 24;         // [4] 7 completions per tile (forward layers 0..6)
+  uint64_t* st_done = bars + 28;          // [4] 7 completions per tile
 
   if (warp == kProducerWarp && lane == 0) {
     for (int s = 0; s < kStages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
@@ -220,6 +233,7 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_rgrad_kernel(const Args args)
     for (int b = 0; b < 4; ++b) mbar_init(&acc_full[b], 1);
     for (int b = 0; b < 2; ++b) mbar_init(&acc_empty[b], kEpiWarps);
     mbar_init(c0_free, 1);
+    for (int c = 0; c < 4; ++c) { mbar_init(&st_ready[c], kEpiWarps); mbar_init(&st_done[c], 1); }
     fence_barrier_init();
     mbar_arrive(sched_ready);             // completion 0: iteration 0 runs tile blockIdx.x
   }
@@ -370,6 +384,29 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_rgrad_kernel(const Args args)
         if (stamp) m.dbg_clk[64 + 4 * s + 3] = clock64();
       }
     }
+  } else if (warp == kIoWarp) {
+    // ===================================== training stash: TMA stores, one thread ========
+    if (kTmaSt && tma_st && lane == 0) {
+      const uint8_t* A_hi_io = smem + P::a_hi;
+      for (int iter = 0;; ++iter) {
+        mbar_wait(sched_ready, (uint32_t)iter & 1, 565);
+        const int tile = sched_tile[iter & 1];
+        if (tile >= m.num_tiles) break;
+#pragma unroll 1
+        for (int l = 0; l < 7; ++l) {
+#pragma unroll 1
+          for (int c = 0; c < 4; ++c) {
+            mbar_wait(&st_ready[c], ((uint32_t)iter * 7u + (uint32_t)l) & 1, 630 + c, l);
+            tma_store_3d(A_hi_io + c * kChunkBytes, m.stash_map, c * 64, tile * 128, l * 2);   // value rows of plane l
+            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+            asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+            mbar_arrive(&st_done[c]);                           // the chunk may be overwritten
+          }
+        }
+      }
+      asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+    }
+    __syncwarp();
   } else {
     // ===================================== epilogue warps ================================
     // warp = 4*sub + q: q = TMEM lane quarter (rows 32q..32q+31 = points), sub = 16-column slice of every
@@ -462,6 +499,8 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_rgrad_kernel(const Args args)
           uint32_t r[16];
           tmem_ld_32x32b_x16(lane_taddr + (uint32_t)(buf * 256 + col0), r);
           tmem_wait_ld();
+          // the TMA store of this chunk's previous content (h_l, training stash) has read it
+          if (tma_st && l >= 1) mbar_wait(&st_done[chunk], ((uint32_t)iter * 7u + (uint32_t)(l - 1)) & 1, 620 + chunk, l);
           if (m.dbg_acc && tile == 0) {
 #pragma unroll
             for (int k = 0; k < 16; ++k)
@@ -504,7 +543,10 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_rgrad_kernel(const Args args)
           }
           fence_proxy_async_smem();
           __syncwarp();
-          if (lane == 0) mbar_arrive(&a_ready[chunk]);
+          if (lane == 0) {
+            mbar_arrive(&a_ready[chunk]);
+            if (tma_st && !top) mbar_arrive(&st_ready[chunk]);
+          }
           if (stamp && chunk == 0) m.dbg_clk[4 * l + 2] = clock64();
           if (!top) {                         // after the hand-off, off the MMA's critical path: encode and stash
             uint32_t sw[8];
@@ -518,7 +560,8 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_rgrad_kernel(const Args args)
           }
           // training: value rows [0,P) of the backward's stash U_{l+1} (emap_bwd_tangent_forward adds the
           // tangent rows later) -- after the hand-off, off the MMA's critical path
-          if (m.st_u && ok) stg256_cs(m.st_u + (size_t)l * 2 * (size_t)m.P * 256 + (size_t)pt * 256 + col0, pu);
+          // (by TMA from the A tile where that holds the same fp16 values: every layer but the last, fp16 images)
+          if (m.st_u && ok && (top || !tma_st)) stg256_cs(m.st_u + (size_t)l * 2 * (size_t)m.P * 256 + (size_t)pt * 256 + col0, pu);
         }
         tc_fence_before();
         __syncwarp();
@@ -529,6 +572,7 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_rgrad_kernel(const Args args)
           // skip connection: layer 4 = [h4 ; PE]/sqrt2.  Once its MMAs on chunk 0 are done, the PE image is
           // copied there again as the 5th K chunk of layer 4.
           mbar_wait(c0_free, (uint32_t)iter & 1, 520);
+          if (tma_st) mbar_wait(&st_done[0], ((uint32_t)iter * 7u + 3u) & 1, 625);    // h_4's chunk 0 has been stored
           if (lane == 0) issue_pe_copy(iter & 1);
           __syncwarp();
         }
@@ -728,7 +772,9 @@ static int launch_r(const Args& a_in, size_t scratch_bytes, cudaStream_t stream)
       EMAP_CUDA(cudaStreamSetAttribute(stream, cudaStreamAttributeAccessPolicyWindow, &v));
     }
   }
-  kern<<<grid, kThreads, Plan<NTERMS>::total, stream>>>(a);
+  if (IsFp16<T>::value && a.m.st_u && !(a.flags & kFlagRegStash) &&
+      make_stash_map(a.m.stash_map, a.m.st_u, a.m.P, 128)) return 1;
+  kern<<<grid, kThreadsRg, Plan<NTERMS>::total, stream>>>(a);
   EMAP_CUDA(cudaGetLastError());
   if (persist) {
     cudaStreamAttrValue v;

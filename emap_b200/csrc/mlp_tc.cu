@@ -35,22 +35,6 @@ namespace rg { int set_flags(int v); }   // mlp_rg.cu
 namespace dw { int set_desc_strides(int which, int v); }   // mlp_dw.cu
 namespace rev { int set_dynamic(int v); int set_rolled(int v); int set_tma(int v); }   // mlp_rev.cu
 
-// TMA helpers of the tangent forward's stash traffic (same scheme as mlp_rev.cu)
-__device__ __forceinline__ void tma_load_3d(void* smem_dst, const void* map, int c0, int c1, int c2, uint64_t* bar) {
-  asm volatile(
-      "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];" ::
-          "r"(smem_u32(smem_dst)),
-      "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
-      : "memory");
-}
-__device__ __forceinline__ void tma_store_3d(const void* smem_src, const void* map, int c0, int c1, int c2) {
-  asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.tile.bulk_group [%0, {%2, %3, %4}], [%1];" ::
-                   "l"(reinterpret_cast<uint64_t>(map)),
-               "r"(smem_u32(smem_src)), "r"(c0), "r"(c1), "r"(c2)
-               : "memory");
-}
-template <typename T> struct IsFp16 { static constexpr bool value = false; };
-template <> struct IsFp16<__half> { static constexpr bool value = true; };
 // The tangent forward with TMA-staged stash rows: MODE 3, single fp16 MMA, CL_ = 1 (CL_ = 3 keeps the
 // register-staged round-1 form as A/B switch).  It runs a 19th warp that owns the stash traffic.
 template <int NTERMS, int MODE, typename T, int CL_> struct TmaStash {

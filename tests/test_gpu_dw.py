@@ -116,3 +116,33 @@ def test_tangent_forward_tma_staged_is_bit_identical_to_register_staged(P):
     assert torch.isfinite(outs[0][1].float()).all() and torch.isfinite(outs[0][0].float()).all()
     assert torch.equal(outs[0][0].view(torch.int16), outs[1][0].view(torch.int16))
     assert torch.equal(outs[0][1].view(torch.int16), outs[1][1].view(torch.int16))
+
+
+@pytest.mark.parametrize("P", [90, 128, 3000, 38400, 38411])
+def test_training_stash_by_tma_is_bit_identical_to_register_stores(P):
+    """K1r in training mode writes the value rows of the backward's stash: by TMA stores from the A tile (default,
+    layers 0..6) or with per-thread register stores (rg_flags bit 5, the round-2 form).  Same bits, same udf /
+    gradient; rows past P and the tangent half of every plane stay untouched."""
+    from emap_b200 import ops, _cabi as C
+    from tests.helpers import oracle_params
+    torch.manual_seed(P)
+    dev = torch.device("cuda")
+    p = oracle_params(True)
+    net = ops.PackedNet(10)
+    net.fold(torch.cat([t.reshape(-1) for t in p.tensors()]).to(dev))
+    x = (torch.rand(P, 3, device=dev) * 2 - 1) * 1.2
+    outs = []
+    for flags in (28, 28 | 32):
+        stash = ops.alloc_backward_stash(P, dev)
+        stash[0].fill_(7.0); stash[1].fill_(7.0)
+        try:
+            C.set_option("rg_flags", flags)
+            u, g = ops.udf_forward_grad(net, C.PREC_FP32X3, pts=x, mode="reverse", stash=stash)
+            torch.cuda.synchronize()
+        finally:
+            C.set_option("rg_flags", 28)
+        assert bool((stash[1][:, P:] == 7.0).all()) and bool((stash[0][P:] == 7.0).all())
+        outs.append((u, g, stash[0].clone(), stash[1].clone()))
+    for a, b in zip(outs[0], outs[1]):
+        assert torch.equal(a, b)
+    assert not bool((outs[0][3][:, :P] == 7.0).all(dim=-1).any())          # every value row was written

@@ -11,7 +11,10 @@ with mbarrier phase-parity semantics.  The model raises on
   * TMEM accumulator overwritten before all 16 epilogue warps have read it, or read before complete,
   * the positional-encoding image of a tile (global scratch, double buffered, written by all 16 epilogue warps
     during the previous tile's reverse steps) copied into chunk 0 by the TMA engine before it is complete,
-    overwritten while a copy reads it, or the copy landing in chunk 0 under a running MMA.
+    overwritten while a copy reads it, or the copy landing in chunk 0 under a running MMA,
+  * (training mode) the TMA store of a finished A-tile chunk to the backward's stash -- issued by the 19th warp on
+    st_ready, released by st_done -- reading a chunk that an epilogue warp or a PE copy overwrites under it, or a
+    chunk that does not hold the layer it is meant to store.
 It does not model the arithmetic (tests/test_rg_emulation.py does) nor PTX memory-ordering fences.
 """
 import heapq
@@ -62,9 +65,13 @@ class MBar:
 
 
 class Sim:
-    def __init__(self, nterms, iters, seed, split_tail=False):
+    def __init__(self, nterms, iters, seed, split_tail=False, training=True):
         self.rng = random.Random(seed)
         self.nterms, self.iters = nterms, iters
+        self.training = training
+        self.st_ready = [MBar(f"st_ready{i}", EPI_WARPS) for i in range(4)]
+        self.st_done = [MBar(f"st_done{i}", 1) for i in range(4)]
+        self.store_readers = [0] * 4                                # TMA stash stores in flight reading chunk c
         self.split_tail = split_tail and nterms == 3
         self.parts = 2 if nterms == 3 else 1
         ns = K_STAGES[nterms]
@@ -136,6 +143,8 @@ class Sim:
 
     def run(self):
         roles = {"producer": self.producer(), "issuer": self.issuer()}
+        if self.training:
+            roles["stash_io"] = self.stash_io()
         for w in range(EPI_WARPS):
             roles[f"epi{w}"] = self.epilogue(w)
         for name, gen in roles.items():
@@ -172,6 +181,8 @@ class Sim:
                 raise Hazard(f"PE copy for {(it, s)} reads image {b}: warp {w} wrote {self.img_ver[b][w]}")
         if self.chunk_readers[0]:
             raise Hazard(f"PE copy for {(it, s)} issued into chunk 0 under {self.chunk_readers[0]} MMAs in flight")
+        if self.store_readers[0]:
+            raise Hazard(f"PE copy for {(it, s)} issued into chunk 0 under a stash store reading it")
         if self.chunk0_copy:
             raise Hazard("two PE copies in flight")
         self.chunk0_copy = True
@@ -312,9 +323,30 @@ class Sim:
                     self.commit(lambda f=half_done: (f(half=0), f(half=1)))
                 yield ("delay", self.lat(0.02, 0.1))
 
+    def stash_io(self):
+        """19th warp (training): chunk c of h_{l+1} (forward layers 0..6) from the A tile to the stash, one TMA store"""
+        it = -1
+        while True:
+            it += 1
+            yield ("wait", self.sched_ready, it & 1)
+            if not self._schedule(it):
+                return
+            for l in range(7):
+                for c in range(4):
+                    yield ("wait", self.st_ready[c], (it * 7 + l) & 1)
+                    for w in range(EPI_WARPS):
+                        if self.chunk_ver[c][w] != (it, l + 1):
+                            raise Hazard(f"stash store {(it, l, c)} reads chunk {c}: warp {w} wrote {self.chunk_ver[c][w]}")
+                    self.store_readers[c] += 1
+                    yield ("delay", self.lat(0.3, 3.0))           # cp.async.bulk.wait_group.read 0
+                    self.store_readers[c] -= 1
+                    self.st_done[c].arrive()
+
     def _write_chunk(self, w, phys, tag):
         if self.chunk_readers[phys]:
             raise Hazard(f"warp {w} writes chunk {phys} ({tag}) under {self.chunk_readers[phys]} MMAs in flight")
+        if self.store_readers[phys]:
+            raise Hazard(f"warp {w} writes chunk {phys} ({tag}) under a stash store reading it")
         if phys == 0 and self.chunk0_copy:
             raise Hazard(f"warp {w} writes chunk 0 ({tag}) while a PE copy into it is in flight")
         self.chunk_ver[phys][w] = tag
@@ -360,13 +392,19 @@ class Sim:
                     if chunk == 2:
                         yield ("wait", self.acc_full[buf][1], par)
                     self._read_acc(w, buf, it, l, chunk >> 1)
+                    if self.training and l >= 1 and not getattr(self, "skip_st_done_wait", False):
+                        yield ("wait", self.st_done[chunk], (it * 7 + l - 1) & 1)
                     yield ("delay", self.lat(0.1, 1.0))
                     self._write_chunk(w, chunk, (it, l + 1))
                     self.a_ready[chunk].arrive()
+                    if self.training and l < 7:
+                        self.st_ready[chunk].arrive()
                 self.acc_reads_left[buf] -= 1
                 self.acc_empty[buf].arrive()
                 if l == SKIP - 1 and w == 0:
                     yield ("wait", self.c0_free, it & 1)
+                    if self.training and not getattr(self, "skip_st_done_wait", False):
+                        yield ("wait", self.st_done[0], (it * 7 + 3) & 1)
                     self.a_ready[4].arrive(tx=1)
                     self.pe_copy(it, SKIP, it & 1)
             # (layer 7's epilogue above wrote the sweep's seed alpha_7 as the input of step 8)
@@ -408,6 +446,7 @@ class Sim:
 def test_protocol_no_deadlock_no_hazard(nterms, split):
     for seed in range(40):
         Sim(nterms, iters=3, seed=seed, split_tail=split).run()
+        Sim(nterms, iters=3, seed=seed, split_tail=split, training=False).run()
 
 
 def _heavy_tailed(self, lo, hi):
@@ -431,6 +470,21 @@ def test_model_detects_a_pe_copy_before_the_image_is_complete():
     for seed in range(20):
         sim = Sim(3, iters=2, seed=seed)
         sim.skip_pe_wait = True
+        try:
+            sim.run()
+        except AssertionError:
+            caught += 1
+    assert caught > 0
+
+
+def test_model_detects_a_chunk_overwritten_under_its_stash_store(monkeypatch):
+    """without the st_done waits a slow TMA store still reads the chunk that the next layer's epilogue (or the skip
+    layer's PE copy) overwrites"""
+    monkeypatch.setattr(Sim, "lat", _heavy_tailed)
+    caught = 0
+    for seed in range(40):
+        sim = Sim(3, iters=3, seed=seed)
+        sim.skip_st_done_wait = True
         try:
             sim.run()
         except AssertionError:
@@ -497,9 +551,13 @@ def test_model_constants_match_the_cuda_source():
     assert re.search(r"mbar_init\(&a_ready\[c\], kEpiWarps\)", src) and re.search(r"mbar_init\(&a_ready\[4\], 1\)", src)
     assert re.search(r"mbar_init\(pe_done, kEpiWarps\)", src)
     assert "mbar_wait(pe_done, (uint32_t)(iter + 1) & 1" in src and "mbar_wait(pe_done, 0" in src
-    assert re.search(r"mbar_init\(sched_ready, 1\)", src) and src.count("mbar_wait(sched_ready, (uint32_t)iter & 1") == 3
+    assert re.search(r"mbar_init\(sched_ready, 1\)", src) and src.count("mbar_wait(sched_ready, (uint32_t)iter & 1") == 4
     assert "if (l == 2 && scheduler)" in src and "mbar_wait(sched_ready, (uint32_t)(iter + 1) & 1" in src
     assert re.search(r"mbar_init\(&acc_empty\[b\], kEpiWarps\)", src)
+    assert "mbar_init(&st_ready[c], kEpiWarps); mbar_init(&st_done[c], 1)" in src
+    assert "mbar_wait(&st_ready[c], ((uint32_t)iter * 7u + (uint32_t)l) & 1" in src
+    assert "mbar_wait(&st_done[chunk], ((uint32_t)iter * 7u + (uint32_t)(l - 1)) & 1" in src
+    assert "mbar_wait(&st_done[0], ((uint32_t)iter * 7u + 3u) & 1" in src
     assert "uses & 1" in src and "(uint32_t)iter * kAPerTile + (uint32_t)(s - 1)" in src
     assert "(uint32_t)iter * 2u + (s == kSkipLayer ? 1u : 0u)" in src
     assert "(uint32_t)iter * kUsesPerBuf + (uint32_t)(s >> 1)" in src

@@ -67,11 +67,12 @@ C.set_option("dynamic_tiles", 1)
 C.set_option("rg_flags", 28)
 print("bit-identical static vs dynamic:", [bool(torch.equal(a, b)) for a, b in zip(res[0], res[1])])
 # code-layout variants (rolled MMA-issuer loops), two interleaved rounds against order effects.
-# rg_flags: 8 = dynamic tiles, +4 = rolled issuer, +16 = rolled reverse-epilogue chunk loop (default 28), +2 = persisting L2;
+# rg_flags: 8 = dynamic tiles, +4 = rolled issuer, +16 = rolled reverse-epilogue chunk loop (default 28), +2 = persisting L2,
+# +32 = training stash from registers instead of by TMA;
 # cluster 3 / rev_rolled 0 = the unrolled issuer loops of round 1
 for rnd in range(2):
     line = []
-    for fl in (28, 12, 8, 30):
+    for fl in (28, 28 + 32, 12, 30):
         C.set_option("rg_flags", fl)
         line.append(f"flags {fl}: {t(lambda: ops.udf_forward_grad(net, 3, pts=x, mode='reverse', stash=stash), reps=6):.2f}")
     C.set_option("rg_flags", 28)
