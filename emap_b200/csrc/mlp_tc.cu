@@ -33,7 +33,7 @@ namespace emap {
 
 namespace rg { int set_flags(int v); }   // mlp_rg.cu
 namespace dw { int set_desc_strides(int which, int v); }   // mlp_dw.cu
-namespace rev { int set_dynamic(int v); int set_rolled(int v); int set_tma(int v); }   // mlp_rev.cu
+namespace rev { int set_dynamic(int v); }                  // mlp_rev.cu
 
 // The tangent forward with TMA-staged stash rows: MODE 3, single fp16 MMA, CL_ = 1 (CL_ = 3 keeps the
 // register-staged round-1 form as A/B switch).  It runs a 19th warp that owns the stash traffic.
@@ -932,8 +932,6 @@ extern "C" int emap_set_option(const char* name, int value) {
   if (!strcmp(name, "dw_lbo")) return emap::dw::set_desc_strides(0, value);      // bring-up of mlp_dw.cu's descriptors
   if (!strcmp(name, "dw_sbo")) return emap::dw::set_desc_strides(1, value);
   if (!strcmp(name, "k1_dot")) { emap::g_k1_dot = (value != 0); return 0; }
-  if (!strcmp(name, "rev_rolled")) return emap::rev::set_rolled(value);
-  if (!strcmp(name, "rev_tma")) return emap::rev::set_tma(value);
   if (!strcmp(name, "tan_tma")) { emap::g_tan_tma = value; return 0; }
   if (!strcmp(name, "rg_flags")) return emap::rg::set_flags(value);   // K1r experiment switches (mlp_rg.cu)
   return set_error("unknown option '%s'", name);

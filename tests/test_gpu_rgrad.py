@@ -283,9 +283,10 @@ def test_k1_dot_output_layer(golden, prec, tol):
 
 
 def test_rolled_issuer_variants_of_the_backward_are_bit_identical(golden):
-    """A/B switches that only change code layout (the unrolled MMA-issuer loops of round 1: cluster=3 for the K1
-    family incl. the tangent forward, rev_rolled=0 for the reverse sweep, rg_flags without bits 2 and 4 for K1r)
-    must not change a single bit of the parameter gradients."""
+    """A/B switches that only change code layout or data movement -- the unrolled MMA-issuer loops of round 1
+    (cluster=3 for the K1 family, rg_flags without bits 2 and 4 for K1r), register-staged instead of TMA-staged stash
+    rows in the tangent forward (tan_tma=0) and the training forward (rg_flags bit 5) -- must not change a single
+    bit of the parameter gradients."""
     from emap_b200 import _cabi as C
     from tests.test_gpu_render import build
     g = golden("mlp_pert")
@@ -302,9 +303,9 @@ def test_rolled_issuer_variants_of_the_backward_are_bit_identical(golden):
 
     ref = grads()
     try:
-        C.set_option("cluster", 3); C.set_option("rev_rolled", 0); C.set_option("rev_tma", 0); C.set_option("tan_tma", 0); C.set_option("rg_flags", 8)
+        C.set_option("cluster", 3); C.set_option("tan_tma", 0); C.set_option("rg_flags", 8 | 32)
         got = grads()
     finally:
-        C.set_option("cluster", 1); C.set_option("rev_rolled", 1); C.set_option("rev_tma", 1); C.set_option("tan_tma", 1); C.set_option("rg_flags", 28)
+        C.set_option("cluster", 1); C.set_option("tan_tma", 1); C.set_option("rg_flags", 28)
     for a, b in zip(ref, got):
         assert torch.equal(a, b)

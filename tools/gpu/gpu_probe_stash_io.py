@@ -52,12 +52,5 @@ for rnd in range(2):
     C.set_option("dbg", 0)
     C.set_option("tan_tma", 1)
     print(f"tangent forward round {rnd}: " + "   ".join(out) + "  ms", flush=True)
-    C.set_option("rev_tma", 1)
-    out = [f"TMA-staged {t(rev):.2f} |"]
-    C.set_option("rev_tma", 0)
-    for d, name in ((0, "register-staged: full"), (1, "no stores"), (2, "no loads"), (3, "no loads, no stores")):
-        C.set_option("rev_rolled", 1 | (d << 1))
-        out.append(f"{name} {t(rev):.2f}")
-    C.set_option("rev_rolled", 1)
-    C.set_option("rev_tma", 1)
+    out = [f"TMA-staged {t(rev):.2f}  (register-staged form, removed: 5.9-6.3 full, 4.6-5.0 without stores, 4.0-4.5 without loads, 3.0-3.2 without both)"]
     print(f"reverse sweep round {rnd}: " + "   ".join(out) + "  ms", flush=True)

@@ -69,7 +69,7 @@ print("bit-identical static vs dynamic:", [bool(torch.equal(a, b)) for a, b in z
 # code-layout variants (rolled MMA-issuer loops), two interleaved rounds against order effects.
 # rg_flags: 8 = dynamic tiles, +4 = rolled issuer, +16 = rolled reverse-epilogue chunk loop (default 28), +2 = persisting L2,
 # +32 = training stash from registers instead of by TMA;
-# cluster 3 / rev_rolled 0 = the unrolled issuer loops of round 1
+# cluster 3 = the unrolled issuer loop of round 1
 for rnd in range(2):
     line = []
     for fl in (28, 28 + 32, 12, 30):
@@ -91,9 +91,4 @@ for rnd in range(2):
                                                   C.ptr(scales), C.ptr(stash[0]), C.ptr(stash[1]), st), reps=6)
         line.append(f"cluster {cl}: K1 forward {f:.2f}  tangent fwd {tn:.2f}")
     C.set_option("cluster", 1)
-    for rr in (0, 1):
-        C.set_option("rev_rolled", rr)
-        rv = t(lambda: L.emap_bwd_reverse_sweep(desc, C.ptr(net.packed), C.ptr(coef), C.ptr(stash[1]), C.ptr(st_a), P, st), reps=6)
-        line.append(f"rev_rolled {rr}: reverse sweep {rv:.2f}")
-    C.set_option("rev_rolled", 1)
     print(f"issuer variants round {rnd}: " + "   ".join(line) + "  ms", flush=True)

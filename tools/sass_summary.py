@@ -1,5 +1,5 @@
 """profiles/r02_sass_summary.txt: per kernel of the built library, the SASS mnemonics that prove the Blackwell-native
-paths (tcgen05.mma -> UTC*MMA, tcgen05.ld/st -> LDTM/STTM, TMA -> UBLKCP / UTMALDG), instruction count, registers.
+paths (tcgen05.mma -> UTC*MMA, tcgen05.ld/st -> LDTM/STTM, TMA -> UBLKCP / UTMALDG / UTMASTG), instruction count, registers.
 usage: python tools/sass_summary.py > profiles/r02_sass_summary.txt   (needs only cuobjdump; no GPU)"""
 import collections
 import os
@@ -33,14 +33,14 @@ for ln in sass.splitlines():
     if m and cur:
         op = m.group(1)
         counts[cur]["instructions"] += 1
-        for key in ("UTCHMMA", "UTCQMMA", "LDTM", "STTM", "UBLKCP", "UTMALDG", "UTCBAR", "HMMA", "MUFU", "SYNCS"):
+        for key in ("UTCHMMA", "UTCQMMA", "LDTM", "STTM", "UBLKCP", "UTMALDG", "UTMASTG", "UTCBAR", "HMMA", "MUFU", "SYNCS"):
             if op.startswith(key):
                 counts[cur][key] += 1
-print("kernel | instr | regs | UTCHMMA (tcgen05.mma) | LDTM (tcgen05.ld) | UBLKCP (1-D bulk copy) | UTMALDG (TMA tensor) | "
+print("kernel | instr | regs | UTCHMMA (tcgen05.mma) | LDTM (tcgen05.ld) | UBLKCP (1-D bulk copy) | UTMALDG (TMA tensor load) | UTMASTG (TMA tensor store) | "
       "UTCBAR (tcgen05.commit) | SYNCS (mbarrier) | MUFU | HMMA (legacy mma.sync)")
 for fn in sorted(order, key=lambda f: -counts[f]["instructions"]):
     c = counts[fn]
     name = demangle(fn)
     name = re.sub(r"\(.*$", "", name)[:90]
     print(f"{name} | {c['instructions']} | {regs.get(fn, '?')} | {c['UTCHMMA']} | {c['LDTM']} | {c['UBLKCP']} | "
-          f"{c['UTMALDG']} | {c['UTCBAR']} | {c['SYNCS']} | {c['MUFU']} | {c['HMMA']}")
+          f"{c['UTMALDG']} | {c['UTMASTG']} | {c['UTCBAR']} | {c['SYNCS']} | {c['MUFU']} | {c['HMMA']}")
