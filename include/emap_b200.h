@@ -238,15 +238,24 @@ int emap_rendering_network_forward(const float* const* wt, const float* const* b
                                    void* stream);
 
 /* ---- misc ------------------------------------------------------------------------------------ */
-/* options: "cluster" = 1|2|-2 : weight-stream organisation of the K1/K1g/dual kernels (1 = default);
- *          "rg_flags" : K1r switches, default 8 (bit 3: tiles handed out by a global atomic counter -- 5.24 vs
- *                       6.05 ms per 1 M points on B200; bit 0: N-split of each step's last K chunk; bit 1: launch
- *                       with the sigma scratch as a persisting-L2 access-policy window -- both measured, no gain);
- *          "k1_dot"   : 1 = emap_udf_forward (without pe_out) runs the output layer as an fp32 dot product
- *                       in layer 7's epilogue instead of a ninth MMA step (opt-in until measured);
- *          "dbg"      : timing experiments of mlp_tc.cu (0 in production);
- *          "dbg_iter" : tile iteration of block 0 that the clock64 timelines of the debug entry points stamp;
- *          "dw_lbo" / "dw_sbo" : byte strides of mlp_dw.cu's MN-major operand descriptors (8192 / 1024).      */
+/* options -- A/B switches; every default is the measured-best setting, every alternative is bit-identical to it
+ * (tests/test_gpu_rgrad.py, tests/test_gpu_mlp.py, tests/test_gpu_dw.py):
+ *   "cluster" = 1|2|3|-2 : weight-stream organisation of the K1 / K1g / dual / tangent kernels.  1 (default) = every
+ *               CTA streams its own copy, MMA-issuer loop ROLLED (instruction-cache footprint: K1 2.70 vs 3.04 ms);
+ *               3 = the same with the unrolled issuer of round 1; 2 = multicast pairs; -2 = cta_group::2 pairs;
+ *   "rg_flags" : K1r switches, default 28 = 8 (tiles handed out by a global atomic counter: 5.24 vs 6.05 ms per
+ *               1 M points) | 4 (rolled MMA-issuer loop: 6.35 vs 7.26 ms in training mode) | 16 (rolled chunk loop of
+ *               the reverse epilogue).  bit 0: N-split of each step's last K chunk; bit 1: persisting-L2 window on
+ *               the sigma scratch (both measured, no gain); bit 5 (32): training stash stored from registers
+ *               instead of by TMA from the A tile (6.0 vs 7.1 ms);
+ *   "tan_tma"  : 1 (default) = the tangent forward moves its stash rows through shared memory with the TMA engine
+ *               (2.26 vs 2.63 ms); 0 = register-staged;
+ *   "dynamic_tiles" : 1 (default) = K1 / tangent / dual forward and reverse sweep hand tiles out dynamically;
+ *   "k1_dot"   : 1 = emap_udf_forward (without pe_out) runs the output layer as an fp32 dot product in layer 7's
+ *               epilogue instead of a ninth MMA step (measured: no gain; default 0);
+ *   "dbg"      : timing experiments of mlp_tc.cu (0 in production);
+ *   "dbg_iter" : tile iteration of block 0 that the clock64 timelines of the debug entry points stamp;
+ *   "dw_lbo" / "dw_sbo" : byte strides of mlp_dw.cu's MN-major operand descriptors (8192 / 1024).             */
 int emap_set_option(const char* name, int value);
 /* test hook: MLP forward (mode 0) / forward+grad (mode 1) that also dumps the de-scaled
  * accumulators of tile 0, dbg_acc[9][128][256].                                                  */
