@@ -39,7 +39,7 @@ constexpr uint32_t kUsesPerBuf = 8;               // accumulator uses per tile a
 constexpr uint32_t kAPerTile = 15;                // completions of a_ready[0..3] per tile (steps 0..14)
 constexpr float kAdjScale = 16.f;                 // power of two (headroom: |alpha| < 4095)
 constexpr int kSigmaLayers = 7;                   // sigma_0..sigma_6 (sigma_7 is consumed in registers)
-// sigma in [0,1] is stashed in 16 bits of FIXED point (15-bit exp(-|t|) + the sign of t, see enc_e): what
+// sigma in [0,1] is stashed in 16 bits of FIXED point (15-bit exp(-|t|) + the sign of t, see enc_e2): what
 // matters for the gradient is its absolute error (2^-16), not its relative one -- modelled in
 // tests/test_rg_emulation.py: 1.3e-5 on the gradient against 5e-6 with fp32 sigma and 1.7e-4 with fp16 sigma.
 // Half the L2 traffic of an fp32 stash, and 148 slices (66 MB) fit the 126 MB L2 together with the weights.
@@ -88,8 +88,8 @@ __device__ __forceinline__ constexpr uint32_t step_bytes(int s) {
 }
 
 // sigma scratch: plain (coherent) 256-bit accesses -- the data is rewritten by this kernel, so the read-only
-// path of ldg256 must not be used.  Per element 16 bits: bit 15 = sign of t = 100 a, bits 0..14 =
-// round(32767 exp(-|t|)); sigma = (t >= 0 ? 1 : e) / (1 + e) is rebuilt in the reverse step (one MUFU.RCP there
+// path of ldg256 must not be used.  Per element 16 bits (enc_e2 below): round(32767 exp(-|t|)), t = 100 a, ones'-
+// complemented when t < 0; sigma = (t >= 0 ? 1 : e) / (1 + e) is rebuilt in the reverse step (one MUFU.RCP there
 // instead of MUFU.RCP + F2I in the forward step, which is the longer one).  Both conversions go through the
 // 2^23 magic number on the FMA / ALU pipes -- no F2I / I2F (they share the XU pipe with the MUFUs).
 __device__ __forceinline__ void ld_words8(const uint32_t* p, uint32_t (&u)[8]) {
@@ -98,15 +98,35 @@ __device__ __forceinline__ void ld_words8(const uint32_t* p, uint32_t (&u)[8]) {
                : "l"(p)
                : "memory");
 }
-__device__ __forceinline__ uint32_t enc_e(float e, float t) {     // 16-bit code of (e, sign t)
-  const uint32_t q = __float_as_uint(fmaf(e, kSigmaQ, 12582912.0f));          // low mantissa bits = round(32767 e)
-  return (q & 0x7fffu) | ((__float_as_uint(t) >> 16) & 0x8000u);
+// Two codes per 32-bit word, ONES' COMPLEMENT in 16 bits: q = round(32767 e) for t >= 0, 0xffff ^ q for t < 0 (bit 15 =
+// sign of t either way, and e = 0 keeps its sign).  Encoding a pair costs 2 FFMA (2^23 magic number: the low mantissa
+// bits are q) + PRMT (pack the low halves) + PRMT (sign-replicate the top byte of each t: 0xffff / 0) + XOR -- 2.5
+// instructions per element on the FMA/ALU pipes (the round-2 form extracted and re-inserted the sign bit by bit: 6).
+// (prmt through inline PTX: the __byte_perm intrinsic only documents the 3-bit byte index of each selector nibble;
+//  bit 3 = "replicate the sign of the selected byte" is a PTX prmt feature)
+__device__ __forceinline__ uint32_t prmt(uint32_t a, uint32_t b, uint32_t sel) {
+  uint32_t d;
+  asm("prmt.b32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(sel));
+  return d;
 }
-__device__ __forceinline__ float dec_sigma(uint32_t v) {          // v: 16-bit code in the low half
-  const float ei = __uint_as_float(0x4B000000u | (v & 0x7fffu)) - 8388608.0f;   // 32767 e
-  const float e = ei * (1.0f / kSigmaQ);
-  const float r = rcp_approx(fmaf(ei, 1.0f / kSigmaQ, 1.0f));
-  return (v & 0x8000u) ? e * r : r;
+__device__ __forceinline__ uint32_t enc_e2(float e0, float t0, float e1, float t1) {
+  const uint32_t q0 = __float_as_uint(fmaf(e0, kSigmaQ, 12582912.0f));
+  const uint32_t q1 = __float_as_uint(fmaf(e1, kSigmaQ, 12582912.0f));
+  const uint32_t pack = prmt(q0, q1, 0x5410u);
+  const uint32_t mask = prmt(__float_as_uint(t0), __float_as_uint(t1), 0xFFBBu);
+  return pack ^ mask;
+}
+// sigma / 16 of the two codes of a word (the 1/16 of the operand pre-scale folded into the reciprocal's argument):
+// XOR with the sign-replicated top bytes restores q in both halves, PRMT builds 2^23 + q, and
+// sigma/16 = (t >= 0 ? 1 : e) / (16 + 16 e) with e = q / 32767.
+__device__ __forceinline__ void dec_sigma2(uint32_t w, float& s0, float& s1) {
+  const uint32_t u = w ^ prmt(w, 0u, 0xBB99u);
+  const float q0 = __uint_as_float(prmt(u, 0x4B000000u, 0x7610u)) - 8388608.0f;
+  const float q1 = __uint_as_float(prmt(u, 0x4B000000u, 0x7632u)) - 8388608.0f;
+  const float r0 = rcp_approx(fmaf(q0, 16.0f / kSigmaQ, 16.0f));
+  const float r1 = rcp_approx(fmaf(q1, 16.0f / kSigmaQ, 16.0f));
+  s0 = (w & 0x8000u) ? (q0 * (1.0f / kSigmaQ)) * r0 : r0;
+  s1 = (w & 0x80000000u) ? (q1 * (1.0f / kSigmaQ)) * r1 : r1;
 }
 
 // J_gamma^T applied to 16 consecutive PE adjoints adj[i] <-> PE slot k = kbase + i (rg_pe_ref order,
@@ -507,8 +527,7 @@ __global__ void __launch_bounds__(kThreadsRg, 1) mlp_rgrad_kernel(const __grid_c
               m.dbg_acc[((size_t)l * 128 + row) * 256 + col0 + k] = __uint_as_float(r[k]) * kInvWeightScale;
           }
           uint32_t* sgp = sg_ptr(top ? 0 : l, chunk);
-          float ev[16];                       // e = exp(-|t|) of this thread's 16 columns ...
-          uint32_t tneg = 0;                  // ... and the sign bits of t: sigma_l is rebuilt from them in the sweep
+          uint32_t sw[8];                     // (e, sign t) codes of this thread's 16 columns: sigma_l for the sweep
           uint32_t pu[8];                     // h_{l+1} of this thread's 16 columns as fp16 (training stash)
 #pragma unroll
           for (int g = 0; g < 2; ++g) {
@@ -517,10 +536,13 @@ __global__ void __launch_bounds__(kThreadsRg, 1) mlp_rgrad_kernel(const __grid_c
             float h[8];
             if (!top) {
 #pragma unroll
-              for (int j = 0; j < 8; ++j) {
-                const float t = fmaf(__uint_as_float(r[g * 8 + j]), k1, bb[j]);
-                h[j] = softplus100_e(t, ev[g * 8 + j]);
-                tneg |= (__float_as_uint(t) >> 31) << (g * 8 + j);
+              for (int j = 0; j < 8; j += 2) {
+                const float t0 = fmaf(__uint_as_float(r[g * 8 + j]), k1, bb[j]);
+                const float t1 = fmaf(__uint_as_float(r[g * 8 + j + 1]), k1, bb[j + 1]);
+                float e0, e1;
+                h[j] = softplus100_e(t0, e0);
+                h[j + 1] = softplus100_e(t1, e1);
+                sw[g * 4 + (j >> 1)] = enc_e2(e0, t0, e1, t1);
               }
               store_group<NTERMS, T>(dst_hi, dst_lo, row, sub * 2 + g, h);
             } else {
@@ -548,16 +570,7 @@ __global__ void __launch_bounds__(kThreadsRg, 1) mlp_rgrad_kernel(const __grid_c
             if (tma_st && !top) mbar_arrive(&st_ready[chunk]);
           }
           if (stamp && chunk == 0) m.dbg_clk[4 * l + 2] = clock64();
-          if (!top) {                         // after the hand-off, off the MMA's critical path: encode and stash
-            uint32_t sw[8];
-#pragma unroll
-            for (int j = 0; j < 8; ++j) {
-              const uint32_t c0 = (__float_as_uint(fmaf(ev[2 * j], kSigmaQ, 12582912.0f)) & 0x7fffu) | (((tneg >> (2 * j)) & 1u) << 15);
-              const uint32_t c1 = (__float_as_uint(fmaf(ev[2 * j + 1], kSigmaQ, 12582912.0f)) & 0x7fffu) | (((tneg >> (2 * j + 1)) & 1u) << 15);
-              sw[j] = c0 | (c1 << 16);
-            }
-            stg256(sgp, sw);
-          }
+          if (!top) stg256(sgp, sw);          // after the hand-off: off the MMA's critical path
           // training: value rows [0,P) of the backward's stash U_{l+1} (emap_bwd_tangent_forward adds the
           // tangent rows later) -- after the hand-off, off the MMA's critical path
           // (by TMA from the A tile where that holds the same fp16 values: every layer but the last, fp16 images)
@@ -612,8 +625,12 @@ __global__ void __launch_bounds__(kThreadsRg, 1) mlp_rgrad_kernel(const __grid_c
           }
           float v[16];
 #pragma unroll
-          for (int j = 0; j < 16; ++j)
-            v[j] = __uint_as_float(r[j]) * kInvWeightScale * dec_sigma((j & 1) ? (sgc[j >> 1] >> 16) : sgc[j >> 1]);
+          for (int j = 0; j < 16; j += 2) {
+            float s0, s1;
+            dec_sigma2(sgc[j >> 1], s0, s1);                     // sigma / 16 (kInvWeightScale folded in)
+            v[j] = __uint_as_float(r[j]) * s0;
+            v[j + 1] = __uint_as_float(r[j + 1]) * s1;
+          }
           if (chunk < 3) fetch_sigma(chunk + 1);
           if (chunk == 3 && l == kSkipLayer) {
             // columns n >= out3 of alpha_4 W_4 are the adjoint of the skip input's PE part (slot

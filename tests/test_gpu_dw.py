@@ -76,7 +76,7 @@ def _reverse_sweep_reference(net, st_u, coef, P):
             if lt == 4:
                 Wl = Wl.clone()
                 Wl[:, out3:] = 0.0                                             # PE inputs of the skip layer
-            prod = a16.float() @ Wl                                            # [2P, in]
+            prod = a16[:, :Wl.shape[0]].float() @ Wl                           # [2P, in]  (layer 3 has 256 - pe outputs)
             eta, etad = prod[:P, :256], prod[P:, :256]
     return torch.stack(planes[::-1])                                           # [8, 2P, 256]
 
