@@ -95,13 +95,12 @@ static_assert(SmemPlan<3, 1>::total <= 232448 && SmemPlan<3, 0>::total <= 232448
 // per-mode schedule constants (MODE 0 forward, 1 forward+grad (4 rows/point), 2 dual forward with
 // stashes for the backward (2 rows/point, layers 0..7 only -- the output layer is pulled back by a
 // separate small kernel), 3 tangent-only forward of the backward (1 row/point, layers 0..7; the value rows
-// of the stash come from the training forward, mlp_rg.cu), 5 = forward like MODE 0 but with the output layer
-// as an fp32 dot product in layer 7's epilogue instead of a ninth MMA step (opt-in, "k1_dot"))
+// of the stash come from the training forward, mlp_rg.cu))
 template <int MODE> struct ModeInfo {
   static constexpr int kLayers = (MODE >= 2) ? 8 : 9;          // MMA layers per tile
   static constexpr int kUses0 = (MODE >= 2) ? 4 : 5;           // accumulator-0 uses per tile
   static constexpr int kAPerTile = (MODE >= 2) ? 7 : 8;        // a_ready[0..3] completions per tile
-  static constexpr int kPtsPerTile = (MODE == 0 || MODE == 3 || MODE == 5) ? 128 : ((MODE == 1) ? 32 : 64);
+  static constexpr int kPtsPerTile = (MODE == 0 || MODE == 3) ? 128 : ((MODE == 1) ? 32 : 64);
 };
 
 template <typename T> struct Elem;
@@ -256,7 +255,7 @@ __device__ __forceinline__ void pe_stage(const MlpArgs& args, const float (&x)[3
   constexpr int vofs = (HF == 0) ? 4 : 0;
   const int ty = lane & 3;
   float vals[32];
-  if (MODE == 0 || MODE == 4 || MODE == 5) {
+  if (MODE == 0 || MODE == 4) {
     if (HF == 0) { vals[0] = x[0]; vals[1] = x[1]; vals[2] = x[2]; vals[3] = 0.f; }
 #pragma unroll
     for (int i = 0; i < npairs; ++i) {

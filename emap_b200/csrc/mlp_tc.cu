@@ -415,7 +415,7 @@ __global__ void __launch_bounds__(ThreadsOf<NTERMS, MODE, T, CL_>::value, 1) mlp
       }
       // ------------------------------------------------ input stage: positional encoding -> chunk 0
       long long pt;
-      if (MODE == 0 || MODE == 3 || MODE == 5) pt = tile * 128 + row;
+      if (MODE == 0 || MODE == 3) pt = tile * 128 + row;
       else if (MODE == 1) pt = tile * 32 + q * 8 + p8;
       else pt = tile * 64 + q * 16 + (lane >> 1);
       float x[3];
@@ -435,7 +435,6 @@ __global__ void __launch_bounds__(ThreadsOf<NTERMS, MODE, T, CL_>::value, 1) mlp
       }
 
       // ------------------------------------------------ hidden layers 0..7
-      float dot8 = 0.f;               // MODE 5: this thread's share of a_8 = w_8 . h_8 (its 64 columns)
       for (int l = 0; l < 8; ++l) {
         const int buf = l & 1;
         const bool stamp = args.dbg_clk && blockIdx.x == 0 && iter == args.dbg_iter && warp == 0 && lane == 0;
@@ -478,10 +477,10 @@ __global__ void __launch_bounds__(ThreadsOf<NTERMS, MODE, T, CL_>::value, 1) mlp
           // the bias words this lane needs, issued before the accumulator load so that their L1/L2
           // latency hides under the tcgen05.ld wait (ncu: 8 % of the dual kernel's samples sat on it)
           //   MODE 0: 16 columns; MODE 1: the lane's 4 value columns; MODE 2: the lane's 8 columns
-          constexpr int kBiasVec = (MODE == 0 || MODE == 5) ? 4 : ((MODE == 1 || MODE == 3) ? 1 : 2);   // MODE 3: unused
+          constexpr int kBiasVec = (MODE == 0) ? 4 : ((MODE == 1 || MODE == 3) ? 1 : 2);   // MODE 3: unused
           float4 bv[kBiasVec];
           {
-            const int bofs = (MODE == 0 || MODE == 3 || MODE == 5) ? 0 : ((MODE == 1) ? 4 * ty : 8 * (lane & 1));
+            const int bofs = (MODE == 0 || MODE == 3) ? 0 : ((MODE == 1) ? 4 * ty : 8 * (lane & 1));
 #pragma unroll
             for (int i = 0; i < kBiasVec; ++i) bv[i] = __ldg(reinterpret_cast<const float4*>(bl + col0 + bofs) + i);
           }
@@ -574,7 +573,7 @@ __global__ void __launch_bounds__(ThreadsOf<NTERMS, MODE, T, CL_>::value, 1) mlp
             }
             if (okp && !(args.dbg_flags & 8) && !tma)      // (dbg 8: timing experiment without the stash stores)
               st_dst = args.st_u + (size_t)l * 2 * (size_t)args.P * 256 + ((size_t)args.P + (size_t)pt) * 256 + col0;
-          } else if (MODE == 0 || MODE == 5) {
+          } else if (MODE == 0) {
 #pragma unroll
             for (int g = 0; g < 2; ++g) {
               const float4 bA = bv[(2 * g) % kBiasVec], bB = bv[(2 * g + 1) % kBiasVec];
@@ -585,17 +584,7 @@ __global__ void __launch_bounds__(ThreadsOf<NTERMS, MODE, T, CL_>::value, 1) mlp
                 float dummy;
                 h[j] = softplus100<false>(fmaf(__uint_as_float(r[g * 8 + j]), k1, bb[j]), dummy);
               }
-              if (MODE == 5 && l == 7) {
-                // h_8 feeds only the output layer: a_8 += w_8 . h_8 in fp32, no A-tile write, no ninth MMA step
-                const float* w8 = reinterpret_cast<const float*>(args.packed + hdr->weff_layer_off[8]) + col0 + g * 8;
-                const float4 wA = __ldg(reinterpret_cast<const float4*>(w8));
-                const float4 wB = __ldg(reinterpret_cast<const float4*>(w8 + 4));
-                const float ww[8] = {wA.x, wA.y, wA.z, wA.w, wB.x, wB.y, wB.z, wB.w};
-#pragma unroll
-                for (int j = 0; j < 8; ++j) dot8 = fmaf(ww[j], h[j], dot8);
-              } else {
-                store_group<NTERMS, T>(dst_hi, dst_lo, row, sub * 2 + g, h);
-              }
+              store_group<NTERMS, T>(dst_hi, dst_lo, row, sub * 2 + g, h);
             }
           } else {
             // Exchange slots of point p8: four 16-byte slots (columns 4i..4i+3).  Single-MMA modes have a
@@ -677,21 +666,6 @@ __global__ void __launch_bounds__(ThreadsOf<NTERMS, MODE, T, CL_>::value, 1) mlp
         }
       }
 
-      if (MODE == 5) {
-        // output layer: sum the four column slices' shares of a_8.  The A tile is dead (layer 7's MMAs have
-        // completed): 16 bytes per (point, sub) inside the chunk-3 rows of this lane quarter, which only its own
-        // four warps write later; they meet on a named barrier before and after (same scheme as mlp_rg.cu).
-        float* slots = reinterpret_cast<float*>(A_hi + 3 * kChunkBytes + (q * 32 + (lane >> 1)) * 128 + (lane & 1) * 64);
-        slots[sub * 4] = dot8;
-        asm volatile("bar.sync %0, %1;" ::"r"(1 + q), "r"(128) : "memory");
-        if (sub == 0 && tile < args.num_tiles && pt < args.P) {
-          const float a = ((slots[0] + slots[4]) + (slots[8] + slots[12])) + b8;
-          const float u = (udf_type == 0) ? fabsf(a) : (udf_type == 1 ? a * a : a);
-          args.udf_out[pt] = u / net_scale;
-        }
-        asm volatile("bar.sync %0, %1;" ::"r"(1 + q), "r"(128) : "memory");
-        continue;
-      }
       // ------------------------------------------------ output layer (layer 8, accumulator buf 0, col 0)
       if (MODE >= 2) continue;        // dual / tangent forward stop at layer 7 (the output layer is pulled back separately)
       mbar_wait(&acc_full[0], ((uint32_t)iter * 5u + 4u) & 1, 510);
@@ -784,9 +758,6 @@ static int launch(const MlpArgs& a_in, cudaStream_t stream) {
 //   1 = every CTA streams its own copy (default), 2 = multicast pairs (cta_group::1),
 //   -2 = CTA pairs driven by one cta_group::2 issuer (fp16 operand images only).
 static int g_cluster = 1;
-// emap_set_option("k1_dot", 1): emap_udf_forward runs MODE 5 (output layer as a dot product in layer 7's
-// epilogue, 8 MMA steps per tile instead of 9) when no PE output is requested.  Opt-in until measured.
-static int g_k1_dot = 0;
 static int g_tan_tma = 1;     // emap_set_option("tan_tma", 0): tangent forward with register-staged stash rows
 
 template <int MODE>
@@ -841,13 +812,6 @@ extern "C" int emap_udf_forward(const emap_net_desc* net, const void* packed, in
   memset(&a, 0, sizeof(a));
   a.packed = (const uint8_t*)packed; a.pts = pts; a.rays_o = rays_o; a.rays_d = rays_d; a.z = z;
   a.n_per_ray = n_per_ray; a.P = P; a.udf_out = udf_out; a.pe_out = pe_out;
-  if (g_k1_dot && !pe_out) {
-    cudaStream_t st = (cudaStream_t)stream;
-    if (precision == EMAP_PREC_FP32X3)
-      return net->elem_type == 0 ? launch<3, 5, __half, 1>(a, st) : launch<3, 5, __nv_bfloat16, 1>(a, st);
-    if (precision == EMAP_PREC_HALF)
-      return net->elem_type == 0 ? launch<1, 5, __half, 1>(a, st) : launch<1, 5, __nv_bfloat16, 1>(a, st);
-  }
   return dispatch<0>(net, precision, a, (cudaStream_t)stream);
 }
 
@@ -931,7 +895,6 @@ extern "C" int emap_set_option(const char* name, int value) {
   if (!strcmp(name, "dynamic_tiles")) { emap::g_dynamic_tiles = value; emap::rev::set_dynamic(value); return 0; }
   if (!strcmp(name, "dw_lbo")) return emap::dw::set_desc_strides(0, value);      // bring-up of mlp_dw.cu's descriptors
   if (!strcmp(name, "dw_sbo")) return emap::dw::set_desc_strides(1, value);
-  if (!strcmp(name, "k1_dot")) { emap::g_k1_dot = (value != 0); return 0; }
   if (!strcmp(name, "tan_tma")) { emap::g_tan_tma = value; return 0; }
   if (!strcmp(name, "rg_flags")) return emap::rg::set_flags(value);   // K1r experiment switches (mlp_rg.cu)
   return set_error("unknown option '%s'", name);

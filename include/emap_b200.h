@@ -251,8 +251,6 @@ int emap_rendering_network_forward(const float* const* wt, const float* const* b
  *   "tan_tma"  : 1 (default) = the tangent forward moves its stash rows through shared memory with the TMA engine
  *               (2.26 vs 2.63 ms); 0 = register-staged;
  *   "dynamic_tiles" : 1 (default) = K1 / tangent / dual forward and reverse sweep hand tiles out dynamically;
- *   "k1_dot"   : 1 = emap_udf_forward (without pe_out) runs the output layer as an fp32 dot product in layer 7's
- *               epilogue instead of a ninth MMA step (measured: no gain; default 0);
  *   "dbg"      : timing experiments of mlp_tc.cu (0 in production);
  *   "dbg_iter" : tile iteration of block 0 that the clock64 timelines of the debug entry points stamp;
  *   "dw_lbo" / "dw_sbo" : byte strides of mlp_dw.cu's MN-major operand descriptors (8192 / 1024).             */

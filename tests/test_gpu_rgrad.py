@@ -250,38 +250,6 @@ def test_shared_backward_render_loss_matches_default():
         assert maxdiff(a, b) <= 2e-2 * (float(a.abs().max()) + 1e-12)
 
 
-# ---------------------------------------------------------------------------------------------------
-# K1 with the output layer as a dot product (mlp_kernel MODE 5, emap_set_option("k1_dot", 1)): the
-# validated 8-layer schedule of the dual forward + MODE 0's epilogue + K1r's final reduction.
-# ---------------------------------------------------------------------------------------------------
-@pytest.mark.parametrize("prec,tol", [("fp32", 5e-5), ("fp16", 3e-3)])
-def test_k1_dot_output_layer(golden, prec, tol):
-    from emap_b200 import ops, _cabi as C
-    from oracle import emap_oracle as O
-    g = golden("mlp_pert")
-    net, p = _net(True)
-    x = g["x"].cuda()
-    u0, _ = ops.udf_forward(net, C.PRECISIONS[prec], pts=x)
-    B, n = 1237, 7
-    o, d = O.synthetic_rays(B)
-    z = torch.rand(B, n) * 3 + 0.5
-    pts = (o[:, None, :] + d[:, None, :] * z[..., None]).reshape(-1, 3)
-    try:
-        C.set_option("k1_dot", 1)
-        u1, _ = ops.udf_forward(net, C.PRECISIONS[prec], pts=x)
-        u2, _ = ops.udf_forward(net, C.PRECISIONS[prec], rays_o=o.cuda(), rays_d=d.cuda(), z=z.cuda())
-        _, pe = ops.udf_forward(net, C.PRECISIONS[prec], pts=x, want_pe=True)     # PE requested -> MODE 0
-        torch.cuda.synchronize()
-    finally:
-        C.set_option("k1_dot", 0)
-    ref = g["udf"][:, 0]
-    assert maxdiff(u1.cpu(), ref) <= tol * max(1.0, float(ref.abs().max()))
-    assert maxdiff(u1, u0) <= 2 * tol
-    ref2 = O.udf_forward(p, pts)[0][:, 0]
-    assert maxdiff(u2.cpu(), ref2) <= tol * max(1.0, float(ref2.abs().max()))
-    assert maxdiff(pe.cpu(), g["pe"]) <= 5e-7
-
-
 def test_rolled_issuer_variants_of_the_backward_are_bit_identical(golden):
     """A/B switches that only change code layout or data movement -- the unrolled MMA-issuer loops of round 1
     (cluster=3 for the K1 family, rg_flags without bits 2 and 4 for K1r), register-staged instead of TMA-staged stash

@@ -33,10 +33,6 @@ def t(fn, reps=5):
 for prec, name in ((3, "fp32x3"), (1, "fp16")):
     # (independent of K1r: first, so that a K1r failure does not lose it)
     f0 = t(lambda: ops.udf_forward(net, prec, pts=x))
-    C.set_option("k1_dot", 1)
-    f1 = t(lambda: ops.udf_forward(net, prec, pts=x))
-    C.set_option("k1_dot", 0)
-    print(f"{name}: K1 forward with the dot-product output layer (k1_dot=1): {f1:.2f} ms (default {f0:.2f} ms)", flush=True)
     uf, gf = ops.udf_forward_grad(net, prec, pts=x, mode="forward")
     ur, gr = ops.udf_forward_grad(net, prec, pts=x, mode="reverse")
     torch.cuda.synchronize()
