@@ -289,9 +289,9 @@ __global__ void __launch_bounds__(kThreadsT, 1) mlp_rev_kernel(const __grid_cons
             tmem_ld_32x32b_x16(lane_taddr + (uint32_t)(buf * 256 + col0), r);
             tmem_wait_ld();
 #pragma unroll
-            for (int k = 0; k < 16; ++k) own[k] = __uint_as_float(r[k]) * kInvWeightScale;
+            for (int k = 0; k < 16; ++k) own[k] = __uint_as_float(r[k]);       // x 16 (operand pre-scale), removed below
           } else {
-            const float cf = t2 ? c_t : c_v;
+            const float cf = (t2 ? c_t : c_v) * kWeightScale;                    // same scale as the accumulators
 #pragma unroll
             for (int k = 0; k < 16; k += 4) {
               const float4 w = __ldg(reinterpret_cast<const float4*>(w8 + col0 + k));
@@ -326,9 +326,11 @@ __global__ void __launch_bounds__(kThreadsT, 1) mlp_rev_kernel(const __grid_cons
             for (int e = 0; e < 2; ++e) {
               const int k = 2 * w + e;
               // sigma = softplus'(a) = 1 - exp(-100 h);  adot * softplus''(a) = 100 * hdot * (1 - sigma)
+              // (the 1/16 that removes the operand pre-scale from eta / etadot is folded into sigma and the
+              //  second-derivative factor: a power of two, so every product rounds exactly as before)
               const float one_m_s = __expf(-kSoftplusBeta * hve[e]);
-              const float sg = 1.0f - one_m_s;
-              al[e] = fmaf(etad[k], kSoftplusBeta * hde[e] * one_m_s, eta[k] * sg);       // alpha
+              const float sg = fmaf(-one_m_s, kInvWeightScale, kInvWeightScale);
+              al[e] = fmaf(etad[k], (kSoftplusBeta * kInvWeightScale) * hde[e] * one_m_s, eta[k] * sg);   // alpha
               ad[e] = etad[k] * sg;                                                       // alphadot
               if (partial && k >= nlive) { al[e] = 0.f; ad[e] = 0.f; }
             }

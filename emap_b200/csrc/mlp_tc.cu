@@ -560,9 +560,11 @@ __global__ void __launch_bounds__(ThreadsOf<NTERMS, MODE, T, CL_>::value, 1) mlp
 #pragma unroll
               for (int w2 = 0; w2 < 4; ++w2) {
                 const float2 h2 = __half22float2(*reinterpret_cast<const __half2*>(&hw[chunk][g * 4 + w2]));
-                const float s0 = 1.0f - __expf(-kSoftplusBeta * h2.x), s1 = 1.0f - __expf(-kSoftplusBeta * h2.y);
-                v8[2 * w2] = s0 * (__uint_as_float(r[g * 8 + 2 * w2]) * kInvWeightScale);
-                v8[2 * w2 + 1] = s1 * (__uint_as_float(r[g * 8 + 2 * w2 + 1]) * kInvWeightScale);
+                // sigma / 16: the operand pre-scale's 1/16 folded in (a power of two: rounds exactly as before)
+                const float s0 = fmaf(-__expf(-kSoftplusBeta * h2.x), kInvWeightScale, kInvWeightScale);
+                const float s1 = fmaf(-__expf(-kSoftplusBeta * h2.y), kInvWeightScale, kInvWeightScale);
+                v8[2 * w2] = s0 * __uint_as_float(r[g * 8 + 2 * w2]);
+                v8[2 * w2 + 1] = s1 * __uint_as_float(r[g * 8 + 2 * w2 + 1]);
               }
               if (l < 7) store_group<NTERMS, T>(dst_hi, dst_lo, row, sub * 2 + g, v8);
 #pragma unroll
