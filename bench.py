@@ -64,15 +64,50 @@ def peaks():
 
 
 class ClockSampler(threading.Thread):
-    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    """SM clock / throttle reasons sampled DURING the timed region: NVML in-process (initialised before the region,
+    first sample taken the moment the thread starts, then every 25 ms), `nvidia-smi -lms` as the fallback -- its
+    start-up alone can outlast a 0.4 s timed region."""
 
     def __init__(self, index=0):
         super().__init__(daemon=True)
         self.index = index
-        self.rows = []
+        self.rows = []            # (sm_mhz, reasons bitmask)
         self.proc = None
+        self.stop_flag = threading.Event()
+        self.nvml = None
+        self.max_mhz = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            phys = index
+            if vis:
+                ids = [v.strip() for v in vis.split(",") if v.strip()]
+                if index < len(ids) and ids[index].isdigit():
+                    phys = int(ids[index])
+            self.handle = pynvml.nvmlDeviceGetHandleByIndex(phys)
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(self.handle, pynvml.NVML_CLOCK_SM))
+            self.nvml = pynvml
+        except Exception:
+            self.nvml = None
+
+    def _sample_nvml(self):
+        n = self.nvml
+        try:
+            reasons = n.nvmlDeviceGetCurrentClocksEventReasons(self.handle)
+        except Exception:
+            reasons = n.nvmlDeviceGetCurrentClocksThrottleReasons(self.handle)
+        self.rows.append((float(n.nvmlDeviceGetClockInfo(self.handle, n.NVML_CLOCK_SM)), int(reasons)))
 
     def run(self):
+        if self.nvml is not None:
+            try:
+                while not self.stop_flag.is_set():
+                    self._sample_nvml()
+                    self.stop_flag.wait(0.025)
+                return
+            except Exception:
+                self.rows = []
         q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
              "clocks_event_reasons.sw_power_cap")
@@ -81,24 +116,31 @@ class ClockSampler(threading.Thread):
                                           "-i", str(self.index), "-lms", "100"], stdout=subprocess.PIPE,
                                          text=True)
             for line in self.proc.stdout:
-                self.rows.append([x.strip() for x in line.split(",")])
+                r = [x.strip() for x in line.split(",")]
+                if len(r) >= 7 and r[0].replace(".", "").isdigit():
+                    bits = sum(b for b, k in ((8, 3), (64, 4), (32, 5), (4, 6)) if r[k].lower().startswith("active"))
+                    self.max_mhz = float(r[1])
+                    self.rows.append((float(r[0]), bits))
         except Exception:
             pass
 
     def stop(self):
+        self.stop_flag.set()
         if self.proc:
             self.proc.terminate()
-        rows = [r for r in self.rows if len(r) >= 7]
+        if self.nvml is not None:
+            self.join(timeout=1.0)
+        rows = list(self.rows)
         if not rows:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unavailable"]}
-        sm = sorted(float(r[0]) for r in rows if r[0].replace(".", "").isdigit())
-        reasons = []
-        for i, name in ((3, "hw_slowdown"), (4, "hw_thermal_slowdown"), (5, "sw_thermal_slowdown"),
-                        (6, "sw_power_cap")):
-            if any(r[i].lower().startswith("active") for r in rows):
-                reasons.append(name)
-        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": float(rows[0][1]),
-                "reasons": reasons, "samples": len(rows)}
+        sm = sorted(r[0] for r in rows)
+        mask = 0
+        for r in rows:
+            mask |= r[1]
+        reasons = [name for bit, name in ((8, "hw_slowdown"), (64, "hw_thermal_slowdown"), (32, "sw_thermal_slowdown"),
+                                          (4, "sw_power_cap")) if mask & bit]
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": self.max_mhz, "reasons": reasons, "samples": len(rows),
+                "source": "nvml" if self.nvml is not None else "nvidia-smi"}
 
 
 def synthetic_problem(B, seed_offset=0):
