@@ -51,8 +51,11 @@ WORKLOADS = {
 # (precision, rays, samples) -> dram__bytes_read.sum + dram__bytes_write.sum.  None = not captured.
 NCU_DRAM_BYTES_PER_LAUNCH = {("forward", "train", "fp32", 4096, 256): 6.490e6,     # K1g (round 1)
                              ("forward", "infer", "fp32", 4096, 256): 6.490e6,
-                             ("reverse", "train", "fp32", 4096, 256): 10.745e9,    # K1r + value stash (round 2)
-                             ("reverse", "infer", "fp32", 4096, 256): None}        # filled from profiles/r02_k1r_infer_ncu_raw.csv
+                             # K1r, final round-2 code (profiles/r02_k1r_{train,infer}_ncu_raw.csv): train = 2.27 GB
+                             # read + 8.39 GB written (4.3 GB of it the backward's value stash, the rest the sigma
+                             # scratch cycling through L2); infer = 0.10 GB read + 2.92 GB written
+                             ("reverse", "train", "fp32", 4096, 256): 10.659e9,
+                             ("reverse", "infer", "fp32", 4096, 256): 3.024e9}
 
 
 def peaks():
@@ -589,7 +592,7 @@ def main():
                 "ceiling": (1.0 / 3.0 if nterms == 3 else 1.0) * (1.0 if rev else 0.5),
                 "traffic": NCU_DRAM_BYTES_PER_LAUNCH.get((args.grad_mode, args.mode, args.precision, B, n)),
                 "traffic_source": "ncu --set full capture of one launch of this workload (dram__bytes_read.sum + "
-                                  "dram__bytes_write.sum; profiles/r02_k1r_ncu_raw.csv, r01_mlp_ncu_raw.csv); in "
+                                  "dram__bytes_write.sum; profiles/r02_k1r_train_ncu_raw.csv, r02_k1r_infer_ncu_raw.csv); in "
                                   "train mode the kernel also writes the backward's fp16 value stash, "
                                   "8 x P x 256 x 2 B = 4.3 GB at P = 1 M",
                 "peak_source": pk_src + " burst bf16 (cuBLAS)",
