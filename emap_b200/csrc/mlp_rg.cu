@@ -528,7 +528,8 @@ __global__ void __launch_bounds__(kThreadsRg, 1) mlp_rgrad_kernel(const __grid_c
           }
           uint32_t* sgp = sg_ptr(top ? 0 : l, chunk);
           uint32_t sw[8];                     // (e, sign t) codes of this thread's 16 columns: sigma_l for the sweep
-          uint32_t pu[8];                     // h_{l+1} of this thread's 16 columns as fp16 (training stash)
+          uint32_t pu[8];                     // h_{l+1} of this thread's 16 columns as fp16 (training stash) ...
+          const bool need_pu = m.st_u != nullptr && (top || !tma_st);   // ... where it is not stored by TMA from the A tile
 #pragma unroll
           for (int g = 0; g < 2; ++g) {
             const float4 bA = bv[2 * g], bB = bv[2 * g + 1];
@@ -560,8 +561,10 @@ __global__ void __launch_bounds__(kThreadsRg, 1) mlp_rgrad_kernel(const __grid_c
               }
               store_group<NTERMS, T>(dst_hi, dst_lo, row, sub * 2 + g, v);
             }
+            if (need_pu) {
 #pragma unroll
-            for (int j = 0; j < 4; ++j) pu[g * 4 + j] = Elem<__half>::pack2(h[2 * j], h[2 * j + 1]);
+              for (int j = 0; j < 4; ++j) pu[g * 4 + j] = Elem<__half>::pack2(h[2 * j], h[2 * j + 1]);
+            }
           }
           fence_proxy_async_smem();
           __syncwarp();
@@ -574,7 +577,7 @@ __global__ void __launch_bounds__(kThreadsRg, 1) mlp_rgrad_kernel(const __grid_c
           // training: value rows [0,P) of the backward's stash U_{l+1} (emap_bwd_tangent_forward adds the
           // tangent rows later) -- after the hand-off, off the MMA's critical path
           // (by TMA from the A tile where that holds the same fp16 values: every layer but the last, fp16 images)
-          if (m.st_u && ok && (top || !tma_st)) stg256_cs(m.st_u + (size_t)l * 2 * (size_t)m.P * 256 + (size_t)pt * 256 + col0, pu);
+          if (need_pu && ok) stg256_cs(m.st_u + (size_t)l * 2 * (size_t)m.P * 256 + (size_t)pt * 256 + col0, pu);
         }
         tc_fence_before();
         __syncwarp();
