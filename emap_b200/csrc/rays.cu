@@ -25,6 +25,8 @@ namespace emap {
 constexpr int kMaxSamples = 512;   // samples per ray (n_samples + n_importance)
 constexpr int kMaxNew = 64;        // new samples per up-sampling step
 constexpr int kRayWarps = 4;       // warps (= rays) per block
+// floats per per-ray shared-memory array for m samples (a multiple of 32, one spare row: bank spread)
+__host__ __device__ inline int ray_stride(int m) { return ((m + 31) & ~31) + 32; }
 
 __device__ __forceinline__ double shfl_up_d(double v, int d) {
   int lo = __double2loint(v), hi = __double2hiint(v);
@@ -48,25 +50,48 @@ __device__ __forceinline__ double warp_sum_d(double v) {
   return v;
 }
 
-// Exclusive running product over arr[0..m) (fp32 in SMEM) in fp64; out[i] = float(prod_{t<i} arr[t]).
-// In-place allowed.  All 32 lanes participate.
+// Scans over a ray's m samples (fp32 in SMEM, accumulated in fp64 like torch's CPU cumprod / cumsum).  BLOCKED: lane l
+// owns the C = ceil(m/32) consecutive samples [l C, l C + C): a sequential local pass, ONE 5-level warp scan of the
+// lane totals, a second local pass -- C + 5 + C dependent fp64 operations instead of the 5 C of a row-by-row
+// shuffle scan (C = 8 at 256 samples; these kernels are latency-bound: one warp per ray, < 1 wave at 4096 rays).
+// In-place allowed (a lane reads and writes only its own block).  All 32 lanes participate.
+
+// Exclusive running product: out[i] = float(prod_{t<i} arr[t]).
 __device__ __forceinline__ void excl_cumprod(const float* arr, float* out, int m, int lane) {
-  double carry = 1.0;
-  for (int base = 0; base < m; base += 32) {
-    const int i = base + lane;
-    const double v = (i < m) ? (double)arr[i] : 1.0;
-    double inc = v;
+  const int C = (m + 31) >> 5, i0 = lane * C;
+  double loc = 1.0;
+  for (int t = 0; t < C; ++t) { const int i = i0 + t; if (i < m) loc *= (double)arr[i]; }
+  double inc = loc;
 #pragma unroll
-    for (int d = 1; d < 32; d <<= 1) {
-      const double t = shfl_up_d(inc, d);
-      if (lane >= d) inc *= t;
-    }
-    double exc = shfl_up_d(inc, 1);
-    if (lane == 0) exc = 1.0;
-    const double tot = shfl_d(inc, 31);
-    __syncwarp();
-    if (i < m) out[i] = (float)(carry * exc);
-    carry *= tot;
+  for (int d = 1; d < 32; d <<= 1) {
+    const double t = shfl_up_d(inc, d);
+    if (lane >= d) inc *= t;
+  }
+  double run = shfl_up_d(inc, 1);
+  if (lane == 0) run = 1.0;
+  for (int t = 0; t < C; ++t) {
+    const int i = i0 + t;
+    if (i < m) { const double v = (double)arr[i]; out[i] = (float)run; run *= v; }
+  }
+  __syncwarp();
+}
+
+// Inclusive running sum shifted by one: out[0] = 0, out[i + 1] = float(sum_{t<=i} arr[t] / total)   (the CDF)
+__device__ __forceinline__ void cdf_cumsum(const float* arr, float* out, int m, float total, int lane) {
+  const int C = (m + 31) >> 5, i0 = lane * C;
+  double loc = 0.0;
+  for (int t = 0; t < C; ++t) { const int i = i0 + t; if (i < m) loc += (double)(arr[i] / total); }
+  double inc = loc;
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    const double t = shfl_up_d(inc, d);
+    if (lane >= d) inc += t;
+  }
+  double run = shfl_up_d(inc, 1);
+  if (lane == 0) { run = 0.0; out[0] = 0.f; }
+  for (int t = 0; t < C; ++t) {
+    const int i = i0 + t;
+    if (i < m) { run += (double)(arr[i] / total); out[i + 1] = (float)run; }
   }
   __syncwarp();
 }
@@ -129,18 +154,21 @@ struct UpsampleArgs {
 };
 
 __global__ void __launch_bounds__(kRayWarps * 32) upsample_step_kernel(const UpsampleArgs a) {
-  __shared__ float s_z[kRayWarps][kMaxSamples];
-  __shared__ float s_u[kRayWarps][kMaxSamples];
-  __shared__ float s_a[kRayWarps][kMaxSamples];     // scratch: vp terms / alpha / cdf
-  __shared__ float s_b[kRayWarps][kMaxSamples];     // scratch: vis_prob / weights
+  // per-ray arrays in DYNAMIC shared memory sized by the actual sample count (ray_stride(n + ka) floats each): with
+  // static [kMaxSamples] arrays a block took 36 KiB -> 6 blocks per SM, and 4096 rays (1024 blocks) needed 1.15 waves
+  extern __shared__ float s_dyn[];
   __shared__ float s_new[kRayWarps][kMaxNew];
   __shared__ float s_add[kRayWarps][2 * kMaxNew];
   const int wib = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int ray = blockIdx.x * kRayWarps + wib;
   if (ray >= a.B) return;
-  float* zs = s_z[wib]; float* us = s_u[wib]; float* sa = s_a[wib]; float* sb = s_b[wib];
-  float* zn = s_new[wib];
   const int n = a.n, ka = a.ka, m = n + ka;
+  const int rs = ray_stride(m);
+  float* zs = s_dyn + (size_t)(wib * 4 + 0) * rs;
+  float* us = s_dyn + (size_t)(wib * 4 + 1) * rs;
+  float* sa = s_dyn + (size_t)(wib * 4 + 2) * rs;     // scratch: vp terms / alpha / cdf
+  float* sb = s_dyn + (size_t)(wib * 4 + 3) * rs;     // scratch: vis_prob / weights
+  float* zn = s_new[wib];
 
   // ---- (a12) merge pending samples: z sorted union, udf permuted alike
   if (ka > 0) {
@@ -243,24 +271,7 @@ __global__ void __launch_bounds__(kRayWarps * 32) upsample_step_kernel(const Ups
   for (int i = lane; i < m - 1; i += 32) { sb[i] = sb[i] + 1e-5f; part += (double)sb[i]; }
   const float total = (float)warp_sum_d(part);
   __syncwarp();
-  {
-    // cdf[0] = 0; cdf[i+1] = float(cumsum_fp64(pdf)[i]);  stored in sa[0..m)
-    double carry = 0.0;
-    if (lane == 0) sa[0] = 0.f;
-    for (int base = 0; base < m - 1; base += 32) {
-      const int i = base + lane;
-      const double v = (i < m - 1) ? (double)(sb[i] / total) : 0.0;
-      double inc = v;
-#pragma unroll
-      for (int d = 1; d < 32; d <<= 1) {
-        const double t = shfl_up_d(inc, d);
-        if (lane >= d) inc += t;
-      }
-      if (i < m - 1) sa[i + 1] = (float)(carry + inc);
-      carry += shfl_d(inc, 31);
-    }
-  }
-  __syncwarp();
+  cdf_cumsum(sb, sa, m - 1, total, lane);  // cdf[0] = 0; cdf[i+1] = float(cumsum_fp64(pdf)[i]);  stored in sa[0..m)
   for (int j = lane; j < k; j += 32) {
     const float uj = a.u[j];
     int lo = 0, hi = m;                    // searchsorted(cdf, u, right=True): # cdf entries <= u
@@ -316,14 +327,15 @@ struct CoreArgs {
 };
 
 __global__ void __launch_bounds__(kRayWarps * 32) render_core_fwd_kernel(const CoreArgs a) {
-  __shared__ float s_a[kRayWarps][kMaxSamples];
-  __shared__ float s_b[kRayWarps][kMaxSamples];
-  __shared__ float s_c[kRayWarps][kMaxSamples];
+  extern __shared__ float s_dyn[];                  // 3 arrays of ray_stride(n) floats per ray (see upsample_step_kernel)
   const int wib = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int ray = blockIdx.x * kRayWarps + wib;
   if (ray >= a.B) return;
-  float* sa = s_a[wib]; float* sb = s_b[wib]; float* stc = s_c[wib];
   const int n = a.n;
+  const int rs = ray_stride(n);
+  float* sa = s_dyn + (size_t)(wib * 3 + 0) * rs;
+  float* sb = s_dyn + (size_t)(wib * 3 + 1) * rs;
+  float* stc = s_dyn + (size_t)(wib * 3 + 2) * rs;
   const size_t base = (size_t)ray * n;
   const float ox = a.rays_o[ray * 3 + 0], oy = a.rays_o[ray * 3 + 1], oz = a.rays_o[ray * 3 + 2];
   const float dx = a.rays_d[ray * 3 + 0], dy = a.rays_d[ray * 3 + 1], dz = a.rays_d[ray * 3 + 2];
@@ -447,25 +459,23 @@ __global__ void render_reduce_kernel(const double* __restrict__ partials, int B,
 // differentiated with exclusive suffix sums:  d/dm_t prod_{t<i} m_t = (prod)/m_t.
 constexpr int kBwdWarps = 2;
 
-// out[t] = float( sum_{i>t} arr[i] )  in fp64
+// out[t] = float( sum_{i>t} arr[i] )  in fp64 (blocked like excl_cumprod, from the right)
 __device__ __forceinline__ void excl_suffix_sum(const float* arr, float* out, int m, int lane) {
-  double carry = 0.0;
-  const int rows = (m + 31) / 32;
-  for (int rr = rows - 1; rr >= 0; --rr) {
-    const int i = rr * 32 + lane;
-    const double v = (i < m) ? (double)arr[i] : 0.0;
-    double inc = v;                       // inclusive suffix within the row: lane j gets sum_{l>=j}
+  const int C = (m + 31) >> 5, i0 = lane * C;
+  double loc = 0.0;
+  for (int t = C - 1; t >= 0; --t) { const int i = i0 + t; if (i < m) loc += (double)arr[i]; }
+  double inc = loc;                       // inclusive suffix over the lanes: lane j gets sum_{l>=j}
 #pragma unroll
-    for (int d = 1; d < 32; d <<= 1) {
-      int lo = __double2loint(inc), hi = __double2hiint(inc);
-      lo = __shfl_down_sync(0xffffffffu, lo, d);
-      hi = __shfl_down_sync(0xffffffffu, hi, d);
-      if (lane + d < 32) inc += __hiloint2double(hi, lo);
-    }
-    const double tot = shfl_d(inc, 0);
-    __syncwarp();
-    if (i < m) out[i] = (float)(carry + (inc - v));
-    carry += tot;
+  for (int d = 1; d < 32; d <<= 1) {
+    int lo = __double2loint(inc), hi = __double2hiint(inc);
+    lo = __shfl_down_sync(0xffffffffu, lo, d);
+    hi = __shfl_down_sync(0xffffffffu, hi, d);
+    if (lane + d < 32) inc += __hiloint2double(hi, lo);
+  }
+  double run = inc - loc;                 // everything to the right of my block
+  for (int t = C - 1; t >= 0; --t) {
+    const int i = i0 + t;
+    if (i < m) { const double v = (double)arr[i]; out[i] = (float)run; run += v; }
   }
   __syncwarp();
 }
@@ -517,19 +527,18 @@ struct CoreBwdArgs {
 };
 
 __global__ void __launch_bounds__(kBwdWarps * 32) render_core_bwd_kernel(const CoreBwdArgs a) {
-  __shared__ float s_tc[kBwdWarps][kMaxSamples];
-  __shared__ float s_vt[kBwdWarps][kMaxSamples];
-  __shared__ float s_V[kBwdWarps][kMaxSamples];
-  __shared__ float s_al[kBwdWarps][kMaxSamples];
-  __shared__ float s_T[kBwdWarps][kMaxSamples];
-  __shared__ float s_x[kBwdWarps][kMaxSamples];
-  __shared__ float s_y[kBwdWarps][kMaxSamples];
+  // 7 arrays of ray_stride(n) floats per ray, dynamic (static [kMaxSamples] arrays: 29 KiB per 2-warp block ->
+  // 14 resident warps per SM and 2 waves at 4096 rays)
+  extern __shared__ float s_dyn[];
   const int wib = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int ray = blockIdx.x * kBwdWarps + wib;
   if (ray >= a.B) return;
-  float* tcs = s_tc[wib]; float* vt = s_vt[wib]; float* V = s_V[wib]; float* al = s_al[wib];
-  float* T = s_T[wib]; float* sx = s_x[wib]; float* sy = s_y[wib];
   const int n = a.n;
+  const int rs = ray_stride(n);
+  float* tcs = s_dyn + (size_t)(wib * 7 + 0) * rs; float* vt = s_dyn + (size_t)(wib * 7 + 1) * rs;
+  float* V = s_dyn + (size_t)(wib * 7 + 2) * rs;   float* al = s_dyn + (size_t)(wib * 7 + 3) * rs;
+  float* T = s_dyn + (size_t)(wib * 7 + 4) * rs;   float* sx = s_dyn + (size_t)(wib * 7 + 5) * rs;
+  float* sy = s_dyn + (size_t)(wib * 7 + 6) * rs;
   const size_t base = (size_t)ray * n;
   const float ox = a.rays_o[ray * 3 + 0], oy = a.rays_o[ray * 3 + 1], oz = a.rays_o[ray * 3 + 2];
   const float dx = a.rays_d[ray * 3 + 0], dy = a.rays_d[ray * 3 + 1], dz = a.rays_d[ray * 3 + 2];
@@ -625,7 +634,6 @@ __global__ void __launch_bounds__(kBwdWarps * 32) render_core_bwd_kernel(const C
     excl_suffix_sum(sx, sx, n, lane);          // sx[t] = sum_{i>t} dV_i V_i
   }
   __syncwarp();
-
   for (int i = lane; i < n; i += 32) {
     const float udf = a.udf[base + i], dist = a.dists[base + i], mz = a.mid_z[base + i];
     const float gx = a.grad[(base + i) * 3 + 0], gy = a.grad[(base + i) * 3 + 1], gz = a.grad[(base + i) * 3 + 2];
@@ -763,7 +771,8 @@ extern "C" int emap_upsample_step(const float* rays_o, const float* rays_d, cons
   a.u = u; a.z_new = z_new; a.inds = (long long*)inds_out; a.w_out = weights_out;
   a.sample_dist = sample_dist; a.gamma_ptr = gamma_dev; a.B = B; a.k = k; a.inv_s = inv_s; a.beta = beta; a.gamma = gamma;
   a.mode = mode; a.alpha_type = alpha_type; a.status = status;
-  upsample_step_kernel<<<(B + kRayWarps - 1) / kRayWarps, kRayWarps * 32, 0, (cudaStream_t)stream>>>(a);
+  const size_t smem = (size_t)kRayWarps * 4 * ray_stride(n + ka) * sizeof(float);
+  upsample_step_kernel<<<(B + kRayWarps - 1) / kRayWarps, kRayWarps * 32, smem, (cudaStream_t)stream>>>(a);
   EMAP_CUDA(cudaGetLastError());
   return 0;
 }
@@ -797,7 +806,8 @@ extern "C" int emap_render_core_fwd(const float* rays_o, const float* rays_d, co
   a.weights = weights; a.alpha = alpha; a.grad_flip = grad_flip; a.inside_sphere = inside_sphere;
   a.grad_mag = grad_mag; a.edge = edge; a.depth = depth; a.normals = normals; a.partials = partials;
   cudaStream_t st = (cudaStream_t)stream;
-  render_core_fwd_kernel<<<(B + kRayWarps - 1) / kRayWarps, kRayWarps * 32, 0, st>>>(a);
+  render_core_fwd_kernel<<<(B + kRayWarps - 1) / kRayWarps, kRayWarps * 32,
+                           (size_t)kRayWarps * 3 * ray_stride(n) * sizeof(float), st>>>(a);
   EMAP_CUDA(cudaGetLastError());
   render_reduce_kernel<<<1, 1024, 0, st>>>(partials, B, reduced, status);
   EMAP_CUDA(cudaGetLastError());
@@ -826,7 +836,8 @@ extern "C" int emap_render_core_bwd(const float* rays_o, const float* rays_d, co
   a.d_gerr = d_gerr; a.d_gerr_ns = d_gerr_ns; a.d_sparse = d_sparse;
   a.d_udf = d_udf; a.d_grad = d_grad; a.partials = partials;
   cudaStream_t st = (cudaStream_t)stream;
-  render_core_bwd_kernel<<<(B + kBwdWarps - 1) / kBwdWarps, kBwdWarps * 32, 0, st>>>(a);
+  render_core_bwd_kernel<<<(B + kBwdWarps - 1) / kBwdWarps, kBwdWarps * 32,
+                           (size_t)kBwdWarps * 7 * ray_stride(n) * sizeof(float), st>>>(a);
   EMAP_CUDA(cudaGetLastError());
   scalar_reduce_kernel<<<1, 1024, 0, st>>>(partials, B, 3, d_scalars);
   EMAP_CUDA(cudaGetLastError());
