@@ -66,6 +66,15 @@ def test_no_cpu_fallback():
     from emap_b200 import ops
     with pytest.raises(RuntimeError):
         ops.null_direction(torch.zeros(2, 5, 3))
+    # the CUDA-graph wrapper and the standalone RenderingNetwork operator: same rule
+    from emap_b200.graph import GraphedStep
+    from emap_b200.udf_model import RenderingNetwork
+    if not torch.cuda.is_available():
+        with pytest.raises(RuntimeError):
+            GraphedStep(lambda x: (x,), [torch.zeros(1)])
+    rn = RenderingNetwork(d_feature=8, mode="no_normal", d_in=6, d_out=1, d_hidden=16, n_layers=1)
+    with pytest.raises(RuntimeError):
+        rn(torch.zeros(2, 3), None, torch.zeros(2, 3), torch.zeros(2, 8))
 
 
 def test_state_dict_keys_and_init_match_reference(golden):
