@@ -111,6 +111,14 @@ class FlatGradAllReduce:
         if dsts:
             torch._foreach_copy_(dsts, srcs)
 
+    def _mean_all_reduce(self, buf: torch.Tensor, w: int) -> None:
+        """mean over ranks, in place: NCCL averages inside the collective (one launch less); gloo has no AVG"""
+        if buf.is_cuda and dist.get_backend(self.group) == "nccl":
+            dist.all_reduce(buf, op=dist.ReduceOp.AVG, group=self.group)
+        else:
+            dist.all_reduce(buf, op=dist.ReduceOp.SUM, group=self.group)
+            buf.div_(w)
+
     # -- the exchange step -------------------------------------------------------------------
     def allreduce_(self, local_weight: float = 1.0) -> None:
         """SUM over ranks of local_weight * grad, divided by the world size.  local_weight = 1 is the plain
@@ -138,8 +146,7 @@ class FlatGradAllReduce:
                 if local_weight != 1.0:
                     buf.mul_(float(local_weight))
                 if w > 1:
-                    dist.all_reduce(buf, op=dist.ReduceOp.SUM, group=self.group)
-                    buf.div_(w)
+                    self._mean_all_reduce(buf, w)
                 if rest:
                     torch._foreach_copy_(rest, tails)
                 return
@@ -147,8 +154,7 @@ class FlatGradAllReduce:
         if local_weight != 1.0:
             flat.mul_(float(local_weight))
         if w > 1:
-            dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=self.group)
-            flat.div_(w)
+            self._mean_all_reduce(flat, w)
         self.scatter_(flat)
 
 
