@@ -119,7 +119,11 @@ int emap_bwd_top(const emap_net_desc* net, const void* U8_half, const float* w8,
  *     softplus'(a_l) = 1 - exp(-100 h_{l+1}) and adot_l softplus''(a_l) = 100 hdot_{l+1} (1 - sigma_l).
  *  emap_bwd_reverse_sweep: layers 7..0 of the reverse sweep from coef[2P] (emap_bwd_top) and st_u;
  *     writes st_a[8][2P,256] = [alpha_l ; alphadot_l].  The weight gradients are then the contractions
- *     dW_l = A_l^T U_l of emap_bwd_weight_grads, finished by emap_bwd_finish.                         */
+ *     dW_l = A_l^T U_l of emap_bwd_weight_grads, finished by emap_bwd_finish.
+ *  The stashes move through shared memory with the TMA engine (reverse sweep: both; tangent forward: st_u;
+ *  training forward emap_udf_forward_grad_rev: the value rows of st_u; weight gradients: all three): st_u, st_a
+ *  and st_u0 must be 16-byte aligned, dense in the layouts above (any torch allocation is).  Ragged sizes
+ *  (P not a multiple of the 64- / 128-point tiles) are handled by the tensor maps (zero fill / clipping).      */
 int emap_bwd_dual_forward(const emap_net_desc* net, const void* packed, int precision,
                           const float* pts, const float* rays_o, const float* rays_d, const float* z,
                           int32_t n_per_ray, int64_t P, const float* d_grad, const float* scales,
