@@ -253,3 +253,80 @@ def test_split_fp16_numerics_budget():
     # without the 2^4 scale the lo parts of small adjoints go subnormal: must not be better than with it
     _, g1 = _emulate(oracle_params(True, 10), x.float(), split=True, adj_scale=1.0)
     print("grad err scaled", np.abs(g - ref_g).max(), "unscaled", np.abs(g1 - ref_g).max())
+
+
+# ---------------------------------------------------------------------------------------------------
+# The 16-bit sigma codes of K1r (mlp_rg.cu: enc_e2 / dec_sigma2), bit for bit: PTX prmt incl. its sign-replicate
+# mode, the 2^23 magic-number conversions, ones' complement for t < 0.
+# ---------------------------------------------------------------------------------------------------
+def _prmt(a, b, sel):
+    """PTX prmt.b32 (default mode): result byte i = byte (sel nibble i & 7) of {b, a}; nibble bit 3 set -> the byte's
+    sign bit replicated over all 8 bits"""
+    src = [(a >> (8 * i)) & 0xFF for i in range(4)] + [(b >> (8 * i)) & 0xFF for i in range(4)]
+    out = 0
+    for i in range(4):
+        nib = (sel >> (4 * i)) & 0xF
+        byte = src[nib & 7]
+        if nib & 8:
+            byte = 0xFF if byte & 0x80 else 0x00
+        out |= byte << (8 * i)
+    return out
+
+
+def _f2u(x):
+    return int(np.float32(x).view(np.uint32))
+
+
+def _u2f(u):
+    return np.uint32(u).view(np.float32)
+
+
+def _enc_e2(e0, t0, e1, t1):
+    q = np.float32(32767.0)
+    q0 = _f2u(np.float32(np.float32(e0) * q + np.float32(12582912.0)))       # fmaf: exact here (products < 2^15)
+    q1 = _f2u(np.float32(np.float32(e1) * q + np.float32(12582912.0)))
+    return _prmt(q0, q1, 0x5410) ^ _prmt(_f2u(t0), _f2u(t1), 0xFFBB)
+
+
+def _dec_sigma2(w):
+    u = w ^ _prmt(w, 0, 0xBB99)
+    out = []
+    for sel, bit in ((0x7610, 0x8000), (0x7632, 0x80000000)):
+        qf = np.float32(_u2f(_prmt(u, 0x4B000000, sel)) - np.float32(8388608.0))
+        r = np.float32(1.0) / np.float32(qf * np.float32(16.0 / 32767.0) + np.float32(16.0))
+        out.append(np.float32(qf * np.float32(1.0 / 32767.0)) * r if (w & bit) else r)
+    return out
+
+
+def test_sigma_code_roundtrip_bit_model():
+    """decode(encode(exp(-|t|), t)) = sigmoid(t) / 16 within the quantisation step for both signs, both halves of a
+    word, and the edge cases: t = +-0 (e = 1), e rounding to 0 (the sign must survive: sigma -> 0 or 1), the code
+    range (bit 15 = sign of t in both forms)."""
+    rng = np.random.default_rng(0)
+    ts = np.concatenate([rng.normal(0, 4, 400), [0.0, -0.0, 30.0, -30.0, 1e-9, -1e-9, 11.0, -11.0]]).astype(np.float32)
+    worst = 0.0
+    for i in range(0, len(ts) - 1, 2):
+        t0, t1 = ts[i], ts[i + 1]
+        e0, e1 = np.float32(np.exp(-abs(np.float64(t0)))), np.float32(np.exp(-abs(np.float64(t1))))
+        w = _enc_e2(e0, t0, e1, t1)
+        assert 0 <= w < 2 ** 32
+        assert bool(w & 0x8000) == bool(np.signbit(t0)) and bool(w & 0x80000000) == bool(np.signbit(t1))
+        s0, s1 = _dec_sigma2(w)
+        for s, t in ((s0, t0), (s1, t1)):
+            ref = 1.0 / (1.0 + np.exp(-np.float64(t)))
+            worst = max(worst, abs(16.0 * float(s) - ref))
+    assert worst <= 2.0 ** -16 + 1e-7, worst             # half a quantisation step of e, |d sigma / d e| <= 1
+    # saturation keeps the sign: sigma(30) -> 1, sigma(-30) -> 0
+    s_pos, s_neg = _dec_sigma2(_enc_e2(np.float32(np.exp(-30.0)), np.float32(30.0), np.float32(np.exp(-30.0)), np.float32(-30.0)))
+    assert abs(16.0 * float(s_pos) - 1.0) < 1e-6 and abs(16.0 * float(s_neg)) < 1e-6
+
+
+def test_sigma_code_constants_match_the_cuda_source():
+    import os
+    import re
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    src = open(os.path.join(root, "emap_b200", "csrc", "mlp_rg.cu")).read()
+    assert re.search(r"constexpr float kSigmaQ = 32767\.f;", src)
+    for sel in ("0x5410u", "0xFFBBu", "0xBB99u", "0x7610u", "0x7632u"):
+        assert sel in src, sel
+    assert "12582912.0f" in src and "8388608.0f" in src and "0x4B000000u" in src
