@@ -201,3 +201,76 @@ def test_autograd_wiring_of_the_backward_modes(shim, grad_mode, bwd_mode, expect
         assert (len(allocs) == 1) == expect_shared
     finally:
         ops.alloc_backward_stash = real_alloc
+
+
+class _FakeNet(_FakeModule):
+    """+ the renderer-facing method of UDFNetwork"""
+
+    def udf_and_gradient(self, x=None, rays_o=None, rays_d=None, z=None):
+        from emap_b200.autograd import udf_forward_grad_fn
+        return udf_forward_grad_fn(self, x, rays_o, rays_d, z)
+
+
+def _cpu_renderer(ops, **kw):
+    from emap_b200.udf_model import BetaNetwork, SingleVarianceNetwork
+    from emap_b200.udf_renderer_blending import UDFRendererBlending
+    net = _FakeNet(ops)
+    var, beta = SingleVarianceNetwork(0.3), BetaNetwork(0.5, 0.3, 0.3, 5e-5, True, True, False)
+    cfg = dict(n_samples=16, n_importance=8, n_outside=0, up_sample_steps=4, perturb=1.0, device="cpu")
+    cfg.update(kw)
+    return net, UDFRendererBlending(None, net, var, beta, **cfg)
+
+
+def _no_device_queries(monkeypatch, ops):
+    """the status poll and the capture query talk to the CUDA driver: not on this machine"""
+    monkeypatch.setattr(ops, "poll_status", lambda dev: None)
+    monkeypatch.setattr(torch.cuda, "is_current_stream_capturing", lambda: False)
+
+
+def test_render_call_sequence_on_the_recorder(shim, monkeypatch):
+    """UDFRendererBlending.render() end to end on the recorder library (nothing computes): which C-ABI calls one
+    render() makes, in inference and in training, and that nothing but the declared entry points is used."""
+    ops, rec = shim
+    _no_device_queries(monkeypatch, ops)
+    ops.set_grad_mode("reverse"); ops.set_backward_mode("shared")
+    net, r = _cpu_renderer(ops)
+    B = 5
+    o = d = torch.zeros(B, 3)
+    rec.calls.clear()
+    with torch.no_grad():
+        out = r.render(o, d, 0.05, 6.0, torch.ones(B, 1), cos_anneal_ratio=1.0, flip_saturation=0.9)
+    assert out["edge"].shape == (B, 1) and out["weights"].shape == (B, 24)
+    assert rec.calls.count("emap_coarse_z") == 1
+    assert rec.calls.count("emap_udf_forward") == 4                  # coarse samples + 3 of the 4 up-sampling rounds
+    assert rec.calls.count("emap_upsample_step") == 5                # 4 rounds + the final merge
+    assert rec.calls.count("emap_render_prep") == 1 and rec.calls.count("emap_udf_forward_grad_rev") == 1
+    assert rec.calls.count("emap_render_core_fwd") == 1
+    assert not any(c.startswith("emap_bwd") for c in rec.calls)
+    # training: the same forward, then the backward's stages exactly once each
+    rec.calls.clear()
+    out = r.render(o, d, 0.05, 6.0, torch.ones(B, 1), cos_anneal_ratio=1.0, flip_saturation=0.9)
+    (out["edge"].sum() + out["gradient_error"]).backward()
+    for name in ("emap_render_core_bwd", "emap_bwd_cotangent_scales", "emap_bwd_tangent_forward", "emap_bwd_top",
+                 "emap_bwd_reverse_sweep", "emap_bwd_weight_grads", "emap_bwd_finish"):
+        assert rec.calls.count(name) == 1, (name, rec.calls)
+    assert "emap_bwd_dual_forward" not in rec.calls
+    for p in net.params:
+        assert p.grad is not None
+
+
+def test_render_refuses_host_draws_while_a_graph_is_prepared(shim, monkeypatch):
+    """graph.GraphedStep sets ops.graph_prepare during its warm-up: a host-side stratified draw (perturb > 0 without
+    perturb_on_device) is refused there already, before any capture has begun"""
+    ops, rec = shim
+    _no_device_queries(monkeypatch, ops)
+    net, r = _cpu_renderer(ops)
+    o = d = torch.zeros(3, 3)
+    ops.graph_prepare = True
+    try:
+        with pytest.raises(RuntimeError, match="perturb_on_device"):
+            r.render(o, d, 0.05, 6.0, torch.ones(3, 1), cos_anneal_ratio=1.0)
+        r.perturb_on_device = True
+        with torch.no_grad():
+            r.render(o, d, 0.05, 6.0, torch.ones(3, 1), cos_anneal_ratio=1.0)
+    finally:
+        ops.graph_prepare = False
